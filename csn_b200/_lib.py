@@ -1,0 +1,126 @@
+"""ctypes binding of libcsn_b200.so (the C ABI declared in include/csn_b200.h).
+
+There is no CPU fallback: if the shared object is missing or a call fails, an exception is raised.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from pathlib import Path
+
+import torch
+
+_PKG = Path(__file__).resolve().parent
+LIB_PATH = _PKG / "libcsn_b200.so"
+
+CSN_F32, CSN_F16, CSN_BF16 = 0, 1, 2
+MAJOR_K, MAJOR_MN = 0, 1
+
+_DTYPE_CODE = {torch.float32: CSN_F32, torch.float16: CSN_F16, torch.bfloat16: CSN_BF16}
+
+
+class CsnError(RuntimeError):
+    pass
+
+
+class csn_mat(C.Structure):
+    _fields_ = [("ptr", C.c_void_p), ("dtype", C.c_int32), ("major", C.c_int32),
+                ("inner", C.c_int64), ("outer", C.c_int64), ("ld", C.c_int64),
+                ("mn_off", C.c_int64 * 3), ("k_off", C.c_int64 * 3)]
+
+
+class csn_out(C.Structure):
+    _fields_ = [("ptr", C.c_void_p), ("dtype", C.c_int32), ("transposed", C.c_int32),
+                ("ld", C.c_int64), ("off", C.c_int64 * 3), ("accumulate", C.c_int32),
+                ("reserved", C.c_int32)]
+
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    """The loaded shared library. Raises if it has not been built (no fallback exists)."""
+    global _lib
+    if _lib is None:
+        if not LIB_PATH.exists():
+            raise CsnError(
+                f"{LIB_PATH} is missing: build it with `python -m csn_b200.build` "
+                "(csn_b200 has no CPU or PyTorch fallback)")
+        _lib = C.CDLL(str(LIB_PATH))
+        _declare(_lib)
+    return _lib
+
+
+def _declare(L: C.CDLL) -> None:
+    L.csn_last_error.restype = C.c_char_p
+    L.csn_abi_version.restype = C.c_int
+    L.csn_launch_count.restype = C.c_int64
+    L.csn_gemm.restype = C.c_int
+    L.csn_gemm.argtypes = [C.POINTER(csn_mat), C.POINTER(csn_mat), C.POINTER(csn_out), C.c_int32,
+                           C.c_int32, C.c_int32, C.POINTER(C.c_int32), C.c_float, C.c_int32,
+                           C.c_void_p]
+    for name, sig in _EXTRA_SIGNATURES.items():
+        fn = getattr(L, name)
+        fn.restype = C.c_int
+        fn.argtypes = sig
+
+
+# name -> argtypes for the remaining entry points (filled in by the sections below)
+_EXTRA_SIGNATURES: dict[str, list] = {}
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        msg = lib().csn_last_error().decode()
+        raise CsnError(f"{what} failed (rc={rc}): {msg}")
+
+
+def stream_ptr() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def launch_count() -> int:
+    return int(lib().csn_launch_count())
+
+
+def dtype_code(dt: torch.dtype) -> int:
+    return _DTYPE_CODE[dt]
+
+
+def _i3(vals) -> "C.Array":
+    v = list(vals) + [0] * (3 - len(vals))
+    return (C.c_int64 * 3)(*v)
+
+
+def mat(t: torch.Tensor, major: int, mn_off=(), k_off=()) -> csn_mat:
+    """Describe a 2-D strided view [outer, inner] (inner contiguous) as a GEMM operand."""
+    assert t.is_cuda and t.dim() == 2 and t.stride(1) == 1, (t.shape, t.stride())
+    assert t.dtype in (torch.float16, torch.bfloat16)
+    m = csn_mat()
+    m.ptr = t.data_ptr()
+    m.dtype = dtype_code(t.dtype)
+    m.major = major
+    m.inner = t.shape[1]
+    m.outer = t.shape[0]
+    m.ld = t.stride(0)
+    m.mn_off = _i3(mn_off)
+    m.k_off = _i3(k_off)
+    return m
+
+
+def out(t: torch.Tensor, ld: int, transposed: bool = False, off=(), accumulate: bool = False) -> csn_out:
+    assert t.is_cuda
+    o = csn_out()
+    o.ptr = t.data_ptr()
+    o.dtype = dtype_code(t.dtype)
+    o.transposed = int(transposed)
+    o.ld = ld
+    o.off = _i3(off)
+    o.accumulate = int(accumulate)
+    return o
+
+
+def gemm(A: csn_mat, B: csn_mat, D: csn_out, M: int, N: int, K: int, nb=(1, 1, 1), alpha: float = 1.0,
+         split_k: int = 1) -> None:
+    nb3 = (C.c_int32 * 3)(*(list(nb) + [1] * (3 - len(nb))))
+    rc = lib().csn_gemm(C.byref(A), C.byref(B), C.byref(D), M, N, K, nb3, alpha, split_k, stream_ptr())
+    check(rc, "csn_gemm")

@@ -1,0 +1,376 @@
+// csn_gemm: persistent, warp-specialised tcgen05 GEMM for sm_100a.
+//
+//   D[b][m][n] = alpha * sum_k A[b][m][k] * B[b][n][k]
+//
+// Roles inside one 256-thread CTA (one CTA per SM, grid = min(#tiles, #SMs)):
+//   warp 0   : TMA producer  — fills a ring of {A 128x64, B BNx64} 16-bit stages (SWIZZLE_128B)
+//   warp 1   : MMA issuer    — one lane issues tcgen05.mma kind::f16 (M=128, N=BN, K=16) x4 per
+//                              stage, accumulating fp32 in TMEM; tcgen05.commit releases the stage
+//   warp 2   : TMEM allocator
+//   warps 4-7: epilogue      — tcgen05.ld (lane = output row), scale, convert, store / atomic add
+// The accumulator is double-buffered in TMEM (2 x BN columns) so the epilogue of tile i overlaps
+// the main loop of tile i+1.
+//
+// Operands may be K-major (rows of k) or MN-major (rows of mn, i.e. a transposed operand consumed
+// in place): the difference is confined to the TMA box shape and the UMMA descriptor strides.
+#include "host_util.h"
+#include "ptx.cuh"
+
+namespace csn {
+
+constexpr int GEMM_BM = 128;
+constexpr int GEMM_BK = 64;  // 64 x 16-bit = 128 B = one swizzle atom row
+constexpr int GEMM_THREADS = 256;
+
+struct GemmArgs {
+  int M, N, K;
+  int nb0, nb1, nb2;
+  int tiles_m, tiles_n, split_k, kb_per_split, kb_total;
+  long long total_tiles;
+  long long a_mn_off[3], a_k_off[3], b_mn_off[3], b_k_off[3];
+  void* D;
+  long long ldd;
+  long long d_off[3];
+  int out_dtype, transposed, accumulate, vec_ok;
+  float alpha;
+  uint32_t idesc;
+};
+
+template <int BN>
+struct GemmCfg {
+  static constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;
+  static constexpr int B_BYTES = BN * GEMM_BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
+  static constexpr int TMEM_COLS = (2 * BN < 32) ? 32 : 2 * BN;  // 128 / 256 / 512: powers of two
+  static constexpr int BAR_BYTES = 512;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + 1024;  // +1024: alignment slack
+};
+
+struct TileCoord {
+  int b0, b1, b2, mt, nt, ks;
+};
+
+__device__ __forceinline__ TileCoord decode_tile(long long t, const GemmArgs& p) {
+  TileCoord c;
+  c.ks = (int)(t % p.split_k);
+  t /= p.split_k;
+  c.nt = (int)(t % p.tiles_n);
+  t /= p.tiles_n;
+  c.mt = (int)(t % p.tiles_m);
+  t /= p.tiles_m;
+  c.b0 = (int)(t % p.nb0);
+  t /= p.nb0;
+  c.b1 = (int)(t % p.nb1);
+  c.b2 = (int)(t / p.nb1);
+  return c;
+}
+
+__device__ __forceinline__ uint32_t pack16(float a, float b, int dtype) {
+  if (dtype == CSN_F16) {
+    __half2 h = __floats2half2_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&h);
+  } else {
+    __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&h);
+  }
+}
+
+// Store 32 consecutive columns [n, n+32) of output row `row` held in v[] (already scaled).
+__device__ __forceinline__ void store_chunk(const GemmArgs& p, long long base, int row, int n,
+                                            const float (&v)[32]) {
+  const int ncols = min(32, p.N - n);
+  if (!p.transposed) {
+    const long long o = base + (long long)row * p.ldd + n;
+    if (p.accumulate) {
+      float* d = reinterpret_cast<float*>(p.D) + o;
+      for (int j = 0; j < ncols; ++j) atomicAdd(d + j, v[j]);
+    } else if (p.out_dtype == CSN_F32) {
+      float* d = reinterpret_cast<float*>(p.D) + o;
+      if (ncols == 32 && p.vec_ok) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 4)
+          *reinterpret_cast<float4*>(d + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+      } else {
+        for (int j = 0; j < ncols; ++j) d[j] = v[j];
+      }
+    } else {
+      uint16_t* d = reinterpret_cast<uint16_t*>(p.D) + o;
+      if (ncols == 32 && p.vec_ok) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 8) {
+          uint4 q;
+          q.x = pack16(v[j], v[j + 1], p.out_dtype);
+          q.y = pack16(v[j + 2], v[j + 3], p.out_dtype);
+          q.z = pack16(v[j + 4], v[j + 5], p.out_dtype);
+          q.w = pack16(v[j + 6], v[j + 7], p.out_dtype);
+          *reinterpret_cast<uint4*>(d + j) = q;
+        }
+      } else {
+        for (int j = 0; j < ncols; ++j) {
+          uint32_t w = pack16(v[j], 0.f, p.out_dtype);
+          d[j] = (uint16_t)(w & 0xFFFFu);
+        }
+      }
+    }
+  } else {
+    // D[n*ld + m]: for a fixed column the 32 lanes of the warp hold 32 consecutive m -> coalesced.
+    const long long o = base + (long long)n * p.ldd + row;
+    if (p.accumulate) {
+      float* d = reinterpret_cast<float*>(p.D) + o;
+      for (int j = 0; j < ncols; ++j) atomicAdd(d + (long long)j * p.ldd, v[j]);
+    } else if (p.out_dtype == CSN_F32) {
+      float* d = reinterpret_cast<float*>(p.D) + o;
+      for (int j = 0; j < ncols; ++j) d[(long long)j * p.ldd] = v[j];
+    } else {
+      uint16_t* d = reinterpret_cast<uint16_t*>(p.D) + o;
+      for (int j = 0; j < ncols; ++j) {
+        uint32_t w = pack16(v[j], 0.f, p.out_dtype);
+        d[(long long)j * p.ldd] = (uint16_t)(w & 0xFFFFu);
+      }
+    }
+  }
+}
+
+template <int BN, bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+            const __grid_constant__ GemmArgs p) {
+  using Cfg = GemmCfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  // SWIZZLE_128B tiles need 1024-byte alignment.
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const uint32_t smem_base = smem_u32(smem);
+  const uint32_t bar_base = smem_base + Cfg::STAGES * Cfg::STAGE_BYTES;
+  // barrier layout: full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2], tmem_ptr
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (Cfg::STAGES + s); };
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * Cfg::STAGES + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * Cfg::STAGES + 2 + a); };
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES + 8 * (2 * Cfg::STAGES + 4));
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < Cfg::STAGES; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tfull_bar(a), 1);
+      mbar_init(tempty_bar(a), 128);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(smem_u32(tmem_ptr_smem), Cfg::TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int st = 0;
+      uint32_t ph = 0;
+      for (long long t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+        const TileCoord c = decode_tile(t, p);
+        const long long a_mn = c.b0 * p.a_mn_off[0] + c.b1 * p.a_mn_off[1] + c.b2 * p.a_mn_off[2] + (long long)c.mt * GEMM_BM;
+        const long long b_mn = c.b0 * p.b_mn_off[0] + c.b1 * p.b_mn_off[1] + c.b2 * p.b_mn_off[2] + (long long)c.nt * BN;
+        const long long a_k0 = c.b0 * p.a_k_off[0] + c.b1 * p.a_k_off[1] + c.b2 * p.a_k_off[2];
+        const long long b_k0 = c.b0 * p.b_k_off[0] + c.b1 * p.b_k_off[1] + c.b2 * p.b_k_off[2];
+        const int kb0 = c.ks * p.kb_per_split;
+        const int kb1 = min(p.kb_total, kb0 + p.kb_per_split);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(empty_bar(st), ph ^ 1);
+          const uint32_t sA = smem_base + st * Cfg::STAGE_BYTES;
+          const uint32_t sB = sA + Cfg::A_BYTES;
+          mbar_arrive_expect_tx(full_bar(st), Cfg::STAGE_BYTES);
+          const int ka = (int)(a_k0 + (long long)kb * GEMM_BK);
+          const int kbb = (int)(b_k0 + (long long)kb * GEMM_BK);
+          if (!A_MN) {
+            tma_load_2d(sA, &tmA, full_bar(st), ka, (int)a_mn);
+          } else {
+#pragma unroll
+            for (int at = 0; at < GEMM_BM / 64; ++at)
+              tma_load_2d(sA + at * 8192, &tmA, full_bar(st), (int)a_mn + at * 64, ka);
+          }
+          if (!B_MN) {
+            tma_load_2d(sB, &tmB, full_bar(st), kbb, (int)b_mn);
+          } else {
+#pragma unroll
+            for (int at = 0; at < BN / 64; ++at)
+              tma_load_2d(sB + at * 8192, &tmB, full_bar(st), (int)b_mn + at * 64, kbb);
+          }
+          if (++st == Cfg::STAGES) { st = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      int st = 0;
+      uint32_t ph = 0;
+      int acc = 0;
+      uint32_t acc_ph = 0;
+      for (long long t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+        const TileCoord c = decode_tile(t, p);
+        const int kb0 = c.ks * p.kb_per_split;
+        const int kb1 = min(p.kb_total, kb0 + p.kb_per_split);
+        mbar_wait(tempty_bar(acc), acc_ph ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(full_bar(st), ph);
+          tc_fence_after();
+          const uint32_t sA = smem_base + st * Cfg::STAGE_BYTES;
+          const uint32_t sB = sA + Cfg::A_BYTES;
+#pragma unroll
+          for (int k = 0; k < GEMM_BK / 16; ++k) {
+            // K-major: 16 elements = 32 B further along the swizzled row.
+            // MN-major: 16 K-rows of 128 B further down.
+            const uint64_t ad = A_MN ? umma_desc_sw128(sA + k * 2048, 8192, 1024)
+                                     : umma_desc_sw128(sA + k * 32, 0, 1024);
+            const uint64_t bd = B_MN ? umma_desc_sw128(sB + k * 2048, 8192, 1024)
+                                     : umma_desc_sw128(sB + k * 32, 0, 1024);
+            umma_f16_ss(d_tmem, ad, bd, p.idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(empty_bar(st));  // stage reusable once these MMAs have read it
+          if (++st == Cfg::STAGES) { st = 0; ph ^= 1; }
+        }
+        umma_commit(tfull_bar(acc));  // accumulator complete
+        if (++acc == 2) { acc = 0; acc_ph ^= 1; }
+      }
+    }
+  } else if (warp >= 4) {
+    // ------------------------------------------------------------------ epilogue
+    const int q = warp & 3;  // TMEM lane quadrant this warp may access
+    int acc = 0;
+    uint32_t acc_ph = 0;
+    for (long long t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+      const TileCoord c = decode_tile(t, p);
+      const int kb0 = c.ks * p.kb_per_split;
+      const bool has_k = kb0 < p.kb_total;
+      mbar_wait(tfull_bar(acc), acc_ph);
+      tc_fence_after();
+      const int row = c.mt * GEMM_BM + q * 32 + lane;
+      const int n0 = c.nt * BN;
+      const long long base = c.b0 * p.d_off[0] + c.b1 * p.d_off[1] + c.b2 * p.d_off[2];
+      const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + acc * BN;
+#pragma unroll 1
+      for (int cc = 0; cc < BN; cc += 32) {
+        if (n0 + cc >= p.N) break;  // warp-uniform
+        uint32_t r[32];
+        tmem_ld_32x32(taddr + cc, r);
+        tmem_ld_wait();
+        if (row < p.M) {
+          float v[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = has_k ? __uint_as_float(r[j]) * p.alpha : 0.f;
+          store_chunk(p, base, row, n0 + cc, v);
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(tempty_bar(acc));
+      if (++acc == 2) { acc = 0; acc_ph ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
+template <int BN, bool A_MN, bool B_MN>
+static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmArgs& args,
+                       cudaStream_t stream) {
+  using Cfg = GemmCfg<BN>;
+  auto kern = gemm_kernel<BN, A_MN, B_MN>;
+  static bool configured = false;
+  if (!configured) {
+    CSN_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    configured = true;
+  }
+  long long grid = args.total_tiles < num_sms() ? args.total_tiles : num_sms();
+  kern<<<(unsigned)grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, args);
+  CSN_LAUNCH_OK("gemm_kernel");
+  return 0;
+}
+
+template <int BN>
+static int dispatch_major(bool a_mn, bool b_mn, const CUtensorMap& tmA, const CUtensorMap& tmB,
+                          const GemmArgs& args, cudaStream_t stream) {
+  if (!a_mn && !b_mn) return launch_gemm<BN, false, false>(tmA, tmB, args, stream);
+  if (!a_mn && b_mn) return launch_gemm<BN, false, true>(tmA, tmB, args, stream);
+  if (a_mn && !b_mn) return launch_gemm<BN, true, false>(tmA, tmB, args, stream);
+  return launch_gemm<BN, true, true>(tmA, tmB, args, stream);
+}
+
+}  // namespace csn
+
+extern "C" int csn_gemm(const csn_mat* A, const csn_mat* B, const csn_out* D, int32_t M, int32_t N,
+                        int32_t K, const int32_t nb[3], float alpha, int32_t split_k, void* stream) {
+  using namespace csn;
+  clear_error();
+  CSN_CHECK_ARG(A && B && D && nb, "csn_gemm: null argument");
+  CSN_CHECK_ARG(M > 0 && N > 0 && K > 0, "csn_gemm: empty problem M=%d N=%d K=%d", M, N, K);
+  CSN_CHECK_ARG(A->dtype == B->dtype, "csn_gemm: operand dtypes differ");
+  CSN_CHECK_ARG(A->dtype == CSN_F16 || A->dtype == CSN_BF16, "csn_gemm: operands must be f16/bf16");
+  CSN_CHECK_ARG(nb[0] > 0 && nb[1] > 0 && nb[2] > 0, "csn_gemm: batch extents must be >= 1");
+  CSN_CHECK_ARG(split_k >= 1, "csn_gemm: split_k must be >= 1");
+  CSN_CHECK_ARG(split_k == 1 || D->accumulate, "csn_gemm: split_k > 1 requires accumulate");
+  CSN_CHECK_ARG(!D->accumulate || D->dtype == CSN_F32, "csn_gemm: accumulate requires fp32 output");
+  CSN_CHECK_ARG(D->ptr != nullptr && A->ptr != nullptr && B->ptr != nullptr, "csn_gemm: null data pointer");
+
+  const int BN = (N > 128) ? 256 : (N > 64 ? 128 : 64);
+  const bool a_mn = A->major == CSN_MAJOR_MN, b_mn = B->major == CSN_MAJOR_MN;
+
+  CUtensorMap tmA, tmB;
+  int rc;
+  rc = a_mn ? make_tmap_2d(&tmA, A->ptr, A->dtype, A->inner, A->outer, A->ld, 64, 64)
+            : make_tmap_2d(&tmA, A->ptr, A->dtype, A->inner, A->outer, A->ld, 64, GEMM_BM);
+  if (rc) return rc;
+  rc = b_mn ? make_tmap_2d(&tmB, B->ptr, B->dtype, B->inner, B->outer, B->ld, 64, 64)
+            : make_tmap_2d(&tmB, B->ptr, B->dtype, B->inner, B->outer, B->ld, 64, (uint32_t)BN);
+  if (rc) return rc;
+
+  GemmArgs g;
+  memset(&g, 0, sizeof(g));
+  g.M = M; g.N = N; g.K = K;
+  g.nb0 = nb[0]; g.nb1 = nb[1]; g.nb2 = nb[2];
+  g.tiles_m = (M + GEMM_BM - 1) / GEMM_BM;
+  g.tiles_n = (N + BN - 1) / BN;
+  g.kb_total = (K + GEMM_BK - 1) / GEMM_BK;
+  g.split_k = split_k > g.kb_total ? g.kb_total : split_k;
+  g.kb_per_split = (g.kb_total + g.split_k - 1) / g.split_k;
+  g.split_k = (g.kb_total + g.kb_per_split - 1) / g.kb_per_split;  // no empty splits
+  g.total_tiles = (long long)g.nb0 * g.nb1 * g.nb2 * g.tiles_m * g.tiles_n * g.split_k;
+  for (int i = 0; i < 3; ++i) {
+    g.a_mn_off[i] = A->mn_off[i]; g.a_k_off[i] = A->k_off[i];
+    g.b_mn_off[i] = B->mn_off[i]; g.b_k_off[i] = B->k_off[i];
+    g.d_off[i] = D->off[i];
+  }
+  g.D = D->ptr; g.ldd = D->ld; g.out_dtype = D->dtype; g.transposed = D->transposed;
+  g.accumulate = D->accumulate; g.alpha = alpha;
+  const int esz = D->dtype == CSN_F32 ? 4 : 2;
+  bool vec = ((reinterpret_cast<uintptr_t>(D->ptr) & 15) == 0) && ((D->ld * esz) % 16 == 0);
+  for (int i = 0; i < 3; ++i) vec = vec && ((D->off[i] * esz) % 16 == 0);
+  g.vec_ok = vec ? 1 : 0;
+  g.idesc = umma_idesc_f16(A->dtype == CSN_F16 ? 0u : 1u, a_mn ? 1u : 0u, b_mn ? 1u : 0u, (uint32_t)BN);
+
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  if (BN == 256) return dispatch_major<256>(a_mn, b_mn, tmA, tmB, g, s);
+  if (BN == 128) return dispatch_major<128>(a_mn, b_mn, tmA, tmB, g, s);
+  return dispatch_major<64>(a_mn, b_mn, tmA, tmB, g, s);
+}
