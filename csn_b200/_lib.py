@@ -65,7 +65,13 @@ def _declare(L: C.CDLL) -> None:
 
 
 # name -> argtypes for the remaining entry points (filled in by the sections below)
-_EXTRA_SIGNATURES: dict[str, list] = {}
+_EXTRA_SIGNATURES: dict[str, list] = {
+    "csn_normalize_rows": [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_float, C.c_int32, C.c_void_p],
+    "csn_knn_scores": [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_int32,
+                       C.c_void_p, C.c_void_p, C.c_void_p],
+    "csn_knn_reduce": [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int64, C.c_void_p],
+    "csn_topk_rows": [C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p],
+}
 
 
 def check(rc: int, what: str) -> None:

@@ -1,0 +1,160 @@
+"""Host side of the shape-compatibility retrieval path (kNN graph over a shape collection).
+
+Mirrors CrossShapeAt.get_retrieval_measure / get_knn_graph (MID-FC/csa_models.py:244-280), the
+big-class variant (:360-404, candidates = a subset of the collection) and
+HRNetSimCSN.cosine_similarity (MinkowskiNet/models/hrnet.py:472-490).  All arithmetic runs in
+csrc/knn.cu through the C ABI; this file only builds the small work tables.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass
+
+import torch
+
+from . import _lib as L
+
+TILE_ROWS = 128
+NUM_SMS = 148
+
+
+@dataclass
+class ShapeStore:
+    """Unit-norm 16-bit point features of a set of shapes, packed row-wise: shape s occupies rows
+    [row0[s], row0[s] + length[s]) of `rows` (total_rows, 256).  This is the GPU-resident candidate
+    store of SURVEY.md §8e (41 GB fp32 -> 20 GB 16-bit at S = 4000, N = 10k)."""
+    rows: torch.Tensor
+    row0: list[int]
+    length: list[int]
+
+    @property
+    def n_shapes(self) -> int:
+        return len(self.row0)
+
+    def subset(self, idx) -> "ShapeStore":
+        idx = [int(i) for i in idx]
+        return ShapeStore(self.rows, [self.row0[i] for i in idx], [self.length[i] for i in idx])
+
+
+def _normalize_into(src: torch.Tensor, dst: torch.Tensor, eps: float) -> None:
+    assert src.is_cuda and src.dtype == torch.float32 and src.is_contiguous()
+    rows, D = src.shape
+    rc = L.lib().csn_normalize_rows(src.data_ptr(), dst.data_ptr(), rows, D, eps, L.dtype_code(dst.dtype),
+                                    L.stream_ptr())
+    L.check(rc, "csn_normalize_rows")
+
+
+def build_store(feats, dtype: torch.dtype = torch.float16, eps: float = 1e-12) -> ShapeStore:
+    """feats: (S, N, D) fp32 CUDA tensor, or a list of (L_s, D) fp32 CUDA tensors (ragged)."""
+    if isinstance(feats, torch.Tensor):
+        assert feats.dim() == 3
+        S, N, D = feats.shape
+        src = feats.contiguous().view(S * N, D)
+        dst = torch.empty(S * N, D, dtype=dtype, device=feats.device)
+        _normalize_into(src, dst, eps)
+        return ShapeStore(dst, [s * N for s in range(S)], [N] * S)
+    lens = [int(f.shape[0]) for f in feats]
+    D = int(feats[0].shape[1])
+    total = sum(lens)
+    dst = torch.empty(total, D, dtype=dtype, device=feats[0].device)
+    row0, r = [], 0
+    for f, n in zip(feats, lens):
+        _normalize_into(f.contiguous(), dst[r:r + n], eps)
+        row0.append(r)
+        r += n
+    return ShapeStore(dst, row0, lens)
+
+
+def _split_for_balance(n_items: int, n_cand: int) -> int:
+    """Number of candidate-list segments per (query, tile) so that the persistent grid's last wave
+    is nearly full."""
+    best, best_waste = 1, 1.0
+    for ns in range(1, min(16, n_cand) + 1):
+        tot = n_items * ns
+        waste = (math.ceil(tot / NUM_SMS) * NUM_SMS - tot) / tot
+        if waste < best_waste - 1e-9:
+            best, best_waste = ns, waste
+        if best_waste < 0.03:
+            break
+    return best
+
+
+def scores_from_stores(q: ShapeStore, c: ShapeStore, query_block: int = 148) -> torch.Tensor:
+    """(Sq, Sc) fp32 retrieval measure of every query shape against every candidate shape."""
+    dev = q.rows.device
+    Sq, Sc = q.n_shapes, c.n_shapes
+    scores = torch.empty(Sq, Sc, dtype=torch.float32, device=dev)
+    cands = torch.tensor([[r, n] for r, n in zip(c.row0, c.length)], dtype=torch.int32, device=dev)
+    lib = L.lib()
+    for q0 in range(0, Sq, query_block):
+        q1 = min(Sq, q0 + query_block)
+        # tables: items ordered (query, tile, segment); partial rows ordered (query, tile)
+        items, row_of_query = [], []
+        part_rows = 0
+        for s in range(q0, q1):
+            nt = (q.length[s] + TILE_ROWS - 1) // TILE_ROWS
+            row_of_query.append((part_rows, nt))
+            part_rows += nt
+        ns = _split_for_balance(part_rows, Sc)
+        seg = [(i * Sc // ns, (i + 1) * Sc // ns) for i in range(ns)]
+        for s, (prow, nt) in zip(range(q0, q1), row_of_query):
+            for t in range(nt):
+                nvalid = min(TILE_ROWS, q.length[s] - t * TILE_ROWS)
+                for (b, e) in seg:
+                    items.append((q.row0[s] + t * TILE_ROWS, nvalid, b, e - b, (prow + t) * Sc + b, 0))
+        items_t = torch.tensor(items, dtype=torch.int32, device=dev)
+        partial = torch.empty(part_rows * Sc, dtype=torch.float32, device=dev)
+        rc = lib.csn_knn_scores(q.rows.data_ptr(), q.rows.shape[0], c.rows.data_ptr(), c.rows.shape[0],
+                                L.dtype_code(q.rows.dtype), items_t.data_ptr(), len(items), cands.data_ptr(),
+                                partial.data_ptr(), L.stream_ptr())
+        L.check(rc, "csn_knn_scores")
+        uniform = len({nt for _, nt in row_of_query}) == 1 and len({q.length[s] for s in range(q0, q1)}) == 1
+        if uniform:
+            nt = row_of_query[0][1]
+            rc = lib.csn_knn_reduce(partial.data_ptr(), scores[q0:q1].data_ptr(), q1 - q0, Sc, nt,
+                                    q.length[q0], scores.stride(0), L.stream_ptr())
+            L.check(rc, "csn_knn_reduce")
+        else:
+            for s, (prow, nt) in zip(range(q0, q1), row_of_query):
+                rc = lib.csn_knn_reduce(partial[prow * Sc:].data_ptr(), scores[s:s + 1].data_ptr(), 1, Sc, nt,
+                                        q.length[s], scores.stride(0), L.stream_ptr())
+                L.check(rc, "csn_knn_reduce")
+        # keep the tables alive until the kernels that read them have been enqueued on this stream
+        del items_t, partial
+    return scores
+
+
+def topk_rows(scores: torch.Tensor, k: int):
+    """Values and int64 indices of the k largest entries per row, sorted descending."""
+    assert scores.is_cuda and scores.dtype == torch.float32 and scores.dim() == 2 and scores.stride(1) == 1
+    n_rows, n_cols = scores.shape
+    val = torch.empty(n_rows, k, dtype=torch.float32, device=scores.device)
+    idx = torch.empty(n_rows, k, dtype=torch.int64, device=scores.device)
+    rc = L.lib().csn_topk_rows(scores.data_ptr(), scores.stride(0), n_rows, n_cols, k, val.data_ptr(),
+                               idx.data_ptr(), L.stream_ptr())
+    L.check(rc, "csn_topk_rows")
+    return val, idx
+
+
+def retrieval_measure(ssa_feats_1: torch.Tensor, ssa_feats_2: torch.Tensor, dtype=torch.float16,
+                      eps: float = 1e-12) -> torch.Tensor:
+    """get_retrieval_measure (csa_models.py:244-267): (Sq,N,D),(Sc,M,D) fp32 -> (Sq,Sc) fp32."""
+    q = build_store(ssa_feats_1, dtype, eps)
+    same = ssa_feats_2 is ssa_feats_1
+    c = q if same else build_store(ssa_feats_2, dtype, eps)
+    return scores_from_stores(q, c)
+
+
+def knn_graph(ssa_feats_1: torch.Tensor, ssa_feats_2: torch.Tensor, K: int, dtype=torch.float16) -> torch.Tensor:
+    """get_knn_graph (csa_models.py:270-280): indices of the K+1 best candidates per query, sorted
+    descending (self included when the two sets coincide)."""
+    s = retrieval_measure(ssa_feats_1, ssa_feats_2, dtype)
+    return topk_rows(s, K + 1)[1]
+
+
+def cosine_similarity(q: torch.Tensor, k: torch.Tensor, dtype=torch.float16) -> torch.Tensor:
+    """HRNetSimCSN.cosine_similarity (hrnet.py:472-490): rows divided by their raw norm (no eps),
+    mean over q rows of the max over k rows; q (Lq,D), k (Lk,D) -> 0-d tensor."""
+    qs = build_store([q.float()], dtype, 0.0)
+    ks = build_store([k.float()], dtype, 0.0)
+    return scores_from_stores(qs, ks)[0, 0]

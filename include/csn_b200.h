@@ -69,6 +69,40 @@ typedef struct csn_out {
 int csn_gemm(const csn_mat* A, const csn_mat* B, const csn_out* D, int32_t M, int32_t N, int32_t K,
              const int32_t nb[3], float alpha, int32_t split_k, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Shape-compatibility retrieval measure and top-K neighbour selection
+ * (reference: CrossShapeAt.get_retrieval_measure / get_knn_graph, MID-FC/csa_models.py:244-280 and
+ * :360-404; HRNetSimCSN.cosine_similarity, MinkowskiNet/models/hrnet.py:472-490; topk with
+ * self-exclusion, MinkowskiNet/lib/csn_utils.py:91-96).
+ * ------------------------------------------------------------------------------------------- */
+
+/* out[r] = in[r] / max(|in[r]|_2, eps) as 16-bit rows (F.normalize, csa_models.py:253,255; eps = 0
+ * gives the MinkowskiNet variant hrnet.py:475-480).  in: fp32 [rows][D], D in {128,256,384,512}. */
+int csn_normalize_rows(const float* in, void* out, int64_t rows, int32_t D, float eps,
+                       int32_t out_dtype, void* stream);
+
+/* Work tables for csn_knn_scores (int32, device memory):
+ *   items[i] = {q_row0, n_valid, list_begin, list_count, out_off, 0}: a tile of up to 128 query rows
+ *              starting at row q_row0 of feat_q, of which n_valid belong to the query shape, scored
+ *              against candidates cands[list_begin .. list_begin+list_count);
+ *   cands[j] = {row0, len}: a candidate shape occupying rows [row0, row0+len) of feat_c.
+ * partial[out_off + pos] = sum over the tile's valid rows p of max_q <feat_q[p], feat_c[row0+q]>.
+ * feat_q / feat_c: unit-norm 16-bit rows of width 256 (csn_normalize_rows). The N_q x N_c cosine
+ * matrix never leaves TMEM (the reference materialises it: csa_models.py:256). */
+int csn_knn_scores(const void* feat_q, int64_t rows_q, const void* feat_c, int64_t rows_c,
+                   int32_t dtype, const int32_t* items, int32_t n_items, const int32_t* cands,
+                   float* partial, void* stream);
+
+/* scores[q*ld + c] = (sum_{t<ntiles} partial[(q*ntiles+t)*n_cand + c]) / n_rows, summed in a fixed
+ * order (csa_models.py:257 `.max(-1)[0].mean(-1)`). */
+int csn_knn_reduce(const float* partial, float* scores, int32_t n_q, int32_t n_cand, int32_t ntiles,
+                   int32_t n_rows, int64_t ld_scores, void* stream);
+
+/* Per-row top-k (k <= 8), values and int64 indices sorted descending; equal scores: lower index
+ * first (`retrieval_measure.topk(K+1, -1)`, csa_models.py:278,401). */
+int csn_topk_rows(const float* scores, int64_t ld, int32_t n_rows, int32_t n_cols, int32_t k,
+                  float* out_val, int64_t* out_idx, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,95 @@
+"""GPU parity of the retrieval measure / kNN graph against the golden vectors produced by the
+reference (csa_models.py:244-280) and against the CPU oracle on fresh seeded inputs."""
+import numpy as np
+import pytest
+import torch
+
+from csn_b200 import synth
+from tests import golden_util as G
+
+pytestmark = pytest.mark.gpu
+
+# 16-bit operands with 11-bit mantissas: |score error| <= ~3e-6 measured by the reference survey
+# for TF32-class rounding; fp32 accumulation.
+SCORE_TOL_FP16 = 1e-5
+SCORE_TOL_BF16 = 8e-5
+
+
+def _sets_match_up_to_ties(got_idx, ref_scores, K1, tie):
+    """Index sets equal except where the reference scores at the boundary tie within `tie`."""
+    ref_scores = torch.as_tensor(ref_scores)
+    for r in range(ref_scores.shape[0]):
+        want = set(ref_scores[r].topk(K1).indices.tolist())
+        got = set(int(i) for i in got_idx[r])
+        if want == got:
+            continue
+        kth = ref_scores[r].topk(K1).values[-1].item()
+        for j in want ^ got:
+            assert abs(ref_scores[r, j].item() - kth) <= tie, (r, j, ref_scores[r, j].item(), kth)
+
+
+@pytest.mark.parametrize("name", ["knn_small", "knn_10k"])
+def test_scores_and_graph_match_reference_golden(name):
+    from csn_b200 import knn
+    g = G.load(name)
+    K = int(g["K"])
+    f = synth.clustered_shapes(int(g["seed"]), int(g["n_shapes"]), n_points=int(g["n_points"]),
+                               n_categories=int(g["n_categories"])).cuda()
+    s = knn.retrieval_measure(f, f)
+    err = np.abs(s.cpu().numpy() - g["scores"]).max()
+    assert err < SCORE_TOL_FP16, err
+    graph = knn.knn_graph(f, f, K).cpu()
+    _sets_match_up_to_ties(graph, g["scores"], K + 1, 2 * SCORE_TOL_FP16)
+    # self is the best match of every shape (score 1.0)
+    assert torch.equal(graph[:, 0], torch.arange(f.shape[0]))
+    rect = knn.retrieval_measure(f[:3].contiguous(), f[3:].contiguous())
+    assert np.abs(rect.cpu().numpy() - g["scores_rect"]).max() < SCORE_TOL_FP16
+
+
+def test_bf16_variant():
+    from csn_b200 import knn
+    g = G.load("knn_small")
+    f = synth.clustered_shapes(int(g["seed"]), int(g["n_shapes"]), n_points=int(g["n_points"]),
+                               n_categories=int(g["n_categories"])).cuda()
+    s = knn.retrieval_measure(f, f, dtype=torch.bfloat16)
+    assert np.abs(s.cpu().numpy() - g["scores"]).max() < SCORE_TOL_BF16
+
+
+def test_ragged_lengths_against_oracle():
+    """MinkowskiNet-style: shapes of different sizes, divide by the raw norm (hrnet.py:472-490)."""
+    from csn_b200 import knn
+    from oracle import csa_oracle as O
+    gen = synth.gen(7)
+    lens = [37, 128, 129, 300, 1000]
+    shapes = [torch.randn(n, 256, generator=gen) for n in lens]
+    for a in (0, 2, 4):
+        for b in (1, 3):
+            want = O.mink_cosine_similarity(shapes[a], shapes[b]).item()
+            got = knn.cosine_similarity(shapes[a].cuda(), shapes[b].cuda()).item()
+            assert abs(got - want) < SCORE_TOL_FP16, (a, b, got, want)
+
+
+def test_topk_rows_matches_torch():
+    from csn_b200 import knn
+    gen = synth.gen(3)
+    s = torch.randn(37, 1000, generator=gen).cuda()
+    for k in (1, 4, 6, 8):
+        val, idx = knn.topk_rows(s, k)
+        tv, ti = s.topk(k, dim=-1)
+        assert torch.equal(val, tv)
+        assert torch.equal(idx, ti)
+    # ties: lower index first, all entries equal
+    z = torch.zeros(3, 50).cuda()
+    _, idx = knn.topk_rows(z, 5)
+    assert torch.equal(idx.cpu(), torch.arange(5).expand(3, 5))
+
+
+def test_linearity_property_full_size():
+    """Size-independent property at the full N = 10 000: score(A, A) == 1 and scores are invariant
+    to a positive rescaling of either shape's features."""
+    from csn_b200 import knn
+    f = synth.clustered_shapes(5, 3, n_points=10000, n_categories=2).cuda()
+    s1 = knn.retrieval_measure(f, f)
+    s2 = knn.retrieval_measure(f * 3.0, (f * 0.25).contiguous())
+    assert (s1.diag() - 1.0).abs().max().item() < 2e-3  # 16-bit unit vectors: |v|^2 = 1 +- 2^-10
+    assert (s1 - s2).abs().max().item() < SCORE_TOL_FP16
