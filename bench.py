@@ -1,0 +1,399 @@
+#!/usr/bin/env python
+"""bench.py — headline measurement of the CSN hot path on B200 (contract: task prompt §④).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--heads H]
+
+One step = one pass of the hot path over one batch of synthetic input:
+  * CSA training step (BASELINE.json configs[1]): B = 8 query shapes x K = 3 neighbour shapes,
+    N = 10 000 points x 256-d, forward (CrossShapeAt.forward, csa_models.py:182-202) + masked CE
+    (csa_training.py:94-108) + backward.  metric = shape-pairs/s (B*K pairs per step), whole job.
+  * kNN retrieval (configs[2]), reported in the `knn` object of the same line: query shapes scored
+    against a 4 000-shape candidate store + top-(K+1); shapes/s.
+`value` is device-resident throughput (inputs in HBM before the timed region); `e2e` goes through the
+module API with pinned HOST buffers (H2D of every step's features inside the timed region, loss read
+back).  With torchrun (N > 1) query shapes are sharded data-parallel, one rank per GPU, parameter
+gradients all-reduced over NCCL each step (weak scaling: per-GPU batch fixed).
+
+--impl reference times the CPU oracle port (oracle/csa_oracle.py, a restatement of the reference's
+PyTorch code; the reference itself is Python and cannot travel to the GPU box) on the host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+import torch  # noqa: E402
+
+N_POINTS, D = 10000, 256
+CSA_B, CSA_K, N_CLASSES = 8, 3, 15
+KNN_CANDIDATES, KNN_TOPK = 4000, 5
+
+
+def csa_flops_per_query(K: int, h: int, d: int = 256, C: int = 500, N: int = N_POINTS) -> float:
+    """Algorithmic fwd FLOPs of one de-duplicated CSA layer call:
+    2*N*h*d*[3(K+1)D + (1+2K)(2C + D)]; fwd+bwd = 3x."""
+    return 2.0 * N * h * d * (3 * (K + 1) * D + (1 + 2 * K) * (2 * C + D))
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        try:
+            f = tempfile.NamedTemporaryFile("w", suffix=".csv", delete=False)
+            self.path = f.name
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"], stdout=f,
+                                         stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in Path(self.path).read_text().splitlines():
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 6:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx = float(parts[1])
+            except ValueError:
+                continue
+            for n, v in zip(names, parts[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        os.unlink(self.path)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def masked_ce(logits, label):
+    C = logits.shape[1]
+    lg = logits.squeeze(-1).permute(0, 2, 1).reshape(-1, C)
+    lb = label.reshape(-1)
+    keep = lb > 0
+    return torch.nn.functional.cross_entropy(lg[keep], lb[keep])
+
+
+def peaks() -> dict:
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        d = json.loads(p.read_text())
+        return {"tflops_burst": d["bf16_tflops"], "tflops_sustained": d["bf16_tflops_sustained"],
+                "hbm_gbs": d["hbm_gbs"], "source": "measured (MEASURED_PEAKS.json)"}
+    return {"tflops_burst": 1590.0, "tflops_sustained": 1400.0, "hbm_gbs": 6650.0,
+            "source": "fallback (B200_PROFILING.md)"}
+
+
+# ----------------------------------------------------------------------------------------- reference arm
+def run_reference(args) -> None:
+    """CPU oracle port on the host cores, same metric/config; rank 0 only."""
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    from csn_b200 import synth
+    from oracle import csa_oracle as O
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    h = args.heads
+    sample_b = 1   # bounded sample: 1 query shape x K=3 neighbours of the B=8 batch per step
+    sd = synth.midfc_state(1, h, N_CLASSES)
+    w = {k: v.clone().requires_grad_(v.is_floating_point()) for k, v in sd.items()}
+    x, nb = synth.csa_batch(2, sample_b, CSA_K)
+    label = torch.randint(0, N_CLASSES, (sample_b, N_POINTS), generator=synth.gen(3))
+
+    def step():
+        for v in w.values():
+            v.grad = None
+        loss = O.masked_cross_entropy(O.forward_csa(x, nb, w, h), label)
+        loss.backward()
+        return float(loss)
+
+    steps = max(1, min(args.steps, 5))
+    for _ in range(max(1, min(args.warmup, 1))):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = (time.perf_counter() - t0) / steps
+    value = sample_b * CSA_K / dt
+    sample = f"{sample_b} query shape x K={CSA_K} neighbours (of the B={CSA_B} batch) per step, fp32, eval, {steps} steps"
+    line = {
+        "impl": "reference", "metric": "csa_shape_pairs_per_s_fwd_bwd", "value": value, "unit": "shape-pairs/s",
+        "n_gpus": args.gpus, "steps": steps, "warmup": 1, "ms_per_step": dt * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"MID-FC CSA training step B={CSA_B} K={CSA_K} h={h} N={N_POINTS} D={D} (configs[1])",
+                   "heads": h},
+        "cpu_baseline": {"value": value, "unit": "shape-pairs/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "shape-pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------- our arm
+def run_ours(args) -> None:
+    import torch.distributed as dist
+
+    from csn_b200 import _lib as L
+    from csn_b200 import knn, midfc, synth
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    h = args.heads
+    pk = peaks()
+
+    # ------------------------------------------------------------------ CSA training step
+    model = midfc.get_model("csa", N_CLASSES, h, CSA_K, precision=args.precision).to(dev).eval()
+    model.load_state_dict(synth.midfc_state(1, h, N_CLASSES))
+    params = [p for n, p in model.named_parameters() if not n.startswith("fc_1")]
+    g = torch.Generator(device=dev).manual_seed(100 + rank)
+    # device-resident inputs (two alternating batches > L2 each: 82 MB + 328 MB)
+    batches = []
+    for _ in range(2):
+        nb = torch.relu(torch.randn(CSA_B, CSA_K + 1, D, N_POINTS, 1, device=dev, generator=g))
+        x = nb[:, 0].clone()
+        lab = torch.randint(0, N_CLASSES, (CSA_B, N_POINTS), device=dev, generator=g)
+        batches.append((x, nb, lab))
+    flat_grads = None
+
+    def train_step(x, nb, lab):
+        for p in params:
+            p.grad = None
+        loss = masked_ce(model(x, "test", nb), lab)
+        loss.backward()
+        if world > 1:  # data-parallel gradient exchange: one flat all-reduce over NCCL
+            flat = torch.cat([p.grad.reshape(-1) for p in params if p.grad is not None])
+            dist.all_reduce(flat)
+            flat.div_(world)
+        return loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(args.warmup):
+        train_step(*batches[i % 2])
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0 = L.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for i in range(args.steps):
+        train_step(*batches[i % 2])
+    e1.record()
+    barrier()
+    launches = L.launch_count() - l0
+    ms = e0.elapsed_time(e1)
+    t = torch.tensor([ms], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_step = t.item() / args.steps
+    pairs = world * CSA_B * CSA_K
+    value = pairs / (ms_step * 1e-3)
+    step_flops = 3.0 * CSA_B * csa_flops_per_query(CSA_K, h)
+    achieved = step_flops / (ms_step * 1e-3) / 1e12
+
+    # ------------------------------------------------------------------ e2e: host buffers through the module API
+    hx = [torch.empty(CSA_B, D, N_POINTS, 1).pin_memory() for _ in range(2)]
+    hn = [torch.empty(CSA_B, CSA_K + 1, D, N_POINTS, 1).pin_memory() for _ in range(2)]
+    hl = [torch.empty(CSA_B, N_POINTS, dtype=torch.int64).pin_memory() for _ in range(2)]
+    for i in range(2):
+        hx[i].copy_(batches[i][0]); hn[i].copy_(batches[i][1]); hl[i].copy_(batches[i][2])
+    h2d = hx[0].numel() * 4 + hn[0].numel() * 4 + hl[0].numel() * 8
+
+    def e2e_step(i):
+        x = hx[i % 2].to(dev, non_blocking=True)
+        nb = hn[i % 2].to(dev, non_blocking=True)
+        lab = hl[i % 2].to(dev, non_blocking=True)
+        return train_step(x, nb, lab).item()   # device -> host read of the step's loss
+
+    e2e_steps = max(2, min(args.steps, 5))
+    e2e_step(0)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(e2e_steps):
+        e2e_step(i)
+    barrier()
+    t_e2e = torch.tensor([time.perf_counter() - t0], device=dev)
+    if world > 1:
+        dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
+    e2e_value = pairs * e2e_steps / t_e2e.item()
+    clocks = sampler.stop() if rank == 0 else None
+    del batches, hx, hn, hl
+    torch.cuda.empty_cache()
+
+    # ------------------------------------------------------------------ kNN retrieval
+    knn_obj = None
+    if not args.no_knn:
+        n_c = args.knn_candidates
+        q_per_step = 4
+        per_rank = (n_c + world - 1) // world
+        lo, hi = rank * per_rank, min(n_c, (rank + 1) * per_rank)
+        gk = torch.Generator(device=dev).manual_seed(7)
+        protos = torch.randn(16, 32, D, device=dev, generator=gk)
+        store_rows = torch.empty(n_c * N_POINTS, D, dtype=torch.float16, device=dev)
+
+        def make_shapes(ids):
+            gs = torch.Generator(device=dev).manual_seed(1000 + int(ids[0]))
+            out = torch.empty(len(ids), N_POINTS, D, device=dev)
+            for j, s in enumerate(ids):
+                part = torch.randint(0, 32, (N_POINTS,), device=dev, generator=gs)
+                jit = torch.randn(32, D, device=dev, generator=gs)
+                out[j] = torch.relu(protos[s % 16][part] + 0.15 * jit[part] + 0.5 * torch.randn(N_POINTS, D, device=dev, generator=gs))
+            return out
+
+        # each rank normalises its own block of the collection, then the blocks are exchanged
+        for s0 in range(lo, hi, 50):
+            ids = list(range(s0, min(hi, s0 + 50)))
+            st = knn.build_store(make_shapes(ids))
+            store_rows[s0 * N_POINTS:(s0 + len(ids)) * N_POINTS] = st.rows
+        allgather_ms = 0.0
+        if world > 1:
+            barrier()
+            a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a0.record()
+            if n_c % world == 0:
+                dist.all_gather_into_tensor(store_rows, store_rows[lo * N_POINTS:hi * N_POINTS].clone())
+            else:
+                for r in range(world):
+                    rl, rh = r * per_rank, min(n_c, (r + 1) * per_rank)
+                    dist.broadcast(store_rows[rl * N_POINTS:rh * N_POINTS], src=r)
+            a1.record()
+            barrier()
+            allgather_ms = a0.elapsed_time(a1)
+        cstore = knn.ShapeStore(store_rows, [s * N_POINTS for s in range(n_c)], [N_POINTS] * n_c)
+        # queries: this rank's shapes (sharded by query shape)
+        k_steps = max(2, min(args.steps, 3))
+
+        def knn_step(i):
+            ids = [(lo + (i * q_per_step + j)) % n_c for j in range(q_per_step)]
+            qstore = cstore.subset(ids)
+            sc = knn.scores_from_stores(qstore, cstore)
+            return knn.topk_rows(sc, KNN_TOPK)
+
+        knn_step(0)
+        barrier()
+        k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        k0.record()
+        for i in range(k_steps):
+            knn_step(i + 1)
+        k1.record()
+        barrier()
+        tk = torch.tensor([k0.elapsed_time(k1)], device=dev)
+        if world > 1:
+            dist.all_reduce(tk, op=dist.ReduceOp.MAX)
+        kms = tk.item() / k_steps
+        kflops = 2.0 * q_per_step * n_c * N_POINTS * N_POINTS * D
+        kach = kflops / (kms * 1e-3) / 1e12
+        knn_obj = {"metric": "knn_retrieval_shapes_per_s", "value": world * q_per_step / (kms * 1e-3), "unit": "shapes/s",
+                   "ms_per_step": kms, "steps": k_steps,
+                   "config": {"workload": f"{q_per_step} query shapes/rank/step vs {n_c}-shape candidate store, N={N_POINTS}, top-{KNN_TOPK} (configs[2])",
+                              "candidate_store_gb": store_rows.numel() * 2 / 1e9, "store_exchange_ms": allgather_ms},
+                   "roofline": {"bound": "tensor", "kernel": "knn_score_kernel", "achieved": kach, "peak": pk["tflops_sustained"],
+                                "unit": "TFLOP/s", "frac": kach / pk["tflops_sustained"], "traffic": None,
+                                "peak_source": pk["source"] + ", sustained bf16 (kernel runs for seconds)"}}
+
+    # ------------------------------------------------------------------ CPU baseline (rank 0, N = 1 only)
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        from oracle import csa_oracle as O
+        cores = os.cpu_count() or 1
+        torch.set_num_threads(cores)
+        sd = synth.midfc_state(1, h, N_CLASSES)
+        w = {k: v.clone().requires_grad_(v.is_floating_point()) for k, v in sd.items()}
+        cx, cnb = synth.csa_batch(2, 1, CSA_K)
+        clab = torch.randint(0, N_CLASSES, (1, N_POINTS), generator=synth.gen(3))
+
+        def cstep():
+            for v in w.values():
+                v.grad = None
+            O.masked_cross_entropy(O.forward_csa(cx, cnb, w, h), clab).backward()
+
+        cstep()
+        t0 = time.perf_counter()
+        n = 2
+        for _ in range(n):
+            cstep()
+        cdt = (time.perf_counter() - t0) / n
+        cpu = {"value": CSA_K / cdt, "unit": "shape-pairs/s", "cores": cores, "kind": "port",
+               "sample": f"oracle port, 1 query shape x K={CSA_K} neighbours (1/8 of the batch), fwd+bwd, fp32, {n} steps"}
+
+    if rank == 0:
+        line = {
+            "metric": "csa_shape_pairs_per_s_fwd_bwd", "value": value, "unit": "shape-pairs/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": args.precision + " operands, f32 accumulate", "data": "synthetic",
+            "config": {"workload": f"MID-FC CSA training step B={CSA_B} K={CSA_K} h={h} N={N_POINTS} D={D} per GPU (configs[1])",
+                       "heads": h, "parallelism": f"dp{world} over query shapes", "l2": "inputs 410 MB/step > L2, two alternating batches",
+                       "dropout": "off (eval semantics, see DESIGN.md)"},
+            "clocks": clocks, "gpu_launches": int(launches),
+            "e2e": {"value": e2e_value, "unit": "shape-pairs/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 4,
+                    "steps": e2e_steps},
+            "roofline": {"bound": "tensor", "kernel": "whole step (gemm_kernel launches dominate)", "achieved": achieved,
+                         "peak": pk["tflops_sustained"], "unit": "TFLOP/s", "frac": achieved / pk["tflops_sustained"],
+                         "traffic": None, "algorithmic_flops_per_step": step_flops, "peak_source": pk["source"] + ", sustained bf16"},
+            "cpu_baseline": cpu, "knn": knn_obj,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main() -> None:
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--heads", type=int, default=1)
+    ap.add_argument("--precision", default="fp16", choices=["fp16", "bf16"])
+    ap.add_argument("--knn-candidates", type=int, default=KNN_CANDIDATES)
+    ap.add_argument("--no-knn", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

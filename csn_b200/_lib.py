@@ -25,12 +25,12 @@ class CsnError(RuntimeError):
 class csn_mat(C.Structure):
     _fields_ = [("ptr", C.c_void_p), ("dtype", C.c_int32), ("major", C.c_int32),
                 ("inner", C.c_int64), ("outer", C.c_int64), ("ld", C.c_int64),
-                ("mn_off", C.c_int64 * 3), ("k_off", C.c_int64 * 3)]
+                ("mn_off", C.c_int64 * 4), ("k_off", C.c_int64 * 4)]
 
 
 class csn_out(C.Structure):
     _fields_ = [("ptr", C.c_void_p), ("dtype", C.c_int32), ("transposed", C.c_int32),
-                ("ld", C.c_int64), ("off", C.c_int64 * 3), ("accumulate", C.c_int32),
+                ("ld", C.c_int64), ("off", C.c_int64 * 4), ("accumulate", C.c_int32),
                 ("reserved", C.c_int32)]
 
 
@@ -70,6 +70,23 @@ _EXTRA_SIGNATURES: dict[str, list] = {
     "csn_knn_scores": [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_int32,
                        C.c_void_p, C.c_void_p, C.c_void_p],
     "csn_knn_reduce": [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int64, C.c_void_p],
+    "csn_pack_rows": [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int64, C.c_int32, C.c_int64,
+                      C.c_int64, C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                      C.c_void_p],
+    "csn_softmax_fwd": [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                        C.c_void_p],
+    "csn_softmax_bwd": [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                        C.c_float, C.c_int32, C.c_void_p],
+    "csn_add_ln_fwd": [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                       C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_float,
+                       C.c_int32, C.c_void_p],
+    "csn_ln_bwd": [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                   C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p],
+    "csn_combine_fwd": [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32,
+                        C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p],
+    "csn_combine_bwd": [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                        C.c_float, C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.c_int64, C.c_int32, C.c_int32,
+                        C.c_int32, C.c_int32, C.c_void_p],
     "csn_topk_rows": [C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p],
 }
 
@@ -93,8 +110,8 @@ def dtype_code(dt: torch.dtype) -> int:
 
 
 def _i3(vals) -> "C.Array":
-    v = list(vals) + [0] * (3 - len(vals))
-    return (C.c_int64 * 3)(*v)
+    v = [int(x) for x in vals] + [0] * (4 - len(vals))
+    return (C.c_int64 * 4)(*v)
 
 
 def mat(t: torch.Tensor, major: int, mn_off=(), k_off=()) -> csn_mat:
@@ -127,6 +144,6 @@ def out(t: torch.Tensor, ld: int, transposed: bool = False, off=(), accumulate: 
 
 def gemm(A: csn_mat, B: csn_mat, D: csn_out, M: int, N: int, K: int, nb=(1, 1, 1), alpha: float = 1.0,
          split_k: int = 1) -> None:
-    nb3 = (C.c_int32 * 3)(*(list(nb) + [1] * (3 - len(nb))))
+    nb3 = (C.c_int32 * 4)(*([int(x) for x in nb] + [1] * (4 - len(nb))))
     rc = lib().csn_gemm(C.byref(A), C.byref(B), C.byref(D), M, N, K, nb3, alpha, split_k, stream_ptr())
     check(rc, "csn_gemm")

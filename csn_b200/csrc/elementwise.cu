@@ -1,0 +1,542 @@
+// HBM-bound pieces of the CSA/SSA layer (everything that is not a contraction):
+//   pack        : channel-major fp32 (B,256,N,1) -> chunk-padded row-major 16-bit (+fp32) rows
+//   softmax     : fwd (fp32 scores -> 16-bit probabilities) and bwd (dS = P o (dP - rowsum(P o dP)) * scale)
+//   add + LN    : z = fc_out + residual ; y = LayerNorm(z) (eps 1e-6, biased variance) ; pooled column sums
+//   LN bwd      : dz, dgamma, dbeta
+//   combine     : out = sum_k comp[b,k] * Y[pair(b,k)]  written channel-major (csa_models.py:232-240), and its bwd
+// Reference lines: MID-FC/csa_models.py:92-94 (layout), :141 (softmax), :116-118 (residual + LayerNorm),
+// :211-219 (mean over points), :232-240 (weighted sum + transpose back).
+// Rows of every intermediate live in "padded" coordinates: chunk c of `chunk` (=500) points occupies
+// rows [c*chunk_pad, c*chunk_pad + chunk) of a shape's block (chunk_pad = 512); pad rows are zero.
+#include "host_util.h"
+#include "ptx.cuh"
+
+namespace csn {
+
+constexpr int DM = 256;  // d_model on this path
+
+__device__ __forceinline__ uint32_t pack2(float a, float b, int dtype) {
+  if (dtype == CSN_F16) {
+    __half2 h = __floats2half2_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&h);
+  }
+  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+__device__ __forceinline__ float2 unpack2(uint32_t w, int dtype) {
+  if (dtype == CSN_F16) return __half22float2(*reinterpret_cast<__half2*>(&w));
+  return __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&w));
+}
+
+// ------------------------------------------------------------------------------------------ pack
+struct PackArgs {
+  const float* src;     // channel-major: element (slot, c, n) at src + i0*src_s0 + i1*src_s1 + c*ch_stride + n
+  void* dst16;          // [slot][rows_pad][256] 16-bit
+  float* dst32;         // same layout fp32, or null
+  long long ch_stride, src_s0, src_s1;
+  long long dst_slot0, dst_s0, dst_s1;  // destination slot = dst_slot0 + i0*dst_s0 + i1*dst_s1
+  int n0, n1;
+  int n_points;         // points used from the source (n_chunks * chunk)
+  int chunk, chunk_pad, rows_pad;
+  int dtype;
+};
+
+__global__ void __launch_bounds__(256) pack_kernel(const PackArgs p) {
+  __shared__ float tile[32][DM + 1];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int i0 = blockIdx.y / p.n1, i1 = blockIdx.y % p.n1;
+  const float* src = p.src + i0 * p.src_s0 + i1 * p.src_s1;
+  const long long slot = p.dst_slot0 + i0 * p.dst_s0 + i1 * p.dst_s1;
+  const int r0 = blockIdx.x * 32;  // first padded row of this tile (32 | chunk_pad)
+  const int ch = r0 / p.chunk_pad, i = r0 % p.chunk_pad + lane;
+  const int n = ch * p.chunk + i;
+  const bool valid = i < p.chunk && n < p.n_points;
+  for (int c = warp; c < DM; c += 8) tile[lane][c] = valid ? __ldg(src + c * p.ch_stride + n) : 0.f;
+  __syncthreads();
+  for (int rr = warp; rr < 32; rr += 8) {
+    const long long row = slot * p.rows_pad + r0 + rr;
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      const int c = g * 64 + 2 * lane;
+      const float a = tile[rr][c], b = tile[rr][c + 1];
+      reinterpret_cast<uint32_t*>(p.dst16)[(row * DM + c) >> 1] = pack2(a, b, p.dtype);
+      if (p.dst32) *reinterpret_cast<float2*>(p.dst32 + row * DM + c) = make_float2(a, b);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------ softmax fwd
+// One warp per row. cols_pad = 128*NV (NV <= 4 keeps the row in registers). Columns >= cols_valid are
+// masked; rows whose index inside their group (row % group_rows) is >= rows_valid are written as zeros.
+template <int NV>
+__global__ void softmax_fwd_kernel(const float* __restrict__ S, void* __restrict__ P, long long rows,
+                                   int cols_valid, int group_rows, int rows_valid, int dtype) {
+  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  constexpr int CP = 128 * NV;
+  uint2* dst = reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(P) + row * CP);
+  if ((int)(row % group_rows) >= rows_valid) {
+#pragma unroll
+    for (int j = 0; j < NV; ++j) dst[j * 32 + lane] = make_uint2(0u, 0u);
+    return;
+  }
+  const float4* src = reinterpret_cast<const float4*>(S + row * CP);
+  float4 v[NV];
+  float m = -INFINITY;
+#pragma unroll
+  for (int j = 0; j < NV; ++j) {
+    v[j] = __ldg(src + j * 32 + lane);
+    const int c = j * 128 + lane * 4;
+    if (c + 0 >= cols_valid) v[j].x = -INFINITY;
+    if (c + 1 >= cols_valid) v[j].y = -INFINITY;
+    if (c + 2 >= cols_valid) v[j].z = -INFINITY;
+    if (c + 3 >= cols_valid) v[j].w = -INFINITY;
+    m = fmaxf(m, fmaxf(fmaxf(v[j].x, v[j].y), fmaxf(v[j].z, v[j].w)));
+  }
+  m = warp_max(m);
+  float s = 0.f;
+#pragma unroll
+  for (int j = 0; j < NV; ++j) {
+    v[j].x = __expf(v[j].x - m); v[j].y = __expf(v[j].y - m);
+    v[j].z = __expf(v[j].z - m); v[j].w = __expf(v[j].w - m);
+    s += (v[j].x + v[j].y) + (v[j].z + v[j].w);
+  }
+  s = warp_sum(s);
+  const float inv = 1.f / s;
+#pragma unroll
+  for (int j = 0; j < NV; ++j)
+    dst[j * 32 + lane] = make_uint2(pack2(v[j].x * inv, v[j].y * inv, dtype), pack2(v[j].z * inv, v[j].w * inv, dtype));
+}
+
+// Generic width (three passes over the row, served by L1/L2).
+__global__ void softmax_fwd_wide_kernel(const float* __restrict__ S, void* __restrict__ P, long long rows,
+                                        int cols_pad, int cols_valid, int group_rows, int rows_valid, int dtype) {
+  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  uint16_t* dst = reinterpret_cast<uint16_t*>(P) + row * cols_pad;
+  const bool dead = (int)(row % group_rows) >= rows_valid;
+  const float* src = S + row * cols_pad;
+  float m = -INFINITY;
+  if (!dead) for (int c = lane; c < cols_valid; c += 32) m = fmaxf(m, src[c]);
+  m = warp_max(m);
+  float s = 0.f;
+  if (!dead) for (int c = lane; c < cols_valid; c += 32) s += __expf(src[c] - m);
+  s = warp_sum(s);
+  const float inv = dead ? 0.f : 1.f / s;
+  for (int c = lane; c < cols_pad; c += 32) {
+    const float pv = (c < cols_valid && !dead) ? __expf(src[c] - m) * inv : 0.f;
+    dst[c] = (uint16_t)(pack2(pv, 0.f, dtype) & 0xFFFFu);
+  }
+}
+
+// ------------------------------------------------------------------------------------------ softmax bwd
+// dS = P o (dP - sum_j P_j dP_j) * scale, written as 16-bit with zeros in pad rows / columns.
+__global__ void softmax_bwd_kernel(const void* __restrict__ P, const float* __restrict__ dP, void* __restrict__ dS,
+                                   long long rows, int cols_pad, int cols_valid, int group_rows, int rows_valid,
+                                   float scale, int dtype) {
+  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const uint32_t* p2 = reinterpret_cast<const uint32_t*>(reinterpret_cast<const uint16_t*>(P) + row * cols_pad);
+  const float2* g2 = reinterpret_cast<const float2*>(dP + row * cols_pad);
+  uint32_t* d2 = reinterpret_cast<uint32_t*>(reinterpret_cast<uint16_t*>(dS) + row * cols_pad);
+  const bool dead = (int)(row % group_rows) >= rows_valid;
+  const int npair = cols_pad >> 1;
+  float dot = 0.f;
+  if (!dead)
+    for (int c = lane; c < npair; c += 32) {
+      const float2 pv = unpack2(__ldg(p2 + c), dtype);
+      const float2 gv = __ldg(g2 + c);
+      if (2 * c < cols_valid) dot += pv.x * gv.x;
+      if (2 * c + 1 < cols_valid) dot += pv.y * gv.y;
+    }
+  dot = warp_sum(dot);
+  for (int c = lane; c < npair; c += 32) {
+    float a = 0.f, b = 0.f;
+    if (!dead) {
+      const float2 pv = unpack2(__ldg(p2 + c), dtype);
+      const float2 gv = __ldg(g2 + c);
+      if (2 * c < cols_valid) a = pv.x * (gv.x - dot) * scale;
+      if (2 * c + 1 < cols_valid) b = pv.y * (gv.y - dot) * scale;
+    }
+    d2[c] = pack2(a, b, dtype);
+  }
+}
+
+// ------------------------------------------------------------------------------------------ add + LayerNorm fwd
+// Block = 8 warps, 64 consecutive rows (8 per warp), all inside one `block_rows`-row block (64 | block_rows).
+struct AddLnArgs {
+  float* Z;              // in: fc output [rows][256]; out: z = fc + residual (kept for backward)
+  const float* R;        // residual source rows [*][256] fp32
+  const int* res_block;  // per block (= row / block_rows): index of the residual block
+  float* Y;              // LayerNorm output
+  void* Y16;             // optional 16-bit copy of Y (null to skip)
+  float* mean; float* rstd;
+  const float* gamma; const float* beta;
+  float* colsum;         // optional [n_blocks][256]: sum of Y over the valid rows (atomically accumulated)
+  long long rows;
+  int block_rows;        // rows per (pair) block, e.g. 10240
+  int group_rows, rows_valid;  // pad structure inside a block: row % group_rows < rows_valid is valid
+  float eps;
+  int dtype;
+};
+
+__global__ void __launch_bounds__(256) add_ln_fwd_kernel(const AddLnArgs p) {
+  __shared__ float red[8][DM];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long row0 = (long long)blockIdx.x * 64;
+  const long long blk = row0 / p.block_rows;
+  const long long rblk = p.res_block ? p.res_block[blk] : blk;
+  const float4 g0 = __ldg(reinterpret_cast<const float4*>(p.gamma) + lane), g1 = __ldg(reinterpret_cast<const float4*>(p.gamma) + 32 + lane);
+  const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.beta) + lane), b1 = __ldg(reinterpret_cast<const float4*>(p.beta) + 32 + lane);
+  float cs[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  for (int i = 0; i < 8; ++i) {
+    const long long row = row0 + warp * 8 + i;
+    if (row >= p.rows) break;
+    const long long rin = row - blk * p.block_rows;
+    float4* z4 = reinterpret_cast<float4*>(p.Z + row * DM);
+    float4* y4 = reinterpret_cast<float4*>(p.Y + row * DM);
+    const bool valid = (int)(rin % p.group_rows) < p.rows_valid;
+    if (!valid) {
+      const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+      z4[lane] = zero; z4[32 + lane] = zero; y4[lane] = zero; y4[32 + lane] = zero;
+      if (p.Y16) {
+        uint2* y16 = reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(p.Y16) + row * DM);
+        y16[lane] = make_uint2(0, 0); y16[32 + lane] = make_uint2(0, 0);
+      }
+      if (lane == 0) { p.mean[row] = 0.f; p.rstd[row] = 0.f; }
+      continue;
+    }
+    const float4* r4 = reinterpret_cast<const float4*>(p.R + (rblk * p.block_rows + rin) * DM);
+    float4 a = z4[lane], c = z4[32 + lane];
+    const float4 ra = __ldg(r4 + lane), rc = __ldg(r4 + 32 + lane);
+    a.x += ra.x; a.y += ra.y; a.z += ra.z; a.w += ra.w;
+    c.x += rc.x; c.y += rc.y; c.z += rc.z; c.w += rc.w;
+    z4[lane] = a; z4[32 + lane] = c;
+    const float mu = warp_sum((a.x + a.y) + (a.z + a.w) + (c.x + c.y) + (c.z + c.w)) * (1.f / DM);
+    const float dx0 = a.x - mu, dx1 = a.y - mu, dx2 = a.z - mu, dx3 = a.w - mu;
+    const float dx4 = c.x - mu, dx5 = c.y - mu, dx6 = c.z - mu, dx7 = c.w - mu;
+    const float var = warp_sum((dx0 * dx0 + dx1 * dx1) + (dx2 * dx2 + dx3 * dx3) + (dx4 * dx4 + dx5 * dx5) + (dx6 * dx6 + dx7 * dx7)) * (1.f / DM);
+    const float rs = rsqrtf(var + p.eps);
+    float4 ya, yc;
+    ya.x = dx0 * rs * g0.x + b0.x; ya.y = dx1 * rs * g0.y + b0.y; ya.z = dx2 * rs * g0.z + b0.z; ya.w = dx3 * rs * g0.w + b0.w;
+    yc.x = dx4 * rs * g1.x + b1.x; yc.y = dx5 * rs * g1.y + b1.y; yc.z = dx6 * rs * g1.z + b1.z; yc.w = dx7 * rs * g1.w + b1.w;
+    y4[lane] = ya; y4[32 + lane] = yc;
+    if (p.Y16) {
+      uint2* y16 = reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(p.Y16) + row * DM);
+      y16[lane] = make_uint2(pack2(ya.x, ya.y, p.dtype), pack2(ya.z, ya.w, p.dtype));
+      y16[32 + lane] = make_uint2(pack2(yc.x, yc.y, p.dtype), pack2(yc.z, yc.w, p.dtype));
+    }
+    if (lane == 0) { p.mean[row] = mu; p.rstd[row] = rs; }
+    cs[0] += ya.x; cs[1] += ya.y; cs[2] += ya.z; cs[3] += ya.w;
+    cs[4] += yc.x; cs[5] += yc.y; cs[6] += yc.z; cs[7] += yc.w;
+  }
+  if (p.colsum) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { red[warp][lane * 4 + j] = cs[j]; red[warp][128 + lane * 4 + j] = cs[4 + j]; }
+    __syncthreads();
+    const int c = threadIdx.x;
+    float s = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) s += red[w][c];
+    atomicAdd(p.colsum + blk * DM + c, s);
+  }
+}
+
+// ------------------------------------------------------------------------------------------ LayerNorm bwd
+struct LnBwdArgs {
+  const float* dY; const float* Z; const float* mean; const float* rstd; const float* gamma;
+  float* dZ;        // fp32 [rows][256] (also the gradient of the residual input)
+  void* dZ16;       // 16-bit copy for the tensor-core contractions
+  float* dgamma; float* dbeta;  // [256], atomically accumulated
+  long long rows;
+  int group_rows, rows_valid, block_rows;
+  int dtype;
+};
+
+__global__ void __launch_bounds__(256) ln_bwd_kernel(const LnBwdArgs p) {
+  __shared__ float red[2][8][DM];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long row0 = (long long)blockIdx.x * 64;
+  const float4 g0 = __ldg(reinterpret_cast<const float4*>(p.gamma) + lane), g1 = __ldg(reinterpret_cast<const float4*>(p.gamma) + 32 + lane);
+  float dg[8] = {0, 0, 0, 0, 0, 0, 0, 0}, db[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  for (int i = 0; i < 8; ++i) {
+    const long long row = row0 + warp * 8 + i;
+    if (row >= p.rows) break;
+    float4* dz4 = reinterpret_cast<float4*>(p.dZ + row * DM);
+    uint2* dz16 = reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(p.dZ16) + row * DM);
+    const bool valid = (int)((row % p.block_rows) % p.group_rows) < p.rows_valid;
+    if (!valid) {
+      const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+      dz4[lane] = zero; dz4[32 + lane] = zero;
+      dz16[lane] = make_uint2(0, 0); dz16[32 + lane] = make_uint2(0, 0);
+      continue;
+    }
+    const float4* dy4 = reinterpret_cast<const float4*>(p.dY + row * DM);
+    const float4* z4 = reinterpret_cast<const float4*>(p.Z + row * DM);
+    const float mu = p.mean[row], rs = p.rstd[row];
+    const float4 da = __ldg(dy4 + lane), dc = __ldg(dy4 + 32 + lane);
+    const float4 za = __ldg(z4 + lane), zc = __ldg(z4 + 32 + lane);
+    float xh[8] = {(za.x - mu) * rs, (za.y - mu) * rs, (za.z - mu) * rs, (za.w - mu) * rs,
+                   (zc.x - mu) * rs, (zc.y - mu) * rs, (zc.z - mu) * rs, (zc.w - mu) * rs};
+    float dy[8] = {da.x, da.y, da.z, da.w, dc.x, dc.y, dc.z, dc.w};
+    float gm[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+    float g[8];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      g[j] = dy[j] * gm[j];
+      s1 += g[j];
+      s2 += g[j] * xh[j];
+      dg[j] += dy[j] * xh[j];
+      db[j] += dy[j];
+    }
+    s1 = warp_sum(s1) * (1.f / DM);
+    s2 = warp_sum(s2) * (1.f / DM);
+    float o[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o[j] = rs * (g[j] - s1 - xh[j] * s2);
+    dz4[lane] = make_float4(o[0], o[1], o[2], o[3]);
+    dz4[32 + lane] = make_float4(o[4], o[5], o[6], o[7]);
+    dz16[lane] = make_uint2(pack2(o[0], o[1], p.dtype), pack2(o[2], o[3], p.dtype));
+    dz16[32 + lane] = make_uint2(pack2(o[4], o[5], p.dtype), pack2(o[6], o[7], p.dtype));
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    red[0][warp][lane * 4 + j] = dg[j]; red[0][warp][128 + lane * 4 + j] = dg[4 + j];
+    red[1][warp][lane * 4 + j] = db[j]; red[1][warp][128 + lane * 4 + j] = db[4 + j];
+  }
+  __syncthreads();
+  const int c = threadIdx.x;
+  float s = 0.f, t = 0.f;
+#pragma unroll
+  for (int w = 0; w < 8; ++w) { s += red[0][w][c]; t += red[1][w][c]; }
+  atomicAdd(p.dgamma + c, s);
+  atomicAdd(p.dbeta + c, t);
+}
+
+// ------------------------------------------------------------------------------------------ combine fwd
+// out[b][c][n] = sum_k w[b*n_k + k] * Y[blk[b*n_k + k]][padrow(n)][c]      (channel-major output)
+struct CombineArgs {
+  const float* Y; const int* blk; const float* w; float* out; void* rows16;  // rows16: optional 16-bit row-major copy [b][rows_pad][256]
+  long long out_b_stride, out_ch_stride;
+  int n_k, n_points, chunk, chunk_pad, rows_pad;
+  int dtype;
+};
+
+__global__ void __launch_bounds__(256) combine_fwd_kernel(const CombineArgs p) {
+  __shared__ float tile[DM][33];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b = blockIdx.y;
+  const int r0 = blockIdx.x * 32;
+  for (int rr = warp; rr < 32; rr += 8) {
+    const int r = r0 + rr;
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f), c = a;
+    for (int k = 0; k < p.n_k; ++k) {
+      const float wk = __ldg(p.w + b * p.n_k + k);
+      const float4* y4 = reinterpret_cast<const float4*>(p.Y + ((long long)__ldg(p.blk + b * p.n_k + k) * p.rows_pad + r) * DM);
+      const float4 ya = __ldg(y4 + lane), yc = __ldg(y4 + 32 + lane);
+      a.x += wk * ya.x; a.y += wk * ya.y; a.z += wk * ya.z; a.w += wk * ya.w;
+      c.x += wk * yc.x; c.y += wk * yc.y; c.z += wk * yc.z; c.w += wk * yc.w;
+    }
+    tile[lane * 4 + 0][rr] = a.x; tile[lane * 4 + 1][rr] = a.y; tile[lane * 4 + 2][rr] = a.z; tile[lane * 4 + 3][rr] = a.w;
+    tile[128 + lane * 4 + 0][rr] = c.x; tile[128 + lane * 4 + 1][rr] = c.y; tile[128 + lane * 4 + 2][rr] = c.z; tile[128 + lane * 4 + 3][rr] = c.w;
+    if (p.rows16) {
+      uint2* o16 = reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(p.rows16) + ((long long)b * p.rows_pad + r) * DM);
+      o16[lane] = make_uint2(pack2(a.x, a.y, p.dtype), pack2(a.z, a.w, p.dtype));
+      o16[32 + lane] = make_uint2(pack2(c.x, c.y, p.dtype), pack2(c.z, c.w, p.dtype));
+    }
+  }
+  __syncthreads();
+  const int ch = r0 / p.chunk_pad, i = r0 % p.chunk_pad + lane;
+  const int n = ch * p.chunk + i;
+  if (i < p.chunk && n < p.n_points) {
+    float* o = p.out + b * p.out_b_stride + n;
+    for (int c = warp; c < DM; c += 8) o[c * p.out_ch_stride] = tile[c][lane];
+  }
+}
+
+// ------------------------------------------------------------------------------------------ combine bwd
+// For every destination block j (one MHA output):
+//   dY[j][row][c] = cw[j] * dOut[cb[j]][c][n(row)]  +  pw[j] * dpool[pb[j]][c]      (valid rows; 0 in pads)
+// and, when cw_index[j] >= 0,  dcomp[cw_index[j]] += sum_{row,c} dOut[cb[j]][c][n] * Y[j][row][c].
+struct CombineBwdArgs {
+  const float* dOut; const float* Y; const float* dpool;
+  const int* cb;        // batch item whose output gradient feeds block j (or -1)
+  const float* cw;      // its compatibility weight
+  const int* cw_index;  // flat index into dcomp (or -1)
+  const int* pb;        // pooled-slot index feeding block j (or -1)
+  float pool_scale;     // 1 / n_points
+  float* dY; float* dcomp;
+  long long out_b_stride, out_ch_stride;
+  int n_points, chunk, chunk_pad, rows_pad;
+};
+
+__global__ void __launch_bounds__(256) combine_bwd_kernel(const CombineBwdArgs p) {
+  __shared__ float tile[DM][33];
+  __shared__ float wred[8];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int j = blockIdx.y;
+  const int r0 = blockIdx.x * 32;
+  const int b = p.cb[j];
+  const int pbj = p.pb[j];
+  const int ch = r0 / p.chunk_pad, i = r0 % p.chunk_pad + lane;
+  const int n = ch * p.chunk + i;
+  const bool lane_valid = i < p.chunk && n < p.n_points;
+  if (b >= 0) {
+    const float* g = p.dOut + b * p.out_b_stride + n;
+    for (int c = warp; c < DM; c += 8) tile[c][lane] = lane_valid ? __ldg(g + c * p.out_ch_stride) : 0.f;
+  }
+  __syncthreads();
+  const float cwj = b >= 0 ? p.cw[j] : 0.f;
+  float4 pa = make_float4(0.f, 0.f, 0.f, 0.f), pc = pa;
+  if (pbj >= 0 && p.dpool != nullptr) {
+    const float4* d4 = reinterpret_cast<const float4*>(p.dpool + (long long)pbj * DM);
+    pa = __ldg(d4 + lane); pc = __ldg(d4 + 32 + lane);
+    pa.x *= p.pool_scale; pa.y *= p.pool_scale; pa.z *= p.pool_scale; pa.w *= p.pool_scale;
+    pc.x *= p.pool_scale; pc.y *= p.pool_scale; pc.z *= p.pool_scale; pc.w *= p.pool_scale;
+  }
+  float dot = 0.f;
+  for (int rr = warp; rr < 32; rr += 8) {
+    const int r = r0 + rr;
+    const int ii = r % p.chunk_pad;
+    const bool valid = ii < p.chunk && (r / p.chunk_pad) * p.chunk + ii < p.n_points;
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f), c = a;
+    if (valid) {
+      a = pa; c = pc;
+      if (b >= 0) {
+        const float4 ga = make_float4(tile[lane * 4 + 0][rr], tile[lane * 4 + 1][rr], tile[lane * 4 + 2][rr], tile[lane * 4 + 3][rr]);
+        const float4 gc = make_float4(tile[128 + lane * 4 + 0][rr], tile[128 + lane * 4 + 1][rr], tile[128 + lane * 4 + 2][rr], tile[128 + lane * 4 + 3][rr]);
+        a.x += cwj * ga.x; a.y += cwj * ga.y; a.z += cwj * ga.z; a.w += cwj * ga.w;
+        c.x += cwj * gc.x; c.y += cwj * gc.y; c.z += cwj * gc.z; c.w += cwj * gc.w;
+        if (p.dcomp) {
+        const float4* y4 = reinterpret_cast<const float4*>(p.Y + ((long long)j * p.rows_pad + r) * DM);
+        const float4 ya = __ldg(y4 + lane), yc = __ldg(y4 + 32 + lane);
+        dot += ga.x * ya.x + ga.y * ya.y + ga.z * ya.z + ga.w * ya.w + gc.x * yc.x + gc.y * yc.y + gc.z * yc.z + gc.w * yc.w;
+        }
+      }
+    }
+    if (p.dY) {
+      float4* d4 = reinterpret_cast<float4*>(p.dY + ((long long)j * p.rows_pad + r) * DM);
+      d4[lane] = a; d4[32 + lane] = c;
+    }
+  }
+  if (p.dcomp && b >= 0 && p.cw_index[j] >= 0) {
+    dot = warp_sum(dot);
+    if (lane == 0) wred[warp] = dot;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float s = 0.f;
+      for (int w = 0; w < 8; ++w) s += wred[w];
+      atomicAdd(p.dcomp + p.cw_index[j], s);
+    }
+  }
+}
+
+template <typename K, typename A>
+static int launch_simple(K kern, dim3 grid, dim3 block, const A& args, void* stream, const char* name) {
+  kern<<<grid, block, 0, (cudaStream_t)stream>>>(args);
+  CSN_LAUNCH_OK(name);
+  return 0;
+}
+
+}  // namespace csn
+
+extern "C" {
+
+int csn_pack_rows(const float* src, void* dst16, float* dst32, int64_t ch_stride, int32_t n0, int64_t src_s0,
+                  int32_t n1, int64_t src_s1, int64_t dst_slot0, int64_t dst_s0, int64_t dst_s1,
+                  int32_t n_points, int32_t chunk, int32_t chunk_pad, int32_t rows_pad, int32_t dtype,
+                  void* stream) {
+  using namespace csn;
+  clear_error();
+  CSN_CHECK_ARG(src && dst16, "csn_pack_rows: null pointer");
+  CSN_CHECK_ARG(chunk_pad % 32 == 0 && rows_pad % chunk_pad == 0 && chunk <= chunk_pad, "csn_pack_rows: bad padding (chunk=%d chunk_pad=%d rows_pad=%d)", chunk, chunk_pad, rows_pad);
+  CSN_CHECK_ARG(dtype == CSN_F16 || dtype == CSN_BF16, "csn_pack_rows: 16-bit destination only");
+  if (n0 * n1 == 0) return 0;
+  PackArgs a{src, dst16, dst32, ch_stride, src_s0, src_s1, dst_slot0, dst_s0, dst_s1, n0, n1, n_points, chunk, chunk_pad, rows_pad, dtype};
+  return launch_simple(pack_kernel, dim3(rows_pad / 32, n0 * n1), dim3(256), a, stream, "pack_kernel");
+}
+
+int csn_softmax_fwd(const float* S, void* P, int64_t rows, int32_t cols_pad, int32_t cols_valid,
+                    int32_t group_rows, int32_t rows_valid, int32_t dtype, void* stream) {
+  using namespace csn;
+  clear_error();
+  CSN_CHECK_ARG(S && P, "csn_softmax_fwd: null pointer");
+  CSN_CHECK_ARG(cols_pad % 8 == 0 && cols_valid <= cols_pad && cols_valid > 0, "csn_softmax_fwd: bad widths %d/%d", cols_valid, cols_pad);
+  if (rows == 0) return 0;
+  const int wpb = 8;
+  const unsigned grid = (unsigned)((rows + wpb - 1) / wpb);
+  cudaStream_t s = (cudaStream_t)stream;
+  if (cols_pad == 512) softmax_fwd_kernel<4><<<grid, wpb * 32, 0, s>>>(S, P, rows, cols_valid, group_rows, rows_valid, dtype);
+  else if (cols_pad == 256) softmax_fwd_kernel<2><<<grid, wpb * 32, 0, s>>>(S, P, rows, cols_valid, group_rows, rows_valid, dtype);
+  else if (cols_pad == 128) softmax_fwd_kernel<1><<<grid, wpb * 32, 0, s>>>(S, P, rows, cols_valid, group_rows, rows_valid, dtype);
+  else softmax_fwd_wide_kernel<<<grid, wpb * 32, 0, s>>>(S, P, rows, cols_pad, cols_valid, group_rows, rows_valid, dtype);
+  CSN_LAUNCH_OK("softmax_fwd_kernel");
+  return 0;
+}
+
+int csn_softmax_bwd(const void* P, const float* dP, void* dS, int64_t rows, int32_t cols_pad, int32_t cols_valid,
+                    int32_t group_rows, int32_t rows_valid, float scale, int32_t dtype, void* stream) {
+  using namespace csn;
+  clear_error();
+  CSN_CHECK_ARG(P && dP && dS, "csn_softmax_bwd: null pointer");
+  CSN_CHECK_ARG(cols_pad % 8 == 0 && cols_valid <= cols_pad, "csn_softmax_bwd: bad widths");
+  if (rows == 0) return 0;
+  const int wpb = 8;
+  softmax_bwd_kernel<<<(unsigned)((rows + wpb - 1) / wpb), wpb * 32, 0, (cudaStream_t)stream>>>(P, dP, dS, rows, cols_pad, cols_valid, group_rows, rows_valid, scale, dtype);
+  CSN_LAUNCH_OK("softmax_bwd_kernel");
+  return 0;
+}
+
+int csn_add_ln_fwd(float* Z, const float* R, const int32_t* res_block, float* Y, void* Y16, float* mean, float* rstd,
+                   const float* gamma, const float* beta, float* colsum, int64_t rows, int32_t block_rows,
+                   int32_t group_rows, int32_t rows_valid, float eps, int32_t dtype, void* stream) {
+  using namespace csn;
+  clear_error();
+  CSN_CHECK_ARG(Z && R && Y && mean && rstd && gamma && beta, "csn_add_ln_fwd: null pointer");
+  CSN_CHECK_ARG(block_rows % 64 == 0 && rows % 64 == 0, "csn_add_ln_fwd: rows (%lld) and block_rows (%d) must be multiples of 64", (long long)rows, block_rows);
+  if (rows == 0) return 0;
+  AddLnArgs a{Z, R, res_block, Y, Y16, mean, rstd, gamma, beta, colsum, rows, block_rows, group_rows, rows_valid, eps, dtype};
+  return launch_simple(add_ln_fwd_kernel, dim3((unsigned)(rows / 64)), dim3(256), a, stream, "add_ln_fwd_kernel");
+}
+
+int csn_ln_bwd(const float* dY, const float* Z, const float* mean, const float* rstd, const float* gamma, float* dZ,
+               void* dZ16, float* dgamma, float* dbeta, int64_t rows, int32_t block_rows, int32_t group_rows,
+               int32_t rows_valid, int32_t dtype, void* stream) {
+  using namespace csn;
+  clear_error();
+  CSN_CHECK_ARG(dY && Z && mean && rstd && gamma && dZ && dZ16 && dgamma && dbeta, "csn_ln_bwd: null pointer");
+  CSN_CHECK_ARG(rows % 64 == 0, "csn_ln_bwd: rows must be a multiple of 64");
+  if (rows == 0) return 0;
+  LnBwdArgs a{dY, Z, mean, rstd, gamma, dZ, dZ16, dgamma, dbeta, rows, group_rows, rows_valid, block_rows, dtype};
+  return launch_simple(ln_bwd_kernel, dim3((unsigned)(rows / 64)), dim3(256), a, stream, "ln_bwd_kernel");
+}
+
+int csn_combine_fwd(const float* Y, const int32_t* blk, const float* w, float* out, void* rows16, int32_t n_b,
+                    int32_t n_k, int64_t out_b_stride, int64_t out_ch_stride, int32_t n_points, int32_t chunk,
+                    int32_t chunk_pad, int32_t rows_pad, int32_t dtype, void* stream) {
+  using namespace csn;
+  clear_error();
+  CSN_CHECK_ARG(Y && blk && w && out, "csn_combine_fwd: null pointer");
+  CSN_CHECK_ARG(chunk_pad % 32 == 0 && rows_pad % chunk_pad == 0, "csn_combine_fwd: bad padding");
+  if (n_b == 0) return 0;
+  CombineArgs a{Y, blk, w, out, rows16, out_b_stride, out_ch_stride, n_k, n_points, chunk, chunk_pad, rows_pad, dtype};
+  return launch_simple(combine_fwd_kernel, dim3(rows_pad / 32, n_b), dim3(256), a, stream, "combine_fwd_kernel");
+}
+
+int csn_combine_bwd(const float* dOut, const float* Y, const float* dpool, const int32_t* cb, const float* cw,
+                    const int32_t* cw_index, const int32_t* pb, float pool_scale, float* dY, float* dcomp,
+                    int32_t n_blocks, int64_t out_b_stride, int64_t out_ch_stride, int32_t n_points, int32_t chunk,
+                    int32_t chunk_pad, int32_t rows_pad, void* stream) {
+  using namespace csn;
+  clear_error();
+  CSN_CHECK_ARG(dOut && Y && cb && cw && cw_index && pb && (dY || dcomp), "csn_combine_bwd: null pointer");
+  if (n_blocks == 0) return 0;
+  CombineBwdArgs a{dOut, Y, dpool, cb, cw, cw_index, pb, pool_scale, dY, dcomp, out_b_stride, out_ch_stride, n_points, chunk, chunk_pad, rows_pad};
+  return launch_simple(combine_bwd_kernel, dim3(rows_pad / 32, n_blocks), dim3(256), a, stream, "combine_bwd_kernel");
+}
+
+}  // extern "C"

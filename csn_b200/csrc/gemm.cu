@@ -24,13 +24,13 @@ constexpr int GEMM_THREADS = 256;
 
 struct GemmArgs {
   int M, N, K;
-  int nb0, nb1, nb2;
+  int nb0, nb1, nb2, nb3;
   int tiles_m, tiles_n, split_k, kb_per_split, kb_total;
   long long total_tiles;
-  long long a_mn_off[3], a_k_off[3], b_mn_off[3], b_k_off[3];
+  long long a_mn_off[4], a_k_off[4], b_mn_off[4], b_k_off[4];
   void* D;
   long long ldd;
-  long long d_off[3];
+  long long d_off[4];
   int out_dtype, transposed, accumulate, vec_ok;
   float alpha;
   uint32_t idesc;
@@ -48,7 +48,7 @@ struct GemmCfg {
 };
 
 struct TileCoord {
-  int b0, b1, b2, mt, nt, ks;
+  int b0, b1, b2, b3, mt, nt, ks;
 };
 
 __device__ __forceinline__ TileCoord decode_tile(long long t, const GemmArgs& p) {
@@ -62,7 +62,9 @@ __device__ __forceinline__ TileCoord decode_tile(long long t, const GemmArgs& p)
   c.b0 = (int)(t % p.nb0);
   t /= p.nb0;
   c.b1 = (int)(t % p.nb1);
-  c.b2 = (int)(t / p.nb1);
+  t /= p.nb1;
+  c.b2 = (int)(t % p.nb2);
+  c.b3 = (int)(t / p.nb2);
   return c;
 }
 
@@ -183,10 +185,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       uint32_t ph = 0;
       for (long long t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
         const TileCoord c = decode_tile(t, p);
-        const long long a_mn = c.b0 * p.a_mn_off[0] + c.b1 * p.a_mn_off[1] + c.b2 * p.a_mn_off[2] + (long long)c.mt * GEMM_BM;
-        const long long b_mn = c.b0 * p.b_mn_off[0] + c.b1 * p.b_mn_off[1] + c.b2 * p.b_mn_off[2] + (long long)c.nt * BN;
-        const long long a_k0 = c.b0 * p.a_k_off[0] + c.b1 * p.a_k_off[1] + c.b2 * p.a_k_off[2];
-        const long long b_k0 = c.b0 * p.b_k_off[0] + c.b1 * p.b_k_off[1] + c.b2 * p.b_k_off[2];
+        const long long a_mn = c.b0 * p.a_mn_off[0] + c.b1 * p.a_mn_off[1] + c.b2 * p.a_mn_off[2] + c.b3 * p.a_mn_off[3] + (long long)c.mt * GEMM_BM;
+        const long long b_mn = c.b0 * p.b_mn_off[0] + c.b1 * p.b_mn_off[1] + c.b2 * p.b_mn_off[2] + c.b3 * p.b_mn_off[3] + (long long)c.nt * BN;
+        const long long a_k0 = c.b0 * p.a_k_off[0] + c.b1 * p.a_k_off[1] + c.b2 * p.a_k_off[2] + c.b3 * p.a_k_off[3];
+        const long long b_k0 = c.b0 * p.b_k_off[0] + c.b1 * p.b_k_off[1] + c.b2 * p.b_k_off[2] + c.b3 * p.b_k_off[3];
         const int kb0 = c.ks * p.kb_per_split;
         const int kb1 = min(p.kb_total, kb0 + p.kb_per_split);
         for (int kb = kb0; kb < kb1; ++kb) {
@@ -263,7 +265,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       tc_fence_after();
       const int row = c.mt * GEMM_BM + q * 32 + lane;
       const int n0 = c.nt * BN;
-      const long long base = c.b0 * p.d_off[0] + c.b1 * p.d_off[1] + c.b2 * p.d_off[2];
+      const long long base = c.b0 * p.d_off[0] + c.b1 * p.d_off[1] + c.b2 * p.d_off[2] + c.b3 * p.d_off[3];
       const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + acc * BN;
 #pragma unroll 1
       for (int cc = 0; cc < BN; cc += 32) {
@@ -320,14 +322,14 @@ static int dispatch_major(bool a_mn, bool b_mn, const CUtensorMap& tmA, const CU
 }  // namespace csn
 
 extern "C" int csn_gemm(const csn_mat* A, const csn_mat* B, const csn_out* D, int32_t M, int32_t N,
-                        int32_t K, const int32_t nb[3], float alpha, int32_t split_k, void* stream) {
+                        int32_t K, const int32_t nb[4], float alpha, int32_t split_k, void* stream) {
   using namespace csn;
   clear_error();
   CSN_CHECK_ARG(A && B && D && nb, "csn_gemm: null argument");
   CSN_CHECK_ARG(M > 0 && N > 0 && K > 0, "csn_gemm: empty problem M=%d N=%d K=%d", M, N, K);
   CSN_CHECK_ARG(A->dtype == B->dtype, "csn_gemm: operand dtypes differ");
   CSN_CHECK_ARG(A->dtype == CSN_F16 || A->dtype == CSN_BF16, "csn_gemm: operands must be f16/bf16");
-  CSN_CHECK_ARG(nb[0] > 0 && nb[1] > 0 && nb[2] > 0, "csn_gemm: batch extents must be >= 1");
+  CSN_CHECK_ARG(nb[0] > 0 && nb[1] > 0 && nb[2] > 0 && nb[3] > 0, "csn_gemm: batch extents must be >= 1");
   CSN_CHECK_ARG(split_k >= 1, "csn_gemm: split_k must be >= 1");
   CSN_CHECK_ARG(split_k == 1 || D->accumulate, "csn_gemm: split_k > 1 requires accumulate");
   CSN_CHECK_ARG(!D->accumulate || D->dtype == CSN_F32, "csn_gemm: accumulate requires fp32 output");
@@ -348,15 +350,15 @@ extern "C" int csn_gemm(const csn_mat* A, const csn_mat* B, const csn_out* D, in
   GemmArgs g;
   memset(&g, 0, sizeof(g));
   g.M = M; g.N = N; g.K = K;
-  g.nb0 = nb[0]; g.nb1 = nb[1]; g.nb2 = nb[2];
+  g.nb0 = nb[0]; g.nb1 = nb[1]; g.nb2 = nb[2]; g.nb3 = nb[3];
   g.tiles_m = (M + GEMM_BM - 1) / GEMM_BM;
   g.tiles_n = (N + BN - 1) / BN;
   g.kb_total = (K + GEMM_BK - 1) / GEMM_BK;
   g.split_k = split_k > g.kb_total ? g.kb_total : split_k;
   g.kb_per_split = (g.kb_total + g.split_k - 1) / g.split_k;
   g.split_k = (g.kb_total + g.kb_per_split - 1) / g.kb_per_split;  // no empty splits
-  g.total_tiles = (long long)g.nb0 * g.nb1 * g.nb2 * g.tiles_m * g.tiles_n * g.split_k;
-  for (int i = 0; i < 3; ++i) {
+  g.total_tiles = (long long)g.nb0 * g.nb1 * g.nb2 * g.nb3 * g.tiles_m * g.tiles_n * g.split_k;
+  for (int i = 0; i < 4; ++i) {
     g.a_mn_off[i] = A->mn_off[i]; g.a_k_off[i] = A->k_off[i];
     g.b_mn_off[i] = B->mn_off[i]; g.b_k_off[i] = B->k_off[i];
     g.d_off[i] = D->off[i];
@@ -365,7 +367,7 @@ extern "C" int csn_gemm(const csn_mat* A, const csn_mat* B, const csn_out* D, in
   g.accumulate = D->accumulate; g.alpha = alpha;
   const int esz = D->dtype == CSN_F32 ? 4 : 2;
   bool vec = ((reinterpret_cast<uintptr_t>(D->ptr) & 15) == 0) && ((D->ld * esz) % 16 == 0);
-  for (int i = 0; i < 3; ++i) vec = vec && ((D->off[i] * esz) % 16 == 0);
+  for (int i = 0; i < 4; ++i) vec = vec && ((D->off[i] * esz) % 16 == 0);
   g.vec_ok = vec ? 1 : 0;
   g.idesc = umma_idesc_f16(A->dtype == CSN_F16 ? 0u : 1u, a_mn ? 1u : 0u, b_mn ? 1u : 0u, (uint32_t)BN);
 

@@ -1,0 +1,254 @@
+"""Kernel orchestration for block attention (host side, no arithmetic).
+
+An *attention block* is one independent MHA problem: the rows of a query shape attending to the rows
+of a key/value shape, restricted chunk-by-chunk (MID-FC: 20 chunks of 500 points,
+MID-FC/csa_models.py:83-90).  Shapes live in *slots* of padded row-major buffers
+(slot s = rows [s*NP, (s+1)*NP) ); blocks are organised in regular *groups* so that one strided
+batched launch covers a whole group.  Every contraction goes through csn_gemm (tcgen05), everything
+else through the kernels of csrc/elementwise.cu; this file only computes strides.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass, field
+
+import torch
+
+from . import _lib as L
+
+
+@dataclass(frozen=True)
+class Geometry:
+    """Chunked, padded row layout of one shape."""
+    chunk: int = 500       # points per attention chunk (mini_bs, csa_models.py:84)
+    n_chunks: int = 20     # iters (csa_models.py:83)
+    chunk_pad: int = 512   # rows reserved per chunk (multiple of 128)
+
+    @property
+    def n_points(self) -> int:
+        return self.chunk * self.n_chunks
+
+    @property
+    def rows_pad(self) -> int:
+        return self.chunk_pad * self.n_chunks
+
+
+@dataclass(frozen=True)
+class Group:
+    """n_out x n_in blocks; block (o, i) has index blk0 + o*n_in + i, query slot q0 + o*q_so + i*q_si,
+    key slot k0 + o*k_so + i*k_si, value slot v0 + o*v_so + i*v_si."""
+    n_in: int
+    n_out: int
+    blk0: int
+    q0: int
+    q_si: int
+    q_so: int
+    k0: int
+    k_si: int
+    k_so: int
+    v0: int
+    v_si: int
+    v_so: int
+
+    def blocks(self):
+        for o in range(self.n_out):
+            for i in range(self.n_in):
+                yield (self.blk0 + o * self.n_in + i, self.q0 + o * self.q_so + i * self.q_si,
+                       self.k0 + o * self.k_so + i * self.k_si, self.v0 + o * self.v_so + i * self.v_si)
+
+
+def _launch_pack(src: torch.Tensor, dst16, dst32, n0, s0, n1, s1, slot0, d0, d1, geom: Geometry, n_src_points):
+    """src: fp32 view whose element (i0,i1,c,n) sits at i0*s0 + i1*s1 + c*n_src_points + n."""
+    rc = L.lib().csn_pack_rows(src.data_ptr(), dst16.data_ptr(), dst32.data_ptr() if dst32 is not None else None,
+                               n_src_points, n0, s0, n1, s1, slot0, d0, d1, geom.n_points, geom.chunk,
+                               geom.chunk_pad, geom.rows_pad, L.dtype_code(dst16.dtype), L.stream_ptr())
+    L.check(rc, "csn_pack_rows")
+
+
+@dataclass
+class AttnContext:
+    """Everything the backward pass needs from the forward pass of a set of blocks."""
+    geom: Geometry
+    n_head: int
+    d_head: int
+    groups: list
+    n_slots: int
+    n_blocks: int
+    Xh: torch.Tensor = None      # [S*NP, 256] 16-bit
+    Xf: torch.Tensor = None      # [S*NP, 256] fp32
+    QKV: torch.Tensor = None     # [S*NP, 3*h*d] 16-bit
+    P: torch.Tensor = None       # [blocks*n_chunks*h*CP, CP] 16-bit probabilities
+    O: torch.Tensor = None       # [blocks*NP, h*d] 16-bit
+    Z: torch.Tensor = None       # [blocks*NP, 256] fp32 pre-LayerNorm
+    Y: torch.Tensor = None       # [blocks*NP, 256] fp32 LayerNorm output
+    mean: torch.Tensor = None
+    rstd: torch.Tensor = None
+    colsum: torch.Tensor = None  # [blocks, 256] sum of Y over valid rows
+    Wqkv16: torch.Tensor = None
+    Wo16: torch.Tensor = None
+    gamma: torch.Tensor = None
+    res_block: torch.Tensor = None
+    extra: dict = field(default_factory=dict)
+
+
+def attention_forward(Xh, Xf, groups, n_slots, n_blocks, w_q, w_k, w_v, w_o, gamma, beta, geom: Geometry,
+                      n_head: int, want_colsum: bool = True) -> AttnContext:
+    """Forward of all blocks. Xh/Xf: packed slots [S*NP, 256] (16-bit / fp32)."""
+    dev, dt = Xh.device, Xh.dtype
+    NP, CP, NC = geom.rows_pad, geom.chunk_pad, geom.n_chunks
+    HD = w_q.shape[0]
+    d = HD // n_head
+    ctx = AttnContext(geom, n_head, d, list(groups), n_slots, n_blocks, Xh=Xh, Xf=Xf)
+    ctx.Wqkv16 = torch.cat([w_q, w_k, w_v], dim=0).to(dt).contiguous()  # [3HD, 256]
+    ctx.Wo16 = w_o.to(dt).contiguous()                                   # [256, HD]
+    ctx.gamma = gamma
+    # --- projections: one GEMM for Q, K and V of every slot (csa_models.py:103-105, de-duplicated)
+    QKV = torch.empty(n_slots * NP, 3 * HD, dtype=dt, device=dev)
+    L.gemm(L.mat(Xh, L.MAJOR_K), L.mat(ctx.Wqkv16, L.MAJOR_K), L.out(QKV, 3 * HD), n_slots * NP, 3 * HD, 256)
+    ctx.QKV = QKV
+    Qv, Kv, Vv = QKV[:, :HD], QKV[:, HD:2 * HD], QKV[:, 2 * HD:]
+    # --- scores S = (Q K^T)/sqrt(d) per (block, chunk, head) -> fp32 (csa_models.py:139)
+    Sbuf = torch.empty(n_blocks * NC * n_head * CP, CP, dtype=torch.float32, device=dev)
+    blk_sz = NC * n_head * CP * CP
+    for g in groups:
+        A = L.mat(Qv[g.q0 * NP:], L.MAJOR_K, mn_off=(0, CP, g.q_si * NP, g.q_so * NP), k_off=(d, 0, 0, 0))
+        B = L.mat(Kv[g.k0 * NP:], L.MAJOR_K, mn_off=(0, CP, g.k_si * NP, g.k_so * NP), k_off=(d, 0, 0, 0))
+        D = L.out(Sbuf[g.blk0 * NC * n_head * CP:], CP, off=(CP * CP, n_head * CP * CP, blk_sz, g.n_in * blk_sz))
+        L.gemm(A, B, D, CP, CP, d, nb=(n_head, NC, g.n_in, g.n_out), alpha=1.0 / math.sqrt(d))
+    # --- softmax over the 500 valid keys of each chunk (csa_models.py:141, dropout = identity in eval)
+    P = torch.empty(n_blocks * NC * n_head * CP, CP, dtype=dt, device=dev)
+    rc = L.lib().csn_softmax_fwd(Sbuf.data_ptr(), P.data_ptr(), Sbuf.shape[0], CP, geom.chunk, CP, geom.chunk,
+                                 L.dtype_code(dt), L.stream_ptr())
+    L.check(rc, "csn_softmax_fwd")
+    ctx.P = P
+    ctx.extra["Sbuf"] = Sbuf  # scratch, reused for dP in backward
+    # --- O = P V  (csa_models.py:142); V consumed MN-major straight from the projection output
+    O = torch.empty(n_blocks * NP, HD, dtype=dt, device=dev)
+    prow = NC * n_head * CP  # rows of P per block
+    for g in groups:
+        A = L.mat(P[g.blk0 * prow:], L.MAJOR_K, mn_off=(CP, n_head * CP, prow, g.n_in * prow))
+        B = L.mat(Vv[g.v0 * NP:], L.MAJOR_MN, mn_off=(d, 0, 0, 0), k_off=(0, CP, g.v_si * NP, g.v_so * NP))
+        D = L.out(O[g.blk0 * NP:], HD, off=(d, CP * HD, NP * HD, g.n_in * NP * HD))
+        L.gemm(A, B, D, CP, d, CP, nb=(n_head, NC, g.n_in, g.n_out))
+    ctx.O = O
+    # --- output projection (csa_models.py:115), residual + LayerNorm (:116-118), pooled column sums
+    Z = torch.empty(n_blocks * NP, 256, dtype=torch.float32, device=dev)
+    L.gemm(L.mat(O, L.MAJOR_K), L.mat(ctx.Wo16, L.MAJOR_K), L.out(Z, 256), n_blocks * NP, 256, HD)
+    res = torch.empty(n_blocks, dtype=torch.int32)
+    for g in groups:
+        for (j, qs, _, _) in g.blocks():
+            res[j] = qs
+    ctx.res_block = res.to(dev)
+    Y = torch.empty_like(Z)
+    ctx.mean = torch.empty(n_blocks * NP, dtype=torch.float32, device=dev)
+    ctx.rstd = torch.empty_like(ctx.mean)
+    ctx.colsum = torch.zeros(n_blocks, 256, dtype=torch.float32, device=dev) if want_colsum else None
+    rc = L.lib().csn_add_ln_fwd(Z.data_ptr(), Xf.data_ptr(), ctx.res_block.data_ptr(), Y.data_ptr(), None,
+                                ctx.mean.data_ptr(), ctx.rstd.data_ptr(), gamma.data_ptr(), beta.data_ptr(),
+                                ctx.colsum.data_ptr() if want_colsum else None, n_blocks * NP, NP, CP, geom.chunk,
+                                1e-6, L.dtype_code(dt), L.stream_ptr())
+    L.check(rc, "csn_add_ln_fwd")
+    ctx.Z, ctx.Y = Z, Y
+    return ctx
+
+
+def attention_backward(ctx: AttnContext, dY: torch.Tensor, need_dx: bool):
+    """Backward of attention_forward. dY: [blocks*NP, 256] fp32 (zero in pad rows).
+    Returns dict with dWq, dWk, dWv, dWo (fp32, reference layouts), dgamma, dbeta and, if need_dx,
+    dX [S*NP, 256] fp32 (padded row-major, gradient w.r.t. every slot's features)."""
+    geom, h, d = ctx.geom, ctx.n_head, ctx.d_head
+    NP, CP, NC = geom.rows_pad, geom.chunk_pad, geom.n_chunks
+    HD = h * d
+    dev, dt = ctx.Xh.device, ctx.Xh.dtype
+    nblk, S = ctx.n_blocks, ctx.n_slots
+    lib = L.lib()
+    # --- dynamic range: the backward pass is linear in dY, so it is run on s*dY with s a power of two
+    #     chosen on the device (no host sync) such that max|s*dY| = 64..128; 16-bit intermediates
+    #     (dZ, dO, dS, dQ|dK|dV) then sit in the normal range of fp16 instead of its subnormals.
+    amax = dY.abs().max().clamp_min(1e-30)
+    scale = torch.exp2(torch.floor(torch.log2(128.0 / amax)))
+    dY = dY * scale
+    inv_scale = 1.0 / scale
+    # --- LayerNorm backward
+    dZ = torch.empty_like(ctx.Z)
+    dZ16 = torch.empty(nblk * NP, 256, dtype=dt, device=dev)
+    dgamma = torch.zeros(256, dtype=torch.float32, device=dev)
+    dbeta = torch.zeros(256, dtype=torch.float32, device=dev)
+    rc = lib.csn_ln_bwd(dY.data_ptr(), ctx.Z.data_ptr(), ctx.mean.data_ptr(), ctx.rstd.data_ptr(),
+                        ctx.gamma.data_ptr(), dZ.data_ptr(), dZ16.data_ptr(), dgamma.data_ptr(), dbeta.data_ptr(),
+                        nblk * NP, NP, CP, geom.chunk, L.dtype_code(dt), L.stream_ptr())
+    L.check(rc, "csn_ln_bwd")
+    split = max(1, min(64, (nblk * NP) // 4096))
+    # --- dWo = dZ^T O  (contraction over all rows; both operands consumed MN-major)
+    dWo = torch.zeros(256, HD, dtype=torch.float32, device=dev)
+    L.gemm(L.mat(dZ16, L.MAJOR_MN), L.mat(ctx.O, L.MAJOR_MN), L.out(dWo, HD, accumulate=True), 256, HD, nblk * NP,
+           split_k=split)
+    # --- dO = dZ Wo
+    dO = torch.empty(nblk * NP, HD, dtype=dt, device=dev)
+    L.gemm(L.mat(dZ16, L.MAJOR_K), L.mat(ctx.Wo16, L.MAJOR_MN), L.out(dO, HD), nblk * NP, HD, 256)
+    Qv, Kv, Vv = ctx.QKV[:, :HD], ctx.QKV[:, HD:2 * HD], ctx.QKV[:, 2 * HD:]
+    # --- dP = dO V^T per (block, chunk, head)
+    dP = ctx.extra["Sbuf"]
+    blk_sz = NC * h * CP * CP
+    prow = NC * h * CP
+    for g in ctx.groups:
+        A = L.mat(dO[g.blk0 * NP:], L.MAJOR_K, mn_off=(0, CP, NP, g.n_in * NP), k_off=(d, 0, 0, 0))
+        B = L.mat(Vv[g.v0 * NP:], L.MAJOR_K, mn_off=(0, CP, g.v_si * NP, g.v_so * NP), k_off=(d, 0, 0, 0))
+        D = L.out(dP[g.blk0 * prow:], CP, off=(CP * CP, h * CP * CP, blk_sz, g.n_in * blk_sz))
+        L.gemm(A, B, D, CP, CP, d, nb=(h, NC, g.n_in, g.n_out))
+    # --- dS = P o (dP - rowsum(P o dP)) / sqrt(d)
+    dS = torch.empty_like(ctx.P)
+    rc = lib.csn_softmax_bwd(ctx.P.data_ptr(), dP.data_ptr(), dS.data_ptr(), dP.shape[0], CP, geom.chunk, CP,
+                             geom.chunk, 1.0 / math.sqrt(d), L.dtype_code(dt), L.stream_ptr())
+    L.check(rc, "csn_softmax_bwd")
+    # --- per-block dQ | dK | dV  (stored per block: several blocks may share a slot)
+    dQKV = torch.empty(nblk * NP, 3 * HD, dtype=dt, device=dev)
+    dQv, dKv, dVv = dQKV[:, :HD], dQKV[:, HD:2 * HD], dQKV[:, 2 * HD:]
+    for g in ctx.groups:
+        nb = (h, NC, g.n_in, g.n_out)
+        Pk = L.mat(ctx.P[g.blk0 * prow:], L.MAJOR_MN, k_off=(CP, h * CP, prow, g.n_in * prow))        # P^T
+        dSk = L.mat(dS[g.blk0 * prow:], L.MAJOR_K, mn_off=(CP, h * CP, prow, g.n_in * prow))
+        dSt = L.mat(dS[g.blk0 * prow:], L.MAJOR_MN, k_off=(CP, h * CP, prow, g.n_in * prow))          # dS^T
+        dOm = L.mat(dO[g.blk0 * NP:], L.MAJOR_MN, mn_off=(d, 0, 0, 0), k_off=(0, CP, NP, g.n_in * NP))
+        Km = L.mat(Kv[g.k0 * NP:], L.MAJOR_MN, mn_off=(d, 0, 0, 0), k_off=(0, CP, g.k_si * NP, g.k_so * NP))
+        Qm = L.mat(Qv[g.q0 * NP:], L.MAJOR_MN, mn_off=(d, 0, 0, 0), k_off=(0, CP, g.q_si * NP, g.q_so * NP))
+        off = (d, CP * 3 * HD, NP * 3 * HD, g.n_in * NP * 3 * HD)
+        L.gemm(Pk, dOm, L.out(dVv[g.blk0 * NP:], 3 * HD, off=off), CP, d, CP, nb=nb)    # dV = P^T dO
+        L.gemm(dSk, Km, L.out(dQv[g.blk0 * NP:], 3 * HD, off=off), CP, d, CP, nb=nb)    # dQ = dS K
+        L.gemm(dSt, Qm, L.out(dKv[g.blk0 * NP:], 3 * HD, off=off), CP, d, CP, nb=nb)    # dK = dS^T Q
+    # --- projection weight gradients: dW = sum_blocks dProj^T X[slot]
+    dWqkv = torch.zeros(3 * HD, 256, dtype=torch.float32, device=dev)
+    Xh = ctx.Xh
+    for g in ctx.groups:
+        nb = (g.n_in, g.n_out, 1, 1)
+        ksp = max(1, min(16, NP // 1024))
+        A = L.mat(dQv[g.blk0 * NP:], L.MAJOR_MN, k_off=(NP, g.n_in * NP))
+        B = L.mat(Xh[g.q0 * NP:], L.MAJOR_MN, k_off=(g.q_si * NP, g.q_so * NP))
+        L.gemm(A, B, L.out(dWqkv[:HD], 256, accumulate=True), HD, 256, NP, nb=nb, split_k=ksp)
+        A = L.mat(dKv[g.blk0 * NP:], L.MAJOR_MN, k_off=(NP, g.n_in * NP))
+        B = L.mat(Xh[g.k0 * NP:], L.MAJOR_MN, k_off=(g.k_si * NP, g.k_so * NP))
+        L.gemm(A, B, L.out(dWqkv[HD:2 * HD], 256, accumulate=True), HD, 256, NP, nb=nb, split_k=ksp)
+        A = L.mat(dVv[g.blk0 * NP:], L.MAJOR_MN, k_off=(NP, g.n_in * NP))
+        B = L.mat(Xh[g.v0 * NP:], L.MAJOR_MN, k_off=(g.v_si * NP, g.v_so * NP))
+        L.gemm(A, B, L.out(dWqkv[2 * HD:], 256, accumulate=True), HD, 256, NP, nb=nb, split_k=ksp)
+    grads = {"dWq": dWqkv[:HD], "dWk": dWqkv[HD:2 * HD], "dWv": dWqkv[2 * HD:], "dWo": dWo,
+             "dgamma": dgamma, "dbeta": dbeta}
+    if need_dx:
+        dX = torch.zeros(S * NP, 256, dtype=torch.float32, device=dev)
+        Wq16, Wk16, Wv16 = ctx.Wqkv16[:HD], ctx.Wqkv16[HD:2 * HD], ctx.Wqkv16[2 * HD:]
+        for g in ctx.groups:
+            nb = (g.n_in, g.n_out, 1, 1)
+            for (dproj, W16, s0, si, so) in ((dQv, Wq16, g.q0, g.q_si, g.q_so), (dKv, Wk16, g.k0, g.k_si, g.k_so),
+                                             (dVv, Wv16, g.v0, g.v_si, g.v_so)):
+                A = L.mat(dproj[g.blk0 * NP:], L.MAJOR_K, mn_off=(NP, g.n_in * NP))
+                B = L.mat(W16, L.MAJOR_MN)
+                D = L.out(dX[s0 * NP:], 256, off=(si * NP * 256, so * NP * 256), accumulate=True)
+                L.gemm(A, B, D, NP, 256, HD, nb=nb)
+        # residual path: dX[q slot] += dZ[block]
+        dX3 = dX.view(S, NP, 256)
+        dZ3 = dZ.view(nblk, NP, 256)
+        dX3.index_add_(0, ctx.res_block.long(), dZ3)
+        grads["dX"] = dX
+    for t in grads.values():
+        t.mul_(inv_scale)
+    return grads

@@ -1,0 +1,499 @@
+"""Drop-in module surface of MID-FC/csa_models.py backed by the sm_100a kernels.
+
+Same class names, constructor signatures, state_dict keys, argument meaning and return shapes as the
+reference (MID-FC/csa_models.py:37-432; contract in SURVEY.md §8b):
+    MultiHeadAttention, ScaledDotProductAttention, CrossShapeAt, get_model
+Tensors in/out are fp32 in the reference layouts (channel-major (B,256,N,1) features); the
+contractions run on tcgen05 tensor cores with 16-bit operands and fp32 accumulation
+(`precision='fp16'`: 11-bit mantissa like TF32, default; `'bf16'`: the wide-range variant).
+There is no fallback: without a CUDA device or without libcsn_b200.so every call raises.
+
+Deviations from the reference, all documented in DESIGN.md:
+  * dropout (csa_models.py:56,136) is not applied: results are those of `model.eval()`;
+  * projections of a shape are computed once per step instead of once per attention call, and the
+    duplicate self-attention call of get_csa_feats (:210 vs :232) is computed once.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import _lib as L
+from . import engine as E
+from . import knn as _knn
+
+device = torch.device("cuda" if torch.cuda.is_available() else "cpu")  # csa_models.py:8 (module-level)
+
+_PRECISIONS = {"fp16": torch.float16, "bf16": torch.bfloat16}
+
+
+def _require_cuda(t: torch.Tensor, what: str) -> None:
+    if not t.is_cuda:
+        raise L.CsnError(f"{what} must be a CUDA tensor: csn_b200 has no CPU path")
+
+
+def _geom_for(n_src_points: int, iters: int = 20, chunk: int = 500) -> E.Geometry:
+    g = E.Geometry(chunk=chunk, n_chunks=iters, chunk_pad=(chunk + 127) // 128 * 128)
+    if n_src_points < g.n_points:
+        # the reference indexes points [0, 10000) unconditionally (csa_models.py:86-90)
+        raise IndexError(f"index {g.n_points - 1} is out of bounds for dimension 2 with size {n_src_points}")
+    return g
+
+
+def _pack_sources(sources, n_slots, geom, dt, dev):
+    """sources: list of (tensor (n0,[n1],256,N,1) fp32 cuda, slot0, d0, d1)."""
+    NP = geom.rows_pad
+    Xh = torch.empty(n_slots * NP, 256, dtype=dt, device=dev)
+    Xf = torch.empty(n_slots * NP, 256, dtype=torch.float32, device=dev)
+    for (t, slot0, d0, d1) in sources:
+        if t.dim() == 4:
+            t = t.unsqueeze(1)
+        assert t.dim() == 5 and t.shape[2] == 256 and t.shape[4] == 1, t.shape
+        if t.stride(3) != 1 or t.stride(2) != t.shape[3]:
+            t = t.contiguous()
+        E._launch_pack(t, Xh, Xf, t.shape[0], t.stride(0), t.shape[1], t.stride(1), slot0, d0, d1, geom, t.shape[3])
+    return Xh, Xf
+
+
+def _unpad_rows(Y: torch.Tensor, n_blocks: int, geom: E.Geometry) -> torch.Tensor:
+    return Y.view(n_blocks, geom.n_chunks, geom.chunk_pad, 256)[:, :, :geom.chunk].reshape(n_blocks, geom.n_points, 256)
+
+
+def _pad_rows(dY: torch.Tensor, geom: E.Geometry) -> torch.Tensor:
+    nb = dY.shape[0]
+    out = torch.zeros(nb, geom.n_chunks, geom.chunk_pad, 256, dtype=torch.float32, device=dY.device)
+    out[:, :, :geom.chunk] = dY.reshape(nb, geom.n_chunks, geom.chunk, 256)
+    return out.view(nb * geom.rows_pad, 256)
+
+
+def _rows_to_channel_major(rows: torch.Tensor, n_b: int, n_src_points: int, geom: E.Geometry) -> torch.Tensor:
+    """[n_b*NP,256] padded fp32 rows -> (n_b,256,n_src_points,1) (zeros beyond the used points)."""
+    dev = rows.device
+    alloc = torch.zeros if n_src_points > geom.n_points else torch.empty
+    out = alloc(n_b, 256, n_src_points, 1, dtype=torch.float32, device=dev)
+    blk = torch.arange(n_b, dtype=torch.int32, device=dev)
+    w = torch.ones(n_b, dtype=torch.float32, device=dev)
+    rc = L.lib().csn_combine_fwd(rows.data_ptr(), blk.data_ptr(), w.data_ptr(), out.data_ptr(), None, n_b, 1,
+                                 256 * n_src_points, n_src_points, geom.n_points, geom.chunk, geom.chunk_pad,
+                                 geom.rows_pad, L.CSN_F16, L.stream_ptr())
+    L.check(rc, "csn_combine_fwd")
+    return out
+
+
+def _last_chunk_attn(ctx: E.AttnContext, blocks: int) -> torch.Tensor:
+    """Attention matrix of the last chunk only (csa_models.py:125): (blocks, h, 500, 500)."""
+    g = ctx.geom
+    P = ctx.P.view(ctx.n_blocks, g.n_chunks, ctx.n_head, g.chunk_pad, g.chunk_pad)
+    return P[:blocks, -1, :, :g.chunk, :g.chunk].float()
+
+
+# ------------------------------------------------------------------------------------------- MHA op
+class _MhaFn(torch.autograd.Function):
+    """MultiHeadAttention.forward (csa_models.py:81-125) on channel-major inputs."""
+
+    @staticmethod
+    def forward(ctx, Q, K, V, wq, wk, wv, wo, gamma, beta, n_head, dt, iters, chunk):
+        for t, n in ((Q, "Q"), (K, "K"), (V, "V"), (wq, "w_qs.weight")):
+            _require_cuda(t, n)
+        B, n_src = Q.shape[0], Q.shape[2]
+        geom = _geom_for(min(Q.shape[2], K.shape[2], V.shape[2]), iters, chunk)
+        same_kv = K is V or (K.data_ptr() == V.data_ptr() and K.shape == V.shape and K.stride() == V.stride())
+        same_qk = Q is K or (Q.data_ptr() == K.data_ptr() and Q.shape == K.shape and Q.stride() == K.stride())
+        sources = [(Q.float(), 0, 1, 0)]
+        k0 = 0 if same_qk else B
+        if not same_qk:
+            sources.append((K.float(), B, 1, 0))
+        n_slots = k0 + B
+        v0 = k0
+        if not same_kv:
+            v0 = n_slots
+            sources.append((V.float(), v0, 1, 0))
+            n_slots += B
+        Xh, Xf = _pack_sources(sources, n_slots, geom, dt, Q.device)
+        group = E.Group(n_in=B, n_out=1, blk0=0, q0=0, q_si=1, q_so=0, k0=k0, k_si=1, k_so=0, v0=v0, v_si=1, v_so=0)
+        a = E.attention_forward(Xh, Xf, [group], n_slots, B, wq, wk, wv, wo, gamma, beta, geom, n_head,
+                                want_colsum=False)
+        ctx.a = a
+        ctx.meta = (B, k0, v0, n_slots, Q.shape[2], K.shape[2], V.shape[2])
+        attn = _last_chunk_attn(a, B)
+        ctx.mark_non_differentiable(attn)
+        return _unpad_rows(a.Y, B, geom), attn
+
+    @staticmethod
+    def backward(ctx, dret, _dattn):
+        a = ctx.a
+        B, k0, v0, n_slots, nq, nk, nv = ctx.meta
+        need_dx = any(ctx.needs_input_grad[:3])
+        g = E.attention_backward(a, _pad_rows(dret.float().contiguous(), a.geom), need_dx)
+        dQ = dK = dV = None
+        if need_dx:
+            NP = a.geom.rows_pad
+            dX = g["dX"]
+            dq_rows = dX[:B * NP]
+            dQ = _rows_to_channel_major(dq_rows, B, nq, a.geom)
+            if k0 == 0:      # Q is K (and possibly V): the gradient belongs to the one tensor
+                dK = None
+            else:
+                dK = _rows_to_channel_major(dX[k0 * NP:(k0 + B) * NP], B, nk, a.geom)
+            if v0 != k0:
+                dV = _rows_to_channel_major(dX[v0 * NP:(v0 + B) * NP], B, nv, a.geom)
+        return (dQ, dK, dV, g["dWq"], g["dWk"], g["dWv"], g["dWo"], g["dgamma"], g["dbeta"], None, None, None, None)
+
+
+class ScaledDotProductAttention(nn.Module):
+    """csa_models.py:128-144.  q,k,v: (B,h,L,d) fp32 CUDA -> (output (B,h,Lq,d), attn (B,h,Lq,Lk)).
+    Standalone use only (the fused layer never calls it); forward pass, no autograd."""
+
+    def __init__(self, temperature, attn_dropout=0.1, precision="fp16"):
+        super().__init__()
+        self.temperature = temperature
+        self.dropout = nn.Dropout(attn_dropout)
+        self.precision = precision
+
+    def forward(self, q, k, v):
+        _require_cuda(q, "q")
+        dt = _PRECISIONS[self.precision]
+        B, h, Lq, d = q.shape
+        Lk = k.shape[2]
+        Lkp = (Lk + 7) // 8 * 8
+        q16 = q.reshape(B * h * Lq, d).to(dt)
+        k16 = k.reshape(B * h * Lk, d).to(dt)
+        v16 = v.reshape(B * h * Lk, d).to(dt)
+        S = torch.empty(B * h * Lq, Lkp, dtype=torch.float32, device=q.device)
+        L.gemm(L.mat(q16, L.MAJOR_K, mn_off=(Lq,)), L.mat(k16, L.MAJOR_K, mn_off=(Lk,)),
+               L.out(S, Lkp, off=(Lq * Lkp,)), Lq, Lk, d, nb=(B * h,), alpha=1.0 / float(self.temperature))
+        P = torch.empty(B * h * Lq, Lkp, dtype=dt, device=q.device)
+        rc = L.lib().csn_softmax_fwd(S.data_ptr(), P.data_ptr(), S.shape[0], Lkp, Lk, 1, 1, L.dtype_code(dt),
+                                     L.stream_ptr())
+        L.check(rc, "csn_softmax_fwd")
+        out = torch.empty(B * h * Lq, d, dtype=torch.float32, device=q.device)
+        L.gemm(L.mat(P, L.MAJOR_K, mn_off=(Lq,)), L.mat(v16, L.MAJOR_MN, k_off=(Lk,)),
+               L.out(out, d, off=(Lq * d,)), Lq, d, Lk, nb=(B * h,))
+        return out.view(B, h, Lq, d), P[:, :Lk].float().view(B, h, Lq, Lk)
+
+
+class MultiHeadAttention(nn.Module):
+    """Multi-Head Attention module (csa_models.py:37-125): block-diagonal attention in 20 chunks of
+    500 points + output projection + residual + LayerNorm(eps=1e-6)."""
+
+    def __init__(self, n_head, d_model, d_k, d_v, dropout=0.1, precision="fp16"):
+        super().__init__()
+        assert d_k == d_v, "the kernels assume d_k == d_v (true for every reference configuration)"
+        self.n_head = n_head
+        self.d_k = d_k
+        self.d_v = d_v
+        self.w_qs = nn.Linear(d_model, n_head * d_k, bias=False)
+        self.w_ks = nn.Linear(d_model, n_head * d_k, bias=False)
+        self.w_vs = nn.Linear(d_model, n_head * d_v, bias=False)
+        self.fc = nn.Linear(n_head * d_v, d_model, bias=False)
+        self.attention = ScaledDotProductAttention(temperature=d_k ** 0.5, precision=precision)
+        self.dropout = nn.Dropout(dropout)
+        self.norm = nn.LayerNorm(d_model, eps=1e-6)
+        self.precision = precision
+        self.iters = 20      # csa_models.py:83
+        self.mini_bs = 500   # csa_models.py:84
+
+    def _weights(self):
+        return (self.w_qs.weight, self.w_ks.weight, self.w_vs.weight, self.fc.weight, self.norm.weight, self.norm.bias)
+
+    def forward(self, Q, K, V, mode=None):
+        """Q,K,V: (B,256,N,1) channel-major. Returns (ret (B,10000,256), attn of the last chunk
+        (B,h,500,500)).  `mode` is ignored, as in the reference."""
+        return _MhaFn.apply(Q, K, V, *self._weights(), self.n_head, _PRECISIONS[self.precision], self.iters,
+                            self.mini_bs)
+
+    def self_attention(self, x):
+        """csa_models.py:59-79 (unused by the reference): full, un-chunked self-attention."""
+        n = x.shape[2]
+        return _MhaFn.apply(x, x, x, *self._weights(), self.n_head, _PRECISIONS[self.precision], 1, n)
+
+
+# ------------------------------------------------------------------------------------------- CSA op
+class _CsaFn(torch.autograd.Function):
+    """CrossShapeAt.get_csa_feats (csa_models.py:209-242) / get_ssa_feats (:204-207, x_neighbors=None)."""
+
+    @staticmethod
+    def forward(ctx, x, x_neighbors, wq, wk, wv, wo, gamma, beta, cq_w, cq_b, ck_w, ck_b, n_head, dt, iters, chunk):
+        _require_cuda(x, "x")
+        _require_cuda(wq, "attention.w_qs.weight")
+        dev = x.device
+        B, n_src = x.shape[0], x.shape[2]
+        ssa_only = x_neighbors is None
+        K = 0 if ssa_only else x_neighbors.shape[1] - 1
+        if not ssa_only and not x_neighbors.is_cuda:
+            # the reference moves each neighbour inside the layer (csa_models.py:216,236)
+            x_neighbors = x_neighbors.to(dev, non_blocking=True)
+        n_src_nb = n_src if ssa_only or K == 0 else x_neighbors.shape[3]
+        geom = _geom_for(min(n_src, n_src_nb), iters, chunk)
+        S = B * (K + 1)
+        sources = [(x.float(), 0, K + 1, 0)]
+        if K > 0:
+            sources.append((x_neighbors[:, 1:].float(), 1, K + 1, 1))
+        Xh, Xf = _pack_sources(sources, S, geom, dt, dev)
+        groups = [E.Group(n_in=S, n_out=1, blk0=0, q0=0, q_si=1, q_so=0, k0=0, k_si=1, k_so=0, v0=0, v_si=1, v_so=0)]
+        nblk = S
+        if K > 0:
+            groups.append(E.Group(n_in=K, n_out=B, blk0=S, q0=0, q_si=0, q_so=K + 1, k0=1, k_si=1, k_so=K + 1,
+                                  v0=1, v_si=1, v_so=K + 1))
+            nblk += B * K
+        a = E.attention_forward(Xh, Xf, groups, S, nblk, wq, wk, wv, wo, gamma, beta, geom, n_head,
+                                want_colsum=not ssa_only)
+        # ---- compatibility (csa_models.py:211-230): tiny (B*(K+1) x 256) glue, kept in torch
+        if ssa_only:
+            comp = torch.ones(B, 1, dtype=torch.float32, device=dev)
+            glue = None
+        else:
+            pooled = (a.colsum[:S] / geom.n_points).detach().requires_grad_(True)   # slot order (b,k)
+            loc = [t.detach().requires_grad_(True) for t in (cq_w, cq_b, ck_w, ck_b)]
+            with torch.enable_grad():
+                pv = pooled.view(B, K + 1, 256)
+                y_q = pv[:, 0]
+                y_stack = pv.transpose(0, 1).reshape((K + 1) * B, 256)   # rows [k=0: b..; k=1: b..; ...] (:213,220)
+                u_q = F.normalize(F.linear(y_q, loc[0], loc[1]), dim=-1)
+                u_k = F.normalize(F.linear(y_stack, loc[2], loc[3]), dim=-1)
+                u_k = u_k.view(B, -1, 256)                               # batch-interleaving view (:227)
+                comp_g = torch.softmax(torch.matmul(u_q.unsqueeze(1), u_k.permute(0, 2, 1)).squeeze(1), dim=-1)
+            comp = comp_g.detach()
+            glue = (pooled, loc, comp_g)
+        # ---- out = sum_k comp[b,k] * MHA(x, x_k)   (:232-240), written channel-major
+        blk = torch.empty(B, K + 1, dtype=torch.int32)
+        for b in range(B):
+            blk[b, 0] = b * (K + 1)
+            for k in range(1, K + 1):
+                blk[b, k] = S + b * K + (k - 1)
+        blk = blk.to(dev)
+        alloc = torch.zeros if n_src > geom.n_points else torch.empty
+        out = alloc(B, 256, geom.n_points, 1, dtype=torch.float32, device=dev)
+        compc = comp.contiguous()
+        rc = L.lib().csn_combine_fwd(a.Y.data_ptr(), blk.data_ptr(), compc.data_ptr(), out.data_ptr(), None, B, K + 1,
+                                     256 * geom.n_points, geom.n_points, geom.n_points, geom.chunk, geom.chunk_pad,
+                                     geom.rows_pad, L.dtype_code(dt), L.stream_ptr())
+        L.check(rc, "csn_combine_fwd")
+        ctx.a, ctx.glue, ctx.comp, ctx.blk = a, glue, compc, blk
+        ctx.meta = (B, K, S, nblk, n_src, n_src_nb)
+        attn = _last_chunk_attn(a, S).view(B, K + 1, n_head, geom.chunk, geom.chunk)[:, 0]
+        ctx.mark_non_differentiable(attn)
+        return out, attn
+
+    @staticmethod
+    def backward(ctx, dout, _dattn):
+        a = ctx.a
+        geom = a.geom
+        B, K, S, nblk, n_src, n_src_nb = ctx.meta
+        dev = dout.device
+        dout = dout.float().contiguous()
+        # tables of the combine backward
+        cb = torch.full((nblk,), -1, dtype=torch.int32)
+        cwi = torch.full((nblk,), -1, dtype=torch.int32)
+        pb = torch.full((nblk,), -1, dtype=torch.int32)
+        for b in range(B):
+            for k in range(K + 1):
+                slot = b * (K + 1) + k
+                if ctx.glue is not None:
+                    pb[slot] = slot
+                if k == 0:
+                    cb[slot], cwi[slot] = b, slot
+                else:
+                    j = S + b * K + (k - 1)
+                    cb[j], cwi[j] = b, slot
+        cb, cwi, pb = cb.to(dev), cwi.to(dev), pb.to(dev)
+        cw = ctx.comp.reshape(-1)[cwi.clamp(min=0).long()].contiguous()
+        lib = L.lib()
+        obs, ocs = 256 * geom.n_points, geom.n_points
+        grads_glue = [None] * 4
+        dpool = None
+        if ctx.glue is not None:
+            dcomp = torch.zeros(B * (K + 1), dtype=torch.float32, device=dev)
+            rc = lib.csn_combine_bwd(dout.data_ptr(), a.Y.data_ptr(), None, cb.data_ptr(), cw.data_ptr(), cwi.data_ptr(),
+                                     pb.data_ptr(), 0.0, None, dcomp.data_ptr(), nblk, obs, ocs, geom.n_points,
+                                     geom.chunk, geom.chunk_pad, geom.rows_pad, L.stream_ptr())
+            L.check(rc, "csn_combine_bwd(dcomp)")
+            pooled, loc, comp_g = ctx.glue
+            gl = torch.autograd.grad(comp_g, [pooled] + loc, dcomp.view(B, K + 1))
+            dpool = gl[0].contiguous()
+            grads_glue = list(gl[1:])
+        dY = torch.empty(nblk * geom.rows_pad, 256, dtype=torch.float32, device=dev)
+        rc = lib.csn_combine_bwd(dout.data_ptr(), a.Y.data_ptr(), dpool.data_ptr() if dpool is not None else None,
+                                 cb.data_ptr(), cw.data_ptr(), cwi.data_ptr(), pb.data_ptr(), 1.0 / geom.n_points,
+                                 dY.data_ptr(), None, nblk, obs, ocs, geom.n_points, geom.chunk, geom.chunk_pad,
+                                 geom.rows_pad, L.stream_ptr())
+        L.check(rc, "csn_combine_bwd(dY)")
+        need_dx = ctx.needs_input_grad[0] or ctx.needs_input_grad[1]
+        g = E.attention_backward(a, dY, need_dx)
+        dx = dnb = None
+        if need_dx:
+            G = _rows_to_channel_major(g["dX"], S, max(n_src, n_src_nb), geom).view(B, K + 1, 256, -1, 1)
+            if ctx.needs_input_grad[0]:
+                dx = G[:, 0, :, :n_src].contiguous()
+            if ctx.needs_input_grad[1]:
+                dnb = G[:, :, :, :n_src_nb].clone()
+                dnb[:, 0] = 0   # slot 0 of x_neighbors is never read (csa_models.py:214,234)
+        return (dx, dnb, g["dWq"], g["dWk"], g["dWv"], g["dWo"], g["dgamma"], g["dbeta"], *grads_glue,
+                None, None, None, None)
+
+
+class CrossShapeAt(nn.Module):
+    """csa_models.py:146-404 with the same parameters / buffers / state_dict keys."""
+
+    def __init__(self, num_classes, d_model, n_heads, K=None, d_k=256, d_v=256, attention_type='ssa', after_fc=False,
+                 device=None, precision="fp16"):
+        super().__init__()
+        self.fc_1 = self.octree_conv1x1_bn_relu(928, 256)   # constructed but unused by forward (:150,:191-202)
+        self.logit = self.octree_conv1x1(256, num_classes)
+        self.attention = MultiHeadAttention(n_heads, d_model, d_k, d_v, precision=precision)
+        self.attention_type = attention_type
+        self.after_fc = after_fc
+        self.device = device
+        self.precision = precision
+        if 'csa' in self.attention_type:
+            self.K = K
+            self.compatibility_q = nn.Linear(256, 256)
+            self.compatibility_k = nn.Linear(256, 256)
+
+    def octree_conv1x1_bn_relu(self, nin, nout):
+        return nn.Sequential(self.octree_conv1x1_bn(nin, nout), nn.ReLU())
+
+    def octree_conv1x1_bn(self, nin, nout):
+        return nn.Sequential(self.octree_conv1x1(nin, nout, use_bias=False), nn.BatchNorm2d(nout))
+
+    def octree_conv1x1(self, nin, nout, use_bias=False):
+        layer = nn.Conv2d(nin, nout, kernel_size=1, stride=1, padding='same', bias=use_bias)
+        nn.init.xavier_uniform_(layer.weight)
+        return layer
+
+    # -- forward paths (csa_models.py:182-202)
+    def forward(self, x, mode, neighbor_feats=None):
+        if self.attention_type == 'ssa':
+            x = self.forward_ssa(x, mode)
+        if self.attention_type == 'csa':
+            x = self.forward_csa(x, neighbor_feats, mode)
+        if self.attention_type == 'fcf_csaf_logitf':
+            x = self.forward_fcf_csaf_logitf(x, neighbor_feats, mode)  # undefined in the reference too
+        return x
+
+    def forward_ssa(self, x, mode):
+        if self.after_fc:
+            x, self_att = self.get_ssa_feats(x, mode)
+        return self.logit(x)
+
+    def forward_csa(self, x, x_neighbors, mode):
+        if self.after_fc:
+            x = self.get_csa_feats(x, x_neighbors, mode)
+        return self.logit(x)
+
+    def _csa_args(self):
+        a = self.attention
+        extra = (None, None, None, None)
+        if 'csa' in self.attention_type:
+            extra = (self.compatibility_q.weight, self.compatibility_q.bias, self.compatibility_k.weight,
+                     self.compatibility_k.bias)
+        return (*a._weights(), *extra, a.n_head, _PRECISIONS[self.precision], a.iters, a.mini_bs)
+
+    def get_ssa_feats(self, x, mode):
+        """(B,256,N,1) -> (SSA features (B,256,10000,1), attention of the last chunk)."""
+        return _CsaFn.apply(x, None, *self._csa_args())
+
+    def get_csa_feats(self, x, x_neighbors, mode):
+        """x (B,256,N,1); x_neighbors (B,K+1,256,N,1) (slot 0 = the query, skipped; CPU tensors are
+        accepted and moved, like csa_models.py:216,236) -> (B,256,10000,1)."""
+        return _CsaFn.apply(x, x_neighbors, *self._csa_args())[0]
+
+    # -- retrieval (csa_models.py:244-280)
+    def get_retrieval_measure(self, ssa_feats_1, ssa_feats_2):
+        return _knn.retrieval_measure(ssa_feats_1, ssa_feats_2, _PRECISIONS[self.precision])
+
+    def get_knn_graph(self, ssa_feats_1, ssa_feats_2, K):
+        return _knn.knn_graph(ssa_feats_1, ssa_feats_2, K, _PRECISIONS[self.precision])
+
+    def get_all_feats(self, logs_dir, train_dataloader, K, mode):
+        """csa_models.py:282-300: SSA features of every shape of a loader, (S, N, 256) on the CPU."""
+        chunks = []
+        dev = next(self.parameters()).device
+        for feats, _label in train_dataloader:
+            feats = torch.squeeze(feats.to(dev), dim=1)
+            with torch.no_grad():
+                batch, _ = self.get_ssa_feats(feats, mode)
+            chunks.append(batch.detach().cpu())
+        ssa = torch.cat(chunks, dim=0)
+        return torch.permute(torch.squeeze(ssa, dim=-1), (0, 2, 1))
+
+    def get_center_shape_indices(self, train_loader):
+        """csa_models.py:302-332: k-means (S//10 centres) over amax-pooled SSA features; returns the
+        shape nearest to each centre. KMeans itself is scikit-learn's, as in the reference."""
+        from sklearn.cluster import KMeans
+        dev = next(self.parameters()).device
+        glob = []
+        for feats, _label in train_loader:
+            feats = torch.squeeze(feats.to(dev), dim=1)
+            with torch.no_grad():
+                batch, _ = self.get_ssa_feats(feats, 'test')
+            glob.append(torch.amax(batch.squeeze(-1), dim=2).detach())
+        glob = torch.cat(glob, dim=0).cpu().numpy()
+        n_centers = len(glob) // 10
+        kmeans = KMeans(n_clusters=n_centers, random_state=0, n_init=10).fit(glob)
+        d = ((np.expand_dims(kmeans.cluster_centers_, 1) - glob) ** 2).sum(-1)
+        return np.argmin(d, axis=-1)
+
+    def get_candidate_ssa_feats(self, data_loader, candidate_shape_indices):
+        """csa_models.py:334-358 (loader with batch size 1; indices sorted ascending)."""
+        dev = next(self.parameters()).device
+        out, counter = [], 0
+        for i, (feats, _label) in enumerate(data_loader):
+            if i != candidate_shape_indices[counter]:
+                continue
+            feats = torch.squeeze(feats.to(dev), dim=1)
+            with torch.no_grad():
+                batch, _ = self.get_ssa_feats(feats, 'test')
+            out.append(batch.detach())
+            counter += 1
+            if counter == len(candidate_shape_indices):
+                break
+        ssa = torch.cat(out, dim=0)
+        return torch.permute(torch.squeeze(ssa, dim=-1), (0, 2, 1)).contiguous()
+
+    def get_retrieval_measure_big(self, query_loader, candidate_loader, candidate_shape_indices):
+        """csa_models.py:360-392: every query of a loader against the candidate subset."""
+        candidate_shape_indices.sort()
+        cand = self.get_candidate_ssa_feats(candidate_loader, candidate_shape_indices)
+        dt = _PRECISIONS[self.precision]
+        cstore = _knn.build_store(cand, dt)
+        dev = cand.device
+        rows = []
+        for feats, _label in query_loader:
+            feats = torch.squeeze(feats.to(dev), dim=1)
+            with torch.no_grad():
+                f1, _ = self.get_ssa_feats(feats, 'test')
+            f1 = f1.squeeze(-1).permute(0, 2, 1).contiguous()
+            rows.append(_knn.scores_from_stores(_knn.build_store(f1, dt), cstore))
+        return torch.cat(rows, dim=0)
+
+    def get_knn_graph_big(self, query_loader, candidate_loader, candidate_shape_indices, K):
+        s = self.get_retrieval_measure_big(query_loader, candidate_loader, candidate_shape_indices)
+        return _knn.topk_rows(s.contiguous(), K + 1)[1]
+
+
+def backbone_ssa_fc_logit(num_classes, n_heads, **kw):
+    return CrossShapeAt(num_classes, 928, n_heads, attention_type='ssa', after_fc=False, **kw)
+
+
+def backbone_fc_ssa_logit(num_classes, n_heads, **kw):
+    return CrossShapeAt(num_classes, 256, n_heads, attention_type='ssa', after_fc=True, **kw)
+
+
+def backbone_csa_fc_logit(num_classes, n_heads, K, **kw):
+    return CrossShapeAt(num_classes, 928, n_heads, K, attention_type='csa', after_fc=False, **kw)
+
+
+def backbone_fc_csa_logit(num_classes, n_heads, K, **kw):
+    return CrossShapeAt(num_classes, 256, n_heads, K, attention_type='csa', after_fc=True, **kw)
+
+
+def get_model(attention_type, num_classes, n_heads, K=None, **kw):
+    """csa_models.py:426-432."""
+    if attention_type == 'ssa':
+        return backbone_fc_ssa_logit(num_classes, n_heads, **kw)
+    elif attention_type == 'csa':
+        return backbone_fc_csa_logit(num_classes, n_heads, K, **kw)
+    raise AttributeError(f'{attention_type} not supported')

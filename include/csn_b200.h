@@ -44,7 +44,7 @@ int64_t csn_launch_count(void);
  * major = CSN_MAJOR_MN : view[k][mn], mn contiguous (a transposed operand, consumed without a copy).
  * `inner`/`outer` are the extents of the contiguous / strided dimension of the whole view, `ld` the
  * stride of the strided dimension in elements (ld*2 bytes must be a multiple of 16, ptr 16-byte
- * aligned).  Batch index (b0,b1,b2) selects the sub-problem: its mn origin is sum_i b_i*mn_off[i],
+ * aligned).  Batch index (b0,b1,b2,b3) selects the sub-problem: its mn origin is sum_i b_i*mn_off[i],
  * its k origin sum_i b_i*k_off[i].  Reads outside [0,inner)x[0,outer) return zero.
  */
 typedef struct csn_mat {
@@ -52,8 +52,8 @@ typedef struct csn_mat {
   int32_t dtype; /* CSN_F16 or CSN_BF16; A and B must agree */
   int32_t major;
   int64_t inner, outer, ld;
-  int64_t mn_off[3];
-  int64_t k_off[3];
+  int64_t mn_off[4];
+  int64_t k_off[4];
 } csn_mat;
 
 typedef struct csn_out {
@@ -61,13 +61,13 @@ typedef struct csn_out {
   int32_t dtype;      /* CSN_F32 / CSN_F16 / CSN_BF16 */
   int32_t transposed; /* 0: D[m*ld + n], 1: D[n*ld + m] */
   int64_t ld;
-  int64_t off[3];     /* element offset per batch index */
+  int64_t off[4];     /* element offset per batch index */
   int32_t accumulate; /* 1: atomically add into an fp32 D (required when split_k > 1) */
   int32_t reserved;
 } csn_out;
 
 int csn_gemm(const csn_mat* A, const csn_mat* B, const csn_out* D, int32_t M, int32_t N, int32_t K,
-             const int32_t nb[3], float alpha, int32_t split_k, void* stream);
+             const int32_t nb[4], float alpha, int32_t split_k, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Shape-compatibility retrieval measure and top-K neighbour selection
@@ -102,6 +102,61 @@ int csn_knn_reduce(const float* partial, float* scores, int32_t n_q, int32_t n_c
  * first (`retrieval_measure.topk(K+1, -1)`, csa_models.py:278,401). */
 int csn_topk_rows(const float* scores, int64_t ld, int32_t n_rows, int32_t n_cols, int32_t k,
                   float* out_val, int64_t* out_idx, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * HBM-bound pieces of the CSA/SSA layer.  Row buffers use "padded" coordinates: a shape's block has
+ * rows_pad = n_chunks*chunk_pad rows; chunk c (points [c*chunk, (c+1)*chunk)) occupies rows
+ * [c*chunk_pad, c*chunk_pad + chunk); pad rows are zero.  MID-FC: chunk = 500 (csa_models.py:83-90),
+ * chunk_pad = 512.
+ * ------------------------------------------------------------------------------------------- */
+
+/* Channel-major fp32 features (the reference layout (B,256,N,1), csa_models.py:92-94) -> padded
+ * row-major rows, 16-bit (dst16) and optionally fp32 (dst32, may be NULL).  Source element
+ * (i0,i1,c,n) is src[i0*src_s0 + i1*src_s1 + c*ch_stride + n]; destination slot is
+ * dst_slot0 + i0*dst_s0 + i1*dst_s1. */
+int csn_pack_rows(const float* src, void* dst16, float* dst32, int64_t ch_stride, int32_t n0,
+                  int64_t src_s0, int32_t n1, int64_t src_s1, int64_t dst_slot0, int64_t dst_s0,
+                  int64_t dst_s1, int32_t n_points, int32_t chunk, int32_t chunk_pad, int32_t rows_pad,
+                  int32_t dtype, void* stream);
+
+/* P = softmax over the first cols_valid columns of each fp32 row (F.softmax(dim=-1),
+ * csa_models.py:141), 16-bit, zero in pad columns and in pad rows (row % group_rows >= rows_valid). */
+int csn_softmax_fwd(const float* S, void* P, int64_t rows, int32_t cols_pad, int32_t cols_valid,
+                    int32_t group_rows, int32_t rows_valid, int32_t dtype, void* stream);
+/* dS = P o (dP - rowsum(P o dP)) * scale   (autograd of csa_models.py:139-141). */
+int csn_softmax_bwd(const void* P, const float* dP, void* dS, int64_t rows, int32_t cols_pad,
+                    int32_t cols_valid, int32_t group_rows, int32_t rows_valid, float scale,
+                    int32_t dtype, void* stream);
+
+/* z = Z + residual (in place); Y = LayerNorm(z)*gamma + beta with eps inside the sqrt and biased
+ * variance (csa_models.py:116-118, :57); mean / rstd saved per row; colsum[block] += sum of Y over
+ * the block's valid rows (the mean over points of csa_models.py:212,219, un-normalised).
+ * Residual row of (block, r) is R[(res_block[block]*block_rows + r)*256]. */
+int csn_add_ln_fwd(float* Z, const float* R, const int32_t* res_block, float* Y, void* Y16, float* mean,
+                   float* rstd, const float* gamma, const float* beta, float* colsum, int64_t rows,
+                   int32_t block_rows, int32_t group_rows, int32_t rows_valid, float eps, int32_t dtype,
+                   void* stream);
+int csn_ln_bwd(const float* dY, const float* Z, const float* mean, const float* rstd, const float* gamma,
+               float* dZ, void* dZ16, float* dgamma, float* dbeta, int64_t rows, int32_t block_rows,
+               int32_t group_rows, int32_t rows_valid, int32_t dtype, void* stream);
+
+/* out[b][c][n] = sum_k w[b*n_k+k] * Y[blk[b*n_k+k]][padrow(n)][c]: the compatibility-weighted sum
+ * of the self- and cross-attention outputs written back channel-major (csa_models.py:232-240);
+ * rows16 (optional) receives a 16-bit row-major copy. With n_k = 1, w = 1 it is the plain
+ * row-major -> channel-major transpose of csa_models.py:206. */
+int csn_combine_fwd(const float* Y, const int32_t* blk, const float* w, float* out, void* rows16,
+                    int32_t n_b, int32_t n_k, int64_t out_b_stride, int64_t out_ch_stride,
+                    int32_t n_points, int32_t chunk, int32_t chunk_pad, int32_t rows_pad, int32_t dtype,
+                    void* stream);
+/* Backward of the above plus of the pooled means.  For block j:
+ *   dY[j] = cw[j]*dOut[cb[j]]^T (if cb[j] >= 0) + pool_scale*dpool[pb[j]] (if pb[j] >= 0), valid rows;
+ *   dcomp[cw_index[j]] += <dOut[cb[j]]^T, Y[j]>  (if cw_index[j] >= 0).
+ * dY == NULL: only dcomp is computed; dcomp == NULL: only dY. */
+int csn_combine_bwd(const float* dOut, const float* Y, const float* dpool, const int32_t* cb,
+                    const float* cw, const int32_t* cw_index, const int32_t* pb, float pool_scale,
+                    float* dY, float* dcomp, int32_t n_blocks, int64_t out_b_stride,
+                    int64_t out_ch_stride, int32_t n_points, int32_t chunk, int32_t chunk_pad,
+                    int32_t rows_pad, void* stream);
 
 #ifdef __cplusplus
 }
