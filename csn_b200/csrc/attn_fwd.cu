@@ -1,0 +1,440 @@
+// Fused attention forward (flash-style) for sm_100a:   O = softmax(Q K^T / sqrt(d)) V   per work item,
+// with the score matrix living only in TMEM (reference: ScaledDotProductAttention.forward,
+// MID-FC/csa_models.py:138-144 == MinkowskiNet/models/attention.py:69-75, which materialise it).
+//
+// Work item (table in device memory) = 128 query rows of one (block, head) attending to the key rows
+// [kv_row0, kv_row0 + kv_len).  MID-FC: kv range = the 500-point chunk of the query tile
+// (block-diagonal attention, csa_models.py:83-90); MinkowskiNet: the whole key shape.
+//
+// CTA = 256 threads, one CTA per SM, persistent over items:
+//   warp 0    TMA producer : Q tile (resident per item) + ring of K / V slots (SWIZZLE_128B)
+//   warp 1    MMA issuer   : S_j = Q K_j^T (kind::f16, fp32 in TMEM, 2 S buffers) ; O += P_j V_j
+//                            (V consumed MN-major straight from the projection output)
+//   warp 2    TMEM allocator (512 columns: S0 | S1 | O)
+//   warps 4-7 softmax      : lane = query row. tcgen05.ld S_j, running max / sum (online softmax, lazy
+//                            rescale of O only when the max grows by > 2^8), P_j -> SMEM (16-bit,
+//                            128B-swizzled K-major tile = A operand of the P V MMA), final O / l and
+//                            LSE written by the same warps.
+#include "host_util.h"
+#include "ptx.cuh"
+
+namespace csn {
+
+__device__ __forceinline__ float fast_exp2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+struct AttnItem {
+  int q_row0;    // first query row (row of the Q view)
+  int q_valid;   // rows of the tile that exist (<= 128); the others are written as zeros
+  int kv_row0;   // first key/value row
+  int kv_len;    // number of keys this tile attends to
+  int o_row0;    // first output row (row of the O buffer)
+  int col0;      // head * d: column offset in the Q/K/V views and in O
+  int lse_off;   // lse[lse_off + r] for row r of the tile
+  int flags;     // bit 0: write zeros to the tile rows >= q_valid (padded layouts); else leave them untouched
+};
+
+struct AttnFwdArgs {
+  const AttnItem* items;
+  int n_items;
+  void* O;            // 16-bit [rows][ldo]
+  long long ldo;
+  float* lse;         // natural-log sum-exp of the scaled scores per query row
+  float scale_log2;   // (1/sqrt(d)) * log2(e)
+  float scale;        // 1/sqrt(d)
+  int dtype;
+  uint32_t idesc_qk;  // M=128, N=128, both K-major
+  uint32_t idesc_pv;  // M=128, N=d, A K-major, B MN-major
+};
+
+template <int DH>
+struct AttnCfg {
+  static constexpr int KB = DH / 64;                       // k-blocks of the QK^T contraction
+  static constexpr int Q_BYTES = 128 * DH * 2;             // resident query tile
+  static constexpr int P_BYTES = 128 * 128 * 2;            // probabilities of one KV tile (2 k-blocks)
+  static constexpr int SLOT_BYTES = (DH >= 128) ? 32768 : 128 * DH * 2;
+  // K tile (128 keys x DH): slots of [128 keys x (SLOT_BYTES/256) columns]
+  static constexpr int K_SLOTS = (128 * DH * 2) / SLOT_BYTES;
+  static constexpr int KB_PER_KSLOT = KB / K_SLOTS;
+  // V tile (128 keys x DH), MN-major: slots of [KEYS_PER_VSLOT keys x DH columns]
+  static constexpr int V_SLOTS = K_SLOTS;
+  static constexpr int KEYS_PER_VSLOT = 128 / V_SLOTS;
+  static constexpr int NST = (DH >= 128) ? 4 : 8;
+  static constexpr int BAR_BYTES = 256;
+  static constexpr int SMEM_BYTES = Q_BYTES + P_BYTES + NST * SLOT_BYTES + BAR_BYTES + 1024;
+  static constexpr int O_COL = 256;                        // TMEM: S0 @0, S1 @128, O @256 (DH <= 256)
+};
+
+template <int DH>
+__global__ void __launch_bounds__(256, 1)
+attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                const __grid_constant__ CUtensorMap tmV, const __grid_constant__ AttnFwdArgs p) {
+  using Cfg = AttnCfg<DH>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const uint32_t sQ = smem_u32(smem);
+  const uint32_t sP = sQ + Cfg::Q_BYTES;
+  const uint32_t sKV = sP + Cfg::P_BYTES;
+  const uint32_t bar_base = sKV + Cfg::NST * Cfg::SLOT_BYTES;
+  uint8_t* bar_ptr = smem + Cfg::Q_BYTES + Cfg::P_BYTES + Cfg::NST * Cfg::SLOT_BYTES;
+  auto kv_full = [&](int s) { return bar_base + 8u * s; };
+  auto kv_empty = [&](int s) { return bar_base + 8u * (Cfg::NST + s); };
+  const uint32_t bq_full = bar_base + 8u * (2 * Cfg::NST + 0);
+  const uint32_t bq_empty = bar_base + 8u * (2 * Cfg::NST + 1);
+  auto s_full = [&](int b) { return bar_base + 8u * (2 * Cfg::NST + 2 + b); };
+  auto s_empty = [&](int b) { return bar_base + 8u * (2 * Cfg::NST + 4 + b); };
+  const uint32_t bp_full = bar_base + 8u * (2 * Cfg::NST + 6);
+  const uint32_t bp_empty = bar_base + 8u * (2 * Cfg::NST + 7);
+  const uint32_t bo_full = bar_base + 8u * (2 * Cfg::NST + 8);
+  const uint32_t bo_empty = bar_base + 8u * (2 * Cfg::NST + 9);
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bar_ptr + 8 * (2 * Cfg::NST + 10));
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmK);
+    tma_prefetch_desc(&tmV);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < Cfg::NST; ++s) {
+      mbar_init(kv_full(s), 1);
+      mbar_init(kv_empty(s), 1);
+    }
+    mbar_init(bq_full, 1);
+    mbar_init(bq_empty, 1);
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(s_full(b), 1);
+      mbar_init(s_empty(b), 128);
+    }
+    mbar_init(bp_full, 128);
+    mbar_init(bp_empty, 1);
+    mbar_init(bo_full, 1);
+    mbar_init(bo_empty, 128);
+    fence_mbar_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(smem_u32(tmem_ptr_smem), 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp == 0) {
+    // ================================================================== TMA producer
+    if (lane == 0) {
+      int st = 0;
+      uint32_t ph = 0, q_ph = 0;
+      auto load_k = [&](const AttnItem& it, int j) {
+#pragma unroll 1
+        for (int s = 0; s < Cfg::K_SLOTS; ++s) {
+          mbar_wait(kv_empty(st), ph ^ 1);
+          mbar_arrive_expect_tx(kv_full(st), Cfg::SLOT_BYTES);
+#pragma unroll
+          for (int kb = 0; kb < Cfg::KB_PER_KSLOT; ++kb)
+            tma_load_2d(sKV + st * Cfg::SLOT_BYTES + kb * 16384, &tmK, kv_full(st),
+                        it.col0 + (s * Cfg::KB_PER_KSLOT + kb) * 64, it.kv_row0 + j * 128);
+          if (++st == Cfg::NST) { st = 0; ph ^= 1; }
+        }
+      };
+      auto load_v = [&](const AttnItem& it, int j) {
+#pragma unroll 1
+        for (int s = 0; s < Cfg::V_SLOTS; ++s) {
+          mbar_wait(kv_empty(st), ph ^ 1);
+          mbar_arrive_expect_tx(kv_full(st), Cfg::SLOT_BYTES);
+          // MN-major: one box of [KEYS_PER_VSLOT key rows x 64 columns] per 64-column atom
+#pragma unroll
+          for (int a = 0; a < Cfg::KB; ++a)
+            tma_load_2d(sKV + st * Cfg::SLOT_BYTES + a * (Cfg::KEYS_PER_VSLOT * 128), &tmV, kv_full(st),
+                        it.col0 + a * 64, it.kv_row0 + j * 128 + s * Cfg::KEYS_PER_VSLOT);
+          if (++st == Cfg::NST) { st = 0; ph ^= 1; }
+        }
+      };
+      for (int w = blockIdx.x; w < p.n_items; w += gridDim.x) {
+        const AttnItem it = p.items[w];
+        const int nkv = (it.kv_len + 127) >> 7;
+        mbar_wait(bq_empty, q_ph ^ 1);
+        mbar_arrive_expect_tx(bq_full, Cfg::Q_BYTES);
+#pragma unroll
+        for (int kb = 0; kb < Cfg::KB; ++kb)
+          tma_load_2d(sQ + kb * 16384, &tmQ, bq_full, it.col0 + kb * 64, it.q_row0);
+        q_ph ^= 1;
+        // consumption order of the MMA warp: K0, [K1, V0], [K2, V1], ..., V_last
+        load_k(it, 0);
+        for (int j = 0; j < nkv; ++j) {
+          if (j + 1 < nkv) load_k(it, j + 1);
+          load_v(it, j);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================================================================== MMA issuer
+    if (lane == 0) {
+      int st = 0;
+      uint32_t ph = 0, q_ph = 0, p_ph = 0, o_ph = 0;
+      uint32_t s_ph[2] = {0, 0};
+      auto issue_qk = [&](int j, bool last) {
+        const int b = j & 1;
+        mbar_wait(s_empty(b), s_ph[b] ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + b * 128;
+#pragma unroll 1
+        for (int s = 0; s < Cfg::K_SLOTS; ++s) {
+          mbar_wait(kv_full(st), ph);
+          tc_fence_after();
+#pragma unroll
+          for (int kb = 0; kb < Cfg::KB_PER_KSLOT; ++kb) {
+            const uint32_t a_tile = sQ + (s * Cfg::KB_PER_KSLOT + kb) * 16384;
+            const uint32_t b_tile = sKV + st * Cfg::SLOT_BYTES + kb * 16384;
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              umma_f16_ss(d_tmem, umma_desc_sw128(a_tile + k * 32, 0, 1024), umma_desc_sw128(b_tile + k * 32, 0, 1024),
+                          p.idesc_qk, (s | kb | k) ? 1u : 0u);
+          }
+          umma_commit(kv_empty(st));
+          if (++st == Cfg::NST) { st = 0; ph ^= 1; }
+        }
+        umma_commit(s_full(b));
+        if (last) umma_commit(bq_empty);  // every QK^T of this item has been issued: Q tile may be replaced
+        s_ph[b] ^= 1;
+      };
+      for (int w = blockIdx.x; w < p.n_items; w += gridDim.x) {
+        const AttnItem it = p.items[w];
+        const int nkv = (it.kv_len + 127) >> 7;
+        mbar_wait(bq_full, q_ph);
+        q_ph ^= 1;
+        issue_qk(0, nkv == 1);
+        for (int j = 0; j < nkv; ++j) {
+          if (j + 1 < nkv) issue_qk(j + 1, j + 2 == nkv);
+          mbar_wait(bp_full, p_ph);  // P_j is in SMEM (and O was rescaled if needed)
+          p_ph ^= 1;
+          if (j == 0) mbar_wait(bo_empty, o_ph ^ 1);  // previous item's O has been read out
+          tc_fence_after();
+          const uint32_t o_tmem = tmem_base + Cfg::O_COL;
+#pragma unroll 1
+          for (int s = 0; s < Cfg::V_SLOTS; ++s) {
+            mbar_wait(kv_full(st), ph);
+            tc_fence_after();
+            const uint32_t v_tile = sKV + st * Cfg::SLOT_BYTES;
+#pragma unroll
+            for (int k = 0; k < Cfg::KEYS_PER_VSLOT / 16; ++k) {
+              const int key = s * Cfg::KEYS_PER_VSLOT + k * 16;  // key offset inside the 128-key tile
+              const uint32_t a_addr = sP + (key >> 6) * 16384 + (key & 63) * 2;
+              umma_f16_ss(o_tmem, umma_desc_sw128(a_addr, 0, 1024),
+                          umma_desc_sw128(v_tile + k * 2048, Cfg::KEYS_PER_VSLOT * 128, 1024), p.idesc_pv,
+                          (j | s | k) ? 1u : 0u);
+            }
+            umma_commit(kv_empty(st));
+            if (++st == Cfg::NST) { st = 0; ph ^= 1; }
+          }
+          umma_commit(bp_empty);  // P buffer free / O accumulation of tile j complete
+        }
+        umma_commit(bo_full);    // (same completion point as the last bp_empty)
+        o_ph ^= 1;
+      }
+    }
+  } else if (warp >= 4) {
+    // ================================================================== softmax / correction / epilogue
+    const int q = warp & 3;
+    const int r = q * 32 + lane;  // row of the tile owned by this thread
+    const uint32_t lane_addr = uint32_t(q * 32) << 16;
+    uint32_t s_ph[2] = {0, 0};
+    uint32_t pe_ph = 0, of_ph = 0;
+    uint8_t* sP_ptr = smem + Cfg::Q_BYTES;
+    for (int w = blockIdx.x; w < p.n_items; w += gridDim.x) {
+      const AttnItem it = p.items[w];
+      const int nkv = (it.kv_len + 127) >> 7;
+      float m_used = -INFINITY;  // reference max (raw score units)
+      float l = 0.f;
+      for (int j = 0; j < nkv; ++j) {
+        const int b = j & 1;
+        mbar_wait(s_full(b), s_ph[b]);
+        s_ph[b] ^= 1;
+        tc_fence_after();
+        const uint32_t s_addr = tmem_base + lane_addr + b * 128;
+        const int nvalid = min(128, it.kv_len - j * 128);
+        // ---- pass 1: row max of this tile
+        float mx = -INFINITY;
+#pragma unroll 1
+        for (int c = 0; c < 128; c += 32) {
+          uint32_t v[32];
+          tmem_ld_32x32(s_addr + c, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (c + i < nvalid) mx = fmaxf(mx, __uint_as_float(v[i]));
+        }
+        // lazy rescale: keep the old reference max unless the new max exceeds it by more than 2^8
+        float alpha = 1.f;
+        bool need = false;
+        if (j == 0) {
+          m_used = mx;
+        } else if ((mx - m_used) * p.scale_log2 > 8.f) {
+          alpha = fast_exp2((m_used - mx) * p.scale_log2);
+          m_used = mx;
+          need = true;
+        }
+        const float moff = m_used * p.scale_log2;
+        // P tile may be overwritten once the P V MMAs of the previous tile have completed
+        mbar_wait(bp_empty, pe_ph ^ 1);
+        pe_ph ^= 1;
+        tc_fence_after();
+        if (__any_sync(0xffffffffu, need)) {
+          // rescale this warp's 32 rows of O in TMEM (rare)
+          const uint32_t o_addr = tmem_base + lane_addr + Cfg::O_COL;
+#pragma unroll 1
+          for (int c = 0; c < DH; c += 32) {
+            uint32_t v[32];
+            tmem_ld_32x32(o_addr + c, v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * alpha);
+            tmem_st_32x32(o_addr + c, v);
+          }
+          tmem_st_wait();
+          l *= alpha;
+        }
+        // ---- pass 2: p = exp2(s*scale - m), row sum, 16-bit P into the swizzled SMEM tile
+        float lsum = 0.f;
+#pragma unroll 1
+        for (int c = 0; c < 128; c += 32) {
+          uint32_t v[32];
+          tmem_ld_32x32(s_addr + c, v);
+          tmem_ld_wait();
+          uint32_t pk[16];
+#pragma unroll
+          for (int i = 0; i < 32; i += 2) {
+            float p0 = (c + i < nvalid) ? fast_exp2(__uint_as_float(v[i]) * p.scale_log2 - moff) : 0.f;
+            float p1 = (c + i + 1 < nvalid) ? fast_exp2(__uint_as_float(v[i + 1]) * p.scale_log2 - moff) : 0.f;
+            if (p.dtype == CSN_F16) {
+              __half2 h = __floats2half2_rn(p0, p1);
+              pk[i >> 1] = *reinterpret_cast<uint32_t*>(&h);
+              const float2 f = __half22float2(h);  // sum what the MMA will see
+              lsum += f.x + f.y;
+            } else {
+              __nv_bfloat162 h = __floats2bfloat162_rn(p0, p1);
+              pk[i >> 1] = *reinterpret_cast<uint32_t*>(&h);
+              const float2 f = __bfloat1622float2(h);
+              lsum += f.x + f.y;
+            }
+          }
+          // 32 keys = 64 B = four 16-byte chunks of row r in k-block (c >> 6); 128B swizzle: chunk ^= (r & 7)
+          uint8_t* rowp = sP_ptr + (c >> 6) * 16384 + r * 128;
+          const int chunk0 = (c & 63) >> 3;
+#pragma unroll
+          for (int t = 0; t < 4; ++t) {
+            const int ch = (chunk0 + t) ^ (r & 7);
+            *reinterpret_cast<uint4*>(rowp + ch * 16) = make_uint4(pk[4 * t], pk[4 * t + 1], pk[4 * t + 2], pk[4 * t + 3]);
+          }
+        }
+        l += lsum;
+        // S_j fully consumed; P_j visible to the tensor-core (async) proxy
+        tc_fence_before();
+        mbar_arrive(s_empty(b));
+        fence_proxy_async_smem();
+        mbar_arrive(bp_full);
+      }
+      // ---- epilogue: O / l -> 16-bit, LSE
+      mbar_wait(bo_full, of_ph);
+      of_ph ^= 1;
+      tc_fence_after();
+      const float inv_l = 1.f / l;
+      const bool valid = r < it.q_valid;
+      uint16_t* orow = reinterpret_cast<uint16_t*>(p.O) + (long long)(it.o_row0 + r) * p.ldo + it.col0;
+      const uint32_t o_addr = tmem_base + lane_addr + Cfg::O_COL;
+#pragma unroll 1
+      for (int c = 0; c < DH; c += 32) {
+        uint32_t v[32];
+        tmem_ld_32x32(o_addr + c, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; i += 8) {
+          uint32_t w4[4];
+#pragma unroll
+          for (int t = 0; t < 4; ++t) {
+            const float a = valid ? __uint_as_float(v[i + 2 * t]) * inv_l : 0.f;
+            const float bb = valid ? __uint_as_float(v[i + 2 * t + 1]) * inv_l : 0.f;
+            if (p.dtype == CSN_F16) {
+              __half2 h = __floats2half2_rn(a, bb);
+              w4[t] = *reinterpret_cast<uint32_t*>(&h);
+            } else {
+              __nv_bfloat162 h = __floats2bfloat162_rn(a, bb);
+              w4[t] = *reinterpret_cast<uint32_t*>(&h);
+            }
+          }
+          if (valid || (it.flags & 1)) *reinterpret_cast<uint4*>(orow + c + i) = make_uint4(w4[0], w4[1], w4[2], w4[3]);
+        }
+      }
+      if (p.lse && (valid || (it.flags & 1))) p.lse[it.lse_off + r] = valid ? (m_used * p.scale + __logf(l)) : 0.f;
+      tc_fence_before();
+      mbar_arrive(bo_empty);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+template <int DH>
+static int launch_attn_fwd(const CUtensorMap& tmQ, const CUtensorMap& tmK, const CUtensorMap& tmV,
+                           const AttnFwdArgs& a, cudaStream_t stream) {
+  using Cfg = AttnCfg<DH>;
+  auto kern = attn_fwd_kernel<DH>;
+  static bool configured = false;
+  if (!configured) {
+    CSN_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    configured = true;
+  }
+  const int grid = a.n_items < num_sms() ? a.n_items : num_sms();
+  kern<<<grid, 256, Cfg::SMEM_BYTES, stream>>>(tmQ, tmK, tmV, a);
+  CSN_LAUNCH_OK("attn_fwd_kernel");
+  return 0;
+}
+
+}  // namespace csn
+
+extern "C" int csn_attn_fwd(const void* Q, const void* K, const void* V, int64_t q_rows, int64_t kv_rows,
+                            int64_t width, int64_t ldq, int64_t ldk, int64_t ldv, int32_t d_head, int32_t dtype,
+                            const int32_t* items, int32_t n_items, void* O, int64_t ldo, float* lse,
+                            void* stream) {
+  using namespace csn;
+  clear_error();
+  CSN_CHECK_ARG(Q && K && V && items && O, "csn_attn_fwd: null pointer");
+  CSN_CHECK_ARG(d_head == 256 || d_head == 64, "csn_attn_fwd: d_head=%d not supported (64 or 256)", d_head);
+  CSN_CHECK_ARG(dtype == CSN_F16 || dtype == CSN_BF16, "csn_attn_fwd: 16-bit operands only");
+  CSN_CHECK_ARG((ldo * 2) % 16 == 0 && (reinterpret_cast<uintptr_t>(O) & 15) == 0, "csn_attn_fwd: O not 16B aligned");
+  if (n_items == 0) return 0;
+  CUtensorMap tmQ, tmK, tmV;
+  int rc = make_tmap_2d(&tmQ, Q, dtype, width, q_rows, ldq, 64, 128);
+  if (rc) return rc;
+  rc = make_tmap_2d(&tmK, K, dtype, width, kv_rows, ldk, 64, 128);
+  if (rc) return rc;
+  const uint32_t vrows = d_head == 256 ? 64 : 128;  // KEYS_PER_VSLOT
+  rc = make_tmap_2d(&tmV, V, dtype, width, kv_rows, ldv, 64, vrows);
+  if (rc) return rc;
+  AttnFwdArgs a;
+  a.items = reinterpret_cast<const AttnItem*>(items);
+  a.n_items = n_items;
+  a.O = O;
+  a.ldo = ldo;
+  a.lse = lse;
+  a.scale = 1.0f / sqrtf((float)d_head);
+  a.scale_log2 = a.scale * 1.4426950408889634f;
+  a.dtype = dtype;
+  const uint32_t fmt = dtype == CSN_F16 ? 0u : 1u;
+  a.idesc_qk = umma_idesc_f16(fmt, 0, 0, 128);
+  a.idesc_pv = umma_idesc_f16(fmt, 0, 1, (uint32_t)d_head);
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  if (d_head == 256) return launch_attn_fwd<256>(tmQ, tmK, tmV, a, s);
+  return launch_attn_fwd<64>(tmQ, tmK, tmV, a, s);
+}

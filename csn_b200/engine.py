@@ -91,6 +91,66 @@ class AttnContext:
     extra: dict = field(default_factory=dict)
 
 
+_ITEM_CACHE: dict = {}
+
+
+def attn_items(groups, geom: Geometry, n_head: int, d: int, device) -> torch.Tensor:
+    """Work table of csn_attn_fwd for chunked block attention: one item per
+    (block, chunk, head, 128-row query tile)."""
+    key = (tuple(groups), geom, n_head, d, str(device))
+    t = _ITEM_CACHE.get(key)
+    if t is not None:
+        return t
+    NP, CP, NC = geom.rows_pad, geom.chunk_pad, geom.n_chunks
+    tiles = CP // 128
+    rows = []
+    for g in groups:
+        for (j, qs, ks, vs) in g.blocks():
+            assert ks == vs, "fused attention reads K and V rows from the same slot"
+            for c in range(NC):
+                for h in range(n_head):
+                    for t_ in range(tiles):
+                        valid = max(0, min(128, geom.chunk - t_ * 128))
+                        rows.append((qs * NP + c * CP + t_ * 128, valid, ks * NP + c * CP, geom.chunk,
+                                     j * NP + c * CP + t_ * 128, h * d, (j * n_head + h) * NP + c * CP + t_ * 128, 1))
+    t = torch.tensor(rows, dtype=torch.int32).to(device)
+    if len(_ITEM_CACHE) > 16:
+        _ITEM_CACHE.clear()
+    _ITEM_CACHE[key] = t
+    return t
+
+
+def use_fused_attention(d: int) -> bool:
+    import os
+    return d in (64, 256) and os.environ.get("CSN_FUSED_ATTN", "1") != "0"
+
+
+def ctx_with(ctx, QKV):
+    ctx.QKV = QKV
+    return ctx
+
+
+def _scores_and_probs(ctx: "AttnContext"):
+    """Materialised path (also used by backward to rebuild P): S = QK^T/sqrt(d) -> softmax -> 16-bit P."""
+    geom, n_head, d = ctx.geom, ctx.n_head, ctx.d_head
+    NP, CP, NC = geom.rows_pad, geom.chunk_pad, geom.n_chunks
+    HD = n_head * d
+    dev, dt = ctx.Xh.device, ctx.Xh.dtype
+    Qv, Kv = ctx.QKV[:, :HD], ctx.QKV[:, HD:2 * HD]
+    Sbuf = torch.empty(ctx.n_blocks * NC * n_head * CP, CP, dtype=torch.float32, device=dev)
+    blk_sz = NC * n_head * CP * CP
+    for g in ctx.groups:
+        A = L.mat(Qv[g.q0 * NP:], L.MAJOR_K, mn_off=(0, CP, g.q_si * NP, g.q_so * NP), k_off=(d, 0, 0, 0))
+        B = L.mat(Kv[g.k0 * NP:], L.MAJOR_K, mn_off=(0, CP, g.k_si * NP, g.k_so * NP), k_off=(d, 0, 0, 0))
+        D = L.out(Sbuf[g.blk0 * NC * n_head * CP:], CP, off=(CP * CP, n_head * CP * CP, blk_sz, g.n_in * blk_sz))
+        L.gemm(A, B, D, CP, CP, d, nb=(n_head, NC, g.n_in, g.n_out), alpha=1.0 / math.sqrt(d))
+    P = torch.empty(ctx.n_blocks * NC * n_head * CP, CP, dtype=dt, device=dev)
+    rc = L.lib().csn_softmax_fwd(Sbuf.data_ptr(), P.data_ptr(), Sbuf.shape[0], CP, geom.chunk, CP, geom.chunk,
+                                 L.dtype_code(dt), L.stream_ptr())
+    L.check(rc, "csn_softmax_fwd")
+    return Sbuf, P
+
+
 def attention_forward(Xh, Xf, groups, n_slots, n_blocks, w_q, w_k, w_v, w_o, gamma, beta, geom: Geometry,
                       n_head: int, want_colsum: bool = True) -> AttnContext:
     """Forward of all blocks. Xh/Xf: packed slots [S*NP, 256] (16-bit / fp32)."""
@@ -107,29 +167,28 @@ def attention_forward(Xh, Xf, groups, n_slots, n_blocks, w_q, w_k, w_v, w_o, gam
     L.gemm(L.mat(Xh, L.MAJOR_K), L.mat(ctx.Wqkv16, L.MAJOR_K), L.out(QKV, 3 * HD), n_slots * NP, 3 * HD, 256)
     ctx.QKV = QKV
     Qv, Kv, Vv = QKV[:, :HD], QKV[:, HD:2 * HD], QKV[:, 2 * HD:]
-    # --- scores S = (Q K^T)/sqrt(d) per (block, chunk, head) -> fp32 (csa_models.py:139)
-    Sbuf = torch.empty(n_blocks * NC * n_head * CP, CP, dtype=torch.float32, device=dev)
-    blk_sz = NC * n_head * CP * CP
-    for g in groups:
-        A = L.mat(Qv[g.q0 * NP:], L.MAJOR_K, mn_off=(0, CP, g.q_si * NP, g.q_so * NP), k_off=(d, 0, 0, 0))
-        B = L.mat(Kv[g.k0 * NP:], L.MAJOR_K, mn_off=(0, CP, g.k_si * NP, g.k_so * NP), k_off=(d, 0, 0, 0))
-        D = L.out(Sbuf[g.blk0 * NC * n_head * CP:], CP, off=(CP * CP, n_head * CP * CP, blk_sz, g.n_in * blk_sz))
-        L.gemm(A, B, D, CP, CP, d, nb=(n_head, NC, g.n_in, g.n_out), alpha=1.0 / math.sqrt(d))
-    # --- softmax over the 500 valid keys of each chunk (csa_models.py:141, dropout = identity in eval)
-    P = torch.empty(n_blocks * NC * n_head * CP, CP, dtype=dt, device=dev)
-    rc = L.lib().csn_softmax_fwd(Sbuf.data_ptr(), P.data_ptr(), Sbuf.shape[0], CP, geom.chunk, CP, geom.chunk,
-                                 L.dtype_code(dt), L.stream_ptr())
-    L.check(rc, "csn_softmax_fwd")
-    ctx.P = P
-    ctx.extra["Sbuf"] = Sbuf  # scratch, reused for dP in backward
-    # --- O = P V  (csa_models.py:142); V consumed MN-major straight from the projection output
     O = torch.empty(n_blocks * NP, HD, dtype=dt, device=dev)
-    prow = NC * n_head * CP  # rows of P per block
-    for g in groups:
-        A = L.mat(P[g.blk0 * prow:], L.MAJOR_K, mn_off=(CP, n_head * CP, prow, g.n_in * prow))
-        B = L.mat(Vv[g.v0 * NP:], L.MAJOR_MN, mn_off=(d, 0, 0, 0), k_off=(0, CP, g.v_si * NP, g.v_so * NP))
-        D = L.out(O[g.blk0 * NP:], HD, off=(d, CP * HD, NP * HD, g.n_in * NP * HD))
-        L.gemm(A, B, D, CP, d, CP, nb=(n_head, NC, g.n_in, g.n_out))
+    fused = use_fused_attention(d) and all(g.k0 == g.v0 and g.k_si == g.v_si and g.k_so == g.v_so for g in groups)
+    if fused:
+        # --- fused flash-style core (csa_models.py:139-142): scores never leave TMEM
+        items = attn_items(groups, geom, n_head, d, dev)
+        lse = torch.empty(n_blocks * n_head * NP, dtype=torch.float32, device=dev)
+        rc = L.lib().csn_attn_fwd(Qv.data_ptr(), Kv.data_ptr(), Vv.data_ptr(), n_slots * NP, n_slots * NP, HD,
+                                  3 * HD, 3 * HD, 3 * HD, d, L.dtype_code(dt), items.data_ptr(), items.shape[0],
+                                  O.data_ptr(), HD, lse.data_ptr(), L.stream_ptr())
+        L.check(rc, "csn_attn_fwd")
+        ctx.extra["lse"] = lse
+    else:
+        # --- materialised path: S = (Q K^T)/sqrt(d) -> softmax over the 500 valid keys -> O = P V
+        Sbuf, P = _scores_and_probs(ctx_with(ctx, QKV))
+        ctx.P = P
+        ctx.extra["Sbuf"] = Sbuf  # scratch, reused for dP in backward
+        prow = NC * n_head * CP  # rows of P per block
+        for g in groups:
+            A = L.mat(P[g.blk0 * prow:], L.MAJOR_K, mn_off=(CP, n_head * CP, prow, g.n_in * prow))
+            B = L.mat(Vv[g.v0 * NP:], L.MAJOR_MN, mn_off=(d, 0, 0, 0), k_off=(0, CP, g.v_si * NP, g.v_so * NP))
+            D = L.out(O[g.blk0 * NP:], HD, off=(d, CP * HD, NP * HD, g.n_in * NP * HD))
+            L.gemm(A, B, D, CP, d, CP, nb=(n_head, NC, g.n_in, g.n_out))
     ctx.O = O
     # --- output projection (csa_models.py:115), residual + LayerNorm (:116-118), pooled column sums
     Z = torch.empty(n_blocks * NP, 256, dtype=torch.float32, device=dev)
@@ -188,6 +247,8 @@ def attention_backward(ctx: AttnContext, dY: torch.Tensor, need_dx: bool):
     L.gemm(L.mat(dZ16, L.MAJOR_K), L.mat(ctx.Wo16, L.MAJOR_MN), L.out(dO, HD), nblk * NP, HD, 256)
     Qv, Kv, Vv = ctx.QKV[:, :HD], ctx.QKV[:, HD:2 * HD], ctx.QKV[:, 2 * HD:]
     # --- dP = dO V^T per (block, chunk, head)
+    if ctx.P is None:   # fused forward: rebuild the probabilities (materialised backward)
+        ctx.extra["Sbuf"], ctx.P = _scores_and_probs(ctx)
     dP = ctx.extra["Sbuf"]
     blk_sz = NC * h * CP * CP
     prow = NC * h * CP

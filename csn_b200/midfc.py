@@ -85,8 +85,32 @@ def _rows_to_channel_major(rows: torch.Tensor, n_b: int, n_src_points: int, geom
 def _last_chunk_attn(ctx: E.AttnContext, blocks: int) -> torch.Tensor:
     """Attention matrix of the last chunk only (csa_models.py:125): (blocks, h, 500, 500)."""
     g = ctx.geom
+    if ctx.P is None:
+        # fused forward keeps no probabilities: rebuild the last chunk from Q, K (cheap: 1/20 of QK^T)
+        return _attn_of_chunk(ctx, blocks, g.n_chunks - 1)
     P = ctx.P.view(ctx.n_blocks, g.n_chunks, ctx.n_head, g.chunk_pad, g.chunk_pad)
     return P[:blocks, -1, :, :g.chunk, :g.chunk].float()
+
+
+def _attn_of_chunk(ctx: E.AttnContext, blocks: int, c: int) -> torch.Tensor:
+    import math
+    g, h, d = ctx.geom, ctx.n_head, ctx.d_head
+    NP, CP = g.rows_pad, g.chunk_pad
+    HD = h * d
+    dev, dt = ctx.Xh.device, ctx.Xh.dtype
+    table = {j: (qs, ks) for grp in ctx.groups for (j, qs, ks, _) in grp.blocks()}
+    S = torch.empty(blocks * h * CP, CP, dtype=torch.float32, device=dev)
+    Qv, Kv = ctx.QKV[:, :HD], ctx.QKV[:, HD:2 * HD]
+    for j in range(blocks):
+        qs, ks = table[j]
+        A = L.mat(Qv[qs * NP + c * CP:], L.MAJOR_K, k_off=(d,))
+        B = L.mat(Kv[ks * NP + c * CP:], L.MAJOR_K, k_off=(d,))
+        L.gemm(A, B, L.out(S[j * h * CP:], CP, off=(CP * CP,)), CP, CP, d, nb=(h,), alpha=1.0 / math.sqrt(d))
+    P = torch.empty(blocks * h * CP, CP, dtype=dt, device=dev)
+    rc = L.lib().csn_softmax_fwd(S.data_ptr(), P.data_ptr(), S.shape[0], CP, g.chunk, CP, g.chunk, L.dtype_code(dt),
+                                 L.stream_ptr())
+    L.check(rc, "csn_softmax_fwd")
+    return P.view(blocks, h, CP, CP)[:, :, :g.chunk, :g.chunk].float()
 
 
 # ------------------------------------------------------------------------------------------- MHA op

@@ -104,6 +104,23 @@ int csn_topk_rows(const float* scores, int64_t ld, int32_t n_rows, int32_t n_col
                   float* out_val, int64_t* out_idx, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Fused attention core  O = softmax(Q K^T / sqrt(d)) V  (flash-style: the score matrix only exists as
+ * 128x128 fp32 tiles in TMEM).  Replaces ScaledDotProductAttention.forward (csa_models.py:138-144,
+ * MinkowskiNet/models/attention.py:69-75) for every (block, head, 128-row query tile) listed in the
+ * work table `items` (int32 x 8 per item, device memory):
+ *   {q_row0, q_valid, kv_row0, kv_len, o_row0, col0, lse_off, flags}
+ * the tile's queries are rows [q_row0, q_row0+128) of Q (q_valid of them real), its keys/values rows
+ * [kv_row0, kv_row0+kv_len) of K / V, all restricted to columns [col0, col0+d_head); the result goes to
+ * rows [o_row0, ..) / columns [col0, ..) of O (16-bit) and lse[lse_off + r] = log sum_j exp(s_rj).
+ * flags bit 0: rows >= q_valid are written as zeros (padded layouts) instead of being left untouched.
+ * Q, K, V: 16-bit row-major views of `width` columns with leading dimensions ldq / ldk / ldv.
+ * d_head in {64, 256}.
+ * ------------------------------------------------------------------------------------------- */
+int csn_attn_fwd(const void* Q, const void* K, const void* V, int64_t q_rows, int64_t kv_rows, int64_t width,
+                 int64_t ldq, int64_t ldk, int64_t ldv, int32_t d_head, int32_t dtype, const int32_t* items,
+                 int32_t n_items, void* O, int64_t ldo, float* lse, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * HBM-bound pieces of the CSA/SSA layer.  Row buffers use "padded" coordinates: a shape's block has
  * rows_pad = n_chunks*chunk_pad rows; chunk c (points [c*chunk, (c+1)*chunk)) occupies rows
  * [c*chunk_pad, c*chunk_pad + chunk); pad rows are zero.  MID-FC: chunk = 500 (csa_models.py:83-90),

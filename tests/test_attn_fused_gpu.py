@@ -1,0 +1,37 @@
+"""The fused flash-style attention core (csn_attn_fwd) against the materialised tcgen05 path
+(S GEMM -> softmax -> PV GEMM), which is itself pinned to the reference golden vectors."""
+import os
+
+import pytest
+import torch
+
+from csn_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+
+def _run(fused: bool, h: int, B: int = 2):
+    from csn_b200 import midfc
+    os.environ["CSN_FUSED_ATTN"] = "1" if fused else "0"
+    try:
+        m = midfc.MultiHeadAttention(h, 256, 256, 256).cuda().eval()
+        sd = synth.midfc_state(3, h)
+        m.load_state_dict({k[len("attention."):]: v for k, v in sd.items() if k.startswith("attention.")})
+        g = synth.gen(4)
+        xq = synth.iid_features(g, B).cuda().requires_grad_(True)
+        xkv = synth.iid_features(g, B).cuda()
+        y, attn = m(xq, xkv, xkv, "test")
+        gy = torch.randn(y.shape, generator=synth.gen(5)).cuda()
+        (y * gy).sum().backward()
+        return y.detach(), attn.detach(), xq.grad.detach(), m.w_vs.weight.grad.detach()
+    finally:
+        os.environ.pop("CSN_FUSED_ATTN", None)
+
+
+@pytest.mark.parametrize("h", [1, 2])
+def test_fused_matches_materialised(h):
+    a = _run(True, h)
+    b = _run(False, h)
+    for name, x, y in zip(("y", "attn", "dx", "dWv"), a, b):
+        rel = float((x - y).norm() / y.norm())
+        assert rel < 3e-4, (name, rel)
