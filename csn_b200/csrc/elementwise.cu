@@ -175,7 +175,7 @@ struct AddLnArgs {
   void* Y16;             // optional 16-bit copy of Y (null to skip)
   float* mean; float* rstd;
   const float* gamma; const float* beta;
-  float* colsum;         // optional [n_blocks][256]: sum of Y over the valid rows (atomically accumulated)
+  float* colsum;         // optional [rows/64][256]: per-CTA partial sums of Y over its valid rows (csn_colsum_reduce adds them in a fixed order)
   long long rows;
   int block_rows;        // rows per (pair) block, e.g. 10240
   int group_rows, rows_valid;  // pad structure inside a block: row % group_rows < rows_valid is valid
@@ -241,8 +241,17 @@ __global__ void __launch_bounds__(256) add_ln_fwd_kernel(const AddLnArgs p) {
     float s = 0.f;
 #pragma unroll
     for (int w = 0; w < 8; ++w) s += red[w][c];
-    atomicAdd(p.colsum + blk * DM + c, s);
+    p.colsum[(long long)blockIdx.x * DM + c] = s;
   }
+}
+
+// out[b][c] = scale * sum_{i < parts} part[(b*parts + i)][c], fixed order (deterministic pooled means)
+__global__ void colsum_reduce_kernel(const float* __restrict__ part, float* __restrict__ out, int parts, float scale) {
+  const int b = blockIdx.x, c = threadIdx.x;
+  const float* src = part + (long long)b * parts * DM + c;
+  float s = 0.f;
+  for (int i = 0; i < parts; ++i) s += src[(long long)i * DM];
+  out[(long long)b * DM + c] = s * scale;
 }
 
 // ------------------------------------------------------------------------------------------ LayerNorm bwd
@@ -254,6 +263,7 @@ struct LnBwdArgs {
   long long rows;
   int group_rows, rows_valid, block_rows;
   int dtype;
+  const float* amax;   // optional: dY is multiplied by 2^floor(log2(128/amax)) on load (power-of-two loss scaling)
 };
 
 __global__ void __launch_bounds__(256) ln_bwd_kernel(const LnBwdArgs p) {
@@ -262,6 +272,7 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const LnBwdArgs p) {
   const long long row0 = (long long)blockIdx.x * 64;
   const float4 g0 = __ldg(reinterpret_cast<const float4*>(p.gamma) + lane), g1 = __ldg(reinterpret_cast<const float4*>(p.gamma) + 32 + lane);
   float dg[8] = {0, 0, 0, 0, 0, 0, 0, 0}, db[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  const float gscale = p.amax ? exp2f(floorf(log2f(128.f / fmaxf(__ldg(p.amax), 1e-30f)))) : 1.f;
   for (int i = 0; i < 8; ++i) {
     const long long row = row0 + warp * 8 + i;
     if (row >= p.rows) break;
@@ -281,7 +292,7 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const LnBwdArgs p) {
     const float4 za = __ldg(z4 + lane), zc = __ldg(z4 + 32 + lane);
     float xh[8] = {(za.x - mu) * rs, (za.y - mu) * rs, (za.z - mu) * rs, (za.w - mu) * rs,
                    (zc.x - mu) * rs, (zc.y - mu) * rs, (zc.z - mu) * rs, (zc.w - mu) * rs};
-    float dy[8] = {da.x, da.y, da.z, da.w, dc.x, dc.y, dc.z, dc.w};
+    float dy[8] = {da.x * gscale, da.y * gscale, da.z * gscale, da.w * gscale, dc.x * gscale, dc.y * gscale, dc.z * gscale, dc.w * gscale};
     float gm[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
     float g[8];
     float s1 = 0.f, s2 = 0.f;
@@ -372,6 +383,7 @@ struct CombineBwdArgs {
   float* dY; float* dcomp;
   long long out_b_stride, out_ch_stride;
   int n_points, chunk, chunk_pad, rows_pad;
+  float* amax;          // optional: max |dY| over everything written (atomic max on the bit pattern)
 };
 
 __global__ void __launch_bounds__(256) combine_bwd_kernel(const CombineBwdArgs p) {
@@ -399,6 +411,7 @@ __global__ void __launch_bounds__(256) combine_bwd_kernel(const CombineBwdArgs p
     pc.x *= p.pool_scale; pc.y *= p.pool_scale; pc.z *= p.pool_scale; pc.w *= p.pool_scale;
   }
   float dot = 0.f;
+  float amx = 0.f;
   for (int rr = warp; rr < 32; rr += 8) {
     const int r = r0 + rr;
     const int ii = r % p.chunk_pad;
@@ -421,7 +434,13 @@ __global__ void __launch_bounds__(256) combine_bwd_kernel(const CombineBwdArgs p
     if (p.dY) {
       float4* d4 = reinterpret_cast<float4*>(p.dY + ((long long)j * p.rows_pad + r) * DM);
       d4[lane] = a; d4[32 + lane] = c;
+      amx = fmaxf(amx, fmaxf(fmaxf(fabsf(a.x), fabsf(a.y)), fmaxf(fabsf(a.z), fabsf(a.w))));
+      amx = fmaxf(amx, fmaxf(fmaxf(fabsf(c.x), fabsf(c.y)), fmaxf(fabsf(c.z), fabsf(c.w))));
     }
+  }
+  if (p.amax && p.dY) {
+    amx = warp_max(amx);
+    if (lane == 0 && amx > 0.f) atomicMax(reinterpret_cast<int*>(p.amax), __float_as_int(amx));
   }
   if (p.dcomp && b >= 0 && p.cw_index[j] >= 0) {
     dot = warp_sum(dot);
@@ -503,15 +522,25 @@ int csn_add_ln_fwd(float* Z, const float* R, const int32_t* res_block, float* Y,
   return launch_simple(add_ln_fwd_kernel, dim3((unsigned)(rows / 64)), dim3(256), a, stream, "add_ln_fwd_kernel");
 }
 
+int csn_colsum_reduce(const float* part, float* out, int32_t n_blocks, int32_t parts, float scale, void* stream) {
+  using namespace csn;
+  clear_error();
+  CSN_CHECK_ARG(part && out, "csn_colsum_reduce: null pointer");
+  if (n_blocks == 0) return 0;
+  colsum_reduce_kernel<<<n_blocks, DM, 0, (cudaStream_t)stream>>>(part, out, parts, scale);
+  CSN_LAUNCH_OK("colsum_reduce_kernel");
+  return 0;
+}
+
 int csn_ln_bwd(const float* dY, const float* Z, const float* mean, const float* rstd, const float* gamma, float* dZ,
                void* dZ16, float* dgamma, float* dbeta, int64_t rows, int32_t block_rows, int32_t group_rows,
-               int32_t rows_valid, int32_t dtype, void* stream) {
+               int32_t rows_valid, int32_t dtype, const float* amax, void* stream) {
   using namespace csn;
   clear_error();
   CSN_CHECK_ARG(dY && Z && mean && rstd && gamma && dZ && dZ16 && dgamma && dbeta, "csn_ln_bwd: null pointer");
   CSN_CHECK_ARG(rows % 64 == 0, "csn_ln_bwd: rows must be a multiple of 64");
   if (rows == 0) return 0;
-  LnBwdArgs a{dY, Z, mean, rstd, gamma, dZ, dZ16, dgamma, dbeta, rows, group_rows, rows_valid, block_rows, dtype};
+  LnBwdArgs a{dY, Z, mean, rstd, gamma, dZ, dZ16, dgamma, dbeta, rows, group_rows, rows_valid, block_rows, dtype, amax};
   return launch_simple(ln_bwd_kernel, dim3((unsigned)(rows / 64)), dim3(256), a, stream, "ln_bwd_kernel");
 }
 
@@ -530,12 +559,12 @@ int csn_combine_fwd(const float* Y, const int32_t* blk, const float* w, float* o
 int csn_combine_bwd(const float* dOut, const float* Y, const float* dpool, const int32_t* cb, const float* cw,
                     const int32_t* cw_index, const int32_t* pb, float pool_scale, float* dY, float* dcomp,
                     int32_t n_blocks, int64_t out_b_stride, int64_t out_ch_stride, int32_t n_points, int32_t chunk,
-                    int32_t chunk_pad, int32_t rows_pad, void* stream) {
+                    int32_t chunk_pad, int32_t rows_pad, float* amax, void* stream) {
   using namespace csn;
   clear_error();
   CSN_CHECK_ARG(dOut && Y && cb && cw && cw_index && pb && (dY || dcomp), "csn_combine_bwd: null pointer");
   if (n_blocks == 0) return 0;
-  CombineBwdArgs a{dOut, Y, dpool, cb, cw, cw_index, pb, pool_scale, dY, dcomp, out_b_stride, out_ch_stride, n_points, chunk, chunk_pad, rows_pad};
+  CombineBwdArgs a{dOut, Y, dpool, cb, cw, cw_index, pb, pool_scale, dY, dcomp, out_b_stride, out_ch_stride, n_points, chunk, chunk_pad, rows_pad, amax};
   return launch_simple(combine_bwd_kernel, dim3(rows_pad / 32, n_blocks), dim3(256), a, stream, "combine_bwd_kernel");
 }
 

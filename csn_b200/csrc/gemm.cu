@@ -34,6 +34,9 @@ struct GemmArgs {
   int out_dtype, transposed, accumulate, vec_ok;
   float alpha;
   uint32_t idesc;
+  // TMA-store epilogue (row-major, non-accumulating outputs): coordinates of a batch's origin
+  int tma_store;
+  int d_row_off[4], d_col_off[4];
 };
 
 template <int BN>
@@ -44,7 +47,8 @@ struct GemmCfg {
   static constexpr int STAGES = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
   static constexpr int TMEM_COLS = (2 * BN < 32) ? 32 : 2 * BN;  // 128 / 256 / 512: powers of two
   static constexpr int BAR_BYTES = 512;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + 1024;  // +1024: alignment slack
+  static constexpr int STG_BYTES = 4 * 2 * 4096;  // epilogue staging: 4 warps x 2 buffers x (32 rows x 128 B)
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STG_BYTES + BAR_BYTES + 1024;  // +1024: alignment slack
 };
 
 struct TileCoord {
@@ -137,19 +141,20 @@ __device__ __forceinline__ void store_chunk(const GemmArgs& p, long long base, i
 template <int BN, bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-            const __grid_constant__ GemmArgs p) {
+            const __grid_constant__ CUtensorMap tmD, const __grid_constant__ GemmArgs p) {
   using Cfg = GemmCfg<BN>;
   extern __shared__ uint8_t smem_raw[];
   // SWIZZLE_128B tiles need 1024-byte alignment.
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const uint32_t smem_base = smem_u32(smem);
-  const uint32_t bar_base = smem_base + Cfg::STAGES * Cfg::STAGE_BYTES;
+  const uint32_t stg_base = smem_base + Cfg::STAGES * Cfg::STAGE_BYTES;
+  const uint32_t bar_base = stg_base + Cfg::STG_BYTES;
   // barrier layout: full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2], tmem_ptr
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (Cfg::STAGES + s); };
   auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * Cfg::STAGES + a); };
   auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * Cfg::STAGES + 2 + a); };
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES + 8 * (2 * Cfg::STAGES + 4));
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES + Cfg::STG_BYTES + 8 * (2 * Cfg::STAGES + 4));
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -257,6 +262,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     const int q = warp & 3;  // TMEM lane quadrant this warp may access
     int acc = 0;
     uint32_t acc_ph = 0;
+    int stg_flip = 0;
     for (long long t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
       const TileCoord c = decode_tile(t, p);
       const int kb0 = c.ks * p.kb_per_split;
@@ -267,6 +273,52 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       const int n0 = c.nt * BN;
       const long long base = c.b0 * p.d_off[0] + c.b1 * p.d_off[1] + c.b2 * p.d_off[2] + c.b3 * p.d_off[3];
       const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + acc * BN;
+      if (p.tma_store) {
+        // Coalesced path: each warp stages [32 rows x 128 B] slabs (128B-swizzled, conflict-free 16-byte
+        // writes) and hands them to the TMA store engine; two slabs per warp are in flight.
+        const int W = p.out_dtype == CSN_F32 ? 32 : 64;  // columns per 128-byte slab
+        const int row0 = c.b0 * p.d_row_off[0] + c.b1 * p.d_row_off[1] + c.b2 * p.d_row_off[2] + c.b3 * p.d_row_off[3] + c.mt * GEMM_BM + q * 32;
+        const int col0 = c.b0 * p.d_col_off[0] + c.b1 * p.d_col_off[1] + c.b2 * p.d_col_off[2] + c.b3 * p.d_col_off[3] + n0;
+        const bool rows_live = c.mt * GEMM_BM + q * 32 < p.M;  // warp-uniform
+#pragma unroll 1
+        for (int cc = 0; cc < BN; cc += W) {
+          if (n0 + cc >= p.N) break;
+          const uint32_t buf = stg_base + (q * 2 + stg_flip) * 4096;
+          if (lane == 0) tma_store_wait_read<1>();
+          __syncwarp();
+          uint32_t w[32];
+          if (p.out_dtype == CSN_F32) {
+            uint32_t r[32];
+            tmem_ld_32x32(taddr + cc, r);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) w[j] = __float_as_uint(has_k ? __uint_as_float(r[j]) * p.alpha : 0.f);
+          } else {
+            uint32_t r0[32], r1[32];
+            tmem_ld_32x32(taddr + cc, r0);
+            tmem_ld_32x32(taddr + cc + 32, r1);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              w[j] = pack16(has_k ? __uint_as_float(r0[2 * j]) * p.alpha : 0.f, has_k ? __uint_as_float(r0[2 * j + 1]) * p.alpha : 0.f, p.out_dtype);
+              w[16 + j] = pack16(has_k ? __uint_as_float(r1[2 * j]) * p.alpha : 0.f, has_k ? __uint_as_float(r1[2 * j + 1]) * p.alpha : 0.f, p.out_dtype);
+            }
+          }
+          const uint32_t rowaddr = buf + lane * 128;
+#pragma unroll
+          for (int ch = 0; ch < 8; ++ch) {
+            const uint32_t a = rowaddr + (((uint32_t)ch ^ ((uint32_t)lane & 7u)) << 4);
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(w[4 * ch]), "r"(w[4 * ch + 1]), "r"(w[4 * ch + 2]), "r"(w[4 * ch + 3]) : "memory");
+          }
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0 && rows_live) {
+            tma_store_2d(&tmD, buf, col0 + cc, row0);
+            tma_store_commit();
+          }
+          stg_flip ^= 1;
+        }
+      } else
 #pragma unroll 1
       for (int cc = 0; cc < BN; cc += 32) {
         if (n0 + cc >= p.N) break;  // warp-uniform
@@ -284,6 +336,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       mbar_arrive(tempty_bar(acc));
       if (++acc == 2) { acc = 0; acc_ph ^= 1; }
     }
+    if (p.tma_store && lane == 0) tma_store_wait_all();  // staged slabs must be read before the CTA exits
   }
 
   tc_fence_before();
@@ -295,8 +348,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 }
 
 template <int BN, bool A_MN, bool B_MN>
-static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmArgs& args,
-                       cudaStream_t stream) {
+static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmD,
+                       const GemmArgs& args, cudaStream_t stream) {
   using Cfg = GemmCfg<BN>;
   auto kern = gemm_kernel<BN, A_MN, B_MN>;
   static bool configured = false;
@@ -305,18 +358,18 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const Gem
     configured = true;
   }
   long long grid = args.total_tiles < num_sms() ? args.total_tiles : num_sms();
-  kern<<<(unsigned)grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, args);
+  kern<<<(unsigned)grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, tmD, args);
   CSN_LAUNCH_OK("gemm_kernel");
   return 0;
 }
 
 template <int BN>
 static int dispatch_major(bool a_mn, bool b_mn, const CUtensorMap& tmA, const CUtensorMap& tmB,
-                          const GemmArgs& args, cudaStream_t stream) {
-  if (!a_mn && !b_mn) return launch_gemm<BN, false, false>(tmA, tmB, args, stream);
-  if (!a_mn && b_mn) return launch_gemm<BN, false, true>(tmA, tmB, args, stream);
-  if (a_mn && !b_mn) return launch_gemm<BN, true, false>(tmA, tmB, args, stream);
-  return launch_gemm<BN, true, true>(tmA, tmB, args, stream);
+                          const CUtensorMap& tmD, const GemmArgs& args, cudaStream_t stream) {
+  if (!a_mn && !b_mn) return launch_gemm<BN, false, false>(tmA, tmB, tmD, args, stream);
+  if (!a_mn && b_mn) return launch_gemm<BN, false, true>(tmA, tmB, tmD, args, stream);
+  if (a_mn && !b_mn) return launch_gemm<BN, true, false>(tmA, tmB, tmD, args, stream);
+  return launch_gemm<BN, true, true>(tmA, tmB, tmD, args, stream);
 }
 
 }  // namespace csn
@@ -371,8 +424,34 @@ extern "C" int csn_gemm(const csn_mat* A, const csn_mat* B, const csn_out* D, in
   g.vec_ok = vec ? 1 : 0;
   g.idesc = umma_idesc_f16(A->dtype == CSN_F16 ? 0u : 1u, a_mn ? 1u : 0u, b_mn ? 1u : 0u, (uint32_t)BN);
 
+  // TMA-store epilogue when the output is a plain row-major tile grid: every batch origin must be a
+  // (row, col) coordinate of one 2-D view with leading dimension ld, and tiles must not spill into a
+  // neighbouring batch (M multiple of 128 / N multiple of the slab width, or a single batch).
+  CUtensorMap tmD = tmA;
+  g.tma_store = 0;
+  {
+    const int W = D->dtype == CSN_F32 ? 32 : 64;
+    const long long nbt = (long long)nb[0] * nb[1] * nb[2] * nb[3];
+    bool ok = !D->accumulate && !D->transposed && vec && D->ld >= N;
+    ok = ok && (nbt == 1 || (M % GEMM_BM == 0 && N % W == 0));
+    long long max_row = M, max_col = N;
+    for (int i = 0; i < 4 && ok; ++i) {
+      const long long ro = D->off[i] / D->ld, co = D->off[i] % D->ld;
+      if (D->off[i] < 0 || ro > 0x3fffffff) ok = false;
+      g.d_row_off[i] = (int)ro;
+      g.d_col_off[i] = (int)co;
+      max_row += ro * (nb[i] - 1);
+      max_col += co * (nb[i] - 1);
+    }
+    ok = ok && max_col <= D->ld;
+    if (ok) {
+      rc = make_tmap_2d_any(&tmD, D->ptr, D->dtype, nbt == 1 ? N : D->ld, max_row, D->ld, (uint32_t)W, 32);
+      if (rc) return rc;
+      g.tma_store = 1;
+    }
+  }
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-  if (BN == 256) return dispatch_major<256>(a_mn, b_mn, tmA, tmB, g, s);
-  if (BN == 128) return dispatch_major<128>(a_mn, b_mn, tmA, tmB, g, s);
-  return dispatch_major<64>(a_mn, b_mn, tmA, tmB, g, s);
+  if (BN == 256) return dispatch_major<256>(a_mn, b_mn, tmA, tmB, tmD, g, s);
+  if (BN == 128) return dispatch_major<128>(a_mn, b_mn, tmA, tmB, tmD, g, s);
+  return dispatch_major<64>(a_mn, b_mn, tmA, tmB, tmD, g, s);
 }

@@ -72,6 +72,24 @@ int make_tmap_2d(CUtensorMap* tm, const void* ptr, int dtype, int64_t inner, int
   return 0;
 }
 
+int make_tmap_2d_any(CUtensorMap* tm, const void* ptr, int dtype, int64_t inner, int64_t outer,
+                     int64_t ld_elems, uint32_t box_inner, uint32_t box_outer) {
+  if (dtype != CSN_F32) return make_tmap_2d(tm, ptr, dtype, inner, outer, ld_elems, box_inner, box_outer);
+  encode_tiled_fn enc = get_encode();
+  CSN_CHECK_ARG(enc != nullptr, "cuTensorMapEncodeTiled not available (no CUDA driver?)");
+  CSN_CHECK_ARG((reinterpret_cast<uintptr_t>(ptr) & 15) == 0, "tensor map: pointer not 16B aligned");
+  CSN_CHECK_ARG((ld_elems * 4) % 16 == 0, "tensor map: row stride not a 16B multiple");
+  cuuint64_t dims[2] = {(cuuint64_t)inner, (cuuint64_t)outer};
+  cuuint64_t strides[1] = {(cuuint64_t)ld_elems * 4};
+  cuuint32_t box[2] = {box_inner, box_outer};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CSN_CHECK_ARG(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(f32) failed with CUresult %d", (int)r);
+  return 0;
+}
+
 }  // namespace csn
 
 extern "C" {

@@ -21,6 +21,9 @@ int num_sms();
 // Out-of-bounds elements of a box are filled with zeros.  Returns 0 on success.
 int make_tmap_2d(CUtensorMap* tm, const void* ptr, int dtype, int64_t inner, int64_t outer,
                  int64_t ld_elems, uint32_t box_inner, uint32_t box_outer);
+// Same for any element type (CSN_F32 / CSN_F16 / CSN_BF16); box_inner * element size must be 128 B.
+int make_tmap_2d_any(CUtensorMap* tm, const void* ptr, int dtype, int64_t inner, int64_t outer,
+                     int64_t ld_elems, uint32_t box_inner, uint32_t box_outer);
 
 #define CSN_CHECK_ARG(cond, ...)   \
   do {                             \

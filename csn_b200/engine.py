@@ -83,7 +83,7 @@ class AttnContext:
     Y: torch.Tensor = None       # [blocks*NP, 256] fp32 LayerNorm output
     mean: torch.Tensor = None
     rstd: torch.Tensor = None
-    colsum: torch.Tensor = None  # [blocks, 256] sum of Y over valid rows
+    colsum: torch.Tensor = None  # [blocks, 256] mean of Y over the valid rows of each block
     Wqkv16: torch.Tensor = None
     Wo16: torch.Tensor = None
     gamma: torch.Tensor = None
@@ -201,17 +201,28 @@ def attention_forward(Xh, Xf, groups, n_slots, n_blocks, w_q, w_k, w_v, w_o, gam
     Y = torch.empty_like(Z)
     ctx.mean = torch.empty(n_blocks * NP, dtype=torch.float32, device=dev)
     ctx.rstd = torch.empty_like(ctx.mean)
-    ctx.colsum = torch.zeros(n_blocks, 256, dtype=torch.float32, device=dev) if want_colsum else None
+    parts = torch.empty(n_blocks * NP // 64, 256, dtype=torch.float32, device=dev) if want_colsum else None
     rc = L.lib().csn_add_ln_fwd(Z.data_ptr(), Xf.data_ptr(), ctx.res_block.data_ptr(), Y.data_ptr(), None,
                                 ctx.mean.data_ptr(), ctx.rstd.data_ptr(), gamma.data_ptr(), beta.data_ptr(),
-                                ctx.colsum.data_ptr() if want_colsum else None, n_blocks * NP, NP, CP, geom.chunk,
+                                parts.data_ptr() if want_colsum else None, n_blocks * NP, NP, CP, geom.chunk,
                                 1e-6, L.dtype_code(dt), L.stream_ptr())
     L.check(rc, "csn_add_ln_fwd")
+    ctx.colsum = None
+    if want_colsum:   # pooled mean over the points of every block (csa_models.py:212,219), fixed summation order
+        ctx.colsum = torch.empty(n_blocks, 256, dtype=torch.float32, device=dev)
+        rc = L.lib().csn_colsum_reduce(parts.data_ptr(), ctx.colsum.data_ptr(), n_blocks, NP // 64,
+                                       1.0 / geom.n_points, L.stream_ptr())
+        L.check(rc, "csn_colsum_reduce")
     ctx.Z, ctx.Y = Z, Y
     return ctx
 
 
-def attention_backward(ctx: AttnContext, dY: torch.Tensor, need_dx: bool):
+def _pick_split(tiles: int, kb_total: int, target: int = 296) -> int:
+    """split-K factor such that tiles*split is about two waves of 148 CTAs, each split >= 8 k-blocks."""
+    return max(1, min(-(-target // max(tiles, 1)), max(1, kb_total // 8)))
+
+
+def attention_backward(ctx: AttnContext, dY: torch.Tensor, need_dx: bool, amax: torch.Tensor = None):
     """Backward of attention_forward. dY: [blocks*NP, 256] fp32 (zero in pad rows).
     Returns dict with dWq, dWk, dWv, dWo (fp32, reference layouts), dgamma, dbeta and, if need_dx,
     dX [S*NP, 256] fp32 (padded row-major, gradient w.r.t. every slot's features)."""
@@ -224,10 +235,11 @@ def attention_backward(ctx: AttnContext, dY: torch.Tensor, need_dx: bool):
     # --- dynamic range: the backward pass is linear in dY, so it is run on s*dY with s a power of two
     #     chosen on the device (no host sync) such that max|s*dY| = 64..128; 16-bit intermediates
     #     (dZ, dO, dS, dQ|dK|dV) then sit in the normal range of fp16 instead of its subnormals.
-    amax = dY.abs().max().clamp_min(1e-30)
-    scale = torch.exp2(torch.floor(torch.log2(128.0 / amax)))
-    dY = dY * scale
-    inv_scale = 1.0 / scale
+    #     amax comes from the kernel that produced dY (csn_combine_bwd) or is reduced here; the scale
+    #     itself is applied inside csn_ln_bwd when dY is loaded.
+    if amax is None:
+        amax = dY.abs().max().reshape(1)
+    inv_scale = 1.0 / torch.exp2(torch.floor(torch.log2(128.0 / amax.clamp_min(1e-30))))
     # --- LayerNorm backward
     dZ = torch.empty_like(ctx.Z)
     dZ16 = torch.empty(nblk * NP, 256, dtype=dt, device=dev)
@@ -235,9 +247,9 @@ def attention_backward(ctx: AttnContext, dY: torch.Tensor, need_dx: bool):
     dbeta = torch.zeros(256, dtype=torch.float32, device=dev)
     rc = lib.csn_ln_bwd(dY.data_ptr(), ctx.Z.data_ptr(), ctx.mean.data_ptr(), ctx.rstd.data_ptr(),
                         ctx.gamma.data_ptr(), dZ.data_ptr(), dZ16.data_ptr(), dgamma.data_ptr(), dbeta.data_ptr(),
-                        nblk * NP, NP, CP, geom.chunk, L.dtype_code(dt), L.stream_ptr())
+                        nblk * NP, NP, CP, geom.chunk, L.dtype_code(dt), amax.data_ptr(), L.stream_ptr())
     L.check(rc, "csn_ln_bwd")
-    split = max(1, min(64, (nblk * NP) // 4096))
+    split = _pick_split(2 * ((HD + 255) // 256), nblk * NP // 64)
     # --- dWo = dZ^T O  (contraction over all rows; both operands consumed MN-major)
     dWo = torch.zeros(256, HD, dtype=torch.float32, device=dev)
     L.gemm(L.mat(dZ16, L.MAJOR_MN), L.mat(ctx.O, L.MAJOR_MN), L.out(dWo, HD, accumulate=True), 256, HD, nblk * NP,
@@ -277,21 +289,33 @@ def attention_backward(ctx: AttnContext, dY: torch.Tensor, need_dx: bool):
         L.gemm(Pk, dOm, L.out(dVv[g.blk0 * NP:], 3 * HD, off=off), CP, d, CP, nb=nb)    # dV = P^T dO
         L.gemm(dSk, Km, L.out(dQv[g.blk0 * NP:], 3 * HD, off=off), CP, d, CP, nb=nb)    # dQ = dS K
         L.gemm(dSt, Qm, L.out(dKv[g.blk0 * NP:], 3 * HD, off=off), CP, d, CP, nb=nb)    # dK = dS^T Q
-    # --- projection weight gradients: dW = sum_blocks dProj^T X[slot]
+    # --- projection weight gradients: dW = sum_blocks dProj^T X[slot]  (contraction over points, both
+    #     operands consumed MN-major; split-K sized for ~2 waves of CTAs, fp32 atomics into dWqkv)
     dWqkv = torch.zeros(3 * HD, 256, dtype=torch.float32, device=dev)
     Xh = ctx.Xh
     for g in ctx.groups:
+        same = (g.q0, g.q_si, g.q_so) == (g.k0, g.k_si, g.k_so) == (g.v0, g.v_si, g.v_so)
+        if same and g.n_out == 1 and g.q_si == 1:
+            # self blocks over consecutive slots: one long contraction for dWq|dWk|dWv together
+            Kdim = g.n_in * NP
+            A = L.mat(dQKV[g.blk0 * NP:(g.blk0 + g.n_in) * NP], L.MAJOR_MN)
+            B = L.mat(Xh[g.q0 * NP:(g.q0 + g.n_in) * NP], L.MAJOR_MN)
+            L.gemm(A, B, L.out(dWqkv, 256, accumulate=True), 3 * HD, 256, Kdim,
+                   split_k=_pick_split((3 * HD + 127) // 128, Kdim // 64))
+            continue
         nb = (g.n_in, g.n_out, 1, 1)
-        ksp = max(1, min(16, NP // 1024))
-        A = L.mat(dQv[g.blk0 * NP:], L.MAJOR_MN, k_off=(NP, g.n_in * NP))
-        B = L.mat(Xh[g.q0 * NP:], L.MAJOR_MN, k_off=(g.q_si * NP, g.q_so * NP))
-        L.gemm(A, B, L.out(dWqkv[:HD], 256, accumulate=True), HD, 256, NP, nb=nb, split_k=ksp)
-        A = L.mat(dKv[g.blk0 * NP:], L.MAJOR_MN, k_off=(NP, g.n_in * NP))
-        B = L.mat(Xh[g.k0 * NP:], L.MAJOR_MN, k_off=(g.k_si * NP, g.k_so * NP))
-        L.gemm(A, B, L.out(dWqkv[HD:2 * HD], 256, accumulate=True), HD, 256, NP, nb=nb, split_k=ksp)
-        A = L.mat(dVv[g.blk0 * NP:], L.MAJOR_MN, k_off=(NP, g.n_in * NP))
-        B = L.mat(Xh[g.v0 * NP:], L.MAJOR_MN, k_off=(g.v_si * NP, g.v_so * NP))
-        L.gemm(A, B, L.out(dWqkv[2 * HD:], 256, accumulate=True), HD, 256, NP, nb=nb, split_k=ksp)
+        nbt = g.n_in * g.n_out
+        roles = [(dQv, dWqkv[:HD], HD, g.q0, g.q_si, g.q_so)]
+        if (g.k0, g.k_si, g.k_so) == (g.v0, g.v_si, g.v_so):
+            roles.append((dQKV[:, HD:], dWqkv[HD:], 2 * HD, g.k0, g.k_si, g.k_so))
+        else:
+            roles.append((dKv, dWqkv[HD:2 * HD], HD, g.k0, g.k_si, g.k_so))
+            roles.append((dVv, dWqkv[2 * HD:], HD, g.v0, g.v_si, g.v_so))
+        for (dproj, dst, Mdim, s0, si, so) in roles:
+            A = L.mat(dproj[g.blk0 * NP:], L.MAJOR_MN, k_off=(NP, g.n_in * NP))
+            B = L.mat(Xh[s0 * NP:], L.MAJOR_MN, k_off=(si * NP, so * NP))
+            L.gemm(A, B, L.out(dst, 256, accumulate=True), Mdim, 256, NP, nb=nb,
+                   split_k=_pick_split(nbt * ((Mdim + 127) // 128), NP // 64))
     grads = {"dWq": dWqkv[:HD], "dWk": dWqkv[HD:2 * HD], "dWv": dWqkv[2 * HD:], "dWo": dWo,
              "dgamma": dgamma, "dbeta": dbeta}
     if need_dx:

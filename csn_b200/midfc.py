@@ -239,7 +239,8 @@ class _CsaFn(torch.autograd.Function):
     """CrossShapeAt.get_csa_feats (csa_models.py:209-242) / get_ssa_feats (:204-207, x_neighbors=None)."""
 
     @staticmethod
-    def forward(ctx, x, x_neighbors, wq, wk, wv, wo, gamma, beta, cq_w, cq_b, ck_w, ck_b, n_head, dt, iters, chunk):
+    def forward(ctx, x, x_neighbors, wq, wk, wv, wo, gamma, beta, cq_w, cq_b, ck_w, ck_b, n_head, dt, iters, chunk,
+                want_attn=True):
         _require_cuda(x, "x")
         _require_cuda(wq, "attention.w_qs.weight")
         dev = x.device
@@ -269,7 +270,7 @@ class _CsaFn(torch.autograd.Function):
             comp = torch.ones(B, 1, dtype=torch.float32, device=dev)
             glue = None
         else:
-            pooled = (a.colsum[:S] / geom.n_points).detach().requires_grad_(True)   # slot order (b,k)
+            pooled = a.colsum[:S].detach().clone().requires_grad_(True)   # slot order (b,k)
             loc = [t.detach().requires_grad_(True) for t in (cq_w, cq_b, ck_w, ck_b)]
             with torch.enable_grad():
                 pv = pooled.view(B, K + 1, 256)
@@ -297,7 +298,10 @@ class _CsaFn(torch.autograd.Function):
         L.check(rc, "csn_combine_fwd")
         ctx.a, ctx.glue, ctx.comp, ctx.blk = a, glue, compc, blk
         ctx.meta = (B, K, S, nblk, n_src, n_src_nb)
-        attn = _last_chunk_attn(a, S).view(B, K + 1, n_head, geom.chunk, geom.chunk)[:, 0]
+        if want_attn:
+            attn = _last_chunk_attn(a, S).view(B, K + 1, n_head, geom.chunk, geom.chunk)[:, 0]
+        else:   # every reference caller discards it
+            attn = torch.empty(0, device=dev)
         ctx.mark_non_differentiable(attn)
         return out, attn
 
@@ -332,20 +336,21 @@ class _CsaFn(torch.autograd.Function):
             dcomp = torch.zeros(B * (K + 1), dtype=torch.float32, device=dev)
             rc = lib.csn_combine_bwd(dout.data_ptr(), a.Y.data_ptr(), None, cb.data_ptr(), cw.data_ptr(), cwi.data_ptr(),
                                      pb.data_ptr(), 0.0, None, dcomp.data_ptr(), nblk, obs, ocs, geom.n_points,
-                                     geom.chunk, geom.chunk_pad, geom.rows_pad, L.stream_ptr())
+                                     geom.chunk, geom.chunk_pad, geom.rows_pad, None, L.stream_ptr())
             L.check(rc, "csn_combine_bwd(dcomp)")
             pooled, loc, comp_g = ctx.glue
             gl = torch.autograd.grad(comp_g, [pooled] + loc, dcomp.view(B, K + 1))
             dpool = gl[0].contiguous()
             grads_glue = list(gl[1:])
         dY = torch.empty(nblk * geom.rows_pad, 256, dtype=torch.float32, device=dev)
+        amax = torch.zeros(1, dtype=torch.float32, device=dev)
         rc = lib.csn_combine_bwd(dout.data_ptr(), a.Y.data_ptr(), dpool.data_ptr() if dpool is not None else None,
                                  cb.data_ptr(), cw.data_ptr(), cwi.data_ptr(), pb.data_ptr(), 1.0 / geom.n_points,
                                  dY.data_ptr(), None, nblk, obs, ocs, geom.n_points, geom.chunk, geom.chunk_pad,
-                                 geom.rows_pad, L.stream_ptr())
+                                 geom.rows_pad, amax.data_ptr(), L.stream_ptr())
         L.check(rc, "csn_combine_bwd(dY)")
         need_dx = ctx.needs_input_grad[0] or ctx.needs_input_grad[1]
-        g = E.attention_backward(a, dY, need_dx)
+        g = E.attention_backward(a, dY, need_dx, amax)
         dx = dnb = None
         if need_dx:
             G = _rows_to_channel_major(g["dX"], S, max(n_src, n_src_nb), geom).view(B, K + 1, 256, -1, 1)
@@ -355,7 +360,7 @@ class _CsaFn(torch.autograd.Function):
                 dnb = G[:, :, :, :n_src_nb].clone()
                 dnb[:, 0] = 0   # slot 0 of x_neighbors is never read (csa_models.py:214,234)
         return (dx, dnb, g["dWq"], g["dWk"], g["dWv"], g["dWo"], g["dgamma"], g["dbeta"], *grads_glue,
-                None, None, None, None)
+                None, None, None, None, None)
 
 
 class CrossShapeAt(nn.Module):
@@ -422,7 +427,7 @@ class CrossShapeAt(nn.Module):
     def get_csa_feats(self, x, x_neighbors, mode):
         """x (B,256,N,1); x_neighbors (B,K+1,256,N,1) (slot 0 = the query, skipped; CPU tensors are
         accepted and moved, like csa_models.py:216,236) -> (B,256,10000,1)."""
-        return _CsaFn.apply(x, x_neighbors, *self._csa_args())[0]
+        return _CsaFn.apply(x, x_neighbors, *self._csa_args(), False)[0]
 
     # -- retrieval (csa_models.py:244-280)
     def get_retrieval_measure(self, ssa_feats_1, ssa_feats_2):

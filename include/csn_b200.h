@@ -146,16 +146,20 @@ int csn_softmax_bwd(const void* P, const float* dP, void* dS, int64_t rows, int3
                     int32_t dtype, void* stream);
 
 /* z = Z + residual (in place); Y = LayerNorm(z)*gamma + beta with eps inside the sqrt and biased
- * variance (csa_models.py:116-118, :57); mean / rstd saved per row; colsum[block] += sum of Y over
- * the block's valid rows (the mean over points of csa_models.py:212,219, un-normalised).
+ * variance (csa_models.py:116-118, :57); mean / rstd saved per row; colsum (optional, [rows/64][256])
+ * receives per-64-row partial sums of Y over valid rows, which csn_colsum_reduce adds in a fixed order
+ * into the mean over points of csa_models.py:212,219 (deterministic, no atomics).
  * Residual row of (block, r) is R[(res_block[block]*block_rows + r)*256]. */
 int csn_add_ln_fwd(float* Z, const float* R, const int32_t* res_block, float* Y, void* Y16, float* mean,
                    float* rstd, const float* gamma, const float* beta, float* colsum, int64_t rows,
                    int32_t block_rows, int32_t group_rows, int32_t rows_valid, float eps, int32_t dtype,
                    void* stream);
+int csn_colsum_reduce(const float* part, float* out, int32_t n_blocks, int32_t parts, float scale, void* stream);
+/* amax (optional, device): dY is multiplied by the power of two 2^floor(log2(128 / *amax)) on load so
+ * that 16-bit gradient intermediates stay in the normal fp16 range; the caller divides the results. */
 int csn_ln_bwd(const float* dY, const float* Z, const float* mean, const float* rstd, const float* gamma,
                float* dZ, void* dZ16, float* dgamma, float* dbeta, int64_t rows, int32_t block_rows,
-               int32_t group_rows, int32_t rows_valid, int32_t dtype, void* stream);
+               int32_t group_rows, int32_t rows_valid, int32_t dtype, const float* amax, void* stream);
 
 /* out[b][c][n] = sum_k w[b*n_k+k] * Y[blk[b*n_k+k]][padrow(n)][c]: the compatibility-weighted sum
  * of the self- and cross-attention outputs written back channel-major (csa_models.py:232-240);
@@ -168,12 +172,13 @@ int csn_combine_fwd(const float* Y, const int32_t* blk, const float* w, float* o
 /* Backward of the above plus of the pooled means.  For block j:
  *   dY[j] = cw[j]*dOut[cb[j]]^T (if cb[j] >= 0) + pool_scale*dpool[pb[j]] (if pb[j] >= 0), valid rows;
  *   dcomp[cw_index[j]] += <dOut[cb[j]]^T, Y[j]>  (if cw_index[j] >= 0).
- * dY == NULL: only dcomp is computed; dcomp == NULL: only dY. */
+ * dY == NULL: only dcomp is computed; dcomp == NULL: only dY.  amax (optional, device, zero-initialised)
+ * receives max |dY|. */
 int csn_combine_bwd(const float* dOut, const float* Y, const float* dpool, const int32_t* cb,
                     const float* cw, const int32_t* cw_index, const int32_t* pb, float pool_scale,
                     float* dY, float* dcomp, int32_t n_blocks, int64_t out_b_stride,
                     int64_t out_ch_stride, int32_t n_points, int32_t chunk, int32_t chunk_pad,
-                    int32_t rows_pad, void* stream);
+                    int32_t rows_pad, float* amax, void* stream);
 
 #ifdef __cplusplus
 }
