@@ -1,0 +1,422 @@
+// Fused attention backward, query side (autograd of csa_models.py:139-142 / attention.py:69-75):
+//   for one 128-row query tile i and every 128-key tile j of its key range
+//     S  = Q_i K_j^T,  dP = dO_i V_j^T                         (tcgen05, fp32 in TMEM)
+//     P  = exp(S*scale - lse_i),  dS = P o (dP - delta_i) * scale   (registers, lane = query row)
+//     dQ_i += dS K_j                                           (dS staged in SMEM as the A operand;
+//                                                               K_j re-read MN-major from the same rows)
+//   dS is also written to HBM (16-bit) so that dK = dS^T Q runs as one batched csn_gemm.
+//   delta_i = rowsum(dO_i o O_i) comes from csn_attn_delta.
+// CTA layout as in attn_fwd.cu: warp 0 TMA, warp 1 MMA issuer, warp 2 TMEM allocator, warps 4-7
+// element-wise stage + epilogue. TMEM: S @0 (128 cols) | dP @128 (128) | dQ @256 (<= 256).
+#include "host_util.h"
+#include "ptx.cuh"
+
+namespace csn {
+
+__device__ __forceinline__ float fast_exp2_b(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+struct AttnBwdItem {
+  int q_row0;    // first query row in the Q view == first row of dO / dQ (block rows) is given separately
+  int q_valid;   // real query rows in the tile
+  int kv_row0;   // first key row
+  int kv_len;    // keys attended to
+  int o_row0;    // first row of this tile in dO (input) and dQ (output)
+  int col0;      // head * d
+  int stat_off;  // lse[stat_off + r], delta[stat_off + r]
+  int ds_row0;   // first row of this tile in the dS buffer
+  int ds_col0;   // first column of key tile 0 in the dS buffer
+  int flags;     // bit 0: zero-fill rows >= q_valid of dQ
+  int pad0, pad1;
+};
+
+struct AttnBwdArgs {
+  const AttnBwdItem* items;
+  int n_items;
+  void* dQ; long long lddq;
+  void* dS; long long ldds;
+  const float* lse; const float* delta;
+  float scale_log2, scale;
+  int dtype;
+  uint32_t idesc_s;   // M=128, N=128, K-major x K-major
+  uint32_t idesc_dq;  // M=128, N=128 (DH>=128) or DH, A K-major, B MN-major
+};
+
+template <int DH>
+struct BwdCfg {
+  static constexpr int KB = DH / 64;
+  static constexpr int TILE_BYTES = 128 * DH * 2;            // Q_i, dO_i resident
+  static constexpr int DS_BYTES = 128 * 128 * 2;
+  static constexpr int SLOT_BYTES = (DH >= 128) ? 32768 : 128 * DH * 2;   // [128 keys x (SLOT_BYTES/256) cols]
+  static constexpr int SLOTS_PER_TILE = (128 * DH * 2) / SLOT_BYTES;
+  static constexpr int KB_PER_SLOT = KB / SLOTS_PER_TILE;
+  static constexpr int COLS_PER_SLOT = 64 * KB_PER_SLOT;     // dQ columns produced from one K slot
+  static constexpr int NST = (DH >= 128) ? 2 : 6;
+  static constexpr int SMEM_BYTES = 2 * TILE_BYTES + DS_BYTES + NST * SLOT_BYTES + 256 + 1024;
+};
+
+template <int DH>
+__global__ void __launch_bounds__(256, 1)
+attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmDO,
+                   const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
+                   const __grid_constant__ AttnBwdArgs p) {
+  using Cfg = BwdCfg<DH>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const uint32_t sQ = smem_u32(smem);
+  const uint32_t sDO = sQ + Cfg::TILE_BYTES;
+  const uint32_t sDS = sDO + Cfg::TILE_BYTES;
+  const uint32_t sKV = sDS + Cfg::DS_BYTES;
+  const uint32_t bar_base = sKV + Cfg::NST * Cfg::SLOT_BYTES;
+  uint8_t* bar_ptr = smem + 2 * Cfg::TILE_BYTES + Cfg::DS_BYTES + Cfg::NST * Cfg::SLOT_BYTES;
+  auto kv_full = [&](int s) { return bar_base + 8u * s; };
+  auto kv_empty = [&](int s) { return bar_base + 8u * (Cfg::NST + s); };
+  const uint32_t bq_full = bar_base + 8u * (2 * Cfg::NST + 0);
+  const uint32_t bq_empty = bar_base + 8u * (2 * Cfg::NST + 1);
+  const uint32_t sdp_full = bar_base + 8u * (2 * Cfg::NST + 2);   // S and dP of tile j are in TMEM
+  const uint32_t sdp_empty = bar_base + 8u * (2 * Cfg::NST + 3);  // ... and have been read
+  const uint32_t ds_full = bar_base + 8u * (2 * Cfg::NST + 4);    // dS_j is in SMEM
+  const uint32_t ds_empty = bar_base + 8u * (2 * Cfg::NST + 5);   // dQ MMAs of tile j done reading it
+  const uint32_t dq_full = bar_base + 8u * (2 * Cfg::NST + 6);
+  const uint32_t dq_empty = bar_base + 8u * (2 * Cfg::NST + 7);
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bar_ptr + 8 * (2 * Cfg::NST + 8));
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmDO);
+    tma_prefetch_desc(&tmK);
+    tma_prefetch_desc(&tmV);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < Cfg::NST; ++s) {
+      mbar_init(kv_full(s), 1);
+      mbar_init(kv_empty(s), 1);
+    }
+    mbar_init(bq_full, 1);
+    mbar_init(bq_empty, 1);
+    mbar_init(sdp_full, 1);
+    mbar_init(sdp_empty, 128);
+    mbar_init(ds_full, 128);
+    mbar_init(ds_empty, 1);
+    mbar_init(dq_full, 1);
+    mbar_init(dq_empty, 128);
+    fence_mbar_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(smem_u32(tmem_ptr_smem), 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp == 0) {
+    // ================================================================== TMA producer
+    if (lane == 0) {
+      int st = 0;
+      uint32_t ph = 0, q_ph = 0;
+      auto load_tile = [&](const CUtensorMap* tm, int col0, int row0) {   // 128 rows x DH cols, K-major k-blocks
+#pragma unroll 1
+        for (int s = 0; s < Cfg::SLOTS_PER_TILE; ++s) {
+          mbar_wait(kv_empty(st), ph ^ 1);
+          mbar_arrive_expect_tx(kv_full(st), Cfg::SLOT_BYTES);
+#pragma unroll
+          for (int kb = 0; kb < Cfg::KB_PER_SLOT; ++kb)
+            tma_load_2d(sKV + st * Cfg::SLOT_BYTES + kb * 16384, tm, kv_full(st), col0 + (s * Cfg::KB_PER_SLOT + kb) * 64, row0);
+          if (++st == Cfg::NST) { st = 0; ph ^= 1; }
+        }
+      };
+      for (int w = blockIdx.x; w < p.n_items; w += gridDim.x) {
+        const AttnBwdItem it = p.items[w];
+        const int nkv = (it.kv_len + 127) >> 7;
+        mbar_wait(bq_empty, q_ph ^ 1);
+        mbar_arrive_expect_tx(bq_full, 2 * Cfg::TILE_BYTES);
+#pragma unroll
+        for (int kb = 0; kb < Cfg::KB; ++kb) {
+          tma_load_2d(sQ + kb * 16384, &tmQ, bq_full, it.col0 + kb * 64, it.q_row0);
+          tma_load_2d(sDO + kb * 16384, &tmDO, bq_full, it.col0 + kb * 64, it.o_row0);
+        }
+        q_ph ^= 1;
+        for (int j = 0; j < nkv; ++j) {
+          load_tile(&tmK, it.col0, it.kv_row0 + j * 128);   // for S
+          load_tile(&tmV, it.col0, it.kv_row0 + j * 128);   // for dP
+          load_tile(&tmK, it.col0, it.kv_row0 + j * 128);   // for dQ (same bytes, consumed MN-major)
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================================================================== MMA issuer
+    if (lane == 0) {
+      int st = 0;
+      uint32_t ph = 0, q_ph = 0, sdp_ph = 0, ds_ph = 0, dq_ph = 0;
+      auto mma_kmajor = [&](uint32_t a_base, uint32_t d_tmem) {   // D = A_tile (resident) x slots^T
+#pragma unroll 1
+        for (int s = 0; s < Cfg::SLOTS_PER_TILE; ++s) {
+          mbar_wait(kv_full(st), ph);
+          tc_fence_after();
+#pragma unroll
+          for (int kb = 0; kb < Cfg::KB_PER_SLOT; ++kb) {
+            const uint32_t a_tile = a_base + (s * Cfg::KB_PER_SLOT + kb) * 16384;
+            const uint32_t b_tile = sKV + st * Cfg::SLOT_BYTES + kb * 16384;
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              umma_f16_ss(d_tmem, umma_desc_sw128(a_tile + k * 32, 0, 1024), umma_desc_sw128(b_tile + k * 32, 0, 1024),
+                          p.idesc_s, (s | kb | k) ? 1u : 0u);
+          }
+          umma_commit(kv_empty(st));
+          if (++st == Cfg::NST) { st = 0; ph ^= 1; }
+        }
+      };
+      for (int w = blockIdx.x; w < p.n_items; w += gridDim.x) {
+        const AttnBwdItem it = p.items[w];
+        const int nkv = (it.kv_len + 127) >> 7;
+        mbar_wait(bq_full, q_ph);
+        q_ph ^= 1;
+        tc_fence_after();
+        for (int j = 0; j < nkv; ++j) {
+          mbar_wait(sdp_empty, sdp_ph ^ 1);   // S / dP of the previous tile have been read
+          tc_fence_after();
+          mma_kmajor(sQ, tmem_base + 0);      // S  = Q  K_j^T
+          mma_kmajor(sDO, tmem_base + 128);   // dP = dO V_j^T
+          umma_commit(sdp_full);
+          if (j == nkv - 1) umma_commit(bq_empty);   // Q_i / dO_i are not read by the dQ MMAs
+          sdp_ph ^= 1;
+          mbar_wait(ds_full, ds_ph);          // dS_j staged
+          ds_ph ^= 1;
+          if (j == 0) mbar_wait(dq_empty, dq_ph ^ 1);   // previous item's dQ has been read out
+          tc_fence_after();
+#pragma unroll 1
+          for (int s = 0; s < Cfg::SLOTS_PER_TILE; ++s) {
+            mbar_wait(kv_full(st), ph);
+            tc_fence_after();
+            const uint32_t k_tile = sKV + st * Cfg::SLOT_BYTES;
+            const uint32_t d_tmem = tmem_base + 256 + s * Cfg::COLS_PER_SLOT;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {   // 128 keys in steps of 16
+              const uint32_t a_addr = sDS + (k >> 2) * 16384 + (k & 3) * 32;
+              umma_f16_ss(d_tmem, umma_desc_sw128(a_addr, 0, 1024), umma_desc_sw128(k_tile + k * 2048, 16384, 1024),
+                          p.idesc_dq, (j | k) ? 1u : 0u);
+            }
+            umma_commit(kv_empty(st));
+            if (++st == Cfg::NST) { st = 0; ph ^= 1; }
+          }
+          umma_commit(ds_empty);
+        }
+        umma_commit(dq_full);
+        dq_ph ^= 1;
+      }
+    }
+  } else if (warp >= 4) {
+    // ================================================================== element-wise stage + epilogue
+    const int q = warp & 3;
+    const int r = q * 32 + lane;
+    const uint32_t lane_addr = uint32_t(q * 32) << 16;
+    uint32_t sdp_ph = 0, dse_ph = 0, dqf_ph = 0;
+    uint8_t* sDS_ptr = smem + 2 * Cfg::TILE_BYTES;
+    constexpr float LOG2E = 1.4426950408889634f;
+    auto pack_pair = [&](float a, float b) -> uint32_t {
+      if (p.dtype == CSN_F16) {
+        __half2 h = __floats2half2_rn(a, b);
+        return *reinterpret_cast<uint32_t*>(&h);
+      }
+      __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+      return *reinterpret_cast<uint32_t*>(&h);
+    };
+    for (int w = blockIdx.x; w < p.n_items; w += gridDim.x) {
+      const AttnBwdItem it = p.items[w];
+      const int nkv = (it.kv_len + 127) >> 7;
+      const bool valid = r < it.q_valid;
+      const float lse_l2 = valid ? p.lse[it.stat_off + r] * LOG2E : 0.f;
+      const float dlt = valid ? p.delta[it.stat_off + r] : 0.f;
+      uint16_t* ds_row = reinterpret_cast<uint16_t*>(p.dS) + (long long)(it.ds_row0 + r) * p.ldds + it.ds_col0;
+      for (int j = 0; j < nkv; ++j) {
+        mbar_wait(sdp_full, sdp_ph);
+        sdp_ph ^= 1;
+        tc_fence_after();
+        const uint32_t s_addr = tmem_base + lane_addr;
+        const int nvalid = min(128, it.kv_len - j * 128);
+        bool waited = false;
+#pragma unroll 1
+        for (int c = 0; c < 128; c += 32) {
+          uint32_t sv[32], dv[32];
+          tmem_ld_32x32(s_addr + c, sv);
+          tmem_ld_32x32(s_addr + 128 + c, dv);
+          tmem_ld_wait();
+          uint32_t pk[16];
+#pragma unroll
+          for (int i = 0; i < 32; i += 2) {
+            float d0 = 0.f, d1 = 0.f;
+            if (valid && c + i < nvalid)
+              d0 = fast_exp2_b(__uint_as_float(sv[i]) * p.scale_log2 - lse_l2) * (__uint_as_float(dv[i]) - dlt) * p.scale;
+            if (valid && c + i + 1 < nvalid)
+              d1 = fast_exp2_b(__uint_as_float(sv[i + 1]) * p.scale_log2 - lse_l2) * (__uint_as_float(dv[i + 1]) - dlt) * p.scale;
+            pk[i >> 1] = pack_pair(d0, d1);
+          }
+          if (!waited) {
+            mbar_wait(ds_empty, dse_ph ^ 1);   // dQ MMAs of the previous tile no longer read the staging tile
+            dse_ph ^= 1;
+            waited = true;
+          }
+          uint8_t* rowp = sDS_ptr + (c >> 6) * 16384 + r * 128;
+          const int chunk0 = (c & 63) >> 3;
+#pragma unroll
+          for (int t = 0; t < 4; ++t) {
+            const int ch = (chunk0 + t) ^ (r & 7);
+            const uint4 val = make_uint4(pk[4 * t], pk[4 * t + 1], pk[4 * t + 2], pk[4 * t + 3]);
+            *reinterpret_cast<uint4*>(rowp + ch * 16) = val;
+            *reinterpret_cast<uint4*>(ds_row + j * 128 + c + t * 8) = val;   // HBM copy for dK = dS^T Q
+          }
+        }
+        tc_fence_before();
+        mbar_arrive(sdp_empty);
+        fence_proxy_async_smem();
+        mbar_arrive(ds_full);
+      }
+      // ---- epilogue: dQ tile -> 16-bit
+      mbar_wait(dq_full, dqf_ph);
+      dqf_ph ^= 1;
+      tc_fence_after();
+      uint16_t* orow = reinterpret_cast<uint16_t*>(p.dQ) + (long long)(it.o_row0 + r) * p.lddq + it.col0;
+      const uint32_t o_addr = tmem_base + lane_addr + 256;
+#pragma unroll 1
+      for (int c = 0; c < DH; c += 32) {
+        uint32_t v[32];
+        tmem_ld_32x32(o_addr + c, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; i += 8) {
+          uint32_t w4[4];
+#pragma unroll
+          for (int t = 0; t < 4; ++t)
+            w4[t] = pack_pair(valid ? __uint_as_float(v[i + 2 * t]) : 0.f, valid ? __uint_as_float(v[i + 2 * t + 1]) : 0.f);
+          if (valid || (it.flags & 1)) *reinterpret_cast<uint4*>(orow + c + i) = make_uint4(w4[0], w4[1], w4[2], w4[3]);
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(dq_empty);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// delta[(blk*h + head)*rows_pad + row] = sum_c dO[blk*rows_pad + row][head*d + c] * O[...]; one warp per (row, head)
+__global__ void attn_delta_kernel(const void* __restrict__ dO, const void* __restrict__ O, const void* __restrict__ Olo,
+                                  float* __restrict__ delta, long long rows, int rows_pad, int n_head, int d,
+                                  long long ld, int dtype) {
+  const long long wid = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (wid >= rows * n_head) return;
+  const long long row = wid / n_head;
+  const int head = (int)(wid % n_head);
+  const uint32_t* a = reinterpret_cast<const uint32_t*>(reinterpret_cast<const uint16_t*>(dO) + row * ld + head * d);
+  const uint32_t* b = reinterpret_cast<const uint32_t*>(reinterpret_cast<const uint16_t*>(O) + row * ld + head * d);
+  const uint32_t* bl = Olo ? reinterpret_cast<const uint32_t*>(reinterpret_cast<const uint16_t*>(Olo) + row * ld + head * d) : nullptr;
+  const float lo_inv = dtype == CSN_F16 ? 1.f / 2048.f : 1.f / 256.f;
+  float s = 0.f, sl = 0.f;
+  for (int c = lane; c < d / 2; c += 32) {
+    const uint32_t x = __ldg(a + c), y = __ldg(b + c);
+    const uint32_t z = bl ? __ldg(bl + c) : 0u;
+    float2 fx, fy, fz;
+    if (dtype == CSN_F16) {
+      fx = __half22float2(*reinterpret_cast<const __half2*>(&x));
+      fy = __half22float2(*reinterpret_cast<const __half2*>(&y));
+      fz = __half22float2(*reinterpret_cast<const __half2*>(&z));
+    } else {
+      fx = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&x));
+      fy = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&y));
+      fz = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&z));
+    }
+    s += fx.x * fy.x + fx.y * fy.y;
+    sl += fx.x * fz.x + fx.y * fz.y;
+  }
+  s = warp_sum(s) + warp_sum(sl) * lo_inv;
+  if (lane == 0) {
+    const long long blk = row / rows_pad, rin = row % rows_pad;
+    delta[(blk * n_head + head) * rows_pad + rin] = s;
+  }
+}
+
+template <int DH>
+static int launch_dq(const CUtensorMap& tmQ, const CUtensorMap& tmDO, const CUtensorMap& tmK, const CUtensorMap& tmV,
+                     const AttnBwdArgs& a, cudaStream_t stream) {
+  using Cfg = BwdCfg<DH>;
+  auto kern = attn_bwd_dq_kernel<DH>;
+  static bool configured = false;
+  if (!configured) {
+    CSN_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    configured = true;
+  }
+  const int grid = a.n_items < num_sms() ? a.n_items : num_sms();
+  kern<<<grid, 256, Cfg::SMEM_BYTES, stream>>>(tmQ, tmDO, tmK, tmV, a);
+  CSN_LAUNCH_OK("attn_bwd_dq_kernel");
+  return 0;
+}
+
+}  // namespace csn
+
+extern "C" {
+
+int csn_attn_delta(const void* dO, const void* O, const void* O_lo, float* delta, int64_t rows, int32_t rows_pad, int32_t n_head,
+                   int32_t d_head, int64_t ld, int32_t dtype, void* stream) {
+  using namespace csn;
+  clear_error();
+  CSN_CHECK_ARG(dO && O && delta, "csn_attn_delta: null pointer");
+  CSN_CHECK_ARG(d_head % 64 == 0, "csn_attn_delta: d_head must be a multiple of 64");
+  const long long nw = rows * n_head;
+  if (nw == 0) return 0;
+  const int wpb = 8;
+  attn_delta_kernel<<<(unsigned)((nw + wpb - 1) / wpb), wpb * 32, 0, (cudaStream_t)stream>>>(dO, O, O_lo, delta, rows, rows_pad, n_head, d_head, ld, dtype);
+  CSN_LAUNCH_OK("attn_delta_kernel");
+  return 0;
+}
+
+int csn_attn_bwd_dq(const void* Q, const void* dO, const void* K, const void* V, int64_t q_rows, int64_t do_rows,
+                    int64_t kv_rows, int64_t width, int64_t ldq, int64_t lddo, int64_t ldk, int64_t ldv,
+                    int32_t d_head, int32_t dtype, const int32_t* items, int32_t n_items, void* dQ, int64_t lddq,
+                    void* dS, int64_t ldds, const float* lse, const float* delta, void* stream) {
+  using namespace csn;
+  clear_error();
+  CSN_CHECK_ARG(Q && dO && K && V && items && dQ && dS && lse && delta, "csn_attn_bwd_dq: null pointer");
+  CSN_CHECK_ARG(d_head == 256 || d_head == 64, "csn_attn_bwd_dq: d_head=%d not supported (64 or 256)", d_head);
+  CSN_CHECK_ARG(dtype == CSN_F16 || dtype == CSN_BF16, "csn_attn_bwd_dq: 16-bit operands only");
+  CSN_CHECK_ARG((lddq * 2) % 16 == 0 && (ldds * 2) % 16 == 0, "csn_attn_bwd_dq: output strides must be 16B multiples");
+  if (n_items == 0) return 0;
+  CUtensorMap tmQ, tmDO, tmK, tmV;
+  int rc = make_tmap_2d(&tmQ, Q, dtype, width, q_rows, ldq, 64, 128);
+  if (rc) return rc;
+  rc = make_tmap_2d(&tmDO, dO, dtype, width, do_rows, lddo, 64, 128);
+  if (rc) return rc;
+  rc = make_tmap_2d(&tmK, K, dtype, width, kv_rows, ldk, 64, 128);
+  if (rc) return rc;
+  rc = make_tmap_2d(&tmV, V, dtype, width, kv_rows, ldv, 64, 128);
+  if (rc) return rc;
+  AttnBwdArgs a;
+  a.items = reinterpret_cast<const AttnBwdItem*>(items);
+  a.n_items = n_items;
+  a.dQ = dQ; a.lddq = lddq; a.dS = dS; a.ldds = ldds;
+  a.lse = lse; a.delta = delta;
+  a.scale = 1.0f / sqrtf((float)d_head);
+  a.scale_log2 = a.scale * 1.4426950408889634f;
+  a.dtype = dtype;
+  const uint32_t fmt = dtype == CSN_F16 ? 0u : 1u;
+  a.idesc_s = umma_idesc_f16(fmt, 0, 0, 128);
+  a.idesc_dq = umma_idesc_f16(fmt, 0, 1, d_head == 256 ? 128u : 64u);
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  if (d_head == 256) return launch_dq<256>(tmQ, tmDO, tmK, tmV, a, s);
+  return launch_dq<64>(tmQ, tmDO, tmK, tmV, a, s);
+}
+
+}  // extern "C"

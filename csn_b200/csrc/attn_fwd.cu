@@ -35,12 +35,16 @@ struct AttnItem {
   int col0;      // head * d: column offset in the Q/K/V views and in O
   int lse_off;   // lse[lse_off + r] for row r of the tile
   int flags;     // bit 0: write zeros to the tile rows >= q_valid (padded layouts); else leave them untouched
+  int v_row0;    // first row of the MN-major streamed operand (V; dO in dV mode) matching kv_row0
+  int pad;
 };
 
 struct AttnFwdArgs {
   const AttnItem* items;
   int n_items;
   void* O;            // 16-bit [rows][ldo]
+  void* Olo;          // optional 16-bit residual (o - round16(o)) * 2^11 (fp16) / 2^8 (bf16), same layout as O:
+                      // lets the backward pass form delta = rowsum(dO o O) to ~22 bits
   long long ldo;
   float* lse;         // natural-log sum-exp of the scaled scores per query row
   float scale_log2;   // (1/sqrt(d)) * log2(e)
@@ -68,7 +72,7 @@ struct AttnCfg {
   static constexpr int O_COL = 256;                        // TMEM: S0 @0, S1 @128, O @256 (DH <= 256)
 };
 
-template <int DH>
+template <int DH, int MODE>
 __global__ void __launch_bounds__(256, 1)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                 const __grid_constant__ CUtensorMap tmV, const __grid_constant__ AttnFwdArgs p) {
@@ -152,7 +156,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 #pragma unroll
           for (int a = 0; a < Cfg::KB; ++a)
             tma_load_2d(sKV + st * Cfg::SLOT_BYTES + a * (Cfg::KEYS_PER_VSLOT * 128), &tmV, kv_full(st),
-                        it.col0 + a * 64, it.kv_row0 + j * 128 + s * Cfg::KEYS_PER_VSLOT);
+                        it.col0 + a * 64, it.v_row0 + j * 128 + s * Cfg::KEYS_PER_VSLOT);
           if (++st == Cfg::NST) { st = 0; ph ^= 1; }
         }
       };
@@ -247,6 +251,24 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     uint32_t s_ph[2] = {0, 0};
     uint32_t pe_ph = 0, of_ph = 0;
     uint8_t* sP_ptr = smem + Cfg::Q_BYTES;
+    constexpr float LOG2E = 1.4426950408889634f;
+    // 64 columns (two tcgen05.ld in flight) -> 16-bit pairs -> the swizzled A-operand tile of the P V MMA
+    auto store_p64 = [&](int c, const uint32_t (&pk)[32]) {
+      uint8_t* rowp = sP_ptr + (c >> 6) * 16384 + r * 128;
+#pragma unroll
+      for (int t = 0; t < 8; ++t) {
+        const int ch = t ^ (r & 7);
+        *reinterpret_cast<uint4*>(rowp + ch * 16) = make_uint4(pk[4 * t], pk[4 * t + 1], pk[4 * t + 2], pk[4 * t + 3]);
+      }
+    };
+    auto pack_pair = [&](float a, float b) -> uint32_t {
+      if (p.dtype == CSN_F16) {
+        __half2 h = __floats2half2_rn(a, b);
+        return *reinterpret_cast<uint32_t*>(&h);
+      }
+      __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+      return *reinterpret_cast<uint32_t*>(&h);
+    };
     for (int w = blockIdx.x; w < p.n_items; w += gridDim.x) {
       const AttnItem it = p.items[w];
       const int nkv = (it.kv_len + 127) >> 7;
@@ -259,94 +281,146 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         tc_fence_after();
         const uint32_t s_addr = tmem_base + lane_addr + b * 128;
         const int nvalid = min(128, it.kv_len - j * 128);
-        // ---- pass 1: row max of this tile
-        float mx = -INFINITY;
+        bool waited_p = false;
+        if (MODE == 1) {
+          // ---- dV mode: P^T[key][query] = exp(s*scale - lse[query]); statistics come from the forward pass
+          const float* lse_t = p.lse + it.lse_off + j * 128;
 #pragma unroll 1
-        for (int c = 0; c < 128; c += 32) {
-          uint32_t v[32];
-          tmem_ld_32x32(s_addr + c, v);
-          tmem_ld_wait();
-#pragma unroll
-          for (int i = 0; i < 32; ++i)
-            if (c + i < nvalid) mx = fmaxf(mx, __uint_as_float(v[i]));
-        }
-        // lazy rescale: keep the old reference max unless the new max exceeds it by more than 2^8
-        float alpha = 1.f;
-        bool need = false;
-        if (j == 0) {
-          m_used = mx;
-        } else if ((mx - m_used) * p.scale_log2 > 8.f) {
-          alpha = fast_exp2((m_used - mx) * p.scale_log2);
-          m_used = mx;
-          need = true;
-        }
-        const float moff = m_used * p.scale_log2;
-        // P tile may be overwritten once the P V MMAs of the previous tile have completed
-        mbar_wait(bp_empty, pe_ph ^ 1);
-        pe_ph ^= 1;
-        tc_fence_after();
-        if (__any_sync(0xffffffffu, need)) {
-          // rescale this warp's 32 rows of O in TMEM (rare)
-          const uint32_t o_addr = tmem_base + lane_addr + Cfg::O_COL;
-#pragma unroll 1
-          for (int c = 0; c < DH; c += 32) {
-            uint32_t v[32];
-            tmem_ld_32x32(o_addr + c, v);
+          for (int c = 0; c < 128; c += 64) {
+            uint32_t v0[32], v1[32];
+            tmem_ld_32x32(s_addr + c, v0);
+            tmem_ld_32x32(s_addr + c + 32, v1);
             tmem_ld_wait();
+            uint32_t pk[32];
 #pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * alpha);
-            tmem_st_32x32(o_addr + c, v);
-          }
-          tmem_st_wait();
-          l *= alpha;
-        }
-        // ---- pass 2: p = exp2(s*scale - m), row sum, 16-bit P into the swizzled SMEM tile
-        float lsum = 0.f;
-#pragma unroll 1
-        for (int c = 0; c < 128; c += 32) {
-          uint32_t v[32];
-          tmem_ld_32x32(s_addr + c, v);
-          tmem_ld_wait();
-          uint32_t pk[16];
-#pragma unroll
-          for (int i = 0; i < 32; i += 2) {
-            float p0 = (c + i < nvalid) ? fast_exp2(__uint_as_float(v[i]) * p.scale_log2 - moff) : 0.f;
-            float p1 = (c + i + 1 < nvalid) ? fast_exp2(__uint_as_float(v[i + 1]) * p.scale_log2 - moff) : 0.f;
-            if (p.dtype == CSN_F16) {
-              __half2 h = __floats2half2_rn(p0, p1);
-              pk[i >> 1] = *reinterpret_cast<uint32_t*>(&h);
-              const float2 f = __half22float2(h);  // sum what the MMA will see
-              lsum += f.x + f.y;
-            } else {
-              __nv_bfloat162 h = __floats2bfloat162_rn(p0, p1);
-              pk[i >> 1] = *reinterpret_cast<uint32_t*>(&h);
-              const float2 f = __bfloat1622float2(h);
-              lsum += f.x + f.y;
+            for (int i = 0; i < 32; i += 2) {
+              const float a0 = (c + i < nvalid) ? fast_exp2(__uint_as_float(v0[i]) * p.scale_log2 - __ldg(lse_t + c + i) * LOG2E) : 0.f;
+              const float a1 = (c + i + 1 < nvalid) ? fast_exp2(__uint_as_float(v0[i + 1]) * p.scale_log2 - __ldg(lse_t + c + i + 1) * LOG2E) : 0.f;
+              const float b0 = (c + 32 + i < nvalid) ? fast_exp2(__uint_as_float(v1[i]) * p.scale_log2 - __ldg(lse_t + c + 32 + i) * LOG2E) : 0.f;
+              const float b1 = (c + 33 + i < nvalid) ? fast_exp2(__uint_as_float(v1[i + 1]) * p.scale_log2 - __ldg(lse_t + c + 33 + i) * LOG2E) : 0.f;
+              pk[i >> 1] = pack_pair(a0, a1);
+              pk[16 + (i >> 1)] = pack_pair(b0, b1);
             }
+            if (!waited_p) {
+              mbar_wait(bp_empty, pe_ph ^ 1);
+              pe_ph ^= 1;
+              waited_p = true;
+            }
+            store_p64(c, pk);
           }
-          // 32 keys = 64 B = four 16-byte chunks of row r in k-block (c >> 6); 128B swizzle: chunk ^= (r & 7)
-          uint8_t* rowp = sP_ptr + (c >> 6) * 16384 + r * 128;
-          const int chunk0 = (c & 63) >> 3;
+        } else {
+          // ---- forward: online softmax. Tile 0 takes the exact row max first; later tiles are
+          //      exponentiated optimistically against the running reference max and only redone
+          //      (two-pass + rescale of O) if some score exceeds it by more than 2^8.
+          bool two_pass = (j == 0);
+          float alpha = 1.f;
+          bool need = false;
+          float lsum;
+          for (;;) {
+            if (two_pass) {
+              float mx = -INFINITY;
+#pragma unroll 1
+              for (int c = 0; c < 128; c += 64) {
+                uint32_t v0[32], v1[32];
+                tmem_ld_32x32(s_addr + c, v0);
+                tmem_ld_32x32(s_addr + c + 32, v1);
+                tmem_ld_wait();
 #pragma unroll
-          for (int t = 0; t < 4; ++t) {
-            const int ch = (chunk0 + t) ^ (r & 7);
-            *reinterpret_cast<uint4*>(rowp + ch * 16) = make_uint4(pk[4 * t], pk[4 * t + 1], pk[4 * t + 2], pk[4 * t + 3]);
+                for (int i = 0; i < 32; ++i) {
+                  if (c + i < nvalid) mx = fmaxf(mx, __uint_as_float(v0[i]));
+                  if (c + 32 + i < nvalid) mx = fmaxf(mx, __uint_as_float(v1[i]));
+                }
+              }
+              if (j == 0) {
+                m_used = mx;
+              } else if ((mx - m_used) * p.scale_log2 > 8.f) {
+                alpha = fast_exp2((m_used - mx) * p.scale_log2);
+                m_used = mx;
+                need = true;
+              }
+            }
+            const float moff = m_used * p.scale_log2;
+            lsum = 0.f;
+            float cmax = -INFINITY;
+#pragma unroll 1
+            for (int c = 0; c < 128; c += 64) {
+              uint32_t v0[32], v1[32];
+              tmem_ld_32x32(s_addr + c, v0);
+              tmem_ld_32x32(s_addr + c + 32, v1);
+              tmem_ld_wait();
+              uint32_t pk[32];
+              if (nvalid == 128) {
+#pragma unroll
+                for (int i = 0; i < 32; i += 2) {
+                  const float s0 = __uint_as_float(v0[i]), s1 = __uint_as_float(v0[i + 1]);
+                  const float t0 = __uint_as_float(v1[i]), t1 = __uint_as_float(v1[i + 1]);
+                  cmax = fmaxf(cmax, fmaxf(fmaxf(s0, s1), fmaxf(t0, t1)));
+                  const float a0 = fast_exp2(s0 * p.scale_log2 - moff), a1 = fast_exp2(s1 * p.scale_log2 - moff);
+                  const float b0 = fast_exp2(t0 * p.scale_log2 - moff), b1 = fast_exp2(t1 * p.scale_log2 - moff);
+                  lsum += (a0 + a1) + (b0 + b1);
+                  pk[i >> 1] = pack_pair(a0, a1);
+                  pk[16 + (i >> 1)] = pack_pair(b0, b1);
+                }
+              } else {
+#pragma unroll
+                for (int i = 0; i < 32; i += 2) {
+                  const float s0 = (c + i < nvalid) ? __uint_as_float(v0[i]) : -INFINITY;
+                  const float s1 = (c + i + 1 < nvalid) ? __uint_as_float(v0[i + 1]) : -INFINITY;
+                  const float t0 = (c + 32 + i < nvalid) ? __uint_as_float(v1[i]) : -INFINITY;
+                  const float t1 = (c + 33 + i < nvalid) ? __uint_as_float(v1[i + 1]) : -INFINITY;
+                  cmax = fmaxf(cmax, fmaxf(fmaxf(s0, s1), fmaxf(t0, t1)));
+                  const float a0 = fast_exp2(s0 * p.scale_log2 - moff), a1 = fast_exp2(s1 * p.scale_log2 - moff);
+                  const float b0 = fast_exp2(t0 * p.scale_log2 - moff), b1 = fast_exp2(t1 * p.scale_log2 - moff);
+                  lsum += (a0 + a1) + (b0 + b1);
+                  pk[i >> 1] = pack_pair(a0, a1);
+                  pk[16 + (i >> 1)] = pack_pair(b0, b1);
+                }
+              }
+              if (!waited_p) {
+                // P tile may be overwritten once the P V MMAs of the previous tile have completed
+                mbar_wait(bp_empty, pe_ph ^ 1);
+                pe_ph ^= 1;
+                waited_p = true;
+              }
+              store_p64(c, pk);
+            }
+            const bool exceeded = !two_pass && (cmax - m_used) * p.scale_log2 > 8.f;
+            if (!__any_sync(0xffffffffu, exceeded)) break;
+            two_pass = true;  // rare: redo this tile against the new maximum
           }
+          tc_fence_after();
+          if (__any_sync(0xffffffffu, need)) {
+            // rescale this warp's 32 rows of O in TMEM (rare); P V of the previous tile has completed
+            const uint32_t o_addr = tmem_base + lane_addr + Cfg::O_COL;
+#pragma unroll 1
+            for (int c = 0; c < DH; c += 32) {
+              uint32_t v[32];
+              tmem_ld_32x32(o_addr + c, v);
+              tmem_ld_wait();
+#pragma unroll
+              for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * alpha);
+              tmem_st_32x32(o_addr + c, v);
+            }
+            tmem_st_wait();
+            l *= alpha;
+          }
+          l += lsum;
         }
-        l += lsum;
         // S_j fully consumed; P_j visible to the tensor-core (async) proxy
         tc_fence_before();
         mbar_arrive(s_empty(b));
         fence_proxy_async_smem();
         mbar_arrive(bp_full);
       }
-      // ---- epilogue: O / l -> 16-bit, LSE
+      // ---- epilogue: O / l -> 16-bit, LSE   (dV mode: the accumulator as is)
       mbar_wait(bo_full, of_ph);
       of_ph ^= 1;
       tc_fence_after();
-      const float inv_l = 1.f / l;
+      const float inv_l = (MODE == 1) ? 1.f : 1.f / l;
       const bool valid = r < it.q_valid;
       uint16_t* orow = reinterpret_cast<uint16_t*>(p.O) + (long long)(it.o_row0 + r) * p.ldo + it.col0;
+      uint16_t* lrow = (MODE == 0 && p.Olo) ? reinterpret_cast<uint16_t*>(p.Olo) + (long long)(it.o_row0 + r) * p.ldo + it.col0 : nullptr;
+      const float lo_scale = p.dtype == CSN_F16 ? 2048.f : 256.f;
       const uint32_t o_addr = tmem_base + lane_addr + Cfg::O_COL;
 #pragma unroll 1
       for (int c = 0; c < DH; c += 32) {
@@ -355,23 +429,26 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         tmem_ld_wait();
 #pragma unroll
         for (int i = 0; i < 32; i += 8) {
-          uint32_t w4[4];
+          uint32_t w4[4], l4[4];
 #pragma unroll
           for (int t = 0; t < 4; ++t) {
             const float a = valid ? __uint_as_float(v[i + 2 * t]) * inv_l : 0.f;
             const float bb = valid ? __uint_as_float(v[i + 2 * t + 1]) * inv_l : 0.f;
-            if (p.dtype == CSN_F16) {
-              __half2 h = __floats2half2_rn(a, bb);
-              w4[t] = *reinterpret_cast<uint32_t*>(&h);
-            } else {
-              __nv_bfloat162 h = __floats2bfloat162_rn(a, bb);
-              w4[t] = *reinterpret_cast<uint32_t*>(&h);
+            w4[t] = pack_pair(a, bb);
+            if (MODE == 0) {
+              float2 hi;
+              if (p.dtype == CSN_F16) hi = __half22float2(*reinterpret_cast<__half2*>(&w4[t]));
+              else hi = __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&w4[t]));
+              l4[t] = pack_pair((a - hi.x) * lo_scale, (bb - hi.y) * lo_scale);
             }
           }
-          if (valid || (it.flags & 1)) *reinterpret_cast<uint4*>(orow + c + i) = make_uint4(w4[0], w4[1], w4[2], w4[3]);
+          if (valid || (it.flags & 1)) {
+            *reinterpret_cast<uint4*>(orow + c + i) = make_uint4(w4[0], w4[1], w4[2], w4[3]);
+            if (MODE == 0 && lrow) *reinterpret_cast<uint4*>(lrow + c + i) = make_uint4(l4[0], l4[1], l4[2], l4[3]);
+          }
         }
       }
-      if (p.lse && (valid || (it.flags & 1))) p.lse[it.lse_off + r] = valid ? (m_used * p.scale + __logf(l)) : 0.f;
+      if (MODE == 0 && p.lse && (valid || (it.flags & 1))) p.lse[it.lse_off + r] = valid ? (m_used * p.scale + __logf(l)) : 0.f;
       tc_fence_before();
       mbar_arrive(bo_empty);
     }
@@ -385,11 +462,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   }
 }
 
-template <int DH>
+template <int DH, int MODE>
 static int launch_attn_fwd(const CUtensorMap& tmQ, const CUtensorMap& tmK, const CUtensorMap& tmV,
                            const AttnFwdArgs& a, cudaStream_t stream) {
   using Cfg = AttnCfg<DH>;
-  auto kern = attn_fwd_kernel<DH>;
+  auto kern = attn_fwd_kernel<DH, MODE>;
   static bool configured = false;
   if (!configured) {
     CSN_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
@@ -403,10 +480,10 @@ static int launch_attn_fwd(const CUtensorMap& tmQ, const CUtensorMap& tmK, const
 
 }  // namespace csn
 
-extern "C" int csn_attn_fwd(const void* Q, const void* K, const void* V, int64_t q_rows, int64_t kv_rows,
-                            int64_t width, int64_t ldq, int64_t ldk, int64_t ldv, int32_t d_head, int32_t dtype,
-                            const int32_t* items, int32_t n_items, void* O, int64_t ldo, float* lse,
-                            void* stream) {
+static int attn_launch_common(int mode, const void* Q, const void* K, const void* V, int64_t q_rows, int64_t kv_rows,
+                              int64_t v_rows, int64_t width, int64_t ldq, int64_t ldk, int64_t ldv, int32_t d_head, int32_t dtype,
+                              const int32_t* items, int32_t n_items, void* O, int64_t ldo, float* lse,
+                              void* Olo, void* stream) {
   using namespace csn;
   clear_error();
   CSN_CHECK_ARG(Q && K && V && items && O, "csn_attn_fwd: null pointer");
@@ -420,12 +497,13 @@ extern "C" int csn_attn_fwd(const void* Q, const void* K, const void* V, int64_t
   rc = make_tmap_2d(&tmK, K, dtype, width, kv_rows, ldk, 64, 128);
   if (rc) return rc;
   const uint32_t vrows = d_head == 256 ? 64 : 128;  // KEYS_PER_VSLOT
-  rc = make_tmap_2d(&tmV, V, dtype, width, kv_rows, ldv, 64, vrows);
+  rc = make_tmap_2d(&tmV, V, dtype, width, v_rows, ldv, 64, vrows);
   if (rc) return rc;
   AttnFwdArgs a;
   a.items = reinterpret_cast<const AttnItem*>(items);
   a.n_items = n_items;
   a.O = O;
+  a.Olo = Olo;
   a.ldo = ldo;
   a.lse = lse;
   a.scale = 1.0f / sqrtf((float)d_head);
@@ -435,6 +513,31 @@ extern "C" int csn_attn_fwd(const void* Q, const void* K, const void* V, int64_t
   a.idesc_qk = umma_idesc_f16(fmt, 0, 0, 128);
   a.idesc_pv = umma_idesc_f16(fmt, 0, 1, (uint32_t)d_head);
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-  if (d_head == 256) return launch_attn_fwd<256>(tmQ, tmK, tmV, a, s);
-  return launch_attn_fwd<64>(tmQ, tmK, tmV, a, s);
+  if (mode == 0) {
+    if (d_head == 256) return launch_attn_fwd<256, 0>(tmQ, tmK, tmV, a, s);
+    return launch_attn_fwd<64, 0>(tmQ, tmK, tmV, a, s);
+  }
+  CSN_CHECK_ARG(lse != nullptr, "csn_attn_bwd_dv: lse is required");
+  if (d_head == 256) return launch_attn_fwd<256, 1>(tmQ, tmK, tmV, a, s);
+  return launch_attn_fwd<64, 1>(tmQ, tmK, tmV, a, s);
+}
+
+extern "C" int csn_attn_fwd(const void* Q, const void* K, const void* V, int64_t q_rows, int64_t kv_rows,
+                            int64_t width, int64_t ldq, int64_t ldk, int64_t ldv, int32_t d_head, int32_t dtype,
+                            const int32_t* items, int32_t n_items, void* O, int64_t ldo, float* lse,
+                            void* O_lo, void* stream) {
+  return attn_launch_common(0, Q, K, V, q_rows, kv_rows, kv_rows, width, ldq, ldk, ldv, d_head, dtype, items, n_items,
+                            O, ldo, lse, O_lo, stream);
+}
+
+// dV = P^T dO with P^T recomputed from K, Q and the forward log-sum-exp. Same pipeline as the forward
+// kernel with the roles swapped: resident tile = 128 KEY rows (argument Kres), streamed K-major
+// operand = the QUERY rows (Qstr), streamed MN-major operand = dO rows; items[*].lse_off indexes the
+// lse of the first streamed (query) row.
+extern "C" int csn_attn_bwd_dv(const void* Kres, const void* Qstr, const void* dO, int64_t k_rows, int64_t q_rows,
+                               int64_t do_rows, int64_t width, int64_t ldk, int64_t ldq, int64_t lddo, int32_t d_head, int32_t dtype,
+                               const int32_t* items, int32_t n_items, void* dV, int64_t lddv, const float* lse,
+                               void* stream) {
+  return attn_launch_common(1, Kres, Qstr, dO, k_rows, q_rows, do_rows, width, ldk, ldq, lddo, d_head, dtype, items,
+                            n_items, dV, lddv, const_cast<float*>(lse), nullptr, stream);
 }

@@ -10,6 +10,7 @@ else through the kernels of csrc/elementwise.cu; this file only computes strides
 from __future__ import annotations
 
 import math
+import os
 from dataclasses import dataclass, field
 
 import torch
@@ -20,9 +21,14 @@ from . import _lib as L
 @dataclass(frozen=True)
 class Geometry:
     """Chunked, padded row layout of one shape."""
-    chunk: int = 500       # points per attention chunk (mini_bs, csa_models.py:84)
+    chunk: int = 500       # query points per attention chunk (mini_bs, csa_models.py:84)
     n_chunks: int = 20     # iters (csa_models.py:83)
     chunk_pad: int = 512   # rows reserved per chunk (multiple of 128)
+    kv_chunk: int = -1     # key points per chunk when it differs from `chunk` (MinkowskiNet: Lq != Lk)
+
+    @property
+    def kv_len(self) -> int:
+        return self.chunk if self.kv_chunk < 0 else self.kv_chunk
 
     @property
     def n_points(self) -> int:
@@ -94,10 +100,11 @@ class AttnContext:
 _ITEM_CACHE: dict = {}
 
 
-def attn_items(groups, geom: Geometry, n_head: int, d: int, device) -> torch.Tensor:
-    """Work table of csn_attn_fwd for chunked block attention: one item per
-    (block, chunk, head, 128-row query tile)."""
-    key = (tuple(groups), geom, n_head, d, str(device))
+def attn_items(groups, geom: Geometry, n_head: int, d: int, device, kind: str = "fwd") -> torch.Tensor:
+    """Work tables of the fused attention kernels for chunked block attention: one item per
+    (block, chunk, head, 128-row tile). kind: 'fwd' (csn_attn_fwd), 'dv' (csn_attn_bwd_dv: tile of keys),
+    'dq' (csn_attn_bwd_dq: tile of queries)."""
+    key = (tuple(groups), geom, n_head, d, str(device), kind)
     t = _ITEM_CACHE.get(key)
     if t is not None:
         return t
@@ -110,9 +117,19 @@ def attn_items(groups, geom: Geometry, n_head: int, d: int, device) -> torch.Ten
             for c in range(NC):
                 for h in range(n_head):
                     for t_ in range(tiles):
-                        valid = max(0, min(128, geom.chunk - t_ * 128))
-                        rows.append((qs * NP + c * CP + t_ * 128, valid, ks * NP + c * CP, geom.chunk,
-                                     j * NP + c * CP + t_ * 128, h * d, (j * n_head + h) * NP + c * CP + t_ * 128, 1))
+                        valid = max(0, min(128, geom.chunk - t_ * 128))      # query rows of tile t_
+                        kvalid = max(0, min(128, geom.kv_len - t_ * 128))    # key rows of tile t_
+                        stat = (j * n_head + h) * NP + c * CP
+                        if kind == "fwd":
+                            rows.append((qs * NP + c * CP + t_ * 128, valid, ks * NP + c * CP, geom.kv_len,
+                                         j * NP + c * CP + t_ * 128, h * d, stat + t_ * 128, 1, ks * NP + c * CP, 0))
+                        elif kind == "dv":   # resident tile = keys; streamed = queries (Q view) and dO (block rows)
+                            rows.append((ks * NP + c * CP + t_ * 128, kvalid, qs * NP + c * CP, geom.chunk,
+                                         j * NP + c * CP + t_ * 128, h * d, stat, 1, j * NP + c * CP, 0))
+                        else:                # dq
+                            rows.append((qs * NP + c * CP + t_ * 128, valid, ks * NP + c * CP, geom.kv_len,
+                                         j * NP + c * CP + t_ * 128, h * d, stat + t_ * 128,
+                                         ((j * NC + c) * n_head + h) * CP + t_ * 128, 0, 1, 0, 0))
     t = torch.tensor(rows, dtype=torch.int32).to(device)
     if len(_ITEM_CACHE) > 16:
         _ITEM_CACHE.clear()
@@ -145,14 +162,14 @@ def _scores_and_probs(ctx: "AttnContext"):
         D = L.out(Sbuf[g.blk0 * NC * n_head * CP:], CP, off=(CP * CP, n_head * CP * CP, blk_sz, g.n_in * blk_sz))
         L.gemm(A, B, D, CP, CP, d, nb=(n_head, NC, g.n_in, g.n_out), alpha=1.0 / math.sqrt(d))
     P = torch.empty(ctx.n_blocks * NC * n_head * CP, CP, dtype=dt, device=dev)
-    rc = L.lib().csn_softmax_fwd(Sbuf.data_ptr(), P.data_ptr(), Sbuf.shape[0], CP, geom.chunk, CP, geom.chunk,
+    rc = L.lib().csn_softmax_fwd(Sbuf.data_ptr(), P.data_ptr(), Sbuf.shape[0], CP, geom.kv_len, CP, geom.chunk,
                                  L.dtype_code(dt), L.stream_ptr())
     L.check(rc, "csn_softmax_fwd")
     return Sbuf, P
 
 
 def attention_forward(Xh, Xf, groups, n_slots, n_blocks, w_q, w_k, w_v, w_o, gamma, beta, geom: Geometry,
-                      n_head: int, want_colsum: bool = True) -> AttnContext:
+                      n_head: int, want_colsum: bool = True, save_for_backward: bool = True) -> AttnContext:
     """Forward of all blocks. Xh/Xf: packed slots [S*NP, 256] (16-bit / fp32)."""
     dev, dt = Xh.device, Xh.dtype
     NP, CP, NC = geom.rows_pad, geom.chunk_pad, geom.n_chunks
@@ -173,11 +190,14 @@ def attention_forward(Xh, Xf, groups, n_slots, n_blocks, w_q, w_k, w_v, w_o, gam
         # --- fused flash-style core (csa_models.py:139-142): scores never leave TMEM
         items = attn_items(groups, geom, n_head, d, dev)
         lse = torch.empty(n_blocks * n_head * NP, dtype=torch.float32, device=dev)
+        O_lo = torch.empty_like(O) if torch.is_grad_enabled() or save_for_backward else None
         rc = L.lib().csn_attn_fwd(Qv.data_ptr(), Kv.data_ptr(), Vv.data_ptr(), n_slots * NP, n_slots * NP, HD,
                                   3 * HD, 3 * HD, 3 * HD, d, L.dtype_code(dt), items.data_ptr(), items.shape[0],
-                                  O.data_ptr(), HD, lse.data_ptr(), L.stream_ptr())
+                                  O.data_ptr(), HD, lse.data_ptr(), O_lo.data_ptr() if O_lo is not None else None,
+                                  L.stream_ptr())
         L.check(rc, "csn_attn_fwd")
         ctx.extra["lse"] = lse
+        ctx.extra["O_lo"] = O_lo
     else:
         # --- materialised path: S = (Q K^T)/sqrt(d) -> softmax over the 500 valid keys -> O = P V
         Sbuf, P = _scores_and_probs(ctx_with(ctx, QKV))
@@ -215,6 +235,46 @@ def attention_forward(Xh, Xf, groups, n_slots, n_blocks, w_q, w_k, w_v, w_o, gam
         L.check(rc, "csn_colsum_reduce")
     ctx.Z, ctx.Y = Z, Y
     return ctx
+
+
+def _attention_backward_materialised(ctx: AttnContext, dO: torch.Tensor, dQKV: torch.Tensor) -> None:
+    """dQ|dK|dV through materialised P / dP / dS tiles (csn_gemm + csn_softmax_bwd): the fallback for
+    head sizes the fused kernels do not cover, and the cross-check of the fused path in the tests."""
+    geom, h, d = ctx.geom, ctx.n_head, ctx.d_head
+    NP, CP, NC = geom.rows_pad, geom.chunk_pad, geom.n_chunks
+    HD = h * d
+    dt = ctx.Xh.dtype
+    lib = L.lib()
+    Qv, Kv, Vv = ctx.QKV[:, :HD], ctx.QKV[:, HD:2 * HD], ctx.QKV[:, 2 * HD:]
+    dQv, dKv, dVv = dQKV[:, :HD], dQKV[:, HD:2 * HD], dQKV[:, 2 * HD:]
+    if ctx.P is None:   # fused forward: rebuild the probabilities
+        ctx.extra["Sbuf"], ctx.P = _scores_and_probs(ctx)
+    # --- dP = dO V^T per (block, chunk, head)
+    dP = ctx.extra["Sbuf"]
+    blk_sz = NC * h * CP * CP
+    prow = NC * h * CP
+    for g in ctx.groups:
+        A = L.mat(dO[g.blk0 * NP:], L.MAJOR_K, mn_off=(0, CP, NP, g.n_in * NP), k_off=(d, 0, 0, 0))
+        B = L.mat(Vv[g.v0 * NP:], L.MAJOR_K, mn_off=(0, CP, g.v_si * NP, g.v_so * NP), k_off=(d, 0, 0, 0))
+        D = L.out(dP[g.blk0 * prow:], CP, off=(CP * CP, h * CP * CP, blk_sz, g.n_in * blk_sz))
+        L.gemm(A, B, D, CP, CP, d, nb=(h, NC, g.n_in, g.n_out))
+    # --- dS = P o (dP - rowsum(P o dP)) / sqrt(d)
+    dS = torch.empty_like(ctx.P)
+    rc = lib.csn_softmax_bwd(ctx.P.data_ptr(), dP.data_ptr(), dS.data_ptr(), dP.shape[0], CP, geom.kv_len, CP,
+                             geom.chunk, 1.0 / math.sqrt(d), L.dtype_code(dt), L.stream_ptr())
+    L.check(rc, "csn_softmax_bwd")
+    for g in ctx.groups:
+        nb = (h, NC, g.n_in, g.n_out)
+        Pk = L.mat(ctx.P[g.blk0 * prow:], L.MAJOR_MN, k_off=(CP, h * CP, prow, g.n_in * prow))        # P^T
+        dSk = L.mat(dS[g.blk0 * prow:], L.MAJOR_K, mn_off=(CP, h * CP, prow, g.n_in * prow))
+        dSt = L.mat(dS[g.blk0 * prow:], L.MAJOR_MN, k_off=(CP, h * CP, prow, g.n_in * prow))          # dS^T
+        dOm = L.mat(dO[g.blk0 * NP:], L.MAJOR_MN, mn_off=(d, 0, 0, 0), k_off=(0, CP, NP, g.n_in * NP))
+        Km = L.mat(Kv[g.k0 * NP:], L.MAJOR_MN, mn_off=(d, 0, 0, 0), k_off=(0, CP, g.k_si * NP, g.k_so * NP))
+        Qm = L.mat(Qv[g.q0 * NP:], L.MAJOR_MN, mn_off=(d, 0, 0, 0), k_off=(0, CP, g.q_si * NP, g.q_so * NP))
+        off = (d, CP * 3 * HD, NP * 3 * HD, g.n_in * NP * 3 * HD)
+        L.gemm(Pk, dOm, L.out(dVv[g.blk0 * NP:], 3 * HD, off=off), CP, d, CP, nb=nb)    # dV = P^T dO
+        L.gemm(dSk, Km, L.out(dQv[g.blk0 * NP:], 3 * HD, off=off), CP, d, CP, nb=nb)    # dQ = dS K
+        L.gemm(dSt, Qm, L.out(dKv[g.blk0 * NP:], 3 * HD, off=off), CP, d, CP, nb=nb)    # dK = dS^T Q
 
 
 def _pick_split(tiles: int, kb_total: int, target: int = 296) -> int:
@@ -258,37 +318,40 @@ def attention_backward(ctx: AttnContext, dY: torch.Tensor, need_dx: bool, amax: 
     dO = torch.empty(nblk * NP, HD, dtype=dt, device=dev)
     L.gemm(L.mat(dZ16, L.MAJOR_K), L.mat(ctx.Wo16, L.MAJOR_MN), L.out(dO, HD), nblk * NP, HD, 256)
     Qv, Kv, Vv = ctx.QKV[:, :HD], ctx.QKV[:, HD:2 * HD], ctx.QKV[:, 2 * HD:]
-    # --- dP = dO V^T per (block, chunk, head)
-    if ctx.P is None:   # fused forward: rebuild the probabilities (materialised backward)
-        ctx.extra["Sbuf"], ctx.P = _scores_and_probs(ctx)
-    dP = ctx.extra["Sbuf"]
-    blk_sz = NC * h * CP * CP
-    prow = NC * h * CP
-    for g in ctx.groups:
-        A = L.mat(dO[g.blk0 * NP:], L.MAJOR_K, mn_off=(0, CP, NP, g.n_in * NP), k_off=(d, 0, 0, 0))
-        B = L.mat(Vv[g.v0 * NP:], L.MAJOR_K, mn_off=(0, CP, g.v_si * NP, g.v_so * NP), k_off=(d, 0, 0, 0))
-        D = L.out(dP[g.blk0 * prow:], CP, off=(CP * CP, h * CP * CP, blk_sz, g.n_in * blk_sz))
-        L.gemm(A, B, D, CP, CP, d, nb=(h, NC, g.n_in, g.n_out))
-    # --- dS = P o (dP - rowsum(P o dP)) / sqrt(d)
-    dS = torch.empty_like(ctx.P)
-    rc = lib.csn_softmax_bwd(ctx.P.data_ptr(), dP.data_ptr(), dS.data_ptr(), dP.shape[0], CP, geom.chunk, CP,
-                             geom.chunk, 1.0 / math.sqrt(d), L.dtype_code(dt), L.stream_ptr())
-    L.check(rc, "csn_softmax_bwd")
-    # --- per-block dQ | dK | dV  (stored per block: several blocks may share a slot)
+    fused_bwd = ctx.P is None and "lse" in ctx.extra and os.environ.get("CSN_FUSED_BWD", "1") != "0"
     dQKV = torch.empty(nblk * NP, 3 * HD, dtype=dt, device=dev)
     dQv, dKv, dVv = dQKV[:, :HD], dQKV[:, HD:2 * HD], dQKV[:, 2 * HD:]
-    for g in ctx.groups:
-        nb = (h, NC, g.n_in, g.n_out)
-        Pk = L.mat(ctx.P[g.blk0 * prow:], L.MAJOR_MN, k_off=(CP, h * CP, prow, g.n_in * prow))        # P^T
-        dSk = L.mat(dS[g.blk0 * prow:], L.MAJOR_K, mn_off=(CP, h * CP, prow, g.n_in * prow))
-        dSt = L.mat(dS[g.blk0 * prow:], L.MAJOR_MN, k_off=(CP, h * CP, prow, g.n_in * prow))          # dS^T
-        dOm = L.mat(dO[g.blk0 * NP:], L.MAJOR_MN, mn_off=(d, 0, 0, 0), k_off=(0, CP, NP, g.n_in * NP))
-        Km = L.mat(Kv[g.k0 * NP:], L.MAJOR_MN, mn_off=(d, 0, 0, 0), k_off=(0, CP, g.k_si * NP, g.k_so * NP))
-        Qm = L.mat(Qv[g.q0 * NP:], L.MAJOR_MN, mn_off=(d, 0, 0, 0), k_off=(0, CP, g.q_si * NP, g.q_so * NP))
-        off = (d, CP * 3 * HD, NP * 3 * HD, g.n_in * NP * 3 * HD)
-        L.gemm(Pk, dOm, L.out(dVv[g.blk0 * NP:], 3 * HD, off=off), CP, d, CP, nb=nb)    # dV = P^T dO
-        L.gemm(dSk, Km, L.out(dQv[g.blk0 * NP:], 3 * HD, off=off), CP, d, CP, nb=nb)    # dQ = dS K
-        L.gemm(dSt, Qm, L.out(dKv[g.blk0 * NP:], 3 * HD, off=off), CP, d, CP, nb=nb)    # dK = dS^T Q
+    prow = NC * h * CP
+    if fused_bwd:
+        # --- fused attention backward: delta, dV (P^T rebuilt from lse), dQ (+ dS to HBM), dK = dS^T Q
+        lse = ctx.extra["lse"]
+        delta = torch.empty_like(lse)
+        O_lo = ctx.extra.get("O_lo")
+        rc = lib.csn_attn_delta(dO.data_ptr(), ctx.O.data_ptr(), O_lo.data_ptr() if O_lo is not None else None,
+                                delta.data_ptr(), nblk * NP, NP, h, d, HD, L.dtype_code(dt), L.stream_ptr())
+        L.check(rc, "csn_attn_delta")
+        it_dv = attn_items(ctx.groups, geom, h, d, dev, "dv")
+        rc = lib.csn_attn_bwd_dv(Kv.data_ptr(), Qv.data_ptr(), dO.data_ptr(), S * NP, S * NP, nblk * NP, HD, 3 * HD, 3 * HD, HD,
+                                 d, L.dtype_code(dt), it_dv.data_ptr(), it_dv.shape[0], dVv.data_ptr(), 3 * HD,
+                                 lse.data_ptr(), L.stream_ptr())
+        L.check(rc, "csn_attn_bwd_dv")
+        # the dQ kernel writes the key tiles it visits; columns beyond them must read as zeros in dS^T Q
+        alloc = torch.empty if ((geom.kv_len + 127) // 128) * 128 >= CP else torch.zeros
+        dS = alloc(nblk * prow, CP, dtype=dt, device=dev)
+        it_dq = attn_items(ctx.groups, geom, h, d, dev, "dq")
+        rc = lib.csn_attn_bwd_dq(Qv.data_ptr(), dO.data_ptr(), Kv.data_ptr(), Vv.data_ptr(), S * NP, nblk * NP, S * NP,
+                                 HD, 3 * HD, HD, 3 * HD, 3 * HD, d, L.dtype_code(dt), it_dq.data_ptr(),
+                                 it_dq.shape[0], dQv.data_ptr(), 3 * HD, dS.data_ptr(), CP, lse.data_ptr(),
+                                 delta.data_ptr(), L.stream_ptr())
+        L.check(rc, "csn_attn_bwd_dq")
+        for g in ctx.groups:
+            nb = (h, NC, g.n_in, g.n_out)
+            dSt = L.mat(dS[g.blk0 * prow:], L.MAJOR_MN, k_off=(CP, h * CP, prow, g.n_in * prow))          # dS^T
+            Qm = L.mat(Qv[g.q0 * NP:], L.MAJOR_MN, mn_off=(d, 0, 0, 0), k_off=(0, CP, g.q_si * NP, g.q_so * NP))
+            off = (d, CP * 3 * HD, NP * 3 * HD, g.n_in * NP * 3 * HD)
+            L.gemm(dSt, Qm, L.out(dKv[g.blk0 * NP:], 3 * HD, off=off), CP, d, CP, nb=nb)    # dK = dS^T Q
+    else:
+        _attention_backward_materialised(ctx, dO, dQKV)
     # --- projection weight gradients: dW = sum_blocks dProj^T X[slot]  (contraction over points, both
     #     operands consumed MN-major; split-K sized for ~2 waves of CTAs, fp32 atomics into dWqkv)
     dWqkv = torch.zeros(3 * HD, 256, dtype=torch.float32, device=dev)

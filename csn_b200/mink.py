@@ -1,0 +1,210 @@
+"""Drop-in surface of the MinkowskiNet CSA head's attention (MinkowskiNet/models/attention.py and the
+CSA block of MinkowskiNet/models/hrnet.py:359-490), backed by the same sm_100a kernels as the MID-FC
+path: one attention "chunk" is the whole shape (full L_q x L_k attention, h = 4, d = 64), the score
+matrix never leaves TMEM.
+
+Classes / functions (reference names): MultiHeadAttention, ScaledDotProductAttention,
+ScaledDotProduct, cosine_similarity (HRNetSimCSN.cosine_similarity), csa_block (the per-batch-item
+loop of HRNetSimCSN.forward on dense per-shape feature lists — the MinkowskiEngine sparse-tensor
+wrapping stays the reference's), topk_neighbors (lib/csn_utils.py:91-96).
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import _lib as L
+from . import engine as E
+from . import knn as _knn
+from .midfc import _PRECISIONS, ScaledDotProductAttention, _require_cuda  # noqa: F401  (same semantics)
+
+
+def _pack_rows(x: torch.Tensor, n_pad: int, dt) -> tuple[torch.Tensor, torch.Tensor]:
+    """(B, L, 256) fp32 row-major -> padded 16-bit and fp32 slot buffers [B*n_pad, 256] (pad rows zero)."""
+    B, Lx, D = x.shape
+    xh = torch.zeros(B, n_pad, D, dtype=dt, device=x.device)
+    xf = torch.zeros(B, n_pad, D, dtype=torch.float32, device=x.device)
+    xh[:, :Lx] = x.to(dt)
+    xf[:, :Lx] = x
+    return xh.view(B * n_pad, D), xf.view(B * n_pad, D)
+
+
+class _MhaFullFn(torch.autograd.Function):
+    """MultiHeadAttention.forward of MinkowskiNet/models/attention.py:31-56 (k and v may be the same
+    tensor, as in every reference call hrnet.py:407,463)."""
+
+    @staticmethod
+    def forward(ctx, q, k, v, wq, wk, wv, wo, gamma, beta, n_head, dt, need_attn):
+        for t, n in ((q, "q"), (k, "k"), (v, "v"), (wq, "w_qs.weight")):
+            _require_cuda(t, n)
+        B, Lq, D = q.shape
+        Lk = k.shape[1]
+        assert D == 256, "d_model = 256 on this path (lib/config.py:49)"
+        same_kv = k is v or (k.data_ptr() == v.data_ptr() and k.shape == v.shape and k.stride() == v.stride())
+        if not same_kv and not torch.equal(k, v):
+            raise NotImplementedError("csn_b200.mink.MultiHeadAttention reads keys and values from one tensor "
+                                      "(the only call pattern of the reference)")
+        same_qk = q is k or (q.data_ptr() == k.data_ptr() and q.shape == k.shape and q.stride() == k.stride())
+        n_pad = (max(Lq, Lk) + 127) // 128 * 128
+        geom = E.Geometry(chunk=Lq, n_chunks=1, chunk_pad=n_pad, kv_chunk=Lk)
+        qh, qf = _pack_rows(q.float(), n_pad, dt)
+        if same_qk:
+            Xh, Xf, k0, n_slots = qh, qf, 0, B
+        else:
+            kh, kf = _pack_rows(k.float(), n_pad, dt)
+            Xh, Xf, k0, n_slots = torch.cat([qh, kh]), torch.cat([qf, kf]), B, 2 * B
+        group = E.Group(n_in=B, n_out=1, blk0=0, q0=0, q_si=1, q_so=0, k0=k0, k_si=1, k_so=0, v0=k0, v_si=1, v_so=0)
+        a = E.attention_forward(Xh, Xf, [group], n_slots, B, wq, wk, wv, wo, gamma, beta, geom, n_head,
+                                want_colsum=False)
+        ctx.a = a
+        ctx.meta = (B, Lq, Lk, k0, n_pad)
+        out = a.Y.view(B, n_pad, 256)[:, :Lq].contiguous()
+        if need_attn:
+            attn = _full_attn(a, B, Lq, Lk)
+        else:
+            attn = torch.empty(0, device=q.device)
+        ctx.mark_non_differentiable(attn)
+        return out, attn
+
+    @staticmethod
+    def backward(ctx, dout, _dattn):
+        a = ctx.a
+        B, Lq, Lk, k0, n_pad = ctx.meta
+        dY = torch.zeros(B, n_pad, 256, dtype=torch.float32, device=dout.device)
+        dY[:, :Lq] = dout
+        need_dx = any(ctx.needs_input_grad[:3])
+        g = E.attention_backward(a, dY.view(B * n_pad, 256), need_dx)
+        dq = dk = None
+        if need_dx:
+            dX = g["dX"].view(-1, n_pad, 256)
+            dq = dX[:B, :Lq].contiguous()
+            if k0 != 0:
+                dk = dX[k0:k0 + B, :Lk].contiguous()
+        return (dq, dk, None, g["dWq"], g["dWk"], g["dWv"], g["dWo"], g["dgamma"], g["dbeta"], None, None, None)
+
+
+def _full_attn(a: E.AttnContext, B: int, Lq: int, Lk: int) -> torch.Tensor:
+    """(B, h, Lq, Lk) attention matrix, materialised on request only (it defeats the fused kernel's
+    purpose; both reference callers discard it: hrnet.py:407,463)."""
+    h, d, g = a.n_head, a.d_head, a.geom
+    NP = g.rows_pad
+    HD = h * d
+    dev, dt = a.Xh.device, a.Xh.dtype
+    Lkp = (Lk + 7) // 8 * 8
+    table = {j: (qs, ks) for grp in a.groups for (j, qs, ks, _) in grp.blocks()}
+    S = torch.empty(B * h * Lq, Lkp, dtype=torch.float32, device=dev)
+    Qv, Kv = a.QKV[:, :HD], a.QKV[:, HD:2 * HD]
+    for j in range(B):
+        qs, ks = table[j]
+        L.gemm(L.mat(Qv[qs * NP:], L.MAJOR_K, k_off=(d,)), L.mat(Kv[ks * NP:], L.MAJOR_K, k_off=(d,)),
+               L.out(S[j * h * Lq:], Lkp, off=(Lq * Lkp,)), Lq, Lk, d, nb=(h,), alpha=1.0 / math.sqrt(d))
+    P = torch.empty(B * h * Lq, Lkp, dtype=dt, device=dev)
+    rc = L.lib().csn_softmax_fwd(S.data_ptr(), P.data_ptr(), S.shape[0], Lkp, Lk, 1, 1, L.dtype_code(dt), L.stream_ptr())
+    L.check(rc, "csn_softmax_fwd")
+    return P[:, :Lk].float().view(B, h, Lq, Lk)
+
+
+class MultiHeadAttention(nn.Module):
+    """Multi-Head Attention module of MinkowskiNet/models/attention.py:9-56.
+    forward(q, k, v) -> (out (B, Lq, d_model), attn); attn is None unless `return_attn=True`
+    (API decision of SURVEY.md §8b: the full (B,h,Lq,Lk) matrix is only materialised on request)."""
+
+    def __init__(self, n_head, d_model, d_k, d_v, dropout=0.1, precision="fp16", return_attn=False):
+        super().__init__()
+        assert d_k == d_v
+        self.n_head = n_head
+        self.d_k = d_k
+        self.d_v = d_v
+        self.w_qs = nn.Linear(d_model, n_head * d_k, bias=False)
+        self.w_ks = nn.Linear(d_model, n_head * d_k, bias=False)
+        self.w_vs = nn.Linear(d_model, n_head * d_v, bias=False)
+        self.fc = nn.Linear(n_head * d_v, d_model, bias=False)
+        self.attention = ScaledDotProductAttention(temperature=d_k ** 0.5, precision=precision)
+        self.dropout = nn.Dropout(dropout)
+        self.norm = nn.LayerNorm(d_model, eps=1e-6)
+        self.precision = precision
+        self.return_attn = return_attn
+
+    def forward(self, q, k, v):
+        out, attn = _MhaFullFn.apply(q, k, v, self.w_qs.weight, self.w_ks.weight, self.w_vs.weight, self.fc.weight,
+                                     self.norm.weight, self.norm.bias, self.n_head, _PRECISIONS[self.precision],
+                                     self.return_attn)
+        return out, (attn if self.return_attn else None)
+
+
+class ScaledDotProduct(nn.Module):
+    """attention.py:78-113 on dense inputs: (q k^T) / temperature.  Operands here are 256-d global
+    descriptors (hrnet.py:392-394), i.e. a handful of dot products: kept in PyTorch."""
+
+    def __init__(self, temperature):
+        super().__init__()
+        self.temperature = temperature
+
+    def forward(self, q, k):
+        if q.ndim == 2:
+            q = q.unsqueeze(0)
+        if k.ndim == 2:
+            k = k.unsqueeze(0)
+        return torch.bmm(q, k.permute(0, 2, 1)) / self.temperature
+
+    def __repr__(self):
+        return f"{self.__class__.__name__}(temperature={self.temperature})"
+
+
+def cosine_similarity(q: torch.Tensor, k: torch.Tensor, precision: str = "fp16") -> torch.Tensor:
+    """HRNetSimCSN.cosine_similarity (hrnet.py:472-490)."""
+    return _knn.cosine_similarity(q, k, _PRECISIONS[precision])
+
+
+class CSAHead(nn.Module):
+    """The attention part of HRNetSimCSN (hrnet.py:343,355-357): `MHA`, `linear_q`, `linear_k`, `sim`
+    with the reference attribute names, operating on dense per-shape feature lists."""
+
+    def __init__(self, d_model=256, n_head=4, precision="fp16"):
+        super().__init__()
+        self.d_model = d_model
+        self.n_head = n_head
+        self.MHA = MultiHeadAttention(n_head, d_model, d_model // n_head, d_model // n_head, precision=precision)
+        self.linear_q = nn.Linear(d_model, d_model, bias=False)
+        self.linear_k = nn.Linear(d_model, d_model, bias=False)
+        self.sim = ScaledDotProduct(d_model ** 0.5)
+
+    def get_SSA(self, feats):
+        """hrnet.py:456-470 over a list of (L_b, 256) tensors."""
+        return [self.MHA(f[None], f[None], f[None])[0][0] for f in feats]
+
+    def forward(self, query_feats, key_feats=None, return_ssa=False):
+        """CSA block of HRNetSimCSN.forward (hrnet.py:370-417). query_feats: list over batch items of
+        (L_b, 256); key_feats: list over the K neighbours of such lists. Returns the list of CSA
+        features per batch item (the SSA features when key_feats is empty / return_ssa)."""
+        q_ssa = self.get_SSA(query_feats)
+        if return_ssa or not key_feats:
+            return q_ssa
+        keys_ssa = [q_ssa] + [self.get_SSA(kf) for kf in key_feats]
+        out = []
+        for b, ssa_b in enumerate(q_ssa):
+            g_q = F.normalize(self.linear_q(ssa_b.mean(dim=0)), dim=-1)
+            sims = []
+            for ks in keys_ssa:
+                g_k = F.normalize(self.linear_k(ks[b].mean(dim=0)), dim=-1)
+                sims.append(self.sim(g_q.unsqueeze(0), g_k.unsqueeze(0)).squeeze())
+            comp = F.softmax(torch.stack(sims), dim=0)
+            csa = comp[0] * ssa_b
+            for i, kf in enumerate(key_feats):
+                cross, _ = self.MHA(query_feats[b][None], kf[b][None], kf[b][None])
+                csa = csa + comp[i + 1] * cross[0]
+            out.append(csa)
+        return out
+
+
+def topk_neighbors(similarity: torch.Tensor, K: int, self_index=None) -> torch.Tensor:
+    """lib/csn_utils.py:91-96: topk(K); if the query itself is among them, topk(K+1) without it."""
+    s = similarity.reshape(1, -1).float().contiguous()
+    idx = _knn.topk_rows(s, K)[1][0]
+    if self_index is not None and bool((idx == self_index).any()):
+        idx = _knn.topk_rows(s, K + 1)[1][0]
+        idx = idx[idx != self_index]
+    return idx

@@ -107,18 +107,42 @@ int csn_topk_rows(const float* scores, int64_t ld, int32_t n_rows, int32_t n_col
  * Fused attention core  O = softmax(Q K^T / sqrt(d)) V  (flash-style: the score matrix only exists as
  * 128x128 fp32 tiles in TMEM).  Replaces ScaledDotProductAttention.forward (csa_models.py:138-144,
  * MinkowskiNet/models/attention.py:69-75) for every (block, head, 128-row query tile) listed in the
- * work table `items` (int32 x 8 per item, device memory):
- *   {q_row0, q_valid, kv_row0, kv_len, o_row0, col0, lse_off, flags}
+ * work table `items` (int32 x 10 per item, device memory):
+ *   {q_row0, q_valid, kv_row0, kv_len, o_row0, col0, lse_off, flags, v_row0, 0}
  * the tile's queries are rows [q_row0, q_row0+128) of Q (q_valid of them real), its keys/values rows
  * [kv_row0, kv_row0+kv_len) of K / V, all restricted to columns [col0, col0+d_head); the result goes to
  * rows [o_row0, ..) / columns [col0, ..) of O (16-bit) and lse[lse_off + r] = log sum_j exp(s_rj).
+ * (V rows start at v_row0, normally == kv_row0).
  * flags bit 0: rows >= q_valid are written as zeros (padded layouts) instead of being left untouched.
  * Q, K, V: 16-bit row-major views of `width` columns with leading dimensions ldq / ldk / ldv.
- * d_head in {64, 256}.
+ * d_head in {64, 256}.  O_lo (optional, same layout as O) receives the rounding residual of O,
+ * (o - round16(o)) * 2^11 (fp16) or * 2^8 (bf16), which csn_attn_delta uses to form
+ * delta = rowsum(dO o O) to ~22 bits (a 16-bit O alone costs 1e-3 on dQ/dK when all value rows share
+ * a large mean, as post-ReLU features do).
  * ------------------------------------------------------------------------------------------- */
 int csn_attn_fwd(const void* Q, const void* K, const void* V, int64_t q_rows, int64_t kv_rows, int64_t width,
                  int64_t ldq, int64_t ldk, int64_t ldv, int32_t d_head, int32_t dtype, const int32_t* items,
-                 int32_t n_items, void* O, int64_t ldo, float* lse, void* stream);
+                 int32_t n_items, void* O, int64_t ldo, float* lse, void* O_lo, void* stream);
+
+/* Backward of the attention core (autograd of csa_models.py:139-142), three pieces:
+ *  csn_attn_delta : delta[(blk*h+head)*rows_pad + r] = sum_c dO[blk*rows_pad+r][head*d+c] * (O + O_lo/2^11)[..]
+ *  csn_attn_bwd_dv: dV = P^T dO, P^T rebuilt from K, Q and the forward lse. Same kernel and item layout
+ *                   as csn_attn_fwd with the roles swapped: the resident 128-row tile holds KEY rows
+ *                   (q_row0/q_valid), kv_row0/kv_len address the QUERY rows (K-major operand), v_row0 the
+ *                   dO rows, lse_off the lse of the first query row, o_row0/col0 the dV tile.
+ *  csn_attn_bwd_dq: per 128-row query tile: S = Q K^T, dP = dO V^T, dS = P o (dP - delta) / sqrt(d),
+ *                   dQ += dS K; dS is also written (16-bit, [ds_row0 + r][ds_col0 + key]) so that
+ *                   dK = dS^T Q runs as one csn_gemm.  items: int32 x 12
+ *   {q_row0, q_valid, kv_row0, kv_len, o_row0 (rows of dO and dQ), col0, stat_off, ds_row0, ds_col0, flags, 0, 0}. */
+int csn_attn_delta(const void* dO, const void* O, const void* O_lo, float* delta, int64_t rows, int32_t rows_pad, int32_t n_head,
+                   int32_t d_head, int64_t ld, int32_t dtype, void* stream);
+int csn_attn_bwd_dv(const void* Kres, const void* Qstr, const void* dO, int64_t k_rows, int64_t q_rows,
+                    int64_t do_rows, int64_t width, int64_t ldk, int64_t ldq, int64_t lddo, int32_t d_head, int32_t dtype,
+                    const int32_t* items, int32_t n_items, void* dV, int64_t lddv, const float* lse, void* stream);
+int csn_attn_bwd_dq(const void* Q, const void* dO, const void* K, const void* V, int64_t q_rows, int64_t do_rows,
+                    int64_t kv_rows, int64_t width, int64_t ldq, int64_t lddo, int64_t ldk, int64_t ldv,
+                    int32_t d_head, int32_t dtype, const int32_t* items, int32_t n_items, void* dQ, int64_t lddq,
+                    void* dS, int64_t ldds, const float* lse, const float* delta, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * HBM-bound pieces of the CSA/SSA layer.  Row buffers use "padded" coordinates: a shape's block has

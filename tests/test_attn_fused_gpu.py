@@ -10,9 +10,10 @@ from csn_b200 import synth
 pytestmark = pytest.mark.gpu
 
 
-def _run(fused: bool, h: int, B: int = 2):
+def _run(fused: bool, h: int, B: int = 2, fused_bwd: bool = True):
     from csn_b200 import midfc
     os.environ["CSN_FUSED_ATTN"] = "1" if fused else "0"
+    os.environ["CSN_FUSED_BWD"] = "1" if fused_bwd else "0"
     try:
         m = midfc.MultiHeadAttention(h, 256, 256, 256).cuda().eval()
         sd = synth.midfc_state(3, h)
@@ -23,15 +24,19 @@ def _run(fused: bool, h: int, B: int = 2):
         y, attn = m(xq, xkv, xkv, "test")
         gy = torch.randn(y.shape, generator=synth.gen(5)).cuda()
         (y * gy).sum().backward()
-        return y.detach(), attn.detach(), xq.grad.detach(), m.w_vs.weight.grad.detach()
+        return (y.detach(), attn.detach(), xq.grad.detach(), m.w_vs.weight.grad.detach(),
+                m.w_qs.weight.grad.detach(), m.w_ks.weight.grad.detach())
     finally:
         os.environ.pop("CSN_FUSED_ATTN", None)
+        os.environ.pop("CSN_FUSED_BWD", None)
 
 
 @pytest.mark.parametrize("h", [1, 2])
 def test_fused_matches_materialised(h):
     a = _run(True, h)
     b = _run(False, h)
-    for name, x, y in zip(("y", "attn", "dx", "dWv"), a, b):
-        rel = float((x - y).norm() / y.norm())
-        assert rel < 3e-4, (name, rel)
+    c = _run(True, h, fused_bwd=False)
+    for other in (b, c):
+        for name, x, y in zip(("y", "attn", "dx", "dWv", "dWq", "dWk"), a, other):
+            rel = float((x - y).norm() / y.norm())
+            assert rel < 4e-4, (name, rel)

@@ -1,0 +1,94 @@
+"""CPU: host-side tables and the sharding logic of the multi-GPU paths (gloo, world_size 2)."""
+import os
+import socket
+
+import pytest
+import torch
+
+from csn_b200 import engine as E
+from csn_b200 import knn, shard
+
+
+def test_state_dict_keys_match_reference_contract():
+    from csn_b200 import midfc, synth
+    m = midfc.get_model("csa", 15, 8, 4)
+    assert set(m.state_dict().keys()) == set(synth.midfc_state(0, 8, 15).keys())
+    assert m.attention.w_qs.weight.shape == (2048, 256)   # d_k = 256 per head
+    s = midfc.get_model("ssa", 15, 1)
+    assert "compatibility_q.weight" not in s.state_dict()
+    with pytest.raises(AttributeError):
+        midfc.get_model("nope", 15, 1)
+
+
+def test_geometry_and_groups():
+    g = E.Geometry()
+    assert (g.n_points, g.rows_pad, g.kv_len) == (10000, 10240, 500)
+    grp = E.Group(n_in=3, n_out=2, blk0=8, q0=0, q_si=0, q_so=4, k0=1, k_si=1, k_so=4, v0=1, v_si=1, v_so=4)
+    blocks = list(grp.blocks())
+    assert blocks[0] == (8, 0, 1, 1) and blocks[-1] == (13, 4, 7, 7) and len(blocks) == 6
+
+
+def test_attention_work_tables():
+    g = E.Geometry(chunk=500, n_chunks=2, chunk_pad=512)
+    grp = E.Group(n_in=2, n_out=1, blk0=0, q0=0, q_si=1, q_so=0, k0=0, k_si=1, k_so=0, v0=0, v_si=1, v_so=0)
+    t = E.attn_items([grp], g, 2, 256, "cpu", "fwd")
+    assert t.shape == (2 * 2 * 2 * 4, 10)
+    assert t[:, 1].tolist()[:4] == [128, 128, 128, 116]          # last tile of a 500-point chunk
+    assert int(t[:, 3].min()) == 500 and int(t[:, 5].max()) == 256
+    d = E.attn_items([grp], g, 2, 256, "cpu", "dq")
+    assert d.shape[1] == 12 and int(d[-1, 7]) == ((1 * 2 + 1) * 2 + 1) * 512 + 384
+
+
+def test_knn_balance_and_store_subset():
+    assert knn._split_for_balance(148, 4000) == 1
+    ns = knn._split_for_balance(316, 4000)
+    assert (316 * ns) % 148 == 0 or (148 - (316 * ns) % 148) / (316 * ns) < 0.03
+    st = knn.ShapeStore(torch.zeros(30, 256, dtype=torch.float16), [0, 10, 20], [10, 10, 10])
+    sub = st.subset([2, 0])
+    assert sub.row0 == [20, 0] and sub.n_shapes == 2
+
+
+def test_shard_ranges_cover_everything():
+    for n, w in ((4000, 8), (10, 3), (7, 8)):
+        spans = [shard.shard_range(n, r, w) for r in range(w)]
+        assert spans[0][0] == 0 and spans[-1][1] == n
+        assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+        assert max(hi - lo for lo, hi in spans) - min(hi - lo for lo, hi in spans) <= 1
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, out):
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        # (1) kNN: each rank scores its block of queries; rows are gathered in query order
+        n_q, n_c, k1 = 7, 5, 3
+        gen = torch.Generator().manual_seed(0)
+        scores = torch.rand(n_q, n_c, generator=gen)
+        lo, hi = shard.shard_range(n_q, rank, world)
+        local = scores[lo:hi].topk(k1, dim=-1).indices
+        graph = shard.gather_rows(local, n_q, rank, world)
+        # (2) training: gradients averaged over ranks with one flat all-reduce
+        grads = [torch.full((3,), float(rank + 1)), torch.full((2, 2), float(10 * (rank + 1)))]
+        shard.allreduce_mean_(grads, world)
+        if rank == 0:
+            torch.save({"graph": graph, "ref": scores.topk(k1, dim=-1).indices, "g0": grads[0], "g1": grads[1]}, out)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_sharding_over_gloo(tmp_path):
+    import torch.multiprocessing as mp
+    out = str(tmp_path / "res.pt")
+    mp.spawn(_worker, args=(2, _free_port(), out), nprocs=2, join=True)
+    r = torch.load(out)
+    assert torch.equal(r["graph"], r["ref"])
+    assert torch.allclose(r["g0"], torch.full((3,), 1.5)) and torch.allclose(r["g1"], torch.full((2, 2), 15.0))

@@ -1,0 +1,74 @@
+"""GPU parity of the MinkowskiNet attention surface (csn_b200.mink) against the reference golden
+vectors (MinkowskiNet/models/attention.py run by oracle/make_golden.py) and the CPU oracle."""
+import pytest
+import torch
+
+from csn_b200 import synth
+from tests import golden_util as G
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-3
+
+
+def _mha(seed, h, precision="fp16", return_attn=False):
+    from csn_b200 import mink
+    m = mink.MultiHeadAttention(h, 256, 256 // h, 256 // h, precision=precision, return_attn=return_attn).cuda().eval()
+    sd = synth.mink_state(seed, h)
+    m.load_state_dict({k[len("MHA."):]: v for k, v in sd.items() if k.startswith("MHA.")})
+    return m
+
+
+def test_mha_forward_backward_matches_reference():
+    g = G.load("mink_mha")
+    seed, h, Lq, Lk = (int(g[k]) for k in ("seed", "n_head", "Lq", "Lk"))
+    m = _mha(seed, h, return_attn=True)
+    gen = synth.gen(seed + 1)
+    q = torch.relu(torch.randn(1, Lq, 256, generator=gen)).cuda().requires_grad_(True)
+    k = torch.relu(torch.randn(1, Lk, 256, generator=gen)).cuda().requires_grad_(True)
+    out, attn = m(q, k, k)
+    gy = torch.randn(out.shape, generator=gen).cuda()
+    (out * gy).sum().backward()
+    assert out.shape == (1, Lq, 256) and attn.shape == (1, h, Lq, Lk)
+    G.compare_sampled(g, "out", out, TOL)
+    G.compare_sampled(g, "attn", attn, 4 * TOL)
+    G.compare_sampled(g, "grad.q", q.grad, TOL)
+    G.compare_sampled(g, "grad.k", k.grad, TOL)
+    for pname in ("w_qs.weight", "w_ks.weight", "w_vs.weight", "fc.weight", "norm.weight", "norm.bias"):
+        G.compare_sampled(g, "grad." + pname, dict(m.named_parameters())[pname].grad, TOL, what=pname)
+
+
+def test_ragged_self_attention_against_oracle():
+    """Lengths that are not multiples of 128, q is k (SSA call pattern hrnet.py:461-463)."""
+    from oracle import csa_oracle as O
+    h = 4
+    m = _mha(7, h)
+    w = synth.mink_state(7, h)
+    for L in (37, 129, 1000):
+        x = torch.relu(torch.randn(1, L, 256, generator=synth.gen(L)))
+        want, _ = O.mha_mink(x, x, x, w, h)
+        got, attn = m(x.cuda(), x.cuda(), x.cuda())
+        assert attn is None
+        assert G.rel_err(got.cpu(), want) < TOL, L
+
+
+def test_csa_head_against_oracle():
+    """CSA block of HRNetSimCSN.forward (hrnet.py:370-417) on a ragged batch, K = 2."""
+    from csn_b200 import mink
+    from oracle import csa_oracle as O
+    h = 4
+    head = mink.CSAHead(256, h).cuda().eval()
+    sd = synth.mink_state(9, h)
+    head.load_state_dict(sd)
+    gen = synth.gen(10)
+    lens_q, lens_k = [150, 333], [[200, 129], [90, 400]]
+    qf = [torch.relu(torch.randn(n, 256, generator=gen)) for n in lens_q]
+    kf = [[torch.relu(torch.randn(n, 256, generator=gen)) for n in ln] for ln in lens_k]
+    want = O.mink_csa_block(qf, kf, sd, h)
+    with torch.no_grad():
+        got = head([t.cuda() for t in qf], [[t.cuda() for t in lst] for lst in kf])
+    for a, b in zip(got, want):
+        assert G.rel_err(a.cpu(), b) < TOL
+    sim = mink.cosine_similarity(qf[0].cuda(), kf[0][1].cuda()).item()
+    assert abs(sim - O.mink_cosine_similarity(qf[0], kf[0][1]).item()) < 1e-5
+    s = torch.tensor([0.1, 0.9, 0.5, 0.7]).cuda()
+    assert mink.topk_neighbors(s, 2, self_index=1).tolist() == O.mink_topk_neighbors(s.cpu(), 2, self_index=1).tolist()
