@@ -58,10 +58,11 @@ struct BwdCfg {
   static constexpr int SMEM_BYTES = 2 * TILE_BYTES + DS_BYTES + NST * SLOT_BYTES + 256 + 1024;
 };
 
-template <int DH>
+template <int DH, int CL>
 __global__ void __launch_bounds__(256, 1)
 attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmDO,
                    const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
+                   const __grid_constant__ CUtensorMap tmDS, const __grid_constant__ CUtensorMap tmDQ,
                    const __grid_constant__ AttnBwdArgs p) {
   using Cfg = BwdCfg<DH>;
   extern __shared__ uint8_t smem_raw[];
@@ -96,7 +97,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < Cfg::NST; ++s) {
       mbar_init(kv_full(s), 1);
-      mbar_init(kv_empty(s), 1);
+      mbar_init(kv_empty(s), CL);
     }
     mbar_init(bq_full, 1);
     mbar_init(bq_empty, 1);
@@ -113,9 +114,16 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     tmem_relinquish();
   }
   tc_fence_before();
-  __syncthreads();
+  if (CL > 1) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+
+  // CL == 2: items 2m / 2m+1 (two query tiles of one (block, chunk, head)) stream the same K / V tiles;
+  // each CTA of the cluster loads half of every streamed slot and multicasts it to both.
+  const int rank = (CL > 1) ? (int)cluster_ctarank() : 0;
+  const int worker = (int)blockIdx.x / CL, n_workers = (int)gridDim.x / CL;
+  const int n_work = p.n_items / CL;
+  constexpr uint16_t MC_MASK = (1u << CL) - 1;
 
   if (warp == 0) {
     // ================================================================== TMA producer
@@ -128,13 +136,17 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
           mbar_wait(kv_empty(st), ph ^ 1);
           mbar_arrive_expect_tx(kv_full(st), Cfg::SLOT_BYTES);
 #pragma unroll
-          for (int kb = 0; kb < Cfg::KB_PER_SLOT; ++kb)
-            tma_load_2d(sKV + st * Cfg::SLOT_BYTES + kb * 16384, tm, kv_full(st), col0 + (s * Cfg::KB_PER_SLOT + kb) * 64, row0);
+          for (int kb = 0; kb < Cfg::KB_PER_SLOT; ++kb) {
+            const uint32_t dst = sKV + st * Cfg::SLOT_BYTES + kb * 16384;
+            const int c0 = col0 + (s * Cfg::KB_PER_SLOT + kb) * 64;
+            if (CL == 1) tma_load_2d(dst, tm, kv_full(st), c0, row0);
+            else if ((kb % CL) == rank) tma_load_2d_mc(dst, tm, kv_full(st), c0, row0, MC_MASK);
+          }
           if (++st == Cfg::NST) { st = 0; ph ^= 1; }
         }
       };
-      for (int w = blockIdx.x; w < p.n_items; w += gridDim.x) {
-        const AttnBwdItem it = p.items[w];
+      for (int wk = worker; wk < n_work; wk += n_workers) {
+        const AttnBwdItem it = p.items[wk * CL + rank];
         const int nkv = (it.kv_len + 127) >> 7;
         mbar_wait(bq_empty, q_ph ^ 1);
         mbar_arrive_expect_tx(bq_full, 2 * Cfg::TILE_BYTES);
@@ -170,12 +182,12 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
               umma_f16_ss(d_tmem, umma_desc_sw128(a_tile + k * 32, 0, 1024), umma_desc_sw128(b_tile + k * 32, 0, 1024),
                           p.idesc_s, (s | kb | k) ? 1u : 0u);
           }
-          umma_commit(kv_empty(st));
+          if (CL == 1) umma_commit(kv_empty(st)); else umma_commit_mc(kv_empty(st), MC_MASK);
           if (++st == Cfg::NST) { st = 0; ph ^= 1; }
         }
       };
-      for (int w = blockIdx.x; w < p.n_items; w += gridDim.x) {
-        const AttnBwdItem it = p.items[w];
+      for (int wk = worker; wk < n_work; wk += n_workers) {
+        const AttnBwdItem it = p.items[wk * CL + rank];
         const int nkv = (it.kv_len + 127) >> 7;
         mbar_wait(bq_full, q_ph);
         q_ph ^= 1;
@@ -204,7 +216,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
               umma_f16_ss(d_tmem, umma_desc_sw128(a_addr, 0, 1024), umma_desc_sw128(k_tile + k * 2048, 16384, 1024),
                           p.idesc_dq, (j | k) ? 1u : 0u);
             }
-            umma_commit(kv_empty(st));
+            if (CL == 1) umma_commit(kv_empty(st)); else umma_commit_mc(kv_empty(st), MC_MASK);
             if (++st == Cfg::NST) { st = 0; ph ^= 1; }
           }
           umma_commit(ds_empty);
@@ -229,13 +241,12 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
       return *reinterpret_cast<uint32_t*>(&h);
     };
-    for (int w = blockIdx.x; w < p.n_items; w += gridDim.x) {
-      const AttnBwdItem it = p.items[w];
+    for (int wk = worker; wk < n_work; wk += n_workers) {
+      const AttnBwdItem it = p.items[wk * CL + rank];
       const int nkv = (it.kv_len + 127) >> 7;
       const bool valid = r < it.q_valid;
       const float lse_l2 = valid ? p.lse[it.stat_off + r] * LOG2E : 0.f;
       const float dlt = valid ? p.delta[it.stat_off + r] : 0.f;
-      uint16_t* ds_row = reinterpret_cast<uint16_t*>(p.dS) + (long long)(it.ds_row0 + r) * p.ldds + it.ds_col0;
       for (int j = 0; j < nkv; ++j) {
         mbar_wait(sdp_full, sdp_ph);
         sdp_ph ^= 1;
@@ -262,6 +273,8 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
           if (!waited) {
             mbar_wait(ds_empty, dse_ph ^ 1);   // dQ MMAs of the previous tile no longer read the staging tile
             dse_ph ^= 1;
+            if (warp == 4 && lane == 0) tma_store_wait_read<0>();   // ... nor does its TMA store to HBM
+            asm volatile("bar.sync 1, 128;" ::: "memory");
             waited = true;
           }
           uint8_t* rowp = sDS_ptr + (c >> 6) * 16384 + r * 128;
@@ -269,43 +282,70 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 #pragma unroll
           for (int t = 0; t < 4; ++t) {
             const int ch = (chunk0 + t) ^ (r & 7);
-            const uint4 val = make_uint4(pk[4 * t], pk[4 * t + 1], pk[4 * t + 2], pk[4 * t + 3]);
-            *reinterpret_cast<uint4*>(rowp + ch * 16) = val;
-            *reinterpret_cast<uint4*>(ds_row + j * 128 + c + t * 8) = val;   // HBM copy for dK = dS^T Q
+            *reinterpret_cast<uint4*>(rowp + ch * 16) = make_uint4(pk[4 * t], pk[4 * t + 1], pk[4 * t + 2], pk[4 * t + 3]);
           }
         }
         tc_fence_before();
         mbar_arrive(sdp_empty);
         fence_proxy_async_smem();
         mbar_arrive(ds_full);
+        // HBM copy of dS_j for dK = dS^T Q: the staged tile is exactly two TMA boxes [128 rows x 64 keys]
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (warp == 4 && lane == 0) {
+          tma_store_2d(&tmDS, sDS, it.ds_col0 + j * 128, it.ds_row0);
+          tma_store_2d(&tmDS, sDS + 16384, it.ds_col0 + j * 128 + 64, it.ds_row0);
+          tma_store_commit();
+        }
       }
       // ---- epilogue: dQ tile -> 16-bit
       mbar_wait(dq_full, dqf_ph);
       dqf_ph ^= 1;
       tc_fence_after();
-      uint16_t* orow = reinterpret_cast<uint16_t*>(p.dQ) + (long long)(it.o_row0 + r) * p.lddq + it.col0;
+      // dQ tile -> 16-bit through this warp's own rows of the dS staging tile and TMA stores (rows >= q_valid: zeros).
+      // The last dS_j of this item has been consumed (dq_full) and its HBM copy is drained first.
+      if (warp == 4 && lane == 0) tma_store_wait_read<0>();
+      asm volatile("bar.sync 1, 128;" ::: "memory");
       const uint32_t o_addr = tmem_base + lane_addr + 256;
+      int slab = 0;
 #pragma unroll 1
-      for (int c = 0; c < DH; c += 32) {
-        uint32_t v[32];
-        tmem_ld_32x32(o_addr + c, v);
+      for (int c = 0; c < DH; c += 64) {
+        uint32_t v0[32], v1[32];
+        tmem_ld_32x32(o_addr + c, v0);
+        tmem_ld_32x32(o_addr + c + 32, v1);
         tmem_ld_wait();
+        uint32_t w[32];
 #pragma unroll
-        for (int i = 0; i < 32; i += 8) {
-          uint32_t w4[4];
-#pragma unroll
-          for (int t = 0; t < 4; ++t)
-            w4[t] = pack_pair(valid ? __uint_as_float(v[i + 2 * t]) : 0.f, valid ? __uint_as_float(v[i + 2 * t + 1]) : 0.f);
-          if (valid || (it.flags & 1)) *reinterpret_cast<uint4*>(orow + c + i) = make_uint4(w4[0], w4[1], w4[2], w4[3]);
+        for (int i = 0; i < 32; i += 2) {
+          w[i >> 1] = pack_pair(valid ? __uint_as_float(v0[i]) : 0.f, valid ? __uint_as_float(v0[i + 1]) : 0.f);
+          w[16 + (i >> 1)] = pack_pair(valid ? __uint_as_float(v1[i]) : 0.f, valid ? __uint_as_float(v1[i + 1]) : 0.f);
         }
+        const uint32_t buf = sDS + (slab & 1) * 16384 + q * 4096;
+        if (lane == 0) tma_store_wait_read<1>();
+        __syncwarp();
+        const uint32_t rowaddr = buf + lane * 128;
+#pragma unroll
+        for (int t = 0; t < 8; ++t) {
+          const uint32_t a = rowaddr + (((uint32_t)t ^ ((uint32_t)lane & 7u)) << 4);
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(w[4 * t]), "r"(w[4 * t + 1]), "r"(w[4 * t + 2]), "r"(w[4 * t + 3]) : "memory");
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_2d(&tmDQ, buf, it.col0 + c, it.o_row0 + q * 32);
+          tma_store_commit();
+        }
+        ++slab;
       }
+      if (lane == 0) tma_store_wait_read<0>();
+      __syncwarp();
       tc_fence_before();
       mbar_arrive(dq_empty);
     }
+    if (lane == 0) tma_store_wait_all();
   }
 
   tc_fence_before();
-  __syncthreads();
+  if (CL > 1) cluster_sync_all(); else __syncthreads();
   if (warp == 2) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
@@ -349,18 +389,33 @@ __global__ void attn_delta_kernel(const void* __restrict__ dO, const void* __res
   }
 }
 
-template <int DH>
+template <int DH, int CL>
 static int launch_dq(const CUtensorMap& tmQ, const CUtensorMap& tmDO, const CUtensorMap& tmK, const CUtensorMap& tmV,
-                     const AttnBwdArgs& a, cudaStream_t stream) {
+                     const CUtensorMap& tmDS, const CUtensorMap& tmDQ, const AttnBwdArgs& a, cudaStream_t stream) {
   using Cfg = BwdCfg<DH>;
-  auto kern = attn_bwd_dq_kernel<DH>;
+  auto kern = attn_bwd_dq_kernel<DH, CL>;
   static bool configured = false;
   if (!configured) {
     CSN_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     configured = true;
   }
-  const int grid = a.n_items < num_sms() ? a.n_items : num_sms();
-  kern<<<grid, 256, Cfg::SMEM_BYTES, stream>>>(tmQ, tmDO, tmK, tmV, a);
+  const int n_work = a.n_items / CL;
+  const int workers = num_sms() / CL;
+  const int grid = (n_work < workers ? n_work : workers) * CL;
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(256);
+  cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CL;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  CSN_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, tmQ, tmDO, tmK, tmV, tmDS, tmDQ, a));
   CSN_LAUNCH_OK("attn_bwd_dq_kernel");
   return 0;
 }
@@ -386,7 +441,8 @@ int csn_attn_delta(const void* dO, const void* O, const void* O_lo, float* delta
 int csn_attn_bwd_dq(const void* Q, const void* dO, const void* K, const void* V, int64_t q_rows, int64_t do_rows,
                     int64_t kv_rows, int64_t width, int64_t ldq, int64_t lddo, int64_t ldk, int64_t ldv,
                     int32_t d_head, int32_t dtype, const int32_t* items, int32_t n_items, void* dQ, int64_t lddq,
-                    void* dS, int64_t ldds, const float* lse, const float* delta, void* stream) {
+                    void* dS, int64_t ds_rows, int64_t ldds, const float* lse, const float* delta, int32_t paired,
+                    void* stream) {
   using namespace csn;
   clear_error();
   CSN_CHECK_ARG(Q && dO && K && V && items && dQ && dS && lse && delta, "csn_attn_bwd_dq: null pointer");
@@ -403,6 +459,11 @@ int csn_attn_bwd_dq(const void* Q, const void* dO, const void* K, const void* V,
   if (rc) return rc;
   rc = make_tmap_2d(&tmV, V, dtype, width, kv_rows, ldv, 64, 128);
   if (rc) return rc;
+  CUtensorMap tmDS, tmDQ;
+  rc = make_tmap_2d(&tmDS, dS, dtype, ldds, ds_rows, ldds, 64, 128);
+  if (rc) return rc;
+  rc = make_tmap_2d(&tmDQ, dQ, dtype, width, do_rows, lddq, 64, 32);
+  if (rc) return rc;
   AttnBwdArgs a;
   a.items = reinterpret_cast<const AttnBwdItem*>(items);
   a.n_items = n_items;
@@ -415,8 +476,11 @@ int csn_attn_bwd_dq(const void* Q, const void* dO, const void* K, const void* V,
   a.idesc_s = umma_idesc_f16(fmt, 0, 0, 128);
   a.idesc_dq = umma_idesc_f16(fmt, 0, 1, d_head == 256 ? 128u : 64u);
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-  if (d_head == 256) return launch_dq<256>(tmQ, tmDO, tmK, tmV, a, s);
-  return launch_dq<64>(tmQ, tmDO, tmK, tmV, a, s);
+  if (d_head == 256) {
+    if (paired && n_items % 2 == 0) return launch_dq<256, 2>(tmQ, tmDO, tmK, tmV, tmDS, tmDQ, a, s);
+    return launch_dq<256, 1>(tmQ, tmDO, tmK, tmV, tmDS, tmDQ, a, s);
+  }
+  return launch_dq<64, 1>(tmQ, tmDO, tmK, tmV, tmDS, tmDQ, a, s);
 }
 
 }  // extern "C"

@@ -72,10 +72,11 @@ struct AttnCfg {
   static constexpr int O_COL = 256;                        // TMEM: S0 @0, S1 @128, O @256 (DH <= 256)
 };
 
-template <int DH, int MODE>
+template <int DH, int MODE, int CL>
 __global__ void __launch_bounds__(256, 1)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
-                const __grid_constant__ CUtensorMap tmV, const __grid_constant__ AttnFwdArgs p) {
+                const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmO,
+                const __grid_constant__ CUtensorMap tmOlo, const __grid_constant__ AttnFwdArgs p) {
   using Cfg = AttnCfg<DH>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -107,7 +108,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < Cfg::NST; ++s) {
       mbar_init(kv_full(s), 1);
-      mbar_init(kv_empty(s), 1);
+      mbar_init(kv_empty(s), CL);   // the slot is refilled by multicast: every CTA of the cluster must have drained it
     }
     mbar_init(bq_full, 1);
     mbar_init(bq_empty, 1);
@@ -126,9 +127,17 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     tmem_relinquish();
   }
   tc_fence_before();
-  __syncthreads();
+  if (CL > 1) cluster_sync_all(); else __syncthreads();   // barrier inits visible cluster-wide before any remote arrive
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+
+  // Work distribution. CL == 2: the two CTAs of a cluster take items 2m and 2m+1, which by construction
+  // of the table share every streamed tile (same key range); each CTA loads half of every streamed slot
+  // and multicasts it to both, halving the L2 -> SM traffic of the streamed operands.
+  const int rank = (CL > 1) ? (int)cluster_ctarank() : 0;
+  const int worker = (int)blockIdx.x / CL, n_workers = (int)gridDim.x / CL;
+  const int n_work = p.n_items / CL;
+  constexpr uint16_t MC_MASK = (1u << CL) - 1;
 
   if (warp == 0) {
     // ================================================================== TMA producer
@@ -141,9 +150,12 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           mbar_wait(kv_empty(st), ph ^ 1);
           mbar_arrive_expect_tx(kv_full(st), Cfg::SLOT_BYTES);
 #pragma unroll
-          for (int kb = 0; kb < Cfg::KB_PER_KSLOT; ++kb)
-            tma_load_2d(sKV + st * Cfg::SLOT_BYTES + kb * 16384, &tmK, kv_full(st),
-                        it.col0 + (s * Cfg::KB_PER_KSLOT + kb) * 64, it.kv_row0 + j * 128);
+          for (int kb = 0; kb < Cfg::KB_PER_KSLOT; ++kb) {
+            const uint32_t dst = sKV + st * Cfg::SLOT_BYTES + kb * 16384;
+            const int c0 = it.col0 + (s * Cfg::KB_PER_KSLOT + kb) * 64, c1 = it.kv_row0 + j * 128;
+            if (CL == 1) tma_load_2d(dst, &tmK, kv_full(st), c0, c1);
+            else if ((kb % CL) == rank) tma_load_2d_mc(dst, &tmK, kv_full(st), c0, c1, MC_MASK);
+          }
           if (++st == Cfg::NST) { st = 0; ph ^= 1; }
         }
       };
@@ -154,14 +166,17 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           mbar_arrive_expect_tx(kv_full(st), Cfg::SLOT_BYTES);
           // MN-major: one box of [KEYS_PER_VSLOT key rows x 64 columns] per 64-column atom
 #pragma unroll
-          for (int a = 0; a < Cfg::KB; ++a)
-            tma_load_2d(sKV + st * Cfg::SLOT_BYTES + a * (Cfg::KEYS_PER_VSLOT * 128), &tmV, kv_full(st),
-                        it.col0 + a * 64, it.v_row0 + j * 128 + s * Cfg::KEYS_PER_VSLOT);
+          for (int a = 0; a < Cfg::KB; ++a) {
+            const uint32_t dst = sKV + st * Cfg::SLOT_BYTES + a * (Cfg::KEYS_PER_VSLOT * 128);
+            const int c0 = it.col0 + a * 64, c1 = it.v_row0 + j * 128 + s * Cfg::KEYS_PER_VSLOT;
+            if (CL == 1) tma_load_2d(dst, &tmV, kv_full(st), c0, c1);
+            else if ((a % CL) == rank) tma_load_2d_mc(dst, &tmV, kv_full(st), c0, c1, MC_MASK);
+          }
           if (++st == Cfg::NST) { st = 0; ph ^= 1; }
         }
       };
-      for (int w = blockIdx.x; w < p.n_items; w += gridDim.x) {
-        const AttnItem it = p.items[w];
+      for (int wk = worker; wk < n_work; wk += n_workers) {
+        const AttnItem it = p.items[wk * CL + rank];
         const int nkv = (it.kv_len + 127) >> 7;
         mbar_wait(bq_empty, q_ph ^ 1);
         mbar_arrive_expect_tx(bq_full, Cfg::Q_BYTES);
@@ -197,19 +212,22 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             const uint32_t a_tile = sQ + (s * Cfg::KB_PER_KSLOT + kb) * 16384;
             const uint32_t b_tile = sKV + st * Cfg::SLOT_BYTES + kb * 16384;
 #pragma unroll
-            for (int k = 0; k < 4; ++k)
-              umma_f16_ss(d_tmem, umma_desc_sw128(a_tile + k * 32, 0, 1024), umma_desc_sw128(b_tile + k * 32, 0, 1024),
-                          p.idesc_qk, (s | kb | k) ? 1u : 0u);
+            for (int k = 0; k < 4; ++k) {
+              // forward: S[query][key] = Q(resident) K(streamed)^T ; dV mode: S[query][key] = Q(streamed) K(resident)^T
+              const uint64_t da = umma_desc_sw128((MODE == 0 ? a_tile : b_tile) + k * 32, 0, 1024);
+              const uint64_t db = umma_desc_sw128((MODE == 0 ? b_tile : a_tile) + k * 32, 0, 1024);
+              umma_f16_ss(d_tmem, da, db, p.idesc_qk, (s | kb | k) ? 1u : 0u);
+            }
           }
-          umma_commit(kv_empty(st));
+          if (CL == 1) umma_commit(kv_empty(st)); else umma_commit_mc(kv_empty(st), MC_MASK);
           if (++st == Cfg::NST) { st = 0; ph ^= 1; }
         }
         umma_commit(s_full(b));
         if (last) umma_commit(bq_empty);  // every QK^T of this item has been issued: Q tile may be replaced
         s_ph[b] ^= 1;
       };
-      for (int w = blockIdx.x; w < p.n_items; w += gridDim.x) {
-        const AttnItem it = p.items[w];
+      for (int wk = worker; wk < n_work; wk += n_workers) {
+        const AttnItem it = p.items[wk * CL + rank];
         const int nkv = (it.kv_len + 127) >> 7;
         mbar_wait(bq_full, q_ph);
         q_ph ^= 1;
@@ -228,13 +246,16 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             const uint32_t v_tile = sKV + st * Cfg::SLOT_BYTES;
 #pragma unroll
             for (int k = 0; k < Cfg::KEYS_PER_VSLOT / 16; ++k) {
-              const int key = s * Cfg::KEYS_PER_VSLOT + k * 16;  // key offset inside the 128-key tile
-              const uint32_t a_addr = sP + (key >> 6) * 16384 + (key & 63) * 2;
-              umma_f16_ss(o_tmem, umma_desc_sw128(a_addr, 0, 1024),
-                          umma_desc_sw128(v_tile + k * 2048, Cfg::KEYS_PER_VSLOT * 128, 1024), p.idesc_pv,
+              const int key = s * Cfg::KEYS_PER_VSLOT + k * 16;  // offset along the contraction inside the 128-row tile
+              // forward: A = P[query][key], K-major (contraction over keys: 32 B per step inside a swizzled row)
+              // dV mode: A = P^T: the same tile [query rows][keys] read MN-major (M = keys contiguous, two
+              //          64-key atoms 16 KB apart; contraction over queries: 16 rows = 2048 B per step)
+              const uint64_t da = (MODE == 0) ? umma_desc_sw128(sP + (key >> 6) * 16384 + (key & 63) * 2, 0, 1024)
+                                              : umma_desc_sw128(sP + (key >> 4) * 2048, 16384, 1024);
+              umma_f16_ss(o_tmem, da, umma_desc_sw128(v_tile + k * 2048, Cfg::KEYS_PER_VSLOT * 128, 1024), p.idesc_pv,
                           (j | s | k) ? 1u : 0u);
             }
-            umma_commit(kv_empty(st));
+            if (CL == 1) umma_commit(kv_empty(st)); else umma_commit_mc(kv_empty(st), MC_MASK);
             if (++st == Cfg::NST) { st = 0; ph ^= 1; }
           }
           umma_commit(bp_empty);  // P buffer free / O accumulation of tile j complete
@@ -269,8 +290,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
       return *reinterpret_cast<uint32_t*>(&h);
     };
-    for (int w = blockIdx.x; w < p.n_items; w += gridDim.x) {
-      const AttnItem it = p.items[w];
+    for (int wk = worker; wk < n_work; wk += n_workers) {
+      const AttnItem it = p.items[wk * CL + rank];
       const int nkv = (it.kv_len + 127) >> 7;
       float m_used = -INFINITY;  // reference max (raw score units)
       float l = 0.f;
@@ -283,8 +304,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         const int nvalid = min(128, it.kv_len - j * 128);
         bool waited_p = false;
         if (MODE == 1) {
-          // ---- dV mode: P^T[key][query] = exp(s*scale - lse[query]); statistics come from the forward pass
-          const float* lse_t = p.lse + it.lse_off + j * 128;
+          // ---- dV mode: lane = query row of the streamed tile, columns = the resident keys.
+          //      P[query][key] = exp(s*scale - lse[query]); statistics come from the forward pass.
+          const bool rvalid = r < nvalid;                       // query row exists
+          const float lse_l2 = rvalid ? p.lse[it.lse_off + j * 128 + r] * LOG2E : 0.f;
+          const int cvalid = rvalid ? it.q_valid : 0;           // resident key columns that exist
 #pragma unroll 1
           for (int c = 0; c < 128; c += 64) {
             uint32_t v0[32], v1[32];
@@ -294,10 +318,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             uint32_t pk[32];
 #pragma unroll
             for (int i = 0; i < 32; i += 2) {
-              const float a0 = (c + i < nvalid) ? fast_exp2(__uint_as_float(v0[i]) * p.scale_log2 - __ldg(lse_t + c + i) * LOG2E) : 0.f;
-              const float a1 = (c + i + 1 < nvalid) ? fast_exp2(__uint_as_float(v0[i + 1]) * p.scale_log2 - __ldg(lse_t + c + i + 1) * LOG2E) : 0.f;
-              const float b0 = (c + 32 + i < nvalid) ? fast_exp2(__uint_as_float(v1[i]) * p.scale_log2 - __ldg(lse_t + c + 32 + i) * LOG2E) : 0.f;
-              const float b1 = (c + 33 + i < nvalid) ? fast_exp2(__uint_as_float(v1[i + 1]) * p.scale_log2 - __ldg(lse_t + c + 33 + i) * LOG2E) : 0.f;
+              const float a0 = (c + i < cvalid) ? fast_exp2(__uint_as_float(v0[i]) * p.scale_log2 - lse_l2) : 0.f;
+              const float a1 = (c + i + 1 < cvalid) ? fast_exp2(__uint_as_float(v0[i + 1]) * p.scale_log2 - lse_l2) : 0.f;
+              const float b0 = (c + 32 + i < cvalid) ? fast_exp2(__uint_as_float(v1[i]) * p.scale_log2 - lse_l2) : 0.f;
+              const float b1 = (c + 33 + i < cvalid) ? fast_exp2(__uint_as_float(v1[i + 1]) * p.scale_log2 - lse_l2) : 0.f;
               pk[i >> 1] = pack_pair(a0, a1);
               pk[16 + (i >> 1)] = pack_pair(b0, b1);
             }
@@ -418,72 +442,121 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       tc_fence_after();
       const float inv_l = (MODE == 1) ? 1.f : 1.f / l;
       const bool valid = r < it.q_valid;
-      uint16_t* orow = reinterpret_cast<uint16_t*>(p.O) + (long long)(it.o_row0 + r) * p.ldo + it.col0;
-      uint16_t* lrow = (MODE == 0 && p.Olo) ? reinterpret_cast<uint16_t*>(p.Olo) + (long long)(it.o_row0 + r) * p.ldo + it.col0 : nullptr;
+      const bool want_lo = (MODE == 0) && p.Olo != nullptr;
       const float lo_scale = p.dtype == CSN_F16 ? 2048.f : 256.f;
       const uint32_t o_addr = tmem_base + lane_addr + Cfg::O_COL;
+      // Coalesced output: every warp stages [its 32 rows x 64 columns] slabs in ITS OWN rows of the (now idle)
+      // P tile — 128B-swizzled, conflict-free 16-byte writes — and hands them to the TMA store engine; two
+      // slabs per warp are in flight. Rows >= q_valid are written as zeros (outputs live in padded layouts).
+      int slab = 0;
 #pragma unroll 1
-      for (int c = 0; c < DH; c += 32) {
-        uint32_t v[32];
-        tmem_ld_32x32(o_addr + c, v);
+      for (int c = 0; c < DH; c += 64) {
+        uint32_t v0[32], v1[32];
+        tmem_ld_32x32(o_addr + c, v0);
+        tmem_ld_32x32(o_addr + c + 32, v1);
         tmem_ld_wait();
+        uint32_t hi[32], lo[32];
 #pragma unroll
-        for (int i = 0; i < 32; i += 8) {
-          uint32_t w4[4], l4[4];
-#pragma unroll
-          for (int t = 0; t < 4; ++t) {
-            const float a = valid ? __uint_as_float(v[i + 2 * t]) * inv_l : 0.f;
-            const float bb = valid ? __uint_as_float(v[i + 2 * t + 1]) * inv_l : 0.f;
-            w4[t] = pack_pair(a, bb);
-            if (MODE == 0) {
-              float2 hi;
-              if (p.dtype == CSN_F16) hi = __half22float2(*reinterpret_cast<__half2*>(&w4[t]));
-              else hi = __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&w4[t]));
-              l4[t] = pack_pair((a - hi.x) * lo_scale, (bb - hi.y) * lo_scale);
+        for (int i = 0; i < 32; i += 2) {
+          const float a0 = valid ? __uint_as_float(v0[i]) * inv_l : 0.f, a1 = valid ? __uint_as_float(v0[i + 1]) * inv_l : 0.f;
+          const float b0 = valid ? __uint_as_float(v1[i]) * inv_l : 0.f, b1 = valid ? __uint_as_float(v1[i + 1]) * inv_l : 0.f;
+          hi[i >> 1] = pack_pair(a0, a1);
+          hi[16 + (i >> 1)] = pack_pair(b0, b1);
+          if (want_lo) {
+            float2 ha, hb;
+            if (p.dtype == CSN_F16) {
+              ha = __half22float2(*reinterpret_cast<__half2*>(&hi[i >> 1]));
+              hb = __half22float2(*reinterpret_cast<__half2*>(&hi[16 + (i >> 1)]));
+            } else {
+              ha = __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&hi[i >> 1]));
+              hb = __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&hi[16 + (i >> 1)]));
             }
-          }
-          if (valid || (it.flags & 1)) {
-            *reinterpret_cast<uint4*>(orow + c + i) = make_uint4(w4[0], w4[1], w4[2], w4[3]);
-            if (MODE == 0 && lrow) *reinterpret_cast<uint4*>(lrow + c + i) = make_uint4(l4[0], l4[1], l4[2], l4[3]);
+            lo[i >> 1] = pack_pair((a0 - ha.x) * lo_scale, (a1 - ha.y) * lo_scale);
+            lo[16 + (i >> 1)] = pack_pair((b0 - hb.x) * lo_scale, (b1 - hb.y) * lo_scale);
           }
         }
+#pragma unroll 1
+        for (int which = 0; which < (want_lo ? 2 : 1); ++which) {
+          const uint32_t buf = sP + (slab & 1) * 16384 + q * 4096;
+          if (lane == 0) tma_store_wait_read<1>();
+          __syncwarp();
+          const uint32_t rowaddr = buf + lane * 128;
+#pragma unroll
+          for (int t = 0; t < 8; ++t) {
+            const uint32_t a = rowaddr + (((uint32_t)t ^ ((uint32_t)lane & 7u)) << 4);
+            if (which == 0)
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(hi[4 * t]), "r"(hi[4 * t + 1]), "r"(hi[4 * t + 2]), "r"(hi[4 * t + 3]) : "memory");
+            else
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(lo[4 * t]), "r"(lo[4 * t + 1]), "r"(lo[4 * t + 2]), "r"(lo[4 * t + 3]) : "memory");
+          }
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_2d(which == 0 ? &tmO : &tmOlo, buf, it.col0 + c, it.o_row0 + q * 32);
+            tma_store_commit();
+          }
+          ++slab;
+        }
       }
-      if (MODE == 0 && p.lse && (valid || (it.flags & 1))) p.lse[it.lse_off + r] = valid ? (m_used * p.scale + __logf(l)) : 0.f;
+      if (lane == 0) tma_store_wait_read<0>();   // this warp's rows of the P tile are written again by the next item
+      __syncwarp();
+      if (MODE == 0 && p.lse) p.lse[it.lse_off + r] = valid ? (m_used * p.scale + __logf(l)) : 0.f;
       tc_fence_before();
       mbar_arrive(bo_empty);
     }
+    if (lane == 0) tma_store_wait_all();
   }
 
   tc_fence_before();
-  __syncthreads();
+  if (CL > 1) cluster_sync_all(); else __syncthreads();   // no CTA exits while its peer may still signal its barriers
   if (warp == 2) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
   }
 }
 
-template <int DH, int MODE>
+template <int DH, int MODE, int CL>
 static int launch_attn_fwd(const CUtensorMap& tmQ, const CUtensorMap& tmK, const CUtensorMap& tmV,
-                           const AttnFwdArgs& a, cudaStream_t stream) {
+                           const CUtensorMap& tmO, const CUtensorMap& tmOlo, const AttnFwdArgs& a, cudaStream_t stream) {
   using Cfg = AttnCfg<DH>;
-  auto kern = attn_fwd_kernel<DH, MODE>;
+  auto kern = attn_fwd_kernel<DH, MODE, CL>;
   static bool configured = false;
   if (!configured) {
     CSN_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     configured = true;
   }
-  const int grid = a.n_items < num_sms() ? a.n_items : num_sms();
-  kern<<<grid, 256, Cfg::SMEM_BYTES, stream>>>(tmQ, tmK, tmV, a);
+  const int n_work = a.n_items / CL;
+  const int workers = num_sms() / CL;
+  const int grid = (n_work < workers ? n_work : workers) * CL;
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(256);
+  cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CL;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  CSN_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, tmQ, tmK, tmV, tmO, tmOlo, a));
   CSN_LAUNCH_OK("attn_fwd_kernel");
   return 0;
+}
+
+// Items 2m / 2m+1 may share a cluster when they stream exactly the same tiles.
+static bool items_pairable(int n_items, int d_head, int paired_flag) {
+  return paired_flag && (n_items % 2 == 0) && d_head == 256;
 }
 
 }  // namespace csn
 
 static int attn_launch_common(int mode, const void* Q, const void* K, const void* V, int64_t q_rows, int64_t kv_rows,
                               int64_t v_rows, int64_t width, int64_t ldq, int64_t ldk, int64_t ldv, int32_t d_head, int32_t dtype,
-                              const int32_t* items, int32_t n_items, void* O, int64_t ldo, float* lse,
-                              void* Olo, void* stream) {
+                              const int32_t* items, int32_t n_items, void* O, int64_t o_rows, int64_t ldo, float* lse,
+                              void* Olo, int32_t paired, void* stream) {
   using namespace csn;
   clear_error();
   CSN_CHECK_ARG(Q && K && V && items && O, "csn_attn_fwd: null pointer");
@@ -511,23 +584,33 @@ static int attn_launch_common(int mode, const void* Q, const void* K, const void
   a.dtype = dtype;
   const uint32_t fmt = dtype == CSN_F16 ? 0u : 1u;
   a.idesc_qk = umma_idesc_f16(fmt, 0, 0, 128);
-  a.idesc_pv = umma_idesc_f16(fmt, 0, 1, (uint32_t)d_head);
+  a.idesc_pv = umma_idesc_f16(fmt, mode == 1 ? 1u : 0u, 1, (uint32_t)d_head);   // dV mode reads P^T (MN-major A)
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  // outputs leave through TMA stores of [32 rows x 64 columns] slabs
+  CUtensorMap tmO, tmOlo;
+  rc = make_tmap_2d(&tmO, O, dtype, width, o_rows, ldo, 64, 32);
+  if (rc) return rc;
+  tmOlo = tmO;
+  if (Olo) {
+    rc = make_tmap_2d(&tmOlo, Olo, dtype, width, o_rows, ldo, 64, 32);
+    if (rc) return rc;
+  }
+  const bool pair = items_pairable(n_items, d_head, paired);
   if (mode == 0) {
-    if (d_head == 256) return launch_attn_fwd<256, 0>(tmQ, tmK, tmV, a, s);
-    return launch_attn_fwd<64, 0>(tmQ, tmK, tmV, a, s);
+    if (d_head == 256) return pair ? launch_attn_fwd<256, 0, 2>(tmQ, tmK, tmV, tmO, tmOlo, a, s) : launch_attn_fwd<256, 0, 1>(tmQ, tmK, tmV, tmO, tmOlo, a, s);
+    return launch_attn_fwd<64, 0, 1>(tmQ, tmK, tmV, tmO, tmOlo, a, s);
   }
   CSN_CHECK_ARG(lse != nullptr, "csn_attn_bwd_dv: lse is required");
-  if (d_head == 256) return launch_attn_fwd<256, 1>(tmQ, tmK, tmV, a, s);
-  return launch_attn_fwd<64, 1>(tmQ, tmK, tmV, a, s);
+  if (d_head == 256) return pair ? launch_attn_fwd<256, 1, 2>(tmQ, tmK, tmV, tmO, tmOlo, a, s) : launch_attn_fwd<256, 1, 1>(tmQ, tmK, tmV, tmO, tmOlo, a, s);
+  return launch_attn_fwd<64, 1, 1>(tmQ, tmK, tmV, tmO, tmOlo, a, s);
 }
 
 extern "C" int csn_attn_fwd(const void* Q, const void* K, const void* V, int64_t q_rows, int64_t kv_rows,
                             int64_t width, int64_t ldq, int64_t ldk, int64_t ldv, int32_t d_head, int32_t dtype,
-                            const int32_t* items, int32_t n_items, void* O, int64_t ldo, float* lse,
-                            void* O_lo, void* stream) {
+                            const int32_t* items, int32_t n_items, void* O, int64_t o_rows, int64_t ldo, float* lse,
+                            void* O_lo, int32_t paired, void* stream) {
   return attn_launch_common(0, Q, K, V, q_rows, kv_rows, kv_rows, width, ldq, ldk, ldv, d_head, dtype, items, n_items,
-                            O, ldo, lse, O_lo, stream);
+                            O, o_rows, ldo, lse, O_lo, paired, stream);
 }
 
 // dV = P^T dO with P^T recomputed from K, Q and the forward log-sum-exp. Same pipeline as the forward
@@ -536,8 +619,8 @@ extern "C" int csn_attn_fwd(const void* Q, const void* K, const void* V, int64_t
 // lse of the first streamed (query) row.
 extern "C" int csn_attn_bwd_dv(const void* Kres, const void* Qstr, const void* dO, int64_t k_rows, int64_t q_rows,
                                int64_t do_rows, int64_t width, int64_t ldk, int64_t ldq, int64_t lddo, int32_t d_head, int32_t dtype,
-                               const int32_t* items, int32_t n_items, void* dV, int64_t lddv, const float* lse,
-                               void* stream) {
+                               const int32_t* items, int32_t n_items, void* dV, int64_t dv_rows, int64_t lddv,
+                               const float* lse, int32_t paired, void* stream) {
   return attn_launch_common(1, Kres, Qstr, dO, k_rows, q_rows, do_rows, width, ldk, ldq, lddo, d_head, dtype, items,
-                            n_items, dV, lddv, const_cast<float*>(lse), nullptr, stream);
+                            n_items, dV, dv_rows, lddv, const_cast<float*>(lse), nullptr, paired, stream);
 }

@@ -264,6 +264,9 @@ struct LnBwdArgs {
   int group_rows, rows_valid, block_rows;
   int dtype;
   const float* amax;   // optional: dY is multiplied by 2^floor(log2(128/amax)) on load (power-of-two loss scaling)
+  const float* bcast;  // optional [n][256]: row vector added to every valid row of a block before anything else
+  const int* bcast_idx;  // per block: row of `bcast` (or -1)
+  float bcast_scale;
 };
 
 __global__ void __launch_bounds__(256) ln_bwd_kernel(const LnBwdArgs p) {
@@ -276,19 +279,28 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const LnBwdArgs p) {
   for (int i = 0; i < 8; ++i) {
     const long long row = row0 + warp * 8 + i;
     if (row >= p.rows) break;
-    float4* dz4 = reinterpret_cast<float4*>(p.dZ + row * DM);
+    float4* dz4 = p.dZ ? reinterpret_cast<float4*>(p.dZ + row * DM) : nullptr;
     uint2* dz16 = reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(p.dZ16) + row * DM);
     const bool valid = (int)((row % p.block_rows) % p.group_rows) < p.rows_valid;
     if (!valid) {
       const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
-      dz4[lane] = zero; dz4[32 + lane] = zero;
+      if (dz4) { dz4[lane] = zero; dz4[32 + lane] = zero; }
       dz16[lane] = make_uint2(0, 0); dz16[32 + lane] = make_uint2(0, 0);
       continue;
     }
     const float4* dy4 = reinterpret_cast<const float4*>(p.dY + row * DM);
     const float4* z4 = reinterpret_cast<const float4*>(p.Z + row * DM);
     const float mu = p.mean[row], rs = p.rstd[row];
-    const float4 da = __ldg(dy4 + lane), dc = __ldg(dy4 + 32 + lane);
+    float4 da = __ldg(dy4 + lane), dc = __ldg(dy4 + 32 + lane);
+    if (p.bcast) {
+      const int bi = __ldg(p.bcast_idx + row / p.block_rows);
+      if (bi >= 0) {
+        const float4* b4 = reinterpret_cast<const float4*>(p.bcast + (long long)bi * DM);
+        const float4 ba = __ldg(b4 + lane), bc = __ldg(b4 + 32 + lane);
+        da.x += ba.x * p.bcast_scale; da.y += ba.y * p.bcast_scale; da.z += ba.z * p.bcast_scale; da.w += ba.w * p.bcast_scale;
+        dc.x += bc.x * p.bcast_scale; dc.y += bc.y * p.bcast_scale; dc.z += bc.z * p.bcast_scale; dc.w += bc.w * p.bcast_scale;
+      }
+    }
     const float4 za = __ldg(z4 + lane), zc = __ldg(z4 + 32 + lane);
     float xh[8] = {(za.x - mu) * rs, (za.y - mu) * rs, (za.z - mu) * rs, (za.w - mu) * rs,
                    (zc.x - mu) * rs, (zc.y - mu) * rs, (zc.z - mu) * rs, (zc.w - mu) * rs};
@@ -309,8 +321,10 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const LnBwdArgs p) {
     float o[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) o[j] = rs * (g[j] - s1 - xh[j] * s2);
-    dz4[lane] = make_float4(o[0], o[1], o[2], o[3]);
-    dz4[32 + lane] = make_float4(o[4], o[5], o[6], o[7]);
+    if (dz4) {
+      dz4[lane] = make_float4(o[0], o[1], o[2], o[3]);
+      dz4[32 + lane] = make_float4(o[4], o[5], o[6], o[7]);
+    }
     dz16[lane] = make_uint2(pack2(o[0], o[1], p.dtype), pack2(o[2], o[3], p.dtype));
     dz16[32 + lane] = make_uint2(pack2(o[4], o[5], p.dtype), pack2(o[6], o[7], p.dtype));
   }
@@ -534,13 +548,15 @@ int csn_colsum_reduce(const float* part, float* out, int32_t n_blocks, int32_t p
 
 int csn_ln_bwd(const float* dY, const float* Z, const float* mean, const float* rstd, const float* gamma, float* dZ,
                void* dZ16, float* dgamma, float* dbeta, int64_t rows, int32_t block_rows, int32_t group_rows,
-               int32_t rows_valid, int32_t dtype, const float* amax, void* stream) {
+               int32_t rows_valid, int32_t dtype, const float* amax, const float* bcast, const int32_t* bcast_idx,
+               float bcast_scale, void* stream) {
   using namespace csn;
   clear_error();
-  CSN_CHECK_ARG(dY && Z && mean && rstd && gamma && dZ && dZ16 && dgamma && dbeta, "csn_ln_bwd: null pointer");
+  CSN_CHECK_ARG(dY && Z && mean && rstd && gamma && dZ16 && dgamma && dbeta, "csn_ln_bwd: null pointer");
+  CSN_CHECK_ARG(!bcast || bcast_idx, "csn_ln_bwd: bcast needs bcast_idx");
   CSN_CHECK_ARG(rows % 64 == 0, "csn_ln_bwd: rows must be a multiple of 64");
   if (rows == 0) return 0;
-  LnBwdArgs a{dY, Z, mean, rstd, gamma, dZ, dZ16, dgamma, dbeta, rows, group_rows, rows_valid, block_rows, dtype, amax};
+  LnBwdArgs a{dY, Z, mean, rstd, gamma, dZ, dZ16, dgamma, dbeta, rows, group_rows, rows_valid, block_rows, dtype, amax, bcast, bcast_idx, bcast_scale};
   return launch_simple(ln_bwd_kernel, dim3((unsigned)(rows / 64)), dim3(256), a, stream, "ln_bwd_kernel");
 }
 

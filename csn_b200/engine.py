@@ -137,6 +137,12 @@ def attn_items(groups, geom: Geometry, n_head: int, d: int, device, kind: str = 
     return t
 
 
+def _paired(geom: Geometry) -> int:
+    """Items are emitted tile-fastest, so items 2m / 2m+1 are two 128-row tiles of the same (block,
+    chunk, head) — they stream identical tiles — whenever a chunk has an even number of tiles."""
+    return int((geom.chunk_pad // 128) % 2 == 0 and os.environ.get("CSN_CLUSTER", "1") != "0")
+
+
 def use_fused_attention(d: int) -> bool:
     import os
     return d in (64, 256) and os.environ.get("CSN_FUSED_ATTN", "1") != "0"
@@ -193,8 +199,8 @@ def attention_forward(Xh, Xf, groups, n_slots, n_blocks, w_q, w_k, w_v, w_o, gam
         O_lo = torch.empty_like(O) if torch.is_grad_enabled() or save_for_backward else None
         rc = L.lib().csn_attn_fwd(Qv.data_ptr(), Kv.data_ptr(), Vv.data_ptr(), n_slots * NP, n_slots * NP, HD,
                                   3 * HD, 3 * HD, 3 * HD, d, L.dtype_code(dt), items.data_ptr(), items.shape[0],
-                                  O.data_ptr(), HD, lse.data_ptr(), O_lo.data_ptr() if O_lo is not None else None,
-                                  L.stream_ptr())
+                                  O.data_ptr(), O.shape[0], HD, lse.data_ptr(), O_lo.data_ptr() if O_lo is not None else None,
+                                  _paired(geom), L.stream_ptr())
         L.check(rc, "csn_attn_fwd")
         ctx.extra["lse"] = lse
         ctx.extra["O_lo"] = O_lo
@@ -282,7 +288,8 @@ def _pick_split(tiles: int, kb_total: int, target: int = 296) -> int:
     return max(1, min(-(-target // max(tiles, 1)), max(1, kb_total // 8)))
 
 
-def attention_backward(ctx: AttnContext, dY: torch.Tensor, need_dx: bool, amax: torch.Tensor = None):
+def attention_backward(ctx: AttnContext, dY: torch.Tensor, need_dx: bool, amax: torch.Tensor = None,
+                       bcast: torch.Tensor = None, bcast_idx: torch.Tensor = None, bcast_scale: float = 0.0):
     """Backward of attention_forward. dY: [blocks*NP, 256] fp32 (zero in pad rows).
     Returns dict with dWq, dWk, dWv, dWo (fp32, reference layouts), dgamma, dbeta and, if need_dx,
     dX [S*NP, 256] fp32 (padded row-major, gradient w.r.t. every slot's features)."""
@@ -301,13 +308,15 @@ def attention_backward(ctx: AttnContext, dY: torch.Tensor, need_dx: bool, amax: 
         amax = dY.abs().max().reshape(1)
     inv_scale = 1.0 / torch.exp2(torch.floor(torch.log2(128.0 / amax.clamp_min(1e-30))))
     # --- LayerNorm backward
-    dZ = torch.empty_like(ctx.Z)
+    dZ = torch.empty_like(ctx.Z) if need_dx else None
     dZ16 = torch.empty(nblk * NP, 256, dtype=dt, device=dev)
     dgamma = torch.zeros(256, dtype=torch.float32, device=dev)
     dbeta = torch.zeros(256, dtype=torch.float32, device=dev)
     rc = lib.csn_ln_bwd(dY.data_ptr(), ctx.Z.data_ptr(), ctx.mean.data_ptr(), ctx.rstd.data_ptr(),
-                        ctx.gamma.data_ptr(), dZ.data_ptr(), dZ16.data_ptr(), dgamma.data_ptr(), dbeta.data_ptr(),
-                        nblk * NP, NP, CP, geom.chunk, L.dtype_code(dt), amax.data_ptr(), L.stream_ptr())
+                        ctx.gamma.data_ptr(), dZ.data_ptr() if dZ is not None else None, dZ16.data_ptr(),
+                        dgamma.data_ptr(), dbeta.data_ptr(), nblk * NP, NP, CP, geom.chunk, L.dtype_code(dt),
+                        amax.data_ptr(), bcast.data_ptr() if bcast is not None else None,
+                        bcast_idx.data_ptr() if bcast_idx is not None else None, bcast_scale, L.stream_ptr())
     L.check(rc, "csn_ln_bwd")
     split = _pick_split(2 * ((HD + 255) // 256), nblk * NP // 64)
     # --- dWo = dZ^T O  (contraction over all rows; both operands consumed MN-major)
@@ -332,8 +341,8 @@ def attention_backward(ctx: AttnContext, dY: torch.Tensor, need_dx: bool, amax: 
         L.check(rc, "csn_attn_delta")
         it_dv = attn_items(ctx.groups, geom, h, d, dev, "dv")
         rc = lib.csn_attn_bwd_dv(Kv.data_ptr(), Qv.data_ptr(), dO.data_ptr(), S * NP, S * NP, nblk * NP, HD, 3 * HD, 3 * HD, HD,
-                                 d, L.dtype_code(dt), it_dv.data_ptr(), it_dv.shape[0], dVv.data_ptr(), 3 * HD,
-                                 lse.data_ptr(), L.stream_ptr())
+                                 d, L.dtype_code(dt), it_dv.data_ptr(), it_dv.shape[0], dVv.data_ptr(), nblk * NP, 3 * HD,
+                                 lse.data_ptr(), _paired(geom), L.stream_ptr())
         L.check(rc, "csn_attn_bwd_dv")
         # the dQ kernel writes the key tiles it visits; columns beyond them must read as zeros in dS^T Q
         alloc = torch.empty if ((geom.kv_len + 127) // 128) * 128 >= CP else torch.zeros
@@ -341,8 +350,8 @@ def attention_backward(ctx: AttnContext, dY: torch.Tensor, need_dx: bool, amax: 
         it_dq = attn_items(ctx.groups, geom, h, d, dev, "dq")
         rc = lib.csn_attn_bwd_dq(Qv.data_ptr(), dO.data_ptr(), Kv.data_ptr(), Vv.data_ptr(), S * NP, nblk * NP, S * NP,
                                  HD, 3 * HD, HD, 3 * HD, 3 * HD, d, L.dtype_code(dt), it_dq.data_ptr(),
-                                 it_dq.shape[0], dQv.data_ptr(), 3 * HD, dS.data_ptr(), CP, lse.data_ptr(),
-                                 delta.data_ptr(), L.stream_ptr())
+                                 it_dq.shape[0], dQv.data_ptr(), 3 * HD, dS.data_ptr(), dS.shape[0], CP, lse.data_ptr(),
+                                 delta.data_ptr(), _paired(geom), L.stream_ptr())
         L.check(rc, "csn_attn_bwd_dq")
         for g in ctx.groups:
             nb = (h, NC, g.n_in, g.n_out)

@@ -332,25 +332,26 @@ class _CsaFn(torch.autograd.Function):
         obs, ocs = 256 * geom.n_points, geom.n_points
         grads_glue = [None] * 4
         dpool = None
+        # one pass: dY = comp * dOut^T for the blocks of the weighted sum, dcomp = <dOut^T, Y>; the gradient
+        # of the pooled means is a per-block row vector and is added inside csn_ln_bwd (never materialised)
+        dY = torch.empty(nblk * geom.rows_pad, 256, dtype=torch.float32, device=dev)
+        amax = torch.zeros(1, dtype=torch.float32, device=dev)
+        dcomp = torch.zeros(B * (K + 1), dtype=torch.float32, device=dev) if ctx.glue is not None else None
+        nopool = torch.full((nblk,), -1, dtype=torch.int32, device=dev)
+        rc = lib.csn_combine_bwd(dout.data_ptr(), a.Y.data_ptr(), None, cb.data_ptr(), cw.data_ptr(), cwi.data_ptr(),
+                                 nopool.data_ptr(), 0.0, dY.data_ptr(), dcomp.data_ptr() if dcomp is not None else None,
+                                 nblk, obs, ocs, geom.n_points, geom.chunk, geom.chunk_pad, geom.rows_pad,
+                                 amax.data_ptr(), L.stream_ptr())
+        L.check(rc, "csn_combine_bwd")
         if ctx.glue is not None:
-            dcomp = torch.zeros(B * (K + 1), dtype=torch.float32, device=dev)
-            rc = lib.csn_combine_bwd(dout.data_ptr(), a.Y.data_ptr(), None, cb.data_ptr(), cw.data_ptr(), cwi.data_ptr(),
-                                     pb.data_ptr(), 0.0, None, dcomp.data_ptr(), nblk, obs, ocs, geom.n_points,
-                                     geom.chunk, geom.chunk_pad, geom.rows_pad, None, L.stream_ptr())
-            L.check(rc, "csn_combine_bwd(dcomp)")
             pooled, loc, comp_g = ctx.glue
             gl = torch.autograd.grad(comp_g, [pooled] + loc, dcomp.view(B, K + 1))
             dpool = gl[0].contiguous()
             grads_glue = list(gl[1:])
-        dY = torch.empty(nblk * geom.rows_pad, 256, dtype=torch.float32, device=dev)
-        amax = torch.zeros(1, dtype=torch.float32, device=dev)
-        rc = lib.csn_combine_bwd(dout.data_ptr(), a.Y.data_ptr(), dpool.data_ptr() if dpool is not None else None,
-                                 cb.data_ptr(), cw.data_ptr(), cwi.data_ptr(), pb.data_ptr(), 1.0 / geom.n_points,
-                                 dY.data_ptr(), None, nblk, obs, ocs, geom.n_points, geom.chunk, geom.chunk_pad,
-                                 geom.rows_pad, amax.data_ptr(), L.stream_ptr())
-        L.check(rc, "csn_combine_bwd(dY)")
+            amax = amax + dpool.abs().max() / geom.n_points   # bound on |dY + dpool/N| for the gradient scaling
         need_dx = ctx.needs_input_grad[0] or ctx.needs_input_grad[1]
-        g = E.attention_backward(a, dY, need_dx, amax)
+        g = E.attention_backward(a, dY, need_dx, amax, bcast=dpool, bcast_idx=pb if dpool is not None else None,
+                                 bcast_scale=1.0 / geom.n_points)
         dx = dnb = None
         if need_dx:
             G = _rows_to_channel_major(g["dX"], S, max(n_src, n_src_nb), geom).view(B, K + 1, 256, -1, 1)

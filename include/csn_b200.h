@@ -113,16 +113,20 @@ int csn_topk_rows(const float* scores, int64_t ld, int32_t n_rows, int32_t n_col
  * [kv_row0, kv_row0+kv_len) of K / V, all restricted to columns [col0, col0+d_head); the result goes to
  * rows [o_row0, ..) / columns [col0, ..) of O (16-bit) and lse[lse_off + r] = log sum_j exp(s_rj).
  * (V rows start at v_row0, normally == kv_row0).
- * flags bit 0: rows >= q_valid are written as zeros (padded layouts) instead of being left untouched.
+ * The whole 128-row tile is written (TMA stores), rows >= q_valid as zeros: O lives in a padded layout
+ * with o_rows rows in total.
  * Q, K, V: 16-bit row-major views of `width` columns with leading dimensions ldq / ldk / ldv.
  * d_head in {64, 256}.  O_lo (optional, same layout as O) receives the rounding residual of O,
  * (o - round16(o)) * 2^11 (fp16) or * 2^8 (bf16), which csn_attn_delta uses to form
  * delta = rowsum(dO o O) to ~22 bits (a 16-bit O alone costs 1e-3 on dQ/dK when all value rows share
  * a large mean, as post-ReLU features do).
+ * paired != 0 asserts that items 2m and 2m+1 stream exactly the same K/V tiles (same kv_row0, kv_len,
+ * col0, v_row0): they then run as a 2-CTA cluster whose TMA loads are multicast to both CTAs.
  * ------------------------------------------------------------------------------------------- */
 int csn_attn_fwd(const void* Q, const void* K, const void* V, int64_t q_rows, int64_t kv_rows, int64_t width,
                  int64_t ldq, int64_t ldk, int64_t ldv, int32_t d_head, int32_t dtype, const int32_t* items,
-                 int32_t n_items, void* O, int64_t ldo, float* lse, void* O_lo, void* stream);
+                 int32_t n_items, void* O, int64_t o_rows, int64_t ldo, float* lse, void* O_lo, int32_t paired,
+                 void* stream);
 
 /* Backward of the attention core (autograd of csa_models.py:139-142), three pieces:
  *  csn_attn_delta : delta[(blk*h+head)*rows_pad + r] = sum_c dO[blk*rows_pad+r][head*d+c] * (O + O_lo/2^11)[..]
@@ -138,11 +142,13 @@ int csn_attn_delta(const void* dO, const void* O, const void* O_lo, float* delta
                    int32_t d_head, int64_t ld, int32_t dtype, void* stream);
 int csn_attn_bwd_dv(const void* Kres, const void* Qstr, const void* dO, int64_t k_rows, int64_t q_rows,
                     int64_t do_rows, int64_t width, int64_t ldk, int64_t ldq, int64_t lddo, int32_t d_head, int32_t dtype,
-                    const int32_t* items, int32_t n_items, void* dV, int64_t lddv, const float* lse, void* stream);
+                    const int32_t* items, int32_t n_items, void* dV, int64_t dv_rows, int64_t lddv, const float* lse,
+                    int32_t paired, void* stream);
 int csn_attn_bwd_dq(const void* Q, const void* dO, const void* K, const void* V, int64_t q_rows, int64_t do_rows,
                     int64_t kv_rows, int64_t width, int64_t ldq, int64_t lddo, int64_t ldk, int64_t ldv,
                     int32_t d_head, int32_t dtype, const int32_t* items, int32_t n_items, void* dQ, int64_t lddq,
-                    void* dS, int64_t ldds, const float* lse, const float* delta, void* stream);
+                    void* dS, int64_t ds_rows, int64_t ldds, const float* lse, const float* delta, int32_t paired,
+                    void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * HBM-bound pieces of the CSA/SSA layer.  Row buffers use "padded" coordinates: a shape's block has
@@ -179,11 +185,15 @@ int csn_add_ln_fwd(float* Z, const float* R, const int32_t* res_block, float* Y,
                    int32_t block_rows, int32_t group_rows, int32_t rows_valid, float eps, int32_t dtype,
                    void* stream);
 int csn_colsum_reduce(const float* part, float* out, int32_t n_blocks, int32_t parts, float scale, void* stream);
-/* amax (optional, device): dY is multiplied by the power of two 2^floor(log2(128 / *amax)) on load so
+/* dZ may be NULL (only the 16-bit copy is written).  bcast (optional, [n][256]) adds the row
+ * bcast_scale * bcast[bcast_idx[block]] to every valid row of a block before the backward formula: the
+ * gradient of the pooled mean (csa_models.py:212,219) without materialising it.
+ * amax (optional, device): dY is multiplied by the power of two 2^floor(log2(128 / *amax)) on load so
  * that 16-bit gradient intermediates stay in the normal fp16 range; the caller divides the results. */
 int csn_ln_bwd(const float* dY, const float* Z, const float* mean, const float* rstd, const float* gamma,
                float* dZ, void* dZ16, float* dgamma, float* dbeta, int64_t rows, int32_t block_rows,
-               int32_t group_rows, int32_t rows_valid, int32_t dtype, const float* amax, void* stream);
+               int32_t group_rows, int32_t rows_valid, int32_t dtype, const float* amax, const float* bcast,
+               const int32_t* bcast_idx, float bcast_scale, void* stream);
 
 /* out[b][c][n] = sum_k w[b*n_k+k] * Y[blk[b*n_k+k]][padrow(n)][c]: the compatibility-weighted sum
  * of the self- and cross-attention outputs written back channel-major (csa_models.py:232-240);
