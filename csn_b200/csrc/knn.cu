@@ -228,6 +228,195 @@ knn_score_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   }
 }
 
+// --------------------------------------------------------------------------- exact re-scoring
+// Same pipeline with split operands: every unit-norm feature x is stored as hi = fp16(x) and
+// lo = fp16((x - hi) * 2^11), i.e. a 22-bit significand.  Per tile two accumulators are kept,
+//   acc0 = A_hi B_hi^T ,  acc1 = A_hi B_lo^T + A_lo B_hi^T ,   cos = acc0 + acc1 * 2^-11
+// (the lo*lo term is < 2^-22 and dropped), which reproduces the reference's fp32 cosines to ~1e-7.
+// It re-scores only the (query, candidate) pairs whose coarse score lies in the band around the
+// (K+1)-th best, so that top-K index sets match the reference except for ties below 1e-6.
+constexpr int KNX_BN = 128;
+constexpr int KNX_A_BYTES = 2 * KNN_BM * KNN_D * 2;   // hi + lo query tiles, 128 KB resident
+constexpr int KNX_B_STAGE = 2 * KNX_BN * 64 * 2;      // hi + lo k-block of 128 candidate rows, 32 KB
+constexpr int KNX_STAGES = 3;
+constexpr int KNX_SMEM = KNX_A_BYTES + KNX_STAGES * KNX_B_STAGE + 1024 + 1024;
+
+__global__ void __launch_bounds__(KNN_THREADS, 1)
+knn_score_exact_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_constant__ CUtensorMap tmQl,
+                       const __grid_constant__ CUtensorMap tmCh, const __grid_constant__ CUtensorMap tmCl,
+                       const __grid_constant__ KnnArgs p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const uint32_t sAh = smem_u32(smem);
+  const uint32_t sAl = sAh + KNN_BM * KNN_D * 2;
+  const uint32_t sB = sAh + KNX_A_BYTES;
+  const uint32_t bar_base = sB + KNX_STAGES * KNX_B_STAGE;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (KNX_STAGES + s); };
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * KNX_STAGES + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * KNX_STAGES + 2 + a); };
+  const uint32_t a_full = bar_base + 8u * (2 * KNX_STAGES + 4);
+  const uint32_t a_empty = bar_base + 8u * (2 * KNX_STAGES + 5);
+  uint8_t* bar_ptr = smem + KNX_A_BYTES + KNX_STAGES * KNX_B_STAGE;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bar_ptr + 8 * (2 * KNX_STAGES + 6));
+  float* red = reinterpret_cast<float*>(bar_ptr + 256);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < KNX_STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 128); }
+    mbar_init(a_full, 1);
+    mbar_init(a_empty, 1);
+    fence_mbar_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(smem_u32(tmem_ptr_smem), 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int st = 0;
+      uint32_t ph = 0, a_ph = 0;
+      for (int it = blockIdx.x; it < p.n_items; it += gridDim.x) {
+        const KnnItem item = p.items[it];
+        mbar_wait(a_empty, a_ph ^ 1);
+        mbar_arrive_expect_tx(a_full, KNX_A_BYTES);
+#pragma unroll
+        for (int kb = 0; kb < KNN_KB; ++kb) {
+          tma_load_2d(sAh + kb * (KNN_BM * 128), &tmQh, a_full, kb * 64, item.q_row0);
+          tma_load_2d(sAl + kb * (KNN_BM * 128), &tmQl, a_full, kb * 64, item.q_row0);
+        }
+        a_ph ^= 1;
+        for (int pos = 0; pos < item.list_count; ++pos) {
+          const KnnCand c = p.cands[item.list_begin + pos];
+          const int ntiles = (c.len + KNX_BN - 1) / KNX_BN;
+          for (int nt = 0; nt < ntiles; ++nt) {
+#pragma unroll 1
+            for (int kb = 0; kb < KNN_KB; ++kb) {
+              mbar_wait(empty_bar(st), ph ^ 1);
+              mbar_arrive_expect_tx(full_bar(st), KNX_B_STAGE);
+              tma_load_2d(sB + st * KNX_B_STAGE, &tmCh, full_bar(st), kb * 64, c.row0 + nt * KNX_BN);
+              tma_load_2d(sB + st * KNX_B_STAGE + KNX_BN * 128, &tmCl, full_bar(st), kb * 64, c.row0 + nt * KNX_BN);
+              if (++st == KNX_STAGES) { st = 0; ph ^= 1; }
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      int st = 0, acc = 0;
+      uint32_t ph = 0, acc_ph = 0, a_ph = 0;
+      for (int it = blockIdx.x; it < p.n_items; it += gridDim.x) {
+        const KnnItem item = p.items[it];
+        mbar_wait(a_full, a_ph);
+        a_ph ^= 1;
+        tc_fence_after();
+        for (int pos = 0; pos < item.list_count; ++pos) {
+          const KnnCand c = p.cands[item.list_begin + pos];
+          const int ntiles = (c.len + KNX_BN - 1) / KNX_BN;
+          for (int nt = 0; nt < ntiles; ++nt) {
+            mbar_wait(tempty_bar(acc), acc_ph ^ 1);
+            tc_fence_after();
+            const uint32_t d0 = tmem_base + acc * 2 * KNX_BN;   // hi*hi
+            const uint32_t d1 = d0 + KNX_BN;                    // cross terms (scaled by 2^11)
+#pragma unroll 1
+            for (int kb = 0; kb < KNN_KB; ++kb) {
+              mbar_wait(full_bar(st), ph);
+              tc_fence_after();
+              const uint32_t ah = sAh + kb * (KNN_BM * 128), al = sAl + kb * (KNN_BM * 128);
+              const uint32_t bh = sB + st * KNX_B_STAGE, bl = bh + KNX_BN * 128;
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                const uint64_t dah = umma_desc_sw128(ah + k * 32, 0, 1024), dal = umma_desc_sw128(al + k * 32, 0, 1024);
+                const uint64_t dbh = umma_desc_sw128(bh + k * 32, 0, 1024), dbl = umma_desc_sw128(bl + k * 32, 0, 1024);
+                umma_f16_ss(d0, dah, dbh, p.idesc, (kb | k) ? 1u : 0u);
+                umma_f16_ss(d1, dah, dbl, p.idesc, (kb | k) ? 1u : 0u);
+                umma_f16_ss(d1, dal, dbh, p.idesc, 1u);
+              }
+              umma_commit(empty_bar(st));
+              if (++st == KNX_STAGES) { st = 0; ph ^= 1; }
+            }
+            umma_commit(tfull_bar(acc));
+            if (++acc == 2) { acc = 0; acc_ph ^= 1; }
+          }
+        }
+        umma_commit(a_empty);
+      }
+    }
+  } else if (warp >= 4) {
+    const int q = warp & 3;
+    int acc = 0;
+    uint32_t acc_ph = 0;
+    int flip = 0;
+    for (int it = blockIdx.x; it < p.n_items; it += gridDim.x) {
+      const KnnItem item = p.items[it];
+      const bool row_valid = (q * 32 + lane) < item.n_valid;
+      for (int pos = 0; pos < item.list_count; ++pos) {
+        const KnnCand c = p.cands[item.list_begin + pos];
+        const int ntiles = (c.len + KNX_BN - 1) / KNX_BN;
+        float run = -INFINITY;
+        for (int nt = 0; nt < ntiles; ++nt) {
+          mbar_wait(tfull_bar(acc), acc_ph);
+          tc_fence_after();
+          const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + acc * 2 * KNX_BN;
+          const int ncols = min(KNX_BN, c.len - nt * KNX_BN);
+#pragma unroll 1
+          for (int cc = 0; cc < ncols; cc += 32) {
+            uint32_t r0[32], r1[32];
+            tmem_ld_32x32(taddr + cc, r0);
+            tmem_ld_32x32(taddr + KNX_BN + cc, r1);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (cc + j < ncols) run = fmaxf(run, __uint_as_float(r0[j]) + __uint_as_float(r1[j]) * (1.f / 2048.f));
+          }
+          tc_fence_before();
+          mbar_arrive(tempty_bar(acc));
+          if (++acc == 2) { acc = 0; acc_ph ^= 1; }
+        }
+        const float s = warp_sum(row_valid ? run : 0.f);
+        if (lane == 0) red[flip * 4 + q] = s;
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (warp == 4 && lane == 0)
+          p.partial[item.out_off + pos] = (red[flip * 4 + 0] + red[flip * 4 + 1]) + (red[flip * 4 + 2] + red[flip * 4 + 3]);
+        flip ^= 1;
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// out_hi = fp16(x / max(|x|, eps)), out_lo = fp16((x/|x| - out_hi) * 2^11): the split unit-norm rows
+__global__ void normalize_rows_split_kernel(const float* __restrict__ in, __half* __restrict__ out_hi,
+                                            __half* __restrict__ out_lo, long long rows, int D, float eps) {
+  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const float* src = in + row * D;
+  float ss = 0.f;
+  for (int c = lane; c < D; c += 32) { const float v = __ldg(src + c); ss += v * v; }
+  ss = warp_sum(ss);
+  const float inv = 1.f / fmaxf(sqrtf(ss), eps);
+  for (int c = lane; c < D; c += 32) {
+    const float v = __ldg(src + c) * inv;
+    const __half h = __float2half_rn(v);
+    out_hi[row * D + c] = h;
+    out_lo[row * D + c] = __float2half_rn((v - __half2float(h)) * 2048.f);
+  }
+}
+
 // --------------------------------------------------------------------------- normalise rows
 // One warp per row of D floats: out = v / max(|v|_2, eps) as 16-bit. D must be a multiple of 128.
 __global__ void normalize_rows_kernel(const float* __restrict__ in, void* __restrict__ out, long long rows,
@@ -375,6 +564,52 @@ int csn_knn_scores(const void* feat_q, int64_t rows_q, const void* feat_c, int64
   const int grid = n_items < num_sms() ? n_items : num_sms();
   knn_score_kernel<<<grid, KNN_THREADS, KNN_SMEM, (cudaStream_t)stream>>>(tmQ, tmC, a);
   CSN_LAUNCH_OK("knn_score_kernel");
+  return 0;
+}
+
+int csn_normalize_rows_split(const float* in, void* out_hi, void* out_lo, int64_t rows, int32_t D, float eps,
+                             void* stream) {
+  using namespace csn;
+  clear_error();
+  CSN_CHECK_ARG(in && out_hi && out_lo, "csn_normalize_rows_split: null pointer");
+  if (rows == 0) return 0;
+  const int wpb = 8;
+  normalize_rows_split_kernel<<<(unsigned)((rows + wpb - 1) / wpb), wpb * 32, 0, (cudaStream_t)stream>>>(
+      in, reinterpret_cast<__half*>(out_hi), reinterpret_cast<__half*>(out_lo), rows, D, eps);
+  CSN_LAUNCH_OK("normalize_rows_split_kernel");
+  return 0;
+}
+
+int csn_knn_scores_exact(const void* q_hi, const void* q_lo, int64_t rows_q, const void* c_hi, const void* c_lo,
+                         int64_t rows_c, const int32_t* items, int32_t n_items, const int32_t* cands, float* partial,
+                         void* stream) {
+  using namespace csn;
+  clear_error();
+  CSN_CHECK_ARG(q_hi && q_lo && c_hi && c_lo && items && cands && partial, "csn_knn_scores_exact: null pointer");
+  if (n_items == 0) return 0;
+  CUtensorMap tmQh, tmQl, tmCh, tmCl;
+  int rc = make_tmap_2d(&tmQh, q_hi, CSN_F16, KNN_D, rows_q, KNN_D, 64, KNN_BM);
+  if (rc) return rc;
+  rc = make_tmap_2d(&tmQl, q_lo, CSN_F16, KNN_D, rows_q, KNN_D, 64, KNN_BM);
+  if (rc) return rc;
+  rc = make_tmap_2d(&tmCh, c_hi, CSN_F16, KNN_D, rows_c, KNN_D, 64, KNX_BN);
+  if (rc) return rc;
+  rc = make_tmap_2d(&tmCl, c_lo, CSN_F16, KNN_D, rows_c, KNN_D, 64, KNX_BN);
+  if (rc) return rc;
+  KnnArgs a;
+  a.items = reinterpret_cast<const KnnItem*>(items);
+  a.cands = reinterpret_cast<const KnnCand*>(cands);
+  a.partial = partial;
+  a.n_items = n_items;
+  a.idesc = umma_idesc_f16(0u, 0, 0, KNX_BN);
+  static bool configured = false;
+  if (!configured) {
+    CSN_CUDA_OK(cudaFuncSetAttribute(knn_score_exact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, KNX_SMEM));
+    configured = true;
+  }
+  const int grid = n_items < num_sms() ? n_items : num_sms();
+  knn_score_exact_kernel<<<grid, KNN_THREADS, KNX_SMEM, (cudaStream_t)stream>>>(tmQh, tmQl, tmCh, tmCl, a);
+  CSN_LAUNCH_OK("knn_score_exact_kernel");
   return 0;
 }
 

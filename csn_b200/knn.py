@@ -26,6 +26,7 @@ class ShapeStore:
     rows: torch.Tensor
     row0: list[int]
     length: list[int]
+    rows_lo: torch.Tensor = None   # optional fp16 residual (x - fp16(x)) * 2^11 for the exact re-score
 
     @property
     def n_shapes(self) -> int:
@@ -33,7 +34,7 @@ class ShapeStore:
 
     def subset(self, idx) -> "ShapeStore":
         idx = [int(i) for i in idx]
-        return ShapeStore(self.rows, [self.row0[i] for i in idx], [self.length[i] for i in idx])
+        return ShapeStore(self.rows, [self.row0[i] for i in idx], [self.length[i] for i in idx], self.rows_lo)
 
 
 def _normalize_into(src: torch.Tensor, dst: torch.Tensor, eps: float) -> None:
@@ -44,15 +45,28 @@ def _normalize_into(src: torch.Tensor, dst: torch.Tensor, eps: float) -> None:
     L.check(rc, "csn_normalize_rows")
 
 
-def build_store(feats, dtype: torch.dtype = torch.float16, eps: float = 1e-12) -> ShapeStore:
-    """feats: (S, N, D) fp32 CUDA tensor, or a list of (L_s, D) fp32 CUDA tensors (ragged)."""
+def _normalize_split_into(src: torch.Tensor, hi: torch.Tensor, lo: torch.Tensor, eps: float) -> None:
+    rows, D = src.shape
+    rc = L.lib().csn_normalize_rows_split(src.data_ptr(), hi.data_ptr(), lo.data_ptr(), rows, D, eps, L.stream_ptr())
+    L.check(rc, "csn_normalize_rows_split")
+
+
+def build_store(feats, dtype: torch.dtype = torch.float16, eps: float = 1e-12, exact: bool = False) -> ShapeStore:
+    """feats: (S, N, D) fp32 CUDA tensor, or a list of (L_s, D) fp32 CUDA tensors (ragged).
+    exact=True (fp16 only) also keeps the rounding residual of every row, which the exact re-scoring of
+    the top-K boundary band needs."""
     if isinstance(feats, torch.Tensor):
         assert feats.dim() == 3
         S, N, D = feats.shape
         src = feats.contiguous().view(S * N, D)
         dst = torch.empty(S * N, D, dtype=dtype, device=feats.device)
-        _normalize_into(src, dst, eps)
-        return ShapeStore(dst, [s * N for s in range(S)], [N] * S)
+        lo = None
+        if exact and dtype == torch.float16:
+            lo = torch.empty_like(dst)
+            _normalize_split_into(src, dst, lo, eps)
+        else:
+            _normalize_into(src, dst, eps)
+        return ShapeStore(dst, [s * N for s in range(S)], [N] * S, lo)
     lens = [int(f.shape[0]) for f in feats]
     D = int(feats[0].shape[1])
     total = sum(lens)
@@ -136,6 +150,53 @@ def topk_rows(scores: torch.Tensor, k: int):
     return val, idx
 
 
+def refine_band(scores: torch.Tensor, q: ShapeStore, c: ShapeStore, k: int, margin: float = 4e-5) -> torch.Tensor:
+    """Exact re-score of the top-k boundary band.  For every query the candidates whose coarse score is
+    within `margin` of (or above) the k-th best are re-scored with split fp16 operands (22-bit
+    significands, csn_knn_scores_exact) and patched into `scores` in place: the top-k index sets then
+    match an fp32 evaluation except for genuine ties below ~1e-6 (BASELINE.json's criterion); the 16-bit
+    coarse pass alone is only good to ~1e-5."""
+    assert q.rows_lo is not None and c.rows_lo is not None, "build the stores with exact=True"
+    dev = scores.device
+    Sq, Sc = scores.shape
+    k = min(k, Sc)
+    kth = scores.topk(k, dim=-1).values[:, -1:]
+    band = (scores >= kth - margin).nonzero()          # (n_pairs, 2), sorted by query (host sync: tiny table)
+    band_cpu = band.cpu()
+    qi, ci = band_cpu[:, 0].tolist(), band_cpu[:, 1].tolist()
+    items, cands, elem_pair = [], [], []
+    n_pairs = len(qi)
+    start = 0
+    out_off = 0
+    while start < n_pairs:
+        end = start
+        while end < n_pairs and qi[end] == qi[start]:
+            end += 1
+        s_q = qi[start]
+        cnt = end - start
+        nt = (q.length[s_q] + TILE_ROWS - 1) // TILE_ROWS
+        for t in range(nt):
+            nvalid = min(TILE_ROWS, q.length[s_q] - t * TILE_ROWS)
+            items.append((q.row0[s_q] + t * TILE_ROWS, nvalid, start, cnt, out_off, 0))
+            elem_pair.extend(range(start, end))
+            out_off += cnt
+        cands.extend((c.row0[j], c.length[j]) for j in ci[start:end])
+        start = end
+    items_t = torch.tensor(items, dtype=torch.int32, device=dev)
+    cands_t = torch.tensor(cands, dtype=torch.int32, device=dev)
+    partial = torch.empty(out_off, dtype=torch.float32, device=dev)
+    rc = L.lib().csn_knn_scores_exact(q.rows.data_ptr(), q.rows_lo.data_ptr(), q.rows.shape[0], c.rows.data_ptr(),
+                                      c.rows_lo.data_ptr(), c.rows.shape[0], items_t.data_ptr(), len(items),
+                                      cands_t.data_ptr(), partial.data_ptr(), L.stream_ptr())
+    L.check(rc, "csn_knn_scores_exact")
+    # sum the row tiles of every pair (fp64 accumulation: order-independent at fp32 resolution)
+    idx = torch.tensor(elem_pair, dtype=torch.int64, device=dev)
+    tot = torch.zeros(n_pairs, dtype=torch.float64, device=dev).index_add_(0, idx, partial.double())
+    lens = torch.tensor([q.length[i] for i in qi], dtype=torch.float64, device=dev)
+    scores[band[:, 0], band[:, 1]] = (tot / lens).float()
+    return scores
+
+
 def retrieval_measure(ssa_feats_1: torch.Tensor, ssa_feats_2: torch.Tensor, dtype=torch.float16,
                       eps: float = 1e-12) -> torch.Tensor:
     """get_retrieval_measure (csa_models.py:244-267): (Sq,N,D),(Sc,M,D) fp32 -> (Sq,Sc) fp32."""
@@ -145,10 +206,17 @@ def retrieval_measure(ssa_feats_1: torch.Tensor, ssa_feats_2: torch.Tensor, dtyp
     return scores_from_stores(q, c)
 
 
-def knn_graph(ssa_feats_1: torch.Tensor, ssa_feats_2: torch.Tensor, K: int, dtype=torch.float16) -> torch.Tensor:
+def knn_graph(ssa_feats_1: torch.Tensor, ssa_feats_2: torch.Tensor, K: int, dtype=torch.float16,
+              exact: bool = True) -> torch.Tensor:
     """get_knn_graph (csa_models.py:270-280): indices of the K+1 best candidates per query, sorted
-    descending (self included when the two sets coincide)."""
-    s = retrieval_measure(ssa_feats_1, ssa_feats_2, dtype)
+    descending (self included when the two sets coincide).  exact=True re-scores the boundary band so
+    that the index sets equal the reference's except for ties below 1e-6."""
+    exact = exact and dtype == torch.float16
+    q = build_store(ssa_feats_1, dtype, exact=exact)
+    c = q if ssa_feats_2 is ssa_feats_1 else build_store(ssa_feats_2, dtype, exact=exact)
+    s = scores_from_stores(q, c)
+    if exact:
+        refine_band(s, q, c, K + 1)
     return topk_rows(s, K + 1)[1]
 
 

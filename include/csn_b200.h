@@ -93,6 +93,15 @@ int csn_knn_scores(const void* feat_q, int64_t rows_q, const void* feat_c, int64
                    int32_t dtype, const int32_t* items, int32_t n_items, const int32_t* cands,
                    float* partial, void* stream);
 
+/* Exact variant for the pairs near the top-K boundary: operands are split into hi = fp16(x) and
+ * lo = fp16((x - hi) * 2^11) (csn_normalize_rows_split), three MMAs per k-step reproduce the fp32
+ * cosines of csa_models.py:256 to ~1e-7. Same work tables as csn_knn_scores. */
+int csn_normalize_rows_split(const float* in, void* out_hi, void* out_lo, int64_t rows, int32_t D, float eps,
+                             void* stream);
+int csn_knn_scores_exact(const void* q_hi, const void* q_lo, int64_t rows_q, const void* c_hi, const void* c_lo,
+                         int64_t rows_c, const int32_t* items, int32_t n_items, const int32_t* cands,
+                         float* partial, void* stream);
+
 /* scores[q*ld + c] = (sum_{t<ntiles} partial[(q*ntiles+t)*n_cand + c]) / n_rows, summed in a fixed
  * order (csa_models.py:257 `.max(-1)[0].mean(-1)`). */
 int csn_knn_reduce(const float* partial, float* scores, int32_t n_q, int32_t n_cand, int32_t ntiles,
