@@ -98,6 +98,28 @@ class AttnContext:
 
 
 _ITEM_CACHE: dict = {}
+_TABLE_CACHE: dict = {}
+
+
+def cached_table(key, device, build):
+    """Small int/float index tables live on the device and are built once per configuration: a
+    host->device copy from pageable memory inside a step would serialise the CPU with the stream."""
+    k = (key, str(device))
+    t = _TABLE_CACHE.get(k)
+    if t is None:
+        if len(_TABLE_CACHE) > 256:
+            _TABLE_CACHE.clear()
+        t = build().to(device)
+        _TABLE_CACHE[k] = t
+    return t
+
+
+def _res_block_table(groups, n_blocks):
+    res = torch.empty(n_blocks, dtype=torch.int32)
+    for g in groups:
+        for (j, qs, _, _) in g.blocks():
+            res[j] = qs
+    return res
 
 
 def attn_items(groups, geom: Geometry, n_head: int, d: int, device, kind: str = "fwd") -> torch.Tensor:
@@ -219,11 +241,8 @@ def attention_forward(Xh, Xf, groups, n_slots, n_blocks, w_q, w_k, w_v, w_o, gam
     # --- output projection (csa_models.py:115), residual + LayerNorm (:116-118), pooled column sums
     Z = torch.empty(n_blocks * NP, 256, dtype=torch.float32, device=dev)
     L.gemm(L.mat(O, L.MAJOR_K), L.mat(ctx.Wo16, L.MAJOR_K), L.out(Z, 256), n_blocks * NP, 256, HD)
-    res = torch.empty(n_blocks, dtype=torch.int32)
-    for g in groups:
-        for (j, qs, _, _) in g.blocks():
-            res[j] = qs
-    ctx.res_block = res.to(dev)
+    ctx.res_block = cached_table(("res_block", tuple(groups), n_blocks), dev,
+                                 lambda: _res_block_table(groups, n_blocks))
     Y = torch.empty_like(Z)
     ctx.mean = torch.empty(n_blocks * NP, dtype=torch.float32, device=dev)
     ctx.rstd = torch.empty_like(ctx.mean)

@@ -73,8 +73,8 @@ def _rows_to_channel_major(rows: torch.Tensor, n_b: int, n_src_points: int, geom
     dev = rows.device
     alloc = torch.zeros if n_src_points > geom.n_points else torch.empty
     out = alloc(n_b, 256, n_src_points, 1, dtype=torch.float32, device=dev)
-    blk = torch.arange(n_b, dtype=torch.int32, device=dev)
-    w = torch.ones(n_b, dtype=torch.float32, device=dev)
+    blk = E.cached_table(("arange", n_b), dev, lambda: torch.arange(n_b, dtype=torch.int32))
+    w = E.cached_table(("ones", n_b), dev, lambda: torch.ones(n_b, dtype=torch.float32))
     rc = L.lib().csn_combine_fwd(rows.data_ptr(), blk.data_ptr(), w.data_ptr(), out.data_ptr(), None, n_b, 1,
                                  256 * n_src_points, n_src_points, geom.n_points, geom.chunk, geom.chunk_pad,
                                  geom.rows_pad, L.CSN_F16, L.stream_ptr())
@@ -283,12 +283,14 @@ class _CsaFn(torch.autograd.Function):
             comp = comp_g.detach()
             glue = (pooled, loc, comp_g)
         # ---- out = sum_k comp[b,k] * MHA(x, x_k)   (:232-240), written channel-major
-        blk = torch.empty(B, K + 1, dtype=torch.int32)
-        for b in range(B):
-            blk[b, 0] = b * (K + 1)
-            for k in range(1, K + 1):
-                blk[b, k] = S + b * K + (k - 1)
-        blk = blk.to(dev)
+        def _blk_table():
+            t = torch.empty(B, K + 1, dtype=torch.int32)
+            for b in range(B):
+                t[b, 0] = b * (K + 1)
+                for k in range(1, K + 1):
+                    t[b, k] = S + b * K + (k - 1)
+            return t
+        blk = E.cached_table(("csa_blk", B, K), dev, _blk_table)
         alloc = torch.zeros if n_src > geom.n_points else torch.empty
         out = alloc(B, 256, geom.n_points, 1, dtype=torch.float32, device=dev)
         compc = comp.contiguous()
@@ -313,21 +315,27 @@ class _CsaFn(torch.autograd.Function):
         dev = dout.device
         dout = dout.float().contiguous()
         # tables of the combine backward
-        cb = torch.full((nblk,), -1, dtype=torch.int32)
-        cwi = torch.full((nblk,), -1, dtype=torch.int32)
-        pb = torch.full((nblk,), -1, dtype=torch.int32)
-        for b in range(B):
-            for k in range(K + 1):
-                slot = b * (K + 1) + k
-                if ctx.glue is not None:
-                    pb[slot] = slot
-                if k == 0:
-                    cb[slot], cwi[slot] = b, slot
-                else:
-                    j = S + b * K + (k - 1)
-                    cb[j], cwi[j] = b, slot
-        cb, cwi, pb = cb.to(dev), cwi.to(dev), pb.to(dev)
-        cw = ctx.comp.reshape(-1)[cwi.clamp(min=0).long()].contiguous()
+        has_glue = ctx.glue is not None
+
+        def _bwd_tables():
+            cb = torch.full((nblk,), -1, dtype=torch.int32)
+            cwi = torch.full((nblk,), -1, dtype=torch.int32)
+            pb = torch.full((nblk,), -1, dtype=torch.int32)
+            for b in range(B):
+                for k in range(K + 1):
+                    slot = b * (K + 1) + k
+                    if has_glue:
+                        pb[slot] = slot
+                    if k == 0:
+                        cb[slot], cwi[slot] = b, slot
+                    else:
+                        j = S + b * K + (k - 1)
+                        cb[j], cwi[j] = b, slot
+            return torch.stack([cb, cwi, pb, torch.full((nblk,), -1, dtype=torch.int32)])
+        tabs = E.cached_table(("csa_bwd", B, K, has_glue), dev, _bwd_tables)
+        cb, cwi, pb, nopool = tabs[0], tabs[1], tabs[2], tabs[3]
+        gidx = E.cached_table(("csa_bwd_gather", B, K, has_glue), dev, lambda: _bwd_tables()[1].clamp(min=0).long())
+        cw = ctx.comp.reshape(-1)[gidx].contiguous()
         lib = L.lib()
         obs, ocs = 256 * geom.n_points, geom.n_points
         grads_glue = [None] * 4
@@ -337,7 +345,6 @@ class _CsaFn(torch.autograd.Function):
         dY = torch.empty(nblk * geom.rows_pad, 256, dtype=torch.float32, device=dev)
         amax = torch.zeros(1, dtype=torch.float32, device=dev)
         dcomp = torch.zeros(B * (K + 1), dtype=torch.float32, device=dev) if ctx.glue is not None else None
-        nopool = torch.full((nblk,), -1, dtype=torch.int32, device=dev)
         rc = lib.csn_combine_bwd(dout.data_ptr(), a.Y.data_ptr(), None, cb.data_ptr(), cw.data_ptr(), cwi.data_ptr(),
                                  nopool.data_ptr(), 0.0, dY.data_ptr(), dcomp.data_ptr() if dcomp is not None else None,
                                  nblk, obs, ocs, geom.n_points, geom.chunk, geom.chunk_pad, geom.rows_pad,
