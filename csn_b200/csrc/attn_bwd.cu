@@ -58,7 +58,7 @@ struct BwdCfg {
   static constexpr int SMEM_BYTES = 2 * TILE_BYTES + DS_BYTES + NST * SLOT_BYTES + 256 + 1024;
 };
 
-template <int DH, int CL>
+template <int DH, int CL, bool WITH_DQ>
 __global__ void __launch_bounds__(256, 1)
 attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmDO,
                    const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
@@ -77,13 +77,15 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   auto kv_empty = [&](int s) { return bar_base + 8u * (Cfg::NST + s); };
   const uint32_t bq_full = bar_base + 8u * (2 * Cfg::NST + 0);
   const uint32_t bq_empty = bar_base + 8u * (2 * Cfg::NST + 1);
-  const uint32_t sdp_full = bar_base + 8u * (2 * Cfg::NST + 2);   // S and dP of tile j are in TMEM
-  const uint32_t sdp_empty = bar_base + 8u * (2 * Cfg::NST + 3);  // ... and have been read
-  const uint32_t ds_full = bar_base + 8u * (2 * Cfg::NST + 4);    // dS_j is in SMEM
-  const uint32_t ds_empty = bar_base + 8u * (2 * Cfg::NST + 5);   // dQ MMAs of tile j done reading it
-  const uint32_t dq_full = bar_base + 8u * (2 * Cfg::NST + 6);
-  const uint32_t dq_empty = bar_base + 8u * (2 * Cfg::NST + 7);
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bar_ptr + 8 * (2 * Cfg::NST + 8));
+  // S and dP of tile j are in TMEM (buffer b) / have been read. Without the dQ accumulator the 256 freed
+  // TMEM columns double-buffer S|dP, so the element-wise stage of tile j overlaps the MMAs of tile j+1.
+  auto sdp_full = [&](int b) { return bar_base + 8u * (2 * Cfg::NST + 2 + b); };
+  auto sdp_empty = [&](int b) { return bar_base + 8u * (2 * Cfg::NST + 4 + b); };
+  const uint32_t ds_full = bar_base + 8u * (2 * Cfg::NST + 6);    // dS_j is in SMEM
+  const uint32_t ds_empty = bar_base + 8u * (2 * Cfg::NST + 7);   // dQ MMAs of tile j done reading it
+  const uint32_t dq_full = bar_base + 8u * (2 * Cfg::NST + 8);
+  const uint32_t dq_empty = bar_base + 8u * (2 * Cfg::NST + 9);
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bar_ptr + 8 * (2 * Cfg::NST + 10));
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -101,8 +103,10 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     }
     mbar_init(bq_full, 1);
     mbar_init(bq_empty, 1);
-    mbar_init(sdp_full, 1);
-    mbar_init(sdp_empty, 128);
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(sdp_full(b), 1);
+      mbar_init(sdp_empty(b), 128);
+    }
     mbar_init(ds_full, 128);
     mbar_init(ds_empty, 1);
     mbar_init(dq_full, 1);
@@ -159,7 +163,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         for (int j = 0; j < nkv; ++j) {
           load_tile(&tmK, it.col0, it.kv_row0 + j * 128);   // for S
           load_tile(&tmV, it.col0, it.kv_row0 + j * 128);   // for dP
-          load_tile(&tmK, it.col0, it.kv_row0 + j * 128);   // for dQ (same bytes, consumed MN-major)
+          if (WITH_DQ) load_tile(&tmK, it.col0, it.kv_row0 + j * 128);   // for dQ (same bytes, consumed MN-major)
         }
       }
     }
@@ -167,7 +171,8 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     // ================================================================== MMA issuer
     if (lane == 0) {
       int st = 0;
-      uint32_t ph = 0, q_ph = 0, sdp_ph = 0, ds_ph = 0, dq_ph = 0;
+      uint32_t ph = 0, q_ph = 0, ds_ph = 0, dq_ph = 0;
+      uint32_t sdp_ph[2] = {0, 0};
       auto mma_kmajor = [&](uint32_t a_base, uint32_t d_tmem) {   // D = A_tile (resident) x slots^T
 #pragma unroll 1
         for (int s = 0; s < Cfg::SLOTS_PER_TILE; ++s) {
@@ -193,13 +198,15 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         q_ph ^= 1;
         tc_fence_after();
         for (int j = 0; j < nkv; ++j) {
-          mbar_wait(sdp_empty, sdp_ph ^ 1);   // S / dP of the previous tile have been read
+          const int b = WITH_DQ ? 0 : (j & 1);
+          mbar_wait(sdp_empty(b), sdp_ph[b] ^ 1);   // S / dP previously held by this buffer have been read
           tc_fence_after();
-          mma_kmajor(sQ, tmem_base + 0);      // S  = Q  K_j^T
-          mma_kmajor(sDO, tmem_base + 128);   // dP = dO V_j^T
-          umma_commit(sdp_full);
+          mma_kmajor(sQ, tmem_base + b * 256);         // S  = Q  K_j^T
+          mma_kmajor(sDO, tmem_base + b * 256 + 128);  // dP = dO V_j^T
+          umma_commit(sdp_full(b));
           if (j == nkv - 1) umma_commit(bq_empty);   // Q_i / dO_i are not read by the dQ MMAs
-          sdp_ph ^= 1;
+          sdp_ph[b] ^= 1;
+          if (!WITH_DQ) continue;
           mbar_wait(ds_full, ds_ph);          // dS_j staged
           ds_ph ^= 1;
           if (j == 0) mbar_wait(dq_empty, dq_ph ^ 1);   // previous item's dQ has been read out
@@ -221,8 +228,10 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
           }
           umma_commit(ds_empty);
         }
-        umma_commit(dq_full);
-        dq_ph ^= 1;
+        if (WITH_DQ) {
+          umma_commit(dq_full);
+          dq_ph ^= 1;
+        }
       }
     }
   } else if (warp >= 4) {
@@ -230,7 +239,8 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     const int q = warp & 3;
     const int r = q * 32 + lane;
     const uint32_t lane_addr = uint32_t(q * 32) << 16;
-    uint32_t sdp_ph = 0, dse_ph = 0, dqf_ph = 0;
+    uint32_t sdp_ph[2] = {0, 0};
+    uint32_t dse_ph = 0, dqf_ph = 0;
     uint8_t* sDS_ptr = smem + 2 * Cfg::TILE_BYTES;
     constexpr float LOG2E = 1.4426950408889634f;
     auto pack_pair = [&](float a, float b) -> uint32_t {
@@ -248,10 +258,11 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       const float lse_l2 = valid ? p.lse[it.stat_off + r] * LOG2E : 0.f;
       const float dlt = valid ? p.delta[it.stat_off + r] : 0.f;
       for (int j = 0; j < nkv; ++j) {
-        mbar_wait(sdp_full, sdp_ph);
-        sdp_ph ^= 1;
+        const int b = WITH_DQ ? 0 : (j & 1);
+        mbar_wait(sdp_full(b), sdp_ph[b]);
+        sdp_ph[b] ^= 1;
         tc_fence_after();
-        const uint32_t s_addr = tmem_base + lane_addr;
+        const uint32_t s_addr = tmem_base + lane_addr + b * 256;
         const int nvalid = min(128, it.kv_len - j * 128);
         bool waited = false;
 #pragma unroll 1
@@ -271,8 +282,10 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
             pk[i >> 1] = pack_pair(d0, d1);
           }
           if (!waited) {
-            mbar_wait(ds_empty, dse_ph ^ 1);   // dQ MMAs of the previous tile no longer read the staging tile
-            dse_ph ^= 1;
+            if (WITH_DQ) {
+              mbar_wait(ds_empty, dse_ph ^ 1);   // dQ MMAs of the previous tile no longer read the staging tile
+              dse_ph ^= 1;
+            }
             if (warp == 4 && lane == 0) tma_store_wait_read<0>();   // ... nor does its TMA store to HBM
             asm volatile("bar.sync 1, 128;" ::: "memory");
             waited = true;
@@ -286,9 +299,9 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
           }
         }
         tc_fence_before();
-        mbar_arrive(sdp_empty);
+        mbar_arrive(sdp_empty(b));
         fence_proxy_async_smem();
-        mbar_arrive(ds_full);
+        if (WITH_DQ) mbar_arrive(ds_full);
         // HBM copy of dS_j for dK = dS^T Q: the staged tile is exactly two TMA boxes [128 rows x 64 keys]
         asm volatile("bar.sync 1, 128;" ::: "memory");
         if (warp == 4 && lane == 0) {
@@ -297,6 +310,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
           tma_store_commit();
         }
       }
+      if (!WITH_DQ) continue;
       // ---- epilogue: dQ tile -> 16-bit
       mbar_wait(dq_full, dqf_ph);
       dqf_ph ^= 1;
@@ -389,11 +403,11 @@ __global__ void attn_delta_kernel(const void* __restrict__ dO, const void* __res
   }
 }
 
-template <int DH, int CL>
+template <int DH, int CL, bool WITH_DQ>
 static int launch_dq(const CUtensorMap& tmQ, const CUtensorMap& tmDO, const CUtensorMap& tmK, const CUtensorMap& tmV,
                      const CUtensorMap& tmDS, const CUtensorMap& tmDQ, const AttnBwdArgs& a, cudaStream_t stream) {
   using Cfg = BwdCfg<DH>;
-  auto kern = attn_bwd_dq_kernel<DH, CL>;
+  auto kern = attn_bwd_dq_kernel<DH, CL, WITH_DQ>;
   static bool configured = false;
   if (!configured) {
     CSN_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
@@ -445,7 +459,7 @@ int csn_attn_bwd_dq(const void* Q, const void* dO, const void* K, const void* V,
                     void* stream) {
   using namespace csn;
   clear_error();
-  CSN_CHECK_ARG(Q && dO && K && V && items && dQ && dS && lse && delta, "csn_attn_bwd_dq: null pointer");
+  CSN_CHECK_ARG(Q && dO && K && V && items && dS && lse && delta, "csn_attn_bwd_dq: null pointer");
   CSN_CHECK_ARG(d_head == 256 || d_head == 64, "csn_attn_bwd_dq: d_head=%d not supported (64 or 256)", d_head);
   CSN_CHECK_ARG(dtype == CSN_F16 || dtype == CSN_BF16, "csn_attn_bwd_dq: 16-bit operands only");
   CSN_CHECK_ARG((lddq * 2) % 16 == 0 && (ldds * 2) % 16 == 0, "csn_attn_bwd_dq: output strides must be 16B multiples");
@@ -462,8 +476,11 @@ int csn_attn_bwd_dq(const void* Q, const void* dO, const void* K, const void* V,
   CUtensorMap tmDS, tmDQ;
   rc = make_tmap_2d(&tmDS, dS, dtype, ldds, ds_rows, ldds, 64, 128);
   if (rc) return rc;
-  rc = make_tmap_2d(&tmDQ, dQ, dtype, width, do_rows, lddq, 64, 32);
-  if (rc) return rc;
+  tmDQ = tmDS;
+  if (dQ != nullptr) {   // dQ == NULL: only dS is produced (dQ = dS K then runs as a csn_gemm)
+    rc = make_tmap_2d(&tmDQ, dQ, dtype, width, do_rows, lddq, 64, 32);
+    if (rc) return rc;
+  }
   AttnBwdArgs a;
   a.items = reinterpret_cast<const AttnBwdItem*>(items);
   a.n_items = n_items;
@@ -476,11 +493,13 @@ int csn_attn_bwd_dq(const void* Q, const void* dO, const void* K, const void* V,
   a.idesc_s = umma_idesc_f16(fmt, 0, 0, 128);
   a.idesc_dq = umma_idesc_f16(fmt, 0, 1, d_head == 256 ? 128u : 64u);
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-  if (d_head == 256) {
-    if (paired && n_items % 2 == 0) return launch_dq<256, 2>(tmQ, tmDO, tmK, tmV, tmDS, tmDQ, a, s);
-    return launch_dq<256, 1>(tmQ, tmDO, tmK, tmV, tmDS, tmDQ, a, s);
+  const bool pair = paired && n_items % 2 == 0 && d_head == 256;
+  if (dQ != nullptr) {
+    if (d_head == 256) return pair ? launch_dq<256, 2, true>(tmQ, tmDO, tmK, tmV, tmDS, tmDQ, a, s) : launch_dq<256, 1, true>(tmQ, tmDO, tmK, tmV, tmDS, tmDQ, a, s);
+    return launch_dq<64, 1, true>(tmQ, tmDO, tmK, tmV, tmDS, tmDQ, a, s);
   }
-  return launch_dq<64, 1>(tmQ, tmDO, tmK, tmV, tmDS, tmDQ, a, s);
+  if (d_head == 256) return pair ? launch_dq<256, 2, false>(tmQ, tmDO, tmK, tmV, tmDS, tmDQ, a, s) : launch_dq<256, 1, false>(tmQ, tmDO, tmK, tmV, tmDS, tmDQ, a, s);
+  return launch_dq<64, 1, false>(tmQ, tmDO, tmK, tmV, tmDS, tmDQ, a, s);
 }
 
 }  // extern "C"

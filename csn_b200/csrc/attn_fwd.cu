@@ -15,6 +15,8 @@
 //                            rescale of O only when the max grows by > 2^8), P_j -> SMEM (16-bit,
 //                            128B-swizzled K-major tile = A operand of the P V MMA), final O / l and
 //                            LSE written by the same warps.
+#include <stdlib.h>
+
 #include "host_util.h"
 #include "ptx.cuh"
 
@@ -52,6 +54,7 @@ struct AttnFwdArgs {
   int dtype;
   uint32_t idesc_qk;  // M=128, N=128, both K-major
   uint32_t idesc_pv;  // M=128, N=d, A K-major, B MN-major
+  int debug;          // experiments only (CSN_ATTN_DEBUG): bit 0 = skip the softmax arithmetic, bit 1 = skip the epilogue stores
 };
 
 template <int DH>
@@ -303,7 +306,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         const uint32_t s_addr = tmem_base + lane_addr + b * 128;
         const int nvalid = min(128, it.kv_len - j * 128);
         bool waited_p = false;
-        if (MODE == 1) {
+        if (p.debug & 1) {
+          mbar_wait(bp_empty, pe_ph ^ 1);
+          pe_ph ^= 1;
+          l = 1.f;
+        } else if (MODE == 1) {
           // ---- dV mode: lane = query row of the streamed tile, columns = the resident keys.
           //      P[query][key] = exp(s*scale - lse[query]); statistics come from the forward pass.
           const bool rvalid = r < nvalid;                       // query row exists
@@ -450,7 +457,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       // slabs per warp are in flight. Rows >= q_valid are written as zeros (outputs live in padded layouts).
       int slab = 0;
 #pragma unroll 1
-      for (int c = 0; c < DH; c += 64) {
+      for (int c = 0; c < ((p.debug & 2) ? 0 : DH); c += 64) {
         uint32_t v0[32], v1[32];
         tmem_ld_32x32(o_addr + c, v0);
         tmem_ld_32x32(o_addr + c + 32, v1);
@@ -582,6 +589,10 @@ static int attn_launch_common(int mode, const void* Q, const void* K, const void
   a.scale = 1.0f / sqrtf((float)d_head);
   a.scale_log2 = a.scale * 1.4426950408889634f;
   a.dtype = dtype;
+  {
+    const char* dbg = getenv("CSN_ATTN_DEBUG");
+    a.debug = dbg ? atoi(dbg) : 0;
+  }
   const uint32_t fmt = dtype == CSN_F16 ? 0u : 1u;
   a.idesc_qk = umma_idesc_f16(fmt, 0, 0, 128);
   a.idesc_pv = umma_idesc_f16(fmt, mode == 1 ? 1u : 0u, 1, (uint32_t)d_head);   // dV mode reads P^T (MN-major A)

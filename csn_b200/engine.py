@@ -367,16 +367,21 @@ def attention_backward(ctx: AttnContext, dY: torch.Tensor, need_dx: bool, amax: 
         alloc = torch.empty if ((geom.kv_len + 127) // 128) * 128 >= CP else torch.zeros
         dS = alloc(nblk * prow, CP, dtype=dt, device=dev)
         it_dq = attn_items(ctx.groups, geom, h, d, dev, "dq")
+        fuse_dq = os.environ.get("CSN_FUSED_DQ", "0") == "1"   # dQ inside the kernel (slower: re-reads K_j)
         rc = lib.csn_attn_bwd_dq(Qv.data_ptr(), dO.data_ptr(), Kv.data_ptr(), Vv.data_ptr(), S * NP, nblk * NP, S * NP,
                                  HD, 3 * HD, HD, 3 * HD, 3 * HD, d, L.dtype_code(dt), it_dq.data_ptr(),
-                                 it_dq.shape[0], dQv.data_ptr(), 3 * HD, dS.data_ptr(), dS.shape[0], CP, lse.data_ptr(),
-                                 delta.data_ptr(), _paired(geom), L.stream_ptr())
+                                 it_dq.shape[0], dQv.data_ptr() if fuse_dq else None, 3 * HD, dS.data_ptr(),
+                                 dS.shape[0], CP, lse.data_ptr(), delta.data_ptr(), _paired(geom), L.stream_ptr())
         L.check(rc, "csn_attn_bwd_dq")
         for g in ctx.groups:
             nb = (h, NC, g.n_in, g.n_out)
+            dSk = L.mat(dS[g.blk0 * prow:], L.MAJOR_K, mn_off=(CP, h * CP, prow, g.n_in * prow))
             dSt = L.mat(dS[g.blk0 * prow:], L.MAJOR_MN, k_off=(CP, h * CP, prow, g.n_in * prow))          # dS^T
+            Km = L.mat(Kv[g.k0 * NP:], L.MAJOR_MN, mn_off=(d, 0, 0, 0), k_off=(0, CP, g.k_si * NP, g.k_so * NP))
             Qm = L.mat(Qv[g.q0 * NP:], L.MAJOR_MN, mn_off=(d, 0, 0, 0), k_off=(0, CP, g.q_si * NP, g.q_so * NP))
             off = (d, CP * 3 * HD, NP * 3 * HD, g.n_in * NP * 3 * HD)
+            if not fuse_dq:
+                L.gemm(dSk, Km, L.out(dQv[g.blk0 * NP:], 3 * HD, off=off), CP, d, CP, nb=nb)    # dQ = dS K
             L.gemm(dSt, Qm, L.out(dKv[g.blk0 * NP:], 3 * HD, off=off), CP, d, CP, nb=nb)    # dK = dS^T Q
     else:
         _attention_backward_materialised(ctx, dO, dQKV)
