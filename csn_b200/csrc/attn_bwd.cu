@@ -131,7 +131,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 
   if (warp == 0) {
     // ================================================================== TMA producer
-    if (lane == 0) {
+    if (elect_one()) {
       int st = 0;
       uint32_t ph = 0, q_ph = 0;
       auto load_tile = [&](const CUtensorMap* tm, int col0, int row0) {   // 128 rows x DH cols, K-major k-blocks
@@ -169,7 +169,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     }
   } else if (warp == 1) {
     // ================================================================== MMA issuer
-    if (lane == 0) {
+    if (elect_one()) {
       int st = 0;
       uint32_t ph = 0, q_ph = 0, ds_ph = 0, dq_ph = 0;
       uint32_t sdp_ph[2] = {0, 0};
@@ -344,7 +344,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         }
         fence_proxy_async_smem();
         __syncwarp();
-        if (lane == 0) {
+        if (elect_one()) {
           tma_store_2d(&tmDQ, buf, it.col0 + c, it.o_row0 + q * 32);
           tma_store_commit();
         }

@@ -144,7 +144,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 
   if (warp == 0) {
     // ================================================================== TMA producer
-    if (lane == 0) {
+    if (elect_one()) {
       int st = 0;
       uint32_t ph = 0, q_ph = 0;
       auto load_k = [&](const AttnItem& it, int j) {
@@ -181,6 +181,24 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       for (int wk = worker; wk < n_work; wk += n_workers) {
         const AttnItem it = p.items[wk * CL + rank];
         const int nkv = (it.kv_len + 127) >> 7;
+        // L2 prefetch of everything the NEXT item of this CTA streams: its first touch would otherwise be an
+        // HBM miss (~2x the L2-hit latency) and the 4-slot ring cannot cover that.
+        if ((p.debug & 4) == 0 && wk + n_workers < n_work) {
+          const AttnItem nx = p.items[(wk + n_workers) * CL + rank];
+          const int nn = (nx.kv_len + 127) >> 7;
+          for (int j = 0; j < nn; ++j) {
+#pragma unroll
+            for (int kb = 0; kb < Cfg::KB; ++kb) {
+              if ((kb % CL) != rank) continue;   // the two CTAs of a cluster stream the same tiles: split the prefetch
+              tma_prefetch_l2_2d(&tmK, nx.col0 + kb * 64, nx.kv_row0 + j * 128);
+#pragma unroll
+              for (int sv = 0; sv < Cfg::V_SLOTS; ++sv)
+                tma_prefetch_l2_2d(&tmV, nx.col0 + kb * 64, nx.v_row0 + j * 128 + sv * Cfg::KEYS_PER_VSLOT);
+            }
+          }
+#pragma unroll
+          for (int kb = 0; kb < Cfg::KB; ++kb) tma_prefetch_l2_2d(&tmQ, nx.col0 + kb * 64, nx.q_row0);
+        }
         mbar_wait(bq_empty, q_ph ^ 1);
         mbar_arrive_expect_tx(bq_full, Cfg::Q_BYTES);
 #pragma unroll
@@ -197,7 +215,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     }
   } else if (warp == 1) {
     // ================================================================== MMA issuer
-    if (lane == 0) {
+    if (elect_one()) {
       int st = 0;
       uint32_t ph = 0, q_ph = 0, p_ph = 0, o_ph = 0;
       uint32_t s_ph[2] = {0, 0};
@@ -498,7 +516,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           }
           fence_proxy_async_smem();
           __syncwarp();
-          if (lane == 0) {
+          if (elect_one()) {
             tma_store_2d(which == 0 ? &tmO : &tmOlo, buf, it.col0 + c, it.o_row0 + q * 32);
             tma_store_commit();
           }

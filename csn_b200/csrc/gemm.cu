@@ -185,7 +185,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
-    if (lane == 0) {
+    if (elect_one()) {
       int st = 0;
       uint32_t ph = 0;
       for (long long t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
@@ -223,7 +223,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
+    if (elect_one()) {
       int st = 0;
       uint32_t ph = 0;
       int acc = 0;

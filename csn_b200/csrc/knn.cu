@@ -96,7 +96,7 @@ knn_score_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   const uint32_t tmem_base = *tmem_ptr_smem;
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one()) {
       int st = 0;
       uint32_t ph = 0, a_ph = 0;
       for (int it = blockIdx.x; it < p.n_items; it += gridDim.x) {
@@ -123,7 +123,7 @@ knn_score_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    if (elect_one()) {
       int st = 0, acc = 0;
       uint32_t ph = 0, acc_ph = 0, a_ph = 0;
       for (int it = blockIdx.x; it < p.n_items; it += gridDim.x) {
@@ -280,7 +280,7 @@ knn_score_exact_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_co
   const uint32_t tmem_base = *tmem_ptr_smem;
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one()) {
       int st = 0;
       uint32_t ph = 0, a_ph = 0;
       for (int it = blockIdx.x; it < p.n_items; it += gridDim.x) {
@@ -310,7 +310,7 @@ knn_score_exact_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_co
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    if (elect_one()) {
       int st = 0, acc = 0;
       uint32_t ph = 0, acc_ph = 0, a_ph = 0;
       for (int it = blockIdx.x; it < p.n_items; it += gridDim.x) {
@@ -507,7 +507,7 @@ __global__ void topk_rows_kernel(const float* __restrict__ scores, long long ld,
       const int ol = __shfl_xor_sync(0xffffffffu, bl, o);
       if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; bl = ol; }
     }
-    if (lane == 0) {
+    if (elect_one()) {
       out_val[(long long)row * kk + r] = bv;
       out_idx[(long long)row * kk + r] = bi;
     }

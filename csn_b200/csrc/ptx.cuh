@@ -20,15 +20,23 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
 
+// One lane of a fully converged warp. Role bodies that issue tcgen05 / TMA instructions branch on THIS
+// (not on `lane == 0`): ptxas recognises the elect.sync idiom, knows a single thread is active inside and
+// keeps descriptors / addresses in uniform registers instead of wrapping every UTCHMMA in a
+// per-thread R2UR broadcast loop (~18 extra instructions per MMA).
 __device__ __forceinline__ bool elect_one() {
-  uint32_t pred;
+  uint32_t pred = 0;
+  uint32_t laneid = 0;
   asm volatile(
       "{\n"
-      ".reg .pred p;\n"
-      "elect.sync _|p, 0xffffffff;\n"
-      "selp.u32 %0, 1, 0, p;\n"
+      ".reg .b32 %%rx;\n"
+      ".reg .pred %%px;\n"
+      "     elect.sync %%rx|%%px, %2;\n"
+      "@%%px mov.s32 %1, 1;\n"
+      "     mov.s32 %0, %%rx;\n"
       "}\n"
-      : "=r"(pred));
+      : "+r"(laneid), "+r"(pred)
+      : "r"(0xFFFFFFFF));
   return pred != 0;
 }
 
@@ -89,6 +97,11 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* tm,
       " [%0], [%1, {%3, %4, %5}], [%2];"
       ::"r"(dst), "l"(tm), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
+}
+
+// Pull a tile into L2 only (no smem, no barrier): hides the HBM miss of a tile that will be loaded later.
+__device__ __forceinline__ void tma_prefetch_l2_2d(const CUtensorMap* tm, int c0, int c1) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(tm), "r"(c0), "r"(c1) : "memory");
 }
 
 // Same load, delivered to the same smem offset of every CTA in `cta_mask` of the cluster; each
