@@ -17,45 +17,9 @@
 //                            LSE written by the same warps.
 #include <stdlib.h>
 
-#include "host_util.h"
-#include "ptx.cuh"
+#include "attn_common.cuh"
 
 namespace csn {
-
-__device__ __forceinline__ float fast_exp2(float x) {
-  float y;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
-
-struct AttnItem {
-  int q_row0;    // first query row (row of the Q view)
-  int q_valid;   // rows of the tile that exist (<= 128); the others are written as zeros
-  int kv_row0;   // first key/value row
-  int kv_len;    // number of keys this tile attends to
-  int o_row0;    // first output row (row of the O buffer)
-  int col0;      // head * d: column offset in the Q/K/V views and in O
-  int lse_off;   // lse[lse_off + r] for row r of the tile
-  int flags;     // bit 0: write zeros to the tile rows >= q_valid (padded layouts); else leave them untouched
-  int v_row0;    // first row of the MN-major streamed operand (V; dO in dV mode) matching kv_row0
-  int pad;
-};
-
-struct AttnFwdArgs {
-  const AttnItem* items;
-  int n_items;
-  void* O;            // 16-bit [rows][ldo]
-  void* Olo;          // optional 16-bit residual (o - round16(o)) * 2^11 (fp16) / 2^8 (bf16), same layout as O:
-                      // lets the backward pass form delta = rowsum(dO o O) to ~22 bits
-  long long ldo;
-  float* lse;         // natural-log sum-exp of the scaled scores per query row
-  float scale_log2;   // (1/sqrt(d)) * log2(e)
-  float scale;        // 1/sqrt(d)
-  int dtype;
-  uint32_t idesc_qk;  // M=128, N=128, both K-major
-  uint32_t idesc_pv;  // M=128, N=d, A K-major, B MN-major
-  int debug;          // experiments only (CSN_ATTN_DEBUG): bit 0 = skip the softmax arithmetic, bit 1 = skip the epilogue stores
-};
 
 template <int DH>
 struct AttnCfg {
@@ -181,24 +145,6 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       for (int wk = worker; wk < n_work; wk += n_workers) {
         const AttnItem it = p.items[wk * CL + rank];
         const int nkv = (it.kv_len + 127) >> 7;
-        // L2 prefetch of everything the NEXT item of this CTA streams: its first touch would otherwise be an
-        // HBM miss (~2x the L2-hit latency) and the 4-slot ring cannot cover that.
-        if ((p.debug & 4) == 0 && wk + n_workers < n_work) {
-          const AttnItem nx = p.items[(wk + n_workers) * CL + rank];
-          const int nn = (nx.kv_len + 127) >> 7;
-          for (int j = 0; j < nn; ++j) {
-#pragma unroll
-            for (int kb = 0; kb < Cfg::KB; ++kb) {
-              if ((kb % CL) != rank) continue;   // the two CTAs of a cluster stream the same tiles: split the prefetch
-              tma_prefetch_l2_2d(&tmK, nx.col0 + kb * 64, nx.kv_row0 + j * 128);
-#pragma unroll
-              for (int sv = 0; sv < Cfg::V_SLOTS; ++sv)
-                tma_prefetch_l2_2d(&tmV, nx.col0 + kb * 64, nx.v_row0 + j * 128 + sv * Cfg::KEYS_PER_VSLOT);
-            }
-          }
-#pragma unroll
-          for (int kb = 0; kb < Cfg::KB; ++kb) tma_prefetch_l2_2d(&tmQ, nx.col0 + kb * 64, nx.q_row0);
-        }
         mbar_wait(bq_empty, q_ph ^ 1);
         mbar_arrive_expect_tx(bq_full, Cfg::Q_BYTES);
 #pragma unroll

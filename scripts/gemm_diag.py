@@ -34,6 +34,9 @@ CASES = {
     "perf_8k": (8192, 8192, 8192, "f16", 0, 0, {"perf": True}),
     "perf_8k_bf16": (8192, 8192, 8192, "bf16", 0, 0, {"perf": True}),
     "perf_proj": (81920, 768, 256, "f16", 0, 0, {"perf": True}),
+    "perf_n256": (37888, 256, 4096, "f16", 0, 0, {"perf": True}),
+    "perf_n128": (37888, 128, 4096, "f16", 0, 0, {"perf": True}),
+    "perf_n64": (37888, 64, 4096, "f16", 0, 0, {"perf": True}),
 }
 
 
