@@ -75,7 +75,7 @@ _EXTRA_SIGNATURES: dict[str, list] = {
     "csn_knn_reduce": [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int64, C.c_void_p],
     "csn_pack_rows": [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int64, C.c_int32, C.c_int64,
                       C.c_int64, C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
-                      C.c_void_p],
+                      C.c_void_p, C.c_void_p],
     "csn_softmax_fwd": [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                         C.c_void_p],
     "csn_softmax_bwd": [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
@@ -86,7 +86,7 @@ _EXTRA_SIGNATURES: dict[str, list] = {
     "csn_colsum_reduce": [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_float, C.c_void_p],
     "csn_ln_bwd": [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                    C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p,
-                   C.c_void_p, C.c_float, C.c_void_p],
+                   C.c_void_p, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p],
     "csn_combine_fwd": [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32,
                         C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p],
     "csn_combine_bwd": [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,

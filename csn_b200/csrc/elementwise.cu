@@ -39,6 +39,7 @@ struct PackArgs {
   int n_points;         // points used from the source (n_chunks * chunk)
   int chunk, chunk_pad, rows_pad;
   int dtype;
+  float* amax;          // optional: max |src| over everything read (atomic max on the bit pattern)
 };
 
 __global__ void __launch_bounds__(256) pack_kernel(const PackArgs p) {
@@ -51,7 +52,16 @@ __global__ void __launch_bounds__(256) pack_kernel(const PackArgs p) {
   const int ch = r0 / p.chunk_pad, i = r0 % p.chunk_pad + lane;
   const int n = ch * p.chunk + i;
   const bool valid = i < p.chunk && n < p.n_points;
-  for (int c = warp; c < DM; c += 8) tile[lane][c] = valid ? __ldg(src + c * p.ch_stride + n) : 0.f;
+  float amx = 0.f;
+  for (int c = warp; c < DM; c += 8) {
+    const float v = valid ? __ldg(src + c * p.ch_stride + n) : 0.f;
+    tile[lane][c] = v;
+    amx = fmaxf(amx, fabsf(v));
+  }
+  if (p.amax) {
+    amx = warp_max(amx);
+    if (lane == 0 && amx > 0.f) atomicMax(reinterpret_cast<int*>(p.amax), __float_as_int(amx));
+  }
   __syncthreads();
   for (int rr = warp; rr < 32; rr += 8) {
     const long long row = slot * p.rows_pad + r0 + rr;
@@ -59,7 +69,7 @@ __global__ void __launch_bounds__(256) pack_kernel(const PackArgs p) {
     for (int g = 0; g < 4; ++g) {
       const int c = g * 64 + 2 * lane;
       const float a = tile[rr][c], b = tile[rr][c + 1];
-      reinterpret_cast<uint32_t*>(p.dst16)[(row * DM + c) >> 1] = pack2(a, b, p.dtype);
+      if (p.dst16) reinterpret_cast<uint32_t*>(p.dst16)[(row * DM + c) >> 1] = pack2(a, b, p.dtype);
       if (p.dst32) *reinterpret_cast<float2*>(p.dst32 + row * DM + c) = make_float2(a, b);
     }
   }
@@ -195,10 +205,10 @@ __global__ void __launch_bounds__(256) add_ln_fwd_kernel(const AddLnArgs p) {
   for (int i = 0; i < 8; ++i) {
     const long long row = row0 + warp * 8 + i;
     if (row >= p.rows) break;
-    const long long rin = row - blk * p.block_rows;
+    const int rin = (int)(row - blk * p.block_rows);
     float4* z4 = reinterpret_cast<float4*>(p.Z + row * DM);
     float4* y4 = reinterpret_cast<float4*>(p.Y + row * DM);
-    const bool valid = (int)(rin % p.group_rows) < p.rows_valid;
+    const bool valid = (rin % p.group_rows) < p.rows_valid;
     if (!valid) {
       const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
       z4[lane] = zero; z4[32 + lane] = zero; y4[lane] = zero; y4[32 + lane] = zero;
@@ -267,6 +277,8 @@ struct LnBwdArgs {
   const float* bcast;  // optional [n][256]: row vector added to every valid row of a block before anything else
   const int* bcast_idx;  // per block: row of `bcast` (or -1)
   float bcast_scale;
+  // implicit upstream gradient: dY[block] = src_w[block] * dYsrc[src_idx[block]] (rows of one shape), or 0 if src_idx < 0
+  const int* src_idx; const float* src_w;
 };
 
 __global__ void __launch_bounds__(256) ln_bwd_kernel(const LnBwdArgs p) {
@@ -276,24 +288,42 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const LnBwdArgs p) {
   const float4 g0 = __ldg(reinterpret_cast<const float4*>(p.gamma) + lane), g1 = __ldg(reinterpret_cast<const float4*>(p.gamma) + 32 + lane);
   float dg[8] = {0, 0, 0, 0, 0, 0, 0, 0}, db[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   const float gscale = p.amax ? exp2f(floorf(log2f(128.f / fmaxf(__ldg(p.amax), 1e-30f)))) : 1.f;
+  // a CTA's 64 rows lie inside one block (64 | block_rows): one 64-bit division per CTA, 32-bit math per row
+  const int blk = (int)(row0 / p.block_rows);
+  const int rin0 = (int)(row0 - (long long)blk * p.block_rows);
+  const int src_i = p.src_idx ? __ldg(p.src_idx + blk) : -1;
+  const float src_wgt = (p.src_idx && src_i >= 0) ? __ldg(p.src_w + blk) : 0.f;
+  const int bc_i = p.bcast ? __ldg(p.bcast_idx + blk) : -1;
   for (int i = 0; i < 8; ++i) {
     const long long row = row0 + warp * 8 + i;
     if (row >= p.rows) break;
+    const int rin = rin0 + warp * 8 + i;
     float4* dz4 = p.dZ ? reinterpret_cast<float4*>(p.dZ + row * DM) : nullptr;
     uint2* dz16 = reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(p.dZ16) + row * DM);
-    const bool valid = (int)((row % p.block_rows) % p.group_rows) < p.rows_valid;
+    const bool valid = (rin % p.group_rows) < p.rows_valid;
     if (!valid) {
       const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
       if (dz4) { dz4[lane] = zero; dz4[32 + lane] = zero; }
       dz16[lane] = make_uint2(0, 0); dz16[32 + lane] = make_uint2(0, 0);
       continue;
     }
-    const float4* dy4 = reinterpret_cast<const float4*>(p.dY + row * DM);
     const float4* z4 = reinterpret_cast<const float4*>(p.Z + row * DM);
     const float mu = p.mean[row], rs = p.rstd[row];
-    float4 da = __ldg(dy4 + lane), dc = __ldg(dy4 + 32 + lane);
+    float4 da = make_float4(0.f, 0.f, 0.f, 0.f), dc = da;
+    if (p.src_idx) {
+      if (src_i >= 0) {
+        const float wgt = src_wgt;
+        const float4* dy4 = reinterpret_cast<const float4*>(p.dY + ((long long)src_i * p.block_rows + rin) * DM);
+        da = __ldg(dy4 + lane); dc = __ldg(dy4 + 32 + lane);
+        da.x *= wgt; da.y *= wgt; da.z *= wgt; da.w *= wgt;
+        dc.x *= wgt; dc.y *= wgt; dc.z *= wgt; dc.w *= wgt;
+      }
+    } else {
+      const float4* dy4 = reinterpret_cast<const float4*>(p.dY + row * DM);
+      da = __ldg(dy4 + lane); dc = __ldg(dy4 + 32 + lane);
+    }
     if (p.bcast) {
-      const int bi = __ldg(p.bcast_idx + row / p.block_rows);
+      const int bi = bc_i;
       if (bi >= 0) {
         const float4* b4 = reinterpret_cast<const float4*>(p.bcast + (long long)bi * DM);
         const float4 ba = __ldg(b4 + lane), bc = __ldg(b4 + 32 + lane);
@@ -482,14 +512,14 @@ extern "C" {
 int csn_pack_rows(const float* src, void* dst16, float* dst32, int64_t ch_stride, int32_t n0, int64_t src_s0,
                   int32_t n1, int64_t src_s1, int64_t dst_slot0, int64_t dst_s0, int64_t dst_s1,
                   int32_t n_points, int32_t chunk, int32_t chunk_pad, int32_t rows_pad, int32_t dtype,
-                  void* stream) {
+                  float* amax, void* stream) {
   using namespace csn;
   clear_error();
-  CSN_CHECK_ARG(src && dst16, "csn_pack_rows: null pointer");
+  CSN_CHECK_ARG(src && (dst16 || dst32), "csn_pack_rows: null pointer");
   CSN_CHECK_ARG(chunk_pad % 32 == 0 && rows_pad % chunk_pad == 0 && chunk <= chunk_pad, "csn_pack_rows: bad padding (chunk=%d chunk_pad=%d rows_pad=%d)", chunk, chunk_pad, rows_pad);
   CSN_CHECK_ARG(dtype == CSN_F16 || dtype == CSN_BF16, "csn_pack_rows: 16-bit destination only");
   if (n0 * n1 == 0) return 0;
-  PackArgs a{src, dst16, dst32, ch_stride, src_s0, src_s1, dst_slot0, dst_s0, dst_s1, n0, n1, n_points, chunk, chunk_pad, rows_pad, dtype};
+  PackArgs a{src, dst16, dst32, ch_stride, src_s0, src_s1, dst_slot0, dst_s0, dst_s1, n0, n1, n_points, chunk, chunk_pad, rows_pad, dtype, amax};
   return launch_simple(pack_kernel, dim3(rows_pad / 32, n0 * n1), dim3(256), a, stream, "pack_kernel");
 }
 
@@ -549,14 +579,15 @@ int csn_colsum_reduce(const float* part, float* out, int32_t n_blocks, int32_t p
 int csn_ln_bwd(const float* dY, const float* Z, const float* mean, const float* rstd, const float* gamma, float* dZ,
                void* dZ16, float* dgamma, float* dbeta, int64_t rows, int32_t block_rows, int32_t group_rows,
                int32_t rows_valid, int32_t dtype, const float* amax, const float* bcast, const int32_t* bcast_idx,
-               float bcast_scale, void* stream) {
+               float bcast_scale, const int32_t* src_idx, const float* src_w, void* stream) {
   using namespace csn;
   clear_error();
   CSN_CHECK_ARG(dY && Z && mean && rstd && gamma && dZ16 && dgamma && dbeta, "csn_ln_bwd: null pointer");
   CSN_CHECK_ARG(!bcast || bcast_idx, "csn_ln_bwd: bcast needs bcast_idx");
-  CSN_CHECK_ARG(rows % 64 == 0, "csn_ln_bwd: rows must be a multiple of 64");
+  CSN_CHECK_ARG(!src_idx || src_w, "csn_ln_bwd: src_idx needs src_w");
+  CSN_CHECK_ARG(rows % 64 == 0 && block_rows % 64 == 0, "csn_ln_bwd: rows and block_rows must be multiples of 64");
   if (rows == 0) return 0;
-  LnBwdArgs a{dY, Z, mean, rstd, gamma, dZ, dZ16, dgamma, dbeta, rows, group_rows, rows_valid, block_rows, dtype, amax, bcast, bcast_idx, bcast_scale};
+  LnBwdArgs a{dY, Z, mean, rstd, gamma, dZ, dZ16, dgamma, dbeta, rows, group_rows, rows_valid, block_rows, dtype, amax, bcast, bcast_idx, bcast_scale, src_idx, src_w};
   return launch_simple(ln_bwd_kernel, dim3((unsigned)(rows / 64)), dim3(256), a, stream, "ln_bwd_kernel");
 }
 

@@ -67,7 +67,7 @@ def _launch_pack(src: torch.Tensor, dst16, dst32, n0, s0, n1, s1, slot0, d0, d1,
     """src: fp32 view whose element (i0,i1,c,n) sits at i0*s0 + i1*s1 + c*n_src_points + n."""
     rc = L.lib().csn_pack_rows(src.data_ptr(), dst16.data_ptr(), dst32.data_ptr() if dst32 is not None else None,
                                n_src_points, n0, s0, n1, s1, slot0, d0, d1, geom.n_points, geom.chunk,
-                               geom.chunk_pad, geom.rows_pad, L.dtype_code(dst16.dtype), L.stream_ptr())
+                               geom.chunk_pad, geom.rows_pad, L.dtype_code(dst16.dtype), None, L.stream_ptr())
     L.check(rc, "csn_pack_rows")
 
 
@@ -308,7 +308,8 @@ def _pick_split(tiles: int, kb_total: int, target: int = 296) -> int:
 
 
 def attention_backward(ctx: AttnContext, dY: torch.Tensor, need_dx: bool, amax: torch.Tensor = None,
-                       bcast: torch.Tensor = None, bcast_idx: torch.Tensor = None, bcast_scale: float = 0.0):
+                       bcast: torch.Tensor = None, bcast_idx: torch.Tensor = None, bcast_scale: float = 0.0,
+                       src_idx: torch.Tensor = None, src_w: torch.Tensor = None):
     """Backward of attention_forward. dY: [blocks*NP, 256] fp32 (zero in pad rows).
     Returns dict with dWq, dWk, dWv, dWo (fp32, reference layouts), dgamma, dbeta and, if need_dx,
     dX [S*NP, 256] fp32 (padded row-major, gradient w.r.t. every slot's features)."""
@@ -335,7 +336,9 @@ def attention_backward(ctx: AttnContext, dY: torch.Tensor, need_dx: bool, amax: 
                         ctx.gamma.data_ptr(), dZ.data_ptr() if dZ is not None else None, dZ16.data_ptr(),
                         dgamma.data_ptr(), dbeta.data_ptr(), nblk * NP, NP, CP, geom.chunk, L.dtype_code(dt),
                         amax.data_ptr(), bcast.data_ptr() if bcast is not None else None,
-                        bcast_idx.data_ptr() if bcast_idx is not None else None, bcast_scale, L.stream_ptr())
+                        bcast_idx.data_ptr() if bcast_idx is not None else None, bcast_scale,
+                        src_idx.data_ptr() if src_idx is not None else None,
+                        src_w.data_ptr() if src_w is not None else None, L.stream_ptr())
     L.check(rc, "csn_ln_bwd")
     split = _pick_split(2 * ((HD + 255) // 256), nblk * NP // 64)
     # --- dWo = dZ^T O  (contraction over all rows; both operands consumed MN-major)

@@ -340,25 +340,31 @@ class _CsaFn(torch.autograd.Function):
         obs, ocs = 256 * geom.n_points, geom.n_points
         grads_glue = [None] * 4
         dpool = None
-        # one pass: dY = comp * dOut^T for the blocks of the weighted sum, dcomp = <dOut^T, Y>; the gradient
-        # of the pooled means is a per-block row vector and is added inside csn_ln_bwd (never materialised)
-        dY = torch.empty(nblk * geom.rows_pad, 256, dtype=torch.float32, device=dev)
+        # dcomp = <dOut^T, Y> per block of the weighted sum (one pass over dOut and Y)
+        dcomp = torch.zeros(B * (K + 1), dtype=torch.float32, device=dev) if has_glue else None
+        if has_glue:
+            rc = lib.csn_combine_bwd(dout.data_ptr(), a.Y.data_ptr(), None, cb.data_ptr(), cw.data_ptr(), cwi.data_ptr(),
+                                     nopool.data_ptr(), 0.0, None, dcomp.data_ptr(), nblk, obs, ocs, geom.n_points,
+                                     geom.chunk, geom.chunk_pad, geom.rows_pad, None, L.stream_ptr())
+            L.check(rc, "csn_combine_bwd")
+        # The upstream gradient of block j is comp[b,k] * dOut[b]^T (+ the pooled-mean row vector): dOut is
+        # transposed ONCE per batch item into padded rows (it stays L2-resident) and csn_ln_bwd forms
+        # cw[j] * dOutT[cb[j]] + dpool[pb[j]]/N on the fly; the (2K+1)x larger dY is never materialised.
+        dOutT = torch.empty(B * geom.rows_pad, 256, dtype=torch.float32, device=dev)
         amax = torch.zeros(1, dtype=torch.float32, device=dev)
-        dcomp = torch.zeros(B * (K + 1), dtype=torch.float32, device=dev) if ctx.glue is not None else None
-        rc = lib.csn_combine_bwd(dout.data_ptr(), a.Y.data_ptr(), None, cb.data_ptr(), cw.data_ptr(), cwi.data_ptr(),
-                                 nopool.data_ptr(), 0.0, dY.data_ptr(), dcomp.data_ptr() if dcomp is not None else None,
-                                 nblk, obs, ocs, geom.n_points, geom.chunk, geom.chunk_pad, geom.rows_pad,
-                                 amax.data_ptr(), L.stream_ptr())
-        L.check(rc, "csn_combine_bwd")
-        if ctx.glue is not None:
+        rc = lib.csn_pack_rows(dout.data_ptr(), None, dOutT.data_ptr(), geom.n_points, B, 256 * geom.n_points, 1, 0, 0, 1, 0,
+                               geom.n_points, geom.chunk, geom.chunk_pad, geom.rows_pad, L.CSN_F16, amax.data_ptr(),
+                               L.stream_ptr())
+        L.check(rc, "csn_pack_rows(dOut)")
+        if has_glue:
             pooled, loc, comp_g = ctx.glue
             gl = torch.autograd.grad(comp_g, [pooled] + loc, dcomp.view(B, K + 1))
             dpool = gl[0].contiguous()
             grads_glue = list(gl[1:])
-            amax = amax + dpool.abs().max() / geom.n_points   # bound on |dY + dpool/N| for the gradient scaling
+            amax = amax + dpool.abs().max() / geom.n_points   # bound on |dY + dpool/N| for the gradient scaling (comp <= 1)
         need_dx = ctx.needs_input_grad[0] or ctx.needs_input_grad[1]
-        g = E.attention_backward(a, dY, need_dx, amax, bcast=dpool, bcast_idx=pb if dpool is not None else None,
-                                 bcast_scale=1.0 / geom.n_points)
+        g = E.attention_backward(a, dOutT, need_dx, amax, bcast=dpool, bcast_idx=pb if dpool is not None else None,
+                                 bcast_scale=1.0 / geom.n_points, src_idx=cb, src_w=cw)
         dx = dnb = None
         if need_dx:
             G = _rows_to_channel_major(g["dX"], S, max(n_src, n_src_nb), geom).view(B, K + 1, 256, -1, 1)

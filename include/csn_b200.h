@@ -170,11 +170,12 @@ int csn_attn_bwd_dq(const void* Q, const void* dO, const void* K, const void* V,
 /* Channel-major fp32 features (the reference layout (B,256,N,1), csa_models.py:92-94) -> padded
  * row-major rows, 16-bit (dst16) and optionally fp32 (dst32, may be NULL).  Source element
  * (i0,i1,c,n) is src[i0*src_s0 + i1*src_s1 + c*ch_stride + n]; destination slot is
- * dst_slot0 + i0*dst_s0 + i1*dst_s1. */
+ * dst_slot0 + i0*dst_s0 + i1*dst_s1.  dst16 may be NULL (fp32 transpose only); amax (optional, device,
+ * zero-initialised) receives max |src|. */
 int csn_pack_rows(const float* src, void* dst16, float* dst32, int64_t ch_stride, int32_t n0,
                   int64_t src_s0, int32_t n1, int64_t src_s1, int64_t dst_slot0, int64_t dst_s0,
                   int64_t dst_s1, int32_t n_points, int32_t chunk, int32_t chunk_pad, int32_t rows_pad,
-                  int32_t dtype, void* stream);
+                  int32_t dtype, float* amax, void* stream);
 
 /* P = softmax over the first cols_valid columns of each fp32 row (F.softmax(dim=-1),
  * csa_models.py:141), 16-bit, zero in pad columns and in pad rows (row % group_rows >= rows_valid). */
@@ -198,12 +199,16 @@ int csn_colsum_reduce(const float* part, float* out, int32_t n_blocks, int32_t p
 /* dZ may be NULL (only the 16-bit copy is written).  bcast (optional, [n][256]) adds the row
  * bcast_scale * bcast[bcast_idx[block]] to every valid row of a block before the backward formula: the
  * gradient of the pooled mean (csa_models.py:212,219) without materialising it.
+ * src_idx/src_w (optional, per block): the upstream gradient of block j is src_w[j] * dY[src_idx[j]] (dY then
+ * holds one block of rows per SOURCE, e.g. the transposed output gradient of each batch item) or zero if
+ * src_idx[j] < 0 — the compatibility-weighted fan-out of csa_models.py:232-238 is never materialised.
  * amax (optional, device): dY is multiplied by the power of two 2^floor(log2(128 / *amax)) on load so
  * that 16-bit gradient intermediates stay in the normal fp16 range; the caller divides the results. */
 int csn_ln_bwd(const float* dY, const float* Z, const float* mean, const float* rstd, const float* gamma,
                float* dZ, void* dZ16, float* dgamma, float* dbeta, int64_t rows, int32_t block_rows,
                int32_t group_rows, int32_t rows_valid, int32_t dtype, const float* amax, const float* bcast,
-               const int32_t* bcast_idx, float bcast_scale, void* stream);
+               const int32_t* bcast_idx, float bcast_scale, const int32_t* src_idx, const float* src_w,
+               void* stream);
 
 /* out[b][c][n] = sum_k w[b*n_k+k] * Y[blk[b*n_k+k]][padrow(n)][c]: the compatibility-weighted sum
  * of the self- and cross-attention outputs written back channel-major (csa_models.py:232-240);
