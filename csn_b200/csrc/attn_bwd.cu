@@ -375,26 +375,30 @@ __global__ void attn_delta_kernel(const void* __restrict__ dO, const void* __res
   if (wid >= rows * n_head) return;
   const long long row = wid / n_head;
   const int head = (int)(wid % n_head);
-  const uint32_t* a = reinterpret_cast<const uint32_t*>(reinterpret_cast<const uint16_t*>(dO) + row * ld + head * d);
-  const uint32_t* b = reinterpret_cast<const uint32_t*>(reinterpret_cast<const uint16_t*>(O) + row * ld + head * d);
-  const uint32_t* bl = Olo ? reinterpret_cast<const uint32_t*>(reinterpret_cast<const uint16_t*>(Olo) + row * ld + head * d) : nullptr;
+  const uint4* a = reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(dO) + row * ld + head * d);
+  const uint4* b = reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(O) + row * ld + head * d);
+  const uint4* bl = Olo ? reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(Olo) + row * ld + head * d) : nullptr;
   const float lo_inv = dtype == CSN_F16 ? 1.f / 2048.f : 1.f / 256.f;
   float s = 0.f, sl = 0.f;
-  for (int c = lane; c < d / 2; c += 32) {
-    const uint32_t x = __ldg(a + c), y = __ldg(b + c);
-    const uint32_t z = bl ? __ldg(bl + c) : 0u;
-    float2 fx, fy, fz;
-    if (dtype == CSN_F16) {
-      fx = __half22float2(*reinterpret_cast<const __half2*>(&x));
-      fy = __half22float2(*reinterpret_cast<const __half2*>(&y));
-      fz = __half22float2(*reinterpret_cast<const __half2*>(&z));
-    } else {
-      fx = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&x));
-      fy = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&y));
-      fz = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&z));
+  for (int c = lane; c < d / 8; c += 32) {   // 8 x 16-bit per 16-byte load
+    const uint4 x4 = __ldg(a + c), y4 = __ldg(b + c);
+    const uint4 z4 = bl ? __ldg(bl + c) : make_uint4(0u, 0u, 0u, 0u);
+    const uint32_t xs[4] = {x4.x, x4.y, x4.z, x4.w}, ys[4] = {y4.x, y4.y, y4.z, y4.w}, zs[4] = {z4.x, z4.y, z4.z, z4.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      float2 fx, fy, fz;
+      if (dtype == CSN_F16) {
+        fx = __half22float2(*reinterpret_cast<const __half2*>(&xs[k]));
+        fy = __half22float2(*reinterpret_cast<const __half2*>(&ys[k]));
+        fz = __half22float2(*reinterpret_cast<const __half2*>(&zs[k]));
+      } else {
+        fx = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&xs[k]));
+        fy = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&ys[k]));
+        fz = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&zs[k]));
+      }
+      s += fx.x * fy.x + fx.y * fy.y;
+      sl += fx.x * fz.x + fx.y * fz.y;
     }
-    s += fx.x * fy.x + fx.y * fy.y;
-    sl += fx.x * fz.x + fx.y * fz.y;
   }
   s = warp_sum(s) + warp_sum(sl) * lo_inv;
   if (lane == 0) {

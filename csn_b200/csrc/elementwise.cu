@@ -207,11 +207,12 @@ __global__ void __launch_bounds__(256) add_ln_fwd_kernel(const AddLnArgs p) {
     if (row >= p.rows) break;
     const int rin = (int)(row - blk * p.block_rows);
     float4* z4 = reinterpret_cast<float4*>(p.Z + row * DM);
-    float4* y4 = reinterpret_cast<float4*>(p.Y + row * DM);
+    float4* y4 = p.Y ? reinterpret_cast<float4*>(p.Y + row * DM) : nullptr;
     const bool valid = (rin % p.group_rows) < p.rows_valid;
     if (!valid) {
       const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
-      z4[lane] = zero; z4[32 + lane] = zero; y4[lane] = zero; y4[32 + lane] = zero;
+      z4[lane] = zero; z4[32 + lane] = zero;
+      if (y4) { y4[lane] = zero; y4[32 + lane] = zero; }
       if (p.Y16) {
         uint2* y16 = reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(p.Y16) + row * DM);
         y16[lane] = make_uint2(0, 0); y16[32 + lane] = make_uint2(0, 0);
@@ -233,7 +234,7 @@ __global__ void __launch_bounds__(256) add_ln_fwd_kernel(const AddLnArgs p) {
     float4 ya, yc;
     ya.x = dx0 * rs * g0.x + b0.x; ya.y = dx1 * rs * g0.y + b0.y; ya.z = dx2 * rs * g0.z + b0.z; ya.w = dx3 * rs * g0.w + b0.w;
     yc.x = dx4 * rs * g1.x + b1.x; yc.y = dx5 * rs * g1.y + b1.y; yc.z = dx6 * rs * g1.z + b1.z; yc.w = dx7 * rs * g1.w + b1.w;
-    y4[lane] = ya; y4[32 + lane] = yc;
+    if (y4) { y4[lane] = ya; y4[32 + lane] = yc; }
     if (p.Y16) {
       uint2* y16 = reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(p.Y16) + row * DM);
       y16[lane] = make_uint2(pack2(ya.x, ya.y, p.dtype), pack2(ya.z, ya.w, p.dtype));
@@ -281,7 +282,7 @@ struct LnBwdArgs {
   const int* src_idx; const float* src_w;
 };
 
-__global__ void __launch_bounds__(256) ln_bwd_kernel(const LnBwdArgs p) {
+__global__ void __launch_bounds__(256, 4) ln_bwd_kernel(const LnBwdArgs p) {
   __shared__ float red[2][8][DM];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long row0 = (long long)blockIdx.x * 64;
@@ -374,11 +375,25 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const LnBwdArgs p) {
 
 // ------------------------------------------------------------------------------------------ combine fwd
 // out[b][c][n] = sum_k w[b*n_k + k] * Y[blk[b*n_k + k]][padrow(n)][c]      (channel-major output)
+struct LnParams {   // when mean != nullptr the row source holds PRE-LayerNorm rows z and y = (z-mean)*rstd*gamma+beta is formed on the fly
+  const float* mean; const float* rstd; const float* gamma; const float* beta;
+};
+
+__device__ __forceinline__ void ln_apply(const LnParams& ln, long long row, int lane, float4& a, float4& c) {
+  if (ln.mean == nullptr) return;
+  const float mu = __ldg(ln.mean + row), rs = __ldg(ln.rstd + row);
+  const float4 g0 = __ldg(reinterpret_cast<const float4*>(ln.gamma) + lane), g1 = __ldg(reinterpret_cast<const float4*>(ln.gamma) + 32 + lane);
+  const float4 b0 = __ldg(reinterpret_cast<const float4*>(ln.beta) + lane), b1 = __ldg(reinterpret_cast<const float4*>(ln.beta) + 32 + lane);
+  a.x = (a.x - mu) * rs * g0.x + b0.x; a.y = (a.y - mu) * rs * g0.y + b0.y; a.z = (a.z - mu) * rs * g0.z + b0.z; a.w = (a.w - mu) * rs * g0.w + b0.w;
+  c.x = (c.x - mu) * rs * g1.x + b1.x; c.y = (c.y - mu) * rs * g1.y + b1.y; c.z = (c.z - mu) * rs * g1.z + b1.z; c.w = (c.w - mu) * rs * g1.w + b1.w;
+}
+
 struct CombineArgs {
   const float* Y; const int* blk; const float* w; float* out; void* rows16;  // rows16: optional 16-bit row-major copy [b][rows_pad][256]
   long long out_b_stride, out_ch_stride;
   int n_k, n_points, chunk, chunk_pad, rows_pad;
   int dtype;
+  LnParams ln;
 };
 
 __global__ void __launch_bounds__(256) combine_fwd_kernel(const CombineArgs p) {
@@ -391,8 +406,10 @@ __global__ void __launch_bounds__(256) combine_fwd_kernel(const CombineArgs p) {
     float4 a = make_float4(0.f, 0.f, 0.f, 0.f), c = a;
     for (int k = 0; k < p.n_k; ++k) {
       const float wk = __ldg(p.w + b * p.n_k + k);
-      const float4* y4 = reinterpret_cast<const float4*>(p.Y + ((long long)__ldg(p.blk + b * p.n_k + k) * p.rows_pad + r) * DM);
-      const float4 ya = __ldg(y4 + lane), yc = __ldg(y4 + 32 + lane);
+      const long long yrow = (long long)__ldg(p.blk + b * p.n_k + k) * p.rows_pad + r;
+      const float4* y4 = reinterpret_cast<const float4*>(p.Y + yrow * DM);
+      float4 ya = __ldg(y4 + lane), yc = __ldg(y4 + 32 + lane);
+      ln_apply(p.ln, yrow, lane, ya, yc);
       a.x += wk * ya.x; a.y += wk * ya.y; a.z += wk * ya.z; a.w += wk * ya.w;
       c.x += wk * yc.x; c.y += wk * yc.y; c.z += wk * yc.z; c.w += wk * yc.w;
     }
@@ -428,6 +445,7 @@ struct CombineBwdArgs {
   long long out_b_stride, out_ch_stride;
   int n_points, chunk, chunk_pad, rows_pad;
   float* amax;          // optional: max |dY| over everything written (atomic max on the bit pattern)
+  LnParams ln;
 };
 
 __global__ void __launch_bounds__(256) combine_bwd_kernel(const CombineBwdArgs p) {
@@ -469,8 +487,10 @@ __global__ void __launch_bounds__(256) combine_bwd_kernel(const CombineBwdArgs p
         a.x += cwj * ga.x; a.y += cwj * ga.y; a.z += cwj * ga.z; a.w += cwj * ga.w;
         c.x += cwj * gc.x; c.y += cwj * gc.y; c.z += cwj * gc.z; c.w += cwj * gc.w;
         if (p.dcomp) {
-        const float4* y4 = reinterpret_cast<const float4*>(p.Y + ((long long)j * p.rows_pad + r) * DM);
-        const float4 ya = __ldg(y4 + lane), yc = __ldg(y4 + 32 + lane);
+        const long long yrow = (long long)j * p.rows_pad + r;
+        const float4* y4 = reinterpret_cast<const float4*>(p.Y + yrow * DM);
+        float4 ya = __ldg(y4 + lane), yc = __ldg(y4 + 32 + lane);
+        ln_apply(p.ln, yrow, lane, ya, yc);
         dot += ga.x * ya.x + ga.y * ya.y + ga.z * ya.z + ga.w * ya.w + gc.x * yc.x + gc.y * yc.y + gc.z * yc.z + gc.w * yc.w;
         }
       }
@@ -495,6 +515,46 @@ __global__ void __launch_bounds__(256) combine_bwd_kernel(const CombineBwdArgs p
       for (int w = 0; w < 8; ++w) s += wred[w];
       atomicAdd(p.dcomp + p.cw_index[j], s);
     }
+  }
+}
+
+// ------------------------------------------------------------------------------------------ block dot
+// dcomp[out_idx[j]] += sum over the valid rows of block j of < G[src_idx[j]][row], y_j[row] >, where y_j is the
+// (re-normalised) LayerNorm output of block j and G holds one block of rows per source (the transposed
+// output gradient).  64 rows per CTA, one warp per row, one atomic per CTA.
+struct BlockDotArgs {
+  const float* G; const float* Z; const int* src_idx; const int* out_idx; float* out;
+  long long rows; int block_rows, group_rows, rows_valid;
+  LnParams ln;
+};
+
+__global__ void __launch_bounds__(256) block_dot_kernel(const BlockDotArgs p) {
+  __shared__ float wred[8];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long row0 = (long long)blockIdx.x * 64;
+  const int blk = (int)(row0 / p.block_rows);
+  const int rin0 = (int)(row0 - (long long)blk * p.block_rows);
+  const int si = __ldg(p.src_idx + blk), oi = __ldg(p.out_idx + blk);
+  if (si < 0 || oi < 0) return;   // uniform per CTA
+  float dot = 0.f;
+  for (int i = 0; i < 8; ++i) {
+    const int rin = rin0 + warp * 8 + i;
+    const long long row = row0 + warp * 8 + i;
+    if (row >= p.rows || (rin % p.group_rows) >= p.rows_valid) continue;
+    const float4* g4 = reinterpret_cast<const float4*>(p.G + ((long long)si * p.block_rows + rin) * DM);
+    const float4* z4 = reinterpret_cast<const float4*>(p.Z + row * DM);
+    const float4 ga = __ldg(g4 + lane), gc = __ldg(g4 + 32 + lane);
+    float4 ya = __ldg(z4 + lane), yc = __ldg(z4 + 32 + lane);
+    ln_apply(p.ln, row, lane, ya, yc);
+    dot += ga.x * ya.x + ga.y * ya.y + ga.z * ya.z + ga.w * ya.w + gc.x * yc.x + gc.y * yc.y + gc.z * yc.z + gc.w * yc.w;
+  }
+  dot = warp_sum(dot);
+  if (lane == 0) wred[warp] = dot;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int w = 0; w < 8; ++w) t += wred[w];
+    atomicAdd(p.out + oi, t);
   }
 }
 
@@ -559,7 +619,7 @@ int csn_add_ln_fwd(float* Z, const float* R, const int32_t* res_block, float* Y,
                    int32_t group_rows, int32_t rows_valid, float eps, int32_t dtype, void* stream) {
   using namespace csn;
   clear_error();
-  CSN_CHECK_ARG(Z && R && Y && mean && rstd && gamma && beta, "csn_add_ln_fwd: null pointer");
+  CSN_CHECK_ARG(Z && R && mean && rstd && gamma && beta, "csn_add_ln_fwd: null pointer");
   CSN_CHECK_ARG(block_rows % 64 == 0 && rows % 64 == 0, "csn_add_ln_fwd: rows (%lld) and block_rows (%d) must be multiples of 64", (long long)rows, block_rows);
   if (rows == 0) return 0;
   AddLnArgs a{Z, R, res_block, Y, Y16, mean, rstd, gamma, beta, colsum, rows, block_rows, group_rows, rows_valid, eps, dtype};
@@ -593,25 +653,40 @@ int csn_ln_bwd(const float* dY, const float* Z, const float* mean, const float* 
 
 int csn_combine_fwd(const float* Y, const int32_t* blk, const float* w, float* out, void* rows16, int32_t n_b,
                     int32_t n_k, int64_t out_b_stride, int64_t out_ch_stride, int32_t n_points, int32_t chunk,
-                    int32_t chunk_pad, int32_t rows_pad, int32_t dtype, void* stream) {
+                    int32_t chunk_pad, int32_t rows_pad, int32_t dtype, const float* ln_mean, const float* ln_rstd,
+                    const float* ln_gamma, const float* ln_beta, void* stream) {
   using namespace csn;
   clear_error();
   CSN_CHECK_ARG(Y && blk && w && out, "csn_combine_fwd: null pointer");
+  CSN_CHECK_ARG(!ln_mean || (ln_rstd && ln_gamma && ln_beta), "csn_combine_fwd: incomplete LayerNorm parameters");
   CSN_CHECK_ARG(chunk_pad % 32 == 0 && rows_pad % chunk_pad == 0, "csn_combine_fwd: bad padding");
   if (n_b == 0) return 0;
-  CombineArgs a{Y, blk, w, out, rows16, out_b_stride, out_ch_stride, n_k, n_points, chunk, chunk_pad, rows_pad, dtype};
+  CombineArgs a{Y, blk, w, out, rows16, out_b_stride, out_ch_stride, n_k, n_points, chunk, chunk_pad, rows_pad, dtype, {ln_mean, ln_rstd, ln_gamma, ln_beta}};
   return launch_simple(combine_fwd_kernel, dim3(rows_pad / 32, n_b), dim3(256), a, stream, "combine_fwd_kernel");
+}
+
+int csn_block_dot(const float* G, const float* Z, const int32_t* src_idx, const int32_t* out_idx, float* out,
+                  int64_t rows, int32_t block_rows, int32_t group_rows, int32_t rows_valid, const float* ln_mean,
+                  const float* ln_rstd, const float* ln_gamma, const float* ln_beta, void* stream) {
+  using namespace csn;
+  clear_error();
+  CSN_CHECK_ARG(G && Z && src_idx && out_idx && out, "csn_block_dot: null pointer");
+  CSN_CHECK_ARG(rows % 64 == 0 && block_rows % 64 == 0, "csn_block_dot: rows and block_rows must be multiples of 64");
+  if (rows == 0) return 0;
+  BlockDotArgs a{G, Z, src_idx, out_idx, out, rows, block_rows, group_rows, rows_valid, {ln_mean, ln_rstd, ln_gamma, ln_beta}};
+  return launch_simple(block_dot_kernel, dim3((unsigned)(rows / 64)), dim3(256), a, stream, "block_dot_kernel");
 }
 
 int csn_combine_bwd(const float* dOut, const float* Y, const float* dpool, const int32_t* cb, const float* cw,
                     const int32_t* cw_index, const int32_t* pb, float pool_scale, float* dY, float* dcomp,
                     int32_t n_blocks, int64_t out_b_stride, int64_t out_ch_stride, int32_t n_points, int32_t chunk,
-                    int32_t chunk_pad, int32_t rows_pad, float* amax, void* stream) {
+                    int32_t chunk_pad, int32_t rows_pad, float* amax, const float* ln_mean, const float* ln_rstd,
+                    const float* ln_gamma, const float* ln_beta, void* stream) {
   using namespace csn;
   clear_error();
   CSN_CHECK_ARG(dOut && Y && cb && cw && cw_index && pb && (dY || dcomp), "csn_combine_bwd: null pointer");
   if (n_blocks == 0) return 0;
-  CombineBwdArgs a{dOut, Y, dpool, cb, cw, cw_index, pb, pool_scale, dY, dcomp, out_b_stride, out_ch_stride, n_points, chunk, chunk_pad, rows_pad, amax};
+  CombineBwdArgs a{dOut, Y, dpool, cb, cw, cw_index, pb, pool_scale, dY, dcomp, out_b_stride, out_ch_stride, n_points, chunk, chunk_pad, rows_pad, amax, {ln_mean, ln_rstd, ln_gamma, ln_beta}};
   return launch_simple(combine_bwd_kernel, dim3(rows_pad / 32, n_blocks), dim3(256), a, stream, "combine_bwd_kernel");
 }
 

@@ -93,6 +93,7 @@ class AttnContext:
     Wqkv16: torch.Tensor = None
     Wo16: torch.Tensor = None
     gamma: torch.Tensor = None
+    beta: torch.Tensor = None
     res_block: torch.Tensor = None
     extra: dict = field(default_factory=dict)
 
@@ -197,7 +198,8 @@ def _scores_and_probs(ctx: "AttnContext"):
 
 
 def attention_forward(Xh, Xf, groups, n_slots, n_blocks, w_q, w_k, w_v, w_o, gamma, beta, geom: Geometry,
-                      n_head: int, want_colsum: bool = True, save_for_backward: bool = True) -> AttnContext:
+                      n_head: int, want_colsum: bool = True, save_for_backward: bool = True,
+                      want_y: bool = True) -> AttnContext:
     """Forward of all blocks. Xh/Xf: packed slots [S*NP, 256] (16-bit / fp32)."""
     dev, dt = Xh.device, Xh.dtype
     NP, CP, NC = geom.rows_pad, geom.chunk_pad, geom.n_chunks
@@ -243,11 +245,12 @@ def attention_forward(Xh, Xf, groups, n_slots, n_blocks, w_q, w_k, w_v, w_o, gam
     L.gemm(L.mat(O, L.MAJOR_K), L.mat(ctx.Wo16, L.MAJOR_K), L.out(Z, 256), n_blocks * NP, 256, HD)
     ctx.res_block = cached_table(("res_block", tuple(groups), n_blocks), dev,
                                  lambda: _res_block_table(groups, n_blocks))
-    Y = torch.empty_like(Z)
+    Y = torch.empty_like(Z) if want_y else None   # CSA: consumers re-normalise z on the fly, Y never hits HBM
     ctx.mean = torch.empty(n_blocks * NP, dtype=torch.float32, device=dev)
     ctx.rstd = torch.empty_like(ctx.mean)
     parts = torch.empty(n_blocks * NP // 64, 256, dtype=torch.float32, device=dev) if want_colsum else None
-    rc = L.lib().csn_add_ln_fwd(Z.data_ptr(), Xf.data_ptr(), ctx.res_block.data_ptr(), Y.data_ptr(), None,
+    rc = L.lib().csn_add_ln_fwd(Z.data_ptr(), Xf.data_ptr(), ctx.res_block.data_ptr(),
+                                Y.data_ptr() if Y is not None else None, None,
                                 ctx.mean.data_ptr(), ctx.rstd.data_ptr(), gamma.data_ptr(), beta.data_ptr(),
                                 parts.data_ptr() if want_colsum else None, n_blocks * NP, NP, CP, geom.chunk,
                                 1e-6, L.dtype_code(dt), L.stream_ptr())
@@ -259,6 +262,7 @@ def attention_forward(Xh, Xf, groups, n_slots, n_blocks, w_q, w_k, w_v, w_o, gam
                                        1.0 / geom.n_points, L.stream_ptr())
         L.check(rc, "csn_colsum_reduce")
     ctx.Z, ctx.Y = Z, Y
+    ctx.beta = beta
     return ctx
 
 

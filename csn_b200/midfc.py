@@ -77,7 +77,7 @@ def _rows_to_channel_major(rows: torch.Tensor, n_b: int, n_src_points: int, geom
     w = E.cached_table(("ones", n_b), dev, lambda: torch.ones(n_b, dtype=torch.float32))
     rc = L.lib().csn_combine_fwd(rows.data_ptr(), blk.data_ptr(), w.data_ptr(), out.data_ptr(), None, n_b, 1,
                                  256 * n_src_points, n_src_points, geom.n_points, geom.chunk, geom.chunk_pad,
-                                 geom.rows_pad, L.CSN_F16, L.stream_ptr())
+                                 geom.rows_pad, L.CSN_F16, None, None, None, None, L.stream_ptr())
     L.check(rc, "csn_combine_fwd")
     return out
 
@@ -264,7 +264,7 @@ class _CsaFn(torch.autograd.Function):
                                   v0=1, v_si=1, v_so=K + 1))
             nblk += B * K
         a = E.attention_forward(Xh, Xf, groups, S, nblk, wq, wk, wv, wo, gamma, beta, geom, n_head,
-                                want_colsum=not ssa_only)
+                                want_colsum=not ssa_only, want_y=False)
         # ---- compatibility (csa_models.py:211-230): tiny (B*(K+1) x 256) glue, kept in torch
         if ssa_only:
             comp = torch.ones(B, 1, dtype=torch.float32, device=dev)
@@ -294,9 +294,11 @@ class _CsaFn(torch.autograd.Function):
         alloc = torch.zeros if n_src > geom.n_points else torch.empty
         out = alloc(B, 256, geom.n_points, 1, dtype=torch.float32, device=dev)
         compc = comp.contiguous()
-        rc = L.lib().csn_combine_fwd(a.Y.data_ptr(), blk.data_ptr(), compc.data_ptr(), out.data_ptr(), None, B, K + 1,
+        # the LayerNorm output is formed on the fly from z, mean, rstd (it is never written to HBM)
+        rc = L.lib().csn_combine_fwd(a.Z.data_ptr(), blk.data_ptr(), compc.data_ptr(), out.data_ptr(), None, B, K + 1,
                                      256 * geom.n_points, geom.n_points, geom.n_points, geom.chunk, geom.chunk_pad,
-                                     geom.rows_pad, L.dtype_code(dt), L.stream_ptr())
+                                     geom.rows_pad, L.dtype_code(dt), a.mean.data_ptr(), a.rstd.data_ptr(),
+                                     gamma.data_ptr(), beta.data_ptr(), L.stream_ptr())
         L.check(rc, "csn_combine_fwd")
         ctx.a, ctx.glue, ctx.comp, ctx.blk = a, glue, compc, blk
         ctx.meta = (B, K, S, nblk, n_src, n_src_nb)
@@ -340,13 +342,6 @@ class _CsaFn(torch.autograd.Function):
         obs, ocs = 256 * geom.n_points, geom.n_points
         grads_glue = [None] * 4
         dpool = None
-        # dcomp = <dOut^T, Y> per block of the weighted sum (one pass over dOut and Y)
-        dcomp = torch.zeros(B * (K + 1), dtype=torch.float32, device=dev) if has_glue else None
-        if has_glue:
-            rc = lib.csn_combine_bwd(dout.data_ptr(), a.Y.data_ptr(), None, cb.data_ptr(), cw.data_ptr(), cwi.data_ptr(),
-                                     nopool.data_ptr(), 0.0, None, dcomp.data_ptr(), nblk, obs, ocs, geom.n_points,
-                                     geom.chunk, geom.chunk_pad, geom.rows_pad, None, L.stream_ptr())
-            L.check(rc, "csn_combine_bwd")
         # The upstream gradient of block j is comp[b,k] * dOut[b]^T (+ the pooled-mean row vector): dOut is
         # transposed ONCE per batch item into padded rows (it stays L2-resident) and csn_ln_bwd forms
         # cw[j] * dOutT[cb[j]] + dpool[pb[j]]/N on the fly; the (2K+1)x larger dY is never materialised.
@@ -356,6 +351,13 @@ class _CsaFn(torch.autograd.Function):
                                geom.n_points, geom.chunk, geom.chunk_pad, geom.rows_pad, L.CSN_F16, amax.data_ptr(),
                                L.stream_ptr())
         L.check(rc, "csn_pack_rows(dOut)")
+        # d comp[b,k] = <dOut[b]^T, MHA_k> with the LayerNorm output re-formed from z on the fly
+        dcomp = torch.zeros(B * (K + 1), dtype=torch.float32, device=dev) if has_glue else None
+        if has_glue:
+            rc = lib.csn_block_dot(dOutT.data_ptr(), a.Z.data_ptr(), cb.data_ptr(), cwi.data_ptr(), dcomp.data_ptr(),
+                                   nblk * geom.rows_pad, geom.rows_pad, geom.chunk_pad, geom.chunk, a.mean.data_ptr(),
+                                   a.rstd.data_ptr(), a.gamma.data_ptr(), a.beta.data_ptr(), L.stream_ptr())
+            L.check(rc, "csn_block_dot")
         if has_glue:
             pooled, loc, comp_g = ctx.glue
             gl = torch.autograd.grad(comp_g, [pooled] + loc, dcomp.view(B, K + 1))

@@ -213,11 +213,21 @@ int csn_ln_bwd(const float* dY, const float* Z, const float* mean, const float* 
 /* out[b][c][n] = sum_k w[b*n_k+k] * Y[blk[b*n_k+k]][padrow(n)][c]: the compatibility-weighted sum
  * of the self- and cross-attention outputs written back channel-major (csa_models.py:232-240);
  * rows16 (optional) receives a 16-bit row-major copy. With n_k = 1, w = 1 it is the plain
- * row-major -> channel-major transpose of csa_models.py:206. */
+ * row-major -> channel-major transpose of csa_models.py:206.  When ln_mean != NULL, `Y` holds the
+ * PRE-LayerNorm rows z and y = (z - mean)*rstd*gamma + beta is formed on the fly (the LayerNorm output is
+ * then never written to HBM). */
 int csn_combine_fwd(const float* Y, const int32_t* blk, const float* w, float* out, void* rows16,
                     int32_t n_b, int32_t n_k, int64_t out_b_stride, int64_t out_ch_stride,
                     int32_t n_points, int32_t chunk, int32_t chunk_pad, int32_t rows_pad, int32_t dtype,
+                    const float* ln_mean, const float* ln_rstd, const float* ln_gamma, const float* ln_beta,
                     void* stream);
+/* out[out_idx[j]] += sum over the valid rows r of block j of <G[src_idx[j]][r], y_j[r]> (y_j = Z rows of
+ * block j, re-normalised on the fly when ln_mean != NULL): the gradient of the compatibility weights,
+ * d comp[b,k] = <dOut[b]^T, MHA(x, x_k)> (autograd of csa_models.py:233,238), from the transposed output
+ * gradient G. */
+int csn_block_dot(const float* G, const float* Z, const int32_t* src_idx, const int32_t* out_idx, float* out,
+                  int64_t rows, int32_t block_rows, int32_t group_rows, int32_t rows_valid, const float* ln_mean,
+                  const float* ln_rstd, const float* ln_gamma, const float* ln_beta, void* stream);
 /* Backward of the above plus of the pooled means.  For block j:
  *   dY[j] = cw[j]*dOut[cb[j]]^T (if cb[j] >= 0) + pool_scale*dpool[pb[j]] (if pb[j] >= 0), valid rows;
  *   dcomp[cw_index[j]] += <dOut[cb[j]]^T, Y[j]>  (if cw_index[j] >= 0).
@@ -227,7 +237,8 @@ int csn_combine_bwd(const float* dOut, const float* Y, const float* dpool, const
                     const float* cw, const int32_t* cw_index, const int32_t* pb, float pool_scale,
                     float* dY, float* dcomp, int32_t n_blocks, int64_t out_b_stride,
                     int64_t out_ch_stride, int32_t n_points, int32_t chunk, int32_t chunk_pad,
-                    int32_t rows_pad, float* amax, void* stream);
+                    int32_t rows_pad, float* amax, const float* ln_mean, const float* ln_rstd,
+                    const float* ln_gamma, const float* ln_beta, void* stream);
 
 #ifdef __cplusplus
 }
