@@ -13,6 +13,8 @@
 //
 // Operands may be K-major (rows of k) or MN-major (rows of mn, i.e. a transposed operand consumed
 // in place): the difference is confined to the TMA box shape and the UMMA descriptor strides.
+#include <stdlib.h>
+
 #include "host_util.h"
 #include "ptx.cuh"
 
@@ -138,7 +140,7 @@ __device__ __forceinline__ void store_chunk(const GemmArgs& p, long long base, i
   }
 }
 
-template <int BN, bool A_MN, bool B_MN>
+template <int BN, bool A_MN, bool B_MN, int CL>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
             const __grid_constant__ CUtensorMap tmD, const __grid_constant__ GemmArgs p) {
@@ -166,7 +168,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < Cfg::STAGES; ++s) {
       mbar_init(full_bar(s), 1);
-      mbar_init(empty_bar(s), 1);
+      mbar_init(empty_bar(s), CL);   // CL == 2: the B half-tiles are multicast, both CTAs must have drained the stage
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
@@ -179,17 +181,23 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     tmem_relinquish();
   }
   tc_fence_before();
-  __syncthreads();
+  if (CL > 1) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  // CL == 2: the two CTAs of a cluster own m-tiles 2i and 2i+1 of the same (batch, n-tile, k-split); each loads
+  // half of every B stage and multicasts it to both, so B crosses L2 -> SM once per pair instead of once per tile.
+  const int rank = (CL > 1) ? (int)cluster_ctarank() : 0;
+  const long long t_first = (long long)blockIdx.x / CL, t_stride = (long long)gridDim.x / CL;
+  constexpr uint16_t MC_MASK = (1u << CL) - 1;
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
     if (elect_one()) {
       int st = 0;
       uint32_t ph = 0;
-      for (long long t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
-        const TileCoord c = decode_tile(t, p);
+      for (long long t = t_first; t < p.total_tiles; t += t_stride) {
+        TileCoord c = decode_tile(t, p);
+        c.mt = c.mt * CL + rank;
         const long long a_mn = c.b0 * p.a_mn_off[0] + c.b1 * p.a_mn_off[1] + c.b2 * p.a_mn_off[2] + c.b3 * p.a_mn_off[3] + (long long)c.mt * GEMM_BM;
         const long long b_mn = c.b0 * p.b_mn_off[0] + c.b1 * p.b_mn_off[1] + c.b2 * p.b_mn_off[2] + c.b3 * p.b_mn_off[3] + (long long)c.nt * BN;
         const long long a_k0 = c.b0 * p.a_k_off[0] + c.b1 * p.a_k_off[1] + c.b2 * p.a_k_off[2] + c.b3 * p.a_k_off[3];
@@ -210,12 +218,22 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             for (int at = 0; at < GEMM_BM / 64; ++at)
               tma_load_2d(sA + at * 8192, &tmA, full_bar(st), (int)a_mn + at * 64, ka);
           }
-          if (!B_MN) {
-            tma_load_2d(sB, &tmB, full_bar(st), kbb, (int)b_mn);
-          } else {
+          if (CL == 1) {
+            if (!B_MN) {
+              tma_load_2d(sB, &tmB, full_bar(st), kbb, (int)b_mn);
+            } else {
 #pragma unroll
-            for (int at = 0; at < BN / 64; ++at)
-              tma_load_2d(sB + at * 8192, &tmB, full_bar(st), (int)b_mn + at * 64, kbb);
+              for (int at = 0; at < BN / 64; ++at)
+                tma_load_2d(sB + at * 8192, &tmB, full_bar(st), (int)b_mn + at * 64, kbb);
+            }
+          } else {
+            if (!B_MN) {   // this CTA's half of the BN rows (box = BN/2 rows), delivered to both CTAs
+              tma_load_2d_mc(sB + rank * (BN / 2) * 128, &tmB, full_bar(st), kbb, (int)b_mn + rank * (BN / 2), MC_MASK);
+            } else {
+#pragma unroll
+              for (int at = 0; at < BN / 64; ++at)
+                if ((at % CL) == rank) tma_load_2d_mc(sB + at * 8192, &tmB, full_bar(st), (int)b_mn + at * 64, kbb, MC_MASK);
+            }
           }
           if (++st == Cfg::STAGES) { st = 0; ph ^= 1; }
         }
@@ -228,7 +246,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       uint32_t ph = 0;
       int acc = 0;
       uint32_t acc_ph = 0;
-      for (long long t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+      for (long long t = t_first; t < p.total_tiles; t += t_stride) {
         const TileCoord c = decode_tile(t, p);
         const int kb0 = c.ks * p.kb_per_split;
         const int kb1 = min(p.kb_total, kb0 + p.kb_per_split);
@@ -250,7 +268,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                                      : umma_desc_sw128(sB + k * 32, 0, 1024);
             umma_f16_ss(d_tmem, ad, bd, p.idesc, (kb > kb0 || k > 0) ? 1u : 0u);
           }
-          umma_commit(empty_bar(st));  // stage reusable once these MMAs have read it
+          if (CL == 1) umma_commit(empty_bar(st)); else umma_commit_mc(empty_bar(st), MC_MASK);  // stage reusable once these MMAs have read it
           if (++st == Cfg::STAGES) { st = 0; ph ^= 1; }
         }
         umma_commit(tfull_bar(acc));  // accumulator complete
@@ -263,8 +281,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     int acc = 0;
     uint32_t acc_ph = 0;
     int stg_flip = 0;
-    for (long long t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
-      const TileCoord c = decode_tile(t, p);
+    for (long long t = t_first; t < p.total_tiles; t += t_stride) {
+      TileCoord c = decode_tile(t, p);
+      c.mt = c.mt * CL + rank;
       const int kb0 = c.ks * p.kb_per_split;
       const bool has_k = kb0 < p.kb_total;
       mbar_wait(tfull_bar(acc), acc_ph);
@@ -340,36 +359,50 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   }
 
   tc_fence_before();
-  __syncthreads();
+  if (CL > 1) cluster_sync_all(); else __syncthreads();
   if (warp == 2) {
     tc_fence_after();
     tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
   }
 }
 
-template <int BN, bool A_MN, bool B_MN>
+template <int BN, bool A_MN, bool B_MN, int CL>
 static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmD,
                        const GemmArgs& args, cudaStream_t stream) {
   using Cfg = GemmCfg<BN>;
-  auto kern = gemm_kernel<BN, A_MN, B_MN>;
+  auto kern = gemm_kernel<BN, A_MN, B_MN, CL>;
   static bool configured = false;
   if (!configured) {
     CSN_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     configured = true;
   }
-  long long grid = args.total_tiles < num_sms() ? args.total_tiles : num_sms();
-  kern<<<(unsigned)grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, tmD, args);
+  const long long workers = num_sms() / CL;
+  const long long grid = (args.total_tiles < workers ? args.total_tiles : workers) * CL;
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3(GEMM_THREADS);
+  cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CL;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  CSN_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmD, args));
   CSN_LAUNCH_OK("gemm_kernel");
   return 0;
 }
 
-template <int BN>
+template <int BN, int CL>
 static int dispatch_major(bool a_mn, bool b_mn, const CUtensorMap& tmA, const CUtensorMap& tmB,
                           const CUtensorMap& tmD, const GemmArgs& args, cudaStream_t stream) {
-  if (!a_mn && !b_mn) return launch_gemm<BN, false, false>(tmA, tmB, tmD, args, stream);
-  if (!a_mn && b_mn) return launch_gemm<BN, false, true>(tmA, tmB, tmD, args, stream);
-  if (a_mn && !b_mn) return launch_gemm<BN, true, false>(tmA, tmB, tmD, args, stream);
-  return launch_gemm<BN, true, true>(tmA, tmB, tmD, args, stream);
+  if (!a_mn && !b_mn) return launch_gemm<BN, false, false, CL>(tmA, tmB, tmD, args, stream);
+  if (!a_mn && b_mn) return launch_gemm<BN, false, true, CL>(tmA, tmB, tmD, args, stream);
+  if (a_mn && !b_mn) return launch_gemm<BN, true, false, CL>(tmA, tmB, tmD, args, stream);
+  return launch_gemm<BN, true, true, CL>(tmA, tmB, tmD, args, stream);
 }
 
 }  // namespace csn
@@ -390,6 +423,10 @@ extern "C" int csn_gemm(const csn_mat* A, const csn_mat* B, const csn_out* D, in
 
   const int BN = (N > 128) ? 256 : (N > 64 ? 128 : 64);
   const bool a_mn = A->major == CSN_MAJOR_MN, b_mn = B->major == CSN_MAJOR_MN;
+  const int tiles_m_all = (M + GEMM_BM - 1) / GEMM_BM;
+  static const bool cluster_ok = getenv("CSN_GEMM_CLUSTER") == nullptr || atoi(getenv("CSN_GEMM_CLUSTER")) != 0;
+  // pairs of m-tiles share their B tiles through a 2-CTA cluster with multicast loads
+  const int CL = (cluster_ok && BN >= 128 && tiles_m_all % 2 == 0) ? 2 : 1;
 
   CUtensorMap tmA, tmB;
   int rc;
@@ -397,14 +434,14 @@ extern "C" int csn_gemm(const csn_mat* A, const csn_mat* B, const csn_out* D, in
             : make_tmap_2d(&tmA, A->ptr, A->dtype, A->inner, A->outer, A->ld, 64, GEMM_BM);
   if (rc) return rc;
   rc = b_mn ? make_tmap_2d(&tmB, B->ptr, B->dtype, B->inner, B->outer, B->ld, 64, 64)
-            : make_tmap_2d(&tmB, B->ptr, B->dtype, B->inner, B->outer, B->ld, 64, (uint32_t)BN);
+            : make_tmap_2d(&tmB, B->ptr, B->dtype, B->inner, B->outer, B->ld, 64, (uint32_t)(BN / CL));
   if (rc) return rc;
 
   GemmArgs g;
   memset(&g, 0, sizeof(g));
   g.M = M; g.N = N; g.K = K;
   g.nb0 = nb[0]; g.nb1 = nb[1]; g.nb2 = nb[2]; g.nb3 = nb[3];
-  g.tiles_m = (M + GEMM_BM - 1) / GEMM_BM;
+  g.tiles_m = tiles_m_all / CL;   // decode space: m-tile PAIRS when CL == 2
   g.tiles_n = (N + BN - 1) / BN;
   g.kb_total = (K + GEMM_BK - 1) / GEMM_BK;
   g.split_k = split_k > g.kb_total ? g.kb_total : split_k;
@@ -451,7 +488,11 @@ extern "C" int csn_gemm(const csn_mat* A, const csn_mat* B, const csn_out* D, in
     }
   }
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-  if (BN == 256) return dispatch_major<256>(a_mn, b_mn, tmA, tmB, tmD, g, s);
-  if (BN == 128) return dispatch_major<128>(a_mn, b_mn, tmA, tmB, tmD, g, s);
-  return dispatch_major<64>(a_mn, b_mn, tmA, tmB, tmD, g, s);
+  if (CL == 2) {
+    if (BN == 256) return dispatch_major<256, 2>(a_mn, b_mn, tmA, tmB, tmD, g, s);
+    return dispatch_major<128, 2>(a_mn, b_mn, tmA, tmB, tmD, g, s);
+  }
+  if (BN == 256) return dispatch_major<256, 1>(a_mn, b_mn, tmA, tmB, tmD, g, s);
+  if (BN == 128) return dispatch_major<128, 1>(a_mn, b_mn, tmA, tmB, tmD, g, s);
+  return dispatch_major<64, 1>(a_mn, b_mn, tmA, tmB, tmD, g, s);
 }

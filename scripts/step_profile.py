@@ -29,7 +29,7 @@ evs = sorted([e for e in prof.events() if e.device_type.name == "CUDA"], key=lam
 per = len(evs) // n
 print("--- kernels of the last step in launch order (>= 20 us)")
 for e in evs[-per:]:
-    if e.device_time >= 20:
+    if e.device_time >= 2:
         print(f"{e.device_time:9.1f} us  {e.name[:90]}")
 tot = collections.OrderedDict()
 for e in prof.events():
