@@ -229,6 +229,27 @@ def run_ours(args) -> None:
     step_flops = 3.0 * CSA_B * csa_flops_per_query(CSA_K, h)
     achieved = step_flops / (ms_step * 1e-3) / 1e12
 
+    # ------------------------------------------------------------------ per-kernel breakdown (outside the timed region)
+    # one extra step with CUDA events around every C-ABI launch on the launching stream
+    L.profile_begin()
+    train_step(*batches[0])
+    prof = L.profile_end()
+    n_blocks = CSA_B * (2 * CSA_K + 1)
+    attn_unit = 4.0 * N_POINTS * 500 * 256 * h * n_blocks          # Q K^T + P V of every block (algorithmic, 500-key chunks)
+    for name, mult in (("csn_attn_fwd", 1.0), ("csn_attn_bwd_dv", 1.0), ("csn_attn_bwd_dq", 1.0)):
+        if name in prof:
+            prof[name]["flops"] = attn_unit * mult                 # dV: S + P^T dO ; dS kernel: S + dP
+    kernels = {}
+    for name, d in sorted(prof.items(), key=lambda kv: -kv[1]["ms"]):
+        e = {"ms": round(d["ms"], 4), "launches": d["launches"]}
+        if d["flops"] > 0:
+            e["tflops"] = round(d["flops"] / (d["ms"] * 1e-3) / 1e12, 1)
+            e["frac_of_sustained_peak"] = round(e["tflops"] / pk["tflops_sustained"], 3)
+        kernels[name] = e
+    dom = max(prof.items(), key=lambda kv: kv[1]["ms"])
+    dom_name, dom_d = dom
+    dom_tflops = dom_d["flops"] / (dom_d["ms"] * 1e-3) / 1e12 if dom_d["flops"] > 0 else None
+
     # ------------------------------------------------------------------ e2e: host buffers through the module API
     hx = [torch.empty(CSA_B, D, N_POINTS, 1).pin_memory() for _ in range(2)]
     hn = [torch.empty(CSA_B, CSA_K + 1, D, N_POINTS, 1).pin_memory() for _ in range(2)]
@@ -390,9 +411,14 @@ def run_ours(args) -> None:
             "clocks": clocks, "gpu_launches": int(launches),
             "e2e": {"value": e2e_value, "unit": "shape-pairs/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 4,
                     "steps": e2e_steps},
-            "roofline": {"bound": "tensor", "kernel": "whole step (gemm_kernel launches dominate)", "achieved": achieved,
-                         "peak": pk["tflops_sustained"], "unit": "TFLOP/s", "frac": achieved / pk["tflops_sustained"],
-                         "traffic": None, "algorithmic_flops_per_step": step_flops, "peak_source": pk["source"] + ", sustained bf16"},
+            "roofline": {"bound": "tensor", "kernel": dom_name + " (largest share of the step, all its launches)",
+                         "achieved": dom_tflops, "peak": pk["tflops_sustained"], "unit": "TFLOP/s",
+                         "frac": (dom_tflops / pk["tflops_sustained"]) if dom_tflops else None, "traffic": None,
+                         "launches_per_step": dom_d["launches"], "ms_per_step": round(dom_d["ms"], 4),
+                         "peak_source": pk["source"] + ", sustained bf16",
+                         "whole_step": {"algorithmic_flops": step_flops, "achieved": achieved,
+                                        "frac": achieved / pk["tflops_sustained"]}},
+            "kernels": kernels,
             "cpu_baseline": cpu, "knn": knn_obj,
         }
         print(json.dumps(line), flush=True)

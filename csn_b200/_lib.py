@@ -62,6 +62,52 @@ def _declare(L: C.CDLL) -> None:
         fn = getattr(L, name)
         fn.restype = C.c_int
         fn.argtypes = sig
+    # every kernel-launching entry point goes through a thin wrapper that can time it with CUDA events on
+    # the launching stream (bench.py's per-kernel roofline); zero overhead beyond one attribute test otherwise
+    for name in list(_EXTRA_SIGNATURES) + ["csn_gemm"]:
+        setattr(L, name, _Timed(name, getattr(L, name)))
+
+
+class _Timed:
+    def __init__(self, name, fn):
+        self.name, self.fn = name, fn
+
+    def __call__(self, *args):
+        if _PROFILE is None:
+            return self.fn(*args)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        rc = self.fn(*args)
+        e1.record()
+        flops = 0.0
+        if self.name == "csn_gemm":   # (A, B, D, M, N, K, nb[4], alpha, split_k, stream)
+            nb = args[6]
+            flops = 2.0 * args[3] * args[4] * args[5] * nb[0] * nb[1] * nb[2] * nb[3]
+        _PROFILE.append((self.name, e0, e1, flops))
+        return rc
+
+
+_PROFILE = None
+
+
+def profile_begin() -> None:
+    """Start recording (name, start event, stop event, flops) for every C-ABI launch."""
+    global _PROFILE
+    _PROFILE = []
+
+
+def profile_end() -> dict:
+    """Stop recording; returns {entry point: {"ms": total, "launches": n, "flops": algorithmic flops if known}}."""
+    global _PROFILE
+    rec, _PROFILE = _PROFILE, None
+    torch.cuda.synchronize()
+    out: dict = {}
+    for name, e0, e1, fl in rec or []:
+        d = out.setdefault(name, {"ms": 0.0, "launches": 0, "flops": 0.0})
+        d["ms"] += e0.elapsed_time(e1)
+        d["launches"] += 1
+        d["flops"] += fl
+    return out
 
 
 # name -> argtypes for the remaining entry points (filled in by the sections below)

@@ -332,7 +332,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           fence_proxy_async_smem();
           __syncwarp();
           if (lane == 0 && rows_live) {
-            tma_store_2d(&tmD, buf, col0 + cc, row0);
+            if (p.accumulate) { if (has_k) tma_reduce_add_2d(&tmD, buf, col0 + cc, row0); }   // split-K partial: += in L2
+            else tma_store_2d(&tmD, buf, col0 + cc, row0);
             tma_store_commit();
           }
           stg_flip ^= 1;
@@ -469,7 +470,7 @@ extern "C" int csn_gemm(const csn_mat* A, const csn_mat* B, const csn_out* D, in
   {
     const int W = D->dtype == CSN_F32 ? 32 : 64;
     const long long nbt = (long long)nb[0] * nb[1] * nb[2] * nb[3];
-    bool ok = !D->accumulate && !D->transposed && vec && D->ld >= N;
+    bool ok = (!D->accumulate || D->dtype == CSN_F32) && !D->transposed && vec && D->ld >= N;
     ok = ok && (nbt == 1 || (M % GEMM_BM == 0 && N % W == 0));
     long long max_row = M, max_col = N;
     for (int i = 0; i < 4 && ok; ++i) {

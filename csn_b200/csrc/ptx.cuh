@@ -132,6 +132,12 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* tm, uint32_t src
                ::"l"(tm), "r"(src), "r"(c0), "r"(c1)
                : "memory");
 }
+// smem -> global tile reduction (element-wise += performed by the L2 on whole lines); element type from the map
+__device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* tm, uint32_t src, int c0, int c1) {
+  asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(tm), "r"(src), "r"(c0), "r"(c1)
+               : "memory");
+}
 __device__ __forceinline__ void tma_store_commit() {
   asm volatile("cp.async.bulk.commit_group;" ::: "memory");
 }

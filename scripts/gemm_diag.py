@@ -37,6 +37,15 @@ CASES = {
     "perf_n256": (37888, 256, 4096, "f16", 0, 0, {"perf": True}),
     "perf_n128": (37888, 128, 4096, "f16", 0, 0, {"perf": True}),
     "perf_n64": (37888, 64, 4096, "f16", 0, 0, {"perf": True}),
+    # shapes of the CSA training step (B=8, K=3): rows = 32 slots / 56 blocks x 10240
+    "perf_8k_mn": (8192, 8192, 8192, "f16", 1, 1, {"perf": True}),
+    "perf_qkv": (327680, 768, 256, "f16", 0, 0, {"perf": True, "out": "f16"}),
+    "perf_oproj": (573440, 256, 256, "f16", 0, 0, {"perf": True}),
+    "perf_do": (573440, 256, 256, "f16", 0, 1, {"perf": True, "out": "f16"}),
+    "perf_wgrad": (768, 256, 327680, "f16", 1, 1, {"perf": True, "split_k": 49}),
+    "perf_wgrad_kk": (768, 256, 327680, "f16", 0, 0, {"perf": True, "split_k": 49}),
+    "perf_dwo": (256, 256, 573440, "f16", 1, 1, {"perf": True, "split_k": 148}),
+    "perf_dwo_kk": (256, 256, 573440, "f16", 0, 0, {"perf": True, "split_k": 148}),
 }
 
 
