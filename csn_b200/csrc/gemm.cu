@@ -22,7 +22,7 @@ namespace csn {
 
 constexpr int GEMM_BM = 128;
 constexpr int GEMM_BK = 64;  // 64 x 16-bit = 128 B = one swizzle atom row
-constexpr int GEMM_THREADS = 256;
+constexpr int GEMM_THREADS = 384;   // warps 0-3: producer / MMA / TMEM alloc / idle, warps 4-11: epilogue
 
 struct GemmArgs {
   int M, N, K;
@@ -39,6 +39,10 @@ struct GemmArgs {
   // TMA-store epilogue (row-major, non-accumulating outputs): coordinates of a batch's origin
   int tma_store;
   int d_row_off[4], d_col_off[4];
+  int stages;     // smem ring depth actually used (<= Cfg::STAGES)
+  int stg_bufs;   // epilogue staging slabs per warp
+  int epi_warps;  // 4, or 8 for short-K problems where the epilogue is the critical path (two warps per TMEM lane quadrant, half the columns each)
+  int debug;   // CSN_GEMM_DEBUG (diagnostics only): 1 = epilogue drains TMEM but stores nothing
 };
 
 template <int BN>
@@ -57,20 +61,25 @@ struct TileCoord {
   int b0, b1, b2, b3, mt, nt, ks;
 };
 
-__device__ __forceinline__ TileCoord decode_tile(long long t, const GemmArgs& p) {
+// 32-bit arithmetic (the host rejects problems with >= 2^31 tiles); divisions by 1 are skipped, which is the
+// common case for the batch dims and split_k.
+__device__ __forceinline__ TileCoord decode_tile(long long t64, const GemmArgs& p) {
   TileCoord c;
-  c.ks = (int)(t % p.split_k);
-  t /= p.split_k;
-  c.nt = (int)(t % p.tiles_n);
-  t /= p.tiles_n;
-  c.mt = (int)(t % p.tiles_m);
-  t /= p.tiles_m;
-  c.b0 = (int)(t % p.nb0);
-  t /= p.nb0;
-  c.b1 = (int)(t % p.nb1);
-  t /= p.nb1;
-  c.b2 = (int)(t % p.nb2);
-  c.b3 = (int)(t / p.nb2);
+  uint32_t t = (uint32_t)t64;
+  auto step = [&](int n) -> int {
+    if (n == 1) return 0;
+    const uint32_t q = t / (uint32_t)n;
+    const int r = (int)(t - q * (uint32_t)n);
+    t = q;
+    return r;
+  };
+  c.ks = step(p.split_k);
+  c.nt = step(p.tiles_n);
+  c.mt = step(p.tiles_m);
+  c.b0 = step(p.nb0);
+  c.b1 = step(p.nb1);
+  c.b2 = step(p.nb2);
+  c.b3 = (int)t;
   return c;
 }
 
@@ -149,14 +158,17 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   // SWIZZLE_128B tiles need 1024-byte alignment.
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const uint32_t smem_base = smem_u32(smem);
-  const uint32_t stg_base = smem_base + Cfg::STAGES * Cfg::STAGE_BYTES;
-  const uint32_t bar_base = stg_base + Cfg::STG_BYTES;
+  // [ring: p.stages x STAGE_BYTES][staging: 4 warps x p.stg_bufs x 4 KB][barriers]; the host trades ring depth for
+  // staging depth (same total) when K is short and the TMA-store epilogue is the critical path
+  const int NST = p.stages;
+  const uint32_t stg_base = smem_base + NST * Cfg::STAGE_BYTES;
+  const uint32_t bar_base = stg_base + p.epi_warps * p.stg_bufs * 4096;
   // barrier layout: full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2], tmem_ptr
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
-  auto empty_bar = [&](int s) { return bar_base + 8u * (Cfg::STAGES + s); };
-  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * Cfg::STAGES + a); };
-  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * Cfg::STAGES + 2 + a); };
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES + Cfg::STG_BYTES + 8 * (2 * Cfg::STAGES + 4));
+  auto empty_bar = [&](int s) { return bar_base + 8u * (NST + s); };
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * NST + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * NST + 2 + a); };
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem + (bar_base - smem_base) + 8 * (2 * NST + 4));
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -166,13 +178,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     tma_prefetch_desc(&tmB);
   }
   if (warp == 1 && lane == 0) {
-    for (int s = 0; s < Cfg::STAGES; ++s) {
+    for (int s = 0; s < NST; ++s) {
       mbar_init(full_bar(s), 1);
       mbar_init(empty_bar(s), CL);   // CL == 2: the B half-tiles are multicast, both CTAs must have drained the stage
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
-      mbar_init(tempty_bar(a), 128);
+      mbar_init(tempty_bar(a), 32 * p.epi_warps);
     }
     fence_mbar_init();
   }
@@ -235,7 +247,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                 if ((at % CL) == rank) tma_load_2d_mc(sB + at * 8192, &tmB, full_bar(st), (int)b_mn + at * 64, kbb, MC_MASK);
             }
           }
-          if (++st == Cfg::STAGES) { st = 0; ph ^= 1; }
+          if (++st == NST) { st = 0; ph ^= 1; }
         }
       }
     }
@@ -269,15 +281,17 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             umma_f16_ss(d_tmem, ad, bd, p.idesc, (kb > kb0 || k > 0) ? 1u : 0u);
           }
           if (CL == 1) umma_commit(empty_bar(st)); else umma_commit_mc(empty_bar(st), MC_MASK);  // stage reusable once these MMAs have read it
-          if (++st == Cfg::STAGES) { st = 0; ph ^= 1; }
+          if (++st == NST) { st = 0; ph ^= 1; }
         }
         umma_commit(tfull_bar(acc));  // accumulator complete
         if (++acc == 2) { acc = 0; acc_ph ^= 1; }
       }
     }
-  } else if (warp >= 4) {
+  } else if (warp >= 4 && warp < 4 + p.epi_warps) {
     // ------------------------------------------------------------------ epilogue
-    const int q = warp & 3;  // TMEM lane quadrant this warp may access
+    const int q = warp & 3;            // TMEM lane quadrant this warp may access
+    const int half = (warp - 4) >> 2;  // with 8 epilogue warps: which half of the tile's columns
+    const int ew = warp - 4;
     int acc = 0;
     uint32_t acc_ph = 0;
     int stg_flip = 0;
@@ -292,51 +306,91 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       const int n0 = c.nt * BN;
       const long long base = c.b0 * p.d_off[0] + c.b1 * p.d_off[1] + c.b2 * p.d_off[2] + c.b3 * p.d_off[3];
       const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + acc * BN;
-      if (p.tma_store) {
+      if (p.debug & 1) {
+      } else if (p.tma_store) {
         // Coalesced path: each warp stages [32 rows x 128 B] slabs (128B-swizzled, conflict-free 16-byte
-        // writes) and hands them to the TMA store engine; two slabs per warp are in flight.
-        const int W = p.out_dtype == CSN_F32 ? 32 : 64;  // columns per 128-byte slab
+        // writes) and hands them to the TMA store engine. Work unit = one x32 TMEM load (32 fp32 columns):
+        // a whole slab for fp32 outputs, half a slab for 16-bit outputs. The load of unit u+1 is in flight
+        // while unit u is converted and staged (tcgen05.ld latency is several hundred cycles while the MMA
+        // pipe is writing the other accumulator).
+        const bool o32 = p.out_dtype == CSN_F32;
+        const int W = o32 ? 32 : 64;  // columns per 128-byte slab
         const int row0 = c.b0 * p.d_row_off[0] + c.b1 * p.d_row_off[1] + c.b2 * p.d_row_off[2] + c.b3 * p.d_row_off[3] + c.mt * GEMM_BM + q * 32;
         const int col0 = c.b0 * p.d_col_off[0] + c.b1 * p.d_col_off[1] + c.b2 * p.d_col_off[2] + c.b3 * p.d_col_off[3] + n0;
         const bool rows_live = c.mt * GEMM_BM + q * 32 < p.M;  // warp-uniform
-#pragma unroll 1
-        for (int cc = 0; cc < BN; cc += W) {
-          if (n0 + cc >= p.N) break;
-          const uint32_t buf = stg_base + (q * 2 + stg_flip) * 4096;
-          if (lane == 0) tma_store_wait_read<1>();
-          __syncwarp();
-          uint32_t w[32];
-          if (p.out_dtype == CSN_F32) {
-            uint32_t r[32];
-            tmem_ld_32x32(taddr + cc, r);
-            tmem_ld_wait();
+        // this warp's unit range [u0, u1): all live units, or one half of them (split on a slab boundary)
+        const int g = o32 ? 1 : 2;                                          // units per slab
+        const int n_slabs = min(BN / W, (p.N - n0 + W - 1) / W);
+        const int s_half = p.epi_warps == 8 ? (n_slabs + 1) / 2 : n_slabs;
+        const int u0 = half * s_half * g, u1 = min(n_slabs, (half + 1) * s_half) * g;
+        const float al = p.alpha;
+        uint32_t ra[32], rb[32];
+        auto emit = [&](const uint32_t (&r)[32], int u) {
+          if (p.debug & 8) { if (r[0] == 0x7fc12345u && r[31] == 0x7fc12345u) atomicAdd(reinterpret_cast<int*>(p.D), 1); return; }   // diagnostics: TMEM loads only
+          const uint32_t buf = stg_base + (ew * p.stg_bufs + stg_flip) * 4096;
+          const uint32_t rowaddr = buf + lane * 128;
+          const bool first = o32 || !(u & 1), last = o32 || (u & 1);
+          if (first) {   // the slab buffer must have been drained by the store issued stg_bufs slabs ago
+            if (lane == 0) { if (p.stg_bufs == 4) tma_store_wait_read<3>(); else tma_store_wait_read<1>(); }
+            __syncwarp();
+          }
+          if (o32) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) w[j] = __float_as_uint(has_k ? __uint_as_float(r[j]) * p.alpha : 0.f);
+            for (int ch = 0; ch < 8; ++ch) {
+              const uint32_t a = rowaddr + (((uint32_t)ch ^ ((uint32_t)lane & 7u)) << 4);
+              uint32_t w0 = 0, w1 = 0, w2 = 0, w3 = 0;
+              if (has_k) {
+                w0 = __float_as_uint(__uint_as_float(r[4 * ch]) * al); w1 = __float_as_uint(__uint_as_float(r[4 * ch + 1]) * al);
+                w2 = __float_as_uint(__uint_as_float(r[4 * ch + 2]) * al); w3 = __float_as_uint(__uint_as_float(r[4 * ch + 3]) * al);
+              }
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(w0), "r"(w1), "r"(w2), "r"(w3) : "memory");
+            }
           } else {
-            uint32_t r0[32], r1[32];
-            tmem_ld_32x32(taddr + cc, r0);
-            tmem_ld_32x32(taddr + cc + 32, r1);
-            tmem_ld_wait();
+            const bool f16 = p.out_dtype == CSN_F16;
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              w[j] = pack16(has_k ? __uint_as_float(r0[2 * j]) * p.alpha : 0.f, has_k ? __uint_as_float(r0[2 * j + 1]) * p.alpha : 0.f, p.out_dtype);
-              w[16 + j] = pack16(has_k ? __uint_as_float(r1[2 * j]) * p.alpha : 0.f, has_k ? __uint_as_float(r1[2 * j + 1]) * p.alpha : 0.f, p.out_dtype);
+            for (int ch = 0; ch < 4; ++ch) {
+              uint32_t w[4];
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const float x = has_k ? __uint_as_float(r[8 * ch + 2 * j]) * al : 0.f;
+                const float y = has_k ? __uint_as_float(r[8 * ch + 2 * j + 1]) * al : 0.f;
+                if (f16) { __half2 h = __floats2half2_rn(x, y); w[j] = *reinterpret_cast<uint32_t*>(&h); }
+                else { __nv_bfloat162 h = __floats2bfloat162_rn(x, y); w[j] = *reinterpret_cast<uint32_t*>(&h); }
+              }
+              const uint32_t a = rowaddr + (((uint32_t)(ch + 4 * (u & 1)) ^ ((uint32_t)lane & 7u)) << 4);
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]) : "memory");
             }
           }
-          const uint32_t rowaddr = buf + lane * 128;
+          if (last) {
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0 && rows_live && !(p.debug & 4)) {
+              const int sl = u / g;
+              if (p.accumulate) { if (has_k) tma_reduce_add_2d(&tmD, buf, col0 + sl * W, row0); }   // split-K partial: += in L2
+              else tma_store_2d(&tmD, buf, col0 + sl * W, row0);
+              tma_store_commit();
+            }
+            if (++stg_flip == p.stg_bufs) stg_flip = 0;
+          }
+        };
+        if (p.debug & 16) {   // diagnostics: staging + stores without touching TMEM
 #pragma unroll
-          for (int ch = 0; ch < 8; ++ch) {
-            const uint32_t a = rowaddr + (((uint32_t)ch ^ ((uint32_t)lane & 7u)) << 4);
-            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(w[4 * ch]), "r"(w[4 * ch + 1]), "r"(w[4 * ch + 2]), "r"(w[4 * ch + 3]) : "memory");
+          for (int j = 0; j < 32; ++j) ra[j] = 0x3c003c00u + j;
+#pragma unroll 1
+          for (int u = u0; u < u1; ++u) emit(ra, u);
+        } else {
+        if (u0 < u1) tmem_ld_32x32(taddr + u0 * 32, ra);
+#pragma unroll 1
+        for (int u = u0; u < u1; u += 2) {
+          tmem_ld_wait();
+          if (u + 1 < u1) tmem_ld_32x32(taddr + (u + 1) * 32, rb);
+          emit(ra, u);
+          if (u + 1 < u1) {
+            tmem_ld_wait();
+            if (u + 2 < u1) tmem_ld_32x32(taddr + (u + 2) * 32, ra);
+            emit(rb, u + 1);
           }
-          fence_proxy_async_smem();
-          __syncwarp();
-          if (lane == 0 && rows_live) {
-            if (p.accumulate) { if (has_k) tma_reduce_add_2d(&tmD, buf, col0 + cc, row0); }   // split-K partial: += in L2
-            else tma_store_2d(&tmD, buf, col0 + cc, row0);
-            tma_store_commit();
-          }
-          stg_flip ^= 1;
+        }
         }
       } else
 #pragma unroll 1
@@ -425,6 +479,7 @@ extern "C" int csn_gemm(const csn_mat* A, const csn_mat* B, const csn_out* D, in
   const int BN = (N > 128) ? 256 : (N > 64 ? 128 : 64);
   const bool a_mn = A->major == CSN_MAJOR_MN, b_mn = B->major == CSN_MAJOR_MN;
   const int tiles_m_all = (M + GEMM_BM - 1) / GEMM_BM;
+  static const int debug_flags = getenv("CSN_GEMM_DEBUG") ? atoi(getenv("CSN_GEMM_DEBUG")) : 0;
   static const bool cluster_ok = getenv("CSN_GEMM_CLUSTER") == nullptr || atoi(getenv("CSN_GEMM_CLUSTER")) != 0;
   // pairs of m-tiles share their B tiles through a 2-CTA cluster with multicast loads
   const int CL = (cluster_ok && BN >= 128 && tiles_m_all % 2 == 0) ? 2 : 1;
@@ -441,6 +496,7 @@ extern "C" int csn_gemm(const csn_mat* A, const csn_mat* B, const csn_out* D, in
   GemmArgs g;
   memset(&g, 0, sizeof(g));
   g.M = M; g.N = N; g.K = K;
+  g.debug = debug_flags;
   g.nb0 = nb[0]; g.nb1 = nb[1]; g.nb2 = nb[2]; g.nb3 = nb[3];
   g.tiles_m = tiles_m_all / CL;   // decode space: m-tile PAIRS when CL == 2
   g.tiles_n = (N + BN - 1) / BN;
@@ -449,6 +505,7 @@ extern "C" int csn_gemm(const csn_mat* A, const csn_mat* B, const csn_out* D, in
   g.kb_per_split = (g.kb_total + g.split_k - 1) / g.split_k;
   g.split_k = (g.kb_total + g.kb_per_split - 1) / g.kb_per_split;  // no empty splits
   g.total_tiles = (long long)g.nb0 * g.nb1 * g.nb2 * g.nb3 * g.tiles_m * g.tiles_n * g.split_k;
+  CSN_CHECK_ARG(g.total_tiles < (1ll << 31), "csn_gemm: too many tiles (%lld)", g.total_tiles);
   for (int i = 0; i < 4; ++i) {
     g.a_mn_off[i] = A->mn_off[i]; g.a_k_off[i] = A->k_off[i];
     g.b_mn_off[i] = B->mn_off[i]; g.b_k_off[i] = B->k_off[i];
@@ -487,6 +544,14 @@ extern "C" int csn_gemm(const csn_mat* A, const csn_mat* B, const csn_out* D, in
       if (rc) return rc;
       g.tma_store = 1;
     }
+  }
+  // smem split: deep ring for long K, deep epilogue staging (4 slabs in flight per warp) for short K
+  {
+    const int full = BN == 256 ? 4 : (BN == 128 ? 6 : 8), shallow = BN == 256 ? 3 : (BN == 128 ? 5 : 6);
+    const bool deep_staging = g.tma_store && g.kb_per_split <= 16;
+    g.stages = deep_staging ? shallow : full;
+    g.stg_bufs = 2;
+    g.epi_warps = deep_staging ? 8 : 4;
   }
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   if (CL == 2) {
