@@ -83,6 +83,8 @@ class _Timed:
         if self.name == "csn_gemm":   # (A, B, D, M, N, K, nb[4], alpha, split_k, stream)
             nb = args[6]
             flops = 2.0 * args[3] * args[4] * args[5] * nb[0] * nb[1] * nb[2] * nb[3]
+        elif self.name == "csn_gemm_res_ln":   # (A, B, Z, ldz, M, K, ...), N = 256
+            flops = 2.0 * args[4] * 256 * args[5]
         _PROFILE.append((self.name, e0, e1, flops))
         return rc
 
@@ -130,6 +132,11 @@ _EXTRA_SIGNATURES: dict[str, list] = {
                        C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_float,
                        C.c_int32, C.c_void_p],
     "csn_colsum_reduce": [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_float, C.c_void_p],
+    "csn_gemm_res_ln": [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_float, C.c_void_p,
+                        C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32,
+                        C.c_int32, C.c_int32, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p],
+    "csn_ln_colsum": [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32,
+                      C.c_int32, C.c_int32, C.c_void_p],
     "csn_ln_bwd": [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                    C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p,
                    C.c_void_p, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p],

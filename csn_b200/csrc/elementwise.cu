@@ -8,6 +8,7 @@
 // :211-219 (mean over points), :232-240 (weighted sum + transpose back).
 // Rows of every intermediate live in "padded" coordinates: chunk c of `chunk` (=500) points occupies
 // rows [c*chunk_pad, c*chunk_pad + chunk) of a shape's block (chunk_pad = 512); pad rows are zero.
+#include <cstdlib>
 #include "host_util.h"
 #include "ptx.cuh"
 
@@ -256,6 +257,44 @@ __global__ void __launch_bounds__(256) add_ln_fwd_kernel(const AddLnArgs p) {
   }
 }
 
+// Per-64-row partial column sums of y = (z - mean)*rstd*gamma + beta over the valid rows, for rows whose statistics
+// were already produced (csn_gemm_res_ln); the same partial layout as add_ln_fwd_kernel's colsum output.
+__global__ void __launch_bounds__(256) ln_colsum_kernel(const float* __restrict__ Z, const float* __restrict__ mean,
+                                                        const float* __restrict__ rstd, const float* __restrict__ gamma,
+                                                        const float* __restrict__ beta, float* __restrict__ colsum,
+                                                        int block_rows, int group_rows, int rows_valid) {
+  __shared__ float red[8][DM];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long row0 = (long long)blockIdx.x * 64;
+  const int rin0 = (int)(row0 % block_rows);
+  float4 sa = make_float4(0.f, 0.f, 0.f, 0.f), sc = sa;
+  float cnt = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const long long row = row0 + warp * 8 + i;
+    const int rin = rin0 + warp * 8 + i;
+    if ((rin % group_rows) >= rows_valid) continue;
+    const float4* z4 = reinterpret_cast<const float4*>(Z + row * DM);
+    const float4 a = __ldg(z4 + lane), c = __ldg(z4 + 32 + lane);
+    const float mu = __ldg(mean + row), rs = __ldg(rstd + row);
+    sa.x += (a.x - mu) * rs; sa.y += (a.y - mu) * rs; sa.z += (a.z - mu) * rs; sa.w += (a.w - mu) * rs;
+    sc.x += (c.x - mu) * rs; sc.y += (c.y - mu) * rs; sc.z += (c.z - mu) * rs; sc.w += (c.w - mu) * rs;
+    cnt += 1.f;
+  }
+  const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma) + lane), g1 = __ldg(reinterpret_cast<const float4*>(gamma) + 32 + lane);
+  const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta) + lane), b1 = __ldg(reinterpret_cast<const float4*>(beta) + 32 + lane);
+  red[warp][lane * 4 + 0] = sa.x * g0.x + cnt * b0.x; red[warp][lane * 4 + 1] = sa.y * g0.y + cnt * b0.y;
+  red[warp][lane * 4 + 2] = sa.z * g0.z + cnt * b0.z; red[warp][lane * 4 + 3] = sa.w * g0.w + cnt * b0.w;
+  red[warp][128 + lane * 4 + 0] = sc.x * g1.x + cnt * b1.x; red[warp][128 + lane * 4 + 1] = sc.y * g1.y + cnt * b1.y;
+  red[warp][128 + lane * 4 + 2] = sc.z * g1.z + cnt * b1.z; red[warp][128 + lane * 4 + 3] = sc.w * g1.w + cnt * b1.w;
+  __syncthreads();
+  const int c = threadIdx.x;
+  float s = 0.f;
+#pragma unroll
+  for (int w = 0; w < 8; ++w) s += red[w][c];
+  colsum[(long long)blockIdx.x * DM + c] = s;
+}
+
 // out[b][c] = scale * sum_{i < parts} part[(b*parts + i)][c], fixed order (deterministic pooled means)
 __global__ void colsum_reduce_kernel(const float* __restrict__ part, float* __restrict__ out, int parts, float scale) {
   const int b = blockIdx.x, c = threadIdx.x;
@@ -280,9 +319,11 @@ struct LnBwdArgs {
   float bcast_scale;
   // implicit upstream gradient: dY[block] = src_w[block] * dYsrc[src_idx[block]] (rows of one shape), or 0 if src_idx < 0
   const int* src_idx; const float* src_w;
+  int debug;
 };
 
-__global__ void __launch_bounds__(256, 4) ln_bwd_kernel(const LnBwdArgs p) {
+template <int MINB>
+__global__ void __launch_bounds__(256, MINB) ln_bwd_kernel(const LnBwdArgs p) {
   __shared__ float red[2][8][DM];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long row0 = (long long)blockIdx.x * 64;
@@ -295,48 +336,54 @@ __global__ void __launch_bounds__(256, 4) ln_bwd_kernel(const LnBwdArgs p) {
   const int src_i = p.src_idx ? __ldg(p.src_idx + blk) : -1;
   const float src_wgt = (p.src_idx && src_i >= 0) ? __ldg(p.src_w + blk) : 0.f;
   const int bc_i = p.bcast ? __ldg(p.bcast_idx + blk) : -1;
-  for (int i = 0; i < 8; ++i) {
+  const float gm[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+  float4 bca = make_float4(0.f, 0.f, 0.f, 0.f), bcc = bca;   // the block's broadcast row (pooled-mean gradient), pre-scaled
+  if (bc_i >= 0) {
+    const float4* b4 = reinterpret_cast<const float4*>(p.bcast + (long long)bc_i * DM);
+    bca = __ldg(b4 + lane); bcc = __ldg(b4 + 32 + lane);
+    bca.x *= p.bcast_scale; bca.y *= p.bcast_scale; bca.z *= p.bcast_scale; bca.w *= p.bcast_scale;
+    bcc.x *= p.bcast_scale; bcc.y *= p.bcast_scale; bcc.z *= p.bcast_scale; bcc.w *= p.bcast_scale;
+  }
+  struct RowIn { float4 da, dc, za, zc; float mu, rs; bool valid; };
+  // all global loads of a row are issued before anything is consumed; two rows are in flight per warp
+  auto load_row = [&](int i) -> RowIn {
+    RowIn r;
     const long long row = row0 + warp * 8 + i;
-    if (row >= p.rows) break;
     const int rin = rin0 + warp * 8 + i;
-    float4* dz4 = p.dZ ? reinterpret_cast<float4*>(p.dZ + row * DM) : nullptr;
-    uint2* dz16 = reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(p.dZ16) + row * DM);
-    const bool valid = (rin % p.group_rows) < p.rows_valid;
-    if (!valid) {
-      const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (dz4) { dz4[lane] = zero; dz4[32 + lane] = zero; }
-      dz16[lane] = make_uint2(0, 0); dz16[32 + lane] = make_uint2(0, 0);
-      continue;
-    }
+    r.valid = row < p.rows && (rin % p.group_rows) < p.rows_valid;
+    r.da = make_float4(0.f, 0.f, 0.f, 0.f); r.dc = r.da; r.za = r.da; r.zc = r.da; r.mu = 0.f; r.rs = 0.f;
+    if (!r.valid) return r;
     const float4* z4 = reinterpret_cast<const float4*>(p.Z + row * DM);
-    const float mu = p.mean[row], rs = p.rstd[row];
-    float4 da = make_float4(0.f, 0.f, 0.f, 0.f), dc = da;
     if (p.src_idx) {
       if (src_i >= 0) {
-        const float wgt = src_wgt;
         const float4* dy4 = reinterpret_cast<const float4*>(p.dY + ((long long)src_i * p.block_rows + rin) * DM);
-        da = __ldg(dy4 + lane); dc = __ldg(dy4 + 32 + lane);
-        da.x *= wgt; da.y *= wgt; da.z *= wgt; da.w *= wgt;
-        dc.x *= wgt; dc.y *= wgt; dc.z *= wgt; dc.w *= wgt;
+        r.da = __ldg(dy4 + lane); r.dc = __ldg(dy4 + 32 + lane);
       }
     } else {
       const float4* dy4 = reinterpret_cast<const float4*>(p.dY + row * DM);
-      da = __ldg(dy4 + lane); dc = __ldg(dy4 + 32 + lane);
+      r.da = __ldg(dy4 + lane); r.dc = __ldg(dy4 + 32 + lane);
     }
-    if (p.bcast) {
-      const int bi = bc_i;
-      if (bi >= 0) {
-        const float4* b4 = reinterpret_cast<const float4*>(p.bcast + (long long)bi * DM);
-        const float4 ba = __ldg(b4 + lane), bc = __ldg(b4 + 32 + lane);
-        da.x += ba.x * p.bcast_scale; da.y += ba.y * p.bcast_scale; da.z += ba.z * p.bcast_scale; da.w += ba.w * p.bcast_scale;
-        dc.x += bc.x * p.bcast_scale; dc.y += bc.y * p.bcast_scale; dc.z += bc.z * p.bcast_scale; dc.w += bc.w * p.bcast_scale;
-      }
+    r.za = __ldg(z4 + lane); r.zc = __ldg(z4 + 32 + lane);
+    r.mu = __ldg(p.mean + row); r.rs = __ldg(p.rstd + row);
+    return r;
+  };
+  auto finish_row = [&](const RowIn& r, int i) {
+    const long long row = row0 + warp * 8 + i;
+    if (row >= p.rows) return;
+    float4* dz4 = p.dZ ? reinterpret_cast<float4*>(p.dZ + row * DM) : nullptr;
+    uint2* dz16 = reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(p.dZ16) + row * DM);
+    if (!r.valid) {
+      const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (dz4) { dz4[lane] = zero; dz4[32 + lane] = zero; }
+      dz16[lane] = make_uint2(0, 0); dz16[32 + lane] = make_uint2(0, 0);
+      return;
     }
-    const float4 za = __ldg(z4 + lane), zc = __ldg(z4 + 32 + lane);
-    float xh[8] = {(za.x - mu) * rs, (za.y - mu) * rs, (za.z - mu) * rs, (za.w - mu) * rs,
-                   (zc.x - mu) * rs, (zc.y - mu) * rs, (zc.z - mu) * rs, (zc.w - mu) * rs};
-    float dy[8] = {da.x * gscale, da.y * gscale, da.z * gscale, da.w * gscale, dc.x * gscale, dc.y * gscale, dc.z * gscale, dc.w * gscale};
-    float gm[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+    const float wgt = p.src_idx ? src_wgt : 1.f;
+    const float mu = r.mu, rs = r.rs;
+    const float xh[8] = {(r.za.x - mu) * rs, (r.za.y - mu) * rs, (r.za.z - mu) * rs, (r.za.w - mu) * rs,
+                         (r.zc.x - mu) * rs, (r.zc.y - mu) * rs, (r.zc.z - mu) * rs, (r.zc.w - mu) * rs};
+    const float dy[8] = {(r.da.x * wgt + bca.x) * gscale, (r.da.y * wgt + bca.y) * gscale, (r.da.z * wgt + bca.z) * gscale, (r.da.w * wgt + bca.w) * gscale,
+                         (r.dc.x * wgt + bcc.x) * gscale, (r.dc.y * wgt + bcc.y) * gscale, (r.dc.z * wgt + bcc.z) * gscale, (r.dc.w * wgt + bcc.w) * gscale};
     float g[8];
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
@@ -358,6 +405,14 @@ __global__ void __launch_bounds__(256, 4) ln_bwd_kernel(const LnBwdArgs p) {
     }
     dz16[lane] = make_uint2(pack2(o[0], o[1], p.dtype), pack2(o[2], o[3], p.dtype));
     dz16[32 + lane] = make_uint2(pack2(o[4], o[5], p.dtype), pack2(o[6], o[7], p.dtype));
+  };
+  RowIn cur = load_row(0);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    RowIn nxt;
+    if (i + 1 < 8) nxt = load_row(i + 1);
+    finish_row(cur, i);
+    if (i + 1 < 8) cur = nxt;
   }
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
@@ -369,6 +424,7 @@ __global__ void __launch_bounds__(256, 4) ln_bwd_kernel(const LnBwdArgs p) {
   float s = 0.f, t = 0.f;
 #pragma unroll
   for (int w = 0; w < 8; ++w) { s += red[0][w][c]; t += red[1][w][c]; }
+  if (p.debug & 1) return;
   atomicAdd(p.dgamma + c, s);
   atomicAdd(p.dbeta + c, t);
 }
@@ -626,6 +682,18 @@ int csn_add_ln_fwd(float* Z, const float* R, const int32_t* res_block, float* Y,
   return launch_simple(add_ln_fwd_kernel, dim3((unsigned)(rows / 64)), dim3(256), a, stream, "add_ln_fwd_kernel");
 }
 
+int csn_ln_colsum(const float* Z, const float* mean, const float* rstd, const float* gamma, const float* beta,
+                  float* colsum, int64_t rows, int32_t block_rows, int32_t group_rows, int32_t rows_valid, void* stream) {
+  using namespace csn;
+  clear_error();
+  CSN_CHECK_ARG(Z && mean && rstd && gamma && beta && colsum, "csn_ln_colsum: null pointer");
+  CSN_CHECK_ARG(block_rows % 64 == 0 && rows % 64 == 0, "csn_ln_colsum: rows (%lld) and block_rows (%d) must be multiples of 64", (long long)rows, block_rows);
+  if (rows == 0) return 0;
+  ln_colsum_kernel<<<(unsigned)(rows / 64), 256, 0, (cudaStream_t)stream>>>(Z, mean, rstd, gamma, beta, colsum, block_rows, group_rows, rows_valid);
+  CSN_LAUNCH_OK("ln_colsum_kernel");
+  return 0;
+}
+
 int csn_colsum_reduce(const float* part, float* out, int32_t n_blocks, int32_t parts, float scale, void* stream) {
   using namespace csn;
   clear_error();
@@ -647,8 +715,11 @@ int csn_ln_bwd(const float* dY, const float* Z, const float* mean, const float* 
   CSN_CHECK_ARG(!src_idx || src_w, "csn_ln_bwd: src_idx needs src_w");
   CSN_CHECK_ARG(rows % 64 == 0 && block_rows % 64 == 0, "csn_ln_bwd: rows and block_rows must be multiples of 64");
   if (rows == 0) return 0;
-  LnBwdArgs a{dY, Z, mean, rstd, gamma, dZ, dZ16, dgamma, dbeta, rows, group_rows, rows_valid, block_rows, dtype, amax, bcast, bcast_idx, bcast_scale, src_idx, src_w};
-  return launch_simple(ln_bwd_kernel, dim3((unsigned)(rows / 64)), dim3(256), a, stream, "ln_bwd_kernel");
+  LnBwdArgs a{dY, Z, mean, rstd, gamma, dZ, dZ16, dgamma, dbeta, rows, group_rows, rows_valid, block_rows, dtype, amax, bcast, bcast_idx, bcast_scale, src_idx, src_w, getenv("CSN_LN_BWD_DEBUG") ? atoi(getenv("CSN_LN_BWD_DEBUG")) : 0};
+  static const int occ = getenv("CSN_LN_BWD_OCC") ? atoi(getenv("CSN_LN_BWD_OCC")) : 3;   // resident CTAs/SM (tuning knob)
+  if (occ >= 4) return launch_simple(ln_bwd_kernel<4>, dim3((unsigned)(rows / 64)), dim3(256), a, stream, "ln_bwd_kernel");
+  if (occ >= 3) return launch_simple(ln_bwd_kernel<3>, dim3((unsigned)(rows / 64)), dim3(256), a, stream, "ln_bwd_kernel");
+  return launch_simple(ln_bwd_kernel<2>, dim3((unsigned)(rows / 64)), dim3(256), a, stream, "ln_bwd_kernel");
 }
 
 int csn_combine_fwd(const float* Y, const int32_t* blk, const float* w, float* out, void* rows16, int32_t n_b,

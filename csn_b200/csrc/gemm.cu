@@ -41,7 +41,16 @@ struct GemmArgs {
   int d_row_off[4], d_col_off[4];
   int stages;     // smem ring depth actually used (<= Cfg::STAGES)
   int stg_bufs;   // epilogue staging slabs per warp
+  int tempty_count;  // arrivals that free an accumulator buffer
+  int alt_tiles;     // LN epilogue with 8 warps: warps 4-7 drain accumulator 0 (even tiles), warps 8-11 accumulator 1 (odd tiles)
   int epi_warps;  // 4, or 8 for short-K problems where the epilogue is the critical path (two warps per TMEM lane quadrant, half the columns each)
+  // fused residual + LayerNorm-statistics epilogue (csn_gemm_res_ln): z = alpha*acc + residual, Z = z, mean/rstd per row
+  int ln;
+  const int* res_sel;         // per block: which of the two channel-major residual tensors (tensor maps tmR0 / tmR1)
+  const int* res_row;         // per block: first channel row of the block's [256][n_points] matrix in that tensor's 2-D view
+  int block_rows, group_rows, rows_valid, n_points;
+  float eps;
+  float* mean; float* rstd;
   int debug;   // CSN_GEMM_DEBUG (diagnostics only): 1 = epilogue drains TMEM but stores nothing
 };
 
@@ -149,10 +158,11 @@ __device__ __forceinline__ void store_chunk(const GemmArgs& p, long long base, i
   }
 }
 
-template <int BN, bool A_MN, bool B_MN, int CL>
+template <int BN, bool A_MN, bool B_MN, int CL, bool LN = false>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-            const __grid_constant__ CUtensorMap tmD, const __grid_constant__ GemmArgs p) {
+            const __grid_constant__ CUtensorMap tmD, const __grid_constant__ CUtensorMap tmR0,
+            const __grid_constant__ CUtensorMap tmR1, const __grid_constant__ GemmArgs p) {
   using Cfg = GemmCfg<BN>;
   extern __shared__ uint8_t smem_raw[];
   // SWIZZLE_128B tiles need 1024-byte alignment.
@@ -184,8 +194,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
-      mbar_init(tempty_bar(a), 32 * p.epi_warps);
+      mbar_init(tempty_bar(a), p.tempty_count);
     }
+    if (LN) for (int i = 0; i < 16; ++i) mbar_init(bar_base + 256 + 8u * i, 1);   // residual slabs: (up to) 8 warps x 2
     fence_mbar_init();
   }
   if (warp == 2) {
@@ -292,10 +303,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     const int q = warp & 3;            // TMEM lane quadrant this warp may access
     const int half = (warp - 4) >> 2;  // with 8 epilogue warps: which half of the tile's columns
     const int ew = warp - 4;
-    int acc = 0;
-    uint32_t acc_ph = 0;
     int stg_flip = 0;
-    for (long long t = t_first; t < p.total_tiles; t += t_stride) {
+    uint32_t res_ph = 0;   // LN epilogue: phase bits of the two residual-slab barriers
+    int it = 0;            // tiles seen so far: tile `it` lives in accumulator it & 1, use (it >> 1) of that buffer
+    for (long long t = t_first; t < p.total_tiles; t += t_stride, ++it) {
+      if (LN && p.alt_tiles && (it & 1) != half) continue;   // the other warp set drains this accumulator
+      const int acc = it & 1;
+      const uint32_t acc_ph = (uint32_t)(it >> 1) & 1u;
       TileCoord c = decode_tile(t, p);
       c.mt = c.mt * CL + rank;
       const int kb0 = c.ks * p.kb_per_split;
@@ -307,6 +321,90 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       const long long base = c.b0 * p.d_off[0] + c.b1 * p.d_off[1] + c.b2 * p.d_off[2] + c.b3 * p.d_off[3];
       const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + acc * BN;
       if (p.debug & 1) {
+      } else if (LN) {
+        // Fused residual + LayerNorm statistics (BN == N == 256: the thread owns its whole output row).
+        // z = alpha*acc + residual.  The residual comes from the reference's channel-major fp32 tensors: a
+        // [32 channels x 32 points] TMA box per 32-column unit lands in a warp-private slab two units ahead of
+        // its use (for a fixed channel the 32 lanes read 32 consecutive floats: conflict-free).  Z leaves through
+        // the slab/TMA-store path; the row's mean and 1/std come from per-unit (mean, M2) pairs merged with
+        // Chan's formula.  Per warp: slabs 0,1 = output staging, slabs 2,3 = residual.
+        const int row0 = c.mt * GEMM_BM + q * 32;
+        const int last_blk = (p.M - 1) / p.block_rows;
+        const int blk0 = min(row0 / p.block_rows, last_blk), rin0 = row0 - blk0 * p.block_rows;   // 32 | block_rows
+        const int grp = rin0 / p.group_rows, j0 = rin0 - grp * p.group_rows;
+        const int pt0 = grp * p.rows_valid + j0;
+        const bool valid = row < p.M && (j0 + lane) < p.rows_valid && (pt0 + lane) < p.n_points;
+        const int sel = __ldg(p.res_sel + blk0), rrow = __ldg(p.res_row + blk0);
+        const CUtensorMap* tmR = sel ? &tmR1 : &tmR0;
+        const uint32_t wbuf = stg_base + ew * 4 * 4096;
+        const uint32_t rbar0 = bar_base + 256 + 8u * (ew * 2);
+        const float al = p.alpha;
+        auto fetch_res = [&](int u) {   // lane 0 only
+          const uint32_t bar = rbar0 + 8u * (u & 1);
+          mbar_arrive_expect_tx(bar, 4096);
+          tma_load_2d(wbuf + (2 + (u & 1)) * 4096, tmR, bar, pt0, rrow + u * 32);
+        };
+        if (lane == 0) { fetch_res(0); fetch_res(1); }
+        float mu = 0.f, m2 = 0.f;
+        uint32_t ra[32], rb[32];
+        auto emit = [&](uint32_t (&r)[32], int u) {
+          // residual slab of this unit
+          mbar_wait(rbar0 + 8u * (u & 1), (res_ph >> (u & 1)) & 1u);
+          res_ph ^= 1u << (u & 1);
+          const uint32_t rs = wbuf + (2 + (u & 1)) * 4096 + (lane & 3) * 4;
+          float z[32];
+          float su = 0.f;
+#pragma unroll
+          for (int jj = 0; jj < 32; ++jj) {
+            float rv;
+            asm volatile("ld.shared.f32 %0, [%1];" : "=f"(rv) : "r"(rs + jj * 128 + ((((uint32_t)lane >> 2) ^ ((uint32_t)jj & 7u)) << 4)));
+            z[jj] = valid ? __uint_as_float(r[jj]) * al + rv : 0.f;
+            su += z[jj];
+          }
+          __syncwarp();
+          if (lane == 0 && u + 2 < BN / 32) fetch_res(u + 2);   // the slab is free again: prefetch two units ahead
+          const float mu_u = su * (1.f / 32.f);
+          float q2 = 0.f;
+#pragma unroll
+          for (int jj = 0; jj < 32; ++jj) { const float dlt = z[jj] - mu_u; q2 += dlt * dlt; }
+          {   // Chan merge of (32u, mu, m2) with (32, mu_u, q2)
+            const float w = 1.f / (float)(u + 1), dlt = mu_u - mu;
+            mu += dlt * w;
+            m2 += q2 + dlt * dlt * (32.f * (float)u * w);
+          }
+          const uint32_t buf = wbuf + stg_flip * 4096;
+          const uint32_t rowaddr = buf + lane * 128;
+          if (lane == 0) tma_store_wait_read<1>();
+          __syncwarp();
+#pragma unroll
+          for (int ch = 0; ch < 8; ++ch) {
+            const uint32_t a = rowaddr + (((uint32_t)ch ^ ((uint32_t)lane & 7u)) << 4);
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(__float_as_uint(z[4 * ch])), "r"(__float_as_uint(z[4 * ch + 1])),
+                         "r"(__float_as_uint(z[4 * ch + 2])), "r"(__float_as_uint(z[4 * ch + 3])) : "memory");
+          }
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0 && row0 < p.M) {
+            tma_store_2d(&tmD, buf, u * 32, row0);
+            tma_store_commit();
+          }
+          stg_flip ^= 1;
+        };
+        constexpr int NU = BN / 32;
+        tmem_ld_32x32(taddr, ra);
+#pragma unroll 1
+        for (int u = 0; u < NU; u += 2) {
+          tmem_ld_wait();
+          tmem_ld_32x32(taddr + (u + 1) * 32, rb);
+          emit(ra, u);
+          tmem_ld_wait();
+          if (u + 2 < NU) tmem_ld_32x32(taddr + (u + 2) * 32, ra);
+          emit(rb, u + 1);
+        }
+        if (row < p.M) {
+          p.mean[row] = valid ? mu : 0.f;
+          p.rstd[row] = valid ? rsqrtf(m2 * (1.f / (float)BN) + p.eps) : 0.f;
+        }
       } else if (p.tma_store) {
         // Coalesced path: each warp stages [32 rows x 128 B] slabs (128B-swizzled, conflict-free 16-byte
         // writes) and hands them to the TMA store engine. Work unit = one x32 TMEM load (32 fp32 columns):
@@ -408,7 +506,6 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       }
       tc_fence_before();
       mbar_arrive(tempty_bar(acc));
-      if (++acc == 2) { acc = 0; acc_ph ^= 1; }
     }
     if (p.tma_store && lane == 0) tma_store_wait_all();  // staged slabs must be read before the CTA exits
   }
@@ -421,11 +518,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   }
 }
 
-template <int BN, bool A_MN, bool B_MN, int CL>
+template <int BN, bool A_MN, bool B_MN, int CL, bool LN = false>
 static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmD,
-                       const GemmArgs& args, cudaStream_t stream) {
+                       const GemmArgs& args, cudaStream_t stream, const CUtensorMap* tmR0 = nullptr,
+                       const CUtensorMap* tmR1 = nullptr) {
   using Cfg = GemmCfg<BN>;
-  auto kern = gemm_kernel<BN, A_MN, B_MN, CL>;
+  auto kern = gemm_kernel<BN, A_MN, B_MN, CL, LN>;
   static bool configured = false;
   if (!configured) {
     CSN_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
@@ -446,7 +544,7 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUt
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  CSN_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmD, args));
+  CSN_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmD, tmR0 ? *tmR0 : tmA, tmR1 ? *tmR1 : tmA, args));
   CSN_LAUNCH_OK("gemm_kernel");
   return 0;
 }
@@ -460,10 +558,16 @@ static int dispatch_major(bool a_mn, bool b_mn, const CUtensorMap& tmA, const CU
   return launch_gemm<BN, true, true, CL>(tmA, tmB, tmD, args, stream);
 }
 
+struct LnEpilogue {
+  const float* res0; long long res0_rows; const float* res1; long long res1_rows; const int* res_sel; const int* res_row;
+  long long res_ld; int block_rows, group_rows, rows_valid, n_points; float eps; float* mean; float* rstd;
+};
+
 }  // namespace csn
 
-extern "C" int csn_gemm(const csn_mat* A, const csn_mat* B, const csn_out* D, int32_t M, int32_t N,
-                        int32_t K, const int32_t nb[4], float alpha, int32_t split_k, void* stream) {
+static int gemm_impl(const csn_mat* A, const csn_mat* B, const csn_out* D, int32_t M, int32_t N,
+                     int32_t K, const int32_t nb[4], float alpha, int32_t split_k, void* stream,
+                     const csn::LnEpilogue* ln) {
   using namespace csn;
   clear_error();
   CSN_CHECK_ARG(A && B && D && nb, "csn_gemm: null argument");
@@ -552,8 +656,31 @@ extern "C" int csn_gemm(const csn_mat* A, const csn_mat* B, const csn_out* D, in
     g.stages = deep_staging ? shallow : full;
     g.stg_bufs = 2;
     g.epi_warps = deep_staging ? 8 : 4;
+    g.tempty_count = 32 * g.epi_warps;
   }
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  if (ln) {
+    const long long nbt = (long long)nb[0] * nb[1] * nb[2] * nb[3];
+    CSN_CHECK_ARG(N == 256 && !a_mn && !b_mn && nbt == 1 && split_k == 1 && D->dtype == CSN_F32 && g.tma_store,
+                  "csn_gemm_res_ln: needs N == 256, K-major operands, one batch, a 16-byte aligned row-major fp32 Z");
+    CSN_CHECK_ARG(ln->block_rows > 0 && ln->group_rows > 0 && ln->rows_valid > 0 && ln->rows_valid <= ln->group_rows &&
+                  ln->block_rows % 32 == 0 && ln->group_rows % 32 == 0,
+                  "csn_gemm_res_ln: bad row structure (block_rows and group_rows must be multiples of 32)");
+    CUtensorMap tmR0, tmR1;
+    rc = make_tmap_2d_any(&tmR0, ln->res0, CSN_F32, ln->res_ld, ln->res0_rows, ln->res_ld, 32, 32);
+    if (rc) return rc;
+    rc = make_tmap_2d_any(&tmR1, ln->res1, CSN_F32, ln->res_ld, ln->res1_rows, ln->res_ld, 32, 32);
+    if (rc) return rc;
+    g.ln = 1;
+    g.res_sel = ln->res_sel; g.res_row = ln->res_row;
+    g.block_rows = ln->block_rows; g.group_rows = ln->group_rows; g.rows_valid = ln->rows_valid; g.n_points = ln->n_points;
+    g.eps = ln->eps; g.mean = ln->mean; g.rstd = ln->rstd;
+    // the thread owns its whole row; two warp sets alternate tiles (one per accumulator buffer); per warp 2 output
+    // + 2 residual slabs -> 128 KB of staging next to a 2-deep operand ring (K is short: the epilogue is the critical path)
+    g.stages = 2; g.stg_bufs = 4; g.epi_warps = 8; g.alt_tiles = 1; g.tempty_count = 128;
+    if (CL == 2) return launch_gemm<256, false, false, 2, true>(tmA, tmB, tmD, g, s, &tmR0, &tmR1);
+    return launch_gemm<256, false, false, 1, true>(tmA, tmB, tmD, g, s, &tmR0, &tmR1);
+  }
   if (CL == 2) {
     if (BN == 256) return dispatch_major<256, 2>(a_mn, b_mn, tmA, tmB, tmD, g, s);
     return dispatch_major<128, 2>(a_mn, b_mn, tmA, tmB, tmD, g, s);
@@ -561,4 +688,27 @@ extern "C" int csn_gemm(const csn_mat* A, const csn_mat* B, const csn_out* D, in
   if (BN == 256) return dispatch_major<256, 1>(a_mn, b_mn, tmA, tmB, tmD, g, s);
   if (BN == 128) return dispatch_major<128, 1>(a_mn, b_mn, tmA, tmB, tmD, g, s);
   return dispatch_major<64, 1>(a_mn, b_mn, tmA, tmB, tmD, g, s);
+}
+
+extern "C" int csn_gemm(const csn_mat* A, const csn_mat* B, const csn_out* D, int32_t M, int32_t N,
+                        int32_t K, const int32_t nb[4], float alpha, int32_t split_k, void* stream) {
+  return gemm_impl(A, B, D, M, N, K, nb, alpha, split_k, stream, nullptr);
+}
+
+extern "C" int csn_gemm_res_ln(const csn_mat* A, const csn_mat* B, float* Z, int64_t ldz, int32_t M, int32_t K,
+                               float alpha, const float* res0, int64_t res0_rows, const float* res1,
+                               int64_t res1_rows, const int32_t* res_sel, const int32_t* res_row, int64_t res_ld,
+                               int32_t n_points, int32_t block_rows, int32_t group_rows, int32_t rows_valid,
+                               float eps, float* mean, float* rstd, void* stream) {
+  using namespace csn;
+  clear_error();
+  CSN_CHECK_ARG(Z && res0 && res_sel && res_row && mean && rstd, "csn_gemm_res_ln: null pointer");
+  CSN_CHECK_ARG(n_points > 0 && n_points <= res_ld, "csn_gemm_res_ln: n_points (%d) must be in (0, res_ld]", n_points);
+  csn_out D;
+  memset(&D, 0, sizeof(D));
+  D.ptr = Z; D.dtype = CSN_F32; D.ld = ldz;
+  LnEpilogue ln{res0, res0_rows, res1 ? res1 : res0, res1 ? res1_rows : res0_rows, res_sel, res_row, res_ld,
+                block_rows, group_rows, rows_valid, n_points, eps, mean, rstd};
+  const int32_t nb[4] = {1, 1, 1, 1};
+  return gemm_impl(A, B, &D, M, 256, K, nb, alpha, 1, stream, &ln);
 }

@@ -13,6 +13,7 @@ import math
 import os
 from dataclasses import dataclass, field
 
+import ctypes as C
 import torch
 
 from . import _lib as L
@@ -197,10 +198,30 @@ def _scores_and_probs(ctx: "AttnContext"):
     return Sbuf, P
 
 
+def use_fused_ln() -> bool:
+    """CSN_FUSED_LN=0 selects the separate projection GEMM + csn_add_ln_fwd pair (tests cross-check the two)."""
+    return os.environ.get("CSN_FUSED_LN", "1") != "0"
+
+
+@dataclass(frozen=True)
+class ChannelMajorResidual:
+    """Where the fp32 residual of every slot lives in the reference's own (.., 256, N, 1) layout: slot s is the
+    [256][N] matrix at bases[sel[s]] + off[s] elements, channel stride ch_stride (csa_models.py:92-94)."""
+    bases: tuple          # up to two fp32 CUDA tensors (kept alive by the caller)
+    sel: tuple            # per slot: index into bases
+    off: tuple            # per slot: element offset
+    ch_stride: int
+    n_points: int
+
+
 def attention_forward(Xh, Xf, groups, n_slots, n_blocks, w_q, w_k, w_v, w_o, gamma, beta, geom: Geometry,
                       n_head: int, want_colsum: bool = True, save_for_backward: bool = True,
-                      want_y: bool = True) -> AttnContext:
-    """Forward of all blocks. Xh/Xf: packed slots [S*NP, 256] (16-bit / fp32)."""
+                      want_y: bool = True, residual_cm: ChannelMajorResidual = None,
+                      colsum_blocks: int = None) -> AttnContext:
+    """Forward of all blocks. Xh/Xf: packed slots [S*NP, 256] (16-bit / fp32). With residual_cm (and want_y False)
+    Xf may be None: the output projection, the residual add and the LayerNorm statistics run as ONE kernel
+    (csn_gemm_res_ln) that reads the residual from the channel-major inputs; colsum then covers the first
+    colsum_blocks blocks only."""
     dev, dt = Xh.device, Xh.dtype
     NP, CP, NC = geom.rows_pad, geom.chunk_pad, geom.n_chunks
     HD = w_q.shape[0]
@@ -242,9 +263,40 @@ def attention_forward(Xh, Xf, groups, n_slots, n_blocks, w_q, w_k, w_v, w_o, gam
     ctx.O = O
     # --- output projection (csa_models.py:115), residual + LayerNorm (:116-118), pooled column sums
     Z = torch.empty(n_blocks * NP, 256, dtype=torch.float32, device=dev)
-    L.gemm(L.mat(O, L.MAJOR_K), L.mat(ctx.Wo16, L.MAJOR_K), L.out(Z, 256), n_blocks * NP, 256, HD)
     ctx.res_block = cached_table(("res_block", tuple(groups), n_blocks), dev,
                                  lambda: _res_block_table(groups, n_blocks))
+    if residual_cm is not None and not want_y and use_fused_ln():
+        r = residual_cm
+        sel = cached_table(("res_sel", tuple(groups), n_blocks, r.sel), dev,
+                           lambda: torch.tensor([r.sel[q] for q in _res_block_table(groups, n_blocks).tolist()], dtype=torch.int32))
+        off = cached_table(("res_row", tuple(groups), n_blocks, r.off, r.ch_stride), dev,
+                           lambda: torch.tensor([r.off[q] // r.ch_stride for q in _res_block_table(groups, n_blocks).tolist()], dtype=torch.int32))
+        ctx.mean = torch.empty(n_blocks * NP, dtype=torch.float32, device=dev)
+        ctx.rstd = torch.empty_like(ctx.mean)
+        A, B = L.mat(O, L.MAJOR_K), L.mat(ctx.Wo16, L.MAJOR_K)
+        b0, b1 = r.bases[0], r.bases[-1]
+        rc = L.lib().csn_gemm_res_ln(C.byref(A), C.byref(B), Z.data_ptr(), 256, n_blocks * NP, HD, 1.0,
+                                     b0.data_ptr(), b0.numel() // r.ch_stride, b1.data_ptr(), b1.numel() // r.ch_stride,
+                                     sel.data_ptr(), off.data_ptr(), r.ch_stride, min(r.n_points, geom.n_points),
+                                     NP, CP, geom.chunk, 1e-6, ctx.mean.data_ptr(), ctx.rstd.data_ptr(), L.stream_ptr())
+        L.check(rc, "csn_gemm_res_ln")
+        ctx.colsum = None
+        if want_colsum:
+            nb_cs = n_blocks if colsum_blocks is None else colsum_blocks
+            parts = torch.empty(nb_cs * NP // 64, 256, dtype=torch.float32, device=dev)
+            rc = L.lib().csn_ln_colsum(Z.data_ptr(), ctx.mean.data_ptr(), ctx.rstd.data_ptr(), gamma.data_ptr(),
+                                       beta.data_ptr(), parts.data_ptr(), nb_cs * NP, NP, CP, geom.chunk, L.stream_ptr())
+            L.check(rc, "csn_ln_colsum")
+            ctx.colsum = torch.empty(nb_cs, 256, dtype=torch.float32, device=dev)
+            rc = L.lib().csn_colsum_reduce(parts.data_ptr(), ctx.colsum.data_ptr(), nb_cs, NP // 64,
+                                           1.0 / geom.n_points, L.stream_ptr())
+            L.check(rc, "csn_colsum_reduce")
+        ctx.Z, ctx.Y = Z, None
+        ctx.beta = beta
+        return ctx
+    if Xf is None:
+        raise L.CsnError("attention_forward: the fp32 row copy Xf is required when the fused residual/LayerNorm epilogue is off")
+    L.gemm(L.mat(O, L.MAJOR_K), L.mat(ctx.Wo16, L.MAJOR_K), L.out(Z, 256), n_blocks * NP, 256, HD)
     Y = torch.empty_like(Z) if want_y else None   # CSA: consumers re-normalise z on the fly, Y never hits HBM
     ctx.mean = torch.empty(n_blocks * NP, dtype=torch.float32, device=dev)
     ctx.rstd = torch.empty_like(ctx.mean)

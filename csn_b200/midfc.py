@@ -16,6 +16,7 @@ Deviations from the reference, all documented in DESIGN.md:
 from __future__ import annotations
 
 import numpy as np
+import contextlib
 import torch
 import torch.nn as nn
 import torch.nn.functional as F
@@ -34,6 +35,18 @@ def _require_cuda(t: torch.Tensor, what: str) -> None:
         raise L.CsnError(f"{what} must be a CUDA tensor: csn_b200 has no CPU path")
 
 
+def neighbors_to_device(x_neighbors: torch.Tensor, dev, stream: "torch.cuda.Stream" = None) -> torch.Tensor:
+    """Host -> device copy of a neighbour tensor (B,K+1,256,N,1) that skips slot 0: the layer never reads it
+    (csa_models.py:214,234 iterate k = 1..K), so a quarter of the bytes (K=3) stay off the PCIe link. The device
+    tensor keeps the (B,K+1,...) shape with slot 0 left uninitialised. With pinned host memory the copies are
+    asynchronous; `stream` (optional) lets an input pipeline stage step i+1 while step i computes."""
+    out = torch.empty(x_neighbors.shape, dtype=x_neighbors.dtype, device=dev)
+    with torch.cuda.stream(stream) if stream is not None else contextlib.nullcontext():
+        for b in range(x_neighbors.shape[0]):
+            out[b, 1:].copy_(x_neighbors[b, 1:], non_blocking=True)
+    return out
+
+
 def _geom_for(n_src_points: int, iters: int = 20, chunk: int = 500) -> E.Geometry:
     g = E.Geometry(chunk=chunk, n_chunks=iters, chunk_pad=(chunk + 127) // 128 * 128)
     if n_src_points < g.n_points:
@@ -42,11 +55,17 @@ def _geom_for(n_src_points: int, iters: int = 20, chunk: int = 500) -> E.Geometr
     return g
 
 
-def _pack_sources(sources, n_slots, geom, dt, dev):
+def _std_layout(t: torch.Tensor) -> torch.Tensor:
+    """(.., 256, N, 1) fully contiguous (the kernels view it as a 2-D [channels of all shapes][N] matrix); copies
+    only if needed."""
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def _pack_sources(sources, n_slots, geom, dt, dev, want_f32: bool = True):
     """sources: list of (tensor (n0,[n1],256,N,1) fp32 cuda, slot0, d0, d1)."""
     NP = geom.rows_pad
     Xh = torch.empty(n_slots * NP, 256, dtype=dt, device=dev)
-    Xf = torch.empty(n_slots * NP, 256, dtype=torch.float32, device=dev)
+    Xf = torch.empty(n_slots * NP, 256, dtype=torch.float32, device=dev) if want_f32 else None
     for (t, slot0, d0, d1) in sources:
         if t.dim() == 4:
             t = t.unsqueeze(1)
@@ -249,14 +268,26 @@ class _CsaFn(torch.autograd.Function):
         K = 0 if ssa_only else x_neighbors.shape[1] - 1
         if not ssa_only and not x_neighbors.is_cuda:
             # the reference moves each neighbour inside the layer (csa_models.py:216,236)
-            x_neighbors = x_neighbors.to(dev, non_blocking=True)
+            x_neighbors = neighbors_to_device(x_neighbors, dev)
         n_src_nb = n_src if ssa_only or K == 0 else x_neighbors.shape[3]
         geom = _geom_for(min(n_src, n_src_nb), iters, chunk)
         S = B * (K + 1)
-        sources = [(x.float(), 0, K + 1, 0)]
+        xs = _std_layout(x.float())
+        sources = [(xs, 0, K + 1, 0)]
+        nbs = None
         if K > 0:
-            sources.append((x_neighbors[:, 1:].float(), 1, K + 1, 1))
-        Xh, Xf = _pack_sources(sources, S, geom, dt, dev)
+            nbs = _std_layout(x_neighbors.float())
+            sources.append((nbs[:, 1:], 1, K + 1, 1))
+        # the residual of the output projection is read straight from these channel-major tensors by the fused
+        # projection/LayerNorm kernel (slot s = b*(K+1)+j: j = 0 the query, j >= 1 neighbour j)
+        res_cm = None
+        if K == 0 or nbs.shape[3] == xs.shape[2]:
+            sel = tuple(0 if j == 0 else 1 for b in range(B) for j in range(K + 1))
+            off = tuple(b * xs.stride(0) if j == 0 else b * nbs.stride(0) + j * nbs.stride(1)
+                        for b in range(B) for j in range(K + 1))
+            res_cm = E.ChannelMajorResidual(bases=(xs,) if K == 0 else (xs, nbs), sel=sel, off=off,
+                                            ch_stride=xs.shape[2], n_points=xs.shape[2])
+        Xh, Xf = _pack_sources(sources, S, geom, dt, dev, want_f32=res_cm is None or not E.use_fused_ln())
         groups = [E.Group(n_in=S, n_out=1, blk0=0, q0=0, q_si=1, q_so=0, k0=0, k_si=1, k_so=0, v0=0, v_si=1, v_so=0)]
         nblk = S
         if K > 0:
@@ -264,7 +295,7 @@ class _CsaFn(torch.autograd.Function):
                                   v0=1, v_si=1, v_so=K + 1))
             nblk += B * K
         a = E.attention_forward(Xh, Xf, groups, S, nblk, wq, wk, wv, wo, gamma, beta, geom, n_head,
-                                want_colsum=not ssa_only, want_y=False)
+                                want_colsum=not ssa_only, want_y=False, residual_cm=res_cm, colsum_blocks=S)
         # ---- compatibility (csa_models.py:211-230): tiny (B*(K+1) x 256) glue, kept in torch
         if ssa_only:
             comp = torch.ones(B, 1, dtype=torch.float32, device=dev)

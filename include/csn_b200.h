@@ -196,6 +196,28 @@ int csn_add_ln_fwd(float* Z, const float* R, const int32_t* res_block, float* Y,
                    int32_t block_rows, int32_t group_rows, int32_t rows_valid, float eps, int32_t dtype,
                    void* stream);
 int csn_colsum_reduce(const float* part, float* out, int32_t n_blocks, int32_t parts, float scale, void* stream);
+
+/* The output projection fused with the residual add and the LayerNorm statistics (csa_models.py:115-118 in one
+ * pass): Z[m][0..256) = alpha * (A B^T)[m] + residual(m), mean[m] / rstd[m] = LayerNorm statistics of that row
+ * (biased variance, eps inside the square root). Z (fp32, row-major, leading dimension ldz) is the only
+ * activation written: consumers re-normalise it on the fly (csn_combine_fwd, csn_block_dot, csn_ln_bwd).
+ * A: [M x K] K-major 16-bit, B: [256 x K] K-major (nn.Linear weight layout).
+ * Residual: row m = block*block_rows + g*group_rows + j (j < rows_valid, else a pad row: Z = 0, mean = rstd = 0)
+ * is point n = g*rows_valid + j of the block's source shape, read from the reference's own channel-major layout
+ * (csa_models.py:92-94,214-216) through TMA: each of the two residual tensors res0 / res1 (the query tensor and
+ * the neighbour tensor) is viewed as a 2-D fp32 matrix [res*_rows][res_ld] whose row r holds one channel of one
+ * shape; the [256][n_points] matrix of `block` starts at row res_row[block] of tensor res_sel[block].  Points
+ * >= n_points are ignored.  The fp32 row-major copy of the inputs that csn_add_ln_fwd needs is never made.
+ * block_rows and group_rows must be multiples of 32; res_ld*4 bytes a multiple of 16. */
+int csn_gemm_res_ln(const csn_mat* A, const csn_mat* B, float* Z, int64_t ldz, int32_t M, int32_t K, float alpha,
+                    const float* res0, int64_t res0_rows, const float* res1, int64_t res1_rows,
+                    const int32_t* res_sel, const int32_t* res_row, int64_t res_ld, int32_t n_points,
+                    int32_t block_rows, int32_t group_rows, int32_t rows_valid, float eps, float* mean,
+                    float* rstd, void* stream);
+/* colsum[(row/64)][c] = sum over the valid rows of the 64-row group of (Z - mean)*rstd*gamma + beta: the partials
+ * csn_colsum_reduce turns into the pooled means, for rows whose statistics came from csn_gemm_res_ln. */
+int csn_ln_colsum(const float* Z, const float* mean, const float* rstd, const float* gamma, const float* beta,
+                  float* colsum, int64_t rows, int32_t block_rows, int32_t group_rows, int32_t rows_valid, void* stream);
 /* dZ may be NULL (only the 16-bit copy is written).  bcast (optional, [n][256]) adds the row
  * bcast_scale * bcast[bcast_idx[block]] to every valid row of a block before the backward formula: the
  * gradient of the pooled mean (csa_models.py:212,219) without materialising it.
