@@ -120,3 +120,25 @@ def test_output_is_independent_of_batch_composition_for_ssa():
         all3, _ = m.get_ssa_feats(x, "test")
         one, _ = m.get_ssa_feats(x[1:2].contiguous(), "test")
     assert torch.equal(all3[1:2], one)
+
+
+def test_fused_projection_layernorm_matches_separate_kernels(monkeypatch):
+    """csn_gemm_res_ln (projection + residual + LayerNorm statistics in one kernel, residual read from the
+    channel-major inputs) against the csn_gemm + csn_add_ln_fwd pair: same Z up to fp32 summation order."""
+    from csn_b200 import midfc
+    B, K, h = 2, 2, 1
+    m = midfc.get_model("csa", 15, h, K).cuda().eval()
+    m.load_state_dict(synth.midfc_state(3, h, 15))
+    x, nb = synth.csa_batch(11, B, K)
+    nb = nb.cuda()
+    outs = {}
+    for mode in ("1", "0"):
+        monkeypatch.setenv("CSN_FUSED_LN", mode)
+        xg = x.cuda().requires_grad_(True)
+        feats = m.get_csa_feats(xg, nb, "test")
+        feats.square().mean().backward()
+        outs[mode] = (feats.detach().clone(), xg.grad.clone(), m.attention.w_qs.weight.grad.clone())
+        m.zero_grad()
+    # gradients pass through 16-bit intermediates: a last-bit difference in Z can flip a rounding
+    for a, b, what, tol in zip(outs["1"], outs["0"], ("feats", "grad x", "grad w_qs"), (2e-5, 2e-4, 2e-4)):
+        assert G.rel_err(a, b) < tol, (what, G.rel_err(a, b))
