@@ -8,6 +8,7 @@
 //   delta_i = rowsum(dO_i o O_i) comes from csn_attn_delta.
 // CTA layout as in attn_fwd.cu: warp 0 TMA, warp 1 MMA issuer, warp 2 TMEM allocator, warps 4-7
 // element-wise stage + epilogue. TMEM: S @0 (128 cols) | dP @128 (128) | dQ @256 (<= 256).
+#include <cstdlib>
 #include "host_util.h"
 #include "ptx.cuh"
 
@@ -43,6 +44,7 @@ struct AttnBwdArgs {
   int dtype;
   uint32_t idesc_s;   // M=128, N=128, K-major x K-major
   uint32_t idesc_dq;  // M=128, N=128 (DH>=128) or DH, A K-major, B MN-major
+  int prefetch;       // wide dS kernel: L2-prefetch the next item's tiles
 };
 
 template <int DH>
@@ -366,6 +368,333 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// dS-only variant for d_head = 256 with 256-key steps.  An SS-mode M=128 tcgen05.mma costs about the same for
+// N = 128 and N = 256 (profiles/r1_experiments.md), so the 128-key tiles of the kernel above leave half of the
+// tensor pipe idle.  Here S = Q_i K^T and dP = dO_i V^T are [128 x 256] accumulators (TMEM columns 0-255 / 256-511,
+// the whole TMEM), each single-buffered but alternating: S_{j+1} is issued as soon as the element-wise warps have
+// turned S_j into P_j (16-bit, kept in registers), dP_{j+1} as soon as dP_j has been read, so the MMA pipe runs
+// while the other accumulator is consumed.  8 element-wise warps: warp pair (q, q+4) shares TMEM lane quadrant q
+// and splits the 256 key columns.
+// Nothing is resident in SMEM: every ring slot carries one 64-column slice of BOTH operands of four MMAs
+// ([128 x 64] of Q_i or dO_i next to [256 x 64] of K or V, 48 KB), so that the ring is 3 deep (a 2-deep ring of
+// 32 KB K/V slices next to resident Q_i/dO_i tiles stalls the MMA pipe on TMA latency: 336 vs 256 us measured
+// without stores) and 32 KB remain for the output slabs.  Q_i/dO_i slices are re-read per key step (L2 hits).
+// L2-prefetching the next item's tiles was tried and is harmful (the prefetches queue in front of the ring's
+// loads in the TMA unit: 328 -> 437 us).
+template <int DBG>
+struct WideCfgT {
+  static constexpr int A_BYTES = 128 * 64 * 2;       // slice of Q_i / dO_i
+  static constexpr int B_BYTES = 256 * 64 * 2;       // slice of K / V
+  static constexpr int SLOT_BYTES = A_BYTES + B_BYTES;
+  static constexpr int NST = DBG == 2 ? 3 : 4;     // measured: 4-deep ring + single slabs 328 us, 3-deep + double slabs 345 us
+  static constexpr int NSLAB = DBG == 2 ? 2 : 1;
+  static constexpr int STG_BYTES = 8 * NSLAB * 4096;     // [32 rows x 64 keys] slabs per element-wise warp
+  static constexpr int SMEM_BYTES = NST * SLOT_BYTES + STG_BYTES + 256 + 1024;
+};
+using WideCfg = WideCfgT<0>;
+
+template <int CL, int DBG = 0>
+__global__ void __launch_bounds__(384, 1)
+attn_bwd_ds_wide_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmDO,
+                        const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
+                        const __grid_constant__ CUtensorMap tmDS, const __grid_constant__ AttnBwdArgs p) {
+  using Cfg = WideCfgT<DBG>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const uint32_t sKV = smem_u32(smem);
+  const uint32_t sSTG = sKV + Cfg::NST * Cfg::SLOT_BYTES;
+  const uint32_t bar_base = sSTG + Cfg::STG_BYTES;
+  uint8_t* bar_ptr = smem + Cfg::NST * Cfg::SLOT_BYTES + Cfg::STG_BYTES;
+  auto kv_full = [&](int s) { return bar_base + 8u * s; };
+  auto kv_empty = [&](int s) { return bar_base + 8u * (Cfg::NST + s); };
+  const uint32_t s_full = bar_base + 8u * (2 * Cfg::NST + 0), s_empty = bar_base + 8u * (2 * Cfg::NST + 1);
+  const uint32_t dp_full = bar_base + 8u * (2 * Cfg::NST + 2), dp_empty = bar_base + 8u * (2 * Cfg::NST + 3);
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bar_ptr + 8 * (2 * Cfg::NST + 4));
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmDO); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < Cfg::NST; ++s) { mbar_init(kv_full(s), 1); mbar_init(kv_empty(s), CL); }
+    mbar_init(s_full, 1); mbar_init(s_empty, 256);
+    mbar_init(dp_full, 1); mbar_init(dp_empty, 256);
+    fence_mbar_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(smem_u32(tmem_ptr_smem), 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  if (CL > 1) cluster_sync_all(); else __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+  const int rank = (CL > 1) ? (int)cluster_ctarank() : 0;
+  const int worker = (int)blockIdx.x / CL, n_workers = (int)gridDim.x / CL;
+  const int n_work = p.n_items / CL;
+  constexpr uint16_t MC_MASK = (1u << CL) - 1;
+
+  if (warp == 0) {
+    // ================================================================== TMA producer
+    if (elect_one()) {
+      int st = 0;
+      uint32_t ph = 0;
+      // one accumulator's operands: 4 slots of { A[128 x 64] from (tmA, a_row0), B[256 x 64] from (tmB, b_row0) }
+      auto load_step = [&](const CUtensorMap* tmA, int a_row0, const CUtensorMap* tmB, int b_row0, int col0) {
+#pragma unroll 1
+        for (int kb = 0; kb < 4; ++kb) {
+          mbar_wait(kv_empty(st), ph ^ 1);
+          mbar_arrive_expect_tx(kv_full(st), Cfg::SLOT_BYTES);
+          const uint32_t dst = sKV + st * Cfg::SLOT_BYTES;
+          tma_load_2d(dst, tmA, kv_full(st), col0 + kb * 64, a_row0);
+          if (CL == 1) {
+            tma_load_2d(dst + Cfg::A_BYTES, tmB, kv_full(st), col0 + kb * 64, b_row0);
+            tma_load_2d(dst + Cfg::A_BYTES + 16384, tmB, kv_full(st), col0 + kb * 64, b_row0 + 128);
+          } else {   // each CTA of the pair loads one 128-key half and multicasts it to both
+            tma_load_2d_mc(dst + Cfg::A_BYTES + rank * 16384, tmB, kv_full(st), col0 + kb * 64, b_row0 + rank * 128, MC_MASK);
+          }
+          if (++st == Cfg::NST) { st = 0; ph ^= 1; }
+        }
+      };
+      for (int wk = worker; wk < n_work; wk += n_workers) {
+        const AttnBwdItem it = p.items[wk * CL + rank];
+        const int nst = (it.kv_len + 255) >> 8;
+        if (p.prefetch && wk + n_workers < n_work) {
+          // first touches of the next item's Q_i / dO_i (and, for the first pair of a chunk, K / V) would reach
+          // the ring with HBM latency, which a 4-deep ring does not cover: pull them into L2 one item ahead
+          const AttnBwdItem nx = p.items[(wk + n_workers) * CL + rank];
+#pragma unroll 1
+          for (int kb = 0; kb < 4; ++kb) {
+            tma_prefetch_l2_2d(&tmQ, nx.col0 + kb * 64, nx.q_row0);
+            tma_prefetch_l2_2d(&tmDO, nx.col0 + kb * 64, nx.o_row0);
+          }
+          if (nx.kv_row0 != it.kv_row0 || nx.col0 != it.col0) {
+            const int nrows = (nx.kv_len + 127) >> 7;
+#pragma unroll 1
+            for (int t = rank; t < nrows; t += CL)
+#pragma unroll 1
+              for (int kb = 0; kb < 4; ++kb) {
+                tma_prefetch_l2_2d(&tmK, nx.col0 + kb * 64, nx.kv_row0 + t * 128);
+                tma_prefetch_l2_2d(&tmV, nx.col0 + kb * 64, nx.kv_row0 + t * 128);
+              }
+          }
+        }
+        for (int j = 0; j < nst; ++j) {
+          load_step(&tmQ, it.q_row0, &tmK, it.kv_row0 + j * 256, it.col0);    // for S
+          load_step(&tmDO, it.o_row0, &tmV, it.kv_row0 + j * 256, it.col0);   // for dP
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================================================================== MMA issuer
+    if (elect_one()) {
+      int st = 0;
+      uint32_t ph = 0, s_ph = 0, dp_ph = 0;
+      auto mma_step = [&](uint32_t d_tmem) {   // D[128 x 256] = sum over 4 slots of A_slice x B_slice^T
+#pragma unroll 1
+        for (int kb = 0; kb < 4; ++kb) {
+          mbar_wait(kv_full(st), ph);
+          tc_fence_after();
+          const uint32_t a_tile = sKV + st * Cfg::SLOT_BYTES;
+          const uint32_t b_tile = a_tile + Cfg::A_BYTES;
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_f16_ss(d_tmem, umma_desc_sw128(a_tile + k * 32, 0, 1024), umma_desc_sw128(b_tile + k * 32, 0, 1024),
+                        p.idesc_s, (kb | k) ? 1u : 0u);
+          if (CL == 1) umma_commit(kv_empty(st)); else umma_commit_mc(kv_empty(st), MC_MASK);
+          if (++st == Cfg::NST) { st = 0; ph ^= 1; }
+        }
+      };
+      for (int wk = worker; wk < n_work; wk += n_workers) {
+        const AttnBwdItem it = p.items[wk * CL + rank];
+        const int nst = (it.kv_len + 255) >> 8;
+        for (int j = 0; j < nst; ++j) {
+          mbar_wait(s_empty, s_ph ^ 1);      // S_{j-1} has been turned into P_{j-1}
+          tc_fence_after();
+          mma_step(tmem_base);               // S = Q K^T
+          umma_commit(s_full);
+          s_ph ^= 1;
+          mbar_wait(dp_empty, dp_ph ^ 1);    // dP_{j-1} has been read
+          tc_fence_after();
+          mma_step(tmem_base + 256);         // dP = dO V^T
+          umma_commit(dp_full);
+          dp_ph ^= 1;
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    // ================================================================== element-wise stage
+    const int ew = warp - 4;
+    const int q = warp & 3, half = ew >> 2;
+    const int r = q * 32 + lane;
+    const uint32_t lane_addr = uint32_t(q * 32) << 16;
+    const uint32_t slab0 = sSTG + ew * Cfg::NSLAB * 4096;
+    int flip = 0;
+    uint32_t s_ph = 0, dp_ph = 0;
+    constexpr float LOG2E = 1.4426950408889634f;
+    const bool f16 = p.dtype == CSN_F16;
+    auto pack_pair = [&](float a, float b) -> uint32_t {
+      if (f16) { __half2 h = __floats2half2_rn(a, b); return *reinterpret_cast<uint32_t*>(&h); }
+      __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+      return *reinterpret_cast<uint32_t*>(&h);
+    };
+    auto unpack_pair = [&](uint32_t w) -> float2 {
+      if (f16) return __half22float2(*reinterpret_cast<__half2*>(&w));
+      return __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&w));
+    };
+    for (int wk = worker; wk < n_work; wk += n_workers) {
+      const AttnBwdItem it = p.items[wk * CL + rank];
+      const int nst = (it.kv_len + 255) >> 8;
+      const bool valid = r < it.q_valid;
+      const float lse_l2 = valid ? p.lse[it.stat_off + r] * LOG2E : 0.f;
+      const float dlt = valid ? p.delta[it.stat_off + r] : 0.f;
+      for (int j = 0; j < nst; ++j) {
+        const int key0 = j * 256 + half * 128;          // first key of this warp's 128 columns
+        const int nvalid = valid ? it.kv_len - key0 : 0;   // columns [0, nvalid) of the 128 are real keys
+        // ---- pass A: S -> P (16-bit pairs in registers)
+        uint32_t pk[64];
+        mbar_wait(s_full, s_ph);
+        s_ph ^= 1;
+        tc_fence_after();
+        {
+          const uint32_t s_addr = tmem_base + lane_addr + half * 128;
+          uint32_t va[32], vb[32];
+          tmem_ld_32x32(s_addr, va);
+#pragma unroll
+          for (int c = 0; c < 4; c += 2) {
+            tmem_ld_wait();
+            tmem_ld_32x32(s_addr + (c + 1) * 32, vb);
+#pragma unroll
+            for (int i = 0; i < 32; i += 2) {
+              const float p0 = (c * 32 + i < nvalid) ? fast_exp2_b(__uint_as_float(va[i]) * p.scale_log2 - lse_l2) : 0.f;
+              const float p1 = (c * 32 + i + 1 < nvalid) ? fast_exp2_b(__uint_as_float(va[i + 1]) * p.scale_log2 - lse_l2) : 0.f;
+              pk[c * 16 + (i >> 1)] = pack_pair(p0, p1);
+            }
+            tmem_ld_wait();
+            if (c + 2 < 4) tmem_ld_32x32(s_addr + (c + 2) * 32, va);
+#pragma unroll
+            for (int i = 0; i < 32; i += 2) {
+              const float p0 = ((c + 1) * 32 + i < nvalid) ? fast_exp2_b(__uint_as_float(vb[i]) * p.scale_log2 - lse_l2) : 0.f;
+              const float p1 = ((c + 1) * 32 + i + 1 < nvalid) ? fast_exp2_b(__uint_as_float(vb[i + 1]) * p.scale_log2 - lse_l2) : 0.f;
+              pk[(c + 1) * 16 + (i >> 1)] = pack_pair(p0, p1);
+            }
+          }
+        }
+        tc_fence_before();
+        mbar_arrive(s_empty);
+        // ---- pass B: dS = P o (dP - delta) * scale -> slab -> HBM.  (dP - delta)*scale is one FFMA per element, the
+        //      product with P is formed in fp32 (packed 16-bit arithmetic here was no faster and cost 1e-4 on dWq).
+        //      Masked columns have P = 0; the select below only guards against non-finite garbage in rows past
+        //      kv_len and is skipped when the whole half is valid.
+        mbar_wait(dp_full, dp_ph);
+        dp_ph ^= 1;
+        tc_fence_after();
+        {
+          const uint32_t d_addr = tmem_base + lane_addr + 256 + half * 128;
+          const float nds = -dlt * p.scale;
+          const bool all_valid = __all_sync(0xffffffffu, nvalid >= 128 || !valid);
+          uint32_t da[32], db[32];
+          auto emit = [&](const uint32_t (&dv)[32], int c) {
+            uint32_t w[16];
+#pragma unroll
+            for (int i = 0; i < 32; i += 2) {
+              float x0 = fmaf(__uint_as_float(dv[i]), p.scale, nds), x1 = fmaf(__uint_as_float(dv[i + 1]), p.scale, nds);
+              if (!all_valid) {
+                x0 = (c * 32 + i < nvalid) ? x0 : 0.f;
+                x1 = (c * 32 + i + 1 < nvalid) ? x1 : 0.f;
+              }
+              const float2 pp = unpack_pair(pk[c * 16 + (i >> 1)]);
+              w[i >> 1] = pack_pair(pp.x * x0, pp.y * x1);
+            }
+            if (DBG == 1) {   // diagnostics: all the arithmetic, no staging / stores
+              uint32_t x = 0;
+#pragma unroll
+              for (int t = 0; t < 16; ++t) x ^= w[t];
+              if (x == 0x12345678u) atomicAdd(reinterpret_cast<int*>(p.dS), 1);
+              return;
+            }
+            const uint32_t slab = slab0 + flip * 4096;
+            if ((c & 1) == 0) {   // the store issued from this slab two slabs ago must have been read
+              if (lane == 0) { if (Cfg::NSLAB == 2) tma_store_wait_read<1>(); else tma_store_wait_read<0>(); }
+              __syncwarp();
+            }
+            const uint32_t rowaddr = slab + lane * 128;
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+              const uint32_t a = rowaddr + ((((uint32_t)(c & 1) * 4 + t) ^ ((uint32_t)lane & 7u)) << 4);
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(w[4 * t]), "r"(w[4 * t + 1]), "r"(w[4 * t + 2]), "r"(w[4 * t + 3]) : "memory");
+            }
+            if (c & 1) {
+              fence_proxy_async_smem();
+              __syncwarp();
+              if (lane == 0) {
+                tma_store_2d(&tmDS, slab, it.ds_col0 + key0 + (c >> 1) * 64, it.ds_row0 + q * 32);
+                tma_store_commit();
+              }
+              if (Cfg::NSLAB == 2) flip ^= 1;
+            }
+          };
+          tmem_ld_32x32(d_addr, da);
+          tmem_ld_wait();
+          tmem_ld_32x32(d_addr + 32, db);
+          emit(da, 0);
+          tmem_ld_wait();
+          tmem_ld_32x32(d_addr + 64, da);
+          emit(db, 1);
+          tmem_ld_wait();
+          tmem_ld_32x32(d_addr + 96, db);
+          emit(da, 2);
+          tmem_ld_wait();
+          tc_fence_before();
+          mbar_arrive(dp_empty);
+          emit(db, 3);
+        }
+      }
+    }
+    if (lane == 0) tma_store_wait_all();
+  }
+
+  tc_fence_before();
+  if (CL > 1) cluster_sync_all(); else __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+template <int CL, int DBG = 0>
+static int launch_ds_wide(const CUtensorMap& tmQ, const CUtensorMap& tmDO, const CUtensorMap& tmK, const CUtensorMap& tmV,
+                          const CUtensorMap& tmDS, const AttnBwdArgs& a, cudaStream_t stream) {
+  auto kern = attn_bwd_ds_wide_kernel<CL, DBG>;
+  using WideCfg = WideCfgT<DBG>;
+  static bool configured = false;
+  if (!configured) {
+    CSN_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, WideCfg::SMEM_BYTES));
+    configured = true;
+  }
+  const int n_work = a.n_items / CL;
+  const int workers = num_sms() / CL;
+  const int grid = (n_work < workers ? n_work : workers) * CL;
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(384);
+  cfg.dynamicSmemBytes = WideCfg::SMEM_BYTES;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CL;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  CSN_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, tmQ, tmDO, tmK, tmV, tmDS, a));
+  CSN_LAUNCH_OK("attn_bwd_ds_wide_kernel");
+  return 0;
+}
+
 // delta[(blk*h + head)*rows_pad + row] = sum_c dO[blk*rows_pad + row][head*d + c] * O[...]; one warp per (row, head)
 __global__ void attn_delta_kernel(const void* __restrict__ dO, const void* __restrict__ O, const void* __restrict__ Olo,
                                   float* __restrict__ delta, long long rows, int rows_pad, int n_head, int d,
@@ -493,6 +822,7 @@ int csn_attn_bwd_dq(const void* Q, const void* dO, const void* K, const void* V,
   a.scale = 1.0f / sqrtf((float)d_head);
   a.scale_log2 = a.scale * 1.4426950408889634f;
   a.dtype = dtype;
+  a.prefetch = 0;
   const uint32_t fmt = dtype == CSN_F16 ? 0u : 1u;
   a.idesc_s = umma_idesc_f16(fmt, 0, 0, 128);
   a.idesc_dq = umma_idesc_f16(fmt, 0, 1, d_head == 256 ? 128u : 64u);
@@ -501,6 +831,18 @@ int csn_attn_bwd_dq(const void* Q, const void* dO, const void* K, const void* V,
   if (dQ != nullptr) {
     if (d_head == 256) return pair ? launch_dq<256, 2, true>(tmQ, tmDO, tmK, tmV, tmDS, tmDQ, a, s) : launch_dq<256, 1, true>(tmQ, tmDO, tmK, tmV, tmDS, tmDQ, a, s);
     return launch_dq<64, 1, true>(tmQ, tmDO, tmK, tmV, tmDS, tmDQ, a, s);
+  }
+  static const int wide = getenv("CSN_DS_WIDE") == nullptr ? 1 : atoi(getenv("CSN_DS_WIDE"));
+  if (d_head == 256 && wide) {   // 256-key steps: N = 256 score tiles
+    CUtensorMap tmDSw;
+    rc = make_tmap_2d(&tmDSw, dS, dtype, ldds, ds_rows, ldds, 64, 32);
+    if (rc) return rc;
+    a.idesc_s = umma_idesc_f16(fmt, 0, 0, 256);
+    static const int pf = getenv("CSN_DS_PREFETCH") == nullptr ? 0 : atoi(getenv("CSN_DS_PREFETCH"));
+    a.prefetch = pf;
+    if (wide == 2) return pair ? launch_ds_wide<2, 1>(tmQ, tmDO, tmK, tmV, tmDSw, a, s) : launch_ds_wide<1, 1>(tmQ, tmDO, tmK, tmV, tmDSw, a, s);   // diagnostics: no staging / stores
+    if (wide == 3) return pair ? launch_ds_wide<2, 2>(tmQ, tmDO, tmK, tmV, tmDSw, a, s) : launch_ds_wide<1, 2>(tmQ, tmDO, tmK, tmV, tmDSw, a, s);   // 3-deep ring, double-buffered slabs
+    return pair ? launch_ds_wide<2>(tmQ, tmDO, tmK, tmV, tmDSw, a, s) : launch_ds_wide<1>(tmQ, tmDO, tmK, tmV, tmDSw, a, s);
   }
   if (d_head == 256) return pair ? launch_dq<256, 2, false>(tmQ, tmDO, tmK, tmV, tmDS, tmDQ, a, s) : launch_dq<256, 1, false>(tmQ, tmDO, tmK, tmV, tmDS, tmDQ, a, s);
   return launch_dq<64, 1, false>(tmQ, tmDO, tmK, tmV, tmDS, tmDQ, a, s);
