@@ -40,5 +40,8 @@ struct AttnFwdArgs {
   int debug;          // experiments only (CSN_ATTN_DEBUG): bit 0 = skip the softmax arithmetic, bit 1 = skip the epilogue stores
 };
 
+// attn_wide.cu: d_head = 256 with [128 x 256] score tiles (mode 0 forward, mode 1 dV)
+int launch_attn_wide(int mode, bool pair, const CUtensorMap& tmQ, const CUtensorMap& tmK, const CUtensorMap& tmV,
+                     const CUtensorMap& tmO, const CUtensorMap& tmOlo, const AttnFwdArgs& a, cudaStream_t stream);
 
 }  // namespace csn

@@ -571,6 +571,16 @@ static int attn_launch_common(int mode, const void* Q, const void* K, const void
     if (rc) return rc;
   }
   const bool pair = items_pairable(n_items, d_head, paired);
+  if (mode == 1) CSN_CHECK_ARG(lse != nullptr, "csn_attn_bwd_dv: lse is required");
+  // [128 x 256] score tiles (attn_wide.cu): bit 0 = forward, bit 1 = dV.  Default: dV only (335 vs 363 us on the
+  // config-2 step); the wide forward kernel is correct but no faster than this file's (405 vs 406 us: its second
+  // output, the rounding residual of O, needs four staging slabs per warp where the P tile offers two).
+  static const int wide = getenv("CSN_ATTN_WIDE") == nullptr ? 2 : atoi(getenv("CSN_ATTN_WIDE"));
+  if (d_head == 256 && ((wide >> mode) & 1)) {
+    a.idesc_qk = umma_idesc_f16(fmt, 0, 0, 256);
+    a.idesc_pv = umma_idesc_f16(fmt, 0, 1, 256);
+    return launch_attn_wide(mode, pair, tmQ, tmK, tmV, tmO, tmOlo, a, s);
+  }
   if (mode == 0) {
     if (d_head == 256) return pair ? launch_attn_fwd<256, 0, 2>(tmQ, tmK, tmV, tmO, tmOlo, a, s) : launch_attn_fwd<256, 0, 1>(tmQ, tmK, tmV, tmO, tmOlo, a, s);
     return launch_attn_fwd<64, 0, 1>(tmQ, tmK, tmV, tmO, tmOlo, a, s);
