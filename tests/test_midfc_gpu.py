@@ -142,3 +142,39 @@ def test_fused_projection_layernorm_matches_separate_kernels(monkeypatch):
     # gradients pass through 16-bit intermediates: a last-bit difference in Z can flip a rounding
     for a, b, what, tol in zip(outs["1"], outs["0"], ("feats", "grad x", "grad w_qs"), (2e-5, 2e-4, 2e-4)):
         assert G.rel_err(a, b) < tol, (what, G.rel_err(a, b))
+
+
+def test_graphed_step_replays_the_eager_step():
+    """csn_b200.graphs.GraphedStep: a captured forward+loss+backward step gives the eager step's loss and
+    gradients, also after the static inputs have been overwritten in place."""
+    from csn_b200 import midfc
+    from csn_b200.graphs import GraphedStep
+    B, K, h, C = 1, 2, 1, 15
+    m = midfc.get_model("csa", C, h, K).cuda().eval()
+    m.load_state_dict(synth.midfc_state(5, h, C))
+    params = [p for n, p in m.named_parameters() if not n.startswith("fc_1")]
+    x0, nb0 = synth.csa_batch(21, B, K)
+    x1, nb1 = synth.csa_batch(22, B, K)
+    lab = _labels(23, B, x0.shape[2], C).cuda()
+
+    def step(x, nb, lab):
+        for p in params:
+            p.grad = None
+        loss = torch.nn.functional.cross_entropy(m(x, "test", nb), lab.unsqueeze(-1), ignore_index=0)
+        loss.backward()
+        return loss
+
+    def eager(x, nb):
+        loss = step(x.cuda(), nb.cuda(), lab)
+        return loss.item(), m.attention.w_qs.weight.grad.clone(), m.compatibility_q.weight.grad.clone()
+
+    want0, want1 = eager(x0, nb0), eager(x1, nb1)
+    xs, nbs = x0.cuda(), nb0.cuda()
+    g = GraphedStep(step, xs, nbs, lab)
+    assert g.launches > 20
+    for want, (x, nb) in ((want0, (x0, nb0)), (want1, (x1, nb1)), (want0, (x0, nb0))):
+        xs.copy_(x.cuda()); nbs.copy_(nb.cuda())
+        loss = g.replay()
+        assert abs(loss.item() - want[0]) < 1e-5
+        assert G.rel_err(m.attention.w_qs.weight.grad, want[1]) < 2e-4
+        assert G.rel_err(m.compatibility_q.weight.grad, want[2]) < 5e-2
