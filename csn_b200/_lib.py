@@ -79,13 +79,18 @@ class _Timed:
         e0.record()
         rc = self.fn(*args)
         e1.record()
-        flops = 0.0
+        flops = nbytes = 0.0
         if self.name == "csn_gemm":   # (A, B, D, M, N, K, nb[4], alpha, split_k, stream)
             nb = args[6]
-            flops = 2.0 * args[3] * args[4] * args[5] * nb[0] * nb[1] * nb[2] * nb[3]
-        elif self.name == "csn_gemm_res_ln":   # (A, B, Z, ldz, M, K, ...), N = 256
+            nbt = nb[0] * nb[1] * nb[2] * nb[3]
+            M, N, K = args[3], args[4], args[5]
+            flops = 2.0 * M * N * K * nbt
+            out_b = 4 if args[2]._obj.dtype == CSN_F32 else 2
+            nbytes = nbt * (2.0 * (M + N) * K + float(out_b) * M * N)   # operands once + output once (algorithmic)
+        elif self.name == "csn_gemm_res_ln":   # (A, B, Z, ldz, M, K, ...), N = 256: A + residual in, Z out
             flops = 2.0 * args[4] * 256 * args[5]
-        _PROFILE.append((self.name, e0, e1, flops))
+            nbytes = args[4] * (2.0 * args[5] + 4.0 * 256 + 4.0 * 256)
+        _PROFILE.append((self.name, e0, e1, flops, nbytes))
         return rc
 
 
@@ -104,11 +109,12 @@ def profile_end() -> dict:
     rec, _PROFILE = _PROFILE, None
     torch.cuda.synchronize()
     out: dict = {}
-    for name, e0, e1, fl in rec or []:
-        d = out.setdefault(name, {"ms": 0.0, "launches": 0, "flops": 0.0})
+    for name, e0, e1, fl, nby in rec or []:
+        d = out.setdefault(name, {"ms": 0.0, "launches": 0, "flops": 0.0, "bytes": 0.0})
         d["ms"] += e0.elapsed_time(e1)
         d["launches"] += 1
         d["flops"] += fl
+        d["bytes"] += nby
     return out
 
 
