@@ -40,3 +40,20 @@ def test_fused_matches_materialised(h):
         for name, x, y in zip(("y", "attn", "dx", "dWv", "dWq", "dWk"), a, other):
             rel = float((x - y).norm() / y.norm())
             assert rel < 4e-4, (name, rel)
+
+
+@pytest.mark.parametrize("env", [{"CSN_ATTN_WIDE": "3"},                          # 256-column tiles for forward AND dV
+                                 {"CSN_ATTN_WIDE": "0", "CSN_DS_WIDE": "0"},      # the 128-key kernels everywhere
+                                 {"CSN_CLUSTER": "0", "CSN_GEMM_CLUSTER": "0"}])  # no 2-CTA clusters / multicast
+def test_kernel_variants_match_materialised(env):
+    """The kernel-selection switches are read once per process, so every variant is checked against the
+    materialised path in its own interpreter."""
+    import subprocess
+    import sys
+    from pathlib import Path
+    root = Path(__file__).resolve().parents[1]
+    e = dict(os.environ)
+    e.update(env)
+    r = subprocess.run([sys.executable, "-m", "pytest", "-x", "-q", "-m", "gpu", str(Path(__file__)),
+                        "-k", "test_fused_matches_materialised"], cwd=root, env=e, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
