@@ -33,9 +33,12 @@ struct AttnCfg {
   // V tile (128 keys x DH), MN-major: slots of [KEYS_PER_VSLOT keys x DH columns]
   static constexpr int V_SLOTS = K_SLOTS;
   static constexpr int KEYS_PER_VSLOT = 128 / V_SLOTS;
+  // (tried for d_head 256: a 3-deep ring + 32 KB of extra output slabs, four per warp -> 426 vs 399 us: the ring
+  //  depth matters more than the slab waits; XSTG_BYTES > 0 re-enables that layout)
   static constexpr int NST = (DH >= 128) ? 4 : 8;
+  static constexpr int XSTG_BYTES = 0;
   static constexpr int BAR_BYTES = 256;
-  static constexpr int SMEM_BYTES = Q_BYTES + P_BYTES + NST * SLOT_BYTES + BAR_BYTES + 1024;
+  static constexpr int SMEM_BYTES = Q_BYTES + P_BYTES + NST * SLOT_BYTES + XSTG_BYTES + BAR_BYTES + 1024;
   static constexpr int O_COL = 256;                        // TMEM: S0 @0, S1 @128, O @256 (DH <= 256)
 };
 
@@ -50,8 +53,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   const uint32_t sQ = smem_u32(smem);
   const uint32_t sP = sQ + Cfg::Q_BYTES;
   const uint32_t sKV = sP + Cfg::P_BYTES;
-  const uint32_t bar_base = sKV + Cfg::NST * Cfg::SLOT_BYTES;
-  uint8_t* bar_ptr = smem + Cfg::Q_BYTES + Cfg::P_BYTES + Cfg::NST * Cfg::SLOT_BYTES;
+  const uint32_t sX = sKV + Cfg::NST * Cfg::SLOT_BYTES;   // extra output staging (d_head 256)
+  const uint32_t bar_base = sX + Cfg::XSTG_BYTES;
+  uint8_t* bar_ptr = smem + Cfg::Q_BYTES + Cfg::P_BYTES + Cfg::NST * Cfg::SLOT_BYTES + Cfg::XSTG_BYTES;
   auto kv_full = [&](int s) { return bar_base + 8u * s; };
   auto kv_empty = [&](int s) { return bar_base + 8u * (Cfg::NST + s); };
   const uint32_t bq_full = bar_base + 8u * (2 * Cfg::NST + 0);
@@ -448,8 +452,15 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         }
 #pragma unroll 1
         for (int which = 0; which < (want_lo ? 2 : 1); ++which) {
-          const uint32_t buf = sP + (slab & 1) * 16384 + q * 4096;
-          if (lane == 0) tma_store_wait_read<1>();
+          uint32_t buf;
+          if (Cfg::XSTG_BYTES > 0) {   // four slabs per warp: two in its rows of the P tile, two in the extra region
+            const int bi = slab & 3;
+            buf = (bi < 2 ? sP + bi * 16384 : sX + (bi - 2) * 16384) + q * 4096;
+            if (lane == 0) tma_store_wait_read<3>();
+          } else {
+            buf = sP + (slab & 1) * 16384 + q * 4096;
+            if (lane == 0) tma_store_wait_read<1>();
+          }
           __syncwarp();
           const uint32_t rowaddr = buf + lane * 128;
 #pragma unroll
