@@ -197,6 +197,12 @@ int csn_add_ln_fwd(float* Z, const float* R, const int32_t* res_block, float* Y,
                    void* stream);
 int csn_colsum_reduce(const float* part, float* out, int32_t n_blocks, int32_t parts, float scale, void* stream);
 
+/* The same contraction for plain problems (K-major A [M x K] and B [N x K], one batch, no split-K) on CTA PAIRS:
+ * one tcgen05.mma.cta_group::2 of M = 256 per two SMs, each CTA holding its 128 rows of A and half of every B
+ * slice (a 6-deep operand ring instead of 4, half the B operand read per SM).  lda / ldb / ldd in elements. */
+int csn_gemm_pair(const void* A, const void* B, void* D, int32_t M, int32_t N, int32_t K, int64_t lda, int64_t ldb,
+                  int64_t ldd, int32_t dtype, int32_t out_dtype, float alpha, void* stream);
+
 /* The output projection fused with the residual add and the LayerNorm statistics (csa_models.py:115-118 in one
  * pass): Z[m][0..256) = alpha * (A B^T)[m] + residual(m), mean[m] / rstd[m] = LayerNorm statistics of that row
  * (biased variance, eps inside the square root). Z (fp32, row-major, leading dimension ldz) is the only

@@ -39,6 +39,12 @@ CASES = {
     "perf_n64": (37888, 64, 4096, "f16", 0, 0, {"perf": True}),
     # shapes of the CSA training step (B=8, K=3): rows = 32 slots / 56 blocks x 10240
     "perf_8k_mn": (8192, 8192, 8192, "f16", 1, 1, {"perf": True}),
+    # CTA-pair kernel (cta_group::2)
+    "pair_small": (512, 512, 256, "f16", 0, 0, {"pair": True}),
+    "pair_ragged": (1000, 700, 320, "f16", 0, 0, {"pair": True}),
+    "pair_f16out": (768, 512, 512, "bf16", 0, 0, {"pair": True, "out": "bf16"}),
+    "pair_8k": (8192, 8192, 8192, "f16", 0, 0, {"pair": True, "perf": True}),
+    "pair_qkv": (327680, 768, 256, "f16", 0, 0, {"pair": True, "perf": True, "out": "f16"}),
     "perf_qkv": (327680, 768, 256, "f16", 0, 0, {"perf": True, "out": "f16"}),
     "perf_oproj": (573440, 256, 256, "f16", 0, 0, {"perf": True}),
     "perf_do": (573440, 256, 256, "f16", 0, 1, {"perf": True, "out": "f16"}),
@@ -93,7 +99,14 @@ def run_case(name: str) -> int:
     if split_k > 1:
         D.zero_()
     Dm = L.out(D, ld, transposed=tr, off=(M * N, M * N * nb[0], M * N * nb[0] * nb[1]), accumulate=split_k > 1)
-    L.gemm(Am, Bm, Dm, M, N, K, nb=nb, alpha=alpha, split_k=split_k)
+    def run():
+        if ex.get("pair"):
+            rc = L.lib().csn_gemm_pair(Ap.data_ptr(), Bp.data_ptr(), D.data_ptr(), M, N, K, K, K, N, L.dtype_code(dtype),
+                                       L.dtype_code(odt), alpha, L.stream_ptr())
+            L.check(rc, "csn_gemm_pair")
+        else:
+            L.gemm(Am, Bm, Dm, M, N, K, nb=nb, alpha=alpha, split_k=split_k)
+    run()
     torch.cuda.synchronize()
     got = D.float().cpu().double()
     if tr:
@@ -124,13 +137,13 @@ def run_case(name: str) -> int:
         print("  got[0,:4,:8]=\n", g0[:4, :8], "\n  ref[0,:4,:8]=\n", ref[0, :4, :8])
     if ex.get("perf"):
         for _ in range(3):
-            L.gemm(Am, Bm, Dm, M, N, K, nb=nb, alpha=alpha, split_k=split_k)
+            run()
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         iters = 10
         e0.record()
         for _ in range(iters):
-            L.gemm(Am, Bm, Dm, M, N, K, nb=nb, alpha=alpha, split_k=split_k)
+            run()
         e1.record()
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / iters
