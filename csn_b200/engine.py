@@ -56,6 +56,10 @@ class Group:
     v0: int
     v_si: int
     v_so: int
+    # ragged batches (MinkowskiNet: every shape has its own number of points): per block, in blocks() order, the
+    # number of real query rows / key rows; empty = the geometry's chunk / kv_len for every block
+    q_lens: tuple = ()
+    kv_lens: tuple = ()
 
     def blocks(self):
         for o in range(self.n_out):
@@ -136,22 +140,28 @@ def attn_items(groups, geom: Geometry, n_head: int, d: int, device, kind: str = 
     tiles = CP // 128
     rows = []
     for g in groups:
-        for (j, qs, ks, vs) in g.blocks():
+        for bi, (j, qs, ks, vs) in enumerate(g.blocks()):
             assert ks == vs, "fused attention reads K and V rows from the same slot"
+            q_len = g.q_lens[bi] if g.q_lens else geom.chunk       # real query rows per chunk of this block
+            kv_len = g.kv_lens[bi] if g.kv_lens else geom.kv_len   # real key rows
+            ragged = bool(g.q_lens or g.kv_lens)   # tiles that lie entirely in the padding are skipped: the caller
+                                                    # zero-initialises O / dQ|dK|dV / dS for ragged batches
             for c in range(NC):
                 for h in range(n_head):
                     for t_ in range(tiles):
-                        valid = max(0, min(128, geom.chunk - t_ * 128))      # query rows of tile t_
-                        kvalid = max(0, min(128, geom.kv_len - t_ * 128))    # key rows of tile t_
+                        valid = max(0, min(128, q_len - t_ * 128))      # query rows of tile t_
+                        kvalid = max(0, min(128, kv_len - t_ * 128))    # key rows of tile t_
                         stat = (j * n_head + h) * NP + c * CP
+                        if ragged and (kvalid if kind == "dv" else valid) == 0:
+                            continue
                         if kind == "fwd":
-                            rows.append((qs * NP + c * CP + t_ * 128, valid, ks * NP + c * CP, geom.kv_len,
+                            rows.append((qs * NP + c * CP + t_ * 128, valid, ks * NP + c * CP, kv_len,
                                          j * NP + c * CP + t_ * 128, h * d, stat + t_ * 128, 1, ks * NP + c * CP, 0))
                         elif kind == "dv":   # resident tile = keys; streamed = queries (Q view) and dO (block rows)
-                            rows.append((ks * NP + c * CP + t_ * 128, kvalid, qs * NP + c * CP, geom.chunk,
+                            rows.append((ks * NP + c * CP + t_ * 128, kvalid, qs * NP + c * CP, q_len,
                                          j * NP + c * CP + t_ * 128, h * d, stat, 1, j * NP + c * CP, 0))
                         else:                # dq
-                            rows.append((qs * NP + c * CP + t_ * 128, valid, ks * NP + c * CP, geom.kv_len,
+                            rows.append((qs * NP + c * CP + t_ * 128, valid, ks * NP + c * CP, kv_len,
                                          j * NP + c * CP + t_ * 128, h * d, stat + t_ * 128,
                                          ((j * NC + c) * n_head + h) * CP + t_ * 128, 0, 1, 0, 0))
     t = torch.tensor(rows, dtype=torch.int32).to(device)
@@ -235,13 +245,14 @@ def attention_forward(Xh, Xf, groups, n_slots, n_blocks, w_q, w_k, w_v, w_o, gam
     L.gemm(L.mat(Xh, L.MAJOR_K), L.mat(ctx.Wqkv16, L.MAJOR_K), L.out(QKV, 3 * HD), n_slots * NP, 3 * HD, 256)
     ctx.QKV = QKV
     Qv, Kv, Vv = QKV[:, :HD], QKV[:, HD:2 * HD], QKV[:, 2 * HD:]
-    O = torch.empty(n_blocks * NP, HD, dtype=dt, device=dev)
+    ragged = any(g.kv_lens or g.q_lens for g in groups)
+    O = (torch.zeros if ragged else torch.empty)(n_blocks * NP, HD, dtype=dt, device=dev)
     fused = use_fused_attention(d) and all(g.k0 == g.v0 and g.k_si == g.v_si and g.k_so == g.v_so for g in groups)
     if fused:
         # --- fused flash-style core (csa_models.py:139-142): scores never leave TMEM
         items = attn_items(groups, geom, n_head, d, dev)
         lse = torch.empty(n_blocks * n_head * NP, dtype=torch.float32, device=dev)
-        O_lo = torch.empty_like(O) if torch.is_grad_enabled() or save_for_backward else None
+        O_lo = (torch.zeros_like(O) if ragged else torch.empty_like(O)) if torch.is_grad_enabled() or save_for_backward else None
         rc = L.lib().csn_attn_fwd(Qv.data_ptr(), Kv.data_ptr(), Vv.data_ptr(), n_slots * NP, n_slots * NP, HD,
                                   3 * HD, 3 * HD, 3 * HD, d, L.dtype_code(dt), items.data_ptr(), items.shape[0],
                                   O.data_ptr(), O.shape[0], HD, lse.data_ptr(), O_lo.data_ptr() if O_lo is not None else None,
@@ -249,6 +260,8 @@ def attention_forward(Xh, Xf, groups, n_slots, n_blocks, w_q, w_k, w_v, w_o, gam
         L.check(rc, "csn_attn_fwd")
         ctx.extra["lse"] = lse
         ctx.extra["O_lo"] = O_lo
+    elif ragged:
+        raise L.CsnError("ragged blocks (per-block q_lens / kv_lens) need the fused attention kernels (d_head 64 or 256)")
     else:
         # --- materialised path: S = (Q K^T)/sqrt(d) -> softmax over the 500 valid keys -> O = P V
         Sbuf, P = _scores_and_probs(ctx_with(ctx, QKV))
@@ -406,7 +419,8 @@ def attention_backward(ctx: AttnContext, dY: torch.Tensor, need_dx: bool, amax: 
     L.gemm(L.mat(dZ16, L.MAJOR_K), L.mat(ctx.Wo16, L.MAJOR_MN), L.out(dO, HD), nblk * NP, HD, 256)
     Qv, Kv, Vv = ctx.QKV[:, :HD], ctx.QKV[:, HD:2 * HD], ctx.QKV[:, 2 * HD:]
     fused_bwd = ctx.P is None and "lse" in ctx.extra and os.environ.get("CSN_FUSED_BWD", "1") != "0"
-    dQKV = torch.empty(nblk * NP, 3 * HD, dtype=dt, device=dev)
+    ragged = any(g.kv_lens or g.q_lens for g in ctx.groups)
+    dQKV = (torch.zeros if ragged else torch.empty)(nblk * NP, 3 * HD, dtype=dt, device=dev)
     dQv, dKv, dVv = dQKV[:, :HD], dQKV[:, HD:2 * HD], dQKV[:, 2 * HD:]
     prow = NC * h * CP
     if fused_bwd:
@@ -423,10 +437,11 @@ def attention_backward(ctx: AttnContext, dY: torch.Tensor, need_dx: bool, amax: 
                                  lse.data_ptr(), _paired(geom), L.stream_ptr())
         L.check(rc, "csn_attn_bwd_dv")
         # the dQ kernel writes the key tiles it visits; columns beyond them must read as zeros in dS^T Q
-        alloc = torch.empty if ((geom.kv_len + 127) // 128) * 128 >= CP else torch.zeros
+        alloc = torch.empty if (((geom.kv_len + 127) // 128) * 128 >= CP and not ragged) else torch.zeros
         dS = alloc(nblk * prow, CP, dtype=dt, device=dev)
         it_dq = attn_items(ctx.groups, geom, h, d, dev, "dq")
-        fuse_dq = os.environ.get("CSN_FUSED_DQ", "0") == "1"   # dQ inside the kernel (slower: re-reads K_j)
+        # dQ inside the kernel: slower at d_head 256 (re-reads K_j through a shallow ring), faster at d_head 64
+        fuse_dq = os.environ.get("CSN_FUSED_DQ", "1" if d == 64 else "0") == "1"
         rc = lib.csn_attn_bwd_dq(Qv.data_ptr(), dO.data_ptr(), Kv.data_ptr(), Vv.data_ptr(), S * NP, nblk * NP, S * NP,
                                  HD, 3 * HD, HD, 3 * HD, 3 * HD, d, L.dtype_code(dt), it_dq.data_ptr(),
                                  it_dq.shape[0], dQv.data_ptr() if fuse_dq else None, 3 * HD, dS.data_ptr(),

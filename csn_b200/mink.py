@@ -86,6 +86,66 @@ class _MhaFullFn(torch.autograd.Function):
         return (dq, dk, None, g["dWq"], g["dWk"], g["dWv"], g["dWo"], g["dgamma"], g["dbeta"], None, None, None)
 
 
+class _MhaBlocksFn(torch.autograd.Function):
+    """A whole batch of MultiHeadAttention calls on RAGGED shapes in one pass of the kernels.
+
+    x_cat: (sum L_s, 256) rows of the distinct shapes s = 0..S-1 (lengths `lens`), concatenated;
+    pairs: tuple of (query shape, key/value shape).  Returns the concatenation over the pairs of
+    MHA(x_q, x_kv, x_kv) (attention.py:31-56), (sum_p L_q(p), 256).  Each shape is projected once; every pair
+    is one attention block with its own (L_q, L_kv) in the kernels' work tables (E.Group.q_lens / kv_lens)."""
+
+    @staticmethod
+    def forward(ctx, x_cat, wq, wk, wv, wo, gamma, beta, n_head, dt, lens, pairs):
+        _require_cuda(x_cat, "x")
+        _require_cuda(wq, "w_qs.weight")
+        dev = x_cat.device
+        S, P = len(lens), len(pairs)
+        n_pad = (max(lens) + 127) // 128 * 128
+        # rows of shape s live in slot s (n_pad rows, zero padded)
+        offs = [0]
+        for n in lens:
+            offs.append(offs[-1] + n)
+        slot_rows = torch.cat([torch.arange(n, dtype=torch.int64) + s * n_pad for s, n in enumerate(lens)]).to(dev, non_blocking=True)
+        Xf = torch.zeros(S * n_pad, 256, dtype=torch.float32, device=dev)
+        Xf[slot_rows] = x_cat.float()
+        Xh = Xf.to(dt)
+        geom = E.Geometry(chunk=n_pad, n_chunks=1, chunk_pad=n_pad, kv_chunk=n_pad)
+        # runs of pairs whose (query, key) slots advance with constant strides become one group each, so that the
+        # batched GEMMs of the backward pass stay batched (SSA of S shapes: one run; K*B cross blocks: K runs)
+        groups = []
+        j = 0
+        while j < P:
+            n = 1
+            if j + 1 < P:
+                dq, dk = pairs[j + 1][0] - pairs[j][0], pairs[j + 1][1] - pairs[j][1]
+                while j + n < P and (pairs[j + n][0] - pairs[j + n - 1][0], pairs[j + n][1] - pairs[j + n - 1][1]) == (dq, dk):
+                    n += 1
+            else:
+                dq = dk = 0
+            if n == 1:
+                dq = dk = 0
+            groups.append(E.Group(n_in=n, n_out=1, blk0=j, q0=pairs[j][0], q_si=dq, q_so=0, k0=pairs[j][1], k_si=dk, k_so=0,
+                                  v0=pairs[j][1], v_si=dk, v_so=0,
+                                  q_lens=tuple(lens[q] for q, _ in pairs[j:j + n]), kv_lens=tuple(lens[k] for _, k in pairs[j:j + n])))
+            j += n
+        a = E.attention_forward(Xh, Xf, groups, S, P, wq, wk, wv, wo, gamma, beta, geom, n_head, want_colsum=False)
+        out_rows = torch.cat([torch.arange(lens[qs], dtype=torch.int64) + j * n_pad for j, (qs, _) in enumerate(pairs)]).to(dev, non_blocking=True)
+        ctx.a = a
+        ctx.meta = (S, P, n_pad, slot_rows, out_rows)
+        return a.Y[out_rows]
+
+    @staticmethod
+    def backward(ctx, dout):
+        a = ctx.a
+        S, P, n_pad, slot_rows, out_rows = ctx.meta
+        dY = torch.zeros(P * n_pad, 256, dtype=torch.float32, device=dout.device)
+        dY[out_rows] = dout.float()
+        need_dx = ctx.needs_input_grad[0]
+        g = E.attention_backward(a, dY, need_dx)
+        dx = g["dX"][slot_rows] if need_dx else None
+        return (dx, g["dWq"], g["dWk"], g["dWv"], g["dWo"], g["dgamma"], g["dbeta"], None, None, None, None)
+
+
 def _full_attn(a: E.AttnContext, B: int, Lq: int, Lk: int) -> torch.Tensor:
     """(B, h, Lq, Lk) attention matrix, materialised on request only (it defeats the fused kernel's
     purpose; both reference callers discard it: hrnet.py:407,463)."""
@@ -134,6 +194,17 @@ class MultiHeadAttention(nn.Module):
                                      self.return_attn)
         return out, (attn if self.return_attn else None)
 
+    def forward_blocks(self, shapes, pairs):
+        """Batched form of `forward` for ragged inputs: shapes = list of (L_s, 256) feature tensors, pairs = list
+        of (query shape index, key/value shape index).  Returns [MHA(shapes[q][None], shapes[k][None],
+        shapes[k][None])[0][0] for (q, k) in pairs], computed in ONE pass of the kernels (each shape projected
+        once, every pair one attention block) instead of len(pairs) module calls."""
+        lens = tuple(int(t.shape[0]) for t in shapes)
+        y = _MhaBlocksFn.apply(torch.cat(list(shapes), dim=0), self.w_qs.weight, self.w_ks.weight, self.w_vs.weight,
+                               self.fc.weight, self.norm.weight, self.norm.bias, self.n_head, _PRECISIONS[self.precision],
+                               lens, tuple((int(a), int(b)) for a, b in pairs))
+        return list(torch.split(y, [lens[q] for q, _ in pairs], dim=0))
+
 
 class ScaledDotProduct(nn.Module):
     """attention.py:78-113 on dense inputs: (q k^T) / temperature.  Operands here are 256-d global
@@ -173,17 +244,22 @@ class CSAHead(nn.Module):
         self.sim = ScaledDotProduct(d_model ** 0.5)
 
     def get_SSA(self, feats):
-        """hrnet.py:456-470 over a list of (L_b, 256) tensors."""
-        return [self.MHA(f[None], f[None], f[None])[0][0] for f in feats]
+        """hrnet.py:456-470 over a list of (L_b, 256) tensors (one batched pass)."""
+        feats = list(feats)
+        return self.MHA.forward_blocks(feats, [(i, i) for i in range(len(feats))])
 
-    def forward(self, query_feats, key_feats=None, return_ssa=False):
+    def forward(self, query_feats, key_feats=None, return_ssa=False, batched=True):
         """CSA block of HRNetSimCSN.forward (hrnet.py:370-417). query_feats: list over batch items of
         (L_b, 256); key_feats: list over the K neighbours of such lists. Returns the list of CSA
-        features per batch item (the SSA features when key_feats is empty / return_ssa)."""
-        q_ssa = self.get_SSA(query_feats)
+        features per batch item (the SSA features when key_feats is empty / return_ssa).
+        batched=True runs the (1+2K)B attention calls of the block as ONE ragged batch of the kernels;
+        batched=False is the reference's call-by-call loop (kept for the parity tests)."""
+        if batched:
+            return self._forward_batched(list(query_feats), [list(kf) for kf in (key_feats or [])], return_ssa)
+        q_ssa = [self.MHA(f[None], f[None], f[None])[0][0] for f in query_feats]
         if return_ssa or not key_feats:
             return q_ssa
-        keys_ssa = [q_ssa] + [self.get_SSA(kf) for kf in key_feats]
+        keys_ssa = [q_ssa] + [[self.MHA(f[None], f[None], f[None])[0][0] for f in kf] for kf in key_feats]
         out = []
         for b, ssa_b in enumerate(q_ssa):
             g_q = F.normalize(self.linear_q(ssa_b.mean(dim=0)), dim=-1)
@@ -196,6 +272,28 @@ class CSAHead(nn.Module):
             for i, kf in enumerate(key_feats):
                 cross, _ = self.MHA(query_feats[b][None], kf[b][None], kf[b][None])
                 csa = csa + comp[i + 1] * cross[0]
+            out.append(csa)
+        return out
+
+    def _forward_batched(self, query_feats, key_feats, return_ssa):
+        B, K = len(query_feats), len(key_feats)
+        if return_ssa or K == 0:
+            return self.get_SSA(query_feats)
+        # shapes: [q_0..q_{B-1}, k^1_0..k^1_{B-1}, ..., k^K_0..]; blocks: SSA of every shape, then the K*B cross blocks
+        shapes = query_feats + [f for kf in key_feats for f in kf]
+        pairs = [(s, s) for s in range(len(shapes))] + [(b, B * (i + 1) + b) for i in range(K) for b in range(B)]
+        ys = self.MHA.forward_blocks(shapes, pairs)
+        n_s = len(shapes)
+        pooled = torch.stack([y.mean(dim=0) for y in ys[:n_s]])                       # (B(K+1), 256)
+        g_q = F.normalize(self.linear_q(pooled[:B]), dim=-1)                          # (B, 256)
+        g_k = F.normalize(self.linear_k(pooled), dim=-1).view(K + 1, B, 256)          # [i][b]
+        sims = torch.einsum("bd,ibd->bi", g_q, g_k) / self.sim.temperature           # (B, K+1)
+        comp = F.softmax(sims, dim=1)
+        out = []
+        for b in range(B):
+            csa = comp[b, 0] * ys[b]
+            for i in range(K):
+                csa = csa + comp[b, i + 1] * ys[n_s + i * B + b]
             out.append(csa)
         return out
 

@@ -72,3 +72,30 @@ def test_csa_head_against_oracle():
     assert abs(sim - O.mink_cosine_similarity(qf[0], kf[0][1]).item()) < 1e-5
     s = torch.tensor([0.1, 0.9, 0.5, 0.7]).cuda()
     assert mink.topk_neighbors(s, 2, self_index=1).tolist() == O.mink_topk_neighbors(s.cpu(), 2, self_index=1).tolist()
+
+
+def test_batched_csa_head_matches_call_by_call_loop():
+    """The ragged one-pass batch (MultiHeadAttention.forward_blocks: per-block lengths in the kernels' work
+    tables) against the reference's call-by-call loop: outputs, input gradients, weight gradients."""
+    from csn_b200 import mink
+    h = 4
+    head = mink.CSAHead(256, h).cuda().eval()
+    head.load_state_dict(synth.mink_state(11, h))
+    gen = synth.gen(12)
+    lens_q, lens_k = [300, 77, 512], [[129, 260, 40], [333, 128, 700]]
+    res = {}
+    for batched in (True, False):
+        g2 = synth.gen(12)
+        qf = [torch.relu(torch.randn(n, 256, generator=g2)).cuda().requires_grad_(True) for n in lens_q]
+        kf = [[torch.relu(torch.randn(n, 256, generator=g2)).cuda().requires_grad_(True) for n in ln] for ln in lens_k]
+        head.zero_grad()
+        out = head(qf, kf, batched=batched)
+        sum((o * torch.linspace(-1, 1, 256, device="cuda")).sum() for o in out).backward()
+        res[batched] = ([o.detach() for o in out], [t.grad.clone() for t in qf] + [t.grad.clone() for lst in kf for t in lst],
+                        head.MHA.w_qs.weight.grad.clone(), head.MHA.fc.weight.grad.clone(), head.linear_k.weight.grad.clone())
+    for a, b in zip(res[True][0], res[False][0]):
+        assert G.rel_err(a, b) < 2e-4
+    for a, b in zip(res[True][1], res[False][1]):
+        assert G.rel_err(a, b) < 1e-3
+    for a, b in zip(res[True][2:], res[False][2:]):
+        assert G.rel_err(a, b) < 1e-3
