@@ -87,6 +87,9 @@ class _Timed:
             flops = 2.0 * M * N * K * nbt
             out_b = 4 if args[2]._obj.dtype == CSN_F32 else 2
             nbytes = nbt * (2.0 * (M + N) * K + float(out_b) * M * N)   # operands once + output once (algorithmic)
+        elif self.name == "csn_gemm_delta":   # (A, B, dO, lddo, M, N, K, ...): A + O + O_lo in, dO out (16-bit)
+            flops = 2.0 * args[4] * args[5] * args[6]
+            nbytes = args[4] * (2.0 * args[6] + 3 * 2.0 * args[5])
         elif self.name == "csn_gemm_res_ln":   # (A, B, Z, ldz, M, K, ...), N = 256: A + residual in, Z out
             flops = 2.0 * args[4] * 256 * args[5]
             nbytes = args[4] * (2.0 * args[5] + 4.0 * 256 + 4.0 * 256)
@@ -141,6 +144,8 @@ _EXTRA_SIGNATURES: dict[str, list] = {
     "csn_gemm_res_ln": [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_float, C.c_void_p,
                         C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32,
                         C.c_int32, C.c_int32, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p],
+    "csn_gemm_delta": [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_float,
+                       C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p],
     "csn_gemm_pair": [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int64, C.c_int64,
                       C.c_int64, C.c_int32, C.c_int32, C.c_float, C.c_void_p],
     "csn_ln_colsum": [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32,

@@ -51,6 +51,11 @@ struct GemmArgs {
   int block_rows, group_rows, rows_valid, n_points;
   float eps;
   float* mean; float* rstd;
+  // fused delta epilogue (csn_gemm_delta): D = dO (16-bit), delta[(blk*n_head + head)*rows_pad + r] = rowsum_head(dO o (O + O_lo/scale))
+  int dl;
+  float* delta;
+  int dl_rows_pad, dl_n_head, dl_d_head;
+  float dl_lo_inv;   // 1/2048 (fp16) or 1/256 (bf16); 0 when there is no O_lo
   int debug;   // CSN_GEMM_DEBUG (diagnostics only): 1 = epilogue drains TMEM but stores nothing
 };
 
@@ -158,7 +163,7 @@ __device__ __forceinline__ void store_chunk(const GemmArgs& p, long long base, i
   }
 }
 
-template <int BN, bool A_MN, bool B_MN, int CL, bool LN = false>
+template <int BN, bool A_MN, bool B_MN, int CL, bool LN = false, bool DL = false>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
             const __grid_constant__ CUtensorMap tmD, const __grid_constant__ CUtensorMap tmR0,
@@ -196,7 +201,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       mbar_init(tfull_bar(a), 1);
       mbar_init(tempty_bar(a), p.tempty_count);
     }
-    if (LN) for (int i = 0; i < 16; ++i) mbar_init(bar_base + 256 + 8u * i, 1);   // residual slabs: (up to) 8 warps x 2
+    if (LN || DL) for (int i = 0; i < 16; ++i) mbar_init(bar_base + 256 + 8u * i, 1);   // epilogue operand slabs: (up to) 8 warps x 2
     fence_mbar_init();
   }
   if (warp == 2) {
@@ -314,6 +319,18 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       c.mt = c.mt * CL + rank;
       const int kb0 = c.ks * p.kb_per_split;
       const bool has_k = kb0 < p.kb_total;
+      if (DL && lane == 0) {
+        // delta epilogue: the first two O / O_lo slabs of this tile are requested before waiting for the accumulator
+        const int prow0 = c.mt * GEMM_BM + q * 32, pn0 = c.nt * BN;
+        const int pn_units = min(BN / 64, (p.N - pn0 + 63) / 64);
+        const uint32_t pbuf = stg_base + ew * 6 * 4096;
+        for (int u = 0; u < 2 && u < pn_units; ++u) {
+          const uint32_t bar = bar_base + 256 + 8u * (ew * 2 + u);
+          mbar_arrive_expect_tx(bar, p.dl_lo_inv != 0.f ? 8192 : 4096);
+          tma_load_2d(pbuf + (2 + u) * 4096, &tmR0, bar, pn0 + u * 64, prow0);
+          if (p.dl_lo_inv != 0.f) tma_load_2d(pbuf + (4 + u) * 4096, &tmR1, bar, pn0 + u * 64, prow0);
+        }
+      }
       mbar_wait(tfull_bar(acc), acc_ph);
       tc_fence_after();
       const int row = c.mt * GEMM_BM + q * 32 + lane;
@@ -321,6 +338,88 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       const long long base = c.b0 * p.d_off[0] + c.b1 * p.d_off[1] + c.b2 * p.d_off[2] + c.b3 * p.d_off[3];
       const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + acc * BN;
       if (p.debug & 1) {
+      } else if (DL) {
+        // dO tile (16-bit out) fused with delta = rowsum_head(dO o O): the thread owns its row; O (and its rounding
+        // residual O_lo) arrive as warp-private [32 rows x 64 cols] TMA boxes two 64-column units ahead (issued before
+        // the wait for the accumulator, so they load under the MMAs).  Per warp: slabs 0,1 output staging, 2,3 O,
+        // 4,5 O_lo.  delta is formed from the ROUNDED dO, the value every later kernel sees.
+        const int row0 = c.mt * GEMM_BM + q * 32;
+        const uint32_t wbuf = stg_base + ew * 6 * 4096;
+        const uint32_t rbar0 = bar_base + 256 + 8u * (ew * 2);
+        const bool has_lo = p.dl_lo_inv != 0.f;
+        const int n_units = min(BN / 64, (p.N - n0 + 63) / 64);
+        auto fetch_o = [&](int u) {   // lane 0 only
+          const uint32_t bar = rbar0 + 8u * (u & 1);
+          mbar_arrive_expect_tx(bar, has_lo ? 8192 : 4096);
+          tma_load_2d(wbuf + (2 + (u & 1)) * 4096, &tmR0, bar, n0 + u * 64, row0);
+          if (has_lo) tma_load_2d(wbuf + (4 + (u & 1)) * 4096, &tmR1, bar, n0 + u * 64, row0);
+        };
+        const int blk = row / p.dl_rows_pad, rin = row - blk * p.dl_rows_pad;
+        const bool f16 = p.out_dtype == CSN_F16;
+        const float al = p.alpha;
+        float dsum = 0.f;
+        const int units_per_head = p.dl_d_head / 64;
+#pragma unroll 1
+        for (int u = 0; u < n_units; ++u) {
+          uint32_t r0[32], r1[32];
+          tmem_ld_32x32(taddr + u * 64, r0);
+          tmem_ld_32x32(taddr + u * 64 + 32, r1);
+          tmem_ld_wait();
+          uint32_t w[32];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            w[j] = pack16(__uint_as_float(r0[2 * j]) * al, __uint_as_float(r0[2 * j + 1]) * al, p.out_dtype);
+            w[16 + j] = pack16(__uint_as_float(r1[2 * j]) * al, __uint_as_float(r1[2 * j + 1]) * al, p.out_dtype);
+          }
+          mbar_wait(rbar0 + 8u * (u & 1), (res_ph >> (u & 1)) & 1u);
+          res_ph ^= 1u << (u & 1);
+          const uint32_t so = wbuf + (2 + (u & 1)) * 4096 + lane * 128, sl = wbuf + (4 + (u & 1)) * 4096 + lane * 128;
+#pragma unroll
+          for (int ch = 0; ch < 8; ++ch) {
+            const uint32_t sw = (((uint32_t)ch ^ ((uint32_t)lane & 7u)) << 4);
+            uint32_t o4[4], l4[4] = {0u, 0u, 0u, 0u};
+            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(o4[0]), "=r"(o4[1]), "=r"(o4[2]), "=r"(o4[3]) : "r"(so + sw));
+            if (has_lo) asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(l4[0]), "=r"(l4[1]), "=r"(l4[2]), "=r"(l4[3]) : "r"(sl + sw));
+#pragma unroll
+            for (int t2 = 0; t2 < 4; ++t2) {
+              float2 dv, ov, lv;
+              const uint32_t dw = w[ch * 4 + t2];
+              if (f16) {
+                dv = __half22float2(*reinterpret_cast<const __half2*>(&dw));
+                ov = __half22float2(*reinterpret_cast<const __half2*>(&o4[t2]));
+                lv = __half22float2(*reinterpret_cast<const __half2*>(&l4[t2]));
+              } else {
+                dv = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&dw));
+                ov = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&o4[t2]));
+                lv = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&l4[t2]));
+              }
+              dsum += dv.x * (ov.x + lv.x * p.dl_lo_inv) + dv.y * (ov.y + lv.y * p.dl_lo_inv);
+            }
+          }
+          __syncwarp();
+          if (lane == 0 && u + 2 < n_units) fetch_o(u + 2);
+          if ((u + 1) % units_per_head == 0) {
+            const int head = (n0 + u * 64) / p.dl_d_head;
+            if (row < p.M) p.delta[((long long)blk * p.dl_n_head + head) * p.dl_rows_pad + rin] = dsum;
+            dsum = 0.f;
+          }
+          const uint32_t buf = wbuf + stg_flip * 4096;
+          if (lane == 0) tma_store_wait_read<1>();
+          __syncwarp();
+          const uint32_t rowaddr = buf + lane * 128;
+#pragma unroll
+          for (int ch = 0; ch < 8; ++ch) {
+            const uint32_t a = rowaddr + (((uint32_t)ch ^ ((uint32_t)lane & 7u)) << 4);
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(w[4 * ch]), "r"(w[4 * ch + 1]), "r"(w[4 * ch + 2]), "r"(w[4 * ch + 3]) : "memory");
+          }
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0 && row0 < p.M) {
+            tma_store_2d(&tmD, buf, n0 + u * 64, row0);
+            tma_store_commit();
+          }
+          stg_flip ^= 1;
+        }
       } else if (LN) {
         // Fused residual + LayerNorm statistics (BN == N == 256: the thread owns its whole output row).
         // z = alpha*acc + residual.  The residual comes from the reference's channel-major fp32 tensors: a
@@ -518,12 +617,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   }
 }
 
-template <int BN, bool A_MN, bool B_MN, int CL, bool LN = false>
+template <int BN, bool A_MN, bool B_MN, int CL, bool LN = false, bool DL = false>
 static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmD,
                        const GemmArgs& args, cudaStream_t stream, const CUtensorMap* tmR0 = nullptr,
                        const CUtensorMap* tmR1 = nullptr) {
   using Cfg = GemmCfg<BN>;
-  auto kern = gemm_kernel<BN, A_MN, B_MN, CL, LN>;
+  auto kern = gemm_kernel<BN, A_MN, B_MN, CL, LN, DL>;
   static bool configured = false;
   if (!configured) {
     CSN_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
@@ -563,11 +662,15 @@ struct LnEpilogue {
   long long res_ld; int block_rows, group_rows, rows_valid, n_points; float eps; float* mean; float* rstd;
 };
 
+struct DeltaEpilogue {
+  const void* O; const void* O_lo; long long ldo; long long o_rows; float* delta; int rows_pad, n_head, d_head;
+};
+
 }  // namespace csn
 
 static int gemm_impl(const csn_mat* A, const csn_mat* B, const csn_out* D, int32_t M, int32_t N,
                      int32_t K, const int32_t nb[4], float alpha, int32_t split_k, void* stream,
-                     const csn::LnEpilogue* ln) {
+                     const csn::LnEpilogue* ln, const csn::DeltaEpilogue* dl = nullptr) {
   using namespace csn;
   clear_error();
   CSN_CHECK_ARG(A && B && D && nb, "csn_gemm: null argument");
@@ -659,6 +762,32 @@ static int gemm_impl(const csn_mat* A, const csn_mat* B, const csn_out* D, int32
     g.tempty_count = 32 * g.epi_warps;
   }
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  if (dl) {
+    const long long nbt = (long long)nb[0] * nb[1] * nb[2] * nb[3];
+    CSN_CHECK_ARG(BN == 256 && !a_mn && nbt == 1 && split_k == 1 && D->dtype != CSN_F32 && g.tma_store,
+                  "csn_gemm_delta: needs N > 128, a K-major A, one batch, a 16-byte aligned row-major 16-bit dO");
+    CSN_CHECK_ARG((dl->d_head == 64 || dl->d_head == 256) && N == dl->n_head * dl->d_head && dl->rows_pad % 32 == 0,
+                  "csn_gemm_delta: d_head must be 64 or 256, N = n_head*d_head, rows_pad a multiple of 32");
+    CUtensorMap tmO, tmOlo;
+    rc = make_tmap_2d(&tmO, dl->O, D->dtype, N, dl->o_rows, dl->ldo, 64, 32);
+    if (rc) return rc;
+    tmOlo = tmO;
+    if (dl->O_lo) {
+      rc = make_tmap_2d(&tmOlo, dl->O_lo, D->dtype, N, dl->o_rows, dl->ldo, 64, 32);
+      if (rc) return rc;
+    }
+    g.dl = 1;
+    g.delta = dl->delta; g.dl_rows_pad = dl->rows_pad; g.dl_n_head = dl->n_head; g.dl_d_head = dl->d_head;
+    g.dl_lo_inv = dl->O_lo ? (D->dtype == CSN_F16 ? 1.f / 2048.f : 1.f / 256.f) : 0.f;
+    // the thread owns its whole row: 4 epilogue warps, per warp 2 output + 2 O + 2 O_lo slabs (96 KB) next to a 2-deep ring
+    g.stages = 2; g.stg_bufs = 6; g.epi_warps = 4; g.alt_tiles = 0; g.tempty_count = 128;
+    if (b_mn) {
+      if (CL == 2) return launch_gemm<256, false, true, 2, false, true>(tmA, tmB, tmD, g, s, &tmO, &tmOlo);
+      return launch_gemm<256, false, true, 1, false, true>(tmA, tmB, tmD, g, s, &tmO, &tmOlo);
+    }
+    if (CL == 2) return launch_gemm<256, false, false, 2, false, true>(tmA, tmB, tmD, g, s, &tmO, &tmOlo);
+    return launch_gemm<256, false, false, 1, false, true>(tmA, tmB, tmD, g, s, &tmO, &tmOlo);
+  }
   if (ln) {
     const long long nbt = (long long)nb[0] * nb[1] * nb[2] * nb[3];
     CSN_CHECK_ARG(N == 256 && !a_mn && !b_mn && nbt == 1 && split_k == 1 && D->dtype == CSN_F32 && g.tma_store,
@@ -711,4 +840,18 @@ extern "C" int csn_gemm_res_ln(const csn_mat* A, const csn_mat* B, float* Z, int
                 block_rows, group_rows, rows_valid, n_points, eps, mean, rstd};
   const int32_t nb[4] = {1, 1, 1, 1};
   return gemm_impl(A, B, &D, M, 256, K, nb, alpha, 1, stream, &ln);
+}
+
+extern "C" int csn_gemm_delta(const csn_mat* A, const csn_mat* B, void* dO, int64_t lddo, int32_t M, int32_t N, int32_t K,
+                              float alpha, const void* O, const void* O_lo, int64_t ldo, float* delta,
+                              int32_t rows_pad, int32_t n_head, int32_t d_head, void* stream) {
+  using namespace csn;
+  clear_error();
+  CSN_CHECK_ARG(A && B && dO && O && delta, "csn_gemm_delta: null pointer");
+  csn_out D;
+  memset(&D, 0, sizeof(D));
+  D.ptr = dO; D.dtype = A->dtype; D.ld = lddo;
+  DeltaEpilogue dl{O, O_lo, ldo, (long long)M, delta, rows_pad, n_head, d_head};
+  const int32_t nb[4] = {1, 1, 1, 1};
+  return gemm_impl(A, B, &D, M, N, K, nb, alpha, 1, stream, nullptr, &dl);
 }

@@ -414,9 +414,21 @@ def attention_backward(ctx: AttnContext, dY: torch.Tensor, need_dx: bool, amax: 
     dWo = torch.zeros(256, HD, dtype=torch.float32, device=dev)
     L.gemm(L.mat(dZ16, L.MAJOR_MN), L.mat(ctx.O, L.MAJOR_MN), L.out(dWo, HD, accumulate=True), 256, HD, nblk * NP,
            split_k=split)
-    # --- dO = dZ Wo
+    # --- dO = dZ Wo; on the fused path the same kernel also forms delta = rowsum(dO o O) per (row, head)
     dO = torch.empty(nblk * NP, HD, dtype=dt, device=dev)
-    L.gemm(L.mat(dZ16, L.MAJOR_K), L.mat(ctx.Wo16, L.MAJOR_MN), L.out(dO, HD), nblk * NP, HD, 256)
+    fused_delta = (ctx.P is None and "lse" in ctx.extra and os.environ.get("CSN_FUSED_BWD", "1") != "0"
+                   and HD > 128 and os.environ.get("CSN_FUSED_DELTA", "1") != "0")
+    delta = None
+    if fused_delta:
+        delta = torch.empty_like(ctx.extra["lse"])
+        O_lo = ctx.extra.get("O_lo")
+        Am, Bm = L.mat(dZ16, L.MAJOR_K), L.mat(ctx.Wo16, L.MAJOR_MN)
+        rc = lib.csn_gemm_delta(C.byref(Am), C.byref(Bm), dO.data_ptr(), HD, nblk * NP, HD, 256, 1.0, ctx.O.data_ptr(),
+                                O_lo.data_ptr() if O_lo is not None else None, HD, delta.data_ptr(), NP, h, d,
+                                L.stream_ptr())
+        L.check(rc, "csn_gemm_delta")
+    else:
+        L.gemm(L.mat(dZ16, L.MAJOR_K), L.mat(ctx.Wo16, L.MAJOR_MN), L.out(dO, HD), nblk * NP, HD, 256)
     Qv, Kv, Vv = ctx.QKV[:, :HD], ctx.QKV[:, HD:2 * HD], ctx.QKV[:, 2 * HD:]
     fused_bwd = ctx.P is None and "lse" in ctx.extra and os.environ.get("CSN_FUSED_BWD", "1") != "0"
     ragged = any(g.kv_lens or g.q_lens for g in ctx.groups)
@@ -426,11 +438,12 @@ def attention_backward(ctx: AttnContext, dY: torch.Tensor, need_dx: bool, amax: 
     if fused_bwd:
         # --- fused attention backward: delta, dV (P^T rebuilt from lse), dQ (+ dS to HBM), dK = dS^T Q
         lse = ctx.extra["lse"]
-        delta = torch.empty_like(lse)
-        O_lo = ctx.extra.get("O_lo")
-        rc = lib.csn_attn_delta(dO.data_ptr(), ctx.O.data_ptr(), O_lo.data_ptr() if O_lo is not None else None,
-                                delta.data_ptr(), nblk * NP, NP, h, d, HD, L.dtype_code(dt), L.stream_ptr())
-        L.check(rc, "csn_attn_delta")
+        if delta is None:
+            delta = torch.empty_like(lse)
+            O_lo = ctx.extra.get("O_lo")
+            rc = lib.csn_attn_delta(dO.data_ptr(), ctx.O.data_ptr(), O_lo.data_ptr() if O_lo is not None else None,
+                                    delta.data_ptr(), nblk * NP, NP, h, d, HD, L.dtype_code(dt), L.stream_ptr())
+            L.check(rc, "csn_attn_delta")
         it_dv = attn_items(ctx.groups, geom, h, d, dev, "dv")
         rc = lib.csn_attn_bwd_dv(Kv.data_ptr(), Qv.data_ptr(), dO.data_ptr(), S * NP, S * NP, nblk * NP, HD, 3 * HD, 3 * HD, HD,
                                  d, L.dtype_code(dt), it_dv.data_ptr(), it_dv.shape[0], dVv.data_ptr(), nblk * NP, 3 * HD,

@@ -220,6 +220,14 @@ int csn_gemm_res_ln(const csn_mat* A, const csn_mat* B, float* Z, int64_t ldz, i
                     const int32_t* res_sel, const int32_t* res_row, int64_t res_ld, int32_t n_points,
                     int32_t block_rows, int32_t group_rows, int32_t rows_valid, float eps, float* mean,
                     float* rstd, void* stream);
+/* dO = alpha * A B^T (16-bit, [M x N], N = n_head*d_head) fused with the attention backward's
+ * delta[(blk*n_head + head)*rows_pad + r] = sum_c dO[m][head*d + c] * (O[m][head*d + c] + O_lo[..]/2^11 (fp16) or /2^8 (bf16)),
+ * m = blk*rows_pad + r: the row-wise dot product that csn_attn_delta computes in a separate pass over dO, O and
+ * O_lo (autograd of csa_models.py:115,142).  O / O_lo: 16-bit row-major [M x N] with leading dimension ldo, O_lo
+ * may be NULL.  A: K-major [M x K]; B: [N x K] in either major; d_head 64 or 256. */
+int csn_gemm_delta(const csn_mat* A, const csn_mat* B, void* dO, int64_t lddo, int32_t M, int32_t N, int32_t K,
+                   float alpha, const void* O, const void* O_lo, int64_t ldo, float* delta, int32_t rows_pad,
+                   int32_t n_head, int32_t d_head, void* stream);
 /* colsum[(row/64)][c] = sum over the valid rows of the 64-row group of (Z - mean)*rstd*gamma + beta: the partials
  * csn_colsum_reduce turns into the pooled means, for rows whose statistics came from csn_gemm_res_ln. */
 int csn_ln_colsum(const float* Z, const float* mean, const float* rstd, const float* gamma, const float* beta,
