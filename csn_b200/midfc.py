@@ -281,7 +281,9 @@ class _CsaFn(torch.autograd.Function):
         # the residual of the output projection is read straight from these channel-major tensors by the fused
         # projection/LayerNorm kernel (slot s = b*(K+1)+j: j = 0 the query, j >= 1 neighbour j)
         res_cm = None
-        if K == 0 or nbs.shape[3] == xs.shape[2]:
+        # (TMA needs 16-byte aligned rows: point counts that are not multiples of 4 take the unfused path)
+        tma_ok = xs.shape[2] % 4 == 0 and xs.data_ptr() % 16 == 0 and (nbs is None or nbs.data_ptr() % 16 == 0)
+        if tma_ok and (K == 0 or nbs.shape[3] == xs.shape[2]):
             sel = tuple(0 if j == 0 else 1 for b in range(B) for j in range(K + 1))
             off = tuple(b * xs.stride(0) if j == 0 else b * nbs.stride(0) + j * nbs.stride(1)
                         for b in range(B) for j in range(K + 1))

@@ -25,6 +25,9 @@ CASES = {
     "mnB": (256, 256, 256, "f16", 0, 1, {}),
     "mnAB": (384, 192, 448, "f16", 1, 1, {}),
     "mnB_n64": (128, 64, 512, "f16", 0, 1, {}),
+    "mnAB_n320": (384, 320, 448, "f16", 1, 1, {}),
+    "mnAB_n512": (256, 512, 256, "f16", 1, 1, {}),
+    "mnAB_m128": (128, 320, 448, "f16", 1, 1, {}),
     "mnA_ragged": (504, 256, 500 - 4, "f16", 1, 0, {}),
     "out_f16_T": (300, 200, 256, "f16", 0, 0, {"out": "f16", "transposed": True}),
     "out_f32_T": (300, 200, 256, "f16", 0, 0, {"transposed": True}),

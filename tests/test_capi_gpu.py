@@ -1,0 +1,114 @@
+"""C-ABI level parity of the GEMM engine and its fused epilogues against plain fp32/fp64 PyTorch on the same
+16-bit operands (the only difference left is the accumulation order): csn_gemm in every operand major, split-K,
+csn_gemm_pair (cta_group::2), csn_gemm_res_ln (projection + residual + LayerNorm statistics, csa_models.py:115-118)
+and csn_gemm_delta (dO = dZ W_o fused with delta = rowsum(dO o O))."""
+import ctypes as C
+
+import pytest
+import torch
+
+from csn_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+
+def _ops(M, N, K, seed, dt=torch.float16):
+    g = synth.gen(seed)
+    A = (torch.randn(M, K, generator=g) * 0.5).to(dt).cuda()
+    B = (torch.randn(N, K, generator=g) * 0.5).to(dt).cuda()
+    return A, B, A.double() @ B.double().t()
+
+
+@pytest.mark.parametrize("a_mn,b_mn", [(0, 0), (1, 0), (0, 1), (1, 1)])
+def test_gemm_all_operand_majors(a_mn, b_mn):
+    from csn_b200 import _lib as L
+    M, N, K = 384, 320, 448
+    A, B, ref = _ops(M, N, K, 1)
+    At, Bt = A.t().contiguous(), B.t().contiguous()   # kept alive: the descriptors hold raw pointers
+    Am = L.mat(At, L.MAJOR_MN) if a_mn else L.mat(A, L.MAJOR_K)
+    Bm = L.mat(Bt, L.MAJOR_MN) if b_mn else L.mat(B, L.MAJOR_K)
+    D = torch.full((M, N), float("nan"), device="cuda")
+    L.gemm(Am, Bm, L.out(D, N), M, N, K, alpha=0.5)
+    assert (D.double() - 0.5 * ref).abs().max() < 2e-5 * ref.abs().max()
+
+
+def test_gemm_split_k_reduce_add_and_bf16():
+    from csn_b200 import _lib as L
+    M, N, K = 256, 256, 8192
+    A, B, ref = _ops(M, N, K, 2, torch.bfloat16)
+    D = torch.zeros(M, N, device="cuda")
+    L.gemm(L.mat(A, L.MAJOR_K), L.mat(B, L.MAJOR_K), L.out(D, N, accumulate=True), M, N, K, split_k=16)
+    assert (D.double() - ref).abs().max() < 2e-5 * ref.abs().max()
+
+
+@pytest.mark.parametrize("M,N,K,out", [(512, 512, 256, torch.float32), (1000, 700, 320, torch.float32),
+                                       (768, 512, 1024, torch.float16)])
+def test_gemm_pair_cta_group_2(M, N, K, out):
+    from csn_b200 import _lib as L
+    A, B, ref = _ops(M, N, K, 3)
+    D = torch.full((M, N), float("nan"), dtype=out, device="cuda")
+    rc = L.lib().csn_gemm_pair(A.data_ptr(), B.data_ptr(), D.data_ptr(), M, N, K, K, K, N, L.dtype_code(A.dtype),
+                               L.dtype_code(out), 1.0, L.stream_ptr())
+    L.check(rc, "csn_gemm_pair")
+    tol = 2e-5 if out == torch.float32 else 1e-3
+    assert (D.double() - ref).abs().max() < tol * ref.abs().max()
+
+
+def test_gemm_res_ln_against_layer_norm():
+    """Z = A W^T + residual (read from a channel-major tensor), mean / rstd = LayerNorm statistics (eps 1e-6, biased)."""
+    from csn_b200 import _lib as L
+    n_blocks, chunk, chunk_pad, n_chunks, n_points = 3, 100, 128, 2, 256   # rows_pad = 256; 200 points used of 256 (row stride must be a 16-byte multiple)
+    NP = chunk_pad * n_chunks
+    M, K = n_blocks * NP, 256
+    g = synth.gen(4)
+    A = (torch.randn(M, K, generator=g) * 0.5).half().cuda()
+    W = (torch.randn(256, K, generator=g) * 0.1).half().cuda()
+    res0 = torch.randn(2, 256, n_points, generator=g).cuda()            # two shapes in tensor 0
+    res1 = torch.randn(1, 2, 256, n_points, generator=g).cuda()         # (1, K+1, 256, N): slot 1 used
+    sel = torch.tensor([0, 1, 0], dtype=torch.int32).cuda()
+    row = torch.tensor([256, 256, 0], dtype=torch.int32).cuda()         # block 0 -> res0[1], block 1 -> res1[0,1], block 2 -> res0[0]
+    Z = torch.full((M, 256), float("nan"), device="cuda")
+    mean = torch.empty(M, device="cuda")
+    rstd = torch.empty(M, device="cuda")
+    Am, Bm = L.mat(A, L.MAJOR_K), L.mat(W, L.MAJOR_K)
+    rc = L.lib().csn_gemm_res_ln(C.byref(Am), C.byref(Bm), Z.data_ptr(), 256, M, K, 1.0, res0.data_ptr(), 2 * 256,
+                                 res1.data_ptr(), 2 * 256, sel.data_ptr(), row.data_ptr(), n_points, chunk * n_chunks,
+                                 NP, chunk_pad, chunk, 1e-6, mean.data_ptr(), rstd.data_ptr(), L.stream_ptr())
+    L.check(rc, "csn_gemm_res_ln")
+    src = [res0[1], res1[0, 1], res0[0]]
+    fc = (A.double() @ W.double().t()).view(n_blocks, n_chunks, chunk_pad, 256)
+    for b in range(n_blocks):
+        for c in range(n_chunks):
+            r = src[b][:, c * chunk:(c + 1) * chunk].t().double()           # (chunk, 256)
+            z = fc[b, c, :chunk] + r
+            got = Z.view(n_blocks, n_chunks, chunk_pad, 256)[b, c]
+            assert (got[:chunk].double() - z).abs().max() < 1e-5 * z.abs().max()
+            assert got[chunk:].abs().max() == 0                               # pad rows are zero
+            mu, var = z.mean(dim=1), z.var(dim=1, unbiased=False)
+            gm = mean.view(n_blocks, n_chunks, chunk_pad)[b, c, :chunk].double()
+            gr = rstd.view(n_blocks, n_chunks, chunk_pad)[b, c, :chunk].double()
+            assert (gm - mu).abs().max() < 1e-5
+            assert ((gr - (var + 1e-6).rsqrt()).abs() / gr).max() < 1e-5
+
+
+@pytest.mark.parametrize("n_head,d_head", [(1, 256), (2, 256), (4, 64)])
+def test_gemm_delta_against_rowsum(n_head, d_head):
+    from csn_b200 import _lib as L
+    NP, nblk = 256, 2
+    M, HD = nblk * NP, n_head * d_head
+    g = synth.gen(5)
+    dZ = (torch.randn(M, 256, generator=g) * 0.5).half().cuda()
+    Wo = (torch.randn(256, HD, generator=g) * 0.1).half().cuda()          # fc.weight (256, h*d): dO = dZ Wo
+    O = torch.randn(M, HD, generator=g).half().cuda()
+    O_lo = (torch.randn(M, HD, generator=g) * 0.3).half().cuda()
+    dO = torch.full((M, HD), float("nan"), dtype=torch.float16, device="cuda")
+    delta = torch.full((nblk * n_head * NP,), float("nan"), device="cuda")
+    Am, Bm = L.mat(dZ, L.MAJOR_K), L.mat(Wo, L.MAJOR_MN)
+    rc = L.lib().csn_gemm_delta(C.byref(Am), C.byref(Bm), dO.data_ptr(), HD, M, HD, 256, 1.0, O.data_ptr(), O_lo.data_ptr(),
+                                HD, delta.data_ptr(), NP, n_head, d_head, L.stream_ptr())
+    L.check(rc, "csn_gemm_delta")
+    ref = dZ.double() @ Wo.double()
+    assert (dO.double() - ref).abs().max() < 2e-3 * ref.abs().max()
+    want = (dO.double() * (O.double() + O_lo.double() / 2048.0)).view(nblk, NP, n_head, d_head).sum(-1).permute(0, 2, 1)
+    got = delta.view(nblk, n_head, NP).double()
+    assert (got - want).abs().max() < 1e-5 * want.abs().max() + 1e-6
