@@ -1,0 +1,63 @@
+"""Edge cases of the module surface: smallest batches, a single neighbour, one-point shapes, one candidate,
+empty candidate sets, and repeated calls with changing shapes (work-table caches)."""
+import pytest
+import torch
+
+from csn_b200 import synth
+from tests import golden_util as G
+
+pytestmark = pytest.mark.gpu
+
+
+def test_csa_smallest_configuration_and_changing_batch_sizes():
+    from csn_b200 import midfc
+    m = midfc.get_model("csa", 4, 1, 1).cuda().eval()
+    outs = {}
+    for B in (1, 3, 1):                      # the cached tables must not leak between batch sizes
+        x, nb = synth.csa_batch(40 + B, B, 1)
+        with torch.no_grad():
+            y = m(x.cuda(), "test", nb.cuda())
+        assert y.shape == (B, 4, 10000, 1) and torch.isfinite(y).all()
+        outs.setdefault(B, []).append(y)
+    assert torch.equal(outs[1][0], outs[1][1])
+
+
+def test_csa_output_of_a_shape_does_not_depend_on_the_rest_of_the_batch():
+    from csn_b200 import midfc
+    m = midfc.get_model("csa", 15, 1, 2).cuda().eval()
+    x, nb = synth.csa_batch(50, 3, 2)
+    with torch.no_grad():
+        all3 = m.get_csa_feats(x.cuda(), nb.cuda(), "test")
+        one = m.get_csa_feats(x[1:2].cuda(), nb[1:2].cuda(), "test")
+    # the reference's batch-interleaving view couples the compatibility weights across the batch for
+    # B > 1, so only B = 1 against itself is invariant; shapes and finiteness are checked for the batch
+    assert all3.shape == (3, 256, 10000, 1) and torch.isfinite(all3).all() and torch.isfinite(one).all()
+
+
+def test_mink_tiny_and_unequal_lengths():
+    from csn_b200 import mink
+    from oracle import csa_oracle as O
+    h = 4
+    m = mink.MultiHeadAttention(h, 256, 64, 64).cuda().eval()
+    w = synth.mink_state(3, h)
+    m.load_state_dict({k[len("MHA."):]: v for k, v in w.items() if k.startswith("MHA.")})
+    for Lq, Lk in ((1, 1), (1, 300), (257, 5), (128, 128)):
+        g = synth.gen(Lq * 1000 + Lk)
+        q = torch.relu(torch.randn(1, Lq, 256, generator=g))
+        k = torch.relu(torch.randn(1, Lk, 256, generator=g))
+        want, _ = O.mha_mink(q, k, k, w, h)
+        got, _ = m(q.cuda(), k.cuda(), k.cuda())
+        assert G.rel_err(got.cpu(), want) < 1e-3, (Lq, Lk)
+
+
+def test_knn_single_candidate_and_k_larger_than_the_collection():
+    from csn_b200 import knn
+    f = synth.clustered_shapes(3, 3, n_points=512).cuda()
+    s = knn.retrieval_measure(f[:1], f[:1])
+    assert s.shape == (1, 1) and abs(s.item() - 1.0) < 1e-5          # a shape against itself
+    s = knn.retrieval_measure(f, f[:2])
+    assert s.shape == (3, 2)
+    idx = knn.knn_graph(f, f, 2)
+    assert idx.shape == (3, 3) and sorted(idx[0].tolist()) == [0, 1, 2]
+    with pytest.raises((RuntimeError, ValueError, IndexError)):
+        knn.knn_graph(f, f, 5)                                        # topk(K+1) with K+1 > S, like torch.topk
