@@ -76,6 +76,47 @@ __global__ void __launch_bounds__(256) pack_kernel(const PackArgs p) {
   }
 }
 
+// 128 points x 64 channels per CTA (grid.z = the four channel groups): every channel row is read as 512 contiguous
+// bytes (four 128-byte requests back to back) instead of 128, which is what the DRAM pages want; the other three
+// quarters of each output row come from the sibling CTAs and merge in L2.
+__global__ void __launch_bounds__(256) pack128_kernel(const PackArgs p) {
+  __shared__ float tile[128][65];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int i0 = blockIdx.y / p.n1, i1 = blockIdx.y % p.n1;
+  const float* src = p.src + i0 * p.src_s0 + i1 * p.src_s1;
+  const long long slot = p.dst_slot0 + i0 * p.dst_s0 + i1 * p.dst_s1;
+  const int r0 = blockIdx.x * 128;            // first padded row of this tile (128 | chunk_pad)
+  const int c0 = blockIdx.z * 64;             // first channel of this CTA
+  const int ch = r0 / p.chunk_pad, ib = r0 % p.chunk_pad;
+  float amx = 0.f;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const int c = warp + 8 * k;
+    const float* row = src + (long long)(c0 + c) * p.ch_stride + (long long)ch * p.chunk;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int i = ib + lane + 32 * j;
+      const int n = ch * p.chunk + i;
+      const float v = (i < p.chunk && n < p.n_points) ? __ldg(row + i) : 0.f;
+      tile[lane + 32 * j][c] = v;
+      amx = fmaxf(amx, fabsf(v));
+    }
+  }
+  if (p.amax) {
+    amx = warp_max(amx);
+    if (lane == 0 && amx > 0.f) atomicMax(reinterpret_cast<int*>(p.amax), __float_as_int(amx));
+  }
+  __syncthreads();
+#pragma unroll 4
+  for (int rr = warp; rr < 128; rr += 8) {
+    const long long row = slot * p.rows_pad + r0 + rr;
+    const int c = c0 + 2 * lane;
+    const float a = tile[rr][2 * lane], b = tile[rr][2 * lane + 1];
+    if (p.dst16) reinterpret_cast<uint32_t*>(p.dst16)[(row * DM + c) >> 1] = pack2(a, b, p.dtype);
+    if (p.dst32) *reinterpret_cast<float2*>(p.dst32 + row * DM + c) = make_float2(a, b);
+  }
+}
+
 // ------------------------------------------------------------------------------------------ softmax fwd
 // One warp per row. cols_pad = 128*NV (NV <= 4 keeps the row in registers). Columns >= cols_valid are
 // masked; rows whose index inside their group (row % group_rows) is >= rows_valid are written as zeros.
@@ -636,6 +677,9 @@ int csn_pack_rows(const float* src, void* dst16, float* dst32, int64_t ch_stride
   CSN_CHECK_ARG(dtype == CSN_F16 || dtype == CSN_BF16, "csn_pack_rows: 16-bit destination only");
   if (n0 * n1 == 0) return 0;
   PackArgs a{src, dst16, dst32, ch_stride, src_s0, src_s1, dst_slot0, dst_s0, dst_s1, n0, n1, n_points, chunk, chunk_pad, rows_pad, dtype, amax};
+  static const bool wide = getenv("CSN_PACK128") == nullptr || atoi(getenv("CSN_PACK128")) != 0;
+  if (wide && chunk_pad % 128 == 0)
+    return launch_simple(pack128_kernel, dim3(rows_pad / 128, n0 * n1, 4), dim3(256), a, stream, "pack128_kernel");
   return launch_simple(pack_kernel, dim3(rows_pad / 32, n0 * n1), dim3(256), a, stream, "pack_kernel");
 }
 
