@@ -352,6 +352,47 @@ def run_ours(args) -> None:
     if world > 1:
         dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
     e2e_value = pairs * e2e_steps / t_e2e.item()
+
+    # ------------------------------------------------------------------ e2e with the GPU-resident feature store
+    # (SURVEY §8f-1): the per-point features are constants of the CSA phase, so only shape ids and labels cross PCIe;
+    # the step's inputs are gathered by id on the device into the static input sets of the graphs.
+    from csn_b200.store import FeatureStore
+    n_store = 96
+    store = FeatureStore(n_store, N_POINTS, D, device=dev)
+    gs_ = torch.Generator(device=dev).manual_seed(7 + rank)
+    for s0 in range(0, n_store, 16):
+        store.feats[s0:s0 + 16] = torch.relu(torch.randn(16, D, N_POINTS, device=dev, generator=gs_))
+    gh = torch.Generator().manual_seed(11 + rank)
+    id_steps = [(torch.randint(0, n_store, (CSA_B,), generator=gh), torch.randint(0, n_store, (CSA_B, CSA_K), generator=gh))
+                for _ in range(8)]
+    hl_s = [torch.randint(0, N_CLASSES, (CSA_B, N_POINTS), generator=gh).pin_memory() for _ in range(2)]
+
+    def store_run(n):
+        last = 0.0
+        for i in range(n):
+            k = i % 2
+            x, nb, lab = batches[k]
+            ids, nbr = id_steps[i % len(id_steps)]
+            store.batch(ids, nbr, out=(x, nb))          # device-side gathers into the static inputs of graph k
+            lab.copy_(hl_s[k], non_blocking=True)
+            last = train_step(k).item()
+        return last
+
+    store_steps = max(2, min(args.steps, 10))
+    store_run(2)
+    barrier()
+    t0 = time.perf_counter()
+    store_run(store_steps)
+    barrier()
+    t_st = torch.tensor([time.perf_counter() - t0], device=dev)
+    if world > 1:
+        dist.all_reduce(t_st, op=dist.ReduceOp.MAX)
+    e2e_store = {"value": pairs * store_steps / t_st.item(), "unit": "shape-pairs/s",
+                 "h2d_bytes_per_step": int(hl_s[0].numel() * 8 + CSA_B * (CSA_K + 1) * 8), "d2h_bytes_per_step": 4,
+                 "steps": store_steps,
+                 "note": "features of the collection resident in HBM (csn_b200.store.FeatureStore), gathered by shape id on "
+                         "the device; only ids and labels cross PCIe"}
+    del store
     clocks = sampler.stop() if rank == 0 else None
     del batches, hx, hn, hl
     graphs = None   # releases the graphs' private memory pools before the 40 GB candidate store is built
@@ -469,6 +510,7 @@ def run_ours(args) -> None:
             "clocks": clocks, "gpu_launches": int(launches),
             "e2e": {"value": e2e_value, "unit": "shape-pairs/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 4,
                     "steps": e2e_steps},
+            "e2e_feature_store": e2e_store,
             "roofline": roof,
             "kernels": kernels,
             "cpu_baseline": cpu, "knn": knn_obj,

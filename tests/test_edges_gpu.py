@@ -61,3 +61,26 @@ def test_knn_single_candidate_and_k_larger_than_the_collection():
     assert idx.shape == (3, 3) and sorted(idx[0].tolist()) == [0, 1, 2]
     with pytest.raises((RuntimeError, ValueError, IndexError)):
         knn.knn_graph(f, f, 5)                                        # topk(K+1) with K+1 > S, like torch.topk
+
+
+def test_feature_store_batches_feed_the_layer_like_host_tensors():
+    """csn_b200.store.FeatureStore: device-side gathers by shape id give the tensors the loader
+    would have produced; the layer's output is identical."""
+    from csn_b200 import midfc
+    from csn_b200.store import FeatureStore
+    S, B, K = 7, 2, 2
+    feats = synth.iid_features(synth.gen(60), S)               # (S, 256, N, 1)
+    store = FeatureStore(S, device="cuda")
+    store.put(list(range(S)), feats)
+    ids, nbr = [5, 1], [[0, 3], [6, 2]]
+    x, xn = store.batch(ids, nbr)
+    assert torch.equal(x.cpu(), feats[ids])
+    for b in range(B):
+        for k in range(K):
+            assert torch.equal(xn[b, k + 1].cpu(), feats[nbr[b][k]])
+    m = midfc.get_model("csa", 15, 1, K).cuda().eval()
+    ref_nb = torch.stack([torch.stack([feats[ids[b]]] + [feats[j] for j in nbr[b]]) for b in range(B)])
+    with torch.no_grad():
+        got = m(x, "test", xn)
+        want = m(feats[ids].cuda(), "test", ref_nb.cuda())
+    assert torch.equal(got, want)
