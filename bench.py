@@ -367,15 +367,35 @@ def run_ours(args) -> None:
                 for _ in range(8)]
     hl_s = [torch.randint(0, N_CLASSES, (CSA_B, N_POINTS), generator=gh).pin_memory() for _ in range(2)]
 
+    consumed_s = [None, None]
+
+    def store_stage(i):   # gathers + label copy of step i into static input set i % 2, on the side stream
+        k = i % 2
+        x, nb, lab = batches[k]
+        ids, nbr = id_steps[i % len(id_steps)]
+        with torch.cuda.stream(copy_stream):
+            if consumed_s[k] is not None:
+                copy_stream.wait_event(consumed_s[k])
+            store.batch(ids, nbr, out=(x, nb))
+            lab.copy_(hl_s[k], non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(copy_stream)
+        return ev
+
     def store_run(n):
+        nxt = store_stage(0)
         last = 0.0
         for i in range(n):
-            k = i % 2
-            x, nb, lab = batches[k]
-            ids, nbr = id_steps[i % len(id_steps)]
-            store.batch(ids, nbr, out=(x, nb))          # device-side gathers into the static inputs of graph k
-            lab.copy_(hl_s[k], non_blocking=True)
-            last = train_step(k).item()
+            ev = nxt
+            cur = torch.cuda.current_stream()
+            cur.wait_event(ev)
+            loss = train_step(i % 2)
+            done = torch.cuda.Event()
+            done.record(cur)
+            consumed_s[i % 2] = done
+            if i + 1 < n:
+                nxt = store_stage(i + 1)   # enqueued behind nothing it conflicts with: overlaps step i
+            last = loss.item()
         return last
 
     store_steps = max(2, min(args.steps, 10))
