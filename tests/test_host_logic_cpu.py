@@ -92,3 +92,23 @@ def test_two_rank_sharding_over_gloo(tmp_path):
     r = torch.load(out)
     assert torch.equal(r["graph"], r["ref"])
     assert torch.allclose(r["g0"], torch.full((3,), 1.5)) and torch.allclose(r["g1"], torch.full((2, 2), 15.0))
+
+
+def test_feature_store_gathers_by_shape_id_on_any_device():
+    """csn_b200.store.FeatureStore is plain tensor indexing: the gather logic is checked here on the CPU."""
+    import torch
+    from csn_b200.store import FeatureStore
+    S, D, N, B, K = 6, 4, 10, 2, 3
+    feats = torch.arange(S * D * N, dtype=torch.float32).view(S, D, N)
+    store = FeatureStore(S, n_points=N, d_model=D, device="cpu")
+    store.put([3, 0, 5, 1, 4, 2], feats[[3, 0, 5, 1, 4, 2]])
+    assert torch.equal(store.feats, feats)
+    ids, nbr = [4, 1], [[0, 2, 5], [3, 3, 4]]
+    x, xn = store.batch(ids, nbr)
+    assert x.shape == (B, D, N, 1) and xn.shape == (B, K + 1, D, N, 1)
+    assert torch.equal(x[..., 0], feats[ids])
+    for b in range(B):
+        for k in range(K):
+            assert torch.equal(xn[b, k + 1, ..., 0], feats[nbr[b][k]])
+    x2, xn2 = store.batch([0, 0], [[1, 1, 1], [2, 2, 2]])      # buffers are reused for the same (B, K)
+    assert x2.data_ptr() == x.data_ptr() and torch.equal(xn2[1, 3, ..., 0], feats[2])
