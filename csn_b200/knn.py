@@ -79,6 +79,19 @@ def build_store(feats, dtype: torch.dtype = torch.float16, eps: float = 1e-12, e
     return ShapeStore(dst, row0, lens)
 
 
+def concat_stores(stores) -> ShapeStore:
+    """One store from several (e.g. built batch by batch while the collection streams through the SSA layer)."""
+    stores = list(stores)
+    rows = torch.cat([s.rows for s in stores], dim=0)
+    lo = torch.cat([s.rows_lo for s in stores], dim=0) if all(s.rows_lo is not None for s in stores) else None
+    row0, length, base = [], [], 0
+    for s in stores:
+        row0 += [base + r for r in s.row0]
+        length += list(s.length)
+        base += s.rows.shape[0]
+    return ShapeStore(rows, row0, length, lo)
+
+
 def _split_for_balance(n_items: int, n_cand: int) -> int:
     """Number of candidate-list segments per (query, tile) so that the persistent grid's last wave
     is nearly full."""

@@ -112,3 +112,30 @@ def test_feature_store_gathers_by_shape_id_on_any_device():
             assert torch.equal(xn[b, k + 1, ..., 0], feats[nbr[b][k]])
     x2, xn2 = store.batch([0, 0], [[1, 1, 1], [2, 2, 2]])      # buffers are reused for the same (B, K)
     assert x2.data_ptr() == x.data_ptr() and torch.equal(xn2[1, 3, ..., 0], feats[2])
+
+
+def test_knn_driver_reads_the_reference_feature_layout(tmp_path):
+    """csn_b200.knn_driver.FeatureFiles: os.listdir order, (1,256,N,1) files, pad-to-10k by repeating leading points
+    (features_data_loader.py:9-48); graph files as csa_training.py:286-290 reads them."""
+    import numpy as np
+    import torch
+    from csn_b200 import knn_driver as D
+    root = tmp_path / "train" / "Bed"
+    (root / "fc_1").mkdir(parents=True)
+    rng = np.random.default_rng(0)
+    a = rng.standard_normal((1, 256, 10000, 1)).astype(np.float32)
+    b = rng.standard_normal((1, 256, 7000, 1)).astype(np.float32)
+    np.save(root / "fc_1" / "a.npy", a)
+    np.save(root / "fc_1" / "b.npy", b)
+    ff = D.FeatureFiles(str(root))
+    assert sorted(ff.files) == ["a.npy", "b.npy"] and len(ff) == 2
+    ib = ff.files.index("b.npy")
+    fb = ff.load(ib)
+    assert fb.shape == (1, 256, 10000, 1)
+    assert torch.equal(fb[:, :, :7000], torch.from_numpy(b)) and torch.equal(fb[:, :, 7000:], torch.from_numpy(b[:, :, :3000]))
+    batches = list(ff.batches(8))
+    assert len(batches) == 1 and batches[0][0].shape == (2, 1, 256, 10000, 1)
+    g = np.arange(6, dtype=np.int64).reshape(2, 3)
+    D.save_graphs(str(tmp_path / "graphs"), g, g[::-1].copy())
+    assert np.array_equal(np.load(tmp_path / "graphs" / "train.npy"), g)
+    assert np.array_equal(np.load(tmp_path / "graphs" / "test.npy"), g[::-1])

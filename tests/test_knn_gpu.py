@@ -127,3 +127,41 @@ def test_exact_rescore_reaches_fp32_accuracy():
         for j in range(10):
             if want[i] - want[j] > 6e-7:
                 assert got[i] > got[j], (i, j)
+
+
+def test_knn_driver_end_to_end(tmp_path):
+    """csn_b200.knn_driver (the reference's missing save_knn_graph.py): feature files -> SSA features -> scores ->
+    train.npy / test.npy, against the module-level path get_all_feats + get_knn_graph (itself pinned to the
+    reference's golden graphs above), for the all-pairs and the big-class (k-means candidates) variants."""
+    import os
+    from csn_b200 import knn_driver as D, midfc
+    K, C, h = 2, 7, 1
+    shapes = synth.clustered_shapes(21, 33, n_categories=3)          # (33, N, 256) row-major
+    cm = shapes.permute(0, 2, 1).unsqueeze(-1).unsqueeze(1).contiguous()   # (33, 1, 256, N, 1) like the .npy files
+    for split, ids in (("train", range(0, 24)), ("test", range(24, 33))):
+        d = tmp_path / split / "Bed" / "fc_1"
+        d.mkdir(parents=True)
+        for i in ids:
+            np.save(d / f"shape_{i:03d}.npy", cm[i].numpy())
+    logs = tmp_path / "logs"
+    logs.mkdir()
+    sd = {k: v for k, v in synth.midfc_state(5, h, C, csa=False).items()}
+    torch.save(sd, logs / "trained_layers.pth")
+    rc = D.main([f"--ssa_logs_dir={logs}", f"--graphs_dir={tmp_path / 'graphs'}", "--partname=Bed", f"--n_heads={h}",
+                 "--batch_size=4", f"--num_classes={C}", f"--K={K}", f"--dataroot={tmp_path}/{{}}/{{}}"])
+    assert rc == 0
+    g_train, g_test = np.load(tmp_path / "graphs" / "train.npy"), np.load(tmp_path / "graphs" / "test.npy")
+    assert g_train.shape == (24, K + 1) and g_test.shape == (9, K + 1)
+    # the module-level path on the same files, in the same (os.listdir) order
+    m = midfc.get_model("ssa", C, h).cuda().eval()
+    m.load_state_dict(sd)
+    tr, te = D.FeatureFiles(str(tmp_path / "train" / "Bed")), D.FeatureFiles(str(tmp_path / "test" / "Bed"))
+    f_tr = m.get_all_feats(None, tr.batches(4), K, "test").cuda()
+    f_te = m.get_all_feats(None, te.batches(4), K, "test").cuda()
+    assert np.array_equal(g_train, m.get_knn_graph(f_tr, f_tr, K).cpu().numpy())
+    assert np.array_equal(g_test, m.get_knn_graph(f_te, f_tr, K).cpu().numpy())
+    assert (g_train[:, 0] == np.arange(24)).all()                     # every train shape retrieves itself first
+    # big-class variant: candidates = shapes nearest to S//10 k-means centres; graph entries are shape indices
+    gb_train, gb_test = D.build_graphs(m, str(tmp_path / "train" / "Bed"), str(tmp_path / "test" / "Bed"), 1, True, 4, "cuda")
+    assert gb_train.shape == (24, 2) and gb_test.shape == (9, 2)
+    assert len(np.unique(gb_train)) <= 24 // 10 and set(np.unique(gb_test)) <= set(np.unique(gb_train))
