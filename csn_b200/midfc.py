@@ -253,6 +253,65 @@ class MultiHeadAttention(nn.Module):
         return _MhaFn.apply(x, x, x, *self._weights(), self.n_head, _PRECISIONS[self.precision], 1, n)
 
 
+# ------------------------------------------------------------------------------------------- fused segmentation loss
+class _SegLossFn(torch.autograd.Function):
+    """loss = masked cross-entropy(logit(feats), labels) (csa_models.py:201 + csa_training.py:94-108) with the
+    logits never materialised on the forward path: one pass over the activation computes the loss, d loss / d feats
+    and d loss / d logits (for the weight gradient)."""
+
+    @staticmethod
+    def _run(f, W, lab, ignore_index, want_grads, gout):
+        B, D, N = f.shape
+        Cn = W.shape[0]
+        dev = f.device
+        n_valid = torch.zeros(1, dtype=torch.int32, device=dev)
+        parts = torch.empty(B * ((N + 127) // 128), dtype=torch.float32, device=dev)
+        dlogits = torch.empty(B, Cn, N, dtype=torch.float32, device=dev) if want_grads else None
+        dfeat = torch.empty_like(f) if want_grads else None
+        rc = L.lib().csn_seg_loss(f.data_ptr(), D * N, N, B, N, W.data_ptr(), Cn, lab.data_ptr(), int(ignore_index),
+                                  n_valid.data_ptr(), parts.data_ptr(), dlogits.data_ptr() if want_grads else None,
+                                  dfeat.data_ptr() if want_grads else None, gout.data_ptr() if gout is not None else None,
+                                  L.stream_ptr())
+        L.check(rc, "csn_seg_loss")
+        return parts, n_valid, dlogits, dfeat
+
+    @staticmethod
+    def forward(ctx, feats, weight, labels, ignore_index):
+        _require_cuda(feats, "feats")
+        B, D, N = feats.shape[0], feats.shape[1], feats.shape[2]
+        assert D == 256
+        f = feats.float().contiguous().view(B, D, N)
+        Cn = weight.shape[0]
+        W = weight.detach().float().reshape(Cn, D).contiguous()
+        lab = labels.reshape(B, N).to(torch.int64).contiguous()
+        parts, n_valid, _, _ = _SegLossFn._run(f, W, lab, ignore_index, False, None)
+        ctx.save_for_backward(f, W, lab)
+        ctx.meta = (feats.shape, weight.shape, ignore_index)
+        return parts.sum() / n_valid.clamp_min(1).to(torch.float32)[0]
+
+    @staticmethod
+    def backward(ctx, gout):
+        # the pass is repeated with the gradient outputs switched on and the upstream gradient as a device scalar:
+        # recomputing 0.6 GFLOP of logits is cheaper than keeping (and rescaling) 82 MB of d feats from the forward
+        f, W, lab = ctx.saved_tensors
+        fshape, wshape, ignore_index = ctx.meta
+        g = gout.detach().float().reshape(1).contiguous()
+        _, _, dlogits, dfeat = _SegLossFn._run(f, W, lab, ignore_index, True, g)
+        gf = dfeat.view(fshape) if ctx.needs_input_grad[0] else None
+        gw = None
+        if ctx.needs_input_grad[1]:   # d logits f^T: the library's conv weight-gradient kernel (0.6 GFLOP), no copies
+            B, D, N = f.shape
+            gw = torch.nn.grad.conv2d_weight(f.view(B, D, N, 1), (wshape[0], D, 1, 1), dlogits.view(B, wshape[0], N, 1)).view(wshape)
+        return gf, gw, None, None
+
+
+def segmentation_loss(feats: torch.Tensor, logit_weight: torch.Tensor, labels: torch.Tensor, ignore_index: int = 0):
+    """Masked cross-entropy of the MID-FC training scripts (csa_training.py:94-108) on top of the bias-free 1x1
+    `logit` conv (csa_models.py:201), fused (SURVEY §8f-3): feats (B,256,N,1), logit_weight (C,256,1,1), labels (B,N);
+    points whose label == ignore_index (0 in the reference) are masked; mean over the others."""
+    return _SegLossFn.apply(feats, logit_weight, labels, ignore_index)
+
+
 # ------------------------------------------------------------------------------------------- CSA op
 class _CsaFn(torch.autograd.Function):
     """CrossShapeAt.get_csa_feats (csa_models.py:209-242) / get_ssa_feats (:204-207, x_neighbors=None)."""
@@ -450,6 +509,15 @@ class CrossShapeAt(nn.Module):
         if self.attention_type == 'fcf_csaf_logitf':
             x = self.forward_fcf_csaf_logitf(x, neighbor_feats, mode)  # undefined in the reference too
         return x
+
+    def forward_loss(self, x, mode, neighbor_feats, labels, ignore_index: int = 0):
+        """forward(...) followed by the training scripts' masked cross-entropy (csa_training.py:94-108), with the
+        logit conv, the loss and their backward fused into one pass over the layer's output (segmentation_loss)."""
+        if self.attention_type == 'csa':
+            feats = self.get_csa_feats(x, neighbor_feats, mode)
+        else:
+            feats, _ = self.get_ssa_feats(x, mode)
+        return segmentation_loss(feats, self.logit.weight, labels, ignore_index)
 
     def forward_ssa(self, x, mode):
         if self.after_fc:

@@ -160,6 +160,18 @@ int csn_attn_bwd_dq(const void* Q, const void* dO, const void* K, const void* V,
                     void* dS, int64_t ds_rows, int64_t ldds, const float* lse, const float* delta, int32_t paired,
                     void* stream);
 
+/* Fused segmentation epilogue: logits = W f (the bias-free 1x1 `logit` conv, csa_models.py:201), masked
+ * cross-entropy (csa_training.py:94-108: mean over the points whose label != ignore_index) and its backward in one
+ * pass over the channel-major activation feat (element (b, k, n) at feat[b*b_stride + k*ch_stride + n], 256 channels):
+ *   *n_valid (zero-initialised device int) <- number of unmasked points;  loss_part[b*ceil(n_points/128) + i] <-
+ *   partial sums of -log p[label] (the loss is their sum / n_valid);  dlogits (optional, [B][C][n_points]) <-
+ *   (softmax - onehot) / n_valid, zero at masked points;  dfeat (optional, feat's layout) <- W^T dlogits;
+ *   both multiplied by *grad_scale when that optional device scalar (the upstream gradient of the loss) is given.
+ * W: [n_classes][256] fp32, n_classes <= 64; labels int64 [B][n_points]. */
+int csn_seg_loss(const float* feat, int64_t b_stride, int64_t ch_stride, int32_t n_batch, int32_t n_points,
+                 const float* W, int32_t n_classes, const int64_t* labels, int32_t ignore_index, int32_t* n_valid,
+                 float* loss_part, float* dlogits, float* dfeat, const float* grad_scale, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * HBM-bound pieces of the CSA/SSA layer.  Row buffers use "padded" coordinates: a shape's block has
  * rows_pad = n_chunks*chunk_pad rows; chunk c (points [c*chunk, (c+1)*chunk)) occupies rows

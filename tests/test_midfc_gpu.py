@@ -178,3 +178,31 @@ def test_graphed_step_replays_the_eager_step():
         assert abs(loss.item() - want[0]) < 1e-5
         assert G.rel_err(m.attention.w_qs.weight.grad, want[1]) < 2e-4
         assert G.rel_err(m.compatibility_q.weight.grad, want[2]) < 5e-2
+
+
+@pytest.mark.parametrize("C", [4, 15, 39, 51])
+def test_fused_segmentation_loss_matches_conv_plus_masked_ce(C):
+    """csn_seg_loss: loss, d/d feats and d/d W against F.conv2d + the reference's masked CE."""
+    from csn_b200 import midfc
+    B, N = 2, 1000 + C          # not a multiple of 128
+    g = synth.gen(70 + C)
+    feats = torch.randn(B, 256, N, 1, generator=g).cuda().requires_grad_(True)
+    W = (torch.randn(C, 256, 1, 1, generator=g) * 0.1).cuda().requires_grad_(True)
+    lab = torch.randint(0, C, (B, N), generator=g).cuda()
+    loss = midfc.segmentation_loss(feats, W, lab)
+    (loss * 1.5).backward()
+    gf, gw = feats.grad.clone(), W.grad.clone()
+    feats.grad = W.grad = None
+    tf32 = torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = False   # compare against true fp32
+    try:
+        ref = _masked_ce(torch.nn.functional.conv2d(feats, W), lab)
+        (ref * 1.5).backward()
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = tf32
+    assert abs(loss.item() - ref.item()) < 1e-5 * max(1.0, abs(ref.item()))
+    assert G.rel_err(gf, feats.grad) < 1e-5
+    assert G.rel_err(gw, W.grad) < 1e-4
+    # all points masked: loss 0, zero gradients, no NaN
+    z = midfc.segmentation_loss(feats.detach(), W.detach(), torch.zeros_like(lab))
+    assert z.item() == 0.0
