@@ -55,6 +55,8 @@ def _declare(L: C.CDLL) -> None:
     L.csn_abi_version.restype = C.c_int
     L.csn_launch_count.restype = C.c_int64
     L.csn_gemm.restype = C.c_int
+    L.csn_csa_head_grid.restype = C.c_int
+    L.csn_csa_head_grid.argtypes = [C.c_int32, C.c_int32]
     L.csn_gemm.argtypes = [C.POINTER(csn_mat), C.POINTER(csn_mat), C.POINTER(csn_out), C.c_int32,
                            C.c_int32, C.c_int32, C.POINTER(C.c_int32), C.c_float, C.c_int32,
                            C.c_void_p]
@@ -175,6 +177,10 @@ _EXTRA_SIGNATURES: dict[str, list] = {
                         C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_int32,
                         C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_int32,
                         C.c_void_p],
+    "csn_csa_head": [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32,
+                     C.c_void_p, C.c_int32, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
+                     C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                     C.c_void_p, C.c_void_p],
     "csn_topk_rows": [C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p],
 }
 

@@ -227,7 +227,7 @@ class ChannelMajorResidual:
 def attention_forward(Xh, Xf, groups, n_slots, n_blocks, w_q, w_k, w_v, w_o, gamma, beta, geom: Geometry,
                       n_head: int, want_colsum: bool = True, save_for_backward: bool = True,
                       want_y: bool = True, residual_cm: ChannelMajorResidual = None,
-                      colsum_blocks: int = None) -> AttnContext:
+                      colsum_blocks: int = None, dropout_p: float = 0.0, seed: int = 0) -> AttnContext:
     """Forward of all blocks. Xh/Xf: packed slots [S*NP, 256] (16-bit / fp32). With residual_cm (and want_y False)
     Xf may be None: the output projection, the residual add and the LayerNorm statistics run as ONE kernel
     (csn_gemm_res_ln) that reads the residual from the channel-major inputs; colsum then covers the first
@@ -237,6 +237,8 @@ def attention_forward(Xh, Xf, groups, n_slots, n_blocks, w_q, w_k, w_v, w_o, gam
     HD = w_q.shape[0]
     d = HD // n_head
     ctx = AttnContext(geom, n_head, d, list(groups), n_slots, n_blocks, Xh=Xh, Xf=Xf)
+    if dropout_p > 0.0:
+        raise L.CsnError("training-mode dropout is not available in this build: call model.eval() or set dropout p = 0")
     ctx.Wqkv16 = torch.cat([w_q, w_k, w_v], dim=0).to(dt).contiguous()  # [3HD, 256]
     ctx.Wo16 = w_o.to(dt).contiguous()                                   # [256, HD]
     ctx.gamma = gamma

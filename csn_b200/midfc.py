@@ -312,87 +312,162 @@ def segmentation_loss(feats: torch.Tensor, logit_weight: torch.Tensor, labels: t
 
 
 # ------------------------------------------------------------------------------------------- CSA op
+class _CsaState:
+    """What the backward pass of the CSA layer needs from its forward pass (shared by _CsaFn and _CsaLossFn)."""
+    __slots__ = ("a", "glue", "comp", "blk", "meta")
+
+
+def _csa_forward_core(x, x_neighbors, wq, wk, wv, wo, gamma, beta, cq_w, cq_b, ck_w, ck_b, n_head, dt, iters, chunk,
+                      dropout_p: float = 0.0, seed: int = 0) -> _CsaState:
+    """Everything of get_csa_feats (csa_models.py:209-230) up to the compatibility weights: packing, projections,
+    the (2K+1)B attention blocks, residual + LayerNorm statistics, pooled means, compatibility softmax."""
+    _require_cuda(x, "x")
+    _require_cuda(wq, "attention.w_qs.weight")
+    dev = x.device
+    B, n_src = x.shape[0], x.shape[2]
+    ssa_only = x_neighbors is None
+    K = 0 if ssa_only else x_neighbors.shape[1] - 1
+    if not ssa_only and not x_neighbors.is_cuda:
+        # the reference moves each neighbour inside the layer (csa_models.py:216,236)
+        x_neighbors = neighbors_to_device(x_neighbors, dev)
+    n_src_nb = n_src if ssa_only or K == 0 else x_neighbors.shape[3]
+    geom = _geom_for(min(n_src, n_src_nb), iters, chunk)
+    S = B * (K + 1)
+    xs = _std_layout(x.float())
+    sources = [(xs, 0, K + 1, 0)]
+    nbs = None
+    if K > 0:
+        nbs = _std_layout(x_neighbors.float())
+        sources.append((nbs[:, 1:], 1, K + 1, 1))
+    # the residual of the output projection is read straight from these channel-major tensors by the fused
+    # projection/LayerNorm kernel (slot s = b*(K+1)+j: j = 0 the query, j >= 1 neighbour j)
+    res_cm = None
+    # (TMA needs 16-byte aligned rows: point counts that are not multiples of 4 take the unfused path)
+    tma_ok = xs.shape[2] % 4 == 0 and xs.data_ptr() % 16 == 0 and (nbs is None or nbs.data_ptr() % 16 == 0)
+    if tma_ok and (K == 0 or nbs.shape[3] == xs.shape[2]):
+        sel = tuple(0 if j == 0 else 1 for b in range(B) for j in range(K + 1))
+        off = tuple(b * xs.stride(0) if j == 0 else b * nbs.stride(0) + j * nbs.stride(1)
+                    for b in range(B) for j in range(K + 1))
+        res_cm = E.ChannelMajorResidual(bases=(xs,) if K == 0 else (xs, nbs), sel=sel, off=off,
+                                        ch_stride=xs.shape[2], n_points=xs.shape[2])
+    Xh, Xf = _pack_sources(sources, S, geom, dt, dev, want_f32=res_cm is None or not E.use_fused_ln())
+    groups = [E.Group(n_in=S, n_out=1, blk0=0, q0=0, q_si=1, q_so=0, k0=0, k_si=1, k_so=0, v0=0, v_si=1, v_so=0)]
+    nblk = S
+    if K > 0:
+        groups.append(E.Group(n_in=K, n_out=B, blk0=S, q0=0, q_si=0, q_so=K + 1, k0=1, k_si=1, k_so=K + 1,
+                              v0=1, v_si=1, v_so=K + 1))
+        nblk += B * K
+    a = E.attention_forward(Xh, Xf, groups, S, nblk, wq, wk, wv, wo, gamma, beta, geom, n_head,
+                            want_colsum=not ssa_only, want_y=False, residual_cm=res_cm, colsum_blocks=S,
+                            dropout_p=dropout_p, seed=seed)
+    # ---- compatibility (csa_models.py:211-230): tiny (B*(K+1) x 256) glue, kept in torch
+    if ssa_only:
+        comp = torch.ones(B, 1, dtype=torch.float32, device=dev)
+        glue = None
+    else:
+        pooled = a.colsum[:S].detach().clone().requires_grad_(True)   # slot order (b,k)
+        loc = [t.detach().requires_grad_(True) for t in (cq_w, cq_b, ck_w, ck_b)]
+        with torch.enable_grad():
+            pv = pooled.view(B, K + 1, 256)
+            y_q = pv[:, 0]
+            y_stack = pv.transpose(0, 1).reshape((K + 1) * B, 256)   # rows [k=0: b..; k=1: b..; ...] (:213,220)
+            u_q = F.normalize(F.linear(y_q, loc[0], loc[1]), dim=-1)
+            u_k = F.normalize(F.linear(y_stack, loc[2], loc[3]), dim=-1)
+            u_k = u_k.view(B, -1, 256)                               # batch-interleaving view (:227, SURVEY F8)
+            comp_g = torch.softmax(torch.matmul(u_q.unsqueeze(1), u_k.permute(0, 2, 1)).squeeze(1), dim=-1)
+        comp = comp_g.detach()
+        glue = (pooled, loc, comp_g)
+
+    def _blk_table():
+        t = torch.empty(B, K + 1, dtype=torch.int32)
+        for b in range(B):
+            t[b, 0] = b * (K + 1)
+            for k in range(1, K + 1):
+                t[b, k] = S + b * K + (k - 1)
+        return t
+    st = _CsaState()
+    st.a, st.glue, st.comp = a, glue, comp.contiguous()
+    st.blk = E.cached_table(("csa_blk", B, K), dev, _blk_table)
+    st.meta = (B, K, S, nblk, n_src, n_src_nb)
+    return st
+
+
+def _csa_bwd_tables(st: _CsaState, dev):
+    B, K, S, nblk, _, _ = st.meta
+    has_glue = st.glue is not None
+
+    def _bwd_tables():
+        cb = torch.full((nblk,), -1, dtype=torch.int32)
+        cwi = torch.full((nblk,), -1, dtype=torch.int32)
+        pb = torch.full((nblk,), -1, dtype=torch.int32)
+        for b in range(B):
+            for k in range(K + 1):
+                slot = b * (K + 1) + k
+                if has_glue:
+                    pb[slot] = slot
+                if k == 0:
+                    cb[slot], cwi[slot] = b, slot
+                else:
+                    j = S + b * K + (k - 1)
+                    cb[j], cwi[j] = b, slot
+        return torch.stack([cb, cwi, pb, torch.full((nblk,), -1, dtype=torch.int32)])
+    tabs = E.cached_table(("csa_bwd", B, K, has_glue), dev, _bwd_tables)
+    gidx = E.cached_table(("csa_bwd_gather", B, K, has_glue), dev, lambda: _bwd_tables()[1].clamp(min=0).long())
+    return tabs[0], tabs[1], tabs[2], gidx
+
+
+def _csa_backward_core(st: _CsaState, dOutT, amax, dcomp, need_dx: bool, out_scale=None):
+    """Backward of _csa_forward_core + the weighted sum, given the output gradient as padded rows dOutT [B*NP, 256]
+    (zero in pad rows), amax >= max|dOutT| (device scalar) and dcomp[b,k] = <dOut[b], MHA_k> (or None without glue).
+    out_scale: optional device scalar multiplied into the whole upstream gradient (d loss of a fused head)."""
+    a = st.a
+    geom = a.geom
+    B, K, S, nblk, n_src, n_src_nb = st.meta
+    dev = dOutT.device
+    cb, cwi, pb, gidx = _csa_bwd_tables(st, dev)
+    cw = st.comp.reshape(-1)[gidx].contiguous()
+    if out_scale is not None:
+        cw = cw * out_scale
+        amax = amax * out_scale.abs()
+    grads_glue = [None] * 4
+    dpool = None
+    if st.glue is not None:
+        pooled, loc, comp_g = st.glue
+        dc = dcomp.view(B, K + 1)
+        if out_scale is not None:
+            dc = dc * out_scale
+        gl = torch.autograd.grad(comp_g, [pooled] + loc, dc)
+        dpool = gl[0].contiguous()
+        grads_glue = list(gl[1:])
+        amax = amax + dpool.abs().max() / geom.n_points   # bound on |dY + dpool/N| for the gradient scaling (comp <= 1)
+    # The upstream gradient of block j is comp[b,k] * dOut[b]^T (+ the pooled-mean row vector): csn_ln_bwd forms
+    # cw[j] * dOutT[cb[j]] + dpool[pb[j]]/N on the fly; the (2K+1)x larger dY is never materialised.
+    g = E.attention_backward(a, dOutT, need_dx, amax, bcast=dpool, bcast_idx=pb if dpool is not None else None,
+                             bcast_scale=1.0 / geom.n_points, src_idx=cb, src_w=cw)
+    return g, grads_glue
+
+
 class _CsaFn(torch.autograd.Function):
     """CrossShapeAt.get_csa_feats (csa_models.py:209-242) / get_ssa_feats (:204-207, x_neighbors=None)."""
 
     @staticmethod
     def forward(ctx, x, x_neighbors, wq, wk, wv, wo, gamma, beta, cq_w, cq_b, ck_w, ck_b, n_head, dt, iters, chunk,
-                want_attn=True):
-        _require_cuda(x, "x")
-        _require_cuda(wq, "attention.w_qs.weight")
+                want_attn=True, dropout_p=0.0, seed=0):
+        st = _csa_forward_core(x, x_neighbors, wq, wk, wv, wo, gamma, beta, cq_w, cq_b, ck_w, ck_b, n_head, dt, iters,
+                               chunk, dropout_p, seed)
+        a, geom = st.a, st.a.geom
+        B, K, S, nblk, n_src, n_src_nb = st.meta
         dev = x.device
-        B, n_src = x.shape[0], x.shape[2]
-        ssa_only = x_neighbors is None
-        K = 0 if ssa_only else x_neighbors.shape[1] - 1
-        if not ssa_only and not x_neighbors.is_cuda:
-            # the reference moves each neighbour inside the layer (csa_models.py:216,236)
-            x_neighbors = neighbors_to_device(x_neighbors, dev)
-        n_src_nb = n_src if ssa_only or K == 0 else x_neighbors.shape[3]
-        geom = _geom_for(min(n_src, n_src_nb), iters, chunk)
-        S = B * (K + 1)
-        xs = _std_layout(x.float())
-        sources = [(xs, 0, K + 1, 0)]
-        nbs = None
-        if K > 0:
-            nbs = _std_layout(x_neighbors.float())
-            sources.append((nbs[:, 1:], 1, K + 1, 1))
-        # the residual of the output projection is read straight from these channel-major tensors by the fused
-        # projection/LayerNorm kernel (slot s = b*(K+1)+j: j = 0 the query, j >= 1 neighbour j)
-        res_cm = None
-        # (TMA needs 16-byte aligned rows: point counts that are not multiples of 4 take the unfused path)
-        tma_ok = xs.shape[2] % 4 == 0 and xs.data_ptr() % 16 == 0 and (nbs is None or nbs.data_ptr() % 16 == 0)
-        if tma_ok and (K == 0 or nbs.shape[3] == xs.shape[2]):
-            sel = tuple(0 if j == 0 else 1 for b in range(B) for j in range(K + 1))
-            off = tuple(b * xs.stride(0) if j == 0 else b * nbs.stride(0) + j * nbs.stride(1)
-                        for b in range(B) for j in range(K + 1))
-            res_cm = E.ChannelMajorResidual(bases=(xs,) if K == 0 else (xs, nbs), sel=sel, off=off,
-                                            ch_stride=xs.shape[2], n_points=xs.shape[2])
-        Xh, Xf = _pack_sources(sources, S, geom, dt, dev, want_f32=res_cm is None or not E.use_fused_ln())
-        groups = [E.Group(n_in=S, n_out=1, blk0=0, q0=0, q_si=1, q_so=0, k0=0, k_si=1, k_so=0, v0=0, v_si=1, v_so=0)]
-        nblk = S
-        if K > 0:
-            groups.append(E.Group(n_in=K, n_out=B, blk0=S, q0=0, q_si=0, q_so=K + 1, k0=1, k_si=1, k_so=K + 1,
-                                  v0=1, v_si=1, v_so=K + 1))
-            nblk += B * K
-        a = E.attention_forward(Xh, Xf, groups, S, nblk, wq, wk, wv, wo, gamma, beta, geom, n_head,
-                                want_colsum=not ssa_only, want_y=False, residual_cm=res_cm, colsum_blocks=S)
-        # ---- compatibility (csa_models.py:211-230): tiny (B*(K+1) x 256) glue, kept in torch
-        if ssa_only:
-            comp = torch.ones(B, 1, dtype=torch.float32, device=dev)
-            glue = None
-        else:
-            pooled = a.colsum[:S].detach().clone().requires_grad_(True)   # slot order (b,k)
-            loc = [t.detach().requires_grad_(True) for t in (cq_w, cq_b, ck_w, ck_b)]
-            with torch.enable_grad():
-                pv = pooled.view(B, K + 1, 256)
-                y_q = pv[:, 0]
-                y_stack = pv.transpose(0, 1).reshape((K + 1) * B, 256)   # rows [k=0: b..; k=1: b..; ...] (:213,220)
-                u_q = F.normalize(F.linear(y_q, loc[0], loc[1]), dim=-1)
-                u_k = F.normalize(F.linear(y_stack, loc[2], loc[3]), dim=-1)
-                u_k = u_k.view(B, -1, 256)                               # batch-interleaving view (:227, SURVEY F8)
-                comp_g = torch.softmax(torch.matmul(u_q.unsqueeze(1), u_k.permute(0, 2, 1)).squeeze(1), dim=-1)
-            comp = comp_g.detach()
-            glue = (pooled, loc, comp_g)
         # ---- out = sum_k comp[b,k] * MHA(x, x_k)   (:232-240), written channel-major
-        def _blk_table():
-            t = torch.empty(B, K + 1, dtype=torch.int32)
-            for b in range(B):
-                t[b, 0] = b * (K + 1)
-                for k in range(1, K + 1):
-                    t[b, k] = S + b * K + (k - 1)
-            return t
-        blk = E.cached_table(("csa_blk", B, K), dev, _blk_table)
         alloc = torch.zeros if n_src > geom.n_points else torch.empty
         out = alloc(B, 256, geom.n_points, 1, dtype=torch.float32, device=dev)
-        compc = comp.contiguous()
         # the LayerNorm output is formed on the fly from z, mean, rstd (it is never written to HBM)
-        rc = L.lib().csn_combine_fwd(a.Z.data_ptr(), blk.data_ptr(), compc.data_ptr(), out.data_ptr(), None, B, K + 1,
+        rc = L.lib().csn_combine_fwd(a.Z.data_ptr(), st.blk.data_ptr(), st.comp.data_ptr(), out.data_ptr(), None, B, K + 1,
                                      256 * geom.n_points, geom.n_points, geom.n_points, geom.chunk, geom.chunk_pad,
                                      geom.rows_pad, L.dtype_code(dt), a.mean.data_ptr(), a.rstd.data_ptr(),
                                      gamma.data_ptr(), beta.data_ptr(), L.stream_ptr())
         L.check(rc, "csn_combine_fwd")
-        ctx.a, ctx.glue, ctx.comp, ctx.blk = a, glue, compc, blk
-        ctx.meta = (B, K, S, nblk, n_src, n_src_nb)
+        ctx.st = st
         if want_attn:
             attn = _last_chunk_attn(a, S).view(B, K + 1, n_head, geom.chunk, geom.chunk)[:, 0]
         else:   # every reference caller discards it (SURVEY F10)
@@ -402,40 +477,15 @@ class _CsaFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, dout, _dattn):
-        a = ctx.a
-        geom = a.geom
-        B, K, S, nblk, n_src, n_src_nb = ctx.meta
+        st = ctx.st
+        a, geom = st.a, st.a.geom
+        B, K, S, nblk, n_src, n_src_nb = st.meta
         dev = dout.device
         dout = dout.float().contiguous()
-        # tables of the combine backward
-        has_glue = ctx.glue is not None
-
-        def _bwd_tables():
-            cb = torch.full((nblk,), -1, dtype=torch.int32)
-            cwi = torch.full((nblk,), -1, dtype=torch.int32)
-            pb = torch.full((nblk,), -1, dtype=torch.int32)
-            for b in range(B):
-                for k in range(K + 1):
-                    slot = b * (K + 1) + k
-                    if has_glue:
-                        pb[slot] = slot
-                    if k == 0:
-                        cb[slot], cwi[slot] = b, slot
-                    else:
-                        j = S + b * K + (k - 1)
-                        cb[j], cwi[j] = b, slot
-            return torch.stack([cb, cwi, pb, torch.full((nblk,), -1, dtype=torch.int32)])
-        tabs = E.cached_table(("csa_bwd", B, K, has_glue), dev, _bwd_tables)
-        cb, cwi, pb, nopool = tabs[0], tabs[1], tabs[2], tabs[3]
-        gidx = E.cached_table(("csa_bwd_gather", B, K, has_glue), dev, lambda: _bwd_tables()[1].clamp(min=0).long())
-        cw = ctx.comp.reshape(-1)[gidx].contiguous()
+        has_glue = st.glue is not None
+        cb, cwi, pb, gidx = _csa_bwd_tables(st, dev)
         lib = L.lib()
-        obs, ocs = 256 * geom.n_points, geom.n_points
-        grads_glue = [None] * 4
-        dpool = None
-        # The upstream gradient of block j is comp[b,k] * dOut[b]^T (+ the pooled-mean row vector): dOut is
-        # transposed ONCE per batch item into padded rows (it stays L2-resident) and csn_ln_bwd forms
-        # cw[j] * dOutT[cb[j]] + dpool[pb[j]]/N on the fly; the (2K+1)x larger dY is never materialised.
+        # dOut is transposed ONCE per batch item into padded rows (it stays L2-resident)
         dOutT = torch.empty(B * geom.rows_pad, 256, dtype=torch.float32, device=dev)
         amax = torch.zeros(1, dtype=torch.float32, device=dev)
         rc = lib.csn_pack_rows(dout.data_ptr(), None, dOutT.data_ptr(), geom.n_points, B, 256 * geom.n_points, 1, 0, 0, 1, 0,
@@ -443,31 +493,97 @@ class _CsaFn(torch.autograd.Function):
                                L.stream_ptr())
         L.check(rc, "csn_pack_rows(dOut)")
         # d comp[b,k] = <dOut[b]^T, MHA_k> with the LayerNorm output re-formed from z on the fly
-        dcomp = torch.zeros(B * (K + 1), dtype=torch.float32, device=dev) if has_glue else None
+        dcomp = None
         if has_glue:
+            dcomp = torch.zeros(B * (K + 1), dtype=torch.float32, device=dev)
             rc = lib.csn_block_dot(dOutT.data_ptr(), a.Z.data_ptr(), cb.data_ptr(), cwi.data_ptr(), dcomp.data_ptr(),
                                    nblk * geom.rows_pad, geom.rows_pad, geom.chunk_pad, geom.chunk, a.mean.data_ptr(),
                                    a.rstd.data_ptr(), a.gamma.data_ptr(), a.beta.data_ptr(), L.stream_ptr())
             L.check(rc, "csn_block_dot")
-        if has_glue:
-            pooled, loc, comp_g = ctx.glue
-            gl = torch.autograd.grad(comp_g, [pooled] + loc, dcomp.view(B, K + 1))
-            dpool = gl[0].contiguous()
-            grads_glue = list(gl[1:])
-            amax = amax + dpool.abs().max() / geom.n_points   # bound on |dY + dpool/N| for the gradient scaling (comp <= 1)
         need_dx = ctx.needs_input_grad[0] or ctx.needs_input_grad[1]
-        g = E.attention_backward(a, dOutT, need_dx, amax, bcast=dpool, bcast_idx=pb if dpool is not None else None,
-                                 bcast_scale=1.0 / geom.n_points, src_idx=cb, src_w=cw)
-        dx = dnb = None
-        if need_dx:
-            G = _rows_to_channel_major(g["dX"], S, max(n_src, n_src_nb), geom).view(B, K + 1, 256, -1, 1)
-            if ctx.needs_input_grad[0]:
-                dx = G[:, 0, :, :n_src].contiguous()
-            if ctx.needs_input_grad[1]:
-                dnb = G[:, :, :, :n_src_nb].clone()
-                dnb[:, 0] = 0   # slot 0 of x_neighbors is never read (csa_models.py:214,234)
+        g, grads_glue = _csa_backward_core(st, dOutT, amax, dcomp, need_dx)
+        dx, dnb = _csa_input_grads(g, st, ctx.needs_input_grad[0], ctx.needs_input_grad[1]) if need_dx else (None, None)
         return (dx, dnb, g["dWq"], g["dWk"], g["dWv"], g["dWo"], g["dgamma"], g["dbeta"], *grads_glue,
-                None, None, None, None, None)
+                None, None, None, None, None, None, None)
+
+
+def _csa_input_grads(g, st: _CsaState, want_x: bool, want_nb: bool):
+    B, K, S, nblk, n_src, n_src_nb = st.meta
+    geom = st.a.geom
+    G = _rows_to_channel_major(g["dX"], S, max(n_src, n_src_nb), geom).view(B, K + 1, 256, -1, 1)
+    dx = G[:, 0, :, :n_src].contiguous() if want_x else None
+    dnb = None
+    if want_nb:
+        dnb = G[:, :, :, :n_src_nb].clone()
+        dnb[:, 0] = 0   # slot 0 of x_neighbors is never read (csa_models.py:214,234)
+    return dx, dnb
+
+
+class _CsaLossFn(torch.autograd.Function):
+    """forward_csa / forward_ssa + the training scripts' masked cross-entropy (csa_models.py:182-242 +
+    csa_training.py:94-134) with the fused head kernel csn_csa_head: the weighted sum of the K+1 attention outputs, the
+    logit conv, the loss, the IoU counters AND their backward (d out as padded rows, d comp, d logit.weight) are one
+    pass over the pre-LayerNorm rows.  Returns (loss, stats) with stats = int32 [3*C + 2]:
+    #pred==c, #label==c, #(pred==c & label==c) over the unmasked points, then #correct and #labels out of range."""
+
+    @staticmethod
+    def forward(ctx, x, x_neighbors, labels, logit_w, ignore_index, wq, wk, wv, wo, gamma, beta, cq_w, cq_b, ck_w, ck_b,
+                n_head, dt, iters, chunk, dropout_p=0.0, seed=0):
+        st = _csa_forward_core(x, x_neighbors, wq, wk, wv, wo, gamma, beta, cq_w, cq_b, ck_w, ck_b, n_head, dt, iters,
+                               chunk, dropout_p, seed)
+        a, geom = st.a, st.a.geom
+        B, K, S, nblk, n_src, n_src_nb = st.meta
+        dev = x.device
+        Cn = logit_w.shape[0]
+        W = logit_w.detach().float().reshape(Cn, 256).contiguous()
+        lab = labels.reshape(B, -1)
+        if lab.dtype != torch.int64 or lab.stride(1) != 1:
+            lab = lab.to(torch.int64).contiguous()
+        if lab.shape[1] < geom.n_points:
+            raise IndexError(f"labels hold {lab.shape[1]} points per shape, the layer uses {geom.n_points}")
+        want_grad = any(ctx.needs_input_grad)
+        lib = L.lib()
+        NP = geom.rows_pad
+        n_tiles = B * (NP // 32)
+        grid = lib.csn_csa_head_grid(B, NP)
+        # one zero-initialised scratch vector: [n_valid | stats (3C+2) | amax | dcomp (B(K+1))]
+        ints = torch.zeros(1 + 3 * Cn + 2, dtype=torch.int32, device=dev)
+        flts = torch.zeros(1 + B * (K + 1), dtype=torch.float32, device=dev)
+        n_valid, stats = ints[:1], ints[1:]
+        amax, dcomp = flts[:1], flts[1:]
+        loss_part = torch.empty(n_tiles, dtype=torch.float32, device=dev)
+        dOutT = torch.empty(B * NP, 256, dtype=torch.float32, device=dev) if want_grad else None
+        dW_part = torch.empty(grid, Cn, 256, dtype=torch.float32, device=dev) if want_grad else None
+        dW = torch.empty(Cn, 256, dtype=torch.float32, device=dev) if want_grad else None
+        has_glue = st.glue is not None
+        rc = lib.csn_csa_head(a.Z.data_ptr(), a.mean.data_ptr(), a.rstd.data_ptr(), gamma.data_ptr(), beta.data_ptr(),
+                              st.blk.data_ptr(), st.comp.data_ptr(), B, K + 1, W.data_ptr(), Cn, lab.data_ptr(), lab.stride(0),
+                              int(ignore_index), n_valid.data_ptr(), geom.n_points, geom.chunk, geom.chunk_pad, NP,
+                              loss_part.data_ptr(), dOutT.data_ptr() if want_grad else None,
+                              amax.data_ptr() if want_grad else None,
+                              dcomp.data_ptr() if (want_grad and has_glue) else None,
+                              dW_part.data_ptr() if want_grad else None, dW.data_ptr() if want_grad else None,
+                              stats.data_ptr(), None, L.stream_ptr())
+        L.check(rc, "csn_csa_head")
+        loss = loss_part.sum() / n_valid.clamp_min(1).to(torch.float32)[0]
+        ctx.st = st
+        ctx.saved = (dOutT, amax, dcomp if has_glue else None, dW, logit_w.shape)
+        ctx.mark_non_differentiable(stats)
+        return loss, stats
+
+    @staticmethod
+    def backward(ctx, gout, _gstats):
+        st = ctx.st
+        dOutT, amax, dcomp, dW, wshape = ctx.saved
+        if dOutT is None:
+            raise L.CsnError("forward_loss ran without gradients enabled: nothing to backpropagate")
+        gs = gout.detach().float().reshape(1)
+        need_dx = ctx.needs_input_grad[0] or ctx.needs_input_grad[1]
+        g, grads_glue = _csa_backward_core(st, dOutT, amax, dcomp, need_dx, out_scale=gs)
+        dx, dnb = _csa_input_grads(g, st, ctx.needs_input_grad[0], ctx.needs_input_grad[1]) if need_dx else (None, None)
+        gw = (dW * gs).view(wshape) if ctx.needs_input_grad[3] else None
+        return (dx, dnb, None, gw, None, g["dWq"], g["dWk"], g["dWv"], g["dWo"], g["dgamma"], g["dbeta"], *grads_glue,
+                None, None, None, None, None, None)
 
 
 class CrossShapeAt(nn.Module):
@@ -509,14 +625,26 @@ class CrossShapeAt(nn.Module):
             x = self.forward_fcf_csaf_logitf(x, neighbor_feats, mode)  # undefined in the reference too
         return x
 
-    def forward_loss(self, x, mode, neighbor_feats, labels, ignore_index: int = 0):
-        """forward(...) followed by the training scripts' masked cross-entropy (csa_training.py:94-108), with the
-        logit conv, the loss and their backward fused into one pass over the layer's output (segmentation_loss)."""
-        if self.attention_type == 'csa':
-            feats = self.get_csa_feats(x, neighbor_feats, mode)
-        else:
-            feats, _ = self.get_ssa_feats(x, mode)
-        return segmentation_loss(feats, self.logit.weight, labels, ignore_index)
+    def forward_loss(self, x, mode, neighbor_feats, labels, ignore_index: int = 0, return_stats: bool = False):
+        """forward(...) followed by the training scripts' masked cross-entropy (csa_training.py:94-108), with the weighted
+        sum of the attention outputs, the logit conv, the loss, the accuracy / IoU counters (csa_training.py:110-134) and
+        their backward fused into one pass over the attention blocks' pre-LayerNorm rows (csn_csa_head).
+        return_stats=True also returns an int32 vector [3*C + 2]: per class #pred, #label, #(pred & label) over the
+        unmasked points (intsc = the third, union = first + second - third), then #correct and #labels out of range."""
+        if not self.after_fc:
+            raise L.CsnError("forward_loss: the fused head follows the attention layer (after_fc=True models)")
+        nb = neighbor_feats if self.attention_type == 'csa' else None
+        p, seed = self._dropout_state()
+        loss, stats = _CsaLossFn.apply(x, nb, labels, self.logit.weight, ignore_index, *self._csa_args(), p, seed)
+        return (loss, stats) if return_stats else loss
+
+    def _dropout_state(self):
+        """(p, seed) of this call: dropout follows `module.training` like the reference (csa_models.py:56,136; `mode`
+        is ignored); the seed is drawn from torch's CPU generator so torch.manual_seed reproduces a run."""
+        p = float(self.attention.dropout.p) if self.training else 0.0
+        if p <= 0.0:
+            return 0.0, 0
+        return p, int(torch.randint(0, 2 ** 31 - 1, (1,)).item())
 
     def forward_ssa(self, x, mode):
         if self.after_fc:
@@ -538,12 +666,12 @@ class CrossShapeAt(nn.Module):
 
     def get_ssa_feats(self, x, mode):
         """(B,256,N,1) -> (SSA features (B,256,10000,1), attention of the last chunk)."""
-        return _CsaFn.apply(x, None, *self._csa_args())
+        return _CsaFn.apply(x, None, *self._csa_args(), True, *self._dropout_state())
 
     def get_csa_feats(self, x, x_neighbors, mode):
         """x (B,256,N,1); x_neighbors (B,K+1,256,N,1) (slot 0 = the query, skipped; CPU tensors are
         accepted and moved, like csa_models.py:216,236) -> (B,256,10000,1)."""
-        return _CsaFn.apply(x, x_neighbors, *self._csa_args(), False)[0]
+        return _CsaFn.apply(x, x_neighbors, *self._csa_args(), False, *self._dropout_state())[0]
 
     # -- retrieval (csa_models.py:244-280)
     def get_retrieval_measure(self, ssa_feats_1, ssa_feats_2):

@@ -172,6 +172,27 @@ int csn_seg_loss(const float* feat, int64_t b_stride, int64_t ch_stride, int32_t
                  const float* W, int32_t n_classes, const int64_t* labels, int32_t ignore_index, int32_t* n_valid,
                  float* loss_part, float* dlogits, float* dfeat, const float* grad_scale, void* stream);
 
+/* Fused CSA head, forward AND backward in one pass over the attention blocks' pre-LayerNorm rows Z
+ * (row r of block j at Z[(j*rows_pad + r)*256], statistics mean/rstd per row, LayerNorm affine gamma/beta):
+ *   y[b][r] = sum_k w[b*n_k+k] * LayerNorm(Z[blk[b*n_k+k]][r])      the weighted sum, csa_models.py:232-238
+ *   logits = W y (csa_models.py:201);  masked cross-entropy and accuracy (csa_training.py:94-108);  per-class IoU
+ *   counters (csa_training.py:110-134);  and, when dOutT != NULL, the backward of all of it:
+ *   dOutT[b*rows_pad + r] = W^T dlogits (row-major padded rows, zero in pad rows / masked points: what csn_ln_bwd
+ *   reads through src_idx),  *amax = max|dOutT|,  dcomp[b*n_k+k] += <dOutT[b], LayerNorm(Z[blk])>,
+ *   dW[c][ch] = sum dlogits[c] y[ch]  (dW_part: [csn_csa_head_grid()][n_classes][256] scratch, reduced in fixed order).
+ * Zero-initialised by the caller: n_valid (1 int), stats (3*n_classes + 2 ints: #pred==c, #label==c, #both, then
+ * #correct, #labels outside [0, n_classes)), amax (1 float), dcomp.  loss_part: n_b*rows_pad/32 floats whose sum
+ * divided by *n_valid is the loss.  y_out (optional): the combined features as padded rows.  labels: int64,
+ * (b, point n) at labels[b*lab_stride + n]; n_k <= 6; n_classes <= 64.
+ * Replaces csn_combine_fwd + the ATen conv/log-softmax/nll kernels and their backwards + csn_pack_rows(dOut) +
+ * csn_block_dot. */
+int csn_csa_head_grid(int32_t n_b, int32_t rows_pad);
+int csn_csa_head(const float* Z, const float* mean, const float* rstd, const float* gamma, const float* beta,
+                 const int32_t* blk, const float* w, int32_t n_b, int32_t n_k, const float* W, int32_t n_classes,
+                 const int64_t* labels, int64_t lab_stride, int32_t ignore_index, int32_t* n_valid, int32_t n_points,
+                 int32_t chunk, int32_t chunk_pad, int32_t rows_pad, float* loss_part, float* dOutT, float* amax,
+                 float* dcomp, float* dW_part, float* dW, int32_t* stats, float* y_out, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * HBM-bound pieces of the CSA/SSA layer.  Row buffers use "padded" coordinates: a shape's block has
  * rows_pad = n_chunks*chunk_pad rows; chunk c (points [c*chunk, (c+1)*chunk)) occupies rows

@@ -206,3 +206,82 @@ def test_fused_segmentation_loss_matches_conv_plus_masked_ce(C):
     # all points masked: loss 0, zero gradients, no NaN
     z = midfc.segmentation_loss(feats.detach(), W.detach(), torch.zeros_like(lab))
     assert z.item() == 0.0
+
+
+@pytest.mark.parametrize("name", ["midfc_csa_cfg1", "midfc_csa_b2_k2_h2"])
+def test_forward_loss_fused_head_matches_reference(name):
+    """CrossShapeAt.forward_loss (csn_csa_head: weighted sum + logit conv + masked CE + IoU counters + their backward in
+    one pass) against the reference's loss and gradients (golden vectors) and against the unfused module path."""
+    from csn_b200 import midfc
+    g = G.load(name)
+    seed, h, K, B, C = (int(g[k]) for k in ("seed", "n_heads", "K", "batch", "num_classes"))
+    tol = TOL["fp16"]
+    m = midfc.get_model("csa", C, h, K).cuda().eval()
+    m.load_state_dict(synth.midfc_state(seed, h, C))
+    x, nb = synth.csa_batch(seed + 1, B, K)
+    label = _labels(seed + 2, B, x.shape[2], C).cuda()
+    x = x.cuda().requires_grad_(True)
+    nb = nb.cuda()
+    loss, stats = m.forward_loss(x, "test", nb, label, return_stats=True)
+    (loss * 2.0).backward()   # a non-unit upstream gradient exercises the out_scale path
+    assert abs(loss.item() - float(g["loss"])) < 10 * tol
+    G.compare_sampled(g, "grad.x", x.grad / 2.0, tol)
+    params = dict(m.named_parameters())
+    names = [k[len("grad."):-len(".values")] for k in g.files
+             if k.startswith("grad.") and k.endswith(".values") and k != "grad.x.values"]
+    assert "logit.weight" in names
+    for pname in names:
+        if pname.startswith("compatibility"):
+            continue   # covered (with its fp64 calibration) by test_compatibility_gradients_against_fp64
+        G.compare_sampled(g, "grad." + pname, params[pname].grad / 2.0, tol, what=pname)
+    # counters (csa_training.py:110-134) against the unfused logits
+    with torch.no_grad():
+        logits = m(x.detach(), "test", nb).squeeze(-1)            # (B, C, N)
+    pred = logits.argmax(1).reshape(-1)
+    lab = label.reshape(-1)
+    keep = lab > 0
+    st = stats.cpu().tolist()
+    n_pred, n_lab, n_both, correct, bad = st[:C], st[C:2 * C], st[2 * C:3 * C], st[3 * C], st[3 * C + 1]
+    assert bad == 0
+    assert n_lab == [int(((lab == c) & keep).sum()) for c in range(C)]
+    want_pred = [int(((pred == c) & keep).sum()) for c in range(C)]
+    want_both = [int(((pred == c) & (lab == c) & keep).sum()) for c in range(C)]
+    # near-ties of the two largest logits may resolve differently (TF32 conv vs fp32 FMA): allow a handful of flips
+    assert sum(abs(a - b) for a, b in zip(n_pred, want_pred)) <= 8
+    assert sum(abs(a - b) for a, b in zip(n_both, want_both)) <= 8
+    assert abs(correct - int(((pred == lab) & keep).sum())) <= 8
+    # forward only (no autograd graph): same loss, no gradient buffers
+    with torch.no_grad():
+        l2 = m.forward_loss(x.detach(), "test", nb, label)
+    assert abs(l2.item() - loss.item()) < 1e-6
+
+
+@pytest.mark.parametrize("C", [4, 33, 51])
+def test_fused_head_class_counts_and_all_masked(C):
+    """Other class counts (template instantiations 16 / 64) against the unfused path, SSA model (no compatibility
+    glue), plus the all-points-masked case (loss 0, zero gradients, no NaN)."""
+    from csn_b200 import midfc
+    m = midfc.get_model("ssa", C, 1).cuda().eval()
+    x = synth.iid_features(synth.gen(40 + C), 1).cuda()
+    lab = _labels(41 + C, 1, x.shape[2], C).cuda()
+    loss = m.forward_loss(x, "test", None, lab)
+    loss.backward()
+    got = {n: p.grad.clone() for n, p in m.named_parameters() if p.grad is not None}
+    m.zero_grad()
+    tf32 = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        ref = _masked_ce(m(x, "test"), lab)
+        ref.backward()
+    finally:
+        torch.backends.cudnn.allow_tf32 = tf32
+    assert abs(loss.item() - ref.item()) < 2e-5 * max(1.0, abs(ref.item()))
+    for n, p in m.named_parameters():
+        if p.grad is not None:
+            assert G.rel_err(got[n], p.grad) < 5e-4, (n, G.rel_err(got[n], p.grad))
+    m.zero_grad()
+    z = m.forward_loss(x, "test", None, torch.zeros_like(lab))
+    z.backward()
+    assert z.item() == 0.0
+    assert all(torch.isfinite(p.grad).all() and float(p.grad.abs().max()) == 0.0
+               for n, p in m.named_parameters() if p.grad is not None)
