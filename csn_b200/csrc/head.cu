@@ -11,12 +11,16 @@
 // + csn_block_dot: the (B,256,N) output activation, the logits and the output gradient never reach HBM in
 // channel-major form, Z is read once from HBM (the second read for dcomp hits L2: same CTA, same tile).
 //
-// CTA = 256 threads, persistent over tiles of 32 padded rows.  Phases per tile:
-//   P1 (warp per row)  : y rows -> SMEM tile
-//   P2 (8 threads/row) : logits, softmax, loss, argmax, dlogits -> SMEM ; IoU counters
-//   P3a (thread = channel): dW += dlogits^T y (register accumulators, flushed once per CTA)
-//   P3b (8 threads/row): dy = W^T dlogits -> the SMEM tile (y is dead)
-//   P4 (warp per row)  : dOutT rows, max|dy|, dcomp dots against the re-normalised Z rows
+// CTA = 256 threads, ONE per SM, persistent over a contiguous range of tiles of R (16 or 8) padded rows.  The Z rows
+// of a tile (R contiguous KB per attention block) and their statistics arrive by 1-D bulk copies (cp.async.bulk +
+// mbarrier) into a 2-stage SMEM ring: the whole next tile is in flight while this one is processed, and the second
+// use of the rows (dcomp) reads SMEM, not L2.  Phases per tile:
+//   P1  (warp per row)       : y rows -> SMEM tile ys
+//   P2a (warp = 32-channel slice of the contraction, thread = 2 rows x 4 classes): partial logits -> SMEM
+//   P2b (warp per row, lane = class): logits, softmax, loss, argmax, dlogits -> SMEM ; IoU counters
+//   P3a (thread = channel)   : dW += dlogits^T y (register accumulators, flushed once per CTA)
+//   P3b (warp = 32 channels, thread = 4 rows x 4 channels): dy = W^T dlogits -> ys (y is dead)
+//   P4  (warp per row)       : dOutT rows, max|dy|, dcomp dots against the re-normalised Z rows (from SMEM)
 #include <stdint.h>
 
 #include "host_util.h"
@@ -25,7 +29,6 @@
 namespace csn {
 
 constexpr int HD_DM = 256;
-constexpr int HD_ROWS = 32;       // rows per tile
 constexpr int HD_LD = 260;        // SMEM row stride in floats (1040 B: 16-byte aligned, bank offset 4 per row)
 constexpr int HD_MAXK = 6;        // K + 1 <= 6 (reference: K <= 5)
 
@@ -36,9 +39,9 @@ struct HeadArgs {
   int n_k;
   const float* W; int C;     // logit weights [C][256]
   const long long* labels; long long lab_stride; int ignore_index;
-  const int* n_valid;        // device scalar: number of unmasked points (csn_count_valid)
+  const int* n_valid;        // device scalar: number of unmasked points
   int n_points, chunk, chunk_pad, rows_pad, n_tiles, tiles_per_b;
-  float* loss_part;          // [n_tiles]: sum of -log p[label] over the tile's valid points
+  float* loss_part;          // [gridDim.x]: sum of -log p[label] over the CTA's valid points
   float* dOutT;              // [n_b*rows_pad][256] or null (forward only)
   float* amax;               // optional: max |dOutT| (atomic max on the bit pattern; zero-initialised by the caller)
   float* dcomp;              // [n_b*n_k], atomically accumulated (zero-initialised by the caller) or null
@@ -47,16 +50,37 @@ struct HeadArgs {
   float* y_out;              // optional [n_b*rows_pad][256]: the combined features, row-major padded rows
 };
 
-template <int CMAX, int NK>
-__global__ void __launch_bounds__(256, 2) csa_head_kernel(const HeadArgs p) {
-  extern __shared__ __align__(16) float hsm[];
-  float* ys = hsm;                                  // [32][260]
-  float* Wsm = ys + HD_ROWS * HD_LD;                // [CMAX][260]
-  float* dls = Wsm + CMAX * HD_LD;                  // [32][CMAX]
-  float* red = dls + HD_ROWS * CMAX;                // [8][8]
-  float* gsm = red + 64;                            // gamma [256] | beta [256]
-  int* hist = reinterpret_cast<int*>(gsm + 512);    // [3*CMAX + 2]
-  constexpr int CPT = CMAX / 8;                     // classes per thread in P2
+template <int CMAX, int NK, int R>
+struct HeadSmem {
+  static constexpr int DLS = CMAX + 4;                       // dlogits row stride (floats)
+  static constexpr int STAGE = NK * (R * HD_DM + 2 * R);     // floats per stage: Z rows, then mean, then rstd
+  static constexpr int OFF_YS = 2 * STAGE;
+  static constexpr int OFF_W = OFF_YS + R * HD_LD;
+  static constexpr int OFF_PART = OFF_W + CMAX * HD_LD;
+  static constexpr int OFF_DLS = OFF_PART + 8 * R * CMAX;
+  static constexpr int OFF_RED = OFF_DLS + R * DLS;
+  static constexpr int OFF_G = OFF_RED + 64;
+  static constexpr int OFF_HIST = OFF_G + 512;
+  static constexpr int OFF_BAR = (OFF_HIST + 3 * CMAX + 2 + 3) / 4 * 4;
+  static constexpr int BYTES = (OFF_BAR + 4) * 4;
+};
+
+template <int CMAX, int NK, int R>
+__global__ void __launch_bounds__(256, 1) csa_head_kernel(const HeadArgs p) {
+  using SM = HeadSmem<CMAX, NK, R>;
+  extern __shared__ __align__(128) float hsm[];
+  float* ys = hsm + SM::OFF_YS;                       // [R][260]
+  float* Wsm = hsm + SM::OFF_W;                       // [CMAX][260]
+  float* part = hsm + SM::OFF_PART;                   // [8][R*CMAX]
+  float* dls = hsm + SM::OFF_DLS;                     // [R][DLS]
+  float* red = hsm + SM::OFF_RED;                     // [8][8]
+  float* gsm = hsm + SM::OFF_G;                       // gamma [256] | beta [256]
+  int* hist = reinterpret_cast<int*>(hsm + SM::OFF_HIST);
+  const uint32_t bar0 = smem_u32(hsm + SM::OFF_BAR);
+  constexpr int RPT = R / 8;                          // rows per thread in P2a / rows per warp in P1, P2b, P4
+  constexpr int CQ = CMAX / 4;                        // classes per thread in P2a
+  constexpr int CL = (CMAX + 31) / 32;                // classes per lane in P2b
+  constexpr int RQ = R / 4;                           // rows per thread in P3b
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const bool grad = p.dOutT != nullptr;
 
@@ -67,51 +91,95 @@ __global__ void __launch_bounds__(256, 2) csa_head_kernel(const HeadArgs p) {
   for (int i = tid; i < 3 * CMAX + 2; i += 256) hist[i] = 0;
   gsm[tid] = __ldg(p.gamma + tid);
   gsm[256 + tid] = __ldg(p.beta + tid);
+  if (tid == 0) {
+    mbar_init(bar0, 1);
+    mbar_init(bar0 + 8, 1);
+    fence_mbar_init();
+  }
   const float4* gs4 = reinterpret_cast<const float4*>(gsm);
   const float inv_nv = 1.f / (float)max(__ldg(p.n_valid), 1);
   float dw[CMAX];
 #pragma unroll
   for (int c = 0; c < CMAX; ++c) dw[c] = 0.f;
-  float amx = 0.f;
+  float amx = 0.f, lacc = 0.f;
+  float dc[NK];
+#pragma unroll
+  for (int k = 0; k < NK; ++k) dc[k] = 0.f;
   __syncthreads();
 
-  for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+  const int t_begin = (int)((long long)p.n_tiles * blockIdx.x / gridDim.x);
+  const int t_end = (int)((long long)p.n_tiles * (blockIdx.x + 1) / gridDim.x);
+  // one thread feeds the ring: R KB of Z rows + R means + R rstds per attention block of the tile's query
+  auto issue = [&](int tile, int stage) {
     const int b = tile / p.tiles_per_b;
-    const int r0 = (tile - b * p.tiles_per_b) * HD_ROWS;
-    // per-(b,k) block index and weight (n_k <= 6 values each, L1-resident)
-    int kb[NK]; float kw[NK];
+    const int r0 = (tile - b * p.tiles_per_b) * R;
+    float* st = hsm + stage * SM::STAGE;
+    const uint32_t bar = bar0 + 8u * stage;
+    mbar_arrive_expect_tx(bar, (uint32_t)p.n_k * (R * HD_DM + 2 * R) * 4u);
+    for (int k = 0; k < p.n_k; ++k) {
+      const long long row = (long long)__ldg(p.blk + b * p.n_k + k) * p.rows_pad + r0;
+      bulk_load_1d(smem_u32(st + k * R * HD_DM), p.Z + row * HD_DM, R * HD_DM * 4, bar);
+      bulk_load_1d(smem_u32(st + NK * R * HD_DM + k * R), p.mean + row, R * 4, bar);
+      bulk_load_1d(smem_u32(st + NK * R * HD_DM + NK * R + k * R), p.rstd + row, R * 4, bar);
+    }
+  };
+  // dcomp partial sums of the current query are kept in registers across its tiles
+  auto flush_dcomp = [&](int b) {   // called by every thread (CTA-uniform)
 #pragma unroll
     for (int k = 0; k < NK; ++k) {
-      kb[k] = (k < p.n_k) ? __ldg(p.blk + b * p.n_k + k) : 0;
-      kw[k] = (k < p.n_k) ? __ldg(p.w + b * p.n_k + k) : 0.f;
+      const float s = warp_sum(dc[k]);
+      if (lane == 0) red[warp * 8 + k] = s;
+      dc[k] = 0.f;
     }
+    __syncthreads();
+    if (tid < p.n_k) {
+      float s = 0.f;
+#pragma unroll
+      for (int w2 = 0; w2 < 8; ++w2) s += red[w2 * 8 + tid];
+      atomicAdd(p.dcomp + b * p.n_k + tid, s);
+    }
+    __syncthreads();
+  };
+  if (tid == 0 && t_begin < t_end) issue(t_begin, 0);
+  int cur_b = -1;
+
+  for (int tile = t_begin; tile < t_end; ++tile) {
+    const int it = tile - t_begin, stage = it & 1;
+    const int b = tile / p.tiles_per_b;
+    const int r0 = (tile - b * p.tiles_per_b) * R;
+    if (b != cur_b) {
+      if (cur_b >= 0 && grad && p.dcomp) flush_dcomp(cur_b);
+      cur_b = b;
+    }
+    if (tid == 0 && tile + 1 < t_end) issue(tile + 1, stage ^ 1);   // that stage was released by the barrier ending tile-1
+    float kw[NK];
     float wsum = 0.f;
 #pragma unroll
-    for (int k = 0; k < NK; ++k) wsum += kw[k];
+    for (int k = 0; k < NK; ++k) {
+      kw[k] = (k < p.n_k) ? __ldg(p.w + b * p.n_k + k) : 0.f;
+      wsum += kw[k];
+    }
+    const float* zs = hsm + stage * SM::STAGE;
+    const float* ms = zs + NK * R * HD_DM;
+    const float* rss = ms + NK * R;
+    mbar_wait(bar0 + 8u * stage, (uint32_t)(it >> 1) & 1u);
 
     // ------------------------------------------------------------------ P1: y rows
-#pragma unroll 1
-    for (int i = 0; i < 4; ++i) {
-      const int rr = warp * 4 + i, r = r0 + rr;
+#pragma unroll
+    for (int i = 0; i < RPT; ++i) {
+      const int rr = warp + 8 * i, r = r0 + rr;
       const int ii = r % p.chunk_pad;
       const bool rvalid = ii < p.chunk && (r / p.chunk_pad) * p.chunk + ii < p.n_points;
       float4 ta = make_float4(0.f, 0.f, 0.f, 0.f), tc = ta;
       if (rvalid) {
-        float4 za[NK], zc[NK]; float mu[NK], rs[NK];
 #pragma unroll
         for (int k = 0; k < NK; ++k)
           if (k < p.n_k) {
-            const long long row = (long long)kb[k] * p.rows_pad + r;
-            const float4* z4 = reinterpret_cast<const float4*>(p.Z + row * HD_DM);
-            za[k] = __ldg(z4 + lane); zc[k] = __ldg(z4 + 32 + lane);
-            mu[k] = __ldg(p.mean + row); rs[k] = __ldg(p.rstd + row);
-          }
-#pragma unroll
-        for (int k = 0; k < NK; ++k)
-          if (k < p.n_k) {
-            const float a = kw[k] * rs[k], m = mu[k];
-            ta.x += a * (za[k].x - m); ta.y += a * (za[k].y - m); ta.z += a * (za[k].z - m); ta.w += a * (za[k].w - m);
-            tc.x += a * (zc[k].x - m); tc.y += a * (zc[k].y - m); tc.z += a * (zc[k].z - m); tc.w += a * (zc[k].w - m);
+            const float4* z4 = reinterpret_cast<const float4*>(zs + (k * R + rr) * HD_DM);
+            const float4 za = z4[lane], zc = z4[32 + lane];
+            const float m = ms[k * R + rr], a = kw[k] * rss[k * R + rr];
+            ta.x += a * (za.x - m); ta.y += a * (za.y - m); ta.z += a * (za.z - m); ta.w += a * (za.w - m);
+            tc.x += a * (zc.x - m); tc.y += a * (zc.y - m); tc.z += a * (zc.z - m); tc.w += a * (zc.w - m);
           }
         const float4 g0 = gs4[lane], g1 = gs4[32 + lane], b0 = gs4[64 + lane], b1 = gs4[96 + lane];
         ta.x = ta.x * g0.x + wsum * b0.x; ta.y = ta.y * g0.y + wsum * b0.y; ta.z = ta.z * g0.z + wsum * b0.z; ta.w = ta.w * g0.w + wsum * b0.w;
@@ -126,58 +194,78 @@ __global__ void __launch_bounds__(256, 2) csa_head_kernel(const HeadArgs p) {
     }
     __syncthreads();
 
-    // ------------------------------------------------------------------ P2: logits -> softmax -> loss / dlogits
+    // ------------------------------------------------------------------ P2a: partial logits over this warp's 32 channels
     {
-      const int rr = tid >> 3, cg = tid & 7, r = r0 + rr;
+      const int rg = lane & 7, cq = lane >> 3;
+      float acc[RPT][CQ];
+#pragma unroll
+      for (int i = 0; i < RPT; ++i)
+#pragma unroll
+        for (int j = 0; j < CQ; ++j) acc[i][j] = 0.f;
+#pragma unroll 2
+      for (int k4 = warp * 8; k4 < warp * 8 + 8; ++k4) {
+        float4 yv[RPT];
+#pragma unroll
+        for (int i = 0; i < RPT; ++i) yv[i] = *reinterpret_cast<const float4*>(ys + (rg + 8 * i) * HD_LD + k4 * 4);
+#pragma unroll
+        for (int j = 0; j < CQ; ++j) {
+          const float4 wv = *reinterpret_cast<const float4*>(Wsm + (cq + 4 * j) * HD_LD + k4 * 4);
+#pragma unroll
+          for (int i = 0; i < RPT; ++i) acc[i][j] += (yv[i].x * wv.x + yv[i].y * wv.y) + (yv[i].z * wv.z + yv[i].w * wv.w);
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < RPT; ++i)
+#pragma unroll
+        for (int j = 0; j < CQ; ++j) part[warp * (R * CMAX) + (rg + 8 * i) * CMAX + cq + 4 * j] = acc[i][j];
+    }
+    __syncthreads();
+
+    // ------------------------------------------------------------------ P2b: softmax, loss, argmax, dlogits, counters
+#pragma unroll
+    for (int i = 0; i < RPT; ++i) {
+      const int rr = warp + 8 * i, r = r0 + rr;
       const int ii = r % p.chunk_pad;
       const int n = (r / p.chunk_pad) * p.chunk + ii;
       const bool rvalid = ii < p.chunk && n < p.n_points;
-      float acc[CPT];
-#pragma unroll
-      for (int i = 0; i < CPT; ++i) acc[i] = 0.f;
-      const float4* y4 = reinterpret_cast<const float4*>(ys + rr * HD_LD);
-#pragma unroll 4
-      for (int k4 = 0; k4 < 64; ++k4) {
-        const float4 yv = y4[k4];
-#pragma unroll
-        for (int i = 0; i < CPT; ++i) {
-          const float4 wv = *reinterpret_cast<const float4*>(Wsm + (cg + 8 * i) * HD_LD + k4 * 4);
-          acc[i] += (yv.x * wv.x + yv.y * wv.y) + (yv.z * wv.z + yv.w * wv.w);
-        }
-      }
-      long long lab = rvalid ? __ldg(p.labels + (long long)b * p.lab_stride + n) : (long long)p.ignore_index;
-      const bool in_range = lab >= 0 && lab < p.C;
-      const bool pvalid = rvalid && lab != p.ignore_index && in_range;
+      float lg[CL];
       float mx = -INFINITY; int bi = 0x7fffffff;
 #pragma unroll
-      for (int i = 0; i < CPT; ++i) {
-        const int c = cg + 8 * i;
-        if (c < p.C && acc[i] > mx) { mx = acc[i]; bi = c; }
+      for (int j = 0; j < CL; ++j) {
+        const int c = lane + 32 * j;
+        float s = 0.f;
+        if (c < CMAX) {
+#pragma unroll
+          for (int w2 = 0; w2 < 8; ++w2) s += part[w2 * (R * CMAX) + rr * CMAX + c];
+        }
+        lg[j] = s;
+        if (c < p.C && s > mx) { mx = s; bi = c; }
       }
 #pragma unroll
-      for (int o = 1; o < 8; o <<= 1) {   // the 8 threads of a row are consecutive lanes
+      for (int o = 1; o < 32; o <<= 1) {
         const float om = __shfl_xor_sync(0xffffffffu, mx, o);
         const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
         if (om > mx || (om == mx && oi < bi)) { mx = om; bi = oi; }
       }
-      float e[CPT], se = 0.f;
+      float e[CL], se = 0.f;
 #pragma unroll
-      for (int i = 0; i < CPT; ++i) {
-        e[i] = (cg + 8 * i < p.C) ? __expf(acc[i] - mx) : 0.f;
-        se += e[i];
+      for (int j = 0; j < CL; ++j) {
+        e[j] = (lane + 32 * j < p.C) ? __expf(lg[j] - mx) : 0.f;
+        se += e[j];
       }
-#pragma unroll
-      for (int o = 1; o < 8; o <<= 1) se += __shfl_xor_sync(0xffffffffu, se, o);
+      se = warp_sum(se);
+      const long long lab = rvalid ? __ldg(p.labels + (long long)b * p.lab_stride + n) : (long long)p.ignore_index;
+      const bool in_range = lab >= 0 && lab < p.C;
+      const bool pvalid = rvalid && lab != p.ignore_index && in_range;
       const float inv = 1.f / se;
-      float lterm = 0.f;
 #pragma unroll
-      for (int i = 0; i < CPT; ++i) {
-        const int c = cg + 8 * i;
+      for (int j = 0; j < CL; ++j) {
+        const int c = lane + 32 * j;
         const bool hit = pvalid && c == (int)lab;
-        if (hit) lterm = -(acc[i] - mx - __logf(se));
-        dls[rr * CMAX + c] = pvalid ? (e[i] * inv - (hit ? 1.f : 0.f)) * inv_nv : 0.f;
+        if (hit) lacc += -(lg[j] - mx - __logf(se));
+        if (c < CMAX) dls[rr * SM::DLS + c] = pvalid ? (e[j] * inv - (hit ? 1.f : 0.f)) * inv_nv : 0.f;
       }
-      if (cg == 0) {
+      if (lane == 0) {
         if (pvalid) {
           atomicAdd(hist + bi, 1);
           atomicAdd(hist + CMAX + (int)lab, 1);
@@ -186,20 +274,17 @@ __global__ void __launch_bounds__(256, 2) csa_head_kernel(const HeadArgs p) {
           atomicAdd(hist + 3 * CMAX + 1, 1);
         }
       }
-      lterm = warp_sum(lterm);
-      if (lane == 0) red[warp] = lterm;
     }
     __syncthreads();
-    if (tid == 0) p.loss_part[tile] = ((red[0] + red[1]) + (red[2] + red[3])) + ((red[4] + red[5]) + (red[6] + red[7]));
-    if (!grad) { __syncthreads(); continue; }
+    if (!grad) continue;   // (the next tile's first barrier orders its ys writes after this tile's reads)
 
     // ------------------------------------------------------------------ P3a: dW[c][tid] += sum_r dl[r][c] * y[r][tid]
 #pragma unroll 4
-    for (int rr = 0; rr < HD_ROWS; ++rr) {
+    for (int rr = 0; rr < R; ++rr) {
       const float yv = ys[rr * HD_LD + tid];
 #pragma unroll
       for (int q = 0; q < CMAX / 4; ++q) {
-        const float4 d4 = *reinterpret_cast<const float4*>(dls + rr * CMAX + q * 4);
+        const float4 d4 = *reinterpret_cast<const float4*>(dls + rr * SM::DLS + q * 4);
         dw[4 * q] += d4.x * yv; dw[4 * q + 1] += d4.y * yv; dw[4 * q + 2] += d4.z * yv; dw[4 * q + 3] += d4.w * yv;
       }
     }
@@ -207,85 +292,63 @@ __global__ void __launch_bounds__(256, 2) csa_head_kernel(const HeadArgs p) {
 
     // ------------------------------------------------------------------ P3b: dy[r][ch] = sum_c dl[r][c] W[c][ch]  (into ys)
     {
-      const int rr = tid >> 3, j = tid & 7;
-      float4 a4[8];
+      const int rg = lane >> 3, ch = warp * 32 + (lane & 7) * 4;
+      float4 a4[RQ];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) a4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll 2
-      for (int c = 0; c < CMAX; ++c) {
-        if (c >= p.C) break;
-        const float d = dls[rr * CMAX + c];
+      for (int i = 0; i < RQ; ++i) a4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 3
+      for (int c = 0; c < p.C; ++c) {
+        const float4 wv = *reinterpret_cast<const float4*>(Wsm + c * HD_LD + ch);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const float4 wv = *reinterpret_cast<const float4*>(Wsm + c * HD_LD + 32 * i + 4 * j);
+        for (int i = 0; i < RQ; ++i) {
+          const float d = dls[(rg + 4 * i) * SM::DLS + c];
           a4[i].x += d * wv.x; a4[i].y += d * wv.y; a4[i].z += d * wv.z; a4[i].w += d * wv.w;
         }
       }
 #pragma unroll
-      for (int i = 0; i < 8; ++i) *reinterpret_cast<float4*>(ys + rr * HD_LD + 32 * i + 4 * j) = a4[i];
+      for (int i = 0; i < RQ; ++i) *reinterpret_cast<float4*>(ys + (rg + 4 * i) * HD_LD + ch) = a4[i];
     }
     __syncthreads();
 
     // ------------------------------------------------------------------ P4: dOutT rows, amax, dcomp
-    {
-      float dc[NK];
 #pragma unroll
-      for (int k = 0; k < NK; ++k) dc[k] = 0.f;
-#pragma unroll 1
-      for (int i = 0; i < 4; ++i) {
-        const int rr = warp * 4 + i, r = r0 + rr;
-        const int ii = r % p.chunk_pad;
-        const bool rvalid = ii < p.chunk && (r / p.chunk_pad) * p.chunk + ii < p.n_points;
-        const float4 da = *reinterpret_cast<const float4*>(ys + rr * HD_LD + lane * 4);
-        const float4 dc4 = *reinterpret_cast<const float4*>(ys + rr * HD_LD + 128 + lane * 4);
-        float4* o4 = reinterpret_cast<float4*>(p.dOutT + ((long long)b * p.rows_pad + r) * HD_DM);
-        o4[lane] = da; o4[32 + lane] = dc4;   // zero rows for pads and masked points
-        amx = fmaxf(amx, fmaxf(fmaxf(fabsf(da.x), fabsf(da.y)), fmaxf(fabsf(da.z), fabsf(da.w))));
-        amx = fmaxf(amx, fmaxf(fmaxf(fabsf(dc4.x), fabsf(dc4.y)), fmaxf(fabsf(dc4.z), fabsf(dc4.w))));
-        if (!rvalid || p.dcomp == nullptr) continue;
-        const float4 g0 = gs4[lane], g1 = gs4[32 + lane], b0 = gs4[64 + lane], b1 = gs4[96 + lane];
-        // dg = dy o gamma, s_b = <dy, beta>: <dy, LN(z_k)> = rs_k * (<dg, z_k> - mu_k * sum(dg)) + s_b
-        const float4 ga = make_float4(da.x * g0.x, da.y * g0.y, da.z * g0.z, da.w * g0.w);
-        const float4 gc = make_float4(dc4.x * g1.x, dc4.y * g1.y, dc4.z * g1.z, dc4.w * g1.w);
-        const float sb = (da.x * b0.x + da.y * b0.y) + (da.z * b0.z + da.w * b0.w) + (dc4.x * b1.x + dc4.y * b1.y) + (dc4.z * b1.z + dc4.w * b1.w);
-        float4 za[NK], zc[NK]; float mu[NK], rs[NK];
+    for (int i = 0; i < RPT; ++i) {
+      const int rr = warp + 8 * i, r = r0 + rr;
+      const int ii = r % p.chunk_pad;
+      const bool rvalid = ii < p.chunk && (r / p.chunk_pad) * p.chunk + ii < p.n_points;
+      const float4 da = *reinterpret_cast<const float4*>(ys + rr * HD_LD + lane * 4);
+      const float4 dd = *reinterpret_cast<const float4*>(ys + rr * HD_LD + 128 + lane * 4);
+      float4* o4 = reinterpret_cast<float4*>(p.dOutT + ((long long)b * p.rows_pad + r) * HD_DM);
+      o4[lane] = da; o4[32 + lane] = dd;   // zero rows for pads and masked points
+      amx = fmaxf(amx, fmaxf(fmaxf(fabsf(da.x), fabsf(da.y)), fmaxf(fabsf(da.z), fabsf(da.w))));
+      amx = fmaxf(amx, fmaxf(fmaxf(fabsf(dd.x), fabsf(dd.y)), fmaxf(fabsf(dd.z), fabsf(dd.w))));
+      if (!rvalid || p.dcomp == nullptr) continue;
+      // dg = dy o gamma, s_b = <dy, beta>: <dy, LN(z_k)> = rs_k * <dg, z_k - mu_k> + s_b
+      const float4 g0 = gs4[lane], g1 = gs4[32 + lane], b0 = gs4[64 + lane], b1 = gs4[96 + lane];
+      const float4 ga = make_float4(da.x * g0.x, da.y * g0.y, da.z * g0.z, da.w * g0.w);
+      const float4 gc = make_float4(dd.x * g1.x, dd.y * g1.y, dd.z * g1.z, dd.w * g1.w);
+      const float sb = (da.x * b0.x + da.y * b0.y) + (da.z * b0.z + da.w * b0.w) + (dd.x * b1.x + dd.y * b1.y) + (dd.z * b1.z + dd.w * b1.w);
 #pragma unroll
-        for (int k = 0; k < NK; ++k)
-          if (k < p.n_k) {
-            const long long row = (long long)kb[k] * p.rows_pad + r;
-            const float4* z4 = reinterpret_cast<const float4*>(p.Z + row * HD_DM);
-            za[k] = __ldg(z4 + lane); zc[k] = __ldg(z4 + 32 + lane);
-            mu[k] = __ldg(p.mean + row); rs[k] = __ldg(p.rstd + row);
-          }
-#pragma unroll
-        for (int k = 0; k < NK; ++k)
-          if (k < p.n_k) {
-            const float m = mu[k];
-            const float s = (ga.x * (za[k].x - m) + ga.y * (za[k].y - m)) + (ga.z * (za[k].z - m) + ga.w * (za[k].w - m)) +
-                            (gc.x * (zc[k].x - m) + gc.y * (zc[k].y - m)) + (gc.z * (zc[k].z - m) + gc.w * (zc[k].w - m));
-            dc[k] += rs[k] * s + sb;
-          }
-      }
-      if (p.dcomp) {
-#pragma unroll
-        for (int k = 0; k < NK; ++k) {
-          const float s = warp_sum(dc[k]);
-          if (lane == 0) red[warp * 8 + k] = s;
+      for (int k = 0; k < NK; ++k)
+        if (k < p.n_k) {
+          const float4* z4 = reinterpret_cast<const float4*>(zs + (k * R + rr) * HD_DM);
+          const float4 za = z4[lane], zc = z4[32 + lane];
+          const float m = ms[k * R + rr];
+          const float s = (ga.x * (za.x - m) + ga.y * (za.y - m)) + (ga.z * (za.z - m) + ga.w * (za.w - m)) +
+                          (gc.x * (zc.x - m) + gc.y * (zc.y - m)) + (gc.z * (zc.z - m) + gc.w * (zc.w - m));
+          dc[k] += rss[k * R + rr] * s + sb;
         }
-      }
     }
-    __syncthreads();
-    if (p.dcomp && tid < p.n_k) {
-      float s = 0.f;
-#pragma unroll
-      for (int w2 = 0; w2 < 8; ++w2) s += red[w2 * 8 + tid];
-      atomicAdd(p.dcomp + b * p.n_k + tid, s);
-    }
-    // (the next tile's P1 writes ys / red only after its own barrier sequence; P4's reads are complete here)
-    __syncthreads();
+    __syncthreads();   // stage and ys are free again
   }
 
   // ---------------------------------------------------------------------- flush
+  __syncthreads();
+  if (grad && p.dcomp && cur_b >= 0) flush_dcomp(cur_b);
+  lacc = warp_sum(lacc);
+  if (lane == 0) red[warp] = lacc;
+  __syncthreads();
+  if (tid == 0) p.loss_part[blockIdx.x] = ((red[0] + red[1]) + (red[2] + red[3])) + ((red[4] + red[5]) + (red[6] + red[7]));
   if (grad) {
 #pragma unroll
     for (int c = 0; c < CMAX; ++c)
@@ -295,7 +358,6 @@ __global__ void __launch_bounds__(256, 2) csa_head_kernel(const HeadArgs p) {
       if (lane == 0 && amx > 0.f) atomicMax(reinterpret_cast<int*>(p.amax), __float_as_int(amx));
     }
   }
-  __syncthreads();
   for (int i = tid; i < 3 * CMAX + 2; i += 256) {
     const int v = hist[i];
     if (v == 0) continue;
@@ -328,10 +390,14 @@ __global__ void head_count_valid_kernel(const long long* __restrict__ labels, lo
   if ((threadIdx.x & 31) == 0 && c) atomicAdd(count, c);
 }
 
-template <int CMAX, int NK>
-static int launch_head_nk(const HeadArgs& a, int grid, cudaStream_t s) {
-  auto kern = csa_head_kernel<CMAX, NK>;
-  const int smem = (HD_ROWS * HD_LD + CMAX * HD_LD + HD_ROWS * CMAX + 64 + 512 + 3 * CMAX + 2) * 4;
+template <int CMAX, int NK, int R>
+static int launch_head_r(const HeadArgs& a0, int n_b, int grid_cap, cudaStream_t s) {
+  HeadArgs a = a0;
+  a.tiles_per_b = a.rows_pad / R;
+  a.n_tiles = n_b * a.tiles_per_b;
+  auto kern = csa_head_kernel<CMAX, NK, R>;
+  constexpr int smem = HeadSmem<CMAX, NK, R>::BYTES;
+  static_assert(smem <= 227 * 1024, "csa_head_kernel: shared memory budget");
   int dev = 0;
   CSN_CUDA_OK(cudaGetDevice(&dev));
   static bool configured[64] = {false};
@@ -339,25 +405,32 @@ static int launch_head_nk(const HeadArgs& a, int grid, cudaStream_t s) {
     CSN_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured[dev] = true;
   }
+  const int grid = a.n_tiles < grid_cap ? a.n_tiles : grid_cap;
   kern<<<grid, 256, smem, s>>>(a);
   CSN_LAUNCH_OK("csa_head_kernel");
   return 0;
 }
 
+// 16-row tiles when the ring (2 stages x n_k x 16 KB) fits next to the class-dependent buffers, else 8-row tiles
 template <int CMAX>
-static int launch_head(const HeadArgs& a, int grid, cudaStream_t s) {
-  if (a.n_k <= 1) return launch_head_nk<CMAX, 1>(a, grid, s);
-  if (a.n_k <= 2) return launch_head_nk<CMAX, 2>(a, grid, s);
-  if (a.n_k <= 4) return launch_head_nk<CMAX, 4>(a, grid, s);
-  return launch_head_nk<CMAX, 6>(a, grid, s);
+static int launch_head(const HeadArgs& a, int n_b, int grid_cap, cudaStream_t s) {
+  if constexpr (CMAX == 16) {
+    if (a.n_k <= 1) return launch_head_r<CMAX, 1, 16>(a, n_b, grid_cap, s);
+    if (a.n_k <= 2) return launch_head_r<CMAX, 2, 16>(a, n_b, grid_cap, s);
+    if (a.n_k <= 4) return launch_head_r<CMAX, 4, 16>(a, n_b, grid_cap, s);
+    return launch_head_r<CMAX, 6, 8>(a, n_b, grid_cap, s);
+  } else {
+  if (a.n_k <= 2) return launch_head_r<CMAX, 2, 8>(a, n_b, grid_cap, s);
+  if (a.n_k <= 4) return launch_head_r<CMAX, 4, 8>(a, n_b, grid_cap, s);
+  return launch_head_r<CMAX, 6, 8>(a, n_b, grid_cap, s);
+  }
 }
 
 }  // namespace csn
 
 extern "C" int csn_csa_head_grid(int32_t n_b, int32_t rows_pad) {
-  const int n_tiles = n_b * (rows_pad / csn::HD_ROWS);
-  const int cap = csn::num_sms() * 2;
-  return n_tiles < cap ? n_tiles : cap;
+  (void)n_b; (void)rows_pad;
+  return csn::num_sms();   // upper bound of the grid (one persistent CTA per SM): size of loss_part / dW_part
 }
 
 extern "C" int csn_csa_head(const float* Z, const float* mean, const float* rstd, const float* gamma, const float* beta,
@@ -372,22 +445,28 @@ extern "C" int csn_csa_head(const float* Z, const float* mean, const float* rstd
                 "csn_csa_head: null pointer");
   CSN_CHECK_ARG(n_k >= 1 && n_k <= HD_MAXK, "csn_csa_head: 1..%d attention blocks per query (got %d)", HD_MAXK, n_k);
   CSN_CHECK_ARG(n_classes >= 1 && n_classes <= 64, "csn_csa_head: 1..64 classes supported (got %d)", n_classes);
-  CSN_CHECK_ARG(chunk_pad % HD_ROWS == 0 && rows_pad % chunk_pad == 0 && chunk <= chunk_pad, "csn_csa_head: bad padding");
+  CSN_CHECK_ARG(chunk_pad % 16 == 0 && rows_pad % chunk_pad == 0 && chunk <= chunk_pad, "csn_csa_head: bad padding");
   CSN_CHECK_ARG(!dOutT || (dW_part && dW), "csn_csa_head: the backward outputs need dW_part and dW");
+  CSN_CHECK_ARG((reinterpret_cast<uintptr_t>(Z) & 15) == 0 && (reinterpret_cast<uintptr_t>(mean) & 15) == 0 &&
+                (reinterpret_cast<uintptr_t>(rstd) & 15) == 0, "csn_csa_head: Z / mean / rstd must be 16-byte aligned");
   if (n_b == 0) return 0;
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   head_count_valid_kernel<<<148, 256, 0, s>>>(reinterpret_cast<const long long*>(labels), lab_stride, n_b, n_points, ignore_index, n_valid);
   CSN_LAUNCH_OK("head_count_valid_kernel");
-  const int grid = csn_csa_head_grid(n_b, rows_pad);
+  const int grid_cap = num_sms();
   HeadArgs a{Z, mean, rstd, gamma, beta, blk, w, n_k, W, n_classes, reinterpret_cast<const long long*>(labels), lab_stride,
-             ignore_index, n_valid, n_points, chunk, chunk_pad, rows_pad, n_b * (rows_pad / HD_ROWS), rows_pad / HD_ROWS,
+             ignore_index, n_valid, n_points, chunk, chunk_pad, rows_pad, 0, 0,
              loss_part, dOutT, amax, dcomp, dW_part, stats, y_out};
   int rc;
-  if (n_classes <= 16) rc = launch_head<16>(a, grid, s);
-  else if (n_classes <= 32) rc = launch_head<32>(a, grid, s);
-  else rc = launch_head<64>(a, grid, s);
+  if (n_classes <= 16) rc = launch_head<16>(a, n_b, grid_cap, s);
+  else if (n_classes <= 32) rc = launch_head<32>(a, n_b, grid_cap, s);
+  else rc = launch_head<64>(a, n_b, grid_cap, s);
   if (rc) return rc;
   if (dOutT) {
+    const int n_tiles16 = n_b * (rows_pad / 16), n_tiles8 = n_b * (rows_pad / 8);
+    // the grid the launch used (mirrors launch_head_r): 16-row tiles only for <= 16 classes and n_k <= 4
+    const int tiles = (n_classes <= 16 && n_k <= 4) ? n_tiles16 : n_tiles8;
+    const int grid = tiles < grid_cap ? tiles : grid_cap;
     head_dw_reduce_kernel<<<n_classes, HD_DM, 0, s>>>(dW_part, dW, grid, n_classes);
     CSN_LAUNCH_OK("head_dw_reduce_kernel");
   }

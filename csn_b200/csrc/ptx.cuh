@@ -99,6 +99,14 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* tm,
       : "memory");
 }
 
+// 1-D bulk copy global -> shared (no tensor map): `bytes` contiguous bytes (multiple of 16, both addresses 16-byte
+// aligned), completion counted on an mbarrier of this CTA.
+__device__ __forceinline__ void bulk_load_1d(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+
 // Pull a tile into L2 only (no smem, no barrier): hides the HBM miss of a tile that will be loaded later.
 __device__ __forceinline__ void tma_prefetch_l2_2d(const CUtensorMap* tm, int c0, int c1) {
   asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(tm), "r"(c0), "r"(c1) : "memory");

@@ -544,14 +544,12 @@ class _CsaLossFn(torch.autograd.Function):
         want_grad = any(ctx.needs_input_grad)
         lib = L.lib()
         NP = geom.rows_pad
-        n_tiles = B * (NP // 32)
-        grid = lib.csn_csa_head_grid(B, NP)
+        grid = lib.csn_csa_head_grid(B, NP)   # one persistent CTA per SM: per-CTA partial sums
         # one zero-initialised scratch vector: [n_valid | stats (3C+2) | amax | dcomp (B(K+1))]
         ints = torch.zeros(1 + 3 * Cn + 2, dtype=torch.int32, device=dev)
-        flts = torch.zeros(1 + B * (K + 1), dtype=torch.float32, device=dev)
+        flts = torch.zeros(1 + B * (K + 1) + grid, dtype=torch.float32, device=dev)
         n_valid, stats = ints[:1], ints[1:]
-        amax, dcomp = flts[:1], flts[1:]
-        loss_part = torch.empty(n_tiles, dtype=torch.float32, device=dev)
+        amax, dcomp, loss_part = flts[:1], flts[1:1 + B * (K + 1)], flts[1 + B * (K + 1):]
         dOutT = torch.empty(B * NP, 256, dtype=torch.float32, device=dev) if want_grad else None
         dW_part = torch.empty(grid, Cn, 256, dtype=torch.float32, device=dev) if want_grad else None
         dW = torch.empty(Cn, 256, dtype=torch.float32, device=dev) if want_grad else None

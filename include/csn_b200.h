@@ -181,8 +181,8 @@ int csn_seg_loss(const float* feat, int64_t b_stride, int64_t ch_stride, int32_t
  *   reads through src_idx),  *amax = max|dOutT|,  dcomp[b*n_k+k] += <dOutT[b], LayerNorm(Z[blk])>,
  *   dW[c][ch] = sum dlogits[c] y[ch]  (dW_part: [csn_csa_head_grid()][n_classes][256] scratch, reduced in fixed order).
  * Zero-initialised by the caller: n_valid (1 int), stats (3*n_classes + 2 ints: #pred==c, #label==c, #both, then
- * #correct, #labels outside [0, n_classes)), amax (1 float), dcomp.  loss_part: n_b*rows_pad/32 floats whose sum
- * divided by *n_valid is the loss.  y_out (optional): the combined features as padded rows.  labels: int64,
+ * #correct, #labels outside [0, n_classes)), amax (1 float), dcomp, loss_part.  loss_part: csn_csa_head_grid() floats
+ * (one partial sum per persistent CTA) whose sum divided by *n_valid is the loss.  y_out (optional): the combined features as padded rows.  labels: int64,
  * (b, point n) at labels[b*lab_stride + n]; n_k <= 6; n_classes <= 64.
  * Replaces csn_combine_fwd + the ATen conv/log-softmax/nll kernels and their backwards + csn_pack_rows(dOut) +
  * csn_block_dot. */

@@ -85,7 +85,27 @@ def golden_midfc_mha(ref_midfc, seed=11, n_heads=1):
     return out
 
 
-def golden_midfc_csa(ref_midfc, seed, n_heads, K, batch, num_classes=15):
+def _fp64_compat_grads(ref_midfc, sd, n_heads, K, x, nb, label, num_classes, grads32):
+    """The same step in fp64 (the reference module cast with .double()): the compatibility_{q,k} gradients are a
+    difference of nearly equal numbers, so fp32 itself is only good to 1e-4..1e-2 there; tests gate the kernels
+    against THESE values with the reference's own fp32 error as the yardstick."""
+    m64 = ref_midfc.get_model("csa", num_classes, n_heads, K).eval()
+    m64.load_state_dict(sd)
+    m64 = m64.double()
+    x64 = x.detach().double().requires_grad_(True)
+    logits = m64.logit(m64.get_csa_feats(x64, nb.double(), "test"))
+    ref_masked_ce(logits, label, num_classes).backward()
+    out = {}
+    for name, p in m64.named_parameters():
+        if p.grad is None or not name.startswith("compatibility"):
+            continue
+        out.update(pack("grad64." + name, sample(p.grad)))
+        g32 = grads32[name].double()
+        out[f"grad64.{name}.ref32_rel_err"] = np.array(float((g32 - p.grad).norm() / p.grad.norm()))
+    return out
+
+
+def golden_midfc_csa(ref_midfc, seed, n_heads, K, batch, num_classes=15, max_elems=4096):
     sd = synth.midfc_state(seed, n_heads, num_classes)
     m = ref_midfc.get_model("csa", num_classes, n_heads, K).eval()
     m.load_state_dict(sd)
@@ -99,16 +119,102 @@ def golden_midfc_csa(ref_midfc, seed, n_heads, K, batch, num_classes=15):
     loss.backward()
     out = {"seed": np.array(seed), "n_heads": np.array(n_heads), "K": np.array(K), "batch": np.array(batch),
            "num_classes": np.array(num_classes), "loss": np.array(loss.item())}
-    out.update(pack("feats", sample(feats)))
-    out.update(pack("logits", sample(logits)))
-    out.update(pack("grad.x", sample(x.grad)))
+    out.update(pack("feats", sample(feats, max_elems)))
+    out.update(pack("logits", sample(logits, max_elems)))
+    out.update(pack("grad.x", sample(x.grad, max_elems)))
+    grads32 = {}
     for name, p in m.named_parameters():
         if p.grad is not None:
-            out.update(pack("grad." + name, sample(p.grad)))
+            out.update(pack("grad." + name, sample(p.grad, max_elems)))
+            grads32[name] = p.grad.detach().clone()
     with torch.no_grad():
         ssa, _ = m.get_ssa_feats(x.detach(), "test")
-    out.update(pack("ssa", sample(ssa)))
+    out.update(pack("ssa", sample(ssa, max_elems)))
+    out.update(_fp64_compat_grads(ref_midfc, sd, n_heads, K, x, nb, label, num_classes, grads32))
     return out
+
+
+def golden_midfc_mha_prefix(ref_midfc, seed=13, n_heads=1, n_used=5000):
+    """Config-5 parity point (N = 5000, iters = 10): the reference hard-codes 20 chunks of 500 points
+    (csa_models.py:83-84), but its attention is block-diagonal, so the first n_used rows of its output on a
+    10 000-point input ARE the iters = n_used/500 result on the first n_used points; the loss touches only them."""
+    sd = synth.midfc_state(seed, n_heads)
+    m = ref_midfc.MultiHeadAttention(n_heads, 256, 256, 256).eval()
+    m.load_state_dict({k[len("attention."):]: v for k, v in sd.items() if k.startswith("attention.")})
+    g = synth.gen(seed + 1)
+    xq = synth.iid_features(g, 1)
+    xkv = synth.iid_features(g, 1)
+    gy = torch.randn(1, n_used, 256, generator=g)
+    y, _ = m(xq, xkv, xkv, "test")
+    (y[:, :n_used] * gy).sum().backward()
+    out = {"seed": np.array(seed), "n_heads": np.array(n_heads), "n_used": np.array(n_used)}
+    out.update(pack("y", sample(y[:, :n_used].contiguous())))
+    for name, p in m.named_parameters():
+        out.update(pack("grad." + name, sample(p.grad)))
+    return out
+
+
+def golden_knn_graph(ref_midfc, seed, n_shapes, n_points, K, n_categories):
+    """A collection large enough that top-(K+1) has to discriminate among hundreds of candidates."""
+    m = ref_midfc.get_model("csa", 15, 1, K).eval()
+    f = synth.clustered_shapes(seed, n_shapes, n_points=n_points, n_categories=n_categories)
+    with torch.no_grad():
+        scores = m.get_retrieval_measure(f, f)
+    return {"seed": np.array(seed), "n_shapes": np.array(n_shapes), "n_points": np.array(n_points),
+            "K": np.array(K), "n_categories": np.array(n_categories),
+            "scores": scores.numpy(), "graph": scores.topk(K + 1, dim=-1).indices.numpy()}
+
+
+def golden_mink_csa_head(ref_mink, seed=51, n_head=4, K=2, lens=(260, 140), key_lens=((190, 310), (120, 90))):
+    """CSA block of HRNetSimCSN.forward (hrnet.py:370-417) with the reference's OWN MultiHeadAttention module
+    (attention.py, imported) and the block's glue applied line by line on dense per-shape tensors (the rest of
+    hrnet.py needs MinkowskiEngine): forward features, and the gradients of a seeded linear loss w.r.t. every
+    parameter and every input (the backbone is trained end to end, trainer_csn.py:200-210)."""
+    import math
+    sd = synth.mink_state(seed, n_head)
+    mha = ref_mink.MultiHeadAttention(n_head, 256, 256 // n_head, 256 // n_head).eval()
+    mha.load_state_dict({k[len("MHA."):]: v for k, v in sd.items() if k.startswith("MHA.")})
+    lin_q = torch.nn.Linear(256, 256, bias=False)
+    lin_k = torch.nn.Linear(256, 256, bias=False)
+    lin_q.weight.data.copy_(sd["linear_q.weight"]); lin_k.weight.data.copy_(sd["linear_k.weight"])
+    g = synth.gen(seed + 1)
+    q_feats = [torch.relu(torch.randn(L, 256, generator=g)).requires_grad_(True) for L in lens]
+    k_feats = [[torch.relu(torch.randn(L, 256, generator=g)).requires_grad_(True) for L in kl] for kl in key_lens]   # [K][B]
+    gys = [torch.randn(L, 256, generator=g) for L in lens]
+
+    def ssa(f):   # hrnet.py:456-470
+        return mha(f[None], f[None], f[None])[0][0]
+
+    q_ssa = [ssa(f) for f in q_feats]
+    key_ssa = [q_ssa] + [[ssa(f) for f in kf] for kf in k_feats]
+    outs = []
+    loss = 0.0
+    for b in range(len(lens)):   # hrnet.py:376-417
+        gq = torch.nn.functional.normalize(lin_q(q_ssa[b].mean(dim=0)), dim=-1)
+        sims = []
+        for ks in key_ssa:
+            gk = torch.nn.functional.normalize(lin_k(ks[b].mean(dim=0)), dim=-1)
+            sims.append((gq * gk).sum() / math.sqrt(256.0))   # ScaledDotProduct(temperature=sqrt(d_model)), :357
+        comp = torch.softmax(torch.stack(sims), dim=0)
+        csa = comp[0] * q_ssa[b]
+        for i in range(K):
+            cross = mha(q_feats[b][None], k_feats[i][b][None], k_feats[i][b][None])[0][0]
+            csa = csa + comp[i + 1] * cross
+        outs.append(csa)
+        loss = loss + (csa * gys[b]).sum()
+    loss.backward()
+    res = {"seed": np.array(seed), "n_head": np.array(n_head), "K": np.array(K), "lens": np.array(lens),
+           "key_lens": np.array(key_lens)}
+    for b, o in enumerate(outs):
+        res.update(pack(f"out{b}", sample(o)))
+        res.update(pack(f"grad.q{b}", sample(q_feats[b].grad)))
+        for i in range(K):
+            res.update(pack(f"grad.k{i}_{b}", sample(k_feats[i][b].grad)))
+    for name, p in mha.named_parameters():
+        res.update(pack("grad.MHA." + name, sample(p.grad)))
+    res.update(pack("grad.linear_q.weight", sample(lin_q.weight.grad)))
+    res.update(pack("grad.linear_k.weight", sample(lin_k.weight.grad)))
+    return res
 
 
 def golden_knn(ref_midfc, seed, n_shapes, n_points, K, n_categories):
@@ -160,6 +266,10 @@ def main() -> None:
         "midfc_mha_h2": lambda: golden_midfc_mha(ref_midfc, seed=12, n_heads=2),
         "midfc_csa_cfg1": lambda: golden_midfc_csa(ref_midfc, seed=21, n_heads=1, K=1, batch=1),
         "midfc_csa_b2_k2_h2": lambda: golden_midfc_csa(ref_midfc, seed=22, n_heads=2, K=2, batch=2),
+        "midfc_csa_b8_k3_h1": lambda: golden_midfc_csa(ref_midfc, seed=23, n_heads=1, K=3, batch=8, max_elems=2048),
+        "midfc_mha_n5000": lambda: golden_midfc_mha_prefix(ref_midfc),
+        "knn_graph_s200": lambda: golden_knn_graph(ref_midfc, seed=43, n_shapes=200, n_points=1000, K=4, n_categories=8),
+        "mink_csa_head": lambda: golden_mink_csa_head(ref_mink),
         "knn_small": lambda: golden_knn(ref_midfc, seed=41, n_shapes=12, n_points=1000, K=3, n_categories=4),
         "knn_10k": lambda: golden_knn(ref_midfc, seed=42, n_shapes=6, n_points=10000, K=2, n_categories=3),
         "mink_mha": lambda: golden_mink_mha(ref_mink),

@@ -49,7 +49,7 @@ def test_mha_forward_matches_reference(name, precision):
 
 
 @pytest.mark.parametrize("name,precision", [("midfc_csa_cfg1", "fp16"), ("midfc_csa_b2_k2_h2", "fp16"),
-                                            ("midfc_csa_cfg1", "bf16")])
+                                            ("midfc_csa_cfg1", "bf16"), ("midfc_csa_b8_k3_h1", "fp16")])
 def test_csa_forward_backward_matches_reference(name, precision):
     from csn_b200 import midfc
     g = G.load(name)
@@ -80,13 +80,12 @@ def test_csa_forward_backward_matches_reference(name, precision):
             G.compare_sampled(g, "grad." + pname, params[pname].grad, tol, what=pname)
             continue
         # Ill-conditioned by construction: d comp depends on <dOut, Y_0 - Y_k>, a difference of two
-        # nearly equal LayerNorm outputs, so the operand rounding of Y (1e-4) is amplified; the
-        # reference's own fp32 result is 3e-4..3e-3 away from fp64 here.  Bound: same
-        # direction/magnitude, and error small against the attention-weight gradients (norm-scaled).
+        # nearly equal LayerNorm outputs; the reference's own fp32 result is 1e-4..1e-2 away from fp64 here.
+        # The relative gate against the fp64 values is test_compatibility_gradients_against_fp64; here: the
+        # error is small against the attention-weight gradients (norm-scaled).
         stride = int(g[f"grad.{pname}.stride"])
         got = params[pname].grad.detach().reshape(-1).double().cpu()[::stride]
         want = torch.from_numpy(g[f"grad.{pname}.values"].astype("float64"))
-        assert G.rel_err(got, want) < 0.35, (pname, G.rel_err(got, want))
         assert float((got - want).norm()) < tol * attn_scale, pname
     with torch.no_grad():
         ssa, attn = m.get_ssa_feats(x.detach(), "test")
@@ -285,3 +284,51 @@ def test_fused_head_class_counts_and_all_masked(C):
     assert z.item() == 0.0
     assert all(torch.isfinite(p.grad).all() and float(p.grad.abs().max()) == 0.0
                for n, p in m.named_parameters() if p.grad is not None)
+
+
+@pytest.mark.parametrize("name", ["midfc_csa_cfg1", "midfc_csa_b2_k2_h2", "midfc_csa_b8_k3_h1"])
+def test_compatibility_gradients_against_fp64(name):
+    """compatibility_{q,k}.{weight,bias} gradients against the reference run in fp64 (oracle/make_golden.py,
+    grad64.*): the yardstick is the reference's OWN fp32 error on the same tensor (grad64.*.ref32_rel_err, a
+    cancellation-dominated quantity).  Gate: kernel error <= max(3 x the reference's fp32 error, 1e-3)."""
+    from csn_b200 import midfc
+    g = G.load(name)
+    seed, h, K, B, C = (int(g[k]) for k in ("seed", "n_heads", "K", "batch", "num_classes"))
+    m = midfc.get_model("csa", C, h, K).cuda().eval()
+    m.load_state_dict(synth.midfc_state(seed, h, C))
+    x, nb = synth.csa_batch(seed + 1, B, K)
+    label = _labels(seed + 2, B, x.shape[2], C).cuda()
+    m.forward_loss(x.cuda(), "test", nb.cuda(), label).backward()
+    params = dict(m.named_parameters())
+    report = {}
+    for pname in ("compatibility_q.weight", "compatibility_q.bias", "compatibility_k.weight", "compatibility_k.bias"):
+        stride = int(g[f"grad64.{pname}.stride"])
+        got = params[pname].grad.detach().reshape(-1).double().cpu()[::stride]
+        want = torch.from_numpy(g[f"grad64.{pname}.values"].astype("float64"))
+        report[pname] = (G.rel_err(got, want), float(g[f"grad64.{pname}.ref32_rel_err"]))
+    print("compat grads (kernel rel err vs fp64, reference fp32 rel err vs fp64):", report)
+    for pname, (err, ref_err) in report.items():
+        assert err <= max(3.0 * ref_err, 1e-3), (pname, err, ref_err)
+
+
+def test_config5_point_n5000_iters10():
+    """Config 5 (N != 10 000, iters = N/500): MultiHeadAttention with iters = 10 on 5 000 points against the first
+    5 000 rows of the reference's output on the 10 000-point input (block-diagonal attention: identical), forward
+    and parameter gradients of a loss that only touches those rows."""
+    from csn_b200 import midfc
+    g = G.load("midfc_mha_n5000")
+    seed, h, n_used = int(g["seed"]), int(g["n_heads"]), int(g["n_used"])
+    sd = synth.midfc_state(seed, h)
+    m = midfc.MultiHeadAttention(h, 256, 256, 256).cuda().eval()
+    m.load_state_dict({k[len("attention."):]: v for k, v in sd.items() if k.startswith("attention.")})
+    m.iters = n_used // 500
+    gen = synth.gen(seed + 1)
+    xq = synth.iid_features(gen, 1)[:, :, :n_used].contiguous().cuda()
+    xkv = synth.iid_features(gen, 1)[:, :, :n_used].contiguous().cuda()
+    gy = torch.randn(1, n_used, 256, generator=gen).cuda()
+    y, attn = m(xq, xkv, xkv, "test")
+    assert y.shape == (1, n_used, 256)
+    (y * gy).sum().backward()
+    G.compare_sampled(g, "y", y, 1e-3)
+    for pname, prm in m.named_parameters():
+        G.compare_sampled(g, "grad." + pname, prm.grad, 1e-3, what=pname)

@@ -99,3 +99,38 @@ def test_batched_csa_head_matches_call_by_call_loop():
         assert G.rel_err(a, b) < 1e-3
     for a, b in zip(res[True][2:], res[False][2:]):
         assert G.rel_err(a, b) < 1e-3
+
+
+@pytest.mark.parametrize("precision,tol", [("fp16", 1e-3), ("bf16", 1e-2)])
+def test_csa_head_forward_backward_matches_reference(precision, tol):
+    """CSA block of HRNetSimCSN.forward (hrnet.py:370-417), forward AND backward, against vectors produced with the
+    reference's own MultiHeadAttention module (tests/golden/mink_csa_head.npz, oracle/make_golden.py): features,
+    gradients w.r.t. every input shape (the backbone trains end to end) and every parameter.  bf16 = config 4's dtype."""
+    from csn_b200 import mink
+    g = G.load("mink_csa_head")
+    seed, h, K = int(g["seed"]), int(g["n_head"]), int(g["K"])
+    lens, key_lens = [int(v) for v in g["lens"]], [[int(v) for v in row] for row in g["key_lens"]]
+    head = mink.CSAHead(256, h, precision=precision).cuda().eval()
+    head.load_state_dict(synth.mink_state(seed, h))
+    gen = synth.gen(seed + 1)
+    qf = [torch.relu(torch.randn(L, 256, generator=gen)).cuda().requires_grad_(True) for L in lens]
+    kf = [[torch.relu(torch.randn(L, 256, generator=gen)).cuda().requires_grad_(True) for L in kl] for kl in key_lens]
+    gys = [torch.randn(L, 256, generator=gen).cuda() for L in lens]
+    outs = head(qf, kf)
+    sum((o * gy).sum() for o, gy in zip(outs, gys)).backward()
+    for b, o in enumerate(outs):
+        G.compare_sampled(g, f"out{b}", o, tol)
+        G.compare_sampled(g, f"grad.q{b}", qf[b].grad, tol)
+        for i in range(K):
+            G.compare_sampled(g, f"grad.k{i}_{b}", kf[i][b].grad, tol)
+    params = dict(head.named_parameters())
+    for pname in ("MHA.w_qs.weight", "MHA.w_ks.weight", "MHA.w_vs.weight", "MHA.fc.weight", "MHA.norm.weight",
+                  "MHA.norm.bias"):
+        G.compare_sampled(g, "grad." + pname, params[pname].grad, tol, what=pname)
+    # linear_q / linear_k see the same cancellation as MID-FC's compatibility layers: norm-scaled bound
+    scale = max(float(g[f"grad.MHA.{n}.sumsq"]) ** 0.5 for n in ("w_qs.weight", "fc.weight"))
+    for pname in ("linear_q.weight", "linear_k.weight"):
+        stride = int(g[f"grad.{pname}.stride"])
+        got = params[pname].grad.detach().reshape(-1).double().cpu()[::stride]
+        want = torch.from_numpy(g[f"grad.{pname}.values"].astype("float64"))
+        assert float((got - want).norm()) < tol * scale, pname

@@ -32,7 +32,7 @@ def test_midfc_mha_needs_10000_points():
         O.mha_midfc(x, x, x, w, 1)
 
 
-@pytest.mark.parametrize("name", ["midfc_csa_cfg1", "midfc_csa_b2_k2_h2"])
+@pytest.mark.parametrize("name", ["midfc_csa_cfg1", "midfc_csa_b2_k2_h2", "midfc_csa_b8_k3_h1"])
 def test_midfc_csa_forward_backward(name):
     g = G.load(name)
     seed, h, K, B, C = (int(g[k]) for k in ("seed", "n_heads", "K", "batch", "num_classes"))
@@ -91,3 +91,43 @@ def test_mink_mha():
         G.compare_sampled(g, "grad." + pname, w["MHA." + pname].grad, 2e-4, what=pname)
     sdp = (q.detach()[0, :5] @ k.detach()[0, :7].t()) / 16.0
     G.compare_sampled(g, "sdp", sdp[None], TOL)
+
+
+def test_midfc_mha_prefix_is_the_short_shape_result():
+    """Config-5 fixture: the oracle with iters = 10 on the first 5 000 points equals the first 5 000 rows of the
+    reference's 10 000-point output (block-diagonal attention)."""
+    g = G.load("midfc_mha_n5000")
+    seed, h, n_used = int(g["seed"]), int(g["n_heads"]), int(g["n_used"])
+    w = {k: v.clone().requires_grad_(True) for k, v in synth.midfc_state(seed, h).items() if k.startswith("attention.")}
+    gen = synth.gen(seed + 1)
+    xq = synth.iid_features(gen, 1)[:, :, :n_used]
+    xkv = synth.iid_features(gen, 1)[:, :, :n_used]
+    gy = torch.randn(1, n_used, 256, generator=gen)
+    y, _ = O.mha_midfc(xq, xkv, xkv, w, h, iters=n_used // 500)
+    (y * gy).sum().backward()
+    G.compare_sampled(g, "y", y, TOL)
+    for k, v in w.items():
+        G.compare_sampled(g, "grad." + k[len("attention."):], v.grad, 2e-4, what=k)
+
+
+def test_mink_csa_head_forward_backward():
+    """oracle.mink_csa_block (the restated glue of hrnet.py:370-417) against the fixture built from the reference's
+    own MultiHeadAttention module: features and every gradient."""
+    g = G.load("mink_csa_head")
+    seed, h, K = int(g["seed"]), int(g["n_head"]), int(g["K"])
+    lens, key_lens = [int(v) for v in g["lens"]], [[int(v) for v in row] for row in g["key_lens"]]
+    w = {k: v.clone().requires_grad_(True) for k, v in synth.mink_state(seed, h).items()}
+    gen = synth.gen(seed + 1)
+    qf = [torch.relu(torch.randn(L, 256, generator=gen)).requires_grad_(True) for L in lens]
+    kf = [[torch.relu(torch.randn(L, 256, generator=gen)).requires_grad_(True) for L in kl] for kl in key_lens]
+    gys = [torch.randn(L, 256, generator=gen) for L in lens]
+    outs = O.mink_csa_block(qf, kf, w, h)
+    sum((o * gy).sum() for o, gy in zip(outs, gys)).backward()
+    for b, o in enumerate(outs):
+        G.compare_sampled(g, f"out{b}", o, TOL)
+        G.compare_sampled(g, f"grad.q{b}", qf[b].grad, 2e-4)
+        for i in range(K):
+            G.compare_sampled(g, f"grad.k{i}_{b}", kf[i][b].grad, 2e-4)
+    for k, v in w.items():
+        if f"grad.{k}.values" in g.files:
+            G.compare_sampled(g, "grad." + k, v.grad, 2e-2 if k.startswith("linear_") else 2e-4, what=k)
