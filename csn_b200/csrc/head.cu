@@ -66,7 +66,7 @@ struct HeadSmem {
 };
 
 template <int CMAX, int NK, int R>
-__global__ void __launch_bounds__(256, 1) csa_head_kernel(const HeadArgs p) {
+__global__ void __launch_bounds__(256, (R == 8 && CMAX == 16 && NK <= 4) ? 2 : 1) csa_head_kernel(const HeadArgs p) {
   using SM = HeadSmem<CMAX, NK, R>;
   extern __shared__ __align__(128) float hsm[];
   float* ys = hsm + SM::OFF_YS;                       // [R][260]
@@ -159,6 +159,8 @@ __global__ void __launch_bounds__(256, 1) csa_head_kernel(const HeadArgs p) {
       kw[k] = (k < p.n_k) ? __ldg(p.w + b * p.n_k + k) : 0.f;
       wsum += kw[k];
     }
+    // a tile lies inside one chunk (R | chunk_pad): one division per tile, additions per row
+    const int t_ch = r0 / p.chunk_pad, t_i0 = r0 - t_ch * p.chunk_pad, t_n0 = t_ch * p.chunk + t_i0;
     const float* zs = hsm + stage * SM::STAGE;
     const float* ms = zs + NK * R * HD_DM;
     const float* rss = ms + NK * R;
@@ -168,8 +170,7 @@ __global__ void __launch_bounds__(256, 1) csa_head_kernel(const HeadArgs p) {
 #pragma unroll
     for (int i = 0; i < RPT; ++i) {
       const int rr = warp + 8 * i, r = r0 + rr;
-      const int ii = r % p.chunk_pad;
-      const bool rvalid = ii < p.chunk && (r / p.chunk_pad) * p.chunk + ii < p.n_points;
+      const bool rvalid = t_i0 + rr < p.chunk && t_n0 + rr < p.n_points;
       float4 ta = make_float4(0.f, 0.f, 0.f, 0.f), tc = ta;
       if (rvalid) {
 #pragma unroll
@@ -224,10 +225,9 @@ __global__ void __launch_bounds__(256, 1) csa_head_kernel(const HeadArgs p) {
     // ------------------------------------------------------------------ P2b: softmax, loss, argmax, dlogits, counters
 #pragma unroll
     for (int i = 0; i < RPT; ++i) {
-      const int rr = warp + 8 * i, r = r0 + rr;
-      const int ii = r % p.chunk_pad;
-      const int n = (r / p.chunk_pad) * p.chunk + ii;
-      const bool rvalid = ii < p.chunk && n < p.n_points;
+      const int rr = warp + 8 * i;
+      const int n = t_n0 + rr;
+      const bool rvalid = t_i0 + rr < p.chunk && n < p.n_points;
       float lg[CL];
       float mx = -INFINITY; int bi = 0x7fffffff;
 #pragma unroll
@@ -314,8 +314,7 @@ __global__ void __launch_bounds__(256, 1) csa_head_kernel(const HeadArgs p) {
 #pragma unroll
     for (int i = 0; i < RPT; ++i) {
       const int rr = warp + 8 * i, r = r0 + rr;
-      const int ii = r % p.chunk_pad;
-      const bool rvalid = ii < p.chunk && (r / p.chunk_pad) * p.chunk + ii < p.n_points;
+      const bool rvalid = t_i0 + rr < p.chunk && t_n0 + rr < p.n_points;
       const float4 da = *reinterpret_cast<const float4*>(ys + rr * HD_LD + lane * 4);
       const float4 dd = *reinterpret_cast<const float4*>(ys + rr * HD_LD + 128 + lane * 4);
       float4* o4 = reinterpret_cast<float4*>(p.dOutT + ((long long)b * p.rows_pad + r) * HD_DM);
@@ -415,9 +414,10 @@ static int launch_head_r(const HeadArgs& a0, int n_b, int grid_cap, cudaStream_t
 template <int CMAX>
 static int launch_head(const HeadArgs& a, int n_b, int grid_cap, cudaStream_t s) {
   if constexpr (CMAX == 16) {
-    if (a.n_k <= 1) return launch_head_r<CMAX, 1, 16>(a, n_b, grid_cap, s);
-    if (a.n_k <= 2) return launch_head_r<CMAX, 2, 16>(a, n_b, grid_cap, s);
-    if (a.n_k <= 4) return launch_head_r<CMAX, 4, 16>(a, n_b, grid_cap, s);
+    // 8-row tiles, ~98 KB of SMEM: two CTAs per SM (16 warps) hide each other's barriers and LDS latencies
+    if (a.n_k <= 1) return launch_head_r<CMAX, 1, 8>(a, n_b, 2 * grid_cap, s);
+    if (a.n_k <= 2) return launch_head_r<CMAX, 2, 8>(a, n_b, 2 * grid_cap, s);
+    if (a.n_k <= 4) return launch_head_r<CMAX, 4, 8>(a, n_b, 2 * grid_cap, s);
     return launch_head_r<CMAX, 6, 8>(a, n_b, grid_cap, s);
   } else {
   if (a.n_k <= 2) return launch_head_r<CMAX, 2, 8>(a, n_b, grid_cap, s);
@@ -430,7 +430,7 @@ static int launch_head(const HeadArgs& a, int n_b, int grid_cap, cudaStream_t s)
 
 extern "C" int csn_csa_head_grid(int32_t n_b, int32_t rows_pad) {
   (void)n_b; (void)rows_pad;
-  return csn::num_sms();   // upper bound of the grid (one persistent CTA per SM): size of loss_part / dW_part
+  return 2 * csn::num_sms();   // upper bound of the grid (persistent CTAs, at most two per SM): size of loss_part / dW_part
 }
 
 extern "C" int csn_csa_head(const float* Z, const float* mean, const float* rstd, const float* gamma, const float* beta,
@@ -463,10 +463,10 @@ extern "C" int csn_csa_head(const float* Z, const float* mean, const float* rstd
   else rc = launch_head<64>(a, n_b, grid_cap, s);
   if (rc) return rc;
   if (dOutT) {
-    const int n_tiles16 = n_b * (rows_pad / 16), n_tiles8 = n_b * (rows_pad / 8);
-    // the grid the launch used (mirrors launch_head_r): 16-row tiles only for <= 16 classes and n_k <= 4
-    const int tiles = (n_classes <= 16 && n_k <= 4) ? n_tiles16 : n_tiles8;
-    const int grid = tiles < grid_cap ? tiles : grid_cap;
+    // the grid the launch used (mirrors launch_head): two CTAs per SM for <= 16 classes and n_k <= 4
+    const int tiles = n_b * (rows_pad / 8);
+    const int cap = (n_classes <= 16 && n_k <= 4) ? 2 * grid_cap : grid_cap;
+    const int grid = tiles < cap ? tiles : cap;
     head_dw_reduce_kernel<<<n_classes, HD_DM, 0, s>>>(dW_part, dW, grid, n_classes);
     CSN_LAUNCH_OK("head_dw_reduce_kernel");
   }

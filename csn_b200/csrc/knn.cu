@@ -468,9 +468,12 @@ __global__ void knn_reduce_kernel(const float* __restrict__ partial, float* __re
 }
 
 // --------------------------------------------------------------------------- top-K per row
-// One warp per row. Each lane keeps its own sorted top-KK (KK <= 8) over the columns it strides,
+// One warp per row. Each lane keeps its own sorted top-KK (KK <= TOPK_MAX) over the columns it strides,
 // then the warp extracts the global top-KK by KK rounds of shuffle arg-max. Ties: lower index wins.
-constexpr int TOPK_MAX = 8;
+// TOPK_MAX is a template parameter (8 / 16 / 32 / 64 list entries per lane): the reference's launcher default
+// K = 10 (run_save_knn.py:34) asks for top-11.
+constexpr int TOPK_LIMIT = 64;
+template <int TOPK_MAX>
 __global__ void topk_rows_kernel(const float* __restrict__ scores, long long ld, int n_rows, int n_cols, int kk,
                                  float* __restrict__ out_val, long long* __restrict__ out_idx) {
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -630,11 +633,16 @@ int csn_topk_rows(const float* scores, int64_t ld, int32_t n_rows, int32_t n_col
   using namespace csn;
   clear_error();
   CSN_CHECK_ARG(scores && out_val && out_idx, "csn_topk_rows: null pointer");
-  CSN_CHECK_ARG(k >= 1 && k <= TOPK_MAX, "csn_topk_rows: k=%d must be in [1,%d]", k, TOPK_MAX);
+  CSN_CHECK_ARG(k >= 1 && k <= TOPK_LIMIT, "csn_topk_rows: k=%d must be in [1,%d]", k, TOPK_LIMIT);
   CSN_CHECK_ARG(k <= n_cols, "csn_topk_rows: k=%d exceeds the number of columns %d", k, n_cols);
   if (n_rows == 0) return 0;
   const int wpb = 4;
-  topk_rows_kernel<<<(n_rows + wpb - 1) / wpb, wpb * 32, 0, (cudaStream_t)stream>>>(scores, ld, n_rows, n_cols, k, out_val, (long long*)out_idx);
+  const dim3 grid((n_rows + wpb - 1) / wpb), block(wpb * 32);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (k <= 8) topk_rows_kernel<8><<<grid, block, 0, st>>>(scores, ld, n_rows, n_cols, k, out_val, (long long*)out_idx);
+  else if (k <= 16) topk_rows_kernel<16><<<grid, block, 0, st>>>(scores, ld, n_rows, n_cols, k, out_val, (long long*)out_idx);
+  else if (k <= 32) topk_rows_kernel<32><<<grid, block, 0, st>>>(scores, ld, n_rows, n_cols, k, out_val, (long long*)out_idx);
+  else topk_rows_kernel<64><<<grid, block, 0, st>>>(scores, ld, n_rows, n_cols, k, out_val, (long long*)out_idx);
   CSN_LAUNCH_OK("topk_rows_kernel");
   return 0;
 }

@@ -16,6 +16,7 @@ from . import _lib as L
 
 TILE_ROWS = 128
 NUM_SMS = 148
+TOPK_LIMIT = 64   # csn_topk_rows: per-lane candidate lists of 8 / 16 / 32 / 64 entries
 
 
 @dataclass

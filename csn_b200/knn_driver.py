@@ -86,6 +86,12 @@ def _graph(q, c, K: int) -> np.ndarray:
 def build_graphs(model, train_root: str, test_root: str, K: int, big: bool, batch_size: int = 8, device="cuda"):
     """(train_graph, test_graph): int64 arrays (S, K+1) as produced by update_knn_graphs (csa_training.py:136-166)."""
     train, test = FeatureFiles(train_root), FeatureFiles(test_root)
+    # reject impossible requests BEFORE the SSA features and the scores are computed (minutes of work)
+    n_cand = len(train) // 10 if big else len(train)
+    if K + 1 > _knn.TOPK_LIMIT:
+        raise ValueError(f"K={K}: csn_topk_rows selects at most {_knn.TOPK_LIMIT} entries per row")
+    if K + 1 > n_cand:
+        raise ValueError(f"K={K}: top-{K + 1} of {n_cand} candidate shapes (torch.topk raises here as well)")
     pooled = [] if big else None
     train_store = ssa_store(model, train, batch_size, device, pooled)
     test_store = ssa_store(model, test, batch_size, device)

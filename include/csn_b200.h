@@ -107,7 +107,7 @@ int csn_knn_scores_exact(const void* q_hi, const void* q_lo, int64_t rows_q, con
 int csn_knn_reduce(const float* partial, float* scores, int32_t n_q, int32_t n_cand, int32_t ntiles,
                    int32_t n_rows, int64_t ld_scores, void* stream);
 
-/* Per-row top-k (k <= 8), values and int64 indices sorted descending; equal scores: lower index
+/* Per-row top-k (k <= 64), values and int64 indices sorted descending; equal scores: lower index
  * first (`retrieval_measure.topk(K+1, -1)`, csa_models.py:278,401). */
 int csn_topk_rows(const float* scores, int64_t ld, int32_t n_rows, int32_t n_cols, int32_t k,
                   float* out_val, int64_t* out_idx, void* stream);

@@ -38,8 +38,10 @@ def test_abi_version_and_error_string(lib):
     rc = lib.csn_normalize_rows(None, None, 4, 256, C.c_float(1e-12), 1, None)
     assert rc != 0
     assert b"null" in lib.csn_last_error()
-    rc = lib.csn_topk_rows(C.c_void_p(16), 8, 1, 4, 9, C.c_void_p(16), C.c_void_p(16), None)
-    assert rc != 0 and b"k=9" in lib.csn_last_error()
+    rc = lib.csn_topk_rows(C.c_void_p(16), 8, 1, 4, 65, C.c_void_p(16), C.c_void_p(16), None)
+    assert rc != 0 and b"k=65" in lib.csn_last_error()
+    rc = lib.csn_topk_rows(C.c_void_p(16), 8, 1, 4, 9, C.c_void_p(16), C.c_void_p(16), None)   # k > number of columns
+    assert rc != 0 and b"exceeds" in lib.csn_last_error()
 
 
 def test_no_cpu_fallback():

@@ -76,7 +76,7 @@ def test_topk_rows_matches_torch():
     from csn_b200 import knn
     gen = synth.gen(3)
     s = torch.randn(37, 1000, generator=gen).cuda()
-    for k in (1, 4, 6, 8):
+    for k in (1, 4, 6, 8, 9, 11, 16, 30, 64):   # 11 = the reference launcher's default K = 10 (run_save_knn.py:34)
         val, idx = knn.topk_rows(s, k)
         tv, ti = s.topk(k, dim=-1)
         assert torch.equal(val, tv)
@@ -161,6 +161,15 @@ def test_knn_driver_end_to_end(tmp_path):
     assert np.array_equal(g_train, m.get_knn_graph(f_tr, f_tr, K).cpu().numpy())
     assert np.array_equal(g_test, m.get_knn_graph(f_te, f_tr, K).cpu().numpy())
     assert (g_train[:, 0] == np.arange(24)).all()                     # every train shape retrieves itself first
+    # the launcher's default K = 10 (run_save_knn.py:34; the reference never passes --K): top-11 per query
+    rc = D.main([f"--ssa_logs_dir={logs}", f"--graphs_dir={tmp_path / 'graphs10'}", "--partname=Bed", f"--n_heads={h}",
+                 "--batch_size=4", f"--num_classes={C}", f"--dataroot={tmp_path}/{{}}/{{}}"])
+    assert rc == 0
+    g10 = np.load(tmp_path / "graphs10" / "train.npy")
+    assert g10.shape == (24, 11) and np.array_equal(g10[:, :K + 1], g_train)
+    assert np.array_equal(g10, m.get_knn_graph(f_tr, f_tr, 10).cpu().numpy())
+    with pytest.raises(ValueError):   # rejected before any scoring: more neighbours than candidate shapes
+        D.build_graphs(m, str(tmp_path / "train" / "Bed"), str(tmp_path / "test" / "Bed"), 30, False, 4, "cuda")
     # big-class variant: candidates = shapes nearest to S//10 k-means centres; graph entries are shape indices
     gb_train, gb_test = D.build_graphs(m, str(tmp_path / "train" / "Bed"), str(tmp_path / "test" / "Bed"), 1, True, 4, "cuda")
     assert gb_train.shape == (24, 2) and gb_test.shape == (9, 2)
