@@ -89,6 +89,11 @@ class _Timed:
             flops = 2.0 * M * N * K * nbt
             out_b = 4 if args[2]._obj.dtype == CSN_F32 else 2
             nbytes = nbt * (2.0 * (M + N) * K + float(out_b) * M * N)   # operands once + output once (algorithmic)
+        elif self.name == "csn_gemm_colbias":   # (A, B, D, M, N, K, alpha, ...)
+            M, N, K = args[3], args[4], args[5]
+            flops = 2.0 * M * N * K
+            out_b = 4 if args[2]._obj.dtype == CSN_F32 else 2
+            nbytes = 2.0 * (M + N) * K + float(out_b) * M * N
         elif self.name == "csn_gemm_delta":   # (A, B, dO, lddo, M, N, K, ...): A + O + O_lo in, dO out (16-bit)
             flops = 2.0 * args[4] * args[5] * args[6]
             nbytes = args[4] * (2.0 * args[6] + 3 * 2.0 * args[5])
@@ -134,7 +139,7 @@ _EXTRA_SIGNATURES: dict[str, list] = {
     "csn_knn_reduce": [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int64, C.c_void_p],
     "csn_pack_rows": [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int64, C.c_int32, C.c_int64,
                       C.c_int64, C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
-                      C.c_void_p, C.c_void_p],
+                      C.c_void_p, C.c_void_p, C.c_void_p],
     "csn_softmax_fwd": [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                         C.c_void_p],
     "csn_softmax_bwd": [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
@@ -145,7 +150,11 @@ _EXTRA_SIGNATURES: dict[str, list] = {
     "csn_colsum_reduce": [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_float, C.c_void_p],
     "csn_gemm_res_ln": [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_float, C.c_void_p,
                         C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32,
-                        C.c_int32, C.c_int32, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p],
+                        C.c_int32, C.c_int32, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p],
+    "csn_gemm_colbias": [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_float, C.c_void_p,
+                         C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_void_p],
+    "csn_sgemm_small": [C.c_void_p, C.c_int64, C.c_void_p, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p, C.c_int32,
+                        C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_float, C.c_int32, C.c_void_p],
     "csn_seg_loss": [C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32,
                      C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p],
     "csn_gemm_delta": [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_float,
@@ -156,7 +165,7 @@ _EXTRA_SIGNATURES: dict[str, list] = {
                       C.c_int32, C.c_int32, C.c_void_p],
     "csn_ln_bwd": [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                    C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p,
-                   C.c_void_p, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p],
+                   C.c_void_p, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p],
     "csn_combine_fwd": [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32,
                         C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p,
                         C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p],

@@ -586,7 +586,9 @@ static int attn_launch_common(int mode, const void* Q, const void* K, const void
   // [128 x 256] score tiles (attn_wide.cu): bit 0 = forward, bit 1 = dV.  Default: dV only (335 vs 363 us on the
   // config-2 step); the wide forward kernel is correct but no faster than this file's (405 vs 406 us: its second
   // output, the rounding residual of O, needs four staging slabs per warp where the P tile offers two).
-  static const int wide = getenv("CSN_ATTN_WIDE") == nullptr ? 2 : atoi(getenv("CSN_ATTN_WIDE"));
+  // Unset: dV always; the forward pass when it has a single output (V centred: no rounding residual of O).
+  static const int wide_env = getenv("CSN_ATTN_WIDE") == nullptr ? -1 : atoi(getenv("CSN_ATTN_WIDE"));
+  const int wide = wide_env >= 0 ? wide_env : (2 | (Olo == nullptr ? 1 : 0));
   if (d_head == 256 && ((wide >> mode) & 1)) {
     a.idesc_qk = umma_idesc_f16(fmt, 0, 0, 256);
     a.idesc_pv = umma_idesc_f16(fmt, 0, 1, 256);

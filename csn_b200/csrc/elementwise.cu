@@ -41,6 +41,7 @@ struct PackArgs {
   int chunk, chunk_pad, rows_pad;
   int dtype;
   float* amax;          // optional: max |src| over everything read (atomic max on the bit pattern)
+  float* chunk_sum;     // optional [slot*n_chunks + chunk][256]: per-chunk channel sums of the valid points (atomically accumulated)
 };
 
 __global__ void __launch_bounds__(256) pack_kernel(const PackArgs p) {
@@ -54,10 +55,15 @@ __global__ void __launch_bounds__(256) pack_kernel(const PackArgs p) {
   const int n = ch * p.chunk + i;
   const bool valid = i < p.chunk && n < p.n_points;
   float amx = 0.f;
+  float* csum = p.chunk_sum ? p.chunk_sum + (slot * (p.rows_pad / p.chunk_pad) + ch) * DM : nullptr;
   for (int c = warp; c < DM; c += 8) {
     const float v = valid ? __ldg(src + c * p.ch_stride + n) : 0.f;
     tile[lane][c] = v;
     amx = fmaxf(amx, fabsf(v));
+    if (csum) {
+      const float sv = warp_sum(v);
+      if (lane == 0) atomicAdd(csum + c, sv);
+    }
   }
   if (p.amax) {
     amx = warp_max(amx);
@@ -89,10 +95,12 @@ __global__ void __launch_bounds__(256) pack128_kernel(const PackArgs p) {
   const int c0 = blockIdx.z * 64;             // first channel of this CTA
   const int ch = r0 / p.chunk_pad, ib = r0 % p.chunk_pad;
   float amx = 0.f;
+  float* csum = p.chunk_sum ? p.chunk_sum + (slot * (p.rows_pad / p.chunk_pad) + ch) * DM + c0 : nullptr;
 #pragma unroll
   for (int k = 0; k < 8; ++k) {
     const int c = warp + 8 * k;
     const float* row = src + (long long)(c0 + c) * p.ch_stride + (long long)ch * p.chunk;
+    float sv = 0.f;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const int i = ib + lane + 32 * j;
@@ -100,6 +108,11 @@ __global__ void __launch_bounds__(256) pack128_kernel(const PackArgs p) {
       const float v = (i < p.chunk && n < p.n_points) ? __ldg(row + i) : 0.f;
       tile[lane + 32 * j][c] = v;
       amx = fmaxf(amx, fabsf(v));
+      sv += v;
+    }
+    if (csum) {
+      sv = warp_sum(sv);
+      if (lane == 0) atomicAdd(csum + c, sv);
     }
   }
   if (p.amax) {
@@ -361,11 +374,14 @@ struct LnBwdArgs {
   // implicit upstream gradient: dY[block] = src_w[block] * dYsrc[src_idx[block]] (rows of one shape), or 0 if src_idx < 0
   const int* src_idx; const float* src_w;
   int debug;
+  float* chunk_gsum;   // optional [rows/group_rows][256]: per-chunk column sums of dZ (atomically accumulated)
 };
 
-template <int MINB>
+template <int MINB, bool GS>
 __global__ void __launch_bounds__(256, MINB) ln_bwd_kernel(const LnBwdArgs p) {
   __shared__ float red[2][8][DM];
+  __shared__ float gsm[GS ? DM : 1];   // per-chunk column sums of dZ, accumulated with shared-memory atomics (no registers)
+  if (GS) { gsm[threadIdx.x] = 0.f; __syncthreads(); }
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long row0 = (long long)blockIdx.x * 64;
   const float4 g0 = __ldg(reinterpret_cast<const float4*>(p.gamma) + lane), g1 = __ldg(reinterpret_cast<const float4*>(p.gamma) + 32 + lane);
@@ -440,6 +456,10 @@ __global__ void __launch_bounds__(256, MINB) ln_bwd_kernel(const LnBwdArgs p) {
     float o[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) o[j] = rs * (g[j] - s1 - xh[j] * s2);
+    if (GS) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { atomicAdd(&gsm[lane * 4 + j], o[j]); atomicAdd(&gsm[128 + lane * 4 + j], o[4 + j]); }
+    }
     if (dz4) {
       dz4[lane] = make_float4(o[0], o[1], o[2], o[3]);
       dz4[32 + lane] = make_float4(o[4], o[5], o[6], o[7]);
@@ -468,6 +488,8 @@ __global__ void __launch_bounds__(256, MINB) ln_bwd_kernel(const LnBwdArgs p) {
   if (p.debug & 1) return;
   atomicAdd(p.dgamma + c, s);
   atomicAdd(p.dbeta + c, t);
+  if (GS)   // the CTA's 64 rows lie inside one chunk (64 | group_rows); gsm is complete after the barrier above
+    atomicAdd(p.chunk_gsum + (row0 / p.group_rows) * DM + c, gsm[c]);
 }
 
 // ------------------------------------------------------------------------------------------ combine fwd
@@ -669,14 +691,14 @@ extern "C" {
 int csn_pack_rows(const float* src, void* dst16, float* dst32, int64_t ch_stride, int32_t n0, int64_t src_s0,
                   int32_t n1, int64_t src_s1, int64_t dst_slot0, int64_t dst_s0, int64_t dst_s1,
                   int32_t n_points, int32_t chunk, int32_t chunk_pad, int32_t rows_pad, int32_t dtype,
-                  float* amax, void* stream) {
+                  float* amax, float* chunk_sum, void* stream) {
   using namespace csn;
   clear_error();
   CSN_CHECK_ARG(src && (dst16 || dst32), "csn_pack_rows: null pointer");
   CSN_CHECK_ARG(chunk_pad % 32 == 0 && rows_pad % chunk_pad == 0 && chunk <= chunk_pad, "csn_pack_rows: bad padding (chunk=%d chunk_pad=%d rows_pad=%d)", chunk, chunk_pad, rows_pad);
   CSN_CHECK_ARG(dtype == CSN_F16 || dtype == CSN_BF16, "csn_pack_rows: 16-bit destination only");
   if (n0 * n1 == 0) return 0;
-  PackArgs a{src, dst16, dst32, ch_stride, src_s0, src_s1, dst_slot0, dst_s0, dst_s1, n0, n1, n_points, chunk, chunk_pad, rows_pad, dtype, amax};
+  PackArgs a{src, dst16, dst32, ch_stride, src_s0, src_s1, dst_slot0, dst_s0, dst_s1, n0, n1, n_points, chunk, chunk_pad, rows_pad, dtype, amax, chunk_sum};
   static const bool wide = getenv("CSN_PACK128") == nullptr || atoi(getenv("CSN_PACK128")) != 0;
   if (wide && chunk_pad % 128 == 0)
     return launch_simple(pack128_kernel, dim3(rows_pad / 128, n0 * n1, 4), dim3(256), a, stream, "pack128_kernel");
@@ -751,19 +773,24 @@ int csn_colsum_reduce(const float* part, float* out, int32_t n_blocks, int32_t p
 int csn_ln_bwd(const float* dY, const float* Z, const float* mean, const float* rstd, const float* gamma, float* dZ,
                void* dZ16, float* dgamma, float* dbeta, int64_t rows, int32_t block_rows, int32_t group_rows,
                int32_t rows_valid, int32_t dtype, const float* amax, const float* bcast, const int32_t* bcast_idx,
-               float bcast_scale, const int32_t* src_idx, const float* src_w, void* stream) {
+               float bcast_scale, const int32_t* src_idx, const float* src_w, float* chunk_gsum, void* stream) {
   using namespace csn;
   clear_error();
   CSN_CHECK_ARG(dY && Z && mean && rstd && gamma && dZ16 && dgamma && dbeta, "csn_ln_bwd: null pointer");
+  CSN_CHECK_ARG(!chunk_gsum || group_rows % 64 == 0, "csn_ln_bwd: chunk_gsum needs group_rows to be a multiple of 64");
   CSN_CHECK_ARG(!bcast || bcast_idx, "csn_ln_bwd: bcast needs bcast_idx");
   CSN_CHECK_ARG(!src_idx || src_w, "csn_ln_bwd: src_idx needs src_w");
   CSN_CHECK_ARG(rows % 64 == 0 && block_rows % 64 == 0, "csn_ln_bwd: rows and block_rows must be multiples of 64");
   if (rows == 0) return 0;
-  LnBwdArgs a{dY, Z, mean, rstd, gamma, dZ, dZ16, dgamma, dbeta, rows, group_rows, rows_valid, block_rows, dtype, amax, bcast, bcast_idx, bcast_scale, src_idx, src_w, getenv("CSN_LN_BWD_DEBUG") ? atoi(getenv("CSN_LN_BWD_DEBUG")) : 0};
+  LnBwdArgs a{dY, Z, mean, rstd, gamma, dZ, dZ16, dgamma, dbeta, rows, group_rows, rows_valid, block_rows, dtype, amax, bcast, bcast_idx, bcast_scale, src_idx, src_w, getenv("CSN_LN_BWD_DEBUG") ? atoi(getenv("CSN_LN_BWD_DEBUG")) : 0, chunk_gsum};
   static const int occ = getenv("CSN_LN_BWD_OCC") ? atoi(getenv("CSN_LN_BWD_OCC")) : 3;   // resident CTAs/SM (tuning knob)
-  if (occ >= 4) return launch_simple(ln_bwd_kernel<4>, dim3((unsigned)(rows / 64)), dim3(256), a, stream, "ln_bwd_kernel");
-  if (occ >= 3) return launch_simple(ln_bwd_kernel<3>, dim3((unsigned)(rows / 64)), dim3(256), a, stream, "ln_bwd_kernel");
-  return launch_simple(ln_bwd_kernel<2>, dim3((unsigned)(rows / 64)), dim3(256), a, stream, "ln_bwd_kernel");
+  if (chunk_gsum) {
+    if (occ >= 3) return launch_simple(ln_bwd_kernel<3, true>, dim3((unsigned)(rows / 64)), dim3(256), a, stream, "ln_bwd_kernel");
+    return launch_simple(ln_bwd_kernel<2, true>, dim3((unsigned)(rows / 64)), dim3(256), a, stream, "ln_bwd_kernel");
+  }
+  if (occ >= 4) return launch_simple(ln_bwd_kernel<4, false>, dim3((unsigned)(rows / 64)), dim3(256), a, stream, "ln_bwd_kernel");
+  if (occ >= 3) return launch_simple(ln_bwd_kernel<3, false>, dim3((unsigned)(rows / 64)), dim3(256), a, stream, "ln_bwd_kernel");
+  return launch_simple(ln_bwd_kernel<2, false>, dim3((unsigned)(rows / 64)), dim3(256), a, stream, "ln_bwd_kernel");
 }
 
 int csn_combine_fwd(const float* Y, const int32_t* blk, const float* w, float* out, void* rows16, int32_t n_b,

@@ -57,6 +57,11 @@ struct GemmArgs {
   int dl_rows_pad, dl_n_head, dl_d_head;
   float dl_lo_inv;   // 1/2048 (fp16) or 1/256 (bf16); 0 when there is no O_lo
   int debug;   // CSN_GEMM_DEBUG (diagnostics only): 1 = epilogue drains TMEM but stores nothing
+  // column bias per row group (csn_gemm_colbias): D[row][col] -= cbias[(row / cb_group)*cb_ld + col - cb_col0] for
+  // col >= cb_col0 and row % cb_group < cb_valid (TMA-store epilogue only).  V is centred on its per-chunk key mean.
+  const float* cbias; long long cb_ld; int cb_col0, cb_group, cb_valid; float cb_inv_alpha;
+  // csn_gemm_res_ln: optional per-chunk row vector added to z, zbias[(row / group_rows)*256 + col]
+  const float* zbias;
 };
 
 template <int BN>
@@ -87,9 +92,17 @@ __device__ __forceinline__ TileCoord decode_tile(long long t64, const GemmArgs& 
     t = q;
     return r;
   };
-  c.ks = step(p.split_k);
-  c.nt = step(p.tiles_n);
-  c.mt = step(p.tiles_m);
+  if (p.split_k > 1) {
+    // split-K (weight gradients: M x N small, K = all points): the CTAs that run concurrently take the m- / n-tiles
+    // of the SAME k range, so every operand k-slice is fetched from HBM once and re-read from L2 by the other tiles
+    c.mt = step(p.tiles_m);
+    c.nt = step(p.tiles_n);
+    c.ks = step(p.split_k);
+  } else {
+    c.ks = 0;
+    c.nt = step(p.tiles_n);
+    c.mt = step(p.tiles_m);
+  }
   c.b0 = step(p.nb0);
   c.b1 = step(p.nb1);
   c.b2 = step(p.nb2);
@@ -453,11 +466,22 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           const uint32_t rs = wbuf + (2 + (u & 1)) * 4096 + (lane & 3) * 4;
           float z[32];
           float su = 0.f;
+          if (p.zbias) {   // warp-uniform row (the warp's 32 rows lie in one chunk): broadcast loads
+            const float4* zb4 = reinterpret_cast<const float4*>(p.zbias + (long long)(row0 / p.group_rows) * BN + u * 32);
+#pragma unroll
+            for (int j4 = 0; j4 < 8; ++j4) {
+              const float4 bv = __ldg(zb4 + j4);
+              z[4 * j4] = bv.x; z[4 * j4 + 1] = bv.y; z[4 * j4 + 2] = bv.z; z[4 * j4 + 3] = bv.w;
+            }
+          } else {
+#pragma unroll
+            for (int jj = 0; jj < 32; ++jj) z[jj] = 0.f;
+          }
 #pragma unroll
           for (int jj = 0; jj < 32; ++jj) {
             float rv;
             asm volatile("ld.shared.f32 %0, [%1];" : "=f"(rv) : "r"(rs + jj * 128 + ((((uint32_t)lane >> 2) ^ ((uint32_t)jj & 7u)) << 4)));
-            z[jj] = valid ? __uint_as_float(r[jj]) * al + rv : 0.f;
+            z[jj] = valid ? __uint_as_float(r[jj]) * al + rv + z[jj] : 0.f;
             su += z[jj];
           }
           __syncwarp();
@@ -522,7 +546,24 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         const int u0 = half * s_half * g, u1 = min(n_slabs, (half + 1) * s_half) * g;
         const float al = p.alpha;
         uint32_t ra[32], rb[32];
-        auto emit = [&](const uint32_t (&r)[32], int u) {
+        // column bias: the 32 rows of this warp lie in one row group, so the bias row is warp-uniform (broadcast loads)
+        const bool cb_rows = p.cbias != nullptr && ((row0 + lane) % p.cb_group) < p.cb_valid;
+        const float* cb_row = p.cbias ? p.cbias + (long long)(row0 / p.cb_group) * p.cb_ld - p.cb_col0 : nullptr;
+        auto emit = [&](uint32_t (&r)[32], int u) {
+          if (p.cbias && has_k && n0 + u * 32 >= p.cb_col0) {
+            const float4* b4 = reinterpret_cast<const float4*>(cb_row + n0 + u * 32);
+#pragma unroll
+            for (int j4 = 0; j4 < 8; ++j4) {
+              const float4 bv = __ldg(b4 + j4);
+              // (alpha * acc - bias) is formed here; the stores below multiply by alpha, so pre-divide the bias
+              if (cb_rows) {
+                r[4 * j4 + 0] = __float_as_uint(__uint_as_float(r[4 * j4 + 0]) - bv.x * p.cb_inv_alpha);
+                r[4 * j4 + 1] = __float_as_uint(__uint_as_float(r[4 * j4 + 1]) - bv.y * p.cb_inv_alpha);
+                r[4 * j4 + 2] = __float_as_uint(__uint_as_float(r[4 * j4 + 2]) - bv.z * p.cb_inv_alpha);
+                r[4 * j4 + 3] = __float_as_uint(__uint_as_float(r[4 * j4 + 3]) - bv.w * p.cb_inv_alpha);
+              }
+            }
+          }
           if (p.debug & 8) { if (r[0] == 0x7fc12345u && r[31] == 0x7fc12345u) atomicAdd(reinterpret_cast<int*>(p.D), 1); return; }   // diagnostics: TMEM loads only
           const uint32_t buf = stg_base + (ew * p.stg_bufs + stg_flip) * 4096;
           const uint32_t rowaddr = buf + lane * 128;
@@ -660,6 +701,11 @@ static int dispatch_major(bool a_mn, bool b_mn, const CUtensorMap& tmA, const CU
 struct LnEpilogue {
   const float* res0; long long res0_rows; const float* res1; long long res1_rows; const int* res_sel; const int* res_row;
   long long res_ld; int block_rows, group_rows, rows_valid, n_points; float eps; float* mean; float* rstd;
+  const float* zbias;
+};
+
+struct ColBias {
+  const float* bias; long long ld; int col0, group_rows, rows_valid;
 };
 
 struct DeltaEpilogue {
@@ -670,7 +716,7 @@ struct DeltaEpilogue {
 
 static int gemm_impl(const csn_mat* A, const csn_mat* B, const csn_out* D, int32_t M, int32_t N,
                      int32_t K, const int32_t nb[4], float alpha, int32_t split_k, void* stream,
-                     const csn::LnEpilogue* ln, const csn::DeltaEpilogue* dl = nullptr) {
+                     const csn::LnEpilogue* ln, const csn::DeltaEpilogue* dl = nullptr, const csn::ColBias* cb = nullptr) {
   using namespace csn;
   clear_error();
   CSN_CHECK_ARG(A && B && D && nb, "csn_gemm: null argument");
@@ -761,6 +807,14 @@ static int gemm_impl(const csn_mat* A, const csn_mat* B, const csn_out* D, int32
     g.epi_warps = deep_staging ? 8 : 4;
     g.tempty_count = 32 * g.epi_warps;
   }
+  if (cb) {
+    CSN_CHECK_ARG(g.tma_store && !D->accumulate, "csn_gemm_colbias: needs a row-major, 16-byte aligned, non-accumulating output");
+    CSN_CHECK_ARG(cb->group_rows % 32 == 0 && cb->col0 % 32 == 0 && cb->ld % 4 == 0 && (reinterpret_cast<uintptr_t>(cb->bias) & 15) == 0,
+                  "csn_gemm_colbias: group_rows and col0 must be multiples of 32, the bias rows 16-byte aligned");
+    CSN_CHECK_ARG((long long)nb[0] * nb[1] * nb[2] * nb[3] == 1, "csn_gemm_colbias: one batch");
+    g.cbias = cb->bias; g.cb_ld = cb->ld; g.cb_col0 = cb->col0; g.cb_group = cb->group_rows; g.cb_valid = cb->rows_valid;
+    g.cb_inv_alpha = 1.f / alpha;
+  }
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   if (dl) {
     const long long nbt = (long long)nb[0] * nb[1] * nb[2] * nb[3];
@@ -803,7 +857,7 @@ static int gemm_impl(const csn_mat* A, const csn_mat* B, const csn_out* D, int32
     g.ln = 1;
     g.res_sel = ln->res_sel; g.res_row = ln->res_row;
     g.block_rows = ln->block_rows; g.group_rows = ln->group_rows; g.rows_valid = ln->rows_valid; g.n_points = ln->n_points;
-    g.eps = ln->eps; g.mean = ln->mean; g.rstd = ln->rstd;
+    g.eps = ln->eps; g.mean = ln->mean; g.rstd = ln->rstd; g.zbias = ln->zbias;
     // the thread owns its whole row; two warp sets alternate tiles (one per accumulator buffer); per warp 2 output
     // + 2 residual slabs -> 128 KB of staging next to a 2-deep operand ring (K is short: the epilogue is the critical path)
     g.stages = 2; g.stg_bufs = 4; g.epi_warps = 8; g.alt_tiles = 1; g.tempty_count = 128;
@@ -828,7 +882,7 @@ extern "C" int csn_gemm_res_ln(const csn_mat* A, const csn_mat* B, float* Z, int
                                float alpha, const float* res0, int64_t res0_rows, const float* res1,
                                int64_t res1_rows, const int32_t* res_sel, const int32_t* res_row, int64_t res_ld,
                                int32_t n_points, int32_t block_rows, int32_t group_rows, int32_t rows_valid,
-                               float eps, float* mean, float* rstd, void* stream) {
+                               float eps, float* mean, float* rstd, const float* zbias, void* stream) {
   using namespace csn;
   clear_error();
   CSN_CHECK_ARG(Z && res0 && res_sel && res_row && mean && rstd, "csn_gemm_res_ln: null pointer");
@@ -837,9 +891,21 @@ extern "C" int csn_gemm_res_ln(const csn_mat* A, const csn_mat* B, float* Z, int
   memset(&D, 0, sizeof(D));
   D.ptr = Z; D.dtype = CSN_F32; D.ld = ldz;
   LnEpilogue ln{res0, res0_rows, res1 ? res1 : res0, res1 ? res1_rows : res0_rows, res_sel, res_row, res_ld,
-                block_rows, group_rows, rows_valid, n_points, eps, mean, rstd};
+                block_rows, group_rows, rows_valid, n_points, eps, mean, rstd, zbias};
+  CSN_CHECK_ARG(!zbias || (reinterpret_cast<uintptr_t>(zbias) & 15) == 0, "csn_gemm_res_ln: zbias must be 16-byte aligned");
   const int32_t nb[4] = {1, 1, 1, 1};
   return gemm_impl(A, B, &D, M, 256, K, nb, alpha, 1, stream, &ln);
+}
+
+extern "C" int csn_gemm_colbias(const csn_mat* A, const csn_mat* B, const csn_out* D, int32_t M, int32_t N, int32_t K,
+                                float alpha, const float* bias, int64_t bias_ld, int32_t col0, int32_t group_rows,
+                                int32_t rows_valid, void* stream) {
+  using namespace csn;
+  clear_error();
+  CSN_CHECK_ARG(bias != nullptr, "csn_gemm_colbias: null bias");
+  ColBias cb{bias, bias_ld, col0, group_rows, rows_valid};
+  const int32_t nb[4] = {1, 1, 1, 1};
+  return gemm_impl(A, B, D, M, N, K, nb, alpha, 1, stream, nullptr, nullptr, &cb);
 }
 
 extern "C" int csn_gemm_delta(const csn_mat* A, const csn_mat* B, void* dO, int64_t lddo, int32_t M, int32_t N, int32_t K,

@@ -44,7 +44,7 @@ struct HeadArgs {
   float* loss_part;          // [gridDim.x]: sum of -log p[label] over the CTA's valid points
   float* dOutT;              // [n_b*rows_pad][256] or null (forward only)
   float* amax;               // optional: max |dOutT| (atomic max on the bit pattern; zero-initialised by the caller)
-  float* dcomp;              // [n_b*n_k], atomically accumulated (zero-initialised by the caller) or null
+  double* dcomp;             // [n_b*n_k] fp64, atomically accumulated (zero-initialised by the caller) or null
   float* dW_part;            // [gridDim.x][C][256] per-CTA partial sums of dlogits^T y
   int* stats;                // [3*C + 2]: #pred==c, #label==c, #both, then #correct, #labels out of range
   float* y_out;              // optional [n_b*rows_pad][256]: the combined features, row-major padded rows
@@ -62,7 +62,8 @@ struct HeadSmem {
   static constexpr int OFF_G = OFF_RED + 64;
   static constexpr int OFF_HIST = OFF_G + 512;
   static constexpr int OFF_BAR = (OFF_HIST + 3 * CMAX + 2 + 3) / 4 * 4;
-  static constexpr int BYTES = (OFF_BAR + 4) * 4;
+  static constexpr int OFF_RED64 = OFF_BAR + 4;              // [8][8] doubles
+  static constexpr int BYTES = (OFF_RED64 + 128) * 4;
 };
 
 template <int CMAX, int NK, int R>
@@ -77,6 +78,7 @@ __global__ void __launch_bounds__(256, (R == 8 && CMAX == 16 && NK <= 4) ? 2 : 1
   float* gsm = hsm + SM::OFF_G;                       // gamma [256] | beta [256]
   int* hist = reinterpret_cast<int*>(hsm + SM::OFF_HIST);
   const uint32_t bar0 = smem_u32(hsm + SM::OFF_BAR);
+  double* red64 = reinterpret_cast<double*>(hsm + SM::OFF_RED64);
   constexpr int RPT = R / 8;                          // rows per thread in P2a / rows per warp in P1, P2b, P4
   constexpr int CQ = CMAX / 4;                        // classes per thread in P2a
   constexpr int CL = (CMAX + 31) / 32;                // classes per lane in P2b
@@ -102,9 +104,11 @@ __global__ void __launch_bounds__(256, (R == 8 && CMAX == 16 && NK <= 4) ? 2 : 1
 #pragma unroll
   for (int c = 0; c < CMAX; ++c) dw[c] = 0.f;
   float amx = 0.f, lacc = 0.f;
-  float dc[NK];
+  // d comp is consumed through differences of nearly equal numbers (softmax backward over the K+1 attention
+  // outputs of one query): its partial sums are carried in fp64 from the per-row dot products onwards
+  double dc[NK];
 #pragma unroll
-  for (int k = 0; k < NK; ++k) dc[k] = 0.f;
+  for (int k = 0; k < NK; ++k) dc[k] = 0.0;
   __syncthreads();
 
   const int t_begin = (int)((long long)p.n_tiles * blockIdx.x / gridDim.x);
@@ -127,15 +131,17 @@ __global__ void __launch_bounds__(256, (R == 8 && CMAX == 16 && NK <= 4) ? 2 : 1
   auto flush_dcomp = [&](int b) {   // called by every thread (CTA-uniform)
 #pragma unroll
     for (int k = 0; k < NK; ++k) {
-      const float s = warp_sum(dc[k]);
-      if (lane == 0) red[warp * 8 + k] = s;
-      dc[k] = 0.f;
+      double s = dc[k];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+      if (lane == 0) red64[warp * 8 + k] = s;
+      dc[k] = 0.0;
     }
     __syncthreads();
     if (tid < p.n_k) {
-      float s = 0.f;
+      double s = 0.0;
 #pragma unroll
-      for (int w2 = 0; w2 < 8; ++w2) s += red[w2 * 8 + tid];
+      for (int w2 = 0; w2 < 8; ++w2) s += red64[w2 * 8 + tid];
       atomicAdd(p.dcomp + b * p.n_k + tid, s);
     }
     __syncthreads();
@@ -335,7 +341,7 @@ __global__ void __launch_bounds__(256, (R == 8 && CMAX == 16 && NK <= 4) ? 2 : 1
           const float m = ms[k * R + rr];
           const float s = (ga.x * (za.x - m) + ga.y * (za.y - m)) + (ga.z * (za.z - m) + ga.w * (za.w - m)) +
                           (gc.x * (zc.x - m) + gc.y * (zc.y - m)) + (gc.z * (zc.z - m) + gc.w * (zc.w - m));
-          dc[k] += rss[k * R + rr] * s + sb;
+          dc[k] += (double)(rss[k * R + rr] * s) + (double)sb;
         }
     }
     __syncthreads();   // stage and ys are free again
@@ -437,7 +443,7 @@ extern "C" int csn_csa_head(const float* Z, const float* mean, const float* rstd
                             const int32_t* blk, const float* w, int32_t n_b, int32_t n_k, const float* W, int32_t n_classes,
                             const int64_t* labels, int64_t lab_stride, int32_t ignore_index, int32_t* n_valid,
                             int32_t n_points, int32_t chunk, int32_t chunk_pad, int32_t rows_pad, float* loss_part,
-                            float* dOutT, float* amax, float* dcomp, float* dW_part, float* dW, int32_t* stats, float* y_out,
+                            float* dOutT, float* amax, double* dcomp, float* dW_part, float* dW, int32_t* stats, float* y_out,
                             void* stream) {
   using namespace csn;
   clear_error();

@@ -94,6 +94,6 @@ int make_tmap_2d_any(CUtensorMap* tm, const void* ptr, int dtype, int64_t inner,
 
 extern "C" {
 const char* csn_last_error(void) { return csn::g_err; }
-int csn_abi_version(void) { return 1; }
+int csn_abi_version(void) { return 2; }
 int64_t csn_launch_count(void) { return csn::launch_counter().load(); }
 }

@@ -68,12 +68,38 @@ class Group:
                        self.k0 + o * self.k_so + i * self.k_si, self.v0 + o * self.v_so + i * self.v_si)
 
 
-def _launch_pack(src: torch.Tensor, dst16, dst32, n0, s0, n1, s1, slot0, d0, d1, geom: Geometry, n_src_points):
-    """src: fp32 view whose element (i0,i1,c,n) sits at i0*s0 + i1*s1 + c*n_src_points + n."""
+def _launch_pack(src: torch.Tensor, dst16, dst32, n0, s0, n1, s1, slot0, d0, d1, geom: Geometry, n_src_points,
+                 chunk_sum=None):
+    """src: fp32 view whose element (i0,i1,c,n) sits at i0*s0 + i1*s1 + c*n_src_points + n.
+    chunk_sum (optional, zero-initialised [n_slots*n_chunks, 256]): per-chunk channel sums of every packed shape."""
     rc = L.lib().csn_pack_rows(src.data_ptr(), dst16.data_ptr(), dst32.data_ptr() if dst32 is not None else None,
                                n_src_points, n0, s0, n1, s1, slot0, d0, d1, geom.n_points, geom.chunk,
-                               geom.chunk_pad, geom.rows_pad, L.dtype_code(dst16.dtype), None, L.stream_ptr())
+                               geom.chunk_pad, geom.rows_pad, L.dtype_code(dst16.dtype), None,
+                               chunk_sum.data_ptr() if chunk_sum is not None else None, L.stream_ptr())
     L.check(rc, "csn_pack_rows")
+
+
+def sgemm_small(A, B, D, M, N, K, alpha=1.0, a_rows=None, b_rows=None, trans_a=False, trans_b=False, accumulate=False):
+    """D[m][n] (+)= alpha * sum_k opA(m,k) opB(n,k) in fp32 on CUDA cores (csn_sgemm_small); 2-D row-major tensors."""
+    rc = L.lib().csn_sgemm_small(A.data_ptr(), A.stride(0), a_rows.data_ptr() if a_rows is not None else None, int(trans_a),
+                                 B.data_ptr(), B.stride(0), b_rows.data_ptr() if b_rows is not None else None, int(trans_b),
+                                 D.data_ptr(), D.stride(0), M, N, K, float(alpha), int(accumulate), L.stream_ptr())
+    L.check(rc, "csn_sgemm_small")
+
+
+def use_centered_v() -> bool:
+    """CSN_CENTER_V=0 keeps V uncentred (and the rounding residual of O) on the fused CSA path; tests cross-check."""
+    return os.environ.get("CSN_CENTER_V", "1") != "0"
+
+
+def _kv_chunk_table(groups, n_blocks, n_chunks):
+    """Row of the per-(slot, chunk) table that belongs to (block j, chunk c): key/value slot of j times n_chunks + c."""
+    t = torch.empty(n_blocks, n_chunks, dtype=torch.int32)
+    ar = torch.arange(n_chunks, dtype=torch.int32)
+    for g in groups:
+        for (j, _, ks, _) in g.blocks():
+            t[j] = ks * n_chunks + ar
+    return t.reshape(-1)
 
 
 @dataclass
@@ -227,7 +253,8 @@ class ChannelMajorResidual:
 def attention_forward(Xh, Xf, groups, n_slots, n_blocks, w_q, w_k, w_v, w_o, gamma, beta, geom: Geometry,
                       n_head: int, want_colsum: bool = True, save_for_backward: bool = True,
                       want_y: bool = True, residual_cm: ChannelMajorResidual = None,
-                      colsum_blocks: int = None, dropout_p: float = 0.0, seed: int = 0) -> AttnContext:
+                      colsum_blocks: int = None, dropout_p: float = 0.0, seed: int = 0,
+                      chunk_sum: torch.Tensor = None) -> AttnContext:
     """Forward of all blocks. Xh/Xf: packed slots [S*NP, 256] (16-bit / fp32). With residual_cm (and want_y False)
     Xf may be None: the output projection, the residual add and the LayerNorm statistics run as ONE kernel
     (csn_gemm_res_ln) that reads the residual from the channel-major inputs; colsum then covers the first
@@ -244,17 +271,36 @@ def attention_forward(Xh, Xf, groups, n_slots, n_blocks, w_q, w_k, w_v, w_o, gam
     ctx.gamma = gamma
     # --- projections: one GEMM for Q, K and V of every slot (csa_models.py:103-105, de-duplicated)
     QKV = torch.empty(n_slots * NP, 3 * HD, dtype=dt, device=dev)
-    L.gemm(L.mat(Xh, L.MAJOR_K), L.mat(ctx.Wqkv16, L.MAJOR_K), L.out(QKV, 3 * HD), n_slots * NP, 3 * HD, 256)
+    ragged = any(g.kv_lens or g.q_lens for g in groups)
+    fused = use_fused_attention(d) and all(g.k0 == g.v0 and g.k_si == g.v_si and g.k_so == g.v_so for g in groups)
+    fused_ln = residual_cm is not None and not want_y and use_fused_ln()
+    # V centred on its per-chunk key mean c = mean_chunk(X) Wv^T (softmax rows sum to one: attn (V - c) + c == attn V):
+    # the 16-bit V - c, the 16-bit O' = attn (V - c) and delta = rowsum(dO o O') lose ~10x less to rounding than V / O
+    # (post-ReLU features give every value row a large common mean), so no rounding residual of O is kept; c Wo^T
+    # re-enters the pre-LayerNorm sum in fp32 (zbias of csn_gemm_res_ln), d fc.weight gets the matching correction.
+    center = fused and fused_ln and not ragged and chunk_sum is not None and use_centered_v()
+    if center:
+        cvec = torch.empty(n_slots * NC, HD, dtype=torch.float32, device=dev)
+        sgemm_small(chunk_sum, w_v.detach().float().contiguous(), cvec, n_slots * NC, HD, 256, alpha=1.0 / geom.chunk)
+        A_, B_, D_ = L.mat(Xh, L.MAJOR_K), L.mat(ctx.Wqkv16, L.MAJOR_K), L.out(QKV, 3 * HD)
+        rc = L.lib().csn_gemm_colbias(C.byref(A_), C.byref(B_), C.byref(D_), n_slots * NP, 3 * HD, 256, 1.0, cvec.data_ptr(),
+                                      HD, 2 * HD, CP, geom.chunk, L.stream_ptr())
+        L.check(rc, "csn_gemm_colbias")
+        kv_idx = cached_table(("kv_chunk", tuple(groups), n_blocks, NC), dev, lambda: _kv_chunk_table(groups, n_blocks, NC))
+        zbias = torch.empty(n_blocks * NC, 256, dtype=torch.float32, device=dev)
+        sgemm_small(cvec, w_o.detach().float().contiguous(), zbias, n_blocks * NC, 256, HD, a_rows=kv_idx)
+        ctx.extra["center"] = (cvec, kv_idx)
+    else:
+        L.gemm(L.mat(Xh, L.MAJOR_K), L.mat(ctx.Wqkv16, L.MAJOR_K), L.out(QKV, 3 * HD), n_slots * NP, 3 * HD, 256)
+        zbias = None
     ctx.QKV = QKV
     Qv, Kv, Vv = QKV[:, :HD], QKV[:, HD:2 * HD], QKV[:, 2 * HD:]
-    ragged = any(g.kv_lens or g.q_lens for g in groups)
     O = (torch.zeros if ragged else torch.empty)(n_blocks * NP, HD, dtype=dt, device=dev)
-    fused = use_fused_attention(d) and all(g.k0 == g.v0 and g.k_si == g.v_si and g.k_so == g.v_so for g in groups)
     if fused:
         # --- fused flash-style core (csa_models.py:139-142): scores never leave TMEM
         items = attn_items(groups, geom, n_head, d, dev)
         lse = torch.empty(n_blocks * n_head * NP, dtype=torch.float32, device=dev)
-        O_lo = (torch.zeros_like(O) if ragged else torch.empty_like(O)) if torch.is_grad_enabled() or save_for_backward else None
+        O_lo = (torch.zeros_like(O) if ragged else torch.empty_like(O)) if (torch.is_grad_enabled() or save_for_backward) and not center else None
         rc = L.lib().csn_attn_fwd(Qv.data_ptr(), Kv.data_ptr(), Vv.data_ptr(), n_slots * NP, n_slots * NP, HD,
                                   3 * HD, 3 * HD, 3 * HD, d, L.dtype_code(dt), items.data_ptr(), items.shape[0],
                                   O.data_ptr(), O.shape[0], HD, lse.data_ptr(), O_lo.data_ptr() if O_lo is not None else None,
@@ -280,7 +326,7 @@ def attention_forward(Xh, Xf, groups, n_slots, n_blocks, w_q, w_k, w_v, w_o, gam
     Z = torch.empty(n_blocks * NP, 256, dtype=torch.float32, device=dev)
     ctx.res_block = cached_table(("res_block", tuple(groups), n_blocks), dev,
                                  lambda: _res_block_table(groups, n_blocks))
-    if residual_cm is not None and not want_y and use_fused_ln():
+    if fused_ln:
         r = residual_cm
         sel = cached_table(("res_sel", tuple(groups), n_blocks, r.sel), dev,
                            lambda: torch.tensor([r.sel[q] for q in _res_block_table(groups, n_blocks).tolist()], dtype=torch.int32))
@@ -293,7 +339,8 @@ def attention_forward(Xh, Xf, groups, n_slots, n_blocks, w_q, w_k, w_v, w_o, gam
         rc = L.lib().csn_gemm_res_ln(C.byref(A), C.byref(B), Z.data_ptr(), 256, n_blocks * NP, HD, 1.0,
                                      b0.data_ptr(), b0.numel() // r.ch_stride, b1.data_ptr(), b1.numel() // r.ch_stride,
                                      sel.data_ptr(), off.data_ptr(), r.ch_stride, min(r.n_points, geom.n_points),
-                                     NP, CP, geom.chunk, 1e-6, ctx.mean.data_ptr(), ctx.rstd.data_ptr(), L.stream_ptr())
+                                     NP, CP, geom.chunk, 1e-6, ctx.mean.data_ptr(), ctx.rstd.data_ptr(),
+                                     zbias.data_ptr() if zbias is not None else None, L.stream_ptr())
         L.check(rc, "csn_gemm_res_ln")
         ctx.colsum = None
         if want_colsum:
@@ -403,19 +450,25 @@ def attention_backward(ctx: AttnContext, dY: torch.Tensor, need_dx: bool, amax: 
     dZ16 = torch.empty(nblk * NP, 256, dtype=dt, device=dev)
     dgamma = torch.zeros(256, dtype=torch.float32, device=dev)
     dbeta = torch.zeros(256, dtype=torch.float32, device=dev)
+    center = ctx.extra.get("center")
+    gsum = torch.zeros(nblk * NC, 256, dtype=torch.float32, device=dev) if center is not None else None
     rc = lib.csn_ln_bwd(dY.data_ptr(), ctx.Z.data_ptr(), ctx.mean.data_ptr(), ctx.rstd.data_ptr(),
                         ctx.gamma.data_ptr(), dZ.data_ptr() if dZ is not None else None, dZ16.data_ptr(),
                         dgamma.data_ptr(), dbeta.data_ptr(), nblk * NP, NP, CP, geom.chunk, L.dtype_code(dt),
                         amax.data_ptr(), bcast.data_ptr() if bcast is not None else None,
                         bcast_idx.data_ptr() if bcast_idx is not None else None, bcast_scale,
                         src_idx.data_ptr() if src_idx is not None else None,
-                        src_w.data_ptr() if src_w is not None else None, L.stream_ptr())
+                        src_w.data_ptr() if src_w is not None else None,
+                        gsum.data_ptr() if gsum is not None else None, L.stream_ptr())
     L.check(rc, "csn_ln_bwd")
     split = _pick_split(2 * ((HD + 255) // 256), nblk * NP // 64)
     # --- dWo = dZ^T O  (contraction over all rows; both operands consumed MN-major)
     dWo = torch.zeros(256, HD, dtype=torch.float32, device=dev)
     L.gemm(L.mat(dZ16, L.MAJOR_MN), L.mat(ctx.O, L.MAJOR_MN), L.out(dWo, HD, accumulate=True), 256, HD, nblk * NP,
            split_k=split)
+    if center is not None:   # ctx.O holds O' = O - c: d fc.weight += sum over chunks of (sum_rows dZ)^T c
+        cvec, kv_idx = center
+        sgemm_small(gsum, cvec, dWo, 256, HD, nblk * NC, b_rows=kv_idx, trans_a=True, trans_b=True, accumulate=True)
     # --- dO = dZ Wo; on the fused path the same kernel also forms delta = rowsum(dO o O) per (row, head)
     dO = torch.empty(nblk * NP, HD, dtype=dt, device=dev)
     fused_delta = (ctx.P is None and "lse" in ctx.extra and os.environ.get("CSN_FUSED_BWD", "1") != "0"

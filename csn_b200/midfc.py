@@ -61,19 +61,21 @@ def _std_layout(t: torch.Tensor) -> torch.Tensor:
     return t if t.is_contiguous() else t.contiguous()
 
 
-def _pack_sources(sources, n_slots, geom, dt, dev, want_f32: bool = True):
-    """sources: list of (tensor (n0,[n1],256,N,1) fp32 cuda, slot0, d0, d1)."""
+def _pack_sources(sources, n_slots, geom, dt, dev, want_f32: bool = True, want_sum: bool = False):
+    """sources: list of (tensor (n0,[n1],256,N,1) fp32 cuda, slot0, d0, d1).  want_sum: also the per-chunk channel
+    sums of every slot, [n_slots*n_chunks, 256] fp32 (the key means V is centred on)."""
     NP = geom.rows_pad
     Xh = torch.empty(n_slots * NP, 256, dtype=dt, device=dev)
     Xf = torch.empty(n_slots * NP, 256, dtype=torch.float32, device=dev) if want_f32 else None
+    xsum = torch.zeros(n_slots * geom.n_chunks, 256, dtype=torch.float32, device=dev) if want_sum else None
     for (t, slot0, d0, d1) in sources:
         if t.dim() == 4:
             t = t.unsqueeze(1)
         assert t.dim() == 5 and t.shape[2] == 256 and t.shape[4] == 1, t.shape
         if t.stride(3) != 1 or t.stride(2) != t.shape[3]:
             t = t.contiguous()
-        E._launch_pack(t, Xh, Xf, t.shape[0], t.stride(0), t.shape[1], t.stride(1), slot0, d0, d1, geom, t.shape[3])
-    return Xh, Xf
+        E._launch_pack(t, Xh, Xf, t.shape[0], t.stride(0), t.shape[1], t.stride(1), slot0, d0, d1, geom, t.shape[3], xsum)
+    return (Xh, Xf, xsum) if want_sum else (Xh, Xf)
 
 
 def _unpad_rows(Y: torch.Tensor, n_blocks: int, geom: E.Geometry) -> torch.Tensor:
@@ -350,7 +352,8 @@ def _csa_forward_core(x, x_neighbors, wq, wk, wv, wo, gamma, beta, cq_w, cq_b, c
                     for b in range(B) for j in range(K + 1))
         res_cm = E.ChannelMajorResidual(bases=(xs,) if K == 0 else (xs, nbs), sel=sel, off=off,
                                         ch_stride=xs.shape[2], n_points=xs.shape[2])
-    Xh, Xf = _pack_sources(sources, S, geom, dt, dev, want_f32=res_cm is None or not E.use_fused_ln())
+    Xh, Xf, xsum = _pack_sources(sources, S, geom, dt, dev, want_f32=res_cm is None or not E.use_fused_ln(),
+                                 want_sum=True)
     groups = [E.Group(n_in=S, n_out=1, blk0=0, q0=0, q_si=1, q_so=0, k0=0, k_si=1, k_so=0, v0=0, v_si=1, v_so=0)]
     nblk = S
     if K > 0:
@@ -359,14 +362,16 @@ def _csa_forward_core(x, x_neighbors, wq, wk, wv, wo, gamma, beta, cq_w, cq_b, c
         nblk += B * K
     a = E.attention_forward(Xh, Xf, groups, S, nblk, wq, wk, wv, wo, gamma, beta, geom, n_head,
                             want_colsum=not ssa_only, want_y=False, residual_cm=res_cm, colsum_blocks=S,
-                            dropout_p=dropout_p, seed=seed)
+                            dropout_p=dropout_p, seed=seed, chunk_sum=xsum)
     # ---- compatibility (csa_models.py:211-230): tiny (B*(K+1) x 256) glue, kept in torch
     if ssa_only:
         comp = torch.ones(B, 1, dtype=torch.float32, device=dev)
         glue = None
     else:
-        pooled = a.colsum[:S].detach().clone().requires_grad_(True)   # slot order (b,k)
-        loc = [t.detach().requires_grad_(True) for t in (cq_w, cq_b, ck_w, ck_b)]
+        # fp64: the backward of this softmax subtracts nearly equal numbers (d comp of the K+1 attention outputs of one
+        # query differ in the 3rd-5th digit), and the tensors are tiny
+        pooled = a.colsum[:S].detach().double().requires_grad_(True)   # slot order (b,k)
+        loc = [t.detach().double().requires_grad_(True) for t in (cq_w, cq_b, ck_w, ck_b)]
         with torch.enable_grad():
             pv = pooled.view(B, K + 1, 256)
             y_q = pv[:, 0]
@@ -375,7 +380,7 @@ def _csa_forward_core(x, x_neighbors, wq, wk, wv, wo, gamma, beta, cq_w, cq_b, c
             u_k = F.normalize(F.linear(y_stack, loc[2], loc[3]), dim=-1)
             u_k = u_k.view(B, -1, 256)                               # batch-interleaving view (:227)
             comp_g = torch.softmax(torch.matmul(u_q.unsqueeze(1), u_k.permute(0, 2, 1)).squeeze(1), dim=-1)
-        comp = comp_g.detach()
+        comp = comp_g.detach().float()
         glue = (pooled, loc, comp_g)
 
     def _blk_table():
@@ -433,12 +438,12 @@ def _csa_backward_core(st: _CsaState, dOutT, amax, dcomp, need_dx: bool, out_sca
     dpool = None
     if st.glue is not None:
         pooled, loc, comp_g = st.glue
-        dc = dcomp.view(B, K + 1)
+        dc = dcomp.view(B, K + 1).double()
         if out_scale is not None:
-            dc = dc * out_scale
+            dc = dc * out_scale.double()
         gl = torch.autograd.grad(comp_g, [pooled] + loc, dc)
-        dpool = gl[0].contiguous()
-        grads_glue = list(gl[1:])
+        dpool = gl[0].float().contiguous()
+        grads_glue = [t.float() for t in gl[1:]]
         amax = amax + dpool.abs().max() / geom.n_points   # bound on |dY + dpool/N| for the gradient scaling (comp <= 1)
     # The upstream gradient of block j is comp[b,k] * dOut[b]^T (+ the pooled-mean row vector): csn_ln_bwd forms
     # cw[j] * dOutT[cb[j]] + dpool[pb[j]]/N on the fly; the (2K+1)x larger dY is never materialised.
@@ -490,7 +495,7 @@ class _CsaFn(torch.autograd.Function):
         amax = torch.zeros(1, dtype=torch.float32, device=dev)
         rc = lib.csn_pack_rows(dout.data_ptr(), None, dOutT.data_ptr(), geom.n_points, B, 256 * geom.n_points, 1, 0, 0, 1, 0,
                                geom.n_points, geom.chunk, geom.chunk_pad, geom.rows_pad, L.CSN_F16, amax.data_ptr(),
-                               L.stream_ptr())
+                               None, L.stream_ptr())
         L.check(rc, "csn_pack_rows(dOut)")
         # d comp[b,k] = <dOut[b]^T, MHA_k> with the LayerNorm output re-formed from z on the fly
         dcomp = None
@@ -545,11 +550,12 @@ class _CsaLossFn(torch.autograd.Function):
         lib = L.lib()
         NP = geom.rows_pad
         grid = lib.csn_csa_head_grid(B, NP)   # one persistent CTA per SM: per-CTA partial sums
-        # one zero-initialised scratch vector: [n_valid | stats (3C+2) | amax | dcomp (B(K+1))]
+        # zero-initialised scratch: [n_valid | stats (3C+2)], [amax | loss partials], d comp (fp64)
         ints = torch.zeros(1 + 3 * Cn + 2, dtype=torch.int32, device=dev)
-        flts = torch.zeros(1 + B * (K + 1) + grid, dtype=torch.float32, device=dev)
+        flts = torch.zeros(1 + grid, dtype=torch.float32, device=dev)
         n_valid, stats = ints[:1], ints[1:]
-        amax, dcomp, loss_part = flts[:1], flts[1:1 + B * (K + 1)], flts[1 + B * (K + 1):]
+        amax, loss_part = flts[:1], flts[1:]
+        dcomp = torch.zeros(B * (K + 1), dtype=torch.float64, device=dev)
         dOutT = torch.empty(B * NP, 256, dtype=torch.float32, device=dev) if want_grad else None
         dW_part = torch.empty(grid, Cn, 256, dtype=torch.float32, device=dev) if want_grad else None
         dW = torch.empty(Cn, 256, dtype=torch.float32, device=dev) if want_grad else None

@@ -178,7 +178,8 @@ int csn_seg_loss(const float* feat, int64_t b_stride, int64_t ch_stride, int32_t
  *   logits = W y (csa_models.py:201);  masked cross-entropy and accuracy (csa_training.py:94-108);  per-class IoU
  *   counters (csa_training.py:110-134);  and, when dOutT != NULL, the backward of all of it:
  *   dOutT[b*rows_pad + r] = W^T dlogits (row-major padded rows, zero in pad rows / masked points: what csn_ln_bwd
- *   reads through src_idx),  *amax = max|dOutT|,  dcomp[b*n_k+k] += <dOutT[b], LayerNorm(Z[blk])>,
+ *   reads through src_idx),  *amax = max|dOutT|,  dcomp[b*n_k+k] += <dOutT[b], LayerNorm(Z[blk])> (fp64: it is
+ *   consumed through differences of nearly equal numbers),
  *   dW[c][ch] = sum dlogits[c] y[ch]  (dW_part: [csn_csa_head_grid()][n_classes][256] scratch, reduced in fixed order).
  * Zero-initialised by the caller: n_valid (1 int), stats (3*n_classes + 2 ints: #pred==c, #label==c, #both, then
  * #correct, #labels outside [0, n_classes)), amax (1 float), dcomp, loss_part.  loss_part: csn_csa_head_grid() floats
@@ -191,7 +192,7 @@ int csn_csa_head(const float* Z, const float* mean, const float* rstd, const flo
                  const int32_t* blk, const float* w, int32_t n_b, int32_t n_k, const float* W, int32_t n_classes,
                  const int64_t* labels, int64_t lab_stride, int32_t ignore_index, int32_t* n_valid, int32_t n_points,
                  int32_t chunk, int32_t chunk_pad, int32_t rows_pad, float* loss_part, float* dOutT, float* amax,
-                 float* dcomp, float* dW_part, float* dW, int32_t* stats, float* y_out, void* stream);
+                 double* dcomp, float* dW_part, float* dW, int32_t* stats, float* y_out, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * HBM-bound pieces of the CSA/SSA layer.  Row buffers use "padded" coordinates: a shape's block has
@@ -204,11 +205,12 @@ int csn_csa_head(const float* Z, const float* mean, const float* rstd, const flo
  * row-major rows, 16-bit (dst16) and optionally fp32 (dst32, may be NULL).  Source element
  * (i0,i1,c,n) is src[i0*src_s0 + i1*src_s1 + c*ch_stride + n]; destination slot is
  * dst_slot0 + i0*dst_s0 + i1*dst_s1.  dst16 may be NULL (fp32 transpose only); amax (optional, device,
- * zero-initialised) receives max |src|. */
+ * zero-initialised) receives max |src|; chunk_sum (optional, device, zero-initialised,
+ * [(slot*n_chunks + chunk)][256]) receives the channel sums over the valid points of every chunk. */
 int csn_pack_rows(const float* src, void* dst16, float* dst32, int64_t ch_stride, int32_t n0,
                   int64_t src_s0, int32_t n1, int64_t src_s1, int64_t dst_slot0, int64_t dst_s0,
                   int64_t dst_s1, int32_t n_points, int32_t chunk, int32_t chunk_pad, int32_t rows_pad,
-                  int32_t dtype, float* amax, void* stream);
+                  int32_t dtype, float* amax, float* chunk_sum, void* stream);
 
 /* P = softmax over the first cols_valid columns of each fp32 row (F.softmax(dim=-1),
  * csa_models.py:141), 16-bit, zero in pad columns and in pad rows (row % group_rows >= rows_valid). */
@@ -247,12 +249,30 @@ int csn_gemm_pair(const void* A, const void* B, void* D, int32_t M, int32_t N, i
  * the neighbour tensor) is viewed as a 2-D fp32 matrix [res*_rows][res_ld] whose row r holds one channel of one
  * shape; the [256][n_points] matrix of `block` starts at row res_row[block] of tensor res_sel[block].  Points
  * >= n_points are ignored.  The fp32 row-major copy of the inputs that csn_add_ln_fwd needs is never made.
- * block_rows and group_rows must be multiples of 32; res_ld*4 bytes a multiple of 16. */
+ * block_rows and group_rows must be multiples of 32; res_ld*4 bytes a multiple of 16.
+ * zbias (optional, fp32 [M / group_rows][256]): a row vector per row group (chunk) added to z before the statistics —
+ * the fc image of the per-chunk value mean when V is centred (csn_gemm_colbias). */
 int csn_gemm_res_ln(const csn_mat* A, const csn_mat* B, float* Z, int64_t ldz, int32_t M, int32_t K, float alpha,
                     const float* res0, int64_t res0_rows, const float* res1, int64_t res1_rows,
                     const int32_t* res_sel, const int32_t* res_row, int64_t res_ld, int32_t n_points,
                     int32_t block_rows, int32_t group_rows, int32_t rows_valid, float eps, float* mean,
-                    float* rstd, void* stream);
+                    float* rstd, const float* zbias, void* stream);
+/* csn_gemm (one batch, no split-K, row-major non-accumulating D) with a per-row-group column bias subtracted in the
+ * epilogue, in fp32 before the output is rounded:
+ *   D[m][n] = alpha * (A B^T)[m][n] - bias[(m / group_rows)*bias_ld + n - col0]   for n >= col0, m % group_rows < rows_valid.
+ * Used for the Q|K|V projection with V centred on its per-chunk key mean c = mean_chunk(X) Wv^T: softmax rows sum to
+ * one, so attn (V - c) + c == attn V (csa_models.py:142) exactly, while the 16-bit V - c, the 16-bit attention output
+ * and delta = rowsum(dO o O) lose ~10x less to rounding (post-ReLU features give V a large common mean). */
+int csn_gemm_colbias(const csn_mat* A, const csn_mat* B, const csn_out* D, int32_t M, int32_t N, int32_t K, float alpha,
+                     const float* bias, int64_t bias_ld, int32_t col0, int32_t group_rows, int32_t rows_valid,
+                     void* stream);
+/* Small fp32 contraction on CUDA cores (fixed summation order): D[m][n] (+)= alpha * sum_k opA(m,k) * opB(n,k), with
+ * opA(m,k) = transA ? A[ra(k)*lda + m] : A[ra(m)*lda + k], ra(i) = a_rows ? a_rows[i] : i (same for B).  For the
+ * few-hundred-row pieces of the layer that must stay fp32: the per-chunk value means and their fc image, and the
+ * matching correction of d fc.weight. */
+int csn_sgemm_small(const float* A, int64_t lda, const int32_t* a_rows, int32_t transA, const float* B, int64_t ldb,
+                    const int32_t* b_rows, int32_t transB, float* D, int64_t ldd, int32_t M, int32_t N, int32_t K,
+                    float alpha, int32_t accumulate, void* stream);
 /* dO = alpha * A B^T (16-bit, [M x N], N = n_head*d_head) fused with the attention backward's
  * delta[(blk*n_head + head)*rows_pad + r] = sum_c dO[m][head*d + c] * (O[m][head*d + c] + O_lo[..]/2^11 (fp16) or /2^8 (bf16)),
  * m = blk*rows_pad + r: the row-wise dot product that csn_attn_delta computes in a separate pass over dO, O and
@@ -272,12 +292,13 @@ int csn_ln_colsum(const float* Z, const float* mean, const float* rstd, const fl
  * holds one block of rows per SOURCE, e.g. the transposed output gradient of each batch item) or zero if
  * src_idx[j] < 0 — the compatibility-weighted fan-out of csa_models.py:232-238 is never materialised.
  * amax (optional, device): dY is multiplied by the power of two 2^floor(log2(128 / *amax)) on load so
- * that 16-bit gradient intermediates stay in the normal fp16 range; the caller divides the results. */
+ * that 16-bit gradient intermediates stay in the normal fp16 range; the caller divides the results.
+ * chunk_gsum (optional, device, zero-initialised, [rows / group_rows][256]): column sums of dZ per row group. */
 int csn_ln_bwd(const float* dY, const float* Z, const float* mean, const float* rstd, const float* gamma,
                float* dZ, void* dZ16, float* dgamma, float* dbeta, int64_t rows, int32_t block_rows,
                int32_t group_rows, int32_t rows_valid, int32_t dtype, const float* amax, const float* bcast,
                const int32_t* bcast_idx, float bcast_scale, const int32_t* src_idx, const float* src_w,
-               void* stream);
+               float* chunk_gsum, void* stream);
 
 /* out[b][c][n] = sum_k w[b*n_k+k] * Y[blk[b*n_k+k]][padrow(n)][c]: the compatibility-weighted sum
  * of the self- and cross-attention outputs written back channel-major (csa_models.py:232-240);

@@ -71,16 +71,18 @@ def test_gemm_res_ln_against_layer_norm():
     mean = torch.empty(M, device="cuda")
     rstd = torch.empty(M, device="cuda")
     Am, Bm = L.mat(A, L.MAJOR_K), L.mat(W, L.MAJOR_K)
+    zbias = torch.randn(n_blocks * n_chunks, 256, generator=g).cuda()   # one row vector per (block, chunk)
     rc = L.lib().csn_gemm_res_ln(C.byref(Am), C.byref(Bm), Z.data_ptr(), 256, M, K, 1.0, res0.data_ptr(), 2 * 256,
                                  res1.data_ptr(), 2 * 256, sel.data_ptr(), row.data_ptr(), n_points, chunk * n_chunks,
-                                 NP, chunk_pad, chunk, 1e-6, mean.data_ptr(), rstd.data_ptr(), L.stream_ptr())
+                                 NP, chunk_pad, chunk, 1e-6, mean.data_ptr(), rstd.data_ptr(), zbias.data_ptr(),
+                                 L.stream_ptr())
     L.check(rc, "csn_gemm_res_ln")
     src = [res0[1], res1[0, 1], res0[0]]
     fc = (A.double() @ W.double().t()).view(n_blocks, n_chunks, chunk_pad, 256)
     for b in range(n_blocks):
         for c in range(n_chunks):
             r = src[b][:, c * chunk:(c + 1) * chunk].t().double()           # (chunk, 256)
-            z = fc[b, c, :chunk] + r
+            z = fc[b, c, :chunk] + r + zbias[b * n_chunks + c].double().cpu()
             got = Z.view(n_blocks, n_chunks, chunk_pad, 256)[b, c]
             assert (got[:chunk].double() - z).abs().max() < 1e-5 * z.abs().max()
             assert got[chunk:].abs().max() == 0                               # pad rows are zero
@@ -112,3 +114,42 @@ def test_gemm_delta_against_rowsum(n_head, d_head):
     want = (dO.double() * (O.double() + O_lo.double() / 2048.0)).view(nblk, NP, n_head, d_head).sum(-1).permute(0, 2, 1)
     got = delta.view(nblk, n_head, NP).double()
     assert (got - want).abs().max() < 1e-5 * want.abs().max() + 1e-6
+
+
+def test_gemm_colbias_and_sgemm_small_through_the_c_abi():
+    """csn_gemm_colbias (projection with V centred on a per-chunk vector, subtracted in fp32 before rounding) and
+    csn_sgemm_small (fp32 contractions with row gathers / transposed operands) against fp64 PyTorch."""
+    from csn_b200 import _lib as L
+    from csn_b200 import engine as E
+    g = synth.gen(14)
+    chunk, chunk_pad, n_groups = 100, 128, 5
+    M, K, N, col0 = n_groups * chunk_pad, 256, 768, 512
+    A = (torch.randn(M, K, generator=g) * 0.5).half().cuda()
+    W = (torch.randn(N, K, generator=g) * 0.1).half().cuda()
+    bias = torch.randn(n_groups, N - col0, generator=g).cuda()
+    D = torch.empty(M, N, dtype=torch.float16, device="cuda")
+    Am, Bm, Dm = L.mat(A, L.MAJOR_K), L.mat(W, L.MAJOR_K), L.out(D, N)
+    rc = L.lib().csn_gemm_colbias(C.byref(Am), C.byref(Bm), C.byref(Dm), M, N, K, 1.0, bias.data_ptr(), N - col0, col0,
+                                  chunk_pad, chunk, L.stream_ptr())
+    L.check(rc, "csn_gemm_colbias")
+    want = (A.double() @ W.double().t()).view(n_groups, chunk_pad, N).cpu()
+    want[:, :chunk, col0:] -= bias.double().cpu()[:, None, :]
+    got = D.double().view(n_groups, chunk_pad, N).cpu()
+    assert (got - want).abs().max() < 2e-3 * want.abs().max()
+    # csn_sgemm_small: plain, gathered A rows, and the transposed / gathered "TN" form with accumulation
+    a = torch.randn(70, 300, generator=g).cuda()
+    b = torch.randn(45, 300, generator=g).cuda()
+    d = torch.empty(70, 45, device="cuda")
+    E.sgemm_small(a, b, d, 70, 45, 300, alpha=0.5)
+    assert torch.allclose(d.double(), 0.5 * a.double() @ b.double().t(), atol=1e-4)
+    idx = torch.randint(0, 70, (33,), generator=g).int().cuda()
+    d2 = torch.empty(33, 45, device="cuda")
+    E.sgemm_small(a, b, d2, 33, 45, 300, a_rows=idx)
+    assert torch.allclose(d2.double(), a[idx.long()].double() @ b.double().t(), atol=1e-4)
+    # D[m][n] += sum_k A[k][m] * B[rows[k]][n]
+    at = torch.randn(50, 70, generator=g).cuda()     # [K][M]
+    bt = torch.randn(20, 45, generator=g).cuda()     # table [*][N]
+    rows = torch.randint(0, 20, (50,), generator=g).int().cuda()
+    d3 = torch.ones(70, 45, device="cuda")
+    E.sgemm_small(at, bt, d3, 70, 45, 50, b_rows=rows, trans_a=True, trans_b=True, accumulate=True)
+    assert torch.allclose(d3.double(), 1.0 + at.double().t() @ bt[rows.long()].double(), atol=1e-4)
