@@ -14,8 +14,12 @@ module API with pinned HOST buffers (H2D of every step's features inside the tim
 back).  With torchrun (N > 1) query shapes are sharded data-parallel, one rank per GPU, parameter
 gradients all-reduced over NCCL each step (weak scaling: per-GPU batch fixed).
 
---impl reference times the CPU oracle port (oracle/csa_oracle.py, a restatement of the reference's
-PyTorch code; the reference itself is Python and cannot travel to the GPU box) on the host cores.
+--impl reference times the reference's own PyTorch implementation of the same step on the host cores: the
+unmodified MID-FC/csa_models.py when oracle/_ref holds it (copied there by __graft_entry__.build() in the build
+container; git-ignored, travels with the snapshot; kind "reference"), else the oracle port (kind "port").
+
+--config 2 (default) is the headline line (configs[1] + the configs[2] kNN sub-object); --config 4 / 5 print the
+MinkowskiNet-head and the N-sweep lines (BASELINE.json configs[3], configs[4]) with the same keys.
 """
 from __future__ import annotations
 
@@ -95,6 +99,77 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
+def host_info() -> dict:
+    """Physical cores and CPU model of the box (BASELINE.md §3 asks for both beside every CPU number)."""
+    model, cores = "unknown", set()
+    try:
+        phys = core = None
+        for line in Path("/proc/cpuinfo").read_text().splitlines():
+            if line.startswith("model name") and model == "unknown":
+                model = line.split(":", 1)[1].strip()
+            elif line.startswith("physical id"):
+                phys = line.split(":", 1)[1].strip()
+            elif line.startswith("core id"):
+                core = line.split(":", 1)[1].strip()
+            elif not line.strip():
+                if phys is not None and core is not None:
+                    cores.add((phys, core))
+                phys = core = None
+    except OSError:
+        pass
+    logical = os.cpu_count() or 1
+    return {"cpu_model": model, "physical_cores": len(cores) or logical, "logical_cpus": logical}
+
+
+def load_reference_midfc():
+    """The unmodified reference module from oracle/_ref (see __graft_entry__.build), or None."""
+    p = ROOT / "oracle" / "_ref" / "MID-FC" / "csa_models.py"
+    if not p.exists():
+        return None
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("ref_csa_models", p)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    mod.device = torch.device("cpu")
+    return mod
+
+
+def cpu_step_factory(h: int, batch: int, K: int):
+    """(step(), kind): one forward + masked CE + backward of the CSA layer on the host, through the reference's own
+    module when available (kind "reference"), else through the oracle port (kind "port").  fp32, eval mode."""
+    from csn_b200 import synth
+    sd = synth.midfc_state(1, h, N_CLASSES)
+    x, nb = synth.csa_batch(2, batch, K)
+    label = torch.randint(0, N_CLASSES, (batch, N_POINTS), generator=synth.gen(3))
+    ref = load_reference_midfc()
+    if ref is not None:
+        m = ref.get_model("csa", N_CLASSES, h, K).eval()
+        m.load_state_dict(sd)
+        params = [p for p in m.parameters()]
+
+        def step():
+            for p in params:
+                p.grad = None
+            logits = m(x, "test", nb)
+            lg = logits.squeeze(-1).permute(0, 2, 1).contiguous().view(-1, N_CLASSES)   # csa_training.py:94-108
+            lb = label.view(-1)
+            keep = torch.where(lb > 0)[0]
+            loss = torch.nn.functional.cross_entropy(lg[keep], lb[keep])
+            loss.backward()
+            return float(loss)
+        return step, "reference"
+    from oracle import csa_oracle as O
+    w = {k: v.clone().requires_grad_(v.is_floating_point()) for k, v in sd.items()}
+
+    def step():
+        for v in w.values():
+            v.grad = None
+        loss = O.masked_cross_entropy(O.forward_csa(x, nb, w, h), label)
+        loss.backward()
+        return float(loss)
+    return step, "port"
+
+
 def masked_ce(logits, label):
     """Mean CE over the points whose label is > 0 (MID-FC/csa_training.py:94-108). Written with
     ignore_index instead of the reference's boolean-mask gather: same value and gradient, but no
@@ -114,44 +189,43 @@ def peaks() -> dict:
 
 # ----------------------------------------------------------------------------------------- reference arm
 def run_reference(args) -> None:
-    """CPU oracle port on the host cores, same metric/config; rank 0 only."""
+    """The reference's CPU implementation of the same step (same batch, same steps / warm-up) on the host cores;
+    rank 0 only."""
     if int(os.environ.get("RANK", "0")) != 0:
         return
-    from csn_b200 import synth
-    from oracle import csa_oracle as O
-
-    cores = os.cpu_count() or 1
+    hi = host_info()
+    cores = hi["physical_cores"]
     torch.set_num_threads(cores)
     h = args.heads
-    sample_b = 1   # bounded sample: 1 query shape x K=3 neighbours of the B=8 batch per step
-    sd = synth.midfc_state(1, h, N_CLASSES)
-    w = {k: v.clone().requires_grad_(v.is_floating_point()) for k, v in sd.items()}
-    x, nb = synth.csa_batch(2, sample_b, CSA_K)
-    label = torch.randint(0, N_CLASSES, (sample_b, N_POINTS), generator=synth.gen(3))
-
-    def step():
-        for v in w.values():
-            v.grad = None
-        loss = O.masked_cross_entropy(O.forward_csa(x, nb, w, h), label)
-        loss.backward()
-        return float(loss)
-
-    steps = max(1, min(args.steps, 5))
-    for _ in range(max(1, min(args.warmup, 1))):
+    batch = CSA_B
+    step, kind = cpu_step_factory(h, batch, CSA_K)
+    t0 = time.perf_counter()
+    step()                                   # first warm-up step, also the probe that bounds the run
+    t1 = time.perf_counter() - t0
+    steps, warmup = args.steps, args.warmup
+    note = ""
+    if t1 * (steps + warmup) > 240.0:        # a slow host: keep the whole run within a few minutes
+        steps = max(1, min(steps, int(200.0 / t1) - 1))
+        warmup = 1
+        note = f" (host step {t1:.1f} s: bounded to {steps} timed steps)"
+    for _ in range(max(0, warmup - 1)):
         step()
     t0 = time.perf_counter()
     for _ in range(steps):
         step()
     dt = (time.perf_counter() - t0) / steps
-    value = sample_b * CSA_K / dt
-    sample = f"{sample_b} query shape x K={CSA_K} neighbours (of the B={CSA_B} batch) per step, fp32, eval, {steps} steps"
+    value = batch * CSA_K / dt
+    sample = (f"full step: {batch} query shapes x K={CSA_K} neighbours, fwd + masked CE + bwd, fp32, eval, {steps} steps, "
+              f"{warmup} warm-up{note}; {hi['cpu_model']}, {cores} physical cores ({hi['logical_cpus']} logical), "
+              f"torch {torch.__version__}")
     line = {
         "impl": "reference", "metric": "csa_shape_pairs_per_s_fwd_bwd", "value": value, "unit": "shape-pairs/s",
-        "n_gpus": args.gpus, "steps": steps, "warmup": 1, "ms_per_step": dt * 1e3, "higher_is_better": True,
+        "n_gpus": args.gpus, "steps": steps, "warmup": warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"MID-FC CSA training step B={CSA_B} K={CSA_K} h={h} N={N_POINTS} D={D} (configs[1])",
                    "heads": h},
-        "cpu_baseline": {"value": value, "unit": "shape-pairs/s", "cores": cores, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": "shape-pairs/s", "cores": cores, "kind": kind, "sample": sample,
+                         "cpu_model": hi["cpu_model"]},
         "e2e": {"value": value, "unit": "shape-pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
@@ -236,22 +310,34 @@ def run_ours(args) -> None:
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    l0 = L.launch_count()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    e0.record()
-    for i in range(args.steps):
-        train_step(i % 2)
-    e1.record()
-    barrier()
-    launches = L.launch_count() - l0
+
+    def timed_block():
+        """EXACTLY args.steps steps between two events, bracketed by barrier + synchronize; max over ranks."""
+        l0 = L.launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record()
+        for i in range(args.steps):
+            train_step(i % 2)
+        e1.record()
+        barrier()
+        t = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return t.item(), L.launch_count() - l0
+
+    # the K-step block is repeated until ~1 s has been timed (a 20-step block is 0.06 s: too short for the clock
+    # sampler and for the power state to settle); the reported figure is the MEDIAN block
+    first_ms, launches = timed_block()
+    n_blocks_timed = int(max(1, min(40, -(-1000.0 // max(first_ms, 1e-3)))))
+    if world > 1:   # every rank must run the same number of blocks
+        nb_t = torch.tensor([n_blocks_timed], device=dev)
+        dist.broadcast(nb_t, 0)
+        n_blocks_timed = int(nb_t.item())
+    block_ms = [first_ms] + [timed_block()[0] for _ in range(n_blocks_timed - 1)]
     if graphs is not None:   # replays do not pass through the C ABI: launches recorded in the graphs x replays
         launches = sum(graphs[i % 2].launches for i in range(args.steps))
-    ms = e0.elapsed_time(e1)
-    t = torch.tensor([ms], device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_step = t.item() / args.steps
+    ms_step = sorted(block_ms)[len(block_ms) // 2] / args.steps
     pairs = world * CSA_B * CSA_K
     value = pairs / (ms_step * 1e-3)
     step_flops = 3.0 * CSA_B * csa_flops_per_query(CSA_K, h)
@@ -262,44 +348,69 @@ def run_ours(args) -> None:
     L.profile_begin()
     eager_step(*batches[0])
     prof = L.profile_end()
-    n_blocks = CSA_B * (2 * CSA_K + 1)
-    attn_unit = 4.0 * N_POINTS * 500 * 256 * h * n_blocks          # Q K^T + P V of every block (algorithmic, 500-key chunks)
-    for name, mult in (("csn_attn_fwd", 1.0), ("csn_attn_bwd_dv", 1.0), ("csn_attn_bwd_dq", 1.0)):
-        if name in prof:
-            prof[name]["flops"] = attn_unit * mult                 # dV: S + P^T dO ; dS kernel: S + dP
+    # ALGORITHMIC work per entry point (N = 10 000 points, 500-key chunks — not the 10 240-row slots /
+    # 512-row chunk tiles the kernels execute; flash recompute of the scores is not counted):
+    #   S = B(K+1) projected shapes, nblk = B(2K+1) attention blocks, unit = one 2*N*C*HD contraction per block
+    S_, nblk, HD = CSA_B * (CSA_K + 1), CSA_B * (2 * CSA_K + 1), 256 * h
+    unit = 2.0 * nblk * N_POINTS * 500 * HD
+    proj = 2.0 * N_POINTS * D * HD
+    alg_flops = {
+        "csn_gemm_colbias": S_ * 3 * proj,                     # Q|K|V projection of every shape (once per step)
+        "csn_attn_fwd": 2 * unit,                              # Q K^T + P V
+        "csn_gemm_res_ln": nblk * proj,                        # out-projection (+ residual + LayerNorm statistics)
+        "csn_gemm_delta": nblk * proj,                         # dO = dZ Wo (+ delta)
+        "csn_attn_bwd_dv": unit,                               # P^T dO
+        "csn_attn_bwd_dq": unit,                               # dP = dO V^T (dS kernel)
+        "csn_gemm": nblk * proj + 2 * unit + 3 * nblk * proj,  # dWo ; dQ = dS K, dK = dS^T Q ; dWq|dWk|dWv
+    }
+    if "csn_gemm_colbias" not in prof:                         # V not centred: the projection is a plain csn_gemm
+        alg_flops["csn_gemm"] += alg_flops.pop("csn_gemm_colbias")
+    # algorithmic bytes of the HBM-bound entry points: every operand / result once at its stored width
+    rows_blk, rows_slot = nblk * N_POINTS, S_ * N_POINTS
+    alg_bytes = {
+        "csn_pack_rows": rows_slot * D * (4 + 2),                              # fp32 in, 16-bit out
+        "csn_gemm_colbias": rows_slot * (2 * D + 2 * 3 * HD),
+        "csn_gemm_res_ln": rows_blk * (2 * HD + 4 * D + 4 * D),                # O + residual in, Z out
+        "csn_ln_colsum": S_ * N_POINTS * 4 * D,
+        "csn_csa_head": rows_blk * 4 * D + CSA_B * N_POINTS * 4 * D,           # Z in (once), dOutT out
+        "csn_ln_bwd": rows_blk * (4 * D + 2 * D) + CSA_B * N_POINTS * 4 * D,   # Z + dOutT in, dZ16 out
+        "csn_gemm_delta": rows_blk * (2 * D + 2 * HD + 2 * HD),                # dZ16 + O in, dO out
+    }
     kernels = {}
     for name, d in sorted(prof.items(), key=lambda kv: -kv[1]["ms"]):
         e = {"ms": round(d["ms"], 4), "launches": d["launches"]}
-        if d["flops"] > 0:
-            e["tflops"] = round(d["flops"] / (d["ms"] * 1e-3) / 1e12, 1)
+        if name in alg_flops:
+            e["tflops"] = round(alg_flops[name] / (d["ms"] * 1e-3) / 1e12, 1)
             e["frac_of_sustained_peak"] = round(e["tflops"] / pk["tflops_sustained"], 3)
-        if d.get("bytes", 0) > 0:
-            e["algorithmic_gbs"] = round(d["bytes"] / (d["ms"] * 1e-3) / 1e9, 1)
+        if name in alg_bytes:
+            e["algorithmic_gbs"] = round(alg_bytes[name] / (d["ms"] * 1e-3) / 1e9, 1)
             e["frac_of_hbm_peak"] = round(e["algorithmic_gbs"] / pk["hbm_gbs"], 3)
         kernels[name] = e
-    dom_name, dom_d = max(prof.items(), key=lambda kv: kv[1]["ms"])
-    dom_tflops = dom_d["flops"] / (dom_d["ms"] * 1e-3) / 1e12 if dom_d["flops"] > 0 else None
-    dom_gbs = dom_d["bytes"] / (dom_d["ms"] * 1e-3) / 1e9 if dom_d.get("bytes", 0) > 0 else None
-    # DRAM bytes per launch of that entry point from the committed ncu --set full capture (profiles/)
-    traffic = None
-    tpath = ROOT / "profiles" / "r1_traffic.json"
+    # dominant kernel = the tensor-core entry point with the largest share of the step (SURVEY §8d classifies every
+    # contraction as tensor-bound); its HBM view is reported beside it
+    dom_name = max((n for n in prof if n in alg_flops), key=lambda n: prof[n]["ms"])
+    dom_d = prof[dom_name]
+    dom_tflops = alg_flops[dom_name] / (dom_d["ms"] * 1e-3) / 1e12
+    traffic_json = {}
+    tpath = ROOT / "profiles" / "r2_traffic.json"
     if tpath.exists():
-        traffic = json.loads(tpath.read_text()).get(dom_name, {}).get("dram_bytes_per_launch")
-    # the roof that binds: the larger of (algorithmic bytes / HBM peak) and (algorithmic flops / tensor peak)
-    f_t = (dom_tflops / pk["tflops_sustained"]) if dom_tflops else 0.0
-    f_h = (dom_gbs / pk["hbm_gbs"]) if dom_gbs else 0.0
-    if f_h >= f_t:
-        roof = {"bound": "hbm", "achieved": dom_gbs, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": f_h,
-                "other_roof": {"bound": "tensor", "achieved": dom_tflops, "peak": pk["tflops_sustained"], "unit": "TFLOP/s", "frac": f_t}}
-    else:
-        roof = {"bound": "tensor", "achieved": dom_tflops, "peak": pk["tflops_sustained"], "unit": "TFLOP/s", "frac": f_t,
-                "other_roof": {"bound": "hbm", "achieved": dom_gbs, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": f_h}}
-    roof.update({"kernel": dom_name + " (entry point with the largest share of the step; all its launches: sum of algorithmic work / sum of durations)",
-                 "traffic": traffic, "launches_per_step": dom_d["launches"], "ms_per_step": round(dom_d["ms"], 4),
-                 "algorithmic_bytes_per_launch": (dom_d["bytes"] / dom_d["launches"]) if dom_d.get("bytes", 0) > 0 else None,
-                 "peak_source": pk["source"] + (", copy bandwidth" if roof["bound"] == "hbm" else ", sustained bf16"),
-                 "whole_step": {"algorithmic_flops": step_flops, "achieved": achieved, "unit": "TFLOP/s",
-                                "frac": achieved / pk["tflops_sustained"]}})
+        traffic_json = json.loads(tpath.read_text())
+    compulsory = (CSA_B * (CSA_K + 1) * N_POINTS * D * 4.0      # the step's distinct input shapes, fp32
+                  + CSA_B * N_POINTS * 8.0)                      # labels
+    roof = {"bound": "tensor", "achieved": dom_tflops, "peak": pk["tflops_sustained"], "unit": "TFLOP/s",
+            "frac": dom_tflops / pk["tflops_sustained"],
+            "kernel": dom_name + " (tensor-core entry point with the largest share of the step; all its launches: "
+                                 "algorithmic FLOPs / sum of CUDA-event durations)",
+            "launches_per_step": dom_d["launches"], "ms_per_step": round(dom_d["ms"], 4),
+            "algorithmic_flops_per_launch": alg_flops[dom_name] / dom_d["launches"],
+            "traffic": traffic_json.get(dom_name, {}).get("dram_bytes_per_launch"),
+            "peak_source": pk["source"] + ", sustained bf16 (kernel timed inside a long step)",
+            "whole_step": {"algorithmic_flops": step_flops, "achieved": achieved, "unit": "TFLOP/s",
+                           "frac": achieved / pk["tflops_sustained"],
+                           "dram_bytes": traffic_json.get("whole_step", {}).get("dram_bytes"),
+                           "compulsory_bytes": compulsory,
+                           "note": "dram_bytes: sum over the step's kernels from the committed ncu --set full capture "
+                                   "(profiles/); compulsory_bytes: the step's distinct inputs once"}}
 
     # ------------------------------------------------------------------ e2e: host buffers through the module API
     hx = [torch.empty(CSA_B, D, N_POINTS, 1).pin_memory() for _ in range(2)]
@@ -499,27 +610,31 @@ def run_ours(args) -> None:
     # ------------------------------------------------------------------ CPU baseline (rank 0, N = 1 only)
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
-        from oracle import csa_oracle as O
-        cores = os.cpu_count() or 1
-        torch.set_num_threads(cores)
-        sd = synth.midfc_state(1, h, N_CLASSES)
-        w = {k: v.clone().requires_grad_(v.is_floating_point()) for k, v in sd.items()}
-        cx, cnb = synth.csa_batch(2, 1, CSA_K)
-        clab = torch.randint(0, N_CLASSES, (1, N_POINTS), generator=synth.gen(3))
-
-        def cstep():
-            for v in w.values():
-                v.grad = None
-            O.masked_cross_entropy(O.forward_csa(cx, cnb, w, h), clab).backward()
-
+        hi = host_info()
+        torch.set_num_threads(hi["physical_cores"])
+        cstep, ckind = cpu_step_factory(h, CSA_B, CSA_K)
         cstep()
         t0 = time.perf_counter()
         n = 2
         for _ in range(n):
             cstep()
         cdt = (time.perf_counter() - t0) / n
-        cpu = {"value": CSA_K / cdt, "unit": "shape-pairs/s", "cores": cores, "kind": "port",
-               "sample": f"oracle port, 1 query shape x K={CSA_K} neighbours (1/8 of the batch), fwd+bwd, fp32, {n} steps"}
+        cpu = {"value": CSA_B * CSA_K / cdt, "unit": "shape-pairs/s", "cores": hi["physical_cores"], "kind": ckind,
+               "cpu_model": hi["cpu_model"],
+               "sample": f"the full step ({CSA_B} query shapes x K={CSA_K}), fwd + masked CE + bwd, fp32, eval, 1 warm-up + {n} steps"}
+        if knn_obj is not None:
+            from oracle import csa_oracle as O
+            from csn_b200 import synth as _synth
+            nq, nc = 4, 24
+            f = _synth.clustered_shapes(5, nq + nc, n_points=N_POINTS, n_categories=4)
+            t0 = time.perf_counter()
+            O.retrieval_measure(f[:nq], f[nq:])
+            kdt = time.perf_counter() - t0
+            per_pair = kdt / (nq * nc)
+            knn_obj["cpu_baseline"] = {"value": 1.0 / (per_pair * args.knn_candidates), "unit": "shapes/s",
+                                       "cores": hi["physical_cores"], "kind": "port", "cpu_model": hi["cpu_model"],
+                                       "sample": f"oracle.retrieval_measure on {nq} queries x {nc} candidates of {N_POINTS} points "
+                                                 f"({per_pair * 1e3:.1f} ms per pair), extrapolated per pair to {args.knn_candidates} candidates"}
 
     if rank == 0:
         line = {

@@ -380,8 +380,14 @@ struct LnBwdArgs {
 template <int MINB, bool GS>
 __global__ void __launch_bounds__(256, MINB) ln_bwd_kernel(const LnBwdArgs p) {
   __shared__ float red[2][8][DM];
-  __shared__ float gsm[GS ? DM : 1];   // per-chunk column sums of dZ, accumulated with shared-memory atomics (no registers)
-  if (GS) { gsm[threadIdx.x] = 0.f; __syncthreads(); }
+  // per-chunk column sums of dZ: every warp accumulates its rows in a private SMEM row (each lane owns its 8 channels:
+  // plain read-modify-write, no atomics, no registers)
+  __shared__ __align__(16) float gsm[GS ? 8 : 1][GS ? DM : 4];
+  if (GS) {
+#pragma unroll
+    for (int w = 0; w < 8; ++w) gsm[w][threadIdx.x] = 0.f;
+    __syncthreads();
+  }
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long row0 = (long long)blockIdx.x * 64;
   const float4 g0 = __ldg(reinterpret_cast<const float4*>(p.gamma) + lane), g1 = __ldg(reinterpret_cast<const float4*>(p.gamma) + 32 + lane);
@@ -457,8 +463,12 @@ __global__ void __launch_bounds__(256, MINB) ln_bwd_kernel(const LnBwdArgs p) {
 #pragma unroll
     for (int j = 0; j < 8; ++j) o[j] = rs * (g[j] - s1 - xh[j] * s2);
     if (GS) {
-#pragma unroll
-      for (int j = 0; j < 4; ++j) { atomicAdd(&gsm[lane * 4 + j], o[j]); atomicAdd(&gsm[128 + lane * 4 + j], o[4 + j]); }
+      float4* ga = reinterpret_cast<float4*>(&gsm[warp][lane * 4]);
+      float4* gc = reinterpret_cast<float4*>(&gsm[warp][128 + lane * 4]);
+      float4 ta = *ga, tc = *gc;
+      ta.x += o[0]; ta.y += o[1]; ta.z += o[2]; ta.w += o[3];
+      tc.x += o[4]; tc.y += o[5]; tc.z += o[6]; tc.w += o[7];
+      *ga = ta; *gc = tc;
     }
     if (dz4) {
       dz4[lane] = make_float4(o[0], o[1], o[2], o[3]);
@@ -488,8 +498,12 @@ __global__ void __launch_bounds__(256, MINB) ln_bwd_kernel(const LnBwdArgs p) {
   if (p.debug & 1) return;
   atomicAdd(p.dgamma + c, s);
   atomicAdd(p.dbeta + c, t);
-  if (GS)   // the CTA's 64 rows lie inside one chunk (64 | group_rows); gsm is complete after the barrier above
-    atomicAdd(p.chunk_gsum + (row0 / p.group_rows) * DM + c, gsm[c]);
+  if (GS) {   // the CTA's 64 rows lie inside one chunk (64 | group_rows); gsm is complete after the barrier above
+    float u = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) u += gsm[w][c];
+    atomicAdd(p.chunk_gsum + (row0 / p.group_rows) * DM + c, u);
+  }
 }
 
 // ------------------------------------------------------------------------------------------ combine fwd

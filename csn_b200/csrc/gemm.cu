@@ -59,7 +59,7 @@ struct GemmArgs {
   int debug;   // CSN_GEMM_DEBUG (diagnostics only): 1 = epilogue drains TMEM but stores nothing
   // column bias per row group (csn_gemm_colbias): D[row][col] -= cbias[(row / cb_group)*cb_ld + col - cb_col0] for
   // col >= cb_col0 and row % cb_group < cb_valid (TMA-store epilogue only).  V is centred on its per-chunk key mean.
-  const float* cbias; long long cb_ld; int cb_col0, cb_group, cb_valid; float cb_inv_alpha;
+  const float* cbias; long long cb_ld; int cb_col0, cb_group, cb_valid;
   // csn_gemm_res_ln: optional per-chunk row vector added to z, zbias[(row / group_rows)*256 + col]
   const float* zbias;
 };
@@ -176,7 +176,7 @@ __device__ __forceinline__ void store_chunk(const GemmArgs& p, long long base, i
   }
 }
 
-template <int BN, bool A_MN, bool B_MN, int CL, bool LN = false, bool DL = false>
+template <int BN, bool A_MN, bool B_MN, int CL, bool LN = false, bool DL = false, bool CB = false>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
             const __grid_constant__ CUtensorMap tmD, const __grid_constant__ CUtensorMap tmR0,
@@ -343,6 +343,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           tma_load_2d(pbuf + (2 + u) * 4096, &tmR0, bar, pn0 + u * 64, prow0);
           if (p.dl_lo_inv != 0.f) tma_load_2d(pbuf + (4 + u) * 4096, &tmR1, bar, pn0 + u * 64, prow0);
         }
+      }
+      if ((CB || LN) && lane < 8) {
+        // per-row-group bias rows (column bias / zbias): pull the tile's 1 KB row into L1 while the MMAs run
+        const int prow = c.mt * GEMM_BM + q * 32;
+        const float* src = nullptr;
+        if (CB && c.nt * BN >= p.cb_col0) src = p.cbias + (long long)(prow / p.cb_group) * p.cb_ld - p.cb_col0 + c.nt * BN;
+        if (LN && p.zbias) src = p.zbias + (long long)(prow / p.group_rows) * BN;
+        if (src) asm volatile("prefetch.global.L1 [%0];" ::"l"(src + lane * 32));
       }
       mbar_wait(tfull_bar(acc), acc_ph);
       tc_fence_after();
@@ -546,22 +554,25 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         const int u0 = half * s_half * g, u1 = min(n_slabs, (half + 1) * s_half) * g;
         const float al = p.alpha;
         uint32_t ra[32], rb[32];
-        // column bias: the 32 rows of this warp lie in one row group, so the bias row is warp-uniform (broadcast loads)
-        const bool cb_rows = p.cbias != nullptr && ((row0 + lane) % p.cb_group) < p.cb_valid;
-        const float* cb_row = p.cbias ? p.cbias + (long long)(row0 / p.cb_group) * p.cb_ld - p.cb_col0 : nullptr;
-        auto emit = [&](uint32_t (&r)[32], int u) {
-          if (p.cbias && has_k && n0 + u * 32 >= p.cb_col0) {
-            const float4* b4 = reinterpret_cast<const float4*>(cb_row + n0 + u * 32);
+        // column bias (CB): the 32 rows of this warp lie in one row group, so the bias row is warp-uniform (broadcast
+        // loads that hit L1: the row's lines are prefetched before the wait for the accumulator)
+        const bool cb_rows = CB && ((row0 + lane) % p.cb_group) < p.cb_valid;
+        const float* cb_row = CB ? p.cbias + (long long)(row0 / p.cb_group) * p.cb_ld - p.cb_col0 : nullptr;
+        const bool cb_tile = CB && has_k && n0 >= p.cb_col0;
+        auto emit = [&](const uint32_t (&r)[32], int u) {
+          float bv[32];
+          if (CB) {
+            if (cb_tile) {
+              const float4* b4 = reinterpret_cast<const float4*>(cb_row + n0 + u * 32);
 #pragma unroll
-            for (int j4 = 0; j4 < 8; ++j4) {
-              const float4 bv = __ldg(b4 + j4);
-              // (alpha * acc - bias) is formed here; the stores below multiply by alpha, so pre-divide the bias
-              if (cb_rows) {
-                r[4 * j4 + 0] = __float_as_uint(__uint_as_float(r[4 * j4 + 0]) - bv.x * p.cb_inv_alpha);
-                r[4 * j4 + 1] = __float_as_uint(__uint_as_float(r[4 * j4 + 1]) - bv.y * p.cb_inv_alpha);
-                r[4 * j4 + 2] = __float_as_uint(__uint_as_float(r[4 * j4 + 2]) - bv.z * p.cb_inv_alpha);
-                r[4 * j4 + 3] = __float_as_uint(__uint_as_float(r[4 * j4 + 3]) - bv.w * p.cb_inv_alpha);
+              for (int j4 = 0; j4 < 8; ++j4) {
+                const float4 t4 = __ldg(b4 + j4);
+                bv[4 * j4] = cb_rows ? t4.x : 0.f; bv[4 * j4 + 1] = cb_rows ? t4.y : 0.f;
+                bv[4 * j4 + 2] = cb_rows ? t4.z : 0.f; bv[4 * j4 + 3] = cb_rows ? t4.w : 0.f;
               }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) bv[j] = 0.f;
             }
           }
           if (p.debug & 8) { if (r[0] == 0x7fc12345u && r[31] == 0x7fc12345u) atomicAdd(reinterpret_cast<int*>(p.D), 1); return; }   // diagnostics: TMEM loads only
@@ -578,8 +589,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
               const uint32_t a = rowaddr + (((uint32_t)ch ^ ((uint32_t)lane & 7u)) << 4);
               uint32_t w0 = 0, w1 = 0, w2 = 0, w3 = 0;
               if (has_k) {
-                w0 = __float_as_uint(__uint_as_float(r[4 * ch]) * al); w1 = __float_as_uint(__uint_as_float(r[4 * ch + 1]) * al);
-                w2 = __float_as_uint(__uint_as_float(r[4 * ch + 2]) * al); w3 = __float_as_uint(__uint_as_float(r[4 * ch + 3]) * al);
+                w0 = __float_as_uint(__uint_as_float(r[4 * ch]) * al - (CB ? bv[4 * ch] : 0.f));
+                w1 = __float_as_uint(__uint_as_float(r[4 * ch + 1]) * al - (CB ? bv[4 * ch + 1] : 0.f));
+                w2 = __float_as_uint(__uint_as_float(r[4 * ch + 2]) * al - (CB ? bv[4 * ch + 2] : 0.f));
+                w3 = __float_as_uint(__uint_as_float(r[4 * ch + 3]) * al - (CB ? bv[4 * ch + 3] : 0.f));
               }
               asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(w0), "r"(w1), "r"(w2), "r"(w3) : "memory");
             }
@@ -590,8 +603,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
               uint32_t w[4];
 #pragma unroll
               for (int j = 0; j < 4; ++j) {
-                const float x = has_k ? __uint_as_float(r[8 * ch + 2 * j]) * al : 0.f;
-                const float y = has_k ? __uint_as_float(r[8 * ch + 2 * j + 1]) * al : 0.f;
+                const float x = has_k ? __uint_as_float(r[8 * ch + 2 * j]) * al - (CB ? bv[8 * ch + 2 * j] : 0.f) : 0.f;
+                const float y = has_k ? __uint_as_float(r[8 * ch + 2 * j + 1]) * al - (CB ? bv[8 * ch + 2 * j + 1] : 0.f) : 0.f;
                 if (f16) { __half2 h = __floats2half2_rn(x, y); w[j] = *reinterpret_cast<uint32_t*>(&h); }
                 else { __nv_bfloat162 h = __floats2bfloat162_rn(x, y); w[j] = *reinterpret_cast<uint32_t*>(&h); }
               }
@@ -658,12 +671,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   }
 }
 
-template <int BN, bool A_MN, bool B_MN, int CL, bool LN = false, bool DL = false>
+template <int BN, bool A_MN, bool B_MN, int CL, bool LN = false, bool DL = false, bool CB = false>
 static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmD,
                        const GemmArgs& args, cudaStream_t stream, const CUtensorMap* tmR0 = nullptr,
                        const CUtensorMap* tmR1 = nullptr) {
   using Cfg = GemmCfg<BN>;
-  auto kern = gemm_kernel<BN, A_MN, B_MN, CL, LN, DL>;
+  auto kern = gemm_kernel<BN, A_MN, B_MN, CL, LN, DL, CB>;
   static bool configured = false;
   if (!configured) {
     CSN_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
@@ -813,7 +826,6 @@ static int gemm_impl(const csn_mat* A, const csn_mat* B, const csn_out* D, int32
                   "csn_gemm_colbias: group_rows and col0 must be multiples of 32, the bias rows 16-byte aligned");
     CSN_CHECK_ARG((long long)nb[0] * nb[1] * nb[2] * nb[3] == 1, "csn_gemm_colbias: one batch");
     g.cbias = cb->bias; g.cb_ld = cb->ld; g.cb_col0 = cb->col0; g.cb_group = cb->group_rows; g.cb_valid = cb->rows_valid;
-    g.cb_inv_alpha = 1.f / alpha;
   }
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   if (dl) {
@@ -863,6 +875,11 @@ static int gemm_impl(const csn_mat* A, const csn_mat* B, const csn_out* D, int32
     g.stages = 2; g.stg_bufs = 4; g.epi_warps = 8; g.alt_tiles = 1; g.tempty_count = 128;
     if (CL == 2) return launch_gemm<256, false, false, 2, true>(tmA, tmB, tmD, g, s, &tmR0, &tmR1);
     return launch_gemm<256, false, false, 1, true>(tmA, tmB, tmD, g, s, &tmR0, &tmR1);
+  }
+  if (cb) {
+    CSN_CHECK_ARG(BN == 256 && !a_mn && !b_mn, "csn_gemm_colbias: needs N > 128 and K-major operands");
+    if (CL == 2) return launch_gemm<256, false, false, 2, false, false, true>(tmA, tmB, tmD, g, s);
+    return launch_gemm<256, false, false, 1, false, false, true>(tmA, tmB, tmD, g, s);
   }
   if (CL == 2) {
     if (BN == 256) return dispatch_major<256, 2>(a_mn, b_mn, tmA, tmB, tmD, g, s);

@@ -82,7 +82,7 @@ def test_gemm_res_ln_against_layer_norm():
     for b in range(n_blocks):
         for c in range(n_chunks):
             r = src[b][:, c * chunk:(c + 1) * chunk].t().double()           # (chunk, 256)
-            z = fc[b, c, :chunk] + r + zbias[b * n_chunks + c].double().cpu()
+            z = fc[b, c, :chunk] + r + zbias[b * n_chunks + c].double()
             got = Z.view(n_blocks, n_chunks, chunk_pad, 256)[b, c]
             assert (got[:chunk].double() - z).abs().max() < 1e-5 * z.abs().max()
             assert got[chunk:].abs().max() == 0                               # pad rows are zero
@@ -132,7 +132,7 @@ def test_gemm_colbias_and_sgemm_small_through_the_c_abi():
     rc = L.lib().csn_gemm_colbias(C.byref(Am), C.byref(Bm), C.byref(Dm), M, N, K, 1.0, bias.data_ptr(), N - col0, col0,
                                   chunk_pad, chunk, L.stream_ptr())
     L.check(rc, "csn_gemm_colbias")
-    want = (A.double() @ W.double().t()).view(n_groups, chunk_pad, N).cpu()
+    want = (A.double() @ W.double().t()).view(n_groups, chunk_pad, N).cpu().clone()
     want[:, :chunk, col0:] -= bias.double().cpu()[:, None, :]
     got = D.double().view(n_groups, chunk_pad, N).cpu()
     assert (got - want).abs().max() < 2e-3 * want.abs().max()
@@ -153,3 +153,10 @@ def test_gemm_colbias_and_sgemm_small_through_the_c_abi():
     d3 = torch.ones(70, 45, device="cuda")
     E.sgemm_small(at, bt, d3, 70, 45, 50, b_rows=rows, trans_a=True, trans_b=True, accumulate=True)
     assert torch.allclose(d3.double(), 1.0 + at.double().t() @ bt[rows.long()].double(), atol=1e-4)
+    # few output tiles + long contraction + accumulate: split over grid.z (atomic partial sums)
+    at2 = torch.randn(700, 100, generator=g).cuda()
+    bt2 = torch.randn(30, 90, generator=g).cuda()
+    rows2 = torch.randint(0, 30, (700,), generator=g).int().cuda()
+    d4 = torch.full((100, 90), 2.0, device="cuda")
+    E.sgemm_small(at2, bt2, d4, 100, 90, 700, b_rows=rows2, trans_a=True, trans_b=True, accumulate=True)
+    assert torch.allclose(d4.double(), 2.0 + at2.double().t() @ bt2[rows2.long()].double(), atol=5e-4)
