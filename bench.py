@@ -156,7 +156,7 @@ def cpu_step_factory(h: int, batch: int, K: int):
             keep = torch.where(lb > 0)[0]
             loss = torch.nn.functional.cross_entropy(lg[keep], lb[keep])
             loss.backward()
-            return float(loss)
+            return float(loss.detach())
         return step, "reference"
     from oracle import csa_oracle as O
     w = {k: v.clone().requires_grad_(v.is_floating_point()) for k, v in sd.items()}
@@ -166,7 +166,7 @@ def cpu_step_factory(h: int, batch: int, K: int):
             v.grad = None
         loss = O.masked_cross_entropy(O.forward_csa(x, nb, w, h), label)
         loss.backward()
-        return float(loss)
+        return float(loss.detach())
     return step, "port"
 
 
@@ -251,6 +251,8 @@ def run_ours(args) -> None:
     # ------------------------------------------------------------------ CSA training step
     model = midfc.get_model("csa", N_CLASSES, h, CSA_K, precision=args.precision).to(dev).eval()
     model.load_state_dict(synth.midfc_state(1, h, N_CLASSES))
+    if args.train_mode:
+        model.train()
     params = [p for n, p in model.named_parameters() if not n.startswith("fc_1")]
     g = torch.Generator(device=dev).manual_seed(100 + rank)
     # device-resident inputs (two alternating batches > L2 each: 82 MB + 328 MB)
@@ -597,10 +599,34 @@ def run_ours(args) -> None:
         if world > 1:
             dist.all_reduce(tk, op=dist.ReduceOp.MAX)
         kms = tk.item() / k_steps
+        # e2e: the query shapes' SSA features start in pinned HOST memory (fp32 rows, as get_all_feats leaves them on the
+        # CPU, csa_models.py:282-300); per step: H2D, normalisation into a query store, scoring against the resident
+        # candidate store, exact band re-score, top-K, neighbour indices read back to the host
+        hq = [make_shapes([(lo + 7 * k_ + j) % n_c for j in range(q_per_step)]).cpu().pin_memory() for k_ in range(2)]
+
+        def knn_e2e_step(i):
+            f = hq[i % 2].to(dev, non_blocking=True)
+            qs = knn.build_store(f, exact=True)
+            sc = knn.scores_from_stores(qs, cstore)
+            knn.refine_band(sc, qs, cstore, KNN_TOPK)
+            return knn.topk_rows(sc, KNN_TOPK)[1].cpu()
+
+        knn_e2e_step(0)
+        barrier()
+        t0 = time.perf_counter()
+        for i in range(k_steps):
+            knn_e2e_step(i + 1)
+        barrier()
+        t_ke = torch.tensor([time.perf_counter() - t0], device=dev)
+        if world > 1:
+            dist.all_reduce(t_ke, op=dist.ReduceOp.MAX)
+        knn_e2e = {"value": world * q_per_step * k_steps / t_ke.item(), "unit": "shapes/s",
+                   "h2d_bytes_per_step": int(hq[0].numel() * 4), "d2h_bytes_per_step": q_per_step * KNN_TOPK * 8,
+                   "steps": k_steps}
         kflops = 2.0 * q_per_step * n_c * N_POINTS * N_POINTS * D
         kach = kflops / (kms * 1e-3) / 1e12
         knn_obj = {"metric": "knn_retrieval_shapes_per_s", "value": world * q_per_step / (kms * 1e-3), "unit": "shapes/s",
-                   "ms_per_step": kms, "steps": k_steps,
+                   "ms_per_step": kms, "steps": k_steps, "e2e": knn_e2e,
                    "config": {"workload": f"{q_per_step} query shapes/rank/step vs {n_c}-shape candidate store, N={N_POINTS}, top-{KNN_TOPK} (configs[2])",
                               "candidate_store_gb": store_rows.numel() * 4 / 1e9, "exact_band_rescore": True, "store_exchange_ms": allgather_ms},
                    "roofline": {"bound": "tensor", "kernel": "knn_score_kernel", "achieved": kach, "peak": pk["tflops_sustained"],
@@ -643,7 +669,11 @@ def run_ours(args) -> None:
             "scaling": "weak", "vs_baseline": None, "dtype": args.precision + " operands, f32 accumulate", "data": "synthetic",
             "config": {"workload": f"MID-FC CSA training step B={CSA_B} K={CSA_K} h={h} N={N_POINTS} D={D} per GPU (configs[1])",
                        "heads": h, "parallelism": f"dp{world} over query shapes", "l2": "inputs 410 MB/step > L2, two alternating batches",
-                       "dropout": "off (eval semantics, see DESIGN.md)",
+                       "dropout": "off (model.eval(): the parity-checkable semantics; training-mode dropout is in the kernels "
+                                  "and measured by --train-mode)" if not args.train_mode else "on (model.train(), p = 0.1)",
+                       "loss": "module forward + ATen conv / cross-entropy" if args.unfused_loss else
+                               "CrossShapeAt.forward_loss (fused head: weighted sum + logit conv + masked CE + IoU counters + backward)",
+                       "timed_blocks": n_blocks_timed, "block_ms": [round(b_, 3) for b_ in block_ms],
                        "launch": launch_mode},
             "clocks": clocks, "gpu_launches": int(launches),
             "e2e": {"value": e2e_value, "unit": "shape-pairs/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 4,
@@ -656,6 +686,169 @@ def run_ours(args) -> None:
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+# ----------------------------------------------------------------------------------------- configs 4 and 5
+def _simple_line(args, metric, value, ms_step, workload, flops, dtype, launches, clocks, e2e, cpu, extra_cfg=None):
+    pk = peaks()
+    ach = flops / (ms_step * 1e-3) / 1e12
+    cfg = {"workload": workload, "parallelism": "1 GPU"}
+    cfg.update(extra_cfg or {})
+    return {"metric": metric, "value": value, "unit": "shape-pairs/s", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": dtype,
+            "data": "synthetic", "config": cfg, "clocks": clocks, "gpu_launches": int(launches), "e2e": e2e,
+            "roofline": {"bound": "tensor", "kernel": "whole step (all launches)", "achieved": ach, "peak": pk["tflops_sustained"],
+                         "unit": "TFLOP/s", "frac": ach / pk["tflops_sustained"], "traffic": None,
+                         "algorithmic_flops": flops, "peak_source": pk["source"] + ", sustained bf16"},
+            "cpu_baseline": cpu}
+
+
+def _time_steps(step, steps, warmup):
+    from csn_b200 import _lib as L
+    for _ in range(warmup):
+        step()
+    torch.cuda.synchronize()
+    l0 = L.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / steps, L.launch_count() - l0
+
+
+def run_config4(args) -> None:
+    """BASELINE.json configs[3]: MinkowskiNet CSA head (hrnet.py:370-417) on a ragged batch of 8 shapes with
+    L_b ~ U[1000, 4000] voxels x 256, K = 3 neighbours, h = 4, d_head = 64, bf16, forward + backward."""
+    from csn_b200 import mink, synth
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(0)
+    B, K, h = 8, 3, 4
+    precision = "bf16" if args.precision == "fp16" and not args.keep_precision else args.precision
+    head = mink.CSAHead(256, h, precision=precision).to(dev).eval()
+    sd = synth.mink_state(2, h)
+    head.load_state_dict(sd, strict=False)
+    lens = synth.ragged_lengths(7, B * (K + 1))
+    g = synth.gen(8)
+    hq = [torch.relu(torch.randn(lens[b], 256, generator=g)).pin_memory() for b in range(B)]
+    hk = [[torch.relu(torch.randn(lens[B * (k + 1) + b], 256, generator=g)).pin_memory() for b in range(B)] for k in range(K)]
+    q = [t.to(dev).requires_grad_(True) for t in hq]
+    keys = [[t.to(dev) for t in row] for row in hk]
+
+    def step(qq=q, kk=keys):
+        for p_ in head.parameters():
+            p_.grad = None
+        out = head(qq, kk)
+        loss = sum(o.square().mean() for o in out)
+        loss.backward()
+        return loss
+
+    sampler = ClockSampler(0)
+    sampler.start()
+    ms, launches = _time_steps(step, args.steps, args.warmup)
+    clocks = sampler.stop()
+    # algorithmic FLOPs (SURVEY §8d, full attention, each shape projected once): fwd+bwd = 3 x fwd
+    HD = 256
+    shapes = lens[:B * (K + 1)]
+    pairs = [(b, b) for b in range(B * (K + 1))] + [(b, B * (k + 1) + b) for k in range(K) for b in range(B)]
+    fwd = sum(3 * 2.0 * L_ * 256 * HD for L_ in shapes) + sum(4.0 * lens[a] * lens[c] * HD + 2.0 * lens[a] * HD * 256 for a, c in pairs)
+    flops = 3.0 * fwd
+
+    def e2e_step():
+        qq = [t.to(dev, non_blocking=True).requires_grad_(True) for t in hq]
+        kk = [[t.to(dev, non_blocking=True) for t in row] for row in hk]
+        return step(qq, kk).item()
+
+    e2e_step()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    n = max(2, min(args.steps, 5))
+    for _ in range(n):
+        e2e_step()
+    torch.cuda.synchronize()
+    e2e_t = (time.perf_counter() - t0) / n
+    e2e = {"value": B * K / e2e_t, "unit": "shape-pairs/s", "h2d_bytes_per_step": int(sum(shapes) * 256 * 4), "d2h_bytes_per_step": 4,
+           "steps": n}
+    cpu = None
+    if not args.no_cpu:
+        from oracle import csa_oracle as O
+        hi = host_info()
+        torch.set_num_threads(hi["physical_cores"])
+        w = {k_: v.clone().requires_grad_(True) for k_, v in sd.items()}
+        cq = [t.clone().requires_grad_(True) for t in hq[:2]]
+        ck = [[t.clone() for t in row[:2]] for row in hk]
+
+        def cstep():
+            for v in w.values():
+                v.grad = None
+            sum(o.square().mean() for o in O.mink_csa_block(cq, ck, w, h)).backward()
+        cstep()
+        t0 = time.perf_counter()
+        cstep()
+        cdt = time.perf_counter() - t0
+        cpu = {"value": 2 * K / cdt, "unit": "shape-pairs/s", "cores": hi["physical_cores"], "kind": "port", "cpu_model": hi["cpu_model"],
+               "sample": f"oracle.mink_csa_block on 2 of the {B} query shapes (x K={K}), fwd+bwd, fp32, 1 warm-up + 1 step"}
+    line = _simple_line(args, "mink_csa_head_shape_pairs_per_s_fwd_bwd", B * K / (ms * 1e-3), ms,
+                        f"MinkowskiNet CSA head B={B} K={K} h={h} d=64, L_b~U[1000,4000] ({sum(lens[:B])} query points), one ragged batch (configs[3])",
+                        flops, precision + " operands, f32 accumulate", launches, clocks, e2e, cpu,
+                        {"l2": f"{sum(shapes) * 256 * 4 / 1e6:.0f} MB of features per step; intermediates >> L2"})
+    print(json.dumps(line), flush=True)
+
+
+def run_config5(args) -> None:
+    """BASELINE.json configs[4]: MID-FC CSA layer at N = 2k ... 40k points per shape (iters = N / 500; the reference only
+    defines N = 10 000), B = 2, K = 3, forward + masked CE + backward as one CUDA graph; one line per N."""
+    from csn_b200 import midfc, synth
+    from csn_b200.graphs import GraphedStep
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(0)
+    B, K, h = 2, 3, args.heads
+    for n in (2000, 5000, 10000, 20000, 40000):
+        m = midfc.get_model("csa", N_CLASSES, h, K, precision=args.precision).to(dev).eval()
+        m.load_state_dict(synth.midfc_state(1, h, N_CLASSES))
+        m.attention.iters = n // 500
+        x, nb = synth.csa_batch(3, B, K, n_points=n)
+        hx, hn = x.pin_memory(), nb.pin_memory()
+        x, nb = x.to(dev), nb.to(dev)
+        lab = torch.randint(0, N_CLASSES, (B, n), generator=synth.gen(4)).to(dev)
+        params = [p_ for k_, p_ in m.named_parameters() if not k_.startswith("fc_1")]
+
+        def step(x_, nb_, lab_):
+            for p_ in params:
+                p_.grad = None
+            loss = m.forward_loss(x_, "test", nb_, lab_)
+            loss.backward()
+            return loss
+
+        gs = GraphedStep(step, x, nb, lab)
+        sampler = ClockSampler(0)
+        sampler.start()
+        ms, _ = _time_steps(gs.replay, max(args.steps, 20), args.warmup)
+        clocks = sampler.stop()
+        flops = 3.0 * B * csa_flops_per_query(K, h, N=n)
+
+        def e2e_step():
+            x.copy_(hx, non_blocking=True)
+            for b in range(B):
+                nb[b, 1:].copy_(hn[b, 1:], non_blocking=True)
+            return gs.replay().item()
+
+        e2e_step()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(5):
+            e2e_step()
+        torch.cuda.synchronize()
+        e2e_t = (time.perf_counter() - t0) / 5
+        e2e = {"value": B * K / e2e_t, "unit": "shape-pairs/s", "h2d_bytes_per_step": int(hx.numel() * 4 + hn[:, 1:].numel() * 4),
+               "d2h_bytes_per_step": 4, "steps": 5}
+        line = _simple_line(args, "csa_shape_pairs_per_s_fwd_bwd", B * K / (ms * 1e-3), ms,
+                            f"MID-FC CSA training step B={B} K={K} h={h} N={n} (iters={n // 500}) (configs[4])", flops,
+                            args.precision + " operands, f32 accumulate", gs.launches, clocks, e2e, None,
+                            {"launch": "CUDA graph replay", "l2": "inputs %.0f MB/step" % ((hx.numel() + hn.numel()) * 4 / 1e6)})
+        print(json.dumps(line), flush=True)
+        del gs, m
 
 
 def main() -> None:
@@ -671,10 +864,19 @@ def main() -> None:
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--unfused-loss", action="store_true", help="module forward + ATen conv / cross-entropy instead of the fused head (CrossShapeAt.forward_loss)")
     ap.add_argument("--no-graph", action="store_true", help="launch the step kernel by kernel instead of replaying a CUDA graph")
+    ap.add_argument("--keep-precision", action="store_true", help="config 4: do not switch to bf16 (its stated dtype)")
+    ap.add_argument("--train-mode", action="store_true", help="model.train(): dropout p = 0.1 on the attention probabilities and the fc output")
+    ap.add_argument("--config", type=int, default=2, choices=[2, 3, 4, 5],
+                    help="BASELINE.json config: 2 = CSA training step (+ the config-3 kNN sub-object; default), 3 = same line, "
+                         "4 = MinkowskiNet CSA head, 5 = N sweep of the MID-FC layer")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
         run_reference(args)
+    elif args.config == 4:
+        run_config4(args)
+    elif args.config == 5:
+        run_config5(args)
     else:
         run_ours(args)
 
