@@ -146,11 +146,11 @@ _EXTRA_SIGNATURES: dict[str, list] = {
                         C.c_float, C.c_int32, C.c_void_p],
     "csn_add_ln_fwd": [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                        C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_float,
-                       C.c_int32, C.c_void_p],
+                       C.c_int32, C.c_uint32, C.c_float, C.c_void_p],
     "csn_colsum_reduce": [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_float, C.c_void_p],
     "csn_gemm_res_ln": [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_float, C.c_void_p,
                         C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32,
-                        C.c_int32, C.c_int32, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p],
+                        C.c_int32, C.c_int32, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_float, C.c_void_p],
     "csn_gemm_colbias": [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_float, C.c_void_p,
                          C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_void_p],
     "csn_sgemm_small": [C.c_void_p, C.c_int64, C.c_void_p, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p, C.c_int32,
@@ -165,7 +165,7 @@ _EXTRA_SIGNATURES: dict[str, list] = {
                       C.c_int32, C.c_int32, C.c_void_p],
     "csn_ln_bwd": [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                    C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p,
-                   C.c_void_p, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p],
+                   C.c_void_p, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_float, C.c_void_p],
     "csn_combine_fwd": [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32,
                         C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p,
                         C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p],
@@ -176,16 +176,16 @@ _EXTRA_SIGNATURES: dict[str, list] = {
                         C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p],
     "csn_attn_fwd": [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int64,
                      C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p,
-                     C.c_void_p, C.c_int32, C.c_void_p],
+                     C.c_void_p, C.c_int32, C.c_uint32, C.c_float, C.c_void_p],
     "csn_attn_delta": [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int64,
                        C.c_int32, C.c_void_p],
     "csn_attn_bwd_dv": [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int64,
                         C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_int64, C.c_int64,
-                        C.c_void_p, C.c_int32, C.c_void_p],
+                        C.c_void_p, C.c_int32, C.c_uint32, C.c_float, C.c_void_p],
     "csn_attn_bwd_dq": [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int64,
                         C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_int32,
                         C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_int32,
-                        C.c_void_p],
+                        C.c_uint32, C.c_float, C.c_void_p],
     "csn_csa_head": [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32,
                      C.c_void_p, C.c_int32, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
                      C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,

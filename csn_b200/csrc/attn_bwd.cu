@@ -11,6 +11,7 @@
 #include <cstdlib>
 #include "host_util.h"
 #include "ptx.cuh"
+#include "attn_common.cuh"
 
 namespace csn {
 
@@ -45,6 +46,9 @@ struct AttnBwdArgs {
   uint32_t idesc_s;   // M=128, N=128, K-major x K-major
   uint32_t idesc_dq;  // M=128, N=128 (DH>=128) or DH, A K-major, B MN-major
   int prefetch;       // wide dS kernel: L2-prefetch the next item's tiles
+  // dropout on the probabilities (attn_common.cuh): dP/dP_dropped = mask/(1-p); row id = stat_off + row, column = key
+  uint32_t drop_seed, drop_thresh;
+  float drop_scale;
 };
 
 template <int DH>
@@ -259,6 +263,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       const bool valid = r < it.q_valid;
       const float lse_l2 = valid ? p.lse[it.stat_off + r] * LOG2E : 0.f;
       const float dlt = valid ? p.delta[it.stat_off + r] : 0.f;
+      const uint32_t rk = drop_row_key(p.drop_seed, (uint32_t)(it.stat_off + r));
       for (int j = 0; j < nkv; ++j) {
         const int b = WITH_DQ ? 0 : (j & 1);
         mbar_wait(sdp_full(b), sdp_ph[b]);
@@ -277,10 +282,16 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 #pragma unroll
           for (int i = 0; i < 32; i += 2) {
             float d0 = 0.f, d1 = 0.f;
+            float m0 = 1.f, m1 = 1.f;   // d P_dropped / d P = mask / (1 - p)
+            if (p.drop_thresh) {
+              const uint32_t hh = drop_pair(rk, (uint32_t)(j * 128 + c + i) >> 1);
+              m0 = drop_keep_lo(hh, p.drop_thresh) ? p.drop_scale : 0.f;
+              m1 = drop_keep_hi(hh, p.drop_thresh) ? p.drop_scale : 0.f;
+            }
             if (valid && c + i < nvalid)
-              d0 = fast_exp2_b(__uint_as_float(sv[i]) * p.scale_log2 - lse_l2) * (__uint_as_float(dv[i]) - dlt) * p.scale;
+              d0 = fast_exp2_b(__uint_as_float(sv[i]) * p.scale_log2 - lse_l2) * (__uint_as_float(dv[i]) * m0 - dlt) * p.scale;
             if (valid && c + i + 1 < nvalid)
-              d1 = fast_exp2_b(__uint_as_float(sv[i + 1]) * p.scale_log2 - lse_l2) * (__uint_as_float(dv[i + 1]) - dlt) * p.scale;
+              d1 = fast_exp2_b(__uint_as_float(sv[i + 1]) * p.scale_log2 - lse_l2) * (__uint_as_float(dv[i + 1]) * m1 - dlt) * p.scale;
             pk[i >> 1] = pack_pair(d0, d1);
           }
           if (!waited) {
@@ -550,6 +561,7 @@ attn_bwd_ds_wide_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
       const bool valid = r < it.q_valid;
       const float lse_l2 = valid ? p.lse[it.stat_off + r] * LOG2E : 0.f;
       const float dlt = valid ? p.delta[it.stat_off + r] : 0.f;
+      const uint32_t rk = drop_row_key(p.drop_seed, (uint32_t)(it.stat_off + r));
       for (int j = 0; j < nst; ++j) {
         const int key0 = j * 256 + half * 128;          // first key of this warp's 128 columns
         const int nvalid = valid ? it.kv_len - key0 : 0;   // columns [0, nvalid) of the 128 are real keys
@@ -600,7 +612,13 @@ attn_bwd_ds_wide_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
             uint32_t w[16];
 #pragma unroll
             for (int i = 0; i < 32; i += 2) {
-              float x0 = fmaf(__uint_as_float(dv[i]), p.scale, nds), x1 = fmaf(__uint_as_float(dv[i + 1]), p.scale, nds);
+              float sc0 = p.scale, sc1 = p.scale;
+              if (p.drop_thresh) {   // d P_dropped / d P = mask / (1 - p)
+                const uint32_t hh = drop_pair(rk, (uint32_t)(key0 + c * 32 + i) >> 1);
+                sc0 = drop_keep_lo(hh, p.drop_thresh) ? p.scale * p.drop_scale : 0.f;
+                sc1 = drop_keep_hi(hh, p.drop_thresh) ? p.scale * p.drop_scale : 0.f;
+              }
+              float x0 = fmaf(__uint_as_float(dv[i]), sc0, nds), x1 = fmaf(__uint_as_float(dv[i + 1]), sc1, nds);
               if (!all_valid) {
                 x0 = (c * 32 + i < nvalid) ? x0 : 0.f;
                 x1 = (c * 32 + i + 1 < nvalid) ? x1 : 0.f;
@@ -789,10 +807,11 @@ int csn_attn_bwd_dq(const void* Q, const void* dO, const void* K, const void* V,
                     int64_t kv_rows, int64_t width, int64_t ldq, int64_t lddo, int64_t ldk, int64_t ldv,
                     int32_t d_head, int32_t dtype, const int32_t* items, int32_t n_items, void* dQ, int64_t lddq,
                     void* dS, int64_t ds_rows, int64_t ldds, const float* lse, const float* delta, int32_t paired,
-                    void* stream) {
+                    uint32_t drop_seed, float drop_p, void* stream) {
   using namespace csn;
   clear_error();
   CSN_CHECK_ARG(Q && dO && K && V && items && dS && lse && delta, "csn_attn_bwd_dq: null pointer");
+  CSN_CHECK_ARG(drop_p >= 0.f && drop_p < 1.f, "csn_attn_bwd_dq: dropout probability %f outside [0, 1)", (double)drop_p);
   CSN_CHECK_ARG(d_head == 256 || d_head == 64, "csn_attn_bwd_dq: d_head=%d not supported (64 or 256)", d_head);
   CSN_CHECK_ARG(dtype == CSN_F16 || dtype == CSN_BF16, "csn_attn_bwd_dq: 16-bit operands only");
   CSN_CHECK_ARG((lddq * 2) % 16 == 0 && (ldds * 2) % 16 == 0, "csn_attn_bwd_dq: output strides must be 16B multiples");
@@ -822,6 +841,9 @@ int csn_attn_bwd_dq(const void* Q, const void* dO, const void* K, const void* V,
   a.scale = 1.0f / sqrtf((float)d_head);
   a.scale_log2 = a.scale * 1.4426950408889634f;
   a.dtype = dtype;
+  a.drop_seed = drop_seed;
+  a.drop_thresh = drop_thresh16(drop_p);
+  a.drop_scale = drop_scale_of(a.drop_thresh);
   a.prefetch = 0;
   const uint32_t fmt = dtype == CSN_F16 ? 0u : 1u;
   a.idesc_s = umma_idesc_f16(fmt, 0, 0, 128);

@@ -21,7 +21,7 @@ struct AttnItem {
   int lse_off;   // lse[lse_off + r] for row r of the tile
   int flags;     // bit 0: write zeros to the tile rows >= q_valid (padded layouts); else leave them untouched
   int v_row0;    // first row of the MN-major streamed operand (V; dO in dV mode) matching kv_row0
-  int pad;
+  int key0;      // dV mode: index of the tile's first resident key inside its chunk (dropout mask column); else 0
 };
 
 struct AttnFwdArgs {
@@ -38,6 +38,10 @@ struct AttnFwdArgs {
   uint32_t idesc_qk;  // M=128, N=128, both K-major
   uint32_t idesc_pv;  // M=128, N=d, A K-major, B MN-major
   int debug;          // experiments only (CSN_ATTN_DEBUG): bit 0 = skip the softmax arithmetic, bit 1 = skip the epilogue stores
+  // dropout on the probabilities: off when drop_thresh == 0.  Row id of a query = its index into lse
+  // (lse_off + row: unique per block, head and row), column = key index inside the chunk.
+  uint32_t drop_seed, drop_thresh;
+  float drop_scale;
 };
 
 // attn_wide.cu: d_head = 256 with [128 x 256] score tiles (mode 0 forward, mode 1 dV)

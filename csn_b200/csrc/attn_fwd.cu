@@ -284,6 +284,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           const bool rvalid = r < nvalid;                       // query row exists
           const float lse_l2 = rvalid ? p.lse[it.lse_off + j * 128 + r] * LOG2E : 0.f;
           const int cvalid = rvalid ? it.q_valid : 0;           // resident key columns that exist
+          const uint32_t rk = drop_row_key(p.drop_seed, (uint32_t)(it.lse_off + j * 128 + r));
 #pragma unroll 1
           for (int c = 0; c < 128; c += 64) {
             uint32_t v0[32], v1[32];
@@ -293,10 +294,15 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             uint32_t pk[32];
 #pragma unroll
             for (int i = 0; i < 32; i += 2) {
-              const float a0 = (c + i < cvalid) ? fast_exp2(__uint_as_float(v0[i]) * p.scale_log2 - lse_l2) : 0.f;
-              const float a1 = (c + i + 1 < cvalid) ? fast_exp2(__uint_as_float(v0[i + 1]) * p.scale_log2 - lse_l2) : 0.f;
-              const float b0 = (c + 32 + i < cvalid) ? fast_exp2(__uint_as_float(v1[i]) * p.scale_log2 - lse_l2) : 0.f;
-              const float b1 = (c + 33 + i < cvalid) ? fast_exp2(__uint_as_float(v1[i + 1]) * p.scale_log2 - lse_l2) : 0.f;
+              float a0 = (c + i < cvalid) ? fast_exp2(__uint_as_float(v0[i]) * p.scale_log2 - lse_l2) : 0.f;
+              float a1 = (c + i + 1 < cvalid) ? fast_exp2(__uint_as_float(v0[i + 1]) * p.scale_log2 - lse_l2) : 0.f;
+              float b0 = (c + 32 + i < cvalid) ? fast_exp2(__uint_as_float(v1[i]) * p.scale_log2 - lse_l2) : 0.f;
+              float b1 = (c + 33 + i < cvalid) ? fast_exp2(__uint_as_float(v1[i + 1]) * p.scale_log2 - lse_l2) : 0.f;
+              if (p.drop_thresh) {   // the forward pass's dropout mask, regenerated (query row id, key column)
+                const uint32_t h0 = drop_pair(rk, (uint32_t)(it.key0 + c + i) >> 1), h1 = drop_pair(rk, (uint32_t)(it.key0 + c + 32 + i) >> 1);
+                a0 = drop_keep_lo(h0, p.drop_thresh) ? a0 * p.drop_scale : 0.f; a1 = drop_keep_hi(h0, p.drop_thresh) ? a1 * p.drop_scale : 0.f;
+                b0 = drop_keep_lo(h1, p.drop_thresh) ? b0 * p.drop_scale : 0.f; b1 = drop_keep_hi(h1, p.drop_thresh) ? b1 * p.drop_scale : 0.f;
+              }
               pk[i >> 1] = pack_pair(a0, a1);
               pk[16 + (i >> 1)] = pack_pair(b0, b1);
             }
@@ -339,6 +345,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
               }
             }
             const float moff = m_used * p.scale_log2;
+            const uint32_t rk = drop_row_key(p.drop_seed, (uint32_t)(it.lse_off + r));
             lsum = 0.f;
             float cmax = -INFINITY;
 #pragma unroll 1
@@ -354,9 +361,14 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                   const float s0 = __uint_as_float(v0[i]), s1 = __uint_as_float(v0[i + 1]);
                   const float t0 = __uint_as_float(v1[i]), t1 = __uint_as_float(v1[i + 1]);
                   cmax = fmaxf(cmax, fmaxf(fmaxf(s0, s1), fmaxf(t0, t1)));
-                  const float a0 = fast_exp2(s0 * p.scale_log2 - moff), a1 = fast_exp2(s1 * p.scale_log2 - moff);
-                  const float b0 = fast_exp2(t0 * p.scale_log2 - moff), b1 = fast_exp2(t1 * p.scale_log2 - moff);
-                  lsum += (a0 + a1) + (b0 + b1);
+                  float a0 = fast_exp2(s0 * p.scale_log2 - moff), a1 = fast_exp2(s1 * p.scale_log2 - moff);
+                  float b0 = fast_exp2(t0 * p.scale_log2 - moff), b1 = fast_exp2(t1 * p.scale_log2 - moff);
+                  lsum += (a0 + a1) + (b0 + b1);   // the softmax denominator sees every key; dropout acts on the result
+                  if (p.drop_thresh) {
+                    const uint32_t h0 = drop_pair(rk, (uint32_t)(j * 128 + c + i) >> 1), h1 = drop_pair(rk, (uint32_t)(j * 128 + c + 32 + i) >> 1);
+                    a0 = drop_keep_lo(h0, p.drop_thresh) ? a0 * p.drop_scale : 0.f; a1 = drop_keep_hi(h0, p.drop_thresh) ? a1 * p.drop_scale : 0.f;
+                    b0 = drop_keep_lo(h1, p.drop_thresh) ? b0 * p.drop_scale : 0.f; b1 = drop_keep_hi(h1, p.drop_thresh) ? b1 * p.drop_scale : 0.f;
+                  }
                   pk[i >> 1] = pack_pair(a0, a1);
                   pk[16 + (i >> 1)] = pack_pair(b0, b1);
                 }
@@ -368,9 +380,14 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                   const float t0 = (c + 32 + i < nvalid) ? __uint_as_float(v1[i]) : -INFINITY;
                   const float t1 = (c + 33 + i < nvalid) ? __uint_as_float(v1[i + 1]) : -INFINITY;
                   cmax = fmaxf(cmax, fmaxf(fmaxf(s0, s1), fmaxf(t0, t1)));
-                  const float a0 = fast_exp2(s0 * p.scale_log2 - moff), a1 = fast_exp2(s1 * p.scale_log2 - moff);
-                  const float b0 = fast_exp2(t0 * p.scale_log2 - moff), b1 = fast_exp2(t1 * p.scale_log2 - moff);
-                  lsum += (a0 + a1) + (b0 + b1);
+                  float a0 = fast_exp2(s0 * p.scale_log2 - moff), a1 = fast_exp2(s1 * p.scale_log2 - moff);
+                  float b0 = fast_exp2(t0 * p.scale_log2 - moff), b1 = fast_exp2(t1 * p.scale_log2 - moff);
+                  lsum += (a0 + a1) + (b0 + b1);   // the softmax denominator sees every key; dropout acts on the result
+                  if (p.drop_thresh) {
+                    const uint32_t h0 = drop_pair(rk, (uint32_t)(j * 128 + c + i) >> 1), h1 = drop_pair(rk, (uint32_t)(j * 128 + c + 32 + i) >> 1);
+                    a0 = drop_keep_lo(h0, p.drop_thresh) ? a0 * p.drop_scale : 0.f; a1 = drop_keep_hi(h0, p.drop_thresh) ? a1 * p.drop_scale : 0.f;
+                    b0 = drop_keep_lo(h1, p.drop_thresh) ? b0 * p.drop_scale : 0.f; b1 = drop_keep_hi(h1, p.drop_thresh) ? b1 * p.drop_scale : 0.f;
+                  }
                   pk[i >> 1] = pack_pair(a0, a1);
                   pk[16 + (i >> 1)] = pack_pair(b0, b1);
                 }
@@ -538,10 +555,11 @@ static bool items_pairable(int n_items, int d_head, int paired_flag) {
 static int attn_launch_common(int mode, const void* Q, const void* K, const void* V, int64_t q_rows, int64_t kv_rows,
                               int64_t v_rows, int64_t width, int64_t ldq, int64_t ldk, int64_t ldv, int32_t d_head, int32_t dtype,
                               const int32_t* items, int32_t n_items, void* O, int64_t o_rows, int64_t ldo, float* lse,
-                              void* Olo, int32_t paired, void* stream) {
+                              void* Olo, int32_t paired, uint32_t drop_seed, float drop_p, void* stream) {
   using namespace csn;
   clear_error();
   CSN_CHECK_ARG(Q && K && V && items && O, "csn_attn_fwd: null pointer");
+  CSN_CHECK_ARG(drop_p >= 0.f && drop_p < 1.f, "csn_attn_fwd: dropout probability %f outside [0, 1)", (double)drop_p);
   CSN_CHECK_ARG(d_head == 256 || d_head == 64, "csn_attn_fwd: d_head=%d not supported (64 or 256)", d_head);
   CSN_CHECK_ARG(dtype == CSN_F16 || dtype == CSN_BF16, "csn_attn_fwd: 16-bit operands only");
   CSN_CHECK_ARG((ldo * 2) % 16 == 0 && (reinterpret_cast<uintptr_t>(O) & 15) == 0, "csn_attn_fwd: O not 16B aligned");
@@ -564,6 +582,9 @@ static int attn_launch_common(int mode, const void* Q, const void* K, const void
   a.scale = 1.0f / sqrtf((float)d_head);
   a.scale_log2 = a.scale * 1.4426950408889634f;
   a.dtype = dtype;
+  a.drop_seed = drop_seed;
+  a.drop_thresh = drop_thresh16(drop_p);
+  a.drop_scale = drop_scale_of(a.drop_thresh);
   {
     const char* dbg = getenv("CSN_ATTN_DEBUG");
     a.debug = dbg ? atoi(dbg) : 0;
@@ -606,9 +627,9 @@ static int attn_launch_common(int mode, const void* Q, const void* K, const void
 extern "C" int csn_attn_fwd(const void* Q, const void* K, const void* V, int64_t q_rows, int64_t kv_rows,
                             int64_t width, int64_t ldq, int64_t ldk, int64_t ldv, int32_t d_head, int32_t dtype,
                             const int32_t* items, int32_t n_items, void* O, int64_t o_rows, int64_t ldo, float* lse,
-                            void* O_lo, int32_t paired, void* stream) {
+                            void* O_lo, int32_t paired, uint32_t drop_seed, float drop_p, void* stream) {
   return attn_launch_common(0, Q, K, V, q_rows, kv_rows, kv_rows, width, ldq, ldk, ldv, d_head, dtype, items, n_items,
-                            O, o_rows, ldo, lse, O_lo, paired, stream);
+                            O, o_rows, ldo, lse, O_lo, paired, drop_seed, drop_p, stream);
 }
 
 // dV = P^T dO with P^T recomputed from K, Q and the forward log-sum-exp. Same pipeline as the forward
@@ -618,7 +639,7 @@ extern "C" int csn_attn_fwd(const void* Q, const void* K, const void* V, int64_t
 extern "C" int csn_attn_bwd_dv(const void* Kres, const void* Qstr, const void* dO, int64_t k_rows, int64_t q_rows,
                                int64_t do_rows, int64_t width, int64_t ldk, int64_t ldq, int64_t lddo, int32_t d_head, int32_t dtype,
                                const int32_t* items, int32_t n_items, void* dV, int64_t dv_rows, int64_t lddv,
-                               const float* lse, int32_t paired, void* stream) {
+                               const float* lse, int32_t paired, uint32_t drop_seed, float drop_p, void* stream) {
   return attn_launch_common(1, Kres, Qstr, dO, k_rows, q_rows, do_rows, width, ldk, ldq, lddo, d_head, dtype, items,
-                            n_items, dV, dv_rows, lddv, const_cast<float*>(lse), nullptr, paired, stream);
+                            n_items, dV, dv_rows, lddv, const_cast<float*>(lse), nullptr, paired, drop_seed, drop_p, stream);
 }

@@ -349,6 +349,7 @@ attn_wide_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         } else {
           const float moff = m_used * p.scale_log2;
           const bool rvalid = (MODE == 0) ? true : (r < it.q_valid);
+          const uint32_t rk0 = drop_row_key(p.drop_seed, (uint32_t)(it.lse_off + r));   // MODE 0: the thread's query row
           const float4* lse4 = reinterpret_cast<const float4*>(xch + half * 128);
           uint32_t va[32], vb[32];
           auto conv = [&](const uint32_t (&v)[32], int c) {
@@ -361,9 +362,28 @@ attn_wide_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
               const float p1 = (rvalid && c0 + 1 < nvalid) ? fast_exp2(__uint_as_float(v[k + 1]) * p.scale_log2 - off.y) : 0.f;
               const float p2 = (rvalid && c0 + 2 < nvalid) ? fast_exp2(__uint_as_float(v[k + 2]) * p.scale_log2 - off.z) : 0.f;
               const float p3 = (rvalid && c0 + 3 < nvalid) ? fast_exp2(__uint_as_float(v[k + 3]) * p.scale_log2 - off.w) : 0.f;
-              lsum += (p0 + p1) + (p2 + p3);
-              pk[c * 16 + (k >> 1)] = pack_pair(p0, p1);
-              pk[c * 16 + (k >> 1) + 1] = pack_pair(p2, p3);
+              lsum += (p0 + p1) + (p2 + p3);   // the softmax denominator sees every key; dropout acts on the result
+              float d0 = p0, d1 = p1, d2 = p2, d3 = p3;
+              if (p.drop_thresh) {
+                if (MODE == 0) {   // row = this thread's query, columns = consecutive keys: one hash per two elements
+                  const uint32_t kc = (uint32_t)(col_first + c0);
+                  const uint32_t h0 = drop_pair(rk0, kc >> 1), h1 = drop_pair(rk0, (kc >> 1) + 1);
+                  d0 = drop_keep_lo(h0, p.drop_thresh) ? p0 * p.drop_scale : 0.f; d1 = drop_keep_hi(h0, p.drop_thresh) ? p1 * p.drop_scale : 0.f;
+                  d2 = drop_keep_lo(h1, p.drop_thresh) ? p2 * p.drop_scale : 0.f; d3 = drop_keep_hi(h1, p.drop_thresh) ? p3 * p.drop_scale : 0.f;
+                } else {           // dV: row = this thread's KEY, columns = consecutive queries: one hash per element
+                  const uint32_t kp = (uint32_t)(it.key0 + r) >> 1;
+                  const bool hi = ((it.key0 + r) & 1) != 0;
+                  const uint32_t q0 = (uint32_t)(it.lse_off + col_first + c0);
+                  const uint32_t h0 = drop_pair(drop_row_key(p.drop_seed, q0), kp), h1 = drop_pair(drop_row_key(p.drop_seed, q0 + 1), kp);
+                  const uint32_t h2 = drop_pair(drop_row_key(p.drop_seed, q0 + 2), kp), h3 = drop_pair(drop_row_key(p.drop_seed, q0 + 3), kp);
+                  d0 = (hi ? drop_keep_hi(h0, p.drop_thresh) : drop_keep_lo(h0, p.drop_thresh)) ? p0 * p.drop_scale : 0.f;
+                  d1 = (hi ? drop_keep_hi(h1, p.drop_thresh) : drop_keep_lo(h1, p.drop_thresh)) ? p1 * p.drop_scale : 0.f;
+                  d2 = (hi ? drop_keep_hi(h2, p.drop_thresh) : drop_keep_lo(h2, p.drop_thresh)) ? p2 * p.drop_scale : 0.f;
+                  d3 = (hi ? drop_keep_hi(h3, p.drop_thresh) : drop_keep_lo(h3, p.drop_thresh)) ? p3 * p.drop_scale : 0.f;
+                }
+              }
+              pk[c * 16 + (k >> 1)] = pack_pair(d0, d1);
+              pk[c * 16 + (k >> 1) + 1] = pack_pair(d2, d3);
             }
           };
           tmem_ld_32x32(s_addr, va);

@@ -246,7 +246,19 @@ struct AddLnArgs {
   int group_rows, rows_valid;  // pad structure inside a block: row % group_rows < rows_valid is valid
   float eps;
   int dtype;
+  uint32_t drop_seed, drop_thresh; float drop_scale;   // dropout on the fc output (csa_models.py:115), off when thresh == 0
 };
+
+// dropout mask of the 8 fc-output values a lane holds for one row (columns lane*4.. and 128 + lane*4..): four hashes
+__device__ __forceinline__ void drop_apply8(uint32_t seed, uint32_t thresh, float scale, uint32_t row, int lane, float4& a, float4& c) {
+  const uint32_t rk = drop_row_key(seed, row);
+  const uint32_t h0 = drop_pair(rk, 2u * lane), h1 = drop_pair(rk, 2u * lane + 1u);
+  const uint32_t h2 = drop_pair(rk, 64u + 2u * lane), h3 = drop_pair(rk, 65u + 2u * lane);
+  a.x = drop_keep_lo(h0, thresh) ? a.x * scale : 0.f; a.y = drop_keep_hi(h0, thresh) ? a.y * scale : 0.f;
+  a.z = drop_keep_lo(h1, thresh) ? a.z * scale : 0.f; a.w = drop_keep_hi(h1, thresh) ? a.w * scale : 0.f;
+  c.x = drop_keep_lo(h2, thresh) ? c.x * scale : 0.f; c.y = drop_keep_hi(h2, thresh) ? c.y * scale : 0.f;
+  c.z = drop_keep_lo(h3, thresh) ? c.z * scale : 0.f; c.w = drop_keep_hi(h3, thresh) ? c.w * scale : 0.f;
+}
 
 __global__ void __launch_bounds__(256) add_ln_fwd_kernel(const AddLnArgs p) {
   __shared__ float red[8][DM];
@@ -277,6 +289,7 @@ __global__ void __launch_bounds__(256) add_ln_fwd_kernel(const AddLnArgs p) {
     }
     const float4* r4 = reinterpret_cast<const float4*>(p.R + (rblk * p.block_rows + rin) * DM);
     float4 a = z4[lane], c = z4[32 + lane];
+    if (p.drop_thresh) drop_apply8(p.drop_seed, p.drop_thresh, p.drop_scale, (uint32_t)row, lane, a, c);
     const float4 ra = __ldg(r4 + lane), rc = __ldg(r4 + 32 + lane);
     a.x += ra.x; a.y += ra.y; a.z += ra.z; a.w += ra.w;
     c.x += rc.x; c.y += rc.y; c.z += rc.z; c.w += rc.w;
@@ -375,6 +388,9 @@ struct LnBwdArgs {
   const int* src_idx; const float* src_w;
   int debug;
   float* chunk_gsum;   // optional [rows/group_rows][256]: per-chunk column sums of dZ (atomically accumulated)
+  // dropout on the fc output: the 16-bit copy (what flows on into fc / the attention output) is masked and scaled,
+  // the fp32 dZ (gradient of the residual input) is not
+  uint32_t drop_seed, drop_thresh; float drop_scale;
 };
 
 template <int MINB, bool GS>
@@ -473,6 +489,11 @@ __global__ void __launch_bounds__(256, MINB) ln_bwd_kernel(const LnBwdArgs p) {
     if (dz4) {
       dz4[lane] = make_float4(o[0], o[1], o[2], o[3]);
       dz4[32 + lane] = make_float4(o[4], o[5], o[6], o[7]);
+    }
+    if (p.drop_thresh) {
+      float4 ma = make_float4(o[0], o[1], o[2], o[3]), mc = make_float4(o[4], o[5], o[6], o[7]);
+      drop_apply8(p.drop_seed, p.drop_thresh, p.drop_scale, (uint32_t)row, lane, ma, mc);
+      o[0] = ma.x; o[1] = ma.y; o[2] = ma.z; o[3] = ma.w; o[4] = mc.x; o[5] = mc.y; o[6] = mc.z; o[7] = mc.w;
     }
     dz16[lane] = make_uint2(pack2(o[0], o[1], p.dtype), pack2(o[2], o[3], p.dtype));
     dz16[32 + lane] = make_uint2(pack2(o[4], o[5], p.dtype), pack2(o[6], o[7], p.dtype));
@@ -752,13 +773,17 @@ int csn_softmax_bwd(const void* P, const float* dP, void* dS, int64_t rows, int3
 
 int csn_add_ln_fwd(float* Z, const float* R, const int32_t* res_block, float* Y, void* Y16, float* mean, float* rstd,
                    const float* gamma, const float* beta, float* colsum, int64_t rows, int32_t block_rows,
-                   int32_t group_rows, int32_t rows_valid, float eps, int32_t dtype, void* stream) {
+                   int32_t group_rows, int32_t rows_valid, float eps, int32_t dtype, uint32_t drop_seed, float drop_p,
+                   void* stream) {
   using namespace csn;
   clear_error();
   CSN_CHECK_ARG(Z && R && mean && rstd && gamma && beta, "csn_add_ln_fwd: null pointer");
+  CSN_CHECK_ARG(drop_p >= 0.f && drop_p < 1.f, "csn_add_ln_fwd: dropout probability outside [0, 1)");
   CSN_CHECK_ARG(block_rows % 64 == 0 && rows % 64 == 0, "csn_add_ln_fwd: rows (%lld) and block_rows (%d) must be multiples of 64", (long long)rows, block_rows);
   if (rows == 0) return 0;
-  AddLnArgs a{Z, R, res_block, Y, Y16, mean, rstd, gamma, beta, colsum, rows, block_rows, group_rows, rows_valid, eps, dtype};
+  const uint32_t dth = drop_thresh16(drop_p);
+  AddLnArgs a{Z, R, res_block, Y, Y16, mean, rstd, gamma, beta, colsum, rows, block_rows, group_rows, rows_valid, eps, dtype,
+              drop_seed, dth, drop_scale_of(dth)};
   return launch_simple(add_ln_fwd_kernel, dim3((unsigned)(rows / 64)), dim3(256), a, stream, "add_ln_fwd_kernel");
 }
 
@@ -787,7 +812,8 @@ int csn_colsum_reduce(const float* part, float* out, int32_t n_blocks, int32_t p
 int csn_ln_bwd(const float* dY, const float* Z, const float* mean, const float* rstd, const float* gamma, float* dZ,
                void* dZ16, float* dgamma, float* dbeta, int64_t rows, int32_t block_rows, int32_t group_rows,
                int32_t rows_valid, int32_t dtype, const float* amax, const float* bcast, const int32_t* bcast_idx,
-               float bcast_scale, const int32_t* src_idx, const float* src_w, float* chunk_gsum, void* stream) {
+               float bcast_scale, const int32_t* src_idx, const float* src_w, float* chunk_gsum, uint32_t drop_seed,
+               float drop_p, void* stream) {
   using namespace csn;
   clear_error();
   CSN_CHECK_ARG(dY && Z && mean && rstd && gamma && dZ16 && dgamma && dbeta, "csn_ln_bwd: null pointer");
@@ -796,7 +822,10 @@ int csn_ln_bwd(const float* dY, const float* Z, const float* mean, const float* 
   CSN_CHECK_ARG(!src_idx || src_w, "csn_ln_bwd: src_idx needs src_w");
   CSN_CHECK_ARG(rows % 64 == 0 && block_rows % 64 == 0, "csn_ln_bwd: rows and block_rows must be multiples of 64");
   if (rows == 0) return 0;
-  LnBwdArgs a{dY, Z, mean, rstd, gamma, dZ, dZ16, dgamma, dbeta, rows, group_rows, rows_valid, block_rows, dtype, amax, bcast, bcast_idx, bcast_scale, src_idx, src_w, getenv("CSN_LN_BWD_DEBUG") ? atoi(getenv("CSN_LN_BWD_DEBUG")) : 0, chunk_gsum};
+  LnBwdArgs a{dY, Z, mean, rstd, gamma, dZ, dZ16, dgamma, dbeta, rows, group_rows, rows_valid, block_rows, dtype, amax, bcast, bcast_idx, bcast_scale, src_idx, src_w, getenv("CSN_LN_BWD_DEBUG") ? atoi(getenv("CSN_LN_BWD_DEBUG")) : 0, chunk_gsum,
+              drop_seed, drop_thresh16(drop_p), drop_scale_of(drop_thresh16(drop_p))};
+  CSN_CHECK_ARG(drop_p >= 0.f && drop_p < 1.f, "csn_ln_bwd: dropout probability outside [0, 1)");
+  CSN_CHECK_ARG(!(chunk_gsum && drop_p > 0.f), "csn_ln_bwd: chunk_gsum (V centring) is not combined with dropout");
   static const int occ = getenv("CSN_LN_BWD_OCC") ? atoi(getenv("CSN_LN_BWD_OCC")) : 3;   // resident CTAs/SM (tuning knob)
   if (chunk_gsum) {
     if (occ >= 3) return launch_simple(ln_bwd_kernel<3, true>, dim3((unsigned)(rows / 64)), dim3(256), a, stream, "ln_bwd_kernel");

@@ -62,6 +62,8 @@ struct GemmArgs {
   const float* cbias; long long cb_ld; int cb_col0, cb_group, cb_valid;
   // csn_gemm_res_ln: optional per-chunk row vector added to z, zbias[(row / group_rows)*256 + col]
   const float* zbias;
+  // csn_gemm_res_ln: dropout on the projection output before the residual add (csa_models.py:115), off when thresh == 0
+  uint32_t drop_seed, drop_thresh; float drop_scale;
 };
 
 template <int BN>
@@ -467,6 +469,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         if (lane == 0) { fetch_res(0); fetch_res(1); }
         float mu = 0.f, m2 = 0.f;
         uint32_t ra[32], rb[32];
+        const uint32_t drop_rk = drop_row_key(p.drop_seed, (uint32_t)row);
         auto emit = [&](uint32_t (&r)[32], int u) {
           // residual slab of this unit
           mbar_wait(rbar0 + 8u * (u & 1), (res_ph >> (u & 1)) & 1u);
@@ -489,7 +492,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           for (int jj = 0; jj < 32; ++jj) {
             float rv;
             asm volatile("ld.shared.f32 %0, [%1];" : "=f"(rv) : "r"(rs + jj * 128 + ((((uint32_t)lane >> 2) ^ ((uint32_t)jj & 7u)) << 4)));
-            z[jj] = valid ? __uint_as_float(r[jj]) * al + rv + z[jj] : 0.f;
+            float fc = __uint_as_float(r[jj]) * al;
+            if (p.drop_thresh) {
+              const uint32_t hh = drop_pair(drop_rk, (uint32_t)(u * 32 + jj) >> 1);   // (compiler shares the hash of a pair)
+              fc = ((jj & 1) ? drop_keep_hi(hh, p.drop_thresh) : drop_keep_lo(hh, p.drop_thresh)) ? fc * p.drop_scale : 0.f;
+            }
+            z[jj] = valid ? fc + rv + z[jj] : 0.f;
             su += z[jj];
           }
           __syncwarp();
@@ -714,7 +722,7 @@ static int dispatch_major(bool a_mn, bool b_mn, const CUtensorMap& tmA, const CU
 struct LnEpilogue {
   const float* res0; long long res0_rows; const float* res1; long long res1_rows; const int* res_sel; const int* res_row;
   long long res_ld; int block_rows, group_rows, rows_valid, n_points; float eps; float* mean; float* rstd;
-  const float* zbias;
+  const float* zbias; uint32_t drop_seed; float drop_p;
 };
 
 struct ColBias {
@@ -870,6 +878,7 @@ static int gemm_impl(const csn_mat* A, const csn_mat* B, const csn_out* D, int32
     g.res_sel = ln->res_sel; g.res_row = ln->res_row;
     g.block_rows = ln->block_rows; g.group_rows = ln->group_rows; g.rows_valid = ln->rows_valid; g.n_points = ln->n_points;
     g.eps = ln->eps; g.mean = ln->mean; g.rstd = ln->rstd; g.zbias = ln->zbias;
+    g.drop_seed = ln->drop_seed; g.drop_thresh = drop_thresh16(ln->drop_p); g.drop_scale = drop_scale_of(g.drop_thresh);
     // the thread owns its whole row; two warp sets alternate tiles (one per accumulator buffer); per warp 2 output
     // + 2 residual slabs -> 128 KB of staging next to a 2-deep operand ring (K is short: the epilogue is the critical path)
     g.stages = 2; g.stg_bufs = 4; g.epi_warps = 8; g.alt_tiles = 1; g.tempty_count = 128;
@@ -899,7 +908,8 @@ extern "C" int csn_gemm_res_ln(const csn_mat* A, const csn_mat* B, float* Z, int
                                float alpha, const float* res0, int64_t res0_rows, const float* res1,
                                int64_t res1_rows, const int32_t* res_sel, const int32_t* res_row, int64_t res_ld,
                                int32_t n_points, int32_t block_rows, int32_t group_rows, int32_t rows_valid,
-                               float eps, float* mean, float* rstd, const float* zbias, void* stream) {
+                               float eps, float* mean, float* rstd, const float* zbias, uint32_t drop_seed, float drop_p,
+                               void* stream) {
   using namespace csn;
   clear_error();
   CSN_CHECK_ARG(Z && res0 && res_sel && res_row && mean && rstd, "csn_gemm_res_ln: null pointer");
@@ -908,7 +918,8 @@ extern "C" int csn_gemm_res_ln(const csn_mat* A, const csn_mat* B, float* Z, int
   memset(&D, 0, sizeof(D));
   D.ptr = Z; D.dtype = CSN_F32; D.ld = ldz;
   LnEpilogue ln{res0, res0_rows, res1 ? res1 : res0, res1 ? res1_rows : res0_rows, res_sel, res_row, res_ld,
-                block_rows, group_rows, rows_valid, n_points, eps, mean, rstd, zbias};
+                block_rows, group_rows, rows_valid, n_points, eps, mean, rstd, zbias, drop_seed, drop_p};
+  CSN_CHECK_ARG(drop_p >= 0.f && drop_p < 1.f, "csn_gemm_res_ln: dropout probability outside [0, 1)");
   CSN_CHECK_ARG(!zbias || (reinterpret_cast<uintptr_t>(zbias) & 15) == 0, "csn_gemm_res_ln: zbias must be 16-byte aligned");
   const int32_t nb[4] = {1, 1, 1, 1};
   return gemm_impl(A, B, &D, M, 256, K, nb, alpha, 1, stream, &ln);

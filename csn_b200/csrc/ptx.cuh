@@ -322,6 +322,31 @@ __device__ __forceinline__ void umma_commit2_mc(uint32_t bar, uint16_t cta_mask)
       : "memory");
 }
 
+// ----------------------------------------------------------------------------- dropout (training mode)
+// nn.Dropout on the attention probabilities (csa_models.py:141, attention.py:72) and on the fc output (:115 / :51).
+// The mask is a pure function of (seed, row id, column): every kernel that needs it — forward, dV, dS for the
+// probabilities; projection epilogue / csn_add_ln_fwd and csn_ln_bwd for the fc output — regenerates it instead of
+// storing it.  One 32-bit hash (lowbias32 finaliser) yields two 16-bit uniforms, for columns (2c, 2c+1) of a row:
+// an element is DROPPED when its uniform is < thresh16 = round(p * 65536); kept elements are scaled by
+// 65536 / (65536 - thresh16)  (= 1/(1-p) up to 2^-16).
+__host__ __device__ __forceinline__ uint32_t drop_mix(uint32_t x) {
+  x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15; x *= 0x846ca68bu; x ^= x >> 16;
+  return x;
+}
+// per-row part of the hash, hoisted out of the column loops
+__host__ __device__ __forceinline__ uint32_t drop_row_key(uint32_t seed, uint32_t row_id) {
+  return row_id * 0x9E3779B1u + seed;   // (cheap on purpose: the dV kernel forms it per element; drop_pair does the mixing)
+}
+// uniforms of columns (2*pair, 2*pair + 1): low / high half of the result
+__host__ __device__ __forceinline__ uint32_t drop_pair(uint32_t row_key, uint32_t pair) {
+  return drop_mix(row_key ^ (pair * 0x85EBCA77u + 0x165667B1u));
+}
+__host__ __device__ __forceinline__ bool drop_keep_lo(uint32_t h, uint32_t thresh16) { return (h & 0xFFFFu) >= thresh16; }
+__host__ __device__ __forceinline__ bool drop_keep_hi(uint32_t h, uint32_t thresh16) { return (h >> 16) >= thresh16; }
+// thresh16 / scale for a drop probability p (0 disables)
+static inline uint32_t drop_thresh16(float p) { return p > 0.f ? (uint32_t)(p * 65536.f + 0.5f) : 0u; }
+static inline float drop_scale_of(uint32_t thresh16) { return 65536.f / (65536.f - (float)thresh16); }
+
 // ----------------------------------------------------------------------------- misc
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

@@ -189,7 +189,7 @@ def attn_items(groups, geom: Geometry, n_head: int, d: int, device, kind: str = 
                                          j * NP + c * CP + t_ * 128, h * d, stat + t_ * 128, 1, ks * NP + c * CP, 0))
                         elif kind == "dv":   # resident tile = keys; streamed = queries (Q view) and dO (block rows)
                             rows.append((ks * NP + c * CP + t_ * 128, kvalid, qs * NP + c * CP, q_len,
-                                         j * NP + c * CP + t_ * 128, h * d, stat, 1, j * NP + c * CP, 0))
+                                         j * NP + c * CP + t_ * 128, h * d, stat, 1, j * NP + c * CP, t_ * 128))
                         else:                # dq
                             rows.append((qs * NP + c * CP + t_ * 128, valid, ks * NP + c * CP, kv_len,
                                          j * NP + c * CP + t_ * 128, h * d, stat + t_ * 128,
@@ -268,8 +268,10 @@ def attention_forward(Xh, Xf, groups, n_slots, n_blocks, w_q, w_k, w_v, w_o, gam
     HD = w_q.shape[0]
     d = HD // n_head
     ctx = AttnContext(geom, n_head, d, list(groups), n_slots, n_blocks, Xh=Xh, Xf=Xf)
-    if dropout_p > 0.0:
-        raise L.CsnError("training-mode dropout is not available in this build: call model.eval() or set dropout p = 0")
+    # training-mode dropout (csa_models.py:115,141): two independent masks (probabilities, fc output), regenerated by
+    # the kernels from (seed, row, column); stored with the context so that the backward pass uses the same ones
+    drop = (float(dropout_p), int(seed) & 0x7FFFFFFF, (int(seed) * 2654435761 + 97) & 0x7FFFFFFF) if dropout_p > 0.0 else (0.0, 0, 0)
+    ctx.extra["drop"] = drop
     ctx.Wqkv16 = torch.cat([w_q, w_k, w_v], dim=0).to(dt).contiguous()  # [3HD, 256]
     ctx.Wo16 = w_o.to(dt).contiguous()                                   # [256, HD]
     ctx.gamma = gamma
@@ -282,7 +284,9 @@ def attention_forward(Xh, Xf, groups, n_slots, n_blocks, w_q, w_k, w_v, w_o, gam
     # the 16-bit V - c, the 16-bit O' = attn (V - c) and delta = rowsum(dO o O') lose ~10x less to rounding than V / O
     # (post-ReLU features give every value row a large common mean), so no rounding residual of O is kept; c Wo^T
     # re-enters the pre-LayerNorm sum in fp32 (zbias of csn_gemm_res_ln), d fc.weight gets the matching correction.
-    center = fused and fused_ln and not ragged and chunk_sum is not None and use_centered_v()
+    center = fused and fused_ln and not ragged and chunk_sum is not None and use_centered_v() and drop[0] == 0.0
+    if drop[0] > 0.0 and not fused:
+        raise L.CsnError("training-mode dropout needs the fused attention kernels (d_head 64 or 256)")
     if center:
         cvec = torch.empty(n_slots * NC, HD, dtype=torch.float32, device=dev)
         sgemm_small(chunk_sum, w_v.detach().float().contiguous(), cvec, n_slots * NC, HD, 256, alpha=1.0 / geom.chunk)
@@ -308,7 +312,7 @@ def attention_forward(Xh, Xf, groups, n_slots, n_blocks, w_q, w_k, w_v, w_o, gam
         rc = L.lib().csn_attn_fwd(Qv.data_ptr(), Kv.data_ptr(), Vv.data_ptr(), n_slots * NP, n_slots * NP, HD,
                                   3 * HD, 3 * HD, 3 * HD, d, L.dtype_code(dt), items.data_ptr(), items.shape[0],
                                   O.data_ptr(), O.shape[0], HD, lse.data_ptr(), O_lo.data_ptr() if O_lo is not None else None,
-                                  _paired(geom), L.stream_ptr())
+                                  _paired(geom), drop[1], drop[0], L.stream_ptr())
         L.check(rc, "csn_attn_fwd")
         ctx.extra["lse"] = lse
         ctx.extra["O_lo"] = O_lo
@@ -344,7 +348,7 @@ def attention_forward(Xh, Xf, groups, n_slots, n_blocks, w_q, w_k, w_v, w_o, gam
                                      b0.data_ptr(), b0.numel() // r.ch_stride, b1.data_ptr(), b1.numel() // r.ch_stride,
                                      sel.data_ptr(), off.data_ptr(), r.ch_stride, min(r.n_points, geom.n_points),
                                      NP, CP, geom.chunk, 1e-6, ctx.mean.data_ptr(), ctx.rstd.data_ptr(),
-                                     zbias.data_ptr() if zbias is not None else None, L.stream_ptr())
+                                     zbias.data_ptr() if zbias is not None else None, drop[2], drop[0], L.stream_ptr())
         L.check(rc, "csn_gemm_res_ln")
         ctx.colsum = None
         if want_colsum:
@@ -371,7 +375,7 @@ def attention_forward(Xh, Xf, groups, n_slots, n_blocks, w_q, w_k, w_v, w_o, gam
                                 Y.data_ptr() if Y is not None else None, None,
                                 ctx.mean.data_ptr(), ctx.rstd.data_ptr(), gamma.data_ptr(), beta.data_ptr(),
                                 parts.data_ptr() if want_colsum else None, n_blocks * NP, NP, CP, geom.chunk,
-                                1e-6, L.dtype_code(dt), L.stream_ptr())
+                                1e-6, L.dtype_code(dt), drop[2], drop[0], L.stream_ptr())
     L.check(rc, "csn_add_ln_fwd")
     ctx.colsum = None
     if want_colsum:   # pooled mean over the points of every block (csa_models.py:212,219), fixed summation order
@@ -455,6 +459,7 @@ def attention_backward(ctx: AttnContext, dY: torch.Tensor, need_dx: bool, amax: 
     dgamma = torch.zeros(256, dtype=torch.float32, device=dev)
     dbeta = torch.zeros(256, dtype=torch.float32, device=dev)
     center = ctx.extra.get("center")
+    drop = ctx.extra.get("drop", (0.0, 0, 0))
     gsum = torch.zeros(nblk * NC, 256, dtype=torch.float32, device=dev) if center is not None else None
     rc = lib.csn_ln_bwd(dY.data_ptr(), ctx.Z.data_ptr(), ctx.mean.data_ptr(), ctx.rstd.data_ptr(),
                         ctx.gamma.data_ptr(), dZ.data_ptr() if dZ is not None else None, dZ16.data_ptr(),
@@ -463,7 +468,7 @@ def attention_backward(ctx: AttnContext, dY: torch.Tensor, need_dx: bool, amax: 
                         bcast_idx.data_ptr() if bcast_idx is not None else None, bcast_scale,
                         src_idx.data_ptr() if src_idx is not None else None,
                         src_w.data_ptr() if src_w is not None else None,
-                        gsum.data_ptr() if gsum is not None else None, L.stream_ptr())
+                        gsum.data_ptr() if gsum is not None else None, drop[2], drop[0], L.stream_ptr())
     L.check(rc, "csn_ln_bwd")
     split = _pick_split(2 * ((HD + 255) // 256), nblk * NP // 64)
     # --- dWo = dZ^T O  (contraction over all rows; both operands consumed MN-major)
@@ -506,7 +511,7 @@ def attention_backward(ctx: AttnContext, dY: torch.Tensor, need_dx: bool, amax: 
         it_dv = attn_items(ctx.groups, geom, h, d, dev, "dv")
         rc = lib.csn_attn_bwd_dv(Kv.data_ptr(), Qv.data_ptr(), dO.data_ptr(), S * NP, S * NP, nblk * NP, HD, 3 * HD, 3 * HD, HD,
                                  d, L.dtype_code(dt), it_dv.data_ptr(), it_dv.shape[0], dVv.data_ptr(), nblk * NP, 3 * HD,
-                                 lse.data_ptr(), _paired(geom), L.stream_ptr())
+                                 lse.data_ptr(), _paired(geom), drop[1], drop[0], L.stream_ptr())
         L.check(rc, "csn_attn_bwd_dv")
         # the dQ kernel writes the key tiles it visits; columns beyond them must read as zeros in dS^T Q
         alloc = torch.empty if (((geom.kv_len + 127) // 128) * 128 >= CP and not ragged) else torch.zeros
@@ -517,7 +522,8 @@ def attention_backward(ctx: AttnContext, dY: torch.Tensor, need_dx: bool, amax: 
         rc = lib.csn_attn_bwd_dq(Qv.data_ptr(), dO.data_ptr(), Kv.data_ptr(), Vv.data_ptr(), S * NP, nblk * NP, S * NP,
                                  HD, 3 * HD, HD, 3 * HD, 3 * HD, d, L.dtype_code(dt), it_dq.data_ptr(),
                                  it_dq.shape[0], dQv.data_ptr() if fuse_dq else None, 3 * HD, dS.data_ptr(),
-                                 dS.shape[0], CP, lse.data_ptr(), delta.data_ptr(), _paired(geom), L.stream_ptr())
+                                 dS.shape[0], CP, lse.data_ptr(), delta.data_ptr(), _paired(geom), drop[1], drop[0],
+                                 L.stream_ptr())
         L.check(rc, "csn_attn_bwd_dq")
         for g in ctx.groups:
             nb = (h, NC, g.n_in, g.n_out)
@@ -530,6 +536,8 @@ def attention_backward(ctx: AttnContext, dY: torch.Tensor, need_dx: bool, amax: 
                 L.gemm(dSk, Km, L.out(dQv[g.blk0 * NP:], 3 * HD, off=off), CP, d, CP, nb=nb)    # dQ = dS K
             L.gemm(dSt, Qm, L.out(dKv[g.blk0 * NP:], 3 * HD, off=off), CP, d, CP, nb=nb)    # dK = dS^T Q
     else:
+        if drop[0] > 0.0:
+            raise L.CsnError("training-mode dropout needs the fused attention backward (CSN_FUSED_BWD=1)")
         _attention_backward_materialised(ctx, dO, dQKV)
     # --- projection weight gradients: dW = sum_blocks dProj^T X[slot]  (contraction over points, both
     #     operands consumed MN-major; split-K sized for ~2 waves of CTAs, fp32 atomics into dWqkv)

@@ -139,7 +139,7 @@ class _MhaFn(torch.autograd.Function):
     """MultiHeadAttention.forward (csa_models.py:81-125) on channel-major inputs."""
 
     @staticmethod
-    def forward(ctx, Q, K, V, wq, wk, wv, wo, gamma, beta, n_head, dt, iters, chunk):
+    def forward(ctx, Q, K, V, wq, wk, wv, wo, gamma, beta, n_head, dt, iters, chunk, dropout_p=0.0, seed=0):
         for t, n in ((Q, "Q"), (K, "K"), (V, "V"), (wq, "w_qs.weight")):
             _require_cuda(t, n)
         B, n_src = Q.shape[0], Q.shape[2]
@@ -159,7 +159,7 @@ class _MhaFn(torch.autograd.Function):
         Xh, Xf = _pack_sources(sources, n_slots, geom, dt, Q.device)
         group = E.Group(n_in=B, n_out=1, blk0=0, q0=0, q_si=1, q_so=0, k0=k0, k_si=1, k_so=0, v0=v0, v_si=1, v_so=0)
         a = E.attention_forward(Xh, Xf, [group], n_slots, B, wq, wk, wv, wo, gamma, beta, geom, n_head,
-                                want_colsum=False)
+                                want_colsum=False, dropout_p=dropout_p, seed=seed)
         ctx.a = a
         ctx.meta = (B, k0, v0, n_slots, Q.shape[2], K.shape[2], V.shape[2])
         attn = _last_chunk_attn(a, B)
@@ -184,7 +184,8 @@ class _MhaFn(torch.autograd.Function):
                 dK = _rows_to_channel_major(dX[k0 * NP:(k0 + B) * NP], B, nk, a.geom)
             if v0 != k0:
                 dV = _rows_to_channel_major(dX[v0 * NP:(v0 + B) * NP], B, nv, a.geom)
-        return (dQ, dK, dV, g["dWq"], g["dWk"], g["dWv"], g["dWo"], g["dgamma"], g["dbeta"], None, None, None, None)
+        return (dQ, dK, dV, g["dWq"], g["dWk"], g["dWv"], g["dWo"], g["dgamma"], g["dbeta"], None, None, None, None,
+                None, None)
 
 
 class ScaledDotProductAttention(nn.Module):
@@ -247,12 +248,22 @@ class MultiHeadAttention(nn.Module):
         """Q,K,V: (B,256,N,1) channel-major. Returns (ret (B,10000,256), attn of the last chunk
         (B,h,500,500)).  `mode` is ignored, as in the reference."""
         return _MhaFn.apply(Q, K, V, *self._weights(), self.n_head, _PRECISIONS[self.precision], self.iters,
-                            self.mini_bs)
+                            self.mini_bs, *self._dropout_state())
+
+    def _dropout_state(self):
+        """(p, seed): dropout follows `module.training` (csa_models.py:56,136; the `mode` argument is ignored).
+        One p serves both nn.Dropout modules of the reference (attention probabilities and fc output: both 0.1).  The
+        seed comes from torch's CPU generator, so torch.manual_seed reproduces a run."""
+        p = float(self.dropout.p) if self.training else 0.0
+        if p <= 0.0:
+            return 0.0, 0
+        return p, int(torch.randint(0, 2 ** 31 - 1, (1,)).item())
 
     def self_attention(self, x):
         """csa_models.py:59-79 (unused by the reference): full, un-chunked self-attention."""
         n = x.shape[2]
-        return _MhaFn.apply(x, x, x, *self._weights(), self.n_head, _PRECISIONS[self.precision], 1, n)
+        return _MhaFn.apply(x, x, x, *self._weights(), self.n_head, _PRECISIONS[self.precision], 1, n,
+                            *self._dropout_state())
 
 
 # ------------------------------------------------------------------------------------------- fused segmentation loss
@@ -643,12 +654,10 @@ class CrossShapeAt(nn.Module):
         return (loss, stats) if return_stats else loss
 
     def _dropout_state(self):
-        """(p, seed) of this call: dropout follows `module.training` like the reference (csa_models.py:56,136; `mode`
-        is ignored); the seed is drawn from torch's CPU generator so torch.manual_seed reproduces a run."""
-        p = float(self.attention.dropout.p) if self.training else 0.0
-        if p <= 0.0:
-            return 0.0, 0
-        return p, int(torch.randint(0, 2 ** 31 - 1, (1,)).item())
+        """(p, seed) of this call (see MultiHeadAttention._dropout_state).  Deviation from the reference, documented in
+        DESIGN.md: SSA(x) is evaluated once per step and its single dropout mask serves both the pooled descriptor and
+        the weighted sum (the reference calls it twice with independent masks, csa_models.py:210 vs :232)."""
+        return self.attention._dropout_state() if self.training else (0.0, 0)
 
     def forward_ssa(self, x, mode):
         if self.after_fc:

@@ -37,7 +37,7 @@ class _MhaFullFn(torch.autograd.Function):
     tensor, as in every reference call hrnet.py:407,463)."""
 
     @staticmethod
-    def forward(ctx, q, k, v, wq, wk, wv, wo, gamma, beta, n_head, dt, need_attn):
+    def forward(ctx, q, k, v, wq, wk, wv, wo, gamma, beta, n_head, dt, need_attn, dropout_p=0.0, seed=0):
         for t, n in ((q, "q"), (k, "k"), (v, "v"), (wq, "w_qs.weight")):
             _require_cuda(t, n)
         B, Lq, D = q.shape
@@ -58,7 +58,7 @@ class _MhaFullFn(torch.autograd.Function):
             Xh, Xf, k0, n_slots = torch.cat([qh, kh]), torch.cat([qf, kf]), B, 2 * B
         group = E.Group(n_in=B, n_out=1, blk0=0, q0=0, q_si=1, q_so=0, k0=k0, k_si=1, k_so=0, v0=k0, v_si=1, v_so=0)
         a = E.attention_forward(Xh, Xf, [group], n_slots, B, wq, wk, wv, wo, gamma, beta, geom, n_head,
-                                want_colsum=False)
+                                want_colsum=False, dropout_p=dropout_p, seed=seed)
         ctx.a = a
         ctx.meta = (B, Lq, Lk, k0, n_pad)
         out = a.Y.view(B, n_pad, 256)[:, :Lq].contiguous()
@@ -83,7 +83,7 @@ class _MhaFullFn(torch.autograd.Function):
             dq = dX[:B, :Lq].contiguous()
             if k0 != 0:
                 dk = dX[k0:k0 + B, :Lk].contiguous()
-        return (dq, dk, None, g["dWq"], g["dWk"], g["dWv"], g["dWo"], g["dgamma"], g["dbeta"], None, None, None)
+        return (dq, dk, None, g["dWq"], g["dWk"], g["dWv"], g["dWo"], g["dgamma"], g["dbeta"], None, None, None, None, None)
 
 
 class _MhaBlocksFn(torch.autograd.Function):
@@ -95,7 +95,7 @@ class _MhaBlocksFn(torch.autograd.Function):
     is one attention block with its own (L_q, L_kv) in the kernels' work tables (E.Group.q_lens / kv_lens)."""
 
     @staticmethod
-    def forward(ctx, x_cat, wq, wk, wv, wo, gamma, beta, n_head, dt, lens, pairs):
+    def forward(ctx, x_cat, wq, wk, wv, wo, gamma, beta, n_head, dt, lens, pairs, dropout_p=0.0, seed=0):
         _require_cuda(x_cat, "x")
         _require_cuda(wq, "w_qs.weight")
         dev = x_cat.device
@@ -128,7 +128,8 @@ class _MhaBlocksFn(torch.autograd.Function):
                                   v0=pairs[j][1], v_si=dk, v_so=0,
                                   q_lens=tuple(lens[q] for q, _ in pairs[j:j + n]), kv_lens=tuple(lens[k] for _, k in pairs[j:j + n])))
             j += n
-        a = E.attention_forward(Xh, Xf, groups, S, P, wq, wk, wv, wo, gamma, beta, geom, n_head, want_colsum=False)
+        a = E.attention_forward(Xh, Xf, groups, S, P, wq, wk, wv, wo, gamma, beta, geom, n_head, want_colsum=False,
+                                dropout_p=dropout_p, seed=seed)
         out_rows = torch.cat([torch.arange(lens[qs], dtype=torch.int64) + j * n_pad for j, (qs, _) in enumerate(pairs)]).to(dev, non_blocking=True)
         ctx.a = a
         ctx.meta = (S, P, n_pad, slot_rows, out_rows)
@@ -143,7 +144,7 @@ class _MhaBlocksFn(torch.autograd.Function):
         need_dx = ctx.needs_input_grad[0]
         g = E.attention_backward(a, dY, need_dx)
         dx = g["dX"][slot_rows] if need_dx else None
-        return (dx, g["dWq"], g["dWk"], g["dWv"], g["dWo"], g["dgamma"], g["dbeta"], None, None, None, None)
+        return (dx, g["dWq"], g["dWk"], g["dWv"], g["dWo"], g["dgamma"], g["dbeta"], None, None, None, None, None, None)
 
 
 def _full_attn(a: E.AttnContext, B: int, Lq: int, Lk: int) -> torch.Tensor:
@@ -191,8 +192,15 @@ class MultiHeadAttention(nn.Module):
     def forward(self, q, k, v):
         out, attn = _MhaFullFn.apply(q, k, v, self.w_qs.weight, self.w_ks.weight, self.w_vs.weight, self.fc.weight,
                                      self.norm.weight, self.norm.bias, self.n_head, _PRECISIONS[self.precision],
-                                     self.return_attn)
+                                     self.return_attn, *self._dropout_state())
         return out, (attn if self.return_attn else None)
+
+    def _dropout_state(self):
+        """(p, seed): dropout follows `module.training` (attention.py:28,51,67,72; both nn.Dropout modules use 0.1)."""
+        p = float(self.dropout.p) if self.training else 0.0
+        if p <= 0.0:
+            return 0.0, 0
+        return p, int(torch.randint(0, 2 ** 31 - 1, (1,)).item())
 
     def forward_blocks(self, shapes, pairs):
         """Batched form of `forward` for ragged inputs: shapes = list of (L_s, 256) feature tensors, pairs = list
@@ -202,7 +210,7 @@ class MultiHeadAttention(nn.Module):
         lens = tuple(int(t.shape[0]) for t in shapes)
         y = _MhaBlocksFn.apply(torch.cat(list(shapes), dim=0), self.w_qs.weight, self.w_ks.weight, self.w_vs.weight,
                                self.fc.weight, self.norm.weight, self.norm.bias, self.n_head, _PRECISIONS[self.precision],
-                               lens, tuple((int(a), int(b)) for a, b in pairs))
+                               lens, tuple((int(a), int(b)) for a, b in pairs), *self._dropout_state())
         return list(torch.split(y, [lens[q] for q, _ in pairs], dim=0))
 
 

@@ -132,10 +132,17 @@ int csn_topk_rows(const float* scores, int64_t ld, int32_t n_rows, int32_t n_col
  * paired != 0 asserts that items 2m and 2m+1 stream exactly the same K/V tiles (same kv_row0, kv_len,
  * col0, v_row0): they then run as a 2-CTA cluster whose TMA loads are multicast to both CTAs.
  * ------------------------------------------------------------------------------------------- */
+/* Training-mode dropout (nn.Dropout on the probabilities, csa_models.py:141 / attention.py:72; on the fc output,
+ * csa_models.py:115 / attention.py:51): drop_p in [0, 1), 0 = off.  The mask is a pure function of (drop_seed, row id,
+ * column) — csrc/attn_common.cuh — regenerated by every kernel that needs it, never stored; pass the same seed and p to
+ * csn_attn_fwd, csn_attn_bwd_dv and csn_attn_bwd_dq of one step (row id = index into lse, column = key index inside
+ * the chunk; the dV work items carry the tile's first key in their last field), and to csn_gemm_res_ln /
+ * csn_add_ln_fwd and csn_ln_bwd for the fc output (row id = row of Z, column = channel).  lse is always the
+ * log-sum-exp of the UNdropped scores. */
 int csn_attn_fwd(const void* Q, const void* K, const void* V, int64_t q_rows, int64_t kv_rows, int64_t width,
                  int64_t ldq, int64_t ldk, int64_t ldv, int32_t d_head, int32_t dtype, const int32_t* items,
                  int32_t n_items, void* O, int64_t o_rows, int64_t ldo, float* lse, void* O_lo, int32_t paired,
-                 void* stream);
+                 uint32_t drop_seed, float drop_p, void* stream);
 
 /* Backward of the attention core (autograd of csa_models.py:139-142), three pieces:
  *  csn_attn_delta : delta[(blk*h+head)*rows_pad + r] = sum_c dO[blk*rows_pad+r][head*d+c] * (O + O_lo/2^11)[..]
@@ -153,12 +160,12 @@ int csn_attn_delta(const void* dO, const void* O, const void* O_lo, float* delta
 int csn_attn_bwd_dv(const void* Kres, const void* Qstr, const void* dO, int64_t k_rows, int64_t q_rows,
                     int64_t do_rows, int64_t width, int64_t ldk, int64_t ldq, int64_t lddo, int32_t d_head, int32_t dtype,
                     const int32_t* items, int32_t n_items, void* dV, int64_t dv_rows, int64_t lddv, const float* lse,
-                    int32_t paired, void* stream);
+                    int32_t paired, uint32_t drop_seed, float drop_p, void* stream);
 int csn_attn_bwd_dq(const void* Q, const void* dO, const void* K, const void* V, int64_t q_rows, int64_t do_rows,
                     int64_t kv_rows, int64_t width, int64_t ldq, int64_t lddo, int64_t ldk, int64_t ldv,
                     int32_t d_head, int32_t dtype, const int32_t* items, int32_t n_items, void* dQ, int64_t lddq,
                     void* dS, int64_t ds_rows, int64_t ldds, const float* lse, const float* delta, int32_t paired,
-                    void* stream);
+                    uint32_t drop_seed, float drop_p, void* stream);
 
 /* Fused segmentation epilogue: logits = W f (the bias-free 1x1 `logit` conv, csa_models.py:201), masked
  * cross-entropy (csa_training.py:94-108: mean over the points whose label != ignore_index) and its backward in one
@@ -229,7 +236,7 @@ int csn_softmax_bwd(const void* P, const float* dP, void* dS, int64_t rows, int3
 int csn_add_ln_fwd(float* Z, const float* R, const int32_t* res_block, float* Y, void* Y16, float* mean,
                    float* rstd, const float* gamma, const float* beta, float* colsum, int64_t rows,
                    int32_t block_rows, int32_t group_rows, int32_t rows_valid, float eps, int32_t dtype,
-                   void* stream);
+                   uint32_t drop_seed, float drop_p, void* stream);
 int csn_colsum_reduce(const float* part, float* out, int32_t n_blocks, int32_t parts, float scale, void* stream);
 
 /* The same contraction for plain problems (K-major A [M x K] and B [N x K], one batch, no split-K) on CTA PAIRS:
@@ -256,7 +263,7 @@ int csn_gemm_res_ln(const csn_mat* A, const csn_mat* B, float* Z, int64_t ldz, i
                     const float* res0, int64_t res0_rows, const float* res1, int64_t res1_rows,
                     const int32_t* res_sel, const int32_t* res_row, int64_t res_ld, int32_t n_points,
                     int32_t block_rows, int32_t group_rows, int32_t rows_valid, float eps, float* mean,
-                    float* rstd, const float* zbias, void* stream);
+                    float* rstd, const float* zbias, uint32_t drop_seed, float drop_p, void* stream);
 /* csn_gemm (one batch, no split-K, row-major non-accumulating D) with a per-row-group column bias subtracted in the
  * epilogue, in fp32 before the output is rounded:
  *   D[m][n] = alpha * (A B^T)[m][n] - bias[(m / group_rows)*bias_ld + n - col0]   for n >= col0, m % group_rows < rows_valid.
@@ -298,7 +305,7 @@ int csn_ln_bwd(const float* dY, const float* Z, const float* mean, const float* 
                float* dZ, void* dZ16, float* dgamma, float* dbeta, int64_t rows, int32_t block_rows,
                int32_t group_rows, int32_t rows_valid, int32_t dtype, const float* amax, const float* bcast,
                const int32_t* bcast_idx, float bcast_scale, const int32_t* src_idx, const float* src_w,
-               float* chunk_gsum, void* stream);
+               float* chunk_gsum, uint32_t drop_seed, float drop_p, void* stream);
 
 /* out[b][c][n] = sum_k w[b*n_k+k] * Y[blk[b*n_k+k]][padrow(n)][c]: the compatibility-weighted sum
  * of the self- and cross-attention outputs written back channel-major (csa_models.py:232-240);

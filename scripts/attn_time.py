@@ -19,7 +19,7 @@ items = E.attn_items(groups, geom, h, d, dev)
 def run():
     rc = L.lib().csn_attn_fwd(QKV[:, :HD].data_ptr(), QKV[:, HD:2*HD].data_ptr(), QKV[:, 2*HD:].data_ptr(), S * NP, S * NP, HD,
                               3 * HD, 3 * HD, 3 * HD, d, L.CSN_F16, items.data_ptr(), items.shape[0], O.data_ptr(), O.shape[0], HD,
-                              lse.data_ptr(), None, int(os.environ.get("PAIRED", "1")), L.stream_ptr())
+                              lse.data_ptr(), None, int(os.environ.get("PAIRED", "1")), 0, 0.0, L.stream_ptr())
     L.check(rc, "attn")
 for _ in range(3): run()
 torch.cuda.synchronize()

@@ -74,7 +74,7 @@ def test_gemm_res_ln_against_layer_norm():
     zbias = torch.randn(n_blocks * n_chunks, 256, generator=g).cuda()   # one row vector per (block, chunk)
     rc = L.lib().csn_gemm_res_ln(C.byref(Am), C.byref(Bm), Z.data_ptr(), 256, M, K, 1.0, res0.data_ptr(), 2 * 256,
                                  res1.data_ptr(), 2 * 256, sel.data_ptr(), row.data_ptr(), n_points, chunk * n_chunks,
-                                 NP, chunk_pad, chunk, 1e-6, mean.data_ptr(), rstd.data_ptr(), zbias.data_ptr(),
+                                 NP, chunk_pad, chunk, 1e-6, mean.data_ptr(), rstd.data_ptr(), zbias.data_ptr(), 0, 0.0,
                                  L.stream_ptr())
     L.check(rc, "csn_gemm_res_ln")
     src = [res0[1], res1[0, 1], res0[0]]
