@@ -472,16 +472,24 @@ def run_ours(args) -> None:
     # ------------------------------------------------------------------ e2e with the GPU-resident feature store
     # (SURVEY §8f-1): the per-point features are constants of the CSA phase, so only shape ids and labels cross PCIe;
     # the step's inputs are gathered by id on the device into the static input sets of the graphs.
-    from csn_b200.store import FeatureStore
-    n_store = 96
-    store = FeatureStore(n_store, N_POINTS, D, device=dev)
+    from csn_b200.store import ShardedFeatureStore
+    per_rank_store = 96
+    n_store = per_rank_store * world
+    store = ShardedFeatureStore(n_store, N_POINTS, D, device=dev)      # rank r holds shapes [96 r, 96 (r+1)) of the collection
     gs_ = torch.Generator(device=dev).manual_seed(7 + rank)
-    for s0 in range(0, n_store, 16):
+    for s0 in range(0, store.hi - store.lo, 16):
         store.feats[s0:s0 + 16] = torch.relu(torch.randn(16, D, N_POINTS, device=dev, generator=gs_))
-    gh = torch.Generator().manual_seed(11 + rank)
-    id_steps = [(torch.randint(0, n_store, (CSA_B,), generator=gh), torch.randint(0, n_store, (CSA_B, CSA_K), generator=gh))
-                for _ in range(8)]
+    # ids of EVERY rank's batch, derived from one shared seed (the replicated kNN graph + a DistributedSampler-style
+    # permutation): queries are the rank's own shapes, neighbours are arbitrary shapes of the collection, so at N ranks
+    # a fraction (N-1)/N of the neighbour blocks is fetched from its owner over NVLink
+    gh = torch.Generator().manual_seed(11)
+    id_steps = []
+    for _ in range(8):
+        ids_all = [(torch.randint(0, per_rank_store, (CSA_B,), generator=gh) + r * per_rank_store).tolist() for r in range(world)]
+        nbr_all = [torch.randint(0, n_store, (CSA_B, CSA_K), generator=gh).tolist() for r in range(world)]
+        id_steps.append((ids_all, nbr_all))
     hl_s = [torch.randint(0, N_CLASSES, (CSA_B, N_POINTS), generator=gh).pin_memory() for _ in range(2)]
+    remote_blocks = []
 
     consumed_s = [None, None]
 
@@ -493,6 +501,7 @@ def run_ours(args) -> None:
             if consumed_s[k] is not None:
                 copy_stream.wait_event(consumed_s[k])
             store.batch(ids, nbr, out=(x, nb))
+            remote_blocks.append(store.last_remote_blocks)
             lab.copy_(hl_s[k], non_blocking=True)
             ev = torch.cuda.Event()
             ev.record(copy_stream)
@@ -526,8 +535,10 @@ def run_ours(args) -> None:
     e2e_store = {"value": pairs * store_steps / t_st.item(), "unit": "shape-pairs/s",
                  "h2d_bytes_per_step": int(hl_s[0].numel() * 8 + CSA_B * (CSA_K + 1) * 8), "d2h_bytes_per_step": 4,
                  "steps": store_steps,
-                 "note": "features of the collection resident in HBM (csn_b200.store.FeatureStore), gathered by shape id on "
-                         "the device; only ids and labels cross PCIe"}
+                 "nvlink_bytes_per_step_per_rank": int(sum(remote_blocks[-store_steps:]) / max(1, store_steps) * D * N_POINTS * 4),
+                 "note": "collection sharded by shape id over the ranks' HBM (csn_b200.store.ShardedFeatureStore): queries are "
+                         "local, neighbour blocks are fetched from their owners by one batched NCCL point-to-point exchange "
+                         "per step on a side stream; only ids and labels cross PCIe"}
     del store
     clocks = sampler.stop() if rank == 0 else None
     del batches, hx, hn, hl

@@ -139,3 +139,39 @@ def test_knn_driver_reads_the_reference_feature_layout(tmp_path):
     D.save_graphs(str(tmp_path / "graphs"), g, g[::-1].copy())
     assert np.array_equal(np.load(tmp_path / "graphs" / "train.npy"), g)
     assert np.array_equal(np.load(tmp_path / "graphs" / "test.npy"), g[::-1])
+
+
+def _store_worker(rank, world, port, out):
+    import torch.distributed as dist
+    from csn_b200.store import ShardedFeatureStore
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        S, D, N, B, K = 7, 4, 6, 2, 3
+        feats = torch.arange(S * D * N, dtype=torch.float32).view(S, D, N)     # the whole collection (for checking)
+        store = ShardedFeatureStore(S, n_points=N, d_model=D, device="cpu")
+        store.put_local(list(range(store.lo, store.hi)), feats[store.lo:store.hi])
+        # rank 0 owns shapes 0..3, rank 1 owns 4..6; neighbours mix local and remote owners, with repeats
+        all_ids = [[0, 3], [4, 6]]
+        all_nbr = [[[1, 5, 5], [6, 2, 4]], [[0, 5, 3], [3, 3, 6]]]
+        x, xn = store.batch(all_ids, all_nbr)
+        ok = torch.equal(x[..., 0], feats[all_ids[rank]])
+        for b in range(B):
+            for k in range(K):
+                ok = ok and torch.equal(xn[b, k + 1, ..., 0], feats[all_nbr[rank][b][k]])
+        send, recv = store.plan(all_nbr)
+        torch.save({"ok": ok, "remote": store.last_remote_blocks, "send": send, "recv": recv}, f"{out}.{rank}")
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sharded_feature_store_fetches_neighbours_from_their_owners(tmp_path):
+    """csn_b200.store.ShardedFeatureStore over 2 gloo ranks: queries are local, neighbours come from the owning rank,
+    every remote block crosses once per step (deduplicated), nothing is sent that the peer already holds."""
+    import torch.multiprocessing as mp
+    out = str(tmp_path / "store")
+    mp.spawn(_store_worker, args=(2, _free_port(), out), nprocs=2, join=True)
+    r0, r1 = torch.load(out + ".0"), torch.load(out + ".1")
+    assert r0["ok"] and r1["ok"]
+    assert r0["remote"] == 3 and r0["recv"][1] == [5, 6, 4] and r0["send"][1] == [0, 3]   # rank 0 needs 5, 6, 4 (5 once)
+    assert r1["remote"] == 2 and r1["recv"][0] == [0, 3] and r1["send"][0] == [5, 6, 4]
