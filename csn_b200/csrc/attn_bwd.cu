@@ -64,7 +64,7 @@ struct BwdCfg {
   static constexpr int SMEM_BYTES = 2 * TILE_BYTES + DS_BYTES + NST * SLOT_BYTES + 256 + 1024;
 };
 
-template <int DH, int CL, bool WITH_DQ>
+template <int DH, int CL, bool WITH_DQ, bool DROP>
 __global__ void __launch_bounds__(256, 1)
 attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmDO,
                    const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
@@ -283,7 +283,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
           for (int i = 0; i < 32; i += 2) {
             float d0 = 0.f, d1 = 0.f;
             float m0 = 1.f, m1 = 1.f;   // d P_dropped / d P = mask / (1 - p)
-            if (p.drop_thresh) {
+            if (DROP) {
               const uint32_t hh = drop_pair(rk, (uint32_t)(j * 128 + c + i) >> 1);
               m0 = drop_keep_lo(hh, p.drop_thresh) ? p.drop_scale : 0.f;
               m1 = drop_keep_hi(hh, p.drop_thresh) ? p.drop_scale : 0.f;
@@ -405,7 +405,7 @@ struct WideCfgT {
 };
 using WideCfg = WideCfgT<0>;
 
-template <int CL, int DBG = 0>
+template <int CL, int DBG, bool DROP>
 __global__ void __launch_bounds__(384, 1)
 attn_bwd_ds_wide_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmDO,
                         const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
@@ -613,7 +613,7 @@ attn_bwd_ds_wide_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
 #pragma unroll
             for (int i = 0; i < 32; i += 2) {
               float sc0 = p.scale, sc1 = p.scale;
-              if (p.drop_thresh) {   // d P_dropped / d P = mask / (1 - p)
+              if (DROP) {   // d P_dropped / d P = mask / (1 - p)
                 const uint32_t hh = drop_pair(rk, (uint32_t)(key0 + c * 32 + i) >> 1);
                 sc0 = drop_keep_lo(hh, p.drop_thresh) ? p.scale * p.drop_scale : 0.f;
                 sc1 = drop_keep_hi(hh, p.drop_thresh) ? p.scale * p.drop_scale : 0.f;
@@ -682,10 +682,10 @@ attn_bwd_ds_wide_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
   }
 }
 
-template <int CL, int DBG = 0>
-static int launch_ds_wide(const CUtensorMap& tmQ, const CUtensorMap& tmDO, const CUtensorMap& tmK, const CUtensorMap& tmV,
+template <int CL, int DBG, bool DROP>
+static int launch_ds_wide_d(const CUtensorMap& tmQ, const CUtensorMap& tmDO, const CUtensorMap& tmK, const CUtensorMap& tmV,
                           const CUtensorMap& tmDS, const AttnBwdArgs& a, cudaStream_t stream) {
-  auto kern = attn_bwd_ds_wide_kernel<CL, DBG>;
+  auto kern = attn_bwd_ds_wide_kernel<CL, DBG, DROP>;
   using WideCfg = WideCfgT<DBG>;
   static bool configured = false;
   if (!configured) {
@@ -754,11 +754,11 @@ __global__ void attn_delta_kernel(const void* __restrict__ dO, const void* __res
   }
 }
 
-template <int DH, int CL, bool WITH_DQ>
-static int launch_dq(const CUtensorMap& tmQ, const CUtensorMap& tmDO, const CUtensorMap& tmK, const CUtensorMap& tmV,
+template <int DH, int CL, bool WITH_DQ, bool DROP>
+static int launch_dq_d(const CUtensorMap& tmQ, const CUtensorMap& tmDO, const CUtensorMap& tmK, const CUtensorMap& tmV,
                      const CUtensorMap& tmDS, const CUtensorMap& tmDQ, const AttnBwdArgs& a, cudaStream_t stream) {
   using Cfg = BwdCfg<DH>;
-  auto kern = attn_bwd_dq_kernel<DH, CL, WITH_DQ>;
+  auto kern = attn_bwd_dq_kernel<DH, CL, WITH_DQ, DROP>;
   static bool configured = false;
   if (!configured) {
     CSN_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
@@ -783,6 +783,20 @@ static int launch_dq(const CUtensorMap& tmQ, const CUtensorMap& tmDO, const CUte
   CSN_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, tmQ, tmDO, tmK, tmV, tmDS, tmDQ, a));
   CSN_LAUNCH_OK("attn_bwd_dq_kernel");
   return 0;
+}
+
+// the dropout code is a compile-time variant: the eval-mode kernels carry none of it
+template <int DH, int CL, bool WITH_DQ>
+static int launch_dq(const CUtensorMap& tmQ, const CUtensorMap& tmDO, const CUtensorMap& tmK, const CUtensorMap& tmV,
+                     const CUtensorMap& tmDS, const CUtensorMap& tmDQ, const AttnBwdArgs& a, cudaStream_t stream) {
+  if (a.drop_thresh) return launch_dq_d<DH, CL, WITH_DQ, true>(tmQ, tmDO, tmK, tmV, tmDS, tmDQ, a, stream);
+  return launch_dq_d<DH, CL, WITH_DQ, false>(tmQ, tmDO, tmK, tmV, tmDS, tmDQ, a, stream);
+}
+template <int CL, int DBG = 0>
+static int launch_ds_wide(const CUtensorMap& tmQ, const CUtensorMap& tmDO, const CUtensorMap& tmK, const CUtensorMap& tmV,
+                          const CUtensorMap& tmDS, const AttnBwdArgs& a, cudaStream_t stream) {
+  if (a.drop_thresh) return launch_ds_wide_d<CL, DBG, true>(tmQ, tmDO, tmK, tmV, tmDS, a, stream);
+  return launch_ds_wide_d<CL, DBG, false>(tmQ, tmDO, tmK, tmV, tmDS, a, stream);
 }
 
 }  // namespace csn

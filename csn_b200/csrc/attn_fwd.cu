@@ -42,7 +42,7 @@ struct AttnCfg {
   static constexpr int O_COL = 256;                        // TMEM: S0 @0, S1 @128, O @256 (DH <= 256)
 };
 
-template <int DH, int MODE, int CL>
+template <int DH, int MODE, int CL, bool DROP>
 __global__ void __launch_bounds__(256, 1)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                 const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmO,
@@ -298,7 +298,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
               float a1 = (c + i + 1 < cvalid) ? fast_exp2(__uint_as_float(v0[i + 1]) * p.scale_log2 - lse_l2) : 0.f;
               float b0 = (c + 32 + i < cvalid) ? fast_exp2(__uint_as_float(v1[i]) * p.scale_log2 - lse_l2) : 0.f;
               float b1 = (c + 33 + i < cvalid) ? fast_exp2(__uint_as_float(v1[i + 1]) * p.scale_log2 - lse_l2) : 0.f;
-              if (p.drop_thresh) {   // the forward pass's dropout mask, regenerated (query row id, key column)
+              if (DROP) {   // the forward pass's dropout mask, regenerated (query row id, key column)
                 const uint32_t h0 = drop_pair(rk, (uint32_t)(it.key0 + c + i) >> 1), h1 = drop_pair(rk, (uint32_t)(it.key0 + c + 32 + i) >> 1);
                 a0 = drop_keep_lo(h0, p.drop_thresh) ? a0 * p.drop_scale : 0.f; a1 = drop_keep_hi(h0, p.drop_thresh) ? a1 * p.drop_scale : 0.f;
                 b0 = drop_keep_lo(h1, p.drop_thresh) ? b0 * p.drop_scale : 0.f; b1 = drop_keep_hi(h1, p.drop_thresh) ? b1 * p.drop_scale : 0.f;
@@ -364,7 +364,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                   float a0 = fast_exp2(s0 * p.scale_log2 - moff), a1 = fast_exp2(s1 * p.scale_log2 - moff);
                   float b0 = fast_exp2(t0 * p.scale_log2 - moff), b1 = fast_exp2(t1 * p.scale_log2 - moff);
                   lsum += (a0 + a1) + (b0 + b1);   // the softmax denominator sees every key; dropout acts on the result
-                  if (p.drop_thresh) {
+                  if (DROP) {
                     const uint32_t h0 = drop_pair(rk, (uint32_t)(j * 128 + c + i) >> 1), h1 = drop_pair(rk, (uint32_t)(j * 128 + c + 32 + i) >> 1);
                     a0 = drop_keep_lo(h0, p.drop_thresh) ? a0 * p.drop_scale : 0.f; a1 = drop_keep_hi(h0, p.drop_thresh) ? a1 * p.drop_scale : 0.f;
                     b0 = drop_keep_lo(h1, p.drop_thresh) ? b0 * p.drop_scale : 0.f; b1 = drop_keep_hi(h1, p.drop_thresh) ? b1 * p.drop_scale : 0.f;
@@ -383,7 +383,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                   float a0 = fast_exp2(s0 * p.scale_log2 - moff), a1 = fast_exp2(s1 * p.scale_log2 - moff);
                   float b0 = fast_exp2(t0 * p.scale_log2 - moff), b1 = fast_exp2(t1 * p.scale_log2 - moff);
                   lsum += (a0 + a1) + (b0 + b1);   // the softmax denominator sees every key; dropout acts on the result
-                  if (p.drop_thresh) {
+                  if (DROP) {
                     const uint32_t h0 = drop_pair(rk, (uint32_t)(j * 128 + c + i) >> 1), h1 = drop_pair(rk, (uint32_t)(j * 128 + c + 32 + i) >> 1);
                     a0 = drop_keep_lo(h0, p.drop_thresh) ? a0 * p.drop_scale : 0.f; a1 = drop_keep_hi(h0, p.drop_thresh) ? a1 * p.drop_scale : 0.f;
                     b0 = drop_keep_lo(h1, p.drop_thresh) ? b0 * p.drop_scale : 0.f; b1 = drop_keep_hi(h1, p.drop_thresh) ? b1 * p.drop_scale : 0.f;
@@ -514,11 +514,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   }
 }
 
-template <int DH, int MODE, int CL>
-static int launch_attn_fwd(const CUtensorMap& tmQ, const CUtensorMap& tmK, const CUtensorMap& tmV,
+template <int DH, int MODE, int CL, bool DROP>
+static int launch_attn_fwd_d(const CUtensorMap& tmQ, const CUtensorMap& tmK, const CUtensorMap& tmV,
                            const CUtensorMap& tmO, const CUtensorMap& tmOlo, const AttnFwdArgs& a, cudaStream_t stream) {
   using Cfg = AttnCfg<DH>;
-  auto kern = attn_fwd_kernel<DH, MODE, CL>;
+  auto kern = attn_fwd_kernel<DH, MODE, CL, DROP>;
   static bool configured = false;
   if (!configured) {
     CSN_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
@@ -543,6 +543,14 @@ static int launch_attn_fwd(const CUtensorMap& tmQ, const CUtensorMap& tmK, const
   CSN_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, tmQ, tmK, tmV, tmO, tmOlo, a));
   CSN_LAUNCH_OK("attn_fwd_kernel");
   return 0;
+}
+
+// the dropout code is a compile-time variant: the eval-mode kernels carry none of it
+template <int DH, int MODE, int CL>
+static int launch_attn_fwd(const CUtensorMap& tmQ, const CUtensorMap& tmK, const CUtensorMap& tmV,
+                           const CUtensorMap& tmO, const CUtensorMap& tmOlo, const AttnFwdArgs& a, cudaStream_t stream) {
+  if (a.drop_thresh) return launch_attn_fwd_d<DH, MODE, CL, true>(tmQ, tmK, tmV, tmO, tmOlo, a, stream);
+  return launch_attn_fwd_d<DH, MODE, CL, false>(tmQ, tmK, tmV, tmO, tmOlo, a, stream);
 }
 
 // Items 2m / 2m+1 may share a cluster when they stream exactly the same tiles.

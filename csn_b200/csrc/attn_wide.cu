@@ -33,7 +33,7 @@ struct WideAttnCfg {
   static constexpr int SMEM_BYTES = R_BYTES + P_BYTES + NST * SLOT_BYTES + XCH_BYTES + BAR_BYTES + 1024;
 };
 
-template <int MODE, int CL>
+template <int MODE, int CL, bool DROP>
 __global__ void __launch_bounds__(384, 1)
 attn_wide_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                  const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmO,
@@ -364,7 +364,7 @@ attn_wide_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
               const float p3 = (rvalid && c0 + 3 < nvalid) ? fast_exp2(__uint_as_float(v[k + 3]) * p.scale_log2 - off.w) : 0.f;
               lsum += (p0 + p1) + (p2 + p3);   // the softmax denominator sees every key; dropout acts on the result
               float d0 = p0, d1 = p1, d2 = p2, d3 = p3;
-              if (p.drop_thresh) {
+              if (DROP) {
                 if (MODE == 0) {   // row = this thread's query, columns = consecutive keys: one hash per two elements
                   const uint32_t kc = (uint32_t)(col_first + c0);
                   const uint32_t h0 = drop_pair(rk0, kc >> 1), h1 = drop_pair(rk0, (kc >> 1) + 1);
@@ -449,10 +449,10 @@ attn_wide_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   }
 }
 
-template <int MODE, int CL>
-static int launch_wide(const CUtensorMap& tmQ, const CUtensorMap& tmK, const CUtensorMap& tmV, const CUtensorMap& tmO,
+template <int MODE, int CL, bool DROP>
+static int launch_wide_d(const CUtensorMap& tmQ, const CUtensorMap& tmK, const CUtensorMap& tmV, const CUtensorMap& tmO,
                        const CUtensorMap& tmOlo, const AttnFwdArgs& a, cudaStream_t stream) {
-  auto kern = attn_wide_kernel<MODE, CL>;
+  auto kern = attn_wide_kernel<MODE, CL, DROP>;
   static bool configured = false;
   if (!configured) {
     CSN_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, WideAttnCfg::SMEM_BYTES));
@@ -477,6 +477,13 @@ static int launch_wide(const CUtensorMap& tmQ, const CUtensorMap& tmK, const CUt
   CSN_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, tmQ, tmK, tmV, tmO, tmOlo, a));
   CSN_LAUNCH_OK("attn_wide_kernel");
   return 0;
+}
+
+template <int MODE, int CL>
+static int launch_wide(const CUtensorMap& tmQ, const CUtensorMap& tmK, const CUtensorMap& tmV, const CUtensorMap& tmO,
+                       const CUtensorMap& tmOlo, const AttnFwdArgs& a, cudaStream_t stream) {
+  if (a.drop_thresh) return launch_wide_d<MODE, CL, true>(tmQ, tmK, tmV, tmO, tmOlo, a, stream);
+  return launch_wide_d<MODE, CL, false>(tmQ, tmK, tmV, tmO, tmOlo, a, stream);
 }
 
 int launch_attn_wide(int mode, bool pair, const CUtensorMap& tmQ, const CUtensorMap& tmK, const CUtensorMap& tmV,

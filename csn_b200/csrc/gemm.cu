@@ -178,7 +178,7 @@ __device__ __forceinline__ void store_chunk(const GemmArgs& p, long long base, i
   }
 }
 
-template <int BN, bool A_MN, bool B_MN, int CL, bool LN = false, bool DL = false, bool CB = false>
+template <int BN, bool A_MN, bool B_MN, int CL, bool LN = false, bool DL = false, bool CB = false, bool DROP = false>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
             const __grid_constant__ CUtensorMap tmD, const __grid_constant__ CUtensorMap tmR0,
@@ -493,7 +493,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             float rv;
             asm volatile("ld.shared.f32 %0, [%1];" : "=f"(rv) : "r"(rs + jj * 128 + ((((uint32_t)lane >> 2) ^ ((uint32_t)jj & 7u)) << 4)));
             float fc = __uint_as_float(r[jj]) * al;
-            if (p.drop_thresh) {
+            if (DROP) {
               const uint32_t hh = drop_pair(drop_rk, (uint32_t)(u * 32 + jj) >> 1);   // (compiler shares the hash of a pair)
               fc = ((jj & 1) ? drop_keep_hi(hh, p.drop_thresh) : drop_keep_lo(hh, p.drop_thresh)) ? fc * p.drop_scale : 0.f;
             }
@@ -679,12 +679,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   }
 }
 
-template <int BN, bool A_MN, bool B_MN, int CL, bool LN = false, bool DL = false, bool CB = false>
+template <int BN, bool A_MN, bool B_MN, int CL, bool LN = false, bool DL = false, bool CB = false, bool DROP = false>
 static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmD,
                        const GemmArgs& args, cudaStream_t stream, const CUtensorMap* tmR0 = nullptr,
                        const CUtensorMap* tmR1 = nullptr) {
   using Cfg = GemmCfg<BN>;
-  auto kern = gemm_kernel<BN, A_MN, B_MN, CL, LN, DL, CB>;
+  auto kern = gemm_kernel<BN, A_MN, B_MN, CL, LN, DL, CB, DROP>;
   static bool configured = false;
   if (!configured) {
     CSN_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
@@ -882,6 +882,10 @@ static int gemm_impl(const csn_mat* A, const csn_mat* B, const csn_out* D, int32
     // the thread owns its whole row; two warp sets alternate tiles (one per accumulator buffer); per warp 2 output
     // + 2 residual slabs -> 128 KB of staging next to a 2-deep operand ring (K is short: the epilogue is the critical path)
     g.stages = 2; g.stg_bufs = 4; g.epi_warps = 8; g.alt_tiles = 1; g.tempty_count = 128;
+    if (g.drop_thresh) {   // training mode: dropout on the projection output (compile-time variant)
+      if (CL == 2) return launch_gemm<256, false, false, 2, true, false, false, true>(tmA, tmB, tmD, g, s, &tmR0, &tmR1);
+      return launch_gemm<256, false, false, 1, true, false, false, true>(tmA, tmB, tmD, g, s, &tmR0, &tmR1);
+    }
     if (CL == 2) return launch_gemm<256, false, false, 2, true>(tmA, tmB, tmD, g, s, &tmR0, &tmR1);
     return launch_gemm<256, false, false, 1, true>(tmA, tmB, tmD, g, s, &tmR0, &tmR1);
   }

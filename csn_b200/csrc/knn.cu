@@ -522,6 +522,100 @@ __global__ void topk_rows_kernel(const float* __restrict__ scores, long long ld,
   }
 }
 
+// --------------------------------------------------------------------------- top-K boundary band, on the device
+// csn_knn_band_select: per query row, the k-th largest coarse score and every candidate within `margin` of it (or
+// above) — the pairs whose order the 16-bit scoring pass cannot be trusted on — written directly as the work tables of
+// csn_knn_scores_exact: candidate list of query q at cands[q*n_cols ...] (ascending candidate index), one item per
+// 128-row tile of the query with list_count = band size.  Nothing returns to the host (the reference's
+// `retrieval_measure.topk(K+1)` csa_models.py:278 is evaluated on scores that are exact where it matters).
+struct BandArgs {
+  const float* scores; long long ld; int n_q, n_cols, k; float margin;
+  const int* q_row0; const int* q_len; const int* item0;   // per query: first feature row, length, first item index
+  const int* c_row0; const int* c_len;                      // per candidate shape
+  int* band_idx; int* counts; KnnCand* cands; KnnItem* items;
+};
+
+template <int TOPK_MAX>
+__global__ void knn_band_select_kernel(const BandArgs p) {
+  const int q = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (q >= p.n_q) return;
+  float v[TOPK_MAX];
+  int ix[TOPK_MAX];
+#pragma unroll
+  for (int i = 0; i < TOPK_MAX; ++i) { v[i] = -INFINITY; ix[i] = 0x7fffffff; }
+  const float* src = p.scores + (long long)q * p.ld;
+  for (int c = lane; c < p.n_cols; c += 32) {
+    float x = src[c];
+    int xi = c;
+#pragma unroll
+    for (int i = 0; i < TOPK_MAX; ++i) {
+      if (i < p.k) {
+        const bool better = (x > v[i]) || (x == v[i] && xi < ix[i]);
+        if (better) { const float tv = v[i]; const int ti = ix[i]; v[i] = x; ix[i] = xi; x = tv; xi = ti; }
+      }
+    }
+  }
+  float kth = 0.f;
+  for (int r = 0; r < p.k; ++r) {
+    float bv = v[0]; int bi = ix[0]; int bl = lane;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      const int ol = __shfl_xor_sync(0xffffffffu, bl, o);
+      if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; bl = ol; }
+    }
+    kth = bv;
+    if (lane == bl) {
+#pragma unroll
+      for (int i = 0; i < TOPK_MAX - 1; ++i) { v[i] = v[i + 1]; ix[i] = ix[i + 1]; }
+      v[TOPK_MAX - 1] = -INFINITY; ix[TOPK_MAX - 1] = 0x7fffffff;
+    }
+  }
+  const float thr = kth - p.margin;
+  int cnt = 0;
+  const long long base = (long long)q * p.n_cols;
+  for (int c0 = 0; c0 < p.n_cols; c0 += 32) {
+    const int c = c0 + lane;
+    const bool in = c < p.n_cols && src[c] >= thr;
+    const unsigned m = __ballot_sync(0xffffffffu, in);
+    if (in) {
+      const int pos = cnt + __popc(m & ((1u << lane) - 1u));
+      p.band_idx[base + pos] = c;
+      p.cands[base + pos] = KnnCand{p.c_row0[c], p.c_len[c]};
+    }
+    cnt += __popc(m);
+  }
+  const int len = p.q_len[q], nt = (len + KNN_BM - 1) / KNN_BM, it0 = p.item0[q];
+  if (lane == 0) p.counts[q] = cnt;
+  for (int t = lane; t < nt; t += 32) {
+    KnnItem it;
+    it.q_row0 = p.q_row0[q] + t * KNN_BM;
+    it.n_valid = min(KNN_BM, len - t * KNN_BM);
+    it.list_begin = (int)base;
+    it.list_count = cnt;
+    it.out_off = (it0 + t) * p.n_cols;
+    it.pad = 0;
+    p.items[it0 + t] = it;
+  }
+}
+
+// scores[q][band_idx[q][i]] = (sum over the query's row tiles of partial[(item0[q] + t)*n_cols + i]) / len_q, tiles summed
+// in a fixed order in fp64
+__global__ void knn_band_patch_kernel(const float* __restrict__ partial, const int* __restrict__ band_idx,
+                                      const int* __restrict__ counts, const int* __restrict__ item0,
+                                      const int* __restrict__ q_len, int n_q, int n_cols, float* __restrict__ scores,
+                                      long long ld) {
+  const int q = blockIdx.y;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= n_q || i >= counts[q]) return;
+  const int len = q_len[q], nt = (len + KNN_BM - 1) / KNN_BM;
+  double s = 0.0;
+  for (int t = 0; t < nt; ++t) s += (double)partial[(long long)(item0[q] + t) * n_cols + i];
+  scores[(long long)q * ld + band_idx[(long long)q * n_cols + i]] = (float)(s / (double)len);
+}
+
 }  // namespace csn
 
 extern "C" {
@@ -644,6 +738,42 @@ int csn_topk_rows(const float* scores, int64_t ld, int32_t n_rows, int32_t n_col
   else if (k <= 32) topk_rows_kernel<32><<<grid, block, 0, st>>>(scores, ld, n_rows, n_cols, k, out_val, (long long*)out_idx);
   else topk_rows_kernel<64><<<grid, block, 0, st>>>(scores, ld, n_rows, n_cols, k, out_val, (long long*)out_idx);
   CSN_LAUNCH_OK("topk_rows_kernel");
+  return 0;
+}
+
+int csn_knn_band_select(const float* scores, int64_t ld, int32_t n_q, int32_t n_cols, int32_t k, float margin,
+                        const int32_t* q_row0, const int32_t* q_len, const int32_t* item0, const int32_t* c_row0,
+                        const int32_t* c_len, int32_t* band_idx, int32_t* counts, int32_t* cands, int32_t* items,
+                        void* stream) {
+  using namespace csn;
+  clear_error();
+  CSN_CHECK_ARG(scores && q_row0 && q_len && item0 && c_row0 && c_len && band_idx && counts && cands && items,
+                "csn_knn_band_select: null pointer");
+  CSN_CHECK_ARG(k >= 1 && k <= TOPK_LIMIT && k <= n_cols, "csn_knn_band_select: k=%d must be in [1, min(%d, n_cols=%d)]", k, TOPK_LIMIT, n_cols);
+  CSN_CHECK_ARG((long long)n_q * n_cols < (1ll << 31), "csn_knn_band_select: query block too large (n_q*n_cols >= 2^31)");
+  if (n_q == 0) return 0;
+  BandArgs a{scores, ld, n_q, n_cols, k, margin, q_row0, q_len, item0, c_row0, c_len, band_idx, counts,
+             reinterpret_cast<KnnCand*>(cands), reinterpret_cast<KnnItem*>(items)};
+  const int wpb = 4;
+  const dim3 grid((n_q + wpb - 1) / wpb), block(wpb * 32);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (k <= 8) knn_band_select_kernel<8><<<grid, block, 0, st>>>(a);
+  else if (k <= 16) knn_band_select_kernel<16><<<grid, block, 0, st>>>(a);
+  else if (k <= 32) knn_band_select_kernel<32><<<grid, block, 0, st>>>(a);
+  else knn_band_select_kernel<64><<<grid, block, 0, st>>>(a);
+  CSN_LAUNCH_OK("knn_band_select_kernel");
+  return 0;
+}
+
+int csn_knn_band_patch(const float* partial, const int32_t* band_idx, const int32_t* counts, const int32_t* item0,
+                       const int32_t* q_len, int32_t n_q, int32_t n_cols, float* scores, int64_t ld, void* stream) {
+  using namespace csn;
+  clear_error();
+  CSN_CHECK_ARG(partial && band_idx && counts && item0 && q_len && scores, "csn_knn_band_patch: null pointer");
+  if (n_q == 0 || n_cols == 0) return 0;
+  knn_band_patch_kernel<<<dim3((n_cols + 127) / 128, n_q), 128, 0, (cudaStream_t)stream>>>(partial, band_idx, counts, item0, q_len,
+                                                                                           n_q, n_cols, scores, ld);
+  CSN_LAUNCH_OK("knn_band_patch_kernel");
   return 0;
 }
 

@@ -63,7 +63,7 @@ __global__ void __launch_bounds__(128) seg_loss_kernel(const SegLossArgs p) {
   }
   // softmax / loss / dlogits
   const long long lab = in ? p.labels[(long long)b * p.n_points + n] : (long long)p.ignore_index;
-  const bool valid = in && lab != p.ignore_index;
+  const bool valid = in && lab != p.ignore_index && lab >= 0 && lab < p.C;   // out-of-range labels are masked (csn_csa_head counts them)
   float mx = -INFINITY;
 #pragma unroll
   for (int c = 0; c < CMAX; ++c) if (c < p.C) mx = fmaxf(mx, acc[c]);
@@ -110,10 +110,12 @@ template <int CMAX>
 static int launch_seg(const SegLossArgs& a, int n_batch, cudaStream_t s) {
   auto kern = seg_loss_kernel<CMAX>;
   const int smem = a.C * 256 * 4;
-  static bool configured = false;
-  if (!configured) {
+  int dev = 0;
+  CSN_CUDA_OK(cudaGetDevice(&dev));
+  static bool configured[64] = {false};   // the attribute is per device
+  if (dev < 64 && !configured[dev]) {
     CSN_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, CMAX * 256 * 4));
-    configured = true;
+    configured[dev] = true;
   }
   kern<<<dim3((a.n_points + 127) / 128, n_batch), 128, smem, s>>>(a);
   CSN_LAUNCH_OK("seg_loss_kernel");

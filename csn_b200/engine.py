@@ -133,8 +133,19 @@ class AttnContext:
     extra: dict = field(default_factory=dict)
 
 
-_ITEM_CACHE: dict = {}
-_TABLE_CACHE: dict = {}
+# Work tables live on the device and are built once per configuration.  Eviction is least-recently-used, one entry at
+# a time; a captured CUDA graph holds raw pointers to the tables of its step, so csn_b200.graphs.GraphedStep pins the
+# entries it saw (pin_tables) for as long as the graph lives.
+from collections import OrderedDict
+
+_ITEM_CACHE: "OrderedDict" = OrderedDict()
+_TABLE_CACHE: "OrderedDict" = OrderedDict()
+_ITEM_CACHE_MAX, _TABLE_CACHE_MAX = 64, 512
+
+
+def pin_tables() -> list:
+    """References to every cached work table (kept by a CUDA graph: evicted entries then stay allocated)."""
+    return list(_ITEM_CACHE.values()) + list(_TABLE_CACHE.values())
 
 
 def cached_table(key, device, build):
@@ -143,10 +154,12 @@ def cached_table(key, device, build):
     k = (key, str(device))
     t = _TABLE_CACHE.get(k)
     if t is None:
-        if len(_TABLE_CACHE) > 256:
-            _TABLE_CACHE.clear()
+        while len(_TABLE_CACHE) >= _TABLE_CACHE_MAX:
+            _TABLE_CACHE.popitem(last=False)
         t = build().to(device)
         _TABLE_CACHE[k] = t
+    else:
+        _TABLE_CACHE.move_to_end(k)
     return t
 
 
@@ -165,6 +178,7 @@ def attn_items(groups, geom: Geometry, n_head: int, d: int, device, kind: str = 
     key = (tuple(groups), geom, n_head, d, str(device), kind)
     t = _ITEM_CACHE.get(key)
     if t is not None:
+        _ITEM_CACHE.move_to_end(key)
         return t
     NP, CP, NC = geom.rows_pad, geom.chunk_pad, geom.n_chunks
     tiles = CP // 128
@@ -195,8 +209,8 @@ def attn_items(groups, geom: Geometry, n_head: int, d: int, device, kind: str = 
                                          j * NP + c * CP + t_ * 128, h * d, stat + t_ * 128,
                                          ((j * NC + c) * n_head + h) * CP + t_ * 128, 0, 1, 0, 0))
     t = torch.tensor(rows, dtype=torch.int32).to(device)
-    if len(_ITEM_CACHE) > 16:
-        _ITEM_CACHE.clear()
+    while len(_ITEM_CACHE) >= _ITEM_CACHE_MAX:
+        _ITEM_CACHE.popitem(last=False)
     _ITEM_CACHE[key] = t
     return t
 
@@ -435,7 +449,7 @@ def _pick_split(tiles: int, kb_total: int, target: int = 296) -> int:
 
 def attention_backward(ctx: AttnContext, dY: torch.Tensor, need_dx: bool, amax: torch.Tensor = None,
                        bcast: torch.Tensor = None, bcast_idx: torch.Tensor = None, bcast_scale: float = 0.0,
-                       src_idx: torch.Tensor = None, src_w: torch.Tensor = None):
+                       src_idx: torch.Tensor = None, src_w: torch.Tensor = None, split_v: bool = False):
     """Backward of attention_forward. dY: [blocks*NP, 256] fp32 (zero in pad rows).
     Returns dict with dWq, dWk, dWv, dWo (fp32, reference layouts), dgamma, dbeta and, if need_dx,
     dX [S*NP, 256] fp32 (padded row-major, gradient w.r.t. every slot's features)."""
@@ -570,15 +584,20 @@ def attention_backward(ctx: AttnContext, dY: torch.Tensor, need_dx: bool, amax: 
              "dgamma": dgamma, "dbeta": dbeta}
     if need_dx:
         dX = torch.zeros(S * NP, 256, dtype=torch.float32, device=dev)
+        # split_v: the gradient that reaches a slot through its VALUE role goes to a separate buffer (callers whose
+        # key and value inputs are distinct autograd tensors holding the same data)
+        dXv = torch.zeros_like(dX) if split_v else dX
         Wq16, Wk16, Wv16 = ctx.Wqkv16[:HD], ctx.Wqkv16[HD:2 * HD], ctx.Wqkv16[2 * HD:]
         for g in ctx.groups:
             nb = (g.n_in, g.n_out, 1, 1)
-            for (dproj, W16, s0, si, so) in ((dQv, Wq16, g.q0, g.q_si, g.q_so), (dKv, Wk16, g.k0, g.k_si, g.k_so),
-                                             (dVv, Wv16, g.v0, g.v_si, g.v_so)):
+            for (dproj, W16, s0, si, so, dst) in ((dQv, Wq16, g.q0, g.q_si, g.q_so, dX), (dKv, Wk16, g.k0, g.k_si, g.k_so, dX),
+                                                  (dVv, Wv16, g.v0, g.v_si, g.v_so, dXv)):
                 A = L.mat(dproj[g.blk0 * NP:], L.MAJOR_K, mn_off=(NP, g.n_in * NP))
                 B = L.mat(W16, L.MAJOR_MN)
-                D = L.out(dX[s0 * NP:], 256, off=(si * NP * 256, so * NP * 256), accumulate=True)
+                D = L.out(dst[s0 * NP:], 256, off=(si * NP * 256, so * NP * 256), accumulate=True)
                 L.gemm(A, B, D, NP, 256, HD, nb=nb)
+        if split_v:
+            grads["dXv"] = dXv
         # residual path: dX[q slot] += dZ[block]
         dX3 = dX.view(S, NP, 256)
         dZ3 = dZ.view(nblk, NP, 256)

@@ -36,6 +36,9 @@ class GraphedStep:
         with torch.cuda.graph(self.graph):
             self.outputs = fn(*static_inputs)
         self.launches = L.launch_count() - n0   # C-ABI kernel launches recorded in the graph
+        # the graph holds raw device pointers to the work tables of its step: keep them allocated while it lives
+        from . import engine as _E
+        self._tables = _E.pin_tables()
 
     def replay(self):
         self.graph.replay()

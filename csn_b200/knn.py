@@ -37,6 +37,26 @@ class ShapeStore:
         idx = [int(i) for i in idx]
         return ShapeStore(self.rows, [self.row0[i] for i in idx], [self.length[i] for i in idx], self.rows_lo)
 
+    def tables(self):
+        """Device copies of (row0, length, item0) as int32 tensors, built once per store: item0[s] = index of the first
+        128-row tile of shape s in the store's tile enumeration (exclusive prefix sum of the tile counts)."""
+        t = getattr(self, "_tables", None)
+        if t is None:
+            import numpy as np
+            row0 = np.asarray(self.row0, dtype=np.int64)
+            length = np.asarray(self.length, dtype=np.int64)
+            nt = (length + TILE_ROWS - 1) // TILE_ROWS
+            item0 = np.concatenate([[0], np.cumsum(nt)[:-1]]) if len(nt) else np.zeros(0, dtype=np.int64)
+            dev = self.rows.device
+            # one pinned staging buffer, asynchronous upload: building the tables never synchronises with the stream
+            host = torch.from_numpy(np.stack([row0, length, item0]).astype(np.int32))
+            if dev.type == "cuda":
+                host = host.pin_memory()
+            d = host.to(dev, non_blocking=True)
+            t = (d[0], d[1], d[2], int(nt.sum()), host)
+            object.__setattr__(self, "_tables", t)
+        return t
+
 
 def _normalize_into(src: torch.Tensor, dst: torch.Tensor, eps: float) -> None:
     assert src.is_cuda and src.dtype == torch.float32 and src.is_contiguous()
@@ -112,25 +132,35 @@ def scores_from_stores(q: ShapeStore, c: ShapeStore, query_block: int = 148) -> 
     dev = q.rows.device
     Sq, Sc = q.n_shapes, c.n_shapes
     scores = torch.empty(Sq, Sc, dtype=torch.float32, device=dev)
-    cands = torch.tensor([[r, n] for r, n in zip(c.row0, c.length)], dtype=torch.int32, device=dev)
+    import numpy as np
+    c_row0, c_len = c.tables()[:2]
+    q.tables()   # (uploaded here so that refine_band finds them cached)
+    cands = torch.stack([c_row0, c_len], dim=1).contiguous()
     lib = L.lib()
+    q_row0_np, q_len_np = np.asarray(q.row0, dtype=np.int64), np.asarray(q.length, dtype=np.int64)
     for q0 in range(0, Sq, query_block):
         q1 = min(Sq, q0 + query_block)
-        # tables: items ordered (query, tile, segment); partial rows ordered (query, tile)
-        items, row_of_query = [], []
-        part_rows = 0
-        for s in range(q0, q1):
-            nt = (q.length[s] + TILE_ROWS - 1) // TILE_ROWS
-            row_of_query.append((part_rows, nt))
-            part_rows += nt
+        # tables (numpy, no Python loops over tiles): items ordered (query, tile, segment); partial rows (query, tile)
+        lens = q_len_np[q0:q1]
+        nts = (lens + TILE_ROWS - 1) // TILE_ROWS
+        prow0 = np.concatenate([[0], np.cumsum(nts)[:-1]])
+        part_rows = int(nts.sum())
+        row_of_query = list(zip(prow0.tolist(), nts.tolist()))
         ns = _split_for_balance(part_rows, Sc)
-        seg = [(i * Sc // ns, (i + 1) * Sc // ns) for i in range(ns)]
-        for s, (prow, nt) in zip(range(q0, q1), row_of_query):
-            for t in range(nt):
-                nvalid = min(TILE_ROWS, q.length[s] - t * TILE_ROWS)
-                for (b, e) in seg:
-                    items.append((q.row0[s] + t * TILE_ROWS, nvalid, b, e - b, (prow + t) * Sc + b, 0))
-        items_t = torch.tensor(items, dtype=torch.int32, device=dev)
+        seg_b = np.arange(ns, dtype=np.int64) * Sc // ns
+        seg_e = (np.arange(ns, dtype=np.int64) + 1) * Sc // ns
+        qi = np.repeat(np.arange(q1 - q0), nts)                                  # query of every (query, tile) row
+        ti = np.arange(part_rows) - np.repeat(prow0, nts)                       # tile index inside its query
+        nvalid = np.minimum(TILE_ROWS, lens[qi] - ti * TILE_ROWS)
+        tab = np.empty((part_rows, ns, 6), dtype=np.int32)
+        tab[:, :, 0] = (q_row0_np[q0:q1][qi] + ti * TILE_ROWS)[:, None]
+        tab[:, :, 1] = nvalid[:, None]
+        tab[:, :, 2] = seg_b[None, :]
+        tab[:, :, 3] = (seg_e - seg_b)[None, :]
+        tab[:, :, 4] = np.arange(part_rows)[:, None] * Sc + seg_b[None, :]
+        tab[:, :, 5] = 0
+        items = tab.reshape(-1, 6)
+        items_t = torch.from_numpy(items).pin_memory().to(dev, non_blocking=True)
         partial = torch.empty(part_rows * Sc, dtype=torch.float32, device=dev)
         rc = lib.csn_knn_scores(q.rows.data_ptr(), q.rows.shape[0], c.rows.data_ptr(), c.rows.shape[0],
                                 L.dtype_code(q.rows.dtype), items_t.data_ptr(), len(items), cands.data_ptr(),
@@ -164,50 +194,42 @@ def topk_rows(scores: torch.Tensor, k: int):
     return val, idx
 
 
-def refine_band(scores: torch.Tensor, q: ShapeStore, c: ShapeStore, k: int, margin: float = 4e-5) -> torch.Tensor:
-    """Exact re-score of the top-k boundary band.  For every query the candidates whose coarse score is
-    within `margin` of (or above) the k-th best are re-scored with split fp16 operands (22-bit
-    significands, csn_knn_scores_exact) and patched into `scores` in place: the top-k index sets then
-    match an fp32 evaluation except for genuine ties below ~1e-6 (BASELINE.json's criterion); the 16-bit
-    coarse pass alone is only good to ~1e-5."""
+def refine_band(scores: torch.Tensor, q: ShapeStore, c: ShapeStore, k: int, margin: float = 4e-5,
+                query_block: int = 64) -> torch.Tensor:
+    """Exact re-score of the top-k boundary band, entirely on the device.  For every query the candidates whose
+    coarse score is within `margin` of (or above) the k-th best are selected by csn_knn_band_select — which writes the
+    work tables of csn_knn_scores_exact itself — re-scored with split fp16 operands (22-bit significands) and patched
+    into `scores` in place by csn_knn_band_patch: the top-k index sets then match an fp32 evaluation except for
+    genuine ties below ~1e-6 (BASELINE.json's criterion); the 16-bit coarse pass alone is only good to ~1e-5.
+    No host synchronisation between the scoring pass and the final indices."""
     assert q.rows_lo is not None and c.rows_lo is not None, "build the stores with exact=True"
     dev = scores.device
     Sq, Sc = scores.shape
     k = min(k, Sc)
-    kth = scores.topk(k, dim=-1).values[:, -1:]
-    band = (scores >= kth - margin).nonzero()          # (n_pairs, 2), sorted by query (host sync: tiny table)
-    band_cpu = band.cpu()
-    qi, ci = band_cpu[:, 0].tolist(), band_cpu[:, 1].tolist()
-    items, cands, elem_pair = [], [], []
-    n_pairs = len(qi)
-    start = 0
-    out_off = 0
-    while start < n_pairs:
-        end = start
-        while end < n_pairs and qi[end] == qi[start]:
-            end += 1
-        s_q = qi[start]
-        cnt = end - start
-        nt = (q.length[s_q] + TILE_ROWS - 1) // TILE_ROWS
-        for t in range(nt):
-            nvalid = min(TILE_ROWS, q.length[s_q] - t * TILE_ROWS)
-            items.append((q.row0[s_q] + t * TILE_ROWS, nvalid, start, cnt, out_off, 0))
-            elem_pair.extend(range(start, end))
-            out_off += cnt
-        cands.extend((c.row0[j], c.length[j]) for j in ci[start:end])
-        start = end
-    items_t = torch.tensor(items, dtype=torch.int32, device=dev)
-    cands_t = torch.tensor(cands, dtype=torch.int32, device=dev)
-    partial = torch.empty(out_off, dtype=torch.float32, device=dev)
-    rc = L.lib().csn_knn_scores_exact(q.rows.data_ptr(), q.rows_lo.data_ptr(), q.rows.shape[0], c.rows.data_ptr(),
-                                      c.rows_lo.data_ptr(), c.rows.shape[0], items_t.data_ptr(), len(items),
-                                      cands_t.data_ptr(), partial.data_ptr(), L.stream_ptr())
-    L.check(rc, "csn_knn_scores_exact")
-    # sum the row tiles of every pair (fp64 accumulation: order-independent at fp32 resolution)
-    idx = torch.tensor(elem_pair, dtype=torch.int64, device=dev)
-    tot = torch.zeros(n_pairs, dtype=torch.float64, device=dev).index_add_(0, idx, partial.double())
-    lens = torch.tensor([q.length[i] for i in qi], dtype=torch.float64, device=dev)
-    scores[band[:, 0], band[:, 1]] = (tot / lens).float()
+    lib = L.lib()
+    c_row0, c_len = c.tables()[:2]
+    for q0 in range(0, Sq, query_block):
+        q1 = min(Sq, q0 + query_block)
+        nq = q1 - q0
+        sub = q.subset(range(q0, q1)) if (q0, q1) != (0, Sq) else q
+        s_row0, s_len, s_item0, n_items = sub.tables()[:4]
+        band_idx = torch.empty(nq * Sc, dtype=torch.int32, device=dev)
+        counts = torch.empty(nq, dtype=torch.int32, device=dev)
+        cands = torch.empty(nq * Sc, 2, dtype=torch.int32, device=dev)
+        items = torch.empty(n_items, 6, dtype=torch.int32, device=dev)
+        partial = torch.empty(n_items * Sc, dtype=torch.float32, device=dev)
+        blk = scores[q0:q1]
+        rc = lib.csn_knn_band_select(blk.data_ptr(), scores.stride(0), nq, Sc, k, float(margin), s_row0.data_ptr(),
+                                     s_len.data_ptr(), s_item0.data_ptr(), c_row0.data_ptr(), c_len.data_ptr(),
+                                     band_idx.data_ptr(), counts.data_ptr(), cands.data_ptr(), items.data_ptr(), L.stream_ptr())
+        L.check(rc, "csn_knn_band_select")
+        rc = lib.csn_knn_scores_exact(q.rows.data_ptr(), q.rows_lo.data_ptr(), q.rows.shape[0], c.rows.data_ptr(),
+                                      c.rows_lo.data_ptr(), c.rows.shape[0], items.data_ptr(), n_items,
+                                      cands.data_ptr(), partial.data_ptr(), L.stream_ptr())
+        L.check(rc, "csn_knn_scores_exact")
+        rc = lib.csn_knn_band_patch(partial.data_ptr(), band_idx.data_ptr(), counts.data_ptr(), s_item0.data_ptr(),
+                                    s_len.data_ptr(), nq, Sc, blk.data_ptr(), scores.stride(0), L.stream_ptr())
+        L.check(rc, "csn_knn_band_patch")
     return scores
 
 

@@ -112,6 +112,21 @@ int csn_knn_reduce(const float* partial, float* scores, int32_t n_q, int32_t n_c
 int csn_topk_rows(const float* scores, int64_t ld, int32_t n_rows, int32_t n_cols, int32_t k,
                   float* out_val, int64_t* out_idx, void* stream);
 
+/* Top-K boundary band on the device (no host round trip between csn_knn_scores and the final indices): for every
+ * query row of `scores` the k-th largest value is found and every candidate within `margin` of it (or above) is
+ * appended, in ascending candidate order, to that query's slice of the csn_knn_scores_exact work tables:
+ *   band_idx[q*n_cols + i] = candidate index, cands[(q*n_cols + i)] = {row0, len} of that candidate, counts[q] = band
+ *   size, items[item0[q] + t] = {q_row0[q] + 128 t, valid rows, q*n_cols, counts[q], (item0[q] + t)*n_cols, 0} for the
+ *   row tiles t of query q (item0 = exclusive prefix sum of the queries' tile counts, built once per store).
+ * csn_knn_scores_exact then runs over sum_q ceil(len_q/128) items with a partial buffer of that many rows of n_cols
+ * floats, and csn_knn_band_patch sums the tiles of every re-scored pair (fixed order, fp64) into scores. */
+int csn_knn_band_select(const float* scores, int64_t ld, int32_t n_q, int32_t n_cols, int32_t k, float margin,
+                        const int32_t* q_row0, const int32_t* q_len, const int32_t* item0, const int32_t* c_row0,
+                        const int32_t* c_len, int32_t* band_idx, int32_t* counts, int32_t* cands, int32_t* items,
+                        void* stream);
+int csn_knn_band_patch(const float* partial, const int32_t* band_idx, const int32_t* counts, const int32_t* item0,
+                       const int32_t* q_len, int32_t n_q, int32_t n_cols, float* scores, int64_t ld, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Fused attention core  O = softmax(Q K^T / sqrt(d)) V  (flash-style: the score matrix only exists as
  * 128x128 fp32 tiles in TMEM).  Replaces ScaledDotProductAttention.forward (csa_models.py:138-144,
