@@ -139,13 +139,14 @@ class _MhaFn(torch.autograd.Function):
     """MultiHeadAttention.forward (csa_models.py:81-125) on channel-major inputs."""
 
     @staticmethod
-    def forward(ctx, Q, K, V, wq, wk, wv, wo, gamma, beta, n_head, dt, iters, chunk, dropout_p=0.0, seed=0):
+    def forward(ctx, Q, K, V, wq, wk, wv, wo, gamma, beta, n_head, dt, iters, chunk, dropout_p=0.0, seed=0,
+                same_qk=False, same_kv=False):
         for t, n in ((Q, "Q"), (K, "K"), (V, "V"), (wq, "w_qs.weight")):
             _require_cuda(t, n)
         B, n_src = Q.shape[0], Q.shape[2]
         geom = _geom_for(min(Q.shape[2], K.shape[2], V.shape[2]), iters, chunk)
-        same_kv = K is V or (K.data_ptr() == V.data_ptr() and K.shape == V.shape and K.stride() == V.stride())
-        same_qk = Q is K or (Q.data_ptr() == K.data_ptr() and Q.shape == K.shape and Q.stride() == K.stride())
+        # same_qk / same_kv: the caller passed the SAME tensor object twice (decided by the module on object identity:
+        # an alias such as k = q.detach() is a different autograd leaf and gets its own slot and its own gradient)
         sources = [(Q.float(), 0, 1, 0)]
         k0 = 0 if same_qk else B
         if not same_qk:
@@ -185,7 +186,7 @@ class _MhaFn(torch.autograd.Function):
             if v0 != k0:
                 dV = _rows_to_channel_major(dX[v0 * NP:(v0 + B) * NP], B, nv, a.geom)
         return (dQ, dK, dV, g["dWq"], g["dWk"], g["dWv"], g["dWo"], g["dgamma"], g["dbeta"], None, None, None, None,
-                None, None)
+                None, None, None, None)
 
 
 class ScaledDotProductAttention(nn.Module):
@@ -248,7 +249,7 @@ class MultiHeadAttention(nn.Module):
         """Q,K,V: (B,256,N,1) channel-major. Returns (ret (B,10000,256), attn of the last chunk
         (B,h,500,500)).  `mode` is ignored, as in the reference."""
         return _MhaFn.apply(Q, K, V, *self._weights(), self.n_head, _PRECISIONS[self.precision], self.iters,
-                            self.mini_bs, *self._dropout_state())
+                            self.mini_bs, *self._dropout_state(), Q is K, K is V)
 
     def _dropout_state(self):
         """(p, seed): dropout follows `module.training` (csa_models.py:56,136; the `mode` argument is ignored).
@@ -263,7 +264,7 @@ class MultiHeadAttention(nn.Module):
         """csa_models.py:59-79 (unused by the reference): full, un-chunked self-attention."""
         n = x.shape[2]
         return _MhaFn.apply(x, x, x, *self._weights(), self.n_head, _PRECISIONS[self.precision], 1, n,
-                            *self._dropout_state())
+                            *self._dropout_state(), True, True)
 
 
 # ------------------------------------------------------------------------------------------- fused segmentation loss

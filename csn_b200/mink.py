@@ -37,17 +37,19 @@ class _MhaFullFn(torch.autograd.Function):
     tensor, as in every reference call hrnet.py:407,463)."""
 
     @staticmethod
-    def forward(ctx, q, k, v, wq, wk, wv, wo, gamma, beta, n_head, dt, need_attn, dropout_p=0.0, seed=0):
+    def forward(ctx, q, k, v, wq, wk, wv, wo, gamma, beta, n_head, dt, need_attn, dropout_p=0.0, seed=0,
+                same_qk=False, same_kv=False):
         for t, n in ((q, "q"), (k, "k"), (v, "v"), (wq, "w_qs.weight")):
             _require_cuda(t, n)
         B, Lq, D = q.shape
         Lk = k.shape[1]
         assert D == 256, "d_model = 256 on this path (lib/config.py:49)"
-        same_kv = k is v or (k.data_ptr() == v.data_ptr() and k.shape == v.shape and k.stride() == v.stride())
-        if not same_kv and not torch.equal(k, v):
+        # same_qk / same_kv are decided by the module on OBJECT identity.  Keys and values are read from one slot (the
+        # only call pattern of the reference, hrnet.py:407,463): distinct tensors must hold the same data, and then
+        # each receives its own gradient (split_v below); an alias such as k = q.detach() gets its own slot.
+        if not same_kv and not (k.shape == v.shape and torch.equal(k, v)):
             raise NotImplementedError("csn_b200.mink.MultiHeadAttention reads keys and values from one tensor "
                                       "(the only call pattern of the reference)")
-        same_qk = q is k or (q.data_ptr() == k.data_ptr() and q.shape == k.shape and q.stride() == k.stride())
         n_pad = (max(Lq, Lk) + 127) // 128 * 128
         geom = E.Geometry(chunk=Lq, n_chunks=1, chunk_pad=n_pad, kv_chunk=Lk)
         qh, qf = _pack_rows(q.float(), n_pad, dt)
@@ -60,7 +62,7 @@ class _MhaFullFn(torch.autograd.Function):
         a = E.attention_forward(Xh, Xf, [group], n_slots, B, wq, wk, wv, wo, gamma, beta, geom, n_head,
                                 want_colsum=False, dropout_p=dropout_p, seed=seed)
         ctx.a = a
-        ctx.meta = (B, Lq, Lk, k0, n_pad)
+        ctx.meta = (B, Lq, Lk, k0, n_pad, same_kv)
         out = a.Y.view(B, n_pad, 256)[:, :Lq].contiguous()
         if need_attn:
             attn = _full_attn(a, B, Lq, Lk)
@@ -72,18 +74,25 @@ class _MhaFullFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dout, _dattn):
         a = ctx.a
-        B, Lq, Lk, k0, n_pad = ctx.meta
+        B, Lq, Lk, k0, n_pad, same_kv = ctx.meta
         dY = torch.zeros(B, n_pad, 256, dtype=torch.float32, device=dout.device)
         dY[:, :Lq] = dout
         need_dx = any(ctx.needs_input_grad[:3])
-        g = E.attention_backward(a, dY.view(B * n_pad, 256), need_dx)
-        dq = dk = None
+        split_v = need_dx and not same_kv      # k and v are different autograd tensors: the value-role gradient is v's
+        g = E.attention_backward(a, dY.view(B * n_pad, 256), need_dx, split_v=split_v)
+        dq = dk = dv = None
         if need_dx:
             dX = g["dX"].view(-1, n_pad, 256)
             dq = dX[:B, :Lq].contiguous()
             if k0 != 0:
                 dk = dX[k0:k0 + B, :Lk].contiguous()
-        return (dq, dk, None, g["dWq"], g["dWk"], g["dWv"], g["dWo"], g["dgamma"], g["dbeta"], None, None, None, None, None)
+            if split_v:
+                dXv = g["dXv"].view(-1, n_pad, 256)
+                dv = dXv[k0:k0 + B, :Lk].contiguous()
+                if k0 == 0:   # q is k (one slot): the key-role gradient is already inside dq
+                    dk = None
+        return (dq, dk, dv, g["dWq"], g["dWk"], g["dWv"], g["dWo"], g["dgamma"], g["dbeta"], None, None, None, None, None,
+                None, None)
 
 
 class _MhaBlocksFn(torch.autograd.Function):
@@ -192,7 +201,7 @@ class MultiHeadAttention(nn.Module):
     def forward(self, q, k, v):
         out, attn = _MhaFullFn.apply(q, k, v, self.w_qs.weight, self.w_ks.weight, self.w_vs.weight, self.fc.weight,
                                      self.norm.weight, self.norm.bias, self.n_head, _PRECISIONS[self.precision],
-                                     self.return_attn, *self._dropout_state())
+                                     self.return_attn, *self._dropout_state(), q is k, k is v)
         return out, (attn if self.return_attn else None)
 
     def _dropout_state(self):

@@ -134,3 +134,32 @@ def test_csa_head_forward_backward_matches_reference(precision, tol):
         got = params[pname].grad.detach().reshape(-1).double().cpu()[::stride]
         want = torch.from_numpy(g[f"grad.{pname}.values"].astype("float64"))
         assert float((got - want).norm()) < tol * scale, pname
+
+
+def test_gradients_follow_autograd_identity_not_storage():
+    """ADVICE (round 1): de-duplication of q / k / v slots is decided on object identity.  (a) distinct k and v tensors
+    holding the same data each receive their own gradient (their sum is the gradient of the shared-tensor call);
+    (b) k = q.detach() shares q's storage but is a different autograd leaf: q receives only the query-role gradient."""
+    m = _mha(7, 4)
+    gen = synth.gen(3)
+    q = torch.relu(torch.randn(1, 200, 256, generator=gen)).cuda()
+    kv = torch.relu(torch.randn(1, 150, 256, generator=gen)).cuda()
+    gy = torch.randn(1, 200, 256, generator=gen).cuda()
+    # shared tensor: reference gradient of the key/value input
+    k0 = kv.clone().requires_grad_(True)
+    (m(q, k0, k0)[0] * gy).sum().backward()
+    # (a) distinct tensors
+    k1, v1 = kv.clone().requires_grad_(True), kv.clone().requires_grad_(True)
+    (m(q, k1, v1)[0] * gy).sum().backward()
+    assert v1.grad is not None and float(v1.grad.abs().max()) > 0 and float(k1.grad.abs().max()) > 0
+    assert G.rel_err(k1.grad + v1.grad, k0.grad) < 2e-4
+    assert G.rel_err(k1.grad, k0.grad) > 1e-2          # the value-role part is no longer credited to k
+    # (b) alias of q's storage
+    q2 = q.clone().requires_grad_(True)
+    (m(q2, q2.detach(), q2.detach())[0] * gy).sum().backward()
+    q3, k3 = q.clone().requires_grad_(True), q.clone()
+    (m(q3, k3, k3)[0] * gy).sum().backward()
+    assert G.rel_err(q2.grad, q3.grad) < 2e-4
+    q4 = q.clone().requires_grad_(True)
+    (m(q4, q4, q4)[0] * gy).sum().backward()          # true self-attention: all three roles
+    assert G.rel_err(q4.grad, q3.grad) > 1e-2
