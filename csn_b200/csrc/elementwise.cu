@@ -393,118 +393,133 @@ struct LnBwdArgs {
   uint32_t drop_seed, drop_thresh; float drop_scale;
 };
 
-template <int MINB, bool GS>
+// Block = 8 warps x 8 rows = 64 consecutive rows: they lie inside one attention block AND one chunk (64 | group_rows),
+// so the valid / pad split, the upstream-gradient source, the broadcast row and every base pointer are CTA constants;
+// the row loop is branch-free FFMA chains (~130 instructions per row), two rows in flight per warp.
+template <int MINB, bool GS, bool DROP>
 __global__ void __launch_bounds__(256, MINB) ln_bwd_kernel(const LnBwdArgs p) {
   __shared__ float red[2][8][DM];
   // per-chunk column sums of dZ: every warp accumulates its rows in a private SMEM row (each lane owns its 8 channels:
   // plain read-modify-write, no atomics, no registers)
   __shared__ __align__(16) float gsm[GS ? 8 : 1][GS ? DM : 4];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (GS) {
 #pragma unroll
     for (int w = 0; w < 8; ++w) gsm[w][threadIdx.x] = 0.f;
     __syncthreads();
   }
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long row0 = (long long)blockIdx.x * 64;
-  const float4 g0 = __ldg(reinterpret_cast<const float4*>(p.gamma) + lane), g1 = __ldg(reinterpret_cast<const float4*>(p.gamma) + 32 + lane);
-  float dg[8] = {0, 0, 0, 0, 0, 0, 0, 0}, db[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-  const float gscale = p.amax ? exp2f(floorf(log2f(128.f / fmaxf(__ldg(p.amax), 1e-30f)))) : 1.f;
-  // a CTA's 64 rows lie inside one block (64 | block_rows): one 64-bit division per CTA, 32-bit math per row
   const int blk = (int)(row0 / p.block_rows);
   const int rin0 = (int)(row0 - (long long)blk * p.block_rows);
-  const int src_i = p.src_idx ? __ldg(p.src_idx + blk) : -1;
-  const float src_wgt = (p.src_idx && src_i >= 0) ? __ldg(p.src_w + blk) : 0.f;
+  const int i0 = rin0 % p.group_rows;                         // first row's index inside its chunk
+  const int nv = max(0, min(64, p.rows_valid - i0));          // rows [0, nv) of the CTA are real points, the rest padding
+  const int w0 = warp * 8;
+  const int nvw = max(0, min(8, nv - w0));                    // valid rows of this warp (warp-uniform)
+  const float gscale = p.amax ? exp2f(floorf(log2f(128.f / fmaxf(__ldg(p.amax), 1e-30f)))) : 1.f;
+  const int src_i = p.src_idx ? __ldg(p.src_idx + blk) : 0;
+  const bool has_dy = !p.src_idx || src_i >= 0;               // CTA-uniform
+  const float wg = (p.src_idx ? (has_dy ? __ldg(p.src_w + blk) : 0.f) : 1.f) * gscale;
   const int bc_i = p.bcast ? __ldg(p.bcast_idx + blk) : -1;
-  const float gm[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
-  float4 bca = make_float4(0.f, 0.f, 0.f, 0.f), bcc = bca;   // the block's broadcast row (pooled-mean gradient), pre-scaled
-  if (bc_i >= 0) {
-    const float4* b4 = reinterpret_cast<const float4*>(p.bcast + (long long)bc_i * DM);
-    bca = __ldg(b4 + lane); bcc = __ldg(b4 + 32 + lane);
-    bca.x *= p.bcast_scale; bca.y *= p.bcast_scale; bca.z *= p.bcast_scale; bca.w *= p.bcast_scale;
-    bcc.x *= p.bcast_scale; bcc.y *= p.bcast_scale; bcc.z *= p.bcast_scale; bcc.w *= p.bcast_scale;
-  }
-  struct RowIn { float4 da, dc, za, zc; float mu, rs; bool valid; };
-  // all global loads of a row are issued before anything is consumed; two rows are in flight per warp
-  auto load_row = [&](int i) -> RowIn {
-    RowIn r;
-    const long long row = row0 + warp * 8 + i;
-    const int rin = rin0 + warp * 8 + i;
-    r.valid = row < p.rows && (rin % p.group_rows) < p.rows_valid;
-    r.da = make_float4(0.f, 0.f, 0.f, 0.f); r.dc = r.da; r.za = r.da; r.zc = r.da; r.mu = 0.f; r.rs = 0.f;
-    if (!r.valid) return r;
-    const float4* z4 = reinterpret_cast<const float4*>(p.Z + row * DM);
-    if (p.src_idx) {
-      if (src_i >= 0) {
-        const float4* dy4 = reinterpret_cast<const float4*>(p.dY + ((long long)src_i * p.block_rows + rin) * DM);
-        r.da = __ldg(dy4 + lane); r.dc = __ldg(dy4 + 32 + lane);
-      }
-    } else {
-      const float4* dy4 = reinterpret_cast<const float4*>(p.dY + row * DM);
-      r.da = __ldg(dy4 + lane); r.dc = __ldg(dy4 + 32 + lane);
-    }
-    r.za = __ldg(z4 + lane); r.zc = __ldg(z4 + 32 + lane);
-    r.mu = __ldg(p.mean + row); r.rs = __ldg(p.rstd + row);
+  // per-channel constants live in SMEM (two LDS.128 pairs per row instead of 16 registers held across the kernel):
+  // gamma, and the block's broadcast row (pooled-mean gradient) pre-scaled
+  __shared__ __align__(16) float cst[2][DM];
+  cst[0][threadIdx.x] = __ldg(p.gamma + threadIdx.x);
+  cst[1][threadIdx.x] = bc_i >= 0 ? __ldg(p.bcast + (long long)bc_i * DM + threadIdx.x) * (p.bcast_scale * gscale) : 0.f;
+  __syncthreads();
+  float dg[8] = {0, 0, 0, 0, 0, 0, 0, 0}, db[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  // base pointers of this warp's 8 rows (one 64-bit computation each)
+  const long long wrow = row0 + w0;
+  const float4* z4 = reinterpret_cast<const float4*>(p.Z + wrow * DM) + lane;
+  const long long drow = p.src_idx ? ((long long)(has_dy ? src_i : 0) * p.block_rows + rin0 + w0) : wrow;
+  const float4* d4 = reinterpret_cast<const float4*>(p.dY + drow * DM) + lane;
+  const float* mup = p.mean + wrow;
+  const float* rsp = p.rstd + wrow;
+  uint2* dz16 = reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(p.dZ16) + wrow * DM) + lane;
+  float4* dz4 = p.dZ ? reinterpret_cast<float4*>(p.dZ + wrow * DM) + lane : nullptr;
+
+  struct Row { float4 za, zc, da, dc; float mu, rs; };
+  auto load_row = [&](int i) -> Row {   // all global loads of a row, issued together
+    Row r;
+    r.za = __ldg(z4 + i * 64); r.zc = __ldg(z4 + i * 64 + 32);
+    r.da = make_float4(0.f, 0.f, 0.f, 0.f); r.dc = r.da;
+    if (has_dy) { r.da = __ldg(d4 + i * 64); r.dc = __ldg(d4 + i * 64 + 32); }
+    r.mu = __ldg(mup + i); r.rs = __ldg(rsp + i);
     return r;
   };
-  auto finish_row = [&](const RowIn& r, int i) {
-    const long long row = row0 + warp * 8 + i;
-    if (row >= p.rows) return;
-    float4* dz4 = p.dZ ? reinterpret_cast<float4*>(p.dZ + row * DM) : nullptr;
-    uint2* dz16 = reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(p.dZ16) + row * DM);
-    if (!r.valid) {
-      const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (dz4) { dz4[lane] = zero; dz4[32 + lane] = zero; }
-      dz16[lane] = make_uint2(0, 0); dz16[32 + lane] = make_uint2(0, 0);
-      return;
-    }
-    const float wgt = p.src_idx ? src_wgt : 1.f;
-    const float mu = r.mu, rs = r.rs;
-    const float xh[8] = {(r.za.x - mu) * rs, (r.za.y - mu) * rs, (r.za.z - mu) * rs, (r.za.w - mu) * rs,
-                         (r.zc.x - mu) * rs, (r.zc.y - mu) * rs, (r.zc.z - mu) * rs, (r.zc.w - mu) * rs};
-    const float dy[8] = {(r.da.x * wgt + bca.x) * gscale, (r.da.y * wgt + bca.y) * gscale, (r.da.z * wgt + bca.z) * gscale, (r.da.w * wgt + bca.w) * gscale,
-                         (r.dc.x * wgt + bcc.x) * gscale, (r.dc.y * wgt + bcc.y) * gscale, (r.dc.z * wgt + bcc.z) * gscale, (r.dc.w * wgt + bcc.w) * gscale};
-    float g[8];
+  auto finish_row = [&](const Row& r, int i) {
+    const float4 g0 = *reinterpret_cast<const float4*>(&cst[0][lane * 4]), g1 = *reinterpret_cast<const float4*>(&cst[0][128 + lane * 4]);
+    const float4 b0 = *reinterpret_cast<const float4*>(&cst[1][lane * 4]), b1 = *reinterpret_cast<const float4*>(&cst[1][128 + lane * 4]);
+    const float gm[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+    const float bc[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+    const float zz[8] = {r.za.x, r.za.y, r.za.z, r.za.w, r.zc.x, r.zc.y, r.zc.z, r.zc.w};
+    const float dd[8] = {r.da.x, r.da.y, r.da.z, r.da.w, r.dc.x, r.dc.y, r.dc.z, r.dc.w};
+    const float rs = r.rs, nb = -r.mu * r.rs;
+    float xh[8], g[8];
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      g[j] = dy[j] * gm[j];
+      xh[j] = fmaf(zz[j], rs, nb);
+      const float dy = fmaf(dd[j], wg, bc[j]);
+      g[j] = dy * gm[j];
       s1 += g[j];
-      s2 += g[j] * xh[j];
-      dg[j] += dy[j] * xh[j];
-      db[j] += dy[j];
+      s2 = fmaf(g[j], xh[j], s2);
+      dg[j] = fmaf(dy, xh[j], dg[j]);
+      db[j] += dy;
     }
-    s1 = warp_sum(s1) * (1.f / DM);
-    s2 = warp_sum(s2) * (1.f / DM);
-    float o[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) o[j] = rs * (g[j] - s1 - xh[j] * s2);
+    for (int o = 16; o > 0; o >>= 1) {
+      s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+      s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+    }
+    const float c1 = -rs * s1 * (1.f / DM), c2 = -rs * s2 * (1.f / DM);
+    float o8[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o8[j] = fmaf(xh[j], c2, fmaf(g[j], rs, c1));
+    if (dz4) {
+      dz4[i * 64] = make_float4(o8[0], o8[1], o8[2], o8[3]);
+      dz4[i * 64 + 32] = make_float4(o8[4], o8[5], o8[6], o8[7]);
+    }
     if (GS) {
       float4* ga = reinterpret_cast<float4*>(&gsm[warp][lane * 4]);
       float4* gc = reinterpret_cast<float4*>(&gsm[warp][128 + lane * 4]);
       float4 ta = *ga, tc = *gc;
-      ta.x += o[0]; ta.y += o[1]; ta.z += o[2]; ta.w += o[3];
-      tc.x += o[4]; tc.y += o[5]; tc.z += o[6]; tc.w += o[7];
+      ta.x += o8[0]; ta.y += o8[1]; ta.z += o8[2]; ta.w += o8[3];
+      tc.x += o8[4]; tc.y += o8[5]; tc.z += o8[6]; tc.w += o8[7];
       *ga = ta; *gc = tc;
     }
-    if (dz4) {
-      dz4[lane] = make_float4(o[0], o[1], o[2], o[3]);
-      dz4[32 + lane] = make_float4(o[4], o[5], o[6], o[7]);
+    if (DROP) {   // the 16-bit copy flows on into fc / the attention output: masked and scaled; the fp32 dZ is not
+      float4 ma = make_float4(o8[0], o8[1], o8[2], o8[3]), mc = make_float4(o8[4], o8[5], o8[6], o8[7]);
+      drop_apply8(p.drop_seed, p.drop_thresh, p.drop_scale, (uint32_t)(wrow + i), lane, ma, mc);
+      o8[0] = ma.x; o8[1] = ma.y; o8[2] = ma.z; o8[3] = ma.w; o8[4] = mc.x; o8[5] = mc.y; o8[6] = mc.z; o8[7] = mc.w;
     }
-    if (p.drop_thresh) {
-      float4 ma = make_float4(o[0], o[1], o[2], o[3]), mc = make_float4(o[4], o[5], o[6], o[7]);
-      drop_apply8(p.drop_seed, p.drop_thresh, p.drop_scale, (uint32_t)row, lane, ma, mc);
-      o[0] = ma.x; o[1] = ma.y; o[2] = ma.z; o[3] = ma.w; o[4] = mc.x; o[5] = mc.y; o[6] = mc.z; o[7] = mc.w;
-    }
-    dz16[lane] = make_uint2(pack2(o[0], o[1], p.dtype), pack2(o[2], o[3], p.dtype));
-    dz16[32 + lane] = make_uint2(pack2(o[4], o[5], p.dtype), pack2(o[6], o[7], p.dtype));
+    dz16[i * 64] = make_uint2(pack2(o8[0], o8[1], p.dtype), pack2(o8[2], o8[3], p.dtype));
+    dz16[i * 64 + 32] = make_uint2(pack2(o8[4], o8[5], p.dtype), pack2(o8[6], o8[7], p.dtype));
   };
-  RowIn cur = load_row(0);
+  auto zero_row = [&](int i) {
+    if (dz4) {
+      const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+      dz4[i * 64] = zero; dz4[i * 64 + 32] = zero;
+    }
+    dz16[i * 64] = make_uint2(0u, 0u); dz16[i * 64 + 32] = make_uint2(0u, 0u);
+  };
+  if (nv == 64) {
+    // 7 of the 8 CTAs of a chunk: every row real.  The condition depends on blockIdx and kernel parameters only, so
+    // the branch is provably uniform (no warp-sync wrappers around the shuffles); fully unrolled, two rows in flight.
+    Row cur = load_row(0);
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    RowIn nxt;
-    if (i + 1 < 8) nxt = load_row(i + 1);
-    finish_row(cur, i);
-    if (i + 1 < 8) cur = nxt;
+    for (int i = 0; i < 8; ++i) {
+      Row nxt;
+      if (i + 1 < 8) nxt = load_row(i + 1);
+      finish_row(cur, i);
+      if (i + 1 < 8) cur = nxt;
+    }
+  } else {
+    // the chunk's tail (pad rows): one row at a time
+#pragma unroll 1
+    for (int i = 0; i < 8; ++i) {
+      if (i < nvw) finish_row(load_row(i), i);
+      else zero_row(i);
+    }
   }
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
@@ -519,7 +534,7 @@ __global__ void __launch_bounds__(256, MINB) ln_bwd_kernel(const LnBwdArgs p) {
   if (p.debug & 1) return;
   atomicAdd(p.dgamma + c, s);
   atomicAdd(p.dbeta + c, t);
-  if (GS) {   // the CTA's 64 rows lie inside one chunk (64 | group_rows); gsm is complete after the barrier above
+  if (GS) {   // gsm is complete after the barrier above
     float u = 0.f;
 #pragma unroll
     for (int w = 0; w < 8; ++w) u += gsm[w][c];
@@ -820,20 +835,21 @@ int csn_ln_bwd(const float* dY, const float* Z, const float* mean, const float* 
   CSN_CHECK_ARG(!chunk_gsum || group_rows % 64 == 0, "csn_ln_bwd: chunk_gsum needs group_rows to be a multiple of 64");
   CSN_CHECK_ARG(!bcast || bcast_idx, "csn_ln_bwd: bcast needs bcast_idx");
   CSN_CHECK_ARG(!src_idx || src_w, "csn_ln_bwd: src_idx needs src_w");
-  CSN_CHECK_ARG(rows % 64 == 0 && block_rows % 64 == 0, "csn_ln_bwd: rows and block_rows must be multiples of 64");
+  CSN_CHECK_ARG(rows % 64 == 0 && block_rows % 64 == 0 && group_rows % 64 == 0 && block_rows % group_rows == 0,
+                "csn_ln_bwd: rows, block_rows and group_rows must be multiples of 64, block_rows a multiple of group_rows");
   if (rows == 0) return 0;
   LnBwdArgs a{dY, Z, mean, rstd, gamma, dZ, dZ16, dgamma, dbeta, rows, group_rows, rows_valid, block_rows, dtype, amax, bcast, bcast_idx, bcast_scale, src_idx, src_w, getenv("CSN_LN_BWD_DEBUG") ? atoi(getenv("CSN_LN_BWD_DEBUG")) : 0, chunk_gsum,
               drop_seed, drop_thresh16(drop_p), drop_scale_of(drop_thresh16(drop_p))};
   CSN_CHECK_ARG(drop_p >= 0.f && drop_p < 1.f, "csn_ln_bwd: dropout probability outside [0, 1)");
   CSN_CHECK_ARG(!(chunk_gsum && drop_p > 0.f), "csn_ln_bwd: chunk_gsum (V centring) is not combined with dropout");
   static const int occ = getenv("CSN_LN_BWD_OCC") ? atoi(getenv("CSN_LN_BWD_OCC")) : 3;   // resident CTAs/SM (tuning knob)
-  if (chunk_gsum) {
-    if (occ >= 3) return launch_simple(ln_bwd_kernel<3, true>, dim3((unsigned)(rows / 64)), dim3(256), a, stream, "ln_bwd_kernel");
-    return launch_simple(ln_bwd_kernel<2, true>, dim3((unsigned)(rows / 64)), dim3(256), a, stream, "ln_bwd_kernel");
-  }
-  if (occ >= 4) return launch_simple(ln_bwd_kernel<4, false>, dim3((unsigned)(rows / 64)), dim3(256), a, stream, "ln_bwd_kernel");
-  if (occ >= 3) return launch_simple(ln_bwd_kernel<3, false>, dim3((unsigned)(rows / 64)), dim3(256), a, stream, "ln_bwd_kernel");
-  return launch_simple(ln_bwd_kernel<2, false>, dim3((unsigned)(rows / 64)), dim3(256), a, stream, "ln_bwd_kernel");
+  const dim3 grid((unsigned)(rows / 64)), block(256);
+  const bool drop = a.drop_thresh != 0;
+  if (chunk_gsum) return launch_simple(ln_bwd_kernel<3, true, false>, grid, block, a, stream, "ln_bwd_kernel");
+  if (drop) return launch_simple(ln_bwd_kernel<3, false, true>, grid, block, a, stream, "ln_bwd_kernel");
+  if (occ >= 4) return launch_simple(ln_bwd_kernel<4, false, false>, grid, block, a, stream, "ln_bwd_kernel");
+  if (occ >= 3) return launch_simple(ln_bwd_kernel<3, false, false>, grid, block, a, stream, "ln_bwd_kernel");
+  return launch_simple(ln_bwd_kernel<2, false, false>, grid, block, a, stream, "ln_bwd_kernel");
 }
 
 int csn_combine_fwd(const float* Y, const int32_t* blk, const float* w, float* out, void* rows16, int32_t n_b,
