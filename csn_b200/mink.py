@@ -323,3 +323,76 @@ def topk_neighbors(similarity: torch.Tensor, K: int, self_index=None) -> torch.T
         idx = _knn.topk_rows(s, K + 1)[1][0]
         idx = idx[idx != self_index]
     return idx
+
+
+# ------------------------------------------------------------------------------------------- sparse-tensor glue
+def split_by_batch(feats: torch.Tensor, batch_col: torch.Tensor, lens=None):
+    """`features_at(sparse_tensor, b)` (lib/utils.py:283-288) for EVERY batch index at once: the rows of `feats`
+    (sum L_b, C) whose batch column (`SparseTensor.C[:, 0]`) equals b, for b = 0 .. B-1, in row order.
+    The reference runs one boolean-mask gather per (item, tensor) — (2 + 2K) B of them per step (hrnet.py:378-410).
+    Here: one bincount (or the per-item voxel counts `lens` the data loader already has: no device sync at all) and,
+    when the rows are grouped by batch index — the layout MinkowskiEngine's batched coordinates have — zero-copy views;
+    otherwise one stable argsort + gather.  Returns (list of (L_b, C) tensors, lens, perm or None)."""
+    bc = batch_col.reshape(-1).to(torch.int64)
+    if lens is None:
+        lens = torch.bincount(bc).tolist()          # the only host sync (the reference's `C[-1, 0] + 1` is one too)
+    lens = [int(v) for v in lens]
+    grouped = bool((bc[1:] >= bc[:-1]).all()) if bc.numel() > 1 else True
+    perm = None
+    if not grouped:
+        perm = torch.argsort(bc, stable=True)
+        feats = feats.index_select(0, perm)
+    return list(torch.split(feats, lens, dim=0)), lens, perm
+
+
+def csa_head_sparse(head: "CSAHead", q_feats: torch.Tensor, q_batch: torch.Tensor, keys=None, lens=None, key_lens=None,
+                    return_ssa: bool = False) -> torch.Tensor:
+    """The CSA block of HRNetSimCSN.forward (hrnet.py:370-417) on the `.F` / `.C[:, 0]` pair of the backbone's
+    sparse tensors: q_feats (sum L_b, 256) with batch column q_batch; keys = list over the K neighbours of
+    (feats, batch column).  Returns the stacked CSA features (sum L_b, 256), item after item in batch order, exactly
+    the tensor the reference wraps into its output SparseTensor (:411-416).  One ragged batch of the kernels."""
+    q_list, _, _ = split_by_batch(q_feats, q_batch, lens)
+    k_lists = []
+    for i, (kf, kb) in enumerate(keys or []):
+        k_lists.append(split_by_batch(kf, kb, key_lens[i] if key_lens is not None else None)[0])
+    out = head(q_list, k_lists, return_ssa=return_ssa)
+    return torch.cat(out, dim=0)
+
+
+def construct_shape_graph(head: "CSAHead", query_shapes, key_shapes, K: int, is_same: bool, precision: str = "fp16",
+                          batch: int = 16):
+    """Neighbour selection of lib/csn_utils.py:46-100 (the `random_pairs=False` branch): SSA features of every query and
+    key shape, cosine-similarity retrieval measure for every (query, key) pair, top-K with self-exclusion.
+    query_shapes / key_shapes: lists of (L, 256) backbone features (the MinkowskiEngine backbone stays the
+    reference's).  The reference keeps the key SSA features in a CPU dict and re-uploads them for every pair
+    (:66-83); here they live in ONE GPU-resident store of unit-norm 16-bit rows (knn.ShapeStore) and all pairs are
+    scored by the tcgen05 retrieval kernel.  Returns [(q_idx, [neighbour indices])] like the reference."""
+    dt = _PRECISIONS[precision]
+
+    def ssa_store(shapes):
+        feats = []
+        with torch.no_grad():
+            for s0 in range(0, len(shapes), batch):
+                feats += [f.float().contiguous() for f in head.get_SSA(shapes[s0:s0 + batch])]
+        return _knn.build_store(feats, dt, eps=0.0)       # hrnet.py:472-490: rows divided by their raw norm
+
+    k_store = ssa_store(key_shapes)
+    q_store = k_store if is_same and query_shapes is key_shapes else ssa_store(query_shapes)
+    sim = _knn.scores_from_stores(q_store, k_store)      # (Sq, Sk)
+    Sq, Sk = sim.shape
+    if is_same:
+        # csn_utils.py:91-96: topk(K); if the query is among them, topk(K+1) without it.  Vectorised: take K+1, drop the
+        # query where present, keep the first K.
+        k1 = min(K + 1, Sk)
+        idx = _knn.topk_rows(sim.contiguous(), k1)[1]
+        self_col = torch.arange(Sq, device=sim.device).unsqueeze(1)
+        keep = idx != self_col
+        in_top_k = (~keep[:, :K]).any(dim=1, keepdim=True)            # the query is among its own top-K
+        pos = torch.arange(k1, device=sim.device).unsqueeze(0).expand(Sq, -1)
+        # rows where self is in the top-K: all non-self entries (K of them); otherwise the plain top-K
+        order = torch.where(in_top_k, torch.where(keep, pos, pos + k1), pos)
+        sel = torch.gather(idx, 1, order.argsort(dim=1, stable=True)[:, :K])
+    else:
+        sel = _knn.topk_rows(sim.contiguous(), min(K, Sk))[1]
+    sel = sel.cpu().tolist()
+    return [(q, sel[q]) for q in range(Sq)]

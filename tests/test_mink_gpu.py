@@ -163,3 +163,56 @@ def test_gradients_follow_autograd_identity_not_storage():
     q4 = q.clone().requires_grad_(True)
     (m(q4, q4, q4)[0] * gy).sum().backward()          # true self-attention: all three roles
     assert G.rel_err(q4.grad, q3.grad) > 1e-2
+
+
+def test_sparse_glue_split_by_batch_and_head():
+    """features_at for all items at once (lib/utils.py:283-288) and the CSA block fed with (.F, .C[:, 0]) pairs: grouped
+    rows give views, shuffled rows are gathered; the stacked output equals the per-item path."""
+    from csn_b200 import mink
+    gen = synth.gen(21)
+    lens = [150, 90, 260]
+    feats = torch.relu(torch.randn(sum(lens), 256, generator=gen)).cuda()
+    bcol = torch.cat([torch.full((n,), b) for b, n in enumerate(lens)]).cuda()
+    parts, got_lens, perm = mink.split_by_batch(feats, bcol)
+    assert got_lens == lens and perm is None
+    assert parts[1].data_ptr() == feats[150:].data_ptr()                      # a view, not a copy
+    for b in range(3):
+        assert torch.equal(parts[b], feats[bcol == b])                        # == features_at(sparse, b)
+    shuffle = torch.randperm(sum(lens), generator=gen).cuda()
+    parts2, _, perm2 = mink.split_by_batch(feats[shuffle], bcol[shuffle])
+    for b in range(3):
+        assert torch.equal(parts2[b], feats[shuffle][bcol[shuffle] == b])
+    parts3, _, _ = mink.split_by_batch(feats, bcol, lens=lens)               # lens from the loader: no device sync
+    assert all(torch.equal(a, b) for a, b in zip(parts, parts3))
+    head = mink.CSAHead(256, 4).cuda().eval()
+    head.load_state_dict(synth.mink_state(9, 4))
+    klens = [[120, 200, 64]]
+    kfeats = torch.relu(torch.randn(sum(klens[0]), 256, generator=gen)).cuda()
+    kcol = torch.cat([torch.full((n,), b) for b, n in enumerate(klens[0])]).cuda()
+    with torch.no_grad():
+        got = mink.csa_head_sparse(head, feats, bcol, [(kfeats, kcol)])
+        want = torch.cat(head(list(torch.split(feats, lens)), [list(torch.split(kfeats, klens[0]))]), dim=0)
+    assert got.shape == (sum(lens), 256) and G.rel_err(got, want) < 1e-5
+
+
+def test_construct_shape_graph_against_oracle():
+    """lib/csn_utils.py:46-100 with a GPU-resident key store: neighbour lists equal the oracle's pair-by-pair loop
+    (mink_cosine_similarity + mink_topk_neighbors), with and without self-exclusion."""
+    from csn_b200 import mink
+    from oracle import csa_oracle as O
+    h, K = 4, 2
+    head = mink.CSAHead(256, h).cuda().eval()
+    sd = synth.mink_state(13, h)
+    head.load_state_dict(sd)
+    gen = synth.gen(14)
+    protos = torch.randn(3, 256, generator=gen)
+    shapes = [torch.relu(protos[i % 3] + 0.7 * torch.randn(int(n), 256, generator=gen)) for i, n in enumerate([140, 90, 200, 77, 160, 128, 111])]
+    ssa = O.mink_ssa(shapes, sd, h)
+    sim = torch.stack([torch.stack([O.mink_cosine_similarity(a, b) for b in ssa]) for a in ssa])
+    dev_shapes = [s.cuda() for s in shapes]
+    got = mink.construct_shape_graph(head, dev_shapes, dev_shapes, K, is_same=True)
+    for q, nb in got:
+        assert nb == O.mink_topk_neighbors(sim[q], K, self_index=q).tolist(), (q, nb)
+    got2 = mink.construct_shape_graph(head, dev_shapes[:3], dev_shapes[3:], K, is_same=False)
+    for q, nb in got2:
+        assert nb == sim[q, 3:].topk(K).indices.tolist(), (q, nb)
