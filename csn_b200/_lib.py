@@ -194,6 +194,8 @@ _EXTRA_SIGNATURES: dict[str, list] = {
                             C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p],
     "csn_knn_band_patch": [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p,
                            C.c_int64, C.c_void_p],
+    "csn_compat_fwd": [C.c_void_p] * 5 + [C.c_int32, C.c_int32] + [C.c_void_p] * 7,
+    "csn_compat_bwd": [C.c_void_p] * 10 + [C.c_int32, C.c_int32] + [C.c_void_p] * 9,
     "csn_topk_rows": [C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p],
 }
 

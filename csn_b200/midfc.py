@@ -375,25 +375,26 @@ def _csa_forward_core(x, x_neighbors, wq, wk, wv, wo, gamma, beta, cq_w, cq_b, c
     a = E.attention_forward(Xh, Xf, groups, S, nblk, wq, wk, wv, wo, gamma, beta, geom, n_head,
                             want_colsum=not ssa_only, want_y=False, residual_cm=res_cm, colsum_blocks=S,
                             dropout_p=dropout_p, seed=seed, chunk_sum=xsum)
-    # ---- compatibility (csa_models.py:211-230): tiny (B*(K+1) x 256) glue, kept in torch
+    # ---- compatibility (csa_models.py:211-230): csn_compat_fwd
     if ssa_only:
         comp = torch.ones(B, 1, dtype=torch.float32, device=dev)
         glue = None
     else:
-        # fp64: the backward of this softmax subtracts nearly equal numbers (d comp of the K+1 attention outputs of one
-        # query differ in the 3rd-5th digit), and the tensors are tiny
-        pooled = a.colsum[:S].detach().double().requires_grad_(True)   # slot order (b,k)
-        loc = [t.detach().double().requires_grad_(True) for t in (cq_w, cq_b, ck_w, ck_b)]
-        with torch.enable_grad():
-            pv = pooled.view(B, K + 1, 256)
-            y_q = pv[:, 0]
-            y_stack = pv.transpose(0, 1).reshape((K + 1) * B, 256)   # rows [k=0: b..; k=1: b..; ...] (:213,220)
-            u_q = F.normalize(F.linear(y_q, loc[0], loc[1]), dim=-1)
-            u_k = F.normalize(F.linear(y_stack, loc[2], loc[3]), dim=-1)
-            u_k = u_k.view(B, -1, 256)                               # batch-interleaving view (:227)
-            comp_g = torch.softmax(torch.matmul(u_q.unsqueeze(1), u_k.permute(0, 2, 1)).squeeze(1), dim=-1)
-        comp = comp_g.detach().float()
-        glue = (pooled, loc, comp_g)
+        # csa_models.py:222-230 incl. the batch-interleaving view, fp64 inside (csrc/compat.cu): the backward
+        # of this softmax subtracts d comp values that agree in their first 3-5 digits, and the tensors are tiny
+        pooled = a.colsum[:S].contiguous()                              # slot order (b, k), fp32
+        K1 = K + 1
+        u_q = torch.empty(B, 256, dtype=torch.float64, device=dev)
+        u_k = torch.empty(S, 256, dtype=torch.float64, device=dev)
+        nrm = torch.empty(B + S, dtype=torch.float64, device=dev)
+        comp64 = torch.empty(B, K1, dtype=torch.float64, device=dev)
+        comp = torch.empty(B, K1, dtype=torch.float32, device=dev)
+        wts = tuple(t.detach().float().contiguous() for t in (cq_w, cq_b, ck_w, ck_b))
+        rc = L.lib().csn_compat_fwd(pooled.data_ptr(), wts[0].data_ptr(), wts[1].data_ptr(), wts[2].data_ptr(), wts[3].data_ptr(),
+                                    B, K1, u_q.data_ptr(), u_k.data_ptr(), nrm[:B].data_ptr(), nrm[B:].data_ptr(),
+                                    comp64.data_ptr(), comp.data_ptr(), L.stream_ptr())
+        L.check(rc, "csn_compat_fwd")
+        glue = (pooled, wts, u_q, u_k, nrm, comp64)
 
     def _blk_table():
         t = torch.empty(B, K + 1, dtype=torch.int32)
@@ -449,14 +450,24 @@ def _csa_backward_core(st: _CsaState, dOutT, amax, dcomp, need_dx: bool, out_sca
     grads_glue = [None] * 4
     dpool = None
     if st.glue is not None:
-        pooled, loc, comp_g = st.glue
-        dc = dcomp.view(B, K + 1).double()
-        if out_scale is not None:
-            dc = dc * out_scale.double()
-        gl = torch.autograd.grad(comp_g, [pooled] + loc, dc)
-        dpool = gl[0].float().contiguous()
-        grads_glue = [t.float() for t in gl[1:]]
-        amax = amax + dpool.abs().max() / geom.n_points   # bound on |dY + dpool/N| for the gradient scaling (comp <= 1)
+        pooled, wts, u_q, u_k, nrm, comp64 = st.glue
+        K1 = K + 1
+        dc = dcomp.reshape(-1)
+        if dc.dtype != torch.float64:
+            dc = dc.double()
+        dlin = torch.empty(B + S, 256, dtype=torch.float64, device=dev)
+        gW = torch.empty(2, 256, 256, dtype=torch.float32, device=dev)
+        gb = torch.empty(2, 256, dtype=torch.float32, device=dev)
+        dpool = torch.empty(S, 256, dtype=torch.float32, device=dev)
+        dp_amax = torch.zeros(1, dtype=torch.float32, device=dev)
+        rc = L.lib().csn_compat_bwd(pooled.data_ptr(), wts[0].data_ptr(), wts[2].data_ptr(), u_q.data_ptr(), u_k.data_ptr(),
+                                    nrm[:B].data_ptr(), nrm[B:].data_ptr(), comp64.data_ptr(), dc.data_ptr(),
+                                    out_scale.data_ptr() if out_scale is not None else None, B, K1,
+                                    dlin[:B].data_ptr(), dlin[B:].data_ptr(), gW[0].data_ptr(), gb[0].data_ptr(),
+                                    gW[1].data_ptr(), gb[1].data_ptr(), dpool.data_ptr(), dp_amax.data_ptr(), L.stream_ptr())
+        L.check(rc, "csn_compat_bwd")
+        grads_glue = [gW[0], gb[0], gW[1], gb[1]]
+        amax = amax + dp_amax / geom.n_points   # bound on |dY + dpool/N| for the gradient scaling (comp <= 1)
     # The upstream gradient of block j is comp[b,k] * dOut[b]^T (+ the pooled-mean row vector): csn_ln_bwd forms
     # cw[j] * dOutT[cb[j]] + dpool[pb[j]]/N on the fly; the (2K+1)x larger dY is never materialised.
     g = E.attention_backward(a, dOutT, need_dx, amax, bcast=dpool, bcast_idx=pb if dpool is not None else None,

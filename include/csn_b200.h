@@ -216,6 +216,21 @@ int csn_csa_head(const float* Z, const float* mean, const float* rstd, const flo
                  int32_t chunk, int32_t chunk_pad, int32_t rows_pad, float* loss_part, float* dOutT, float* amax,
                  double* dcomp, float* dW_part, float* dW, int32_t* stats, float* y_out, void* stream);
 
+/* Shape-compatibility glue (csa_models.py:222-230), forward and backward (csrc/compat.cu), fp64 inside:
+ *   u_q[b] = normalize(Wq pooled[b*K1] + bq),  u_k[r] = normalize(Wk y_stack[r] + bk) with the stacked rows
+ *   y_stack[r] = pooled[(r % B)*K1 + r / B] (rows ordered [k][b], :213,220) and the (B, K1, 256) VIEW of :227:
+ *   comp[b][k] = softmax_k(u_q[b] . u_k[b*K1 + k]).  pooled: fp32 [B*K1][256], slot (b, k) at row b*K1 + k.
+ * csn_compat_bwd: dcomp (fp64 [B*K1]) times the optional device scalar *gscale ->  d weights / biases (fp32), dpool
+ * (fp32 [B*K1][256], gradient of the pooled descriptors) and *dpool_amax = max |dpool| (optional, zero-initialised).
+ * u_q [B][256], u_k [B*K1][256], n_q [B], n_k [B*K1], comp64 [B*K1], dlin_q / dlin_k: fp64 scratch kept by the caller. */
+int csn_compat_fwd(const float* pooled, const float* Wq, const float* bq, const float* Wk, const float* bk, int32_t B,
+                   int32_t K1, double* u_q, double* u_k, double* n_q, double* n_k, double* comp64, float* comp,
+                   void* stream);
+int csn_compat_bwd(const float* pooled, const float* Wq, const float* Wk, const double* u_q, const double* u_k,
+                   const double* n_q, const double* n_k, const double* comp64, const double* dcomp, const float* gscale,
+                   int32_t B, int32_t K1, double* dlin_q, double* dlin_k, float* dWq, float* dbq, float* dWk, float* dbk,
+                   float* dpool, float* dpool_amax, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * HBM-bound pieces of the CSA/SSA layer.  Row buffers use "padded" coordinates: a shape's block has
  * rows_pad = n_chunks*chunk_pad rows; chunk c (points [c*chunk, (c+1)*chunk)) occupies rows

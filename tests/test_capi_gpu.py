@@ -160,3 +160,46 @@ def test_gemm_colbias_and_sgemm_small_through_the_c_abi():
     d4 = torch.full((100, 90), 2.0, device="cuda")
     E.sgemm_small(at2, bt2, d4, 100, 90, 700, b_rows=rows2, trans_a=True, trans_b=True, accumulate=True)
     assert torch.allclose(d4.double(), 2.0 + at2.double().t() @ bt2[rows2.long()].double(), atol=5e-4)
+
+
+@pytest.mark.parametrize("B,K", [(1, 1), (2, 2), (8, 3)])
+def test_compat_glue_kernels_against_torch_fp64(B, K):
+    """csn_compat_fwd / csn_compat_bwd (csa_models.py:222-230 incl. the batch-interleaving view) against the
+    same lines written with torch in fp64 + autograd."""
+    import torch.nn.functional as F
+    from csn_b200 import _lib as L
+    K1, S = K + 1, B * (K + 1)
+    g = synth.gen(100 + B)
+    pooled = torch.randn(S, 256, generator=g).cuda()
+    Wq, Wk = (torch.randn(256, 256, generator=g) * 0.06).cuda(), (torch.randn(256, 256, generator=g) * 0.06).cuda()
+    bq, bk = (torch.randn(256, generator=g) * 0.1).cuda(), (torch.randn(256, generator=g) * 0.1).cuda()
+    dcomp = torch.randn(S, generator=g).double().cuda()
+    gs = torch.tensor([1.7]).cuda()
+    u_q = torch.empty(B, 256, dtype=torch.float64, device="cuda"); u_k = torch.empty(S, 256, dtype=torch.float64, device="cuda")
+    nrm = torch.empty(B + S, dtype=torch.float64, device="cuda")
+    comp64 = torch.empty(B, K1, dtype=torch.float64, device="cuda"); comp = torch.empty(B, K1, device="cuda")
+    rc = L.lib().csn_compat_fwd(pooled.data_ptr(), Wq.data_ptr(), bq.data_ptr(), Wk.data_ptr(), bk.data_ptr(), B, K1, u_q.data_ptr(),
+                                u_k.data_ptr(), nrm[:B].data_ptr(), nrm[B:].data_ptr(), comp64.data_ptr(), comp.data_ptr(), L.stream_ptr())
+    L.check(rc, "csn_compat_fwd")
+    dlin = torch.empty(B + S, 256, dtype=torch.float64, device="cuda")
+    gW = torch.empty(2, 256, 256, device="cuda"); gb = torch.empty(2, 256, device="cuda")
+    dpool = torch.empty(S, 256, device="cuda"); amax = torch.zeros(1, device="cuda")
+    rc = L.lib().csn_compat_bwd(pooled.data_ptr(), Wq.data_ptr(), Wk.data_ptr(), u_q.data_ptr(), u_k.data_ptr(), nrm[:B].data_ptr(),
+                                nrm[B:].data_ptr(), comp64.data_ptr(), dcomp.data_ptr(), gs.data_ptr(), B, K1, dlin[:B].data_ptr(),
+                                dlin[B:].data_ptr(), gW[0].data_ptr(), gb[0].data_ptr(), gW[1].data_ptr(), gb[1].data_ptr(),
+                                dpool.data_ptr(), amax.data_ptr(), L.stream_ptr())
+    L.check(rc, "csn_compat_bwd")
+    # reference lines, fp64
+    p64 = pooled.double().requires_grad_(True)
+    w = [t.double().requires_grad_(True) for t in (Wq, bq, Wk, bk)]
+    pv = p64.view(B, K1, 256)
+    y_q = pv[:, 0]
+    y_stack = pv.transpose(0, 1).reshape(K1 * B, 256)                    # [k = 0: b..; k = 1: b..] (:213,220)
+    uq = F.normalize(F.linear(y_q, w[0], w[1]), dim=-1)
+    uk = F.normalize(F.linear(y_stack, w[2], w[3]), dim=-1).view(B, -1, 256)   # the view of :227
+    want = torch.softmax(torch.matmul(uq.unsqueeze(1), uk.permute(0, 2, 1)).squeeze(1), dim=-1)
+    want.backward(dcomp.view(B, K1) * 1.7)
+    assert (comp64 - want.detach()).abs().max() < 1e-12 and (comp.double() - want.detach()).abs().max() < 1e-6
+    for got, ref in ((gW[0], w[0].grad), (gb[0], w[1].grad), (gW[1], w[2].grad), (gb[1], w[3].grad), (dpool, p64.grad)):
+        assert (got.double() - ref).norm() <= 1e-6 * ref.norm() + 1e-12
+    assert abs(amax.item() - p64.grad.abs().max().item()) <= 1e-6 * p64.grad.abs().max().item()
