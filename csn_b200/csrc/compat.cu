@@ -40,13 +40,22 @@ __global__ void __launch_bounds__(256) compat_linear_kernel(const float* __restr
   const float* bias = is_q ? bq : bk;
   y[tid] = (double)__ldg(pooled + (long long)slot * CD + tid);
   __syncthreads();
-  for (int o = warp * 32; o < warp * 32 + 32; ++o) {
-    const float* w = W + (long long)o * CD;
-    double s = 0.0;
+  double yv[CD / 32];
 #pragma unroll
-    for (int i = 0; i < CD / 32; ++i) s += (double)__ldg(w + lane + 32 * i) * y[lane + 32 * i];
-    s = warp_sum_d(s);
-    if (lane == 0) lin[o] = s + (double)__ldg(bias + o);
+  for (int i = 0; i < CD / 32; ++i) yv[i] = y[lane + 32 * i];
+  for (int o0 = warp * 32; o0 < warp * 32 + 32; o0 += 4) {   // four outputs in flight: independent load / FMA / shuffle chains
+    double s[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float* w = W + (long long)(o0 + j) * CD;
+#pragma unroll
+      for (int i = 0; i < CD / 32; ++i) s[j] += (double)__ldg(w + lane + 32 * i) * yv[i];
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) s[j] += __shfl_xor_sync(0xffffffffu, s[j], o);
+    if (lane < 4) lin[o0 + lane] = (lane == 0 ? s[0] : lane == 1 ? s[1] : lane == 2 ? s[2] : s[3]) + (double)__ldg(bias + o0 + lane);
   }
   __syncthreads();
   double sq = warp_sum_d(lin[tid] * lin[tid]);
@@ -138,11 +147,13 @@ __global__ void __launch_bounds__(256) compat_bwd_w_kernel(const float* __restri
                                                           float* __restrict__ dWk, float* __restrict__ dbk) {
   const int o = blockIdx.x, i = threadIdx.x, S = B * K1;
   double sq = 0.0, sk = 0.0, bq = 0.0, bk = 0.0;
+#pragma unroll 4
   for (int b = 0; b < B; ++b) {
     const double d = dlin_q[(long long)b * CD + o];
     sq += d * (double)__ldg(pooled + (long long)(b * K1) * CD + i);
     bq += d;
   }
+#pragma unroll 8
   for (int r = 0; r < S; ++r) {
     const double d = dlin_k[(long long)r * CD + o];
     sk += d * (double)__ldg(pooled + (long long)stack_slot(r, B, K1) * CD + i);
@@ -166,10 +177,20 @@ __global__ void __launch_bounds__(256) compat_bwd_pool_kernel(const float* __res
   dk[i] = dlin_k[(long long)r * CD + i];
   dq[i] = k == 0 ? dlin_q[(long long)b * CD + i] : 0.0;
   __syncthreads();
-  double s = 0.0;
-  for (int o = 0; o < CD; ++o) s += (double)__ldg(Wk + (long long)o * CD + i) * dk[o];
-  if (k == 0)
-    for (int o = 0; o < CD; ++o) s += (double)__ldg(Wq + (long long)o * CD + i) * dq[o];
+  double acc[4] = {0.0, 0.0, 0.0, 0.0};   // independent chains: 16 weight loads in flight per thread
+#pragma unroll 4
+  for (int o = 0; o < CD; o += 4) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[j] += (double)__ldg(Wk + (long long)(o + j) * CD + i) * dk[o + j];
+  }
+  if (k == 0) {
+#pragma unroll 4
+    for (int o = 0; o < CD; o += 4) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[j] += (double)__ldg(Wq + (long long)(o + j) * CD + i) * dq[o + j];
+    }
+  }
+  const double s = (acc[0] + acc[1]) + (acc[2] + acc[3]);
   dpool[(long long)slot * CD + i] = (float)s;
   if (dpool_amax) {
     float m = warp_max(fabsf((float)s));

@@ -377,9 +377,14 @@ __global__ void __launch_bounds__(256, (R == 8 && CMAX == 16 && NK <= 4) ? 2 : 1
 // dW[c][ch] = scale * sum_i part[i][c][ch]   (fixed order: deterministic)
 __global__ void head_dw_reduce_kernel(const float* __restrict__ part, float* __restrict__ out, int n_part, int C) {
   const int c = blockIdx.x, ch = threadIdx.x;
-  float s = 0.f;
-  for (int i = 0; i < n_part; ++i) s += part[((long long)i * C + c) * HD_DM + ch];
-  out[c * HD_DM + ch] = s;
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};   // eight independent chains (the loads are what costs)
+  int i = 0;
+  for (; i + 8 <= n_part; i += 8) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] += __ldg(part + ((long long)(i + j) * C + c) * HD_DM + ch);
+  }
+  for (; i < n_part; ++i) acc[0] += __ldg(part + ((long long)i * C + c) * HD_DM + ch);
+  out[c * HD_DM + ch] = ((acc[0] + acc[1]) + (acc[2] + acc[3])) + ((acc[4] + acc[5]) + (acc[6] + acc[7]));
 }
 
 __global__ void head_count_valid_kernel(const long long* __restrict__ labels, long long lab_stride, int n_b, int n_points,
