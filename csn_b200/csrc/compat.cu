@@ -198,7 +198,33 @@ __global__ void __launch_bounds__(256) compat_bwd_pool_kernel(const float* __res
   }
 }
 
+// the per-block fan-out weights and the bound of the upstream gradient that csn_ln_bwd needs, in one launch:
+//   cw[j] = comp[cw_index[j]] * gscale   (0 when cw_index[j] < 0),   amax_out = amax_in * |gscale| + dpool_amax / n_points
+__global__ void compat_fanout_kernel(const float* __restrict__ comp, const int* __restrict__ cw_index, int n_blocks,
+                                     const float* __restrict__ gscale, const float* __restrict__ amax_in,
+                                     const float* __restrict__ dpool_amax, float inv_points, float* __restrict__ cw,
+                                     float* __restrict__ amax_out) {
+  const float gs = gscale ? __ldg(gscale) : 1.f;
+  for (int j = threadIdx.x; j < n_blocks; j += blockDim.x) {
+    const int ci = __ldg(cw_index + j);
+    cw[j] = ci >= 0 ? __ldg(comp + ci) * gs : 0.f;
+  }
+  if (threadIdx.x == 0) amax_out[0] = __ldg(amax_in) * fabsf(gs) + (dpool_amax ? __ldg(dpool_amax) * inv_points : 0.f);
+}
+
 }  // namespace csn
+
+extern "C" int csn_compat_fanout(const float* comp, const int32_t* cw_index, int32_t n_blocks, const float* gscale,
+                                 const float* amax_in, const float* dpool_amax, float inv_points, float* cw, float* amax_out,
+                                 void* stream) {
+  using namespace csn;
+  clear_error();
+  CSN_CHECK_ARG(comp && cw_index && amax_in && cw && amax_out, "csn_compat_fanout: null pointer");
+  compat_fanout_kernel<<<1, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(comp, cw_index, n_blocks, gscale, amax_in, dpool_amax,
+                                                                              inv_points, cw, amax_out);
+  CSN_LAUNCH_OK("compat_fanout_kernel");
+  return 0;
+}
 
 extern "C" int csn_compat_fwd(const float* pooled, const float* Wq, const float* bq, const float* Wk, const float* bk,
                               int32_t B, int32_t K1, double* u_q, double* u_k, double* n_q, double* n_k, double* comp64,

@@ -727,6 +727,13 @@ __global__ void __launch_bounds__(256) block_dot_kernel(const BlockDotArgs p) {
   }
 }
 
+// x[i] *= 1 / 2^floor(log2(128 / amax)): undoes the power-of-two loss scaling csn_ln_bwd applied (same formula), for
+// the flat buffer that holds every parameter gradient of a step (one launch instead of one per tensor)
+__global__ void grad_unscale_kernel(float* __restrict__ x, long long n, const float* __restrict__ amax) {
+  const float inv = 1.f / exp2f(floorf(log2f(128.f / fmaxf(__ldg(amax), 1e-30f))));
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) x[i] *= inv;
+}
+
 template <typename K, typename A>
 static int launch_simple(K kern, dim3 grid, dim3 block, const A& args, void* stream, const char* name) {
   kern<<<grid, block, 0, (cudaStream_t)stream>>>(args);
@@ -850,6 +857,17 @@ int csn_ln_bwd(const float* dY, const float* Z, const float* mean, const float* 
   if (occ >= 4) return launch_simple(ln_bwd_kernel<4, false, false>, grid, block, a, stream, "ln_bwd_kernel");
   if (occ >= 3) return launch_simple(ln_bwd_kernel<3, false, false>, grid, block, a, stream, "ln_bwd_kernel");
   return launch_simple(ln_bwd_kernel<2, false, false>, grid, block, a, stream, "ln_bwd_kernel");
+}
+
+int csn_grad_unscale(float* x, int64_t n, const float* amax, void* stream) {
+  using namespace csn;
+  clear_error();
+  CSN_CHECK_ARG(x && amax, "csn_grad_unscale: null pointer");
+  if (n == 0) return 0;
+  const unsigned grid = (unsigned)((n + 1023) / 1024 < 592 ? (n + 1023) / 1024 : 592);
+  grad_unscale_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, n, amax);
+  CSN_LAUNCH_OK("grad_unscale_kernel");
+  return 0;
 }
 
 int csn_combine_fwd(const float* Y, const int32_t* blk, const float* w, float* out, void* rows16, int32_t n_b,

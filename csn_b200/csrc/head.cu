@@ -387,6 +387,15 @@ __global__ void head_dw_reduce_kernel(const float* __restrict__ part, float* __r
   out[c * HD_DM + ch] = ((acc[0] + acc[1]) + (acc[2] + acc[3])) + ((acc[4] + acc[5]) + (acc[6] + acc[7]));
 }
 
+// loss = (sum of the per-CTA partial sums, fixed order) / max(n_valid, 1)
+__global__ void head_loss_kernel(const float* __restrict__ loss_part, int n_part, const int* __restrict__ n_valid,
+                                 float* __restrict__ loss) {
+  float s = 0.f;
+  for (int i = threadIdx.x; i < n_part; i += 32) s += loss_part[i];
+  s = warp_sum(s);
+  if (threadIdx.x == 0) loss[0] = s / (float)max(__ldg(n_valid), 1);
+}
+
 __global__ void head_count_valid_kernel(const long long* __restrict__ labels, long long lab_stride, int n_b, int n_points,
                                         int ignore_index, int* __restrict__ count) {
   int c = 0;
@@ -449,7 +458,7 @@ extern "C" int csn_csa_head(const float* Z, const float* mean, const float* rstd
                             const int64_t* labels, int64_t lab_stride, int32_t ignore_index, int32_t* n_valid,
                             int32_t n_points, int32_t chunk, int32_t chunk_pad, int32_t rows_pad, float* loss_part,
                             float* dOutT, float* amax, double* dcomp, float* dW_part, float* dW, int32_t* stats, float* y_out,
-                            void* stream) {
+                            float* loss, void* stream) {
   using namespace csn;
   clear_error();
   CSN_CHECK_ARG(Z && mean && rstd && gamma && beta && blk && w && W && labels && n_valid && loss_part && stats,
@@ -473,6 +482,10 @@ extern "C" int csn_csa_head(const float* Z, const float* mean, const float* rstd
   else if (n_classes <= 32) rc = launch_head<32>(a, n_b, grid_cap, s);
   else rc = launch_head<64>(a, n_b, grid_cap, s);
   if (rc) return rc;
+  if (loss) {   // (loss_part is zero-initialised by the caller: entries beyond the launched grid do not contribute)
+    head_loss_kernel<<<1, 32, 0, s>>>(loss_part, csn_csa_head_grid(n_b, rows_pad), n_valid, loss);
+    CSN_LAUNCH_OK("head_loss_kernel");
+  }
   if (dOutT) {
     // the grid the launch used (mirrors launch_head): two CTAs per SM for <= 16 classes and n_k <= 4
     const int tiles = n_b * (rows_pad / 8);

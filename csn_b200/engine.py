@@ -466,12 +466,13 @@ def attention_backward(ctx: AttnContext, dY: torch.Tensor, need_dx: bool, amax: 
     #     itself is applied inside csn_ln_bwd when dY is loaded.
     if amax is None:
         amax = dY.abs().max().reshape(1)
-    inv_scale = 1.0 / torch.exp2(torch.floor(torch.log2(128.0 / amax.clamp_min(1e-30))))
+    # every parameter gradient of the step lives in ONE zero-initialised flat buffer (one fill, one csn_grad_unscale):
+    # [dgamma 256 | dbeta 256 | dWo 256*HD | dWqkv 3*HD*256]
+    gflat = torch.zeros(512 + 4 * HD * 256, dtype=torch.float32, device=dev)
     # --- LayerNorm backward
     dZ = torch.empty_like(ctx.Z) if need_dx else None
     dZ16 = torch.empty(nblk * NP, 256, dtype=dt, device=dev)
-    dgamma = torch.zeros(256, dtype=torch.float32, device=dev)
-    dbeta = torch.zeros(256, dtype=torch.float32, device=dev)
+    dgamma, dbeta = gflat[:256], gflat[256:512]
     center = ctx.extra.get("center")
     drop = ctx.extra.get("drop", (0.0, 0, 0))
     gsum = torch.zeros(nblk * NC, 256, dtype=torch.float32, device=dev) if center is not None else None
@@ -486,7 +487,7 @@ def attention_backward(ctx: AttnContext, dY: torch.Tensor, need_dx: bool, amax: 
     L.check(rc, "csn_ln_bwd")
     split = _pick_split(2 * ((HD + 255) // 256), nblk * NP // 64)
     # --- dWo = dZ^T O  (contraction over all rows; both operands consumed MN-major)
-    dWo = torch.zeros(256, HD, dtype=torch.float32, device=dev)
+    dWo = gflat[512:512 + 256 * HD].view(256, HD)
     L.gemm(L.mat(dZ16, L.MAJOR_MN), L.mat(ctx.O, L.MAJOR_MN), L.out(dWo, HD, accumulate=True), 256, HD, nblk * NP,
            split_k=split)
     if center is not None:   # ctx.O holds O' = O - c: d fc.weight += sum over chunks of (sum_rows dZ)^T c
@@ -555,7 +556,7 @@ def attention_backward(ctx: AttnContext, dY: torch.Tensor, need_dx: bool, amax: 
         _attention_backward_materialised(ctx, dO, dQKV)
     # --- projection weight gradients: dW = sum_blocks dProj^T X[slot]  (contraction over points, both
     #     operands consumed MN-major; split-K sized for ~2 waves of CTAs, fp32 atomics into dWqkv)
-    dWqkv = torch.zeros(3 * HD, 256, dtype=torch.float32, device=dev)
+    dWqkv = gflat[512 + 256 * HD:].view(3 * HD, 256)
     Xh = ctx.Xh
     for g in ctx.groups:
         same = (g.q0, g.q_si, g.q_so) == (g.k0, g.k_si, g.k_so) == (g.v0, g.v_si, g.v_so)
@@ -603,6 +604,10 @@ def attention_backward(ctx: AttnContext, dY: torch.Tensor, need_dx: bool, amax: 
         dZ3 = dZ.view(nblk, NP, 256)
         dX3.index_add_(0, ctx.res_block.long(), dZ3)
         grads["dX"] = dX
-    for t in grads.values():
-        t.mul_(inv_scale)
+    rc = lib.csn_grad_unscale(gflat.data_ptr(), gflat.numel(), amax.data_ptr(), L.stream_ptr())
+    L.check(rc, "csn_grad_unscale")
+    for key in ("dX", "dXv"):
+        if key in grads:
+            rc = lib.csn_grad_unscale(grads[key].data_ptr(), grads[key].numel(), amax.data_ptr(), L.stream_ptr())
+            L.check(rc, "csn_grad_unscale")
     return grads

@@ -443,10 +443,6 @@ def _csa_backward_core(st: _CsaState, dOutT, amax, dcomp, need_dx: bool, out_sca
     B, K, S, nblk, n_src, n_src_nb = st.meta
     dev = dOutT.device
     cb, cwi, pb, gidx = _csa_bwd_tables(st, dev)
-    cw = st.comp.reshape(-1)[gidx].contiguous()
-    if out_scale is not None:
-        cw = cw * out_scale
-        amax = amax * out_scale.abs()
     grads_glue = [None] * 4
     dpool = None
     if st.glue is not None:
@@ -467,7 +463,14 @@ def _csa_backward_core(st: _CsaState, dOutT, amax, dcomp, need_dx: bool, out_sca
                                     gW[1].data_ptr(), gb[1].data_ptr(), dpool.data_ptr(), dp_amax.data_ptr(), L.stream_ptr())
         L.check(rc, "csn_compat_bwd")
         grads_glue = [gW[0], gb[0], gW[1], gb[1]]
-        amax = amax + dp_amax / geom.n_points   # bound on |dY + dpool/N| for the gradient scaling (comp <= 1)
+    # per-block fan-out weights cw[j] = comp[b,k] * d loss, and the bound on |dY + dpool/N| for the gradient scaling
+    cw = torch.empty(nblk, dtype=torch.float32, device=dev)
+    amax_b = torch.empty(1, dtype=torch.float32, device=dev)
+    rc = L.lib().csn_compat_fanout(st.comp.data_ptr(), cwi.data_ptr(), nblk, out_scale.data_ptr() if out_scale is not None else None,
+                                   amax.data_ptr(), dp_amax.data_ptr() if st.glue is not None else None, 1.0 / geom.n_points,
+                                   cw.data_ptr(), amax_b.data_ptr(), L.stream_ptr())
+    L.check(rc, "csn_compat_fanout")
+    amax = amax_b
     # The upstream gradient of block j is comp[b,k] * dOut[b]^T (+ the pooled-mean row vector): csn_ln_bwd forms
     # cw[j] * dOutT[cb[j]] + dpool[pb[j]]/N on the fly; the (2K+1)x larger dY is never materialised.
     g = E.attention_backward(a, dOutT, need_dx, amax, bcast=dpool, bcast_idx=pb if dpool is not None else None,
@@ -575,9 +578,9 @@ class _CsaLossFn(torch.autograd.Function):
         grid = lib.csn_csa_head_grid(B, NP)   # one persistent CTA per SM: per-CTA partial sums
         # zero-initialised scratch: [n_valid | stats (3C+2)], [amax | loss partials], d comp (fp64)
         ints = torch.zeros(1 + 3 * Cn + 2, dtype=torch.int32, device=dev)
-        flts = torch.zeros(1 + grid, dtype=torch.float32, device=dev)
+        flts = torch.zeros(2 + grid, dtype=torch.float32, device=dev)
         n_valid, stats = ints[:1], ints[1:]
-        amax, loss_part = flts[:1], flts[1:]
+        amax, loss_buf, loss_part = flts[:1], flts[1:2], flts[2:]
         dcomp = torch.zeros(B * (K + 1), dtype=torch.float64, device=dev)
         dOutT = torch.empty(B * NP, 256, dtype=torch.float32, device=dev) if want_grad else None
         dW_part = torch.empty(grid, Cn, 256, dtype=torch.float32, device=dev) if want_grad else None
@@ -590,9 +593,9 @@ class _CsaLossFn(torch.autograd.Function):
                               amax.data_ptr() if want_grad else None,
                               dcomp.data_ptr() if (want_grad and has_glue) else None,
                               dW_part.data_ptr() if want_grad else None, dW.data_ptr() if want_grad else None,
-                              stats.data_ptr(), None, L.stream_ptr())
+                              stats.data_ptr(), None, loss_buf.data_ptr(), L.stream_ptr())
         L.check(rc, "csn_csa_head")
-        loss = loss_part.sum() / n_valid.clamp_min(1).to(torch.float32)[0]
+        loss = loss_buf[0]
         ctx.st = st
         ctx.saved = (dOutT, amax, dcomp if has_glue else None, dW, logit_w.shape)
         ctx.mark_non_differentiable(stats)

@@ -208,13 +208,13 @@ int csn_seg_loss(const float* feat, int64_t b_stride, int64_t ch_stride, int32_t
  * (one partial sum per persistent CTA) whose sum divided by *n_valid is the loss.  y_out (optional): the combined features as padded rows.  labels: int64,
  * (b, point n) at labels[b*lab_stride + n]; n_k <= 6; n_classes <= 64.
  * Replaces csn_combine_fwd + the ATen conv/log-softmax/nll kernels and their backwards + csn_pack_rows(dOut) +
- * csn_block_dot. */
+ * csn_block_dot.  loss (optional, 1 float): receives sum(loss_part) / max(*n_valid, 1). */
 int csn_csa_head_grid(int32_t n_b, int32_t rows_pad);
 int csn_csa_head(const float* Z, const float* mean, const float* rstd, const float* gamma, const float* beta,
                  const int32_t* blk, const float* w, int32_t n_b, int32_t n_k, const float* W, int32_t n_classes,
                  const int64_t* labels, int64_t lab_stride, int32_t ignore_index, int32_t* n_valid, int32_t n_points,
                  int32_t chunk, int32_t chunk_pad, int32_t rows_pad, float* loss_part, float* dOutT, float* amax,
-                 double* dcomp, float* dW_part, float* dW, int32_t* stats, float* y_out, void* stream);
+                 double* dcomp, float* dW_part, float* dW, int32_t* stats, float* y_out, float* loss, void* stream);
 
 /* Shape-compatibility glue (csa_models.py:222-230), forward and backward (csrc/compat.cu), fp64 inside:
  *   u_q[b] = normalize(Wq pooled[b*K1] + bq),  u_k[r] = normalize(Wk y_stack[r] + bk) with the stacked rows
@@ -226,6 +226,12 @@ int csn_csa_head(const float* Z, const float* mean, const float* rstd, const flo
 int csn_compat_fwd(const float* pooled, const float* Wq, const float* bq, const float* Wk, const float* bk, int32_t B,
                    int32_t K1, double* u_q, double* u_k, double* n_q, double* n_k, double* comp64, float* comp,
                    void* stream);
+/* cw[j] = comp[cw_index[j]] * *gscale (0 for cw_index[j] < 0): the per-block fan-out weights csn_ln_bwd takes as src_w;
+ * *amax_out = *amax_in * |*gscale| + *dpool_amax * inv_points: the bound of the upstream gradient it scales by.
+ * gscale / dpool_amax may be NULL (1 / 0). */
+int csn_compat_fanout(const float* comp, const int32_t* cw_index, int32_t n_blocks, const float* gscale,
+                      const float* amax_in, const float* dpool_amax, float inv_points, float* cw, float* amax_out,
+                      void* stream);
 int csn_compat_bwd(const float* pooled, const float* Wq, const float* Wk, const double* u_q, const double* u_k,
                    const double* n_q, const double* n_k, const double* comp64, const double* dcomp, const float* gscale,
                    int32_t B, int32_t K1, double* dlin_q, double* dlin_k, float* dWq, float* dbq, float* dWk, float* dbk,
@@ -336,6 +342,10 @@ int csn_ln_bwd(const float* dY, const float* Z, const float* mean, const float* 
                int32_t group_rows, int32_t rows_valid, int32_t dtype, const float* amax, const float* bcast,
                const int32_t* bcast_idx, float bcast_scale, const int32_t* src_idx, const float* src_w,
                float* chunk_gsum, uint32_t drop_seed, float drop_p, void* stream);
+
+/* x[i] *= 1 / 2^floor(log2(128 / *amax)), i < n: undoes csn_ln_bwd's power-of-two scaling on the flat buffer that holds
+ * every parameter gradient of a step. */
+int csn_grad_unscale(float* x, int64_t n, const float* amax, void* stream);
 
 /* out[b][c][n] = sum_k w[b*n_k+k] * Y[blk[b*n_k+k]][padrow(n)][c]: the compatibility-weighted sum
  * of the self- and cross-attention outputs written back channel-major (csa_models.py:232-240);
