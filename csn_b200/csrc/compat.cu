@@ -40,22 +40,31 @@ __global__ void __launch_bounds__(256) compat_linear_kernel(const float* __restr
   const float* bias = is_q ? bq : bk;
   y[tid] = (double)__ldg(pooled + (long long)slot * CD + tid);
   __syncthreads();
-  double yv[CD / 32];
+  // the 256-long dot products run in fp32 (operands are fp32; the cancellation this file guards against sits in the
+  // softmax backward, not here); eight outputs in flight per warp: independent load / FMA / shuffle chains
+  float yv[CD / 32];
 #pragma unroll
-  for (int i = 0; i < CD / 32; ++i) yv[i] = y[lane + 32 * i];
-  for (int o0 = warp * 32; o0 < warp * 32 + 32; o0 += 4) {   // four outputs in flight: independent load / FMA / shuffle chains
-    double s[4] = {0.0, 0.0, 0.0, 0.0};
+  for (int i = 0; i < CD / 32; ++i) yv[i] = (float)y[lane + 32 * i];
+  for (int o0 = warp * 32; o0 < warp * 32 + 32; o0 += 8) {
+    float s[8];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
+    for (int j = 0; j < 8; ++j) {
       const float* w = W + (long long)(o0 + j) * CD;
+      float a = 0.f;
 #pragma unroll
-      for (int i = 0; i < CD / 32; ++i) s[j] += (double)__ldg(w + lane + 32 * i) * yv[i];
+      for (int i = 0; i < CD / 32; ++i) a = fmaf(__ldg(w + lane + 32 * i), yv[i], a);
+      s[j] = a;
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1)
 #pragma unroll
-      for (int j = 0; j < 4; ++j) s[j] += __shfl_xor_sync(0xffffffffu, s[j], o);
-    if (lane < 4) lin[o0 + lane] = (lane == 0 ? s[0] : lane == 1 ? s[1] : lane == 2 ? s[2] : s[3]) + (double)__ldg(bias + o0 + lane);
+      for (int j = 0; j < 8; ++j) s[j] += __shfl_xor_sync(0xffffffffu, s[j], o);
+    if (lane < 8) {
+      float v = s[0];
+#pragma unroll
+      for (int j = 1; j < 8; ++j) v = lane == j ? s[j] : v;
+      lin[o0 + lane] = (double)v + (double)__ldg(bias + o0 + lane);
+    }
   }
   __syncthreads();
   double sq = warp_sum_d(lin[tid] * lin[tid]);
@@ -146,22 +155,21 @@ __global__ void __launch_bounds__(256) compat_bwd_w_kernel(const float* __restri
                                                           float* __restrict__ dWq, float* __restrict__ dbq,
                                                           float* __restrict__ dWk, float* __restrict__ dbk) {
   const int o = blockIdx.x, i = threadIdx.x, S = B * K1;
-  double sq = 0.0, sk = 0.0, bq = 0.0, bk = 0.0;
-#pragma unroll 4
+  float sq[2] = {0.f, 0.f}, sk[4] = {0.f, 0.f, 0.f, 0.f}, bq = 0.f, bk = 0.f;   // fp32: plain outer-product sums
   for (int b = 0; b < B; ++b) {
-    const double d = dlin_q[(long long)b * CD + o];
-    sq += d * (double)__ldg(pooled + (long long)(b * K1) * CD + i);
+    const float d = (float)dlin_q[(long long)b * CD + o];
+    sq[b & 1] = fmaf(d, __ldg(pooled + (long long)(b * K1) * CD + i), sq[b & 1]);
     bq += d;
   }
-#pragma unroll 8
+#pragma unroll 4
   for (int r = 0; r < S; ++r) {
-    const double d = dlin_k[(long long)r * CD + o];
-    sk += d * (double)__ldg(pooled + (long long)stack_slot(r, B, K1) * CD + i);
+    const float d = (float)dlin_k[(long long)r * CD + o];
+    sk[r & 3] = fmaf(d, __ldg(pooled + (long long)stack_slot(r, B, K1) * CD + i), sk[r & 3]);
     bk += d;
   }
-  dWq[(long long)o * CD + i] = (float)sq;
-  dWk[(long long)o * CD + i] = (float)sk;
-  if (i == 0) { dbq[o] = (float)bq; dbk[o] = (float)bk; }
+  dWq[(long long)o * CD + i] = sq[0] + sq[1];
+  dWk[(long long)o * CD + i] = (sk[0] + sk[1]) + (sk[2] + sk[3]);
+  if (i == 0) { dbq[o] = bq; dbk[o] = bk; }
 }
 
 // grid = S CTAs (pooled slot) x 256 threads (input channel i): dpool[slot][i] = sum_o Wk[o][i] dlin_k[r(slot)][o]
@@ -169,32 +177,39 @@ __global__ void __launch_bounds__(256) compat_bwd_w_kernel(const float* __restri
 __global__ void __launch_bounds__(256) compat_bwd_pool_kernel(const float* __restrict__ Wq, const float* __restrict__ Wk,
                                                              const double* __restrict__ dlin_q, const double* __restrict__ dlin_k,
                                                              int B, int K1, float* __restrict__ dpool, float* __restrict__ dpool_amax) {
-  __shared__ double dk[CD];
-  __shared__ double dq[CD];
-  const int slot = blockIdx.x, i = threadIdx.x, lane = i & 31;
+  // grid = (S slots, 4 column quarters); thread = (input channel i = 64*blockIdx.y + tid % 64, quarter tid / 64 of the
+  // 256 output channels): 64 (128 for query slots) fp32 FMAs per thread in four independent chains, SMEM reduction
+  __shared__ float dk[CD];
+  __shared__ float dq[CD];
+  __shared__ float part[4][64];
+  const int slot = blockIdx.x, tid = threadIdx.x, iq = tid & 63, qt = tid >> 6, i = blockIdx.y * 64 + iq;
   const int b = slot / K1, k = slot - b * K1;
   const int r = k * B + b;                       // the stack row that holds this slot
-  dk[i] = dlin_k[(long long)r * CD + i];
-  dq[i] = k == 0 ? dlin_q[(long long)b * CD + i] : 0.0;
+  dk[tid] = (float)dlin_k[(long long)r * CD + tid];
+  dq[tid] = k == 0 ? (float)dlin_q[(long long)b * CD + tid] : 0.f;
   __syncthreads();
-  double acc[4] = {0.0, 0.0, 0.0, 0.0};   // independent chains: 16 weight loads in flight per thread
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll 4
-  for (int o = 0; o < CD; o += 4) {
+  for (int o = qt * 64; o < qt * 64 + 64; o += 4) {
 #pragma unroll
-    for (int j = 0; j < 4; ++j) acc[j] += (double)__ldg(Wk + (long long)(o + j) * CD + i) * dk[o + j];
+    for (int j = 0; j < 4; ++j) acc[j] = fmaf(__ldg(Wk + (long long)(o + j) * CD + i), dk[o + j], acc[j]);
   }
   if (k == 0) {
 #pragma unroll 4
-    for (int o = 0; o < CD; o += 4) {
+    for (int o = qt * 64; o < qt * 64 + 64; o += 4) {
 #pragma unroll
-      for (int j = 0; j < 4; ++j) acc[j] += (double)__ldg(Wq + (long long)(o + j) * CD + i) * dq[o + j];
+      for (int j = 0; j < 4; ++j) acc[j] = fmaf(__ldg(Wq + (long long)(o + j) * CD + i), dq[o + j], acc[j]);
     }
   }
-  const double s = (acc[0] + acc[1]) + (acc[2] + acc[3]);
-  dpool[(long long)slot * CD + i] = (float)s;
-  if (dpool_amax) {
-    float m = warp_max(fabsf((float)s));
-    if (lane == 0 && m > 0.f) atomicMax(reinterpret_cast<int*>(dpool_amax), __float_as_int(m));
+  part[qt][iq] = (acc[0] + acc[1]) + (acc[2] + acc[3]);
+  __syncthreads();
+  if (tid < 64) {
+    const float s = (part[0][tid] + part[1][tid]) + (part[2][tid] + part[3][tid]);
+    dpool[(long long)slot * CD + blockIdx.y * 64 + tid] = s;
+    if (dpool_amax) {
+      const float m = warp_max(fabsf(s));
+      if ((tid & 31) == 0 && m > 0.f) atomicMax(reinterpret_cast<int*>(dpool_amax), __float_as_int(m));
+    }
   }
 }
 
@@ -255,7 +270,7 @@ extern "C" int csn_compat_bwd(const float* pooled, const float* Wq, const float*
   CSN_LAUNCH_OK("compat_bwd_lin_kernel");
   compat_bwd_w_kernel<<<CD, 256, 0, s>>>(pooled, dlin_q, dlin_k, B, K1, dWq, dbq, dWk, dbk);
   CSN_LAUNCH_OK("compat_bwd_w_kernel");
-  compat_bwd_pool_kernel<<<B * K1, 256, 0, s>>>(Wq, Wk, dlin_q, dlin_k, B, K1, dpool, dpool_amax);
+  compat_bwd_pool_kernel<<<dim3(B * K1, 4), 256, 0, s>>>(Wq, Wk, dlin_q, dlin_k, B, K1, dpool, dpool_amax);
   CSN_LAUNCH_OK("compat_bwd_pool_kernel");
   return 0;
 }
