@@ -89,6 +89,12 @@ class _Timed:
             flops = 2.0 * M * N * K * nbt
             out_b = 4 if args[2]._obj.dtype == CSN_F32 else 2
             nbytes = nbt * (2.0 * (M + N) * K + float(out_b) * M * N)   # operands once + output once (algorithmic)
+        elif self.name == "csn_gemm_dual":   # (A0, B0, D0, A1, B1, D1, M, N, K, nb, alpha, stream)
+            nb = args[9]
+            nbt = nb[0] * nb[1] * nb[2] * nb[3]
+            M, N, K = args[6], args[7], args[8]
+            flops = 2 * 2.0 * M * N * K * nbt
+            nbytes = 2 * nbt * (2.0 * (M + N) * K + 2.0 * M * N)
         elif self.name == "csn_gemm_colbias":   # (A, B, D, M, N, K, alpha, ...)
             M, N, K = args[3], args[4], args[5]
             flops = 2.0 * M * N * K
@@ -190,6 +196,8 @@ _EXTRA_SIGNATURES: dict[str, list] = {
                      C.c_void_p, C.c_int32, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
                      C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                      C.c_void_p, C.c_void_p, C.c_void_p],
+    "csn_gemm_dual": [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
+                      C.POINTER(C.c_int32), C.c_float, C.c_void_p],
     "csn_grad_unscale": [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p],
     "csn_compat_fanout": [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_void_p,
                           C.c_void_p, C.c_void_p],

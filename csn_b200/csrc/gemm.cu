@@ -64,6 +64,13 @@ struct GemmArgs {
   const float* zbias;
   // csn_gemm_res_ln: dropout on the projection output before the residual add (csa_models.py:115), off when thresh == 0
   uint32_t drop_seed, drop_thresh; float drop_scale;
+  // csn_gemm_dual: a second problem of the same shape whose tiles are interleaved with the first one's, batch by batch
+  // (problem 1: A consumed MN-major through tensor map slot tmR0, B through tmR1): the two problems of the attention
+  // backward that read the same dS tile — dQ = dS K and dK = dS^T Q — run back to back, so the second read hits L2
+  int dual;
+  long long a2_mn_off[4], a2_k_off[4], b2_mn_off[4], b2_k_off[4];
+  int d2_row_off[4], d2_col_off[4], d2_col_base;
+  uint32_t idesc2;
 };
 
 template <int BN>
@@ -79,7 +86,7 @@ struct GemmCfg {
 };
 
 struct TileCoord {
-  int b0, b1, b2, b3, mt, nt, ks;
+  int b0, b1, b2, b3, mt, nt, ks, prob;
 };
 
 // 32-bit arithmetic (the host rejects problems with >= 2^31 tiles); divisions by 1 are skipped, which is the
@@ -105,6 +112,7 @@ __device__ __forceinline__ TileCoord decode_tile(long long t64, const GemmArgs& 
     c.nt = step(p.tiles_n);
     c.mt = step(p.tiles_m);
   }
+  c.prob = p.dual ? step(2) : 0;   // dual launch: [all tiles of problem 0][all tiles of problem 1] of one batch, then the next batch
   c.b0 = step(p.nb0);
   c.b1 = step(p.nb1);
   c.b2 = step(p.nb2);
@@ -178,7 +186,7 @@ __device__ __forceinline__ void store_chunk(const GemmArgs& p, long long base, i
   }
 }
 
-template <int BN, bool A_MN, bool B_MN, int CL, bool LN = false, bool DL = false, bool CB = false, bool DROP = false>
+template <int BN, bool A_MN, bool B_MN, int CL, bool LN = false, bool DL = false, bool CB = false, bool DROP = false, bool DUAL = false>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
             const __grid_constant__ CUtensorMap tmD, const __grid_constant__ CUtensorMap tmR0,
@@ -241,10 +249,18 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       for (long long t = t_first; t < p.total_tiles; t += t_stride) {
         TileCoord c = decode_tile(t, p);
         c.mt = c.mt * CL + rank;
-        const long long a_mn = c.b0 * p.a_mn_off[0] + c.b1 * p.a_mn_off[1] + c.b2 * p.a_mn_off[2] + c.b3 * p.a_mn_off[3] + (long long)c.mt * GEMM_BM;
-        const long long b_mn = c.b0 * p.b_mn_off[0] + c.b1 * p.b_mn_off[1] + c.b2 * p.b_mn_off[2] + c.b3 * p.b_mn_off[3] + (long long)c.nt * BN;
-        const long long a_k0 = c.b0 * p.a_k_off[0] + c.b1 * p.a_k_off[1] + c.b2 * p.a_k_off[2] + c.b3 * p.a_k_off[3];
-        const long long b_k0 = c.b0 * p.b_k_off[0] + c.b1 * p.b_k_off[1] + c.b2 * p.b_k_off[2] + c.b3 * p.b_k_off[3];
+        const bool pr = DUAL && c.prob != 0;
+        const bool a_mnm = DUAL ? pr : A_MN;      // dual: problem 1 consumes A MN-major (dS^T)
+        const long long* amo = pr ? p.a2_mn_off : p.a_mn_off;
+        const long long* ako = pr ? p.a2_k_off : p.a_k_off;
+        const long long* bmo = pr ? p.b2_mn_off : p.b_mn_off;
+        const long long* bko = pr ? p.b2_k_off : p.b_k_off;
+        const CUtensorMap* tA = pr ? &tmR0 : &tmA;
+        const CUtensorMap* tB = pr ? &tmR1 : &tmB;
+        const long long a_mn = c.b0 * amo[0] + c.b1 * amo[1] + c.b2 * amo[2] + c.b3 * amo[3] + (long long)c.mt * GEMM_BM;
+        const long long b_mn = c.b0 * bmo[0] + c.b1 * bmo[1] + c.b2 * bmo[2] + c.b3 * bmo[3] + (long long)c.nt * BN;
+        const long long a_k0 = c.b0 * ako[0] + c.b1 * ako[1] + c.b2 * ako[2] + c.b3 * ako[3];
+        const long long b_k0 = c.b0 * bko[0] + c.b1 * bko[1] + c.b2 * bko[2] + c.b3 * bko[3];
         const int kb0 = c.ks * p.kb_per_split;
         const int kb1 = min(p.kb_total, kb0 + p.kb_per_split);
         for (int kb = kb0; kb < kb1; ++kb) {
@@ -254,28 +270,28 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           mbar_arrive_expect_tx(full_bar(st), Cfg::STAGE_BYTES);
           const int ka = (int)(a_k0 + (long long)kb * GEMM_BK);
           const int kbb = (int)(b_k0 + (long long)kb * GEMM_BK);
-          if (!A_MN) {
-            tma_load_2d(sA, &tmA, full_bar(st), ka, (int)a_mn);
+          if (!a_mnm) {
+            tma_load_2d(sA, tA, full_bar(st), ka, (int)a_mn);
           } else {
 #pragma unroll
             for (int at = 0; at < GEMM_BM / 64; ++at)
-              tma_load_2d(sA + at * 8192, &tmA, full_bar(st), (int)a_mn + at * 64, ka);
+              tma_load_2d(sA + at * 8192, tA, full_bar(st), (int)a_mn + at * 64, ka);
           }
           if (CL == 1) {
             if (!B_MN) {
-              tma_load_2d(sB, &tmB, full_bar(st), kbb, (int)b_mn);
+              tma_load_2d(sB, tB, full_bar(st), kbb, (int)b_mn);
             } else {
 #pragma unroll
               for (int at = 0; at < BN / 64; ++at)
-                tma_load_2d(sB + at * 8192, &tmB, full_bar(st), (int)b_mn + at * 64, kbb);
+                tma_load_2d(sB + at * 8192, tB, full_bar(st), (int)b_mn + at * 64, kbb);
             }
           } else {
             if (!B_MN) {   // this CTA's half of the BN rows (box = BN/2 rows), delivered to both CTAs
-              tma_load_2d_mc(sB + rank * (BN / 2) * 128, &tmB, full_bar(st), kbb, (int)b_mn + rank * (BN / 2), MC_MASK);
+              tma_load_2d_mc(sB + rank * (BN / 2) * 128, tB, full_bar(st), kbb, (int)b_mn + rank * (BN / 2), MC_MASK);
             } else {
 #pragma unroll
               for (int at = 0; at < BN / 64; ++at)
-                if ((at % CL) == rank) tma_load_2d_mc(sB + at * 8192, &tmB, full_bar(st), (int)b_mn + at * 64, kbb, MC_MASK);
+                if ((at % CL) == rank) tma_load_2d_mc(sB + at * 8192, tB, full_bar(st), (int)b_mn + at * 64, kbb, MC_MASK);
             }
           }
           if (++st == NST) { st = 0; ph ^= 1; }
@@ -293,6 +309,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         const TileCoord c = decode_tile(t, p);
         const int kb0 = c.ks * p.kb_per_split;
         const int kb1 = min(p.kb_total, kb0 + p.kb_per_split);
+        const bool a_mnm = DUAL ? (c.prob != 0) : A_MN;
+        const uint32_t idesc_t = (DUAL && c.prob != 0) ? p.idesc2 : p.idesc;
         mbar_wait(tempty_bar(acc), acc_ph ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN;
@@ -305,11 +323,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           for (int k = 0; k < GEMM_BK / 16; ++k) {
             // K-major: 16 elements = 32 B further along the swizzled row.
             // MN-major: 16 K-rows of 128 B further down.
-            const uint64_t ad = A_MN ? umma_desc_sw128(sA + k * 2048, 8192, 1024)
-                                     : umma_desc_sw128(sA + k * 32, 0, 1024);
+            const uint64_t ad = a_mnm ? umma_desc_sw128(sA + k * 2048, 8192, 1024)
+                                      : umma_desc_sw128(sA + k * 32, 0, 1024);
             const uint64_t bd = B_MN ? umma_desc_sw128(sB + k * 2048, 8192, 1024)
                                      : umma_desc_sw128(sB + k * 32, 0, 1024);
-            umma_f16_ss(d_tmem, ad, bd, p.idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            umma_f16_ss(d_tmem, ad, bd, idesc_t, (kb > kb0 || k > 0) ? 1u : 0u);
           }
           if (CL == 1) umma_commit(empty_bar(st)); else umma_commit_mc(empty_bar(st), MC_MASK);  // stage reusable once these MMAs have read it
           if (++st == NST) { st = 0; ph ^= 1; }
@@ -552,8 +570,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         // pipe is writing the other accumulator).
         const bool o32 = p.out_dtype == CSN_F32;
         const int W = o32 ? 32 : 64;  // columns per 128-byte slab
-        const int row0 = c.b0 * p.d_row_off[0] + c.b1 * p.d_row_off[1] + c.b2 * p.d_row_off[2] + c.b3 * p.d_row_off[3] + c.mt * GEMM_BM + q * 32;
-        const int col0 = c.b0 * p.d_col_off[0] + c.b1 * p.d_col_off[1] + c.b2 * p.d_col_off[2] + c.b3 * p.d_col_off[3] + n0;
+        const int* dro = (DUAL && c.prob != 0) ? p.d2_row_off : p.d_row_off;
+        const int* dco = (DUAL && c.prob != 0) ? p.d2_col_off : p.d_col_off;
+        const int row0 = c.b0 * dro[0] + c.b1 * dro[1] + c.b2 * dro[2] + c.b3 * dro[3] + c.mt * GEMM_BM + q * 32;
+        const int col0 = c.b0 * dco[0] + c.b1 * dco[1] + c.b2 * dco[2] + c.b3 * dco[3] + n0 + ((DUAL && c.prob != 0) ? p.d2_col_base : 0);
         const bool rows_live = c.mt * GEMM_BM + q * 32 < p.M;  // warp-uniform
         // this warp's unit range [u0, u1): all live units, or one half of them (split on a slab boundary)
         const int g = o32 ? 1 : 2;                                          // units per slab
@@ -679,12 +699,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   }
 }
 
-template <int BN, bool A_MN, bool B_MN, int CL, bool LN = false, bool DL = false, bool CB = false, bool DROP = false>
+template <int BN, bool A_MN, bool B_MN, int CL, bool LN = false, bool DL = false, bool CB = false, bool DROP = false, bool DUAL = false>
 static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmD,
                        const GemmArgs& args, cudaStream_t stream, const CUtensorMap* tmR0 = nullptr,
                        const CUtensorMap* tmR1 = nullptr) {
   using Cfg = GemmCfg<BN>;
-  auto kern = gemm_kernel<BN, A_MN, B_MN, CL, LN, DL, CB, DROP>;
+  auto kern = gemm_kernel<BN, A_MN, B_MN, CL, LN, DL, CB, DROP, DUAL>;
   static bool configured = false;
   if (!configured) {
     CSN_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
@@ -729,6 +749,10 @@ struct ColBias {
   const float* bias; long long ld; int col0, group_rows, rows_valid;
 };
 
+struct DualProblem {   // the second problem of csn_gemm_dual (same M, N, K and batch extents as the first)
+  const csn_mat* A; const csn_mat* B; const csn_out* D;
+};
+
 struct DeltaEpilogue {
   const void* O; const void* O_lo; long long ldo; long long o_rows; float* delta; int rows_pad, n_head, d_head;
 };
@@ -737,7 +761,8 @@ struct DeltaEpilogue {
 
 static int gemm_impl(const csn_mat* A, const csn_mat* B, const csn_out* D, int32_t M, int32_t N,
                      int32_t K, const int32_t nb[4], float alpha, int32_t split_k, void* stream,
-                     const csn::LnEpilogue* ln, const csn::DeltaEpilogue* dl = nullptr, const csn::ColBias* cb = nullptr) {
+                     const csn::LnEpilogue* ln, const csn::DeltaEpilogue* dl = nullptr, const csn::ColBias* cb = nullptr,
+                     const csn::DualProblem* du = nullptr) {
   using namespace csn;
   clear_error();
   CSN_CHECK_ARG(A && B && D && nb, "csn_gemm: null argument");
@@ -835,7 +860,38 @@ static int gemm_impl(const csn_mat* A, const csn_mat* B, const csn_out* D, int32
     CSN_CHECK_ARG((long long)nb[0] * nb[1] * nb[2] * nb[3] == 1, "csn_gemm_colbias: one batch");
     g.cbias = cb->bias; g.cb_ld = cb->ld; g.cb_col0 = cb->col0; g.cb_group = cb->group_rows; g.cb_valid = cb->rows_valid;
   }
+  CUtensorMap tmA2 = tmA, tmB2 = tmB;
+  if (du) {
+    const csn_mat* A1 = du->A; const csn_mat* B1 = du->B; const csn_out* D1 = du->D;
+    CSN_CHECK_ARG(BN == 256 && !a_mn && b_mn && A1->major == CSN_MAJOR_MN && B1->major == CSN_MAJOR_MN,
+                  "csn_gemm_dual: N > 128; problem 0 = (K-major A, MN-major B), problem 1 = (MN-major A, MN-major B)");
+    CSN_CHECK_ARG(A1->dtype == A->dtype && B1->dtype == A->dtype && D1->dtype == D->dtype && D1->ld == D->ld && !D1->accumulate &&
+                  !D1->transposed && split_k == 1 && g.tma_store, "csn_gemm_dual: the two problems must share dtypes, the output "
+                  "leading dimension and a row-major, 16-byte aligned, non-accumulating output");
+    const long long delta = (reinterpret_cast<const char*>(D1->ptr) - reinterpret_cast<const char*>(D->ptr)) / esz;
+    CSN_CHECK_ARG(delta >= 0 && delta + N <= D->ld, "csn_gemm_dual: D1 must start inside the rows of D0 (same buffer, column offset)");
+    rc = make_tmap_2d(&tmA2, A1->ptr, A1->dtype, A1->inner, A1->outer, A1->ld, 64, 64);
+    if (rc) return rc;
+    rc = make_tmap_2d(&tmB2, B1->ptr, B1->dtype, B1->inner, B1->outer, B1->ld, 64, 64);
+    if (rc) return rc;
+    for (int i = 0; i < 4; ++i) {
+      g.a2_mn_off[i] = A1->mn_off[i]; g.a2_k_off[i] = A1->k_off[i];
+      g.b2_mn_off[i] = B1->mn_off[i]; g.b2_k_off[i] = B1->k_off[i];
+      CSN_CHECK_ARG(D1->off[i] >= 0, "csn_gemm_dual: negative output offset");
+      g.d2_row_off[i] = (int)(D1->off[i] / D1->ld);
+      g.d2_col_off[i] = (int)(D1->off[i] % D1->ld);
+    }
+    g.d2_col_base = (int)delta;
+    g.idesc2 = umma_idesc_f16(A->dtype == CSN_F16 ? 0u : 1u, 1u, 1u, (uint32_t)BN);
+    g.dual = 1;
+    g.total_tiles *= 2;
+    CSN_CHECK_ARG(g.total_tiles < (1ll << 31), "csn_gemm_dual: too many tiles");
+  }
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  if (du) {
+    if (CL == 2) return launch_gemm<256, false, true, 2, false, false, false, false, true>(tmA, tmB, tmD, g, s, &tmA2, &tmB2);
+    return launch_gemm<256, false, true, 1, false, false, false, false, true>(tmA, tmB, tmD, g, s, &tmA2, &tmB2);
+  }
   if (dl) {
     const long long nbt = (long long)nb[0] * nb[1] * nb[2] * nb[3];
     CSN_CHECK_ARG(BN == 256 && !a_mn && nbt == 1 && split_k == 1 && D->dtype != CSN_F32 && g.tma_store,
@@ -906,6 +962,16 @@ static int gemm_impl(const csn_mat* A, const csn_mat* B, const csn_out* D, int32
 extern "C" int csn_gemm(const csn_mat* A, const csn_mat* B, const csn_out* D, int32_t M, int32_t N,
                         int32_t K, const int32_t nb[4], float alpha, int32_t split_k, void* stream) {
   return gemm_impl(A, B, D, M, N, K, nb, alpha, split_k, stream, nullptr);
+}
+
+extern "C" int csn_gemm_dual(const csn_mat* A0, const csn_mat* B0, const csn_out* D0, const csn_mat* A1, const csn_mat* B1,
+                             const csn_out* D1, int32_t M, int32_t N, int32_t K, const int32_t nb[4], float alpha,
+                             void* stream) {
+  using namespace csn;
+  clear_error();
+  CSN_CHECK_ARG(A1 && B1 && D1, "csn_gemm_dual: null argument");
+  DualProblem du{A1, B1, D1};
+  return gemm_impl(A0, B0, D0, M, N, K, nb, alpha, 1, stream, nullptr, nullptr, nullptr, &du);
 }
 
 extern "C" int csn_gemm_res_ln(const csn_mat* A, const csn_mat* B, float* Z, int64_t ldz, int32_t M, int32_t K,

@@ -547,6 +547,16 @@ def attention_backward(ctx: AttnContext, dY: torch.Tensor, need_dx: bool, amax: 
             Km = L.mat(Kv[g.k0 * NP:], L.MAJOR_MN, mn_off=(d, 0, 0, 0), k_off=(0, CP, g.k_si * NP, g.k_so * NP))
             Qm = L.mat(Qv[g.q0 * NP:], L.MAJOR_MN, mn_off=(d, 0, 0, 0), k_off=(0, CP, g.q_si * NP, g.q_so * NP))
             off = (d, CP * 3 * HD, NP * 3 * HD, g.n_in * NP * 3 * HD)
+            if not fuse_dq and d > 128 and os.environ.get("CSN_GEMM_DUAL", "1") != "0":
+                # dQ = dS K and dK = dS^T Q in ONE launch, tiles of the same (block, chunk) back to back: the second
+                # read of the dS tile comes from L2 (csn_gemm_dual)
+                nb4 = (C.c_int32 * 4)(*[int(v) for v in nb])
+                D0 = L.out(dQv[g.blk0 * NP:], 3 * HD, off=off)
+                D1 = L.out(dKv[g.blk0 * NP:], 3 * HD, off=off)
+                rc = lib.csn_gemm_dual(C.byref(dSk), C.byref(Km), C.byref(D0), C.byref(dSt), C.byref(Qm), C.byref(D1),
+                                       CP, d, CP, nb4, 1.0, L.stream_ptr())
+                L.check(rc, "csn_gemm_dual")
+                continue
             if not fuse_dq:
                 L.gemm(dSk, Km, L.out(dQv[g.blk0 * NP:], 3 * HD, off=off), CP, d, CP, nb=nb)    # dQ = dS K
             L.gemm(dSt, Qm, L.out(dKv[g.blk0 * NP:], 3 * HD, off=off), CP, d, CP, nb=nb)    # dK = dS^T Q

@@ -69,6 +69,14 @@ typedef struct csn_out {
 int csn_gemm(const csn_mat* A, const csn_mat* B, const csn_out* D, int32_t M, int32_t N, int32_t K,
              const int32_t nb[4], float alpha, int32_t split_k, void* stream);
 
+/* Two contractions of the same shape (M, N > 128, K, batch extents) in ONE launch, their tiles interleaved batch by
+ * batch: problem 0 = (A0 K-major, B0 MN-major) -> D0, problem 1 = (A1 MN-major, B1 MN-major) -> D1, both outputs 16-bit
+ * row-major views of one buffer (D1->ptr inside D0's rows, same ld).  For the attention backward, dQ = dS K and
+ * dK = dS^T Q (autograd of csa_models.py:139) read the same dS tile: issued back to back, the second read hits L2
+ * instead of HBM. */
+int csn_gemm_dual(const csn_mat* A0, const csn_mat* B0, const csn_out* D0, const csn_mat* A1, const csn_mat* B1,
+                  const csn_out* D1, int32_t M, int32_t N, int32_t K, const int32_t nb[4], float alpha, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Shape-compatibility retrieval measure and top-K neighbour selection
  * (reference: CrossShapeAt.get_retrieval_measure / get_knn_graph, MID-FC/csa_models.py:244-280 and

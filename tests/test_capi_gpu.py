@@ -204,3 +204,31 @@ def test_compat_glue_kernels_against_torch_fp64(B, K):
     for got, ref in ((gW[0], w[0].grad), (gb[0], w[1].grad), (gW[1], w[2].grad), (gb[1], w[3].grad), (dpool, p64.grad)):
         assert (got.double() - ref).norm() <= 2e-5 * ref.norm() + 1e-12
     assert abs(amax.item() - p64.grad.abs().max().item()) <= 1e-4 * p64.grad.abs().max().item()
+
+
+def test_gemm_dual_two_problems_in_one_launch():
+    """csn_gemm_dual: D0 = A0 B0^T-form (A0 K-major, B0 MN-major) and D1 (A1 = A0^T consumed MN-major, B1 MN-major) written
+    into two column ranges of one buffer, batched — the dQ = dS K / dK = dS^T Q pair of the attention backward."""
+    from csn_b200 import _lib as L
+    g = synth.gen(33)
+    nbat, M, N, K = 3, 256, 256, 256          # square dS tiles: M = queries, K = keys for problem 0 and the reverse for problem 1
+    dS = (torch.randn(nbat * M, K, generator=g) * 0.5).half().cuda()        # [batch][query][key]
+    Kmat = (torch.randn(nbat * K, N, generator=g) * 0.5).half().cuda()      # [batch][key][d]
+    Qmat = (torch.randn(nbat * M, N, generator=g) * 0.5).half().cuda()      # [batch][query][d]
+    out = torch.full((nbat * M, 3 * N), float("nan"), dtype=torch.float16, device="cuda")
+    A0 = L.mat(dS, L.MAJOR_K, mn_off=(M,))
+    B0 = L.mat(Kmat, L.MAJOR_MN, k_off=(K,))
+    A1 = L.mat(dS, L.MAJOR_MN, k_off=(M,))
+    B1 = L.mat(Qmat, L.MAJOR_MN, k_off=(M,))
+    D0 = L.out(out[:, :N], 3 * N, off=(M * 3 * N,))
+    D1 = L.out(out[:, N:2 * N], 3 * N, off=(M * 3 * N,))
+    nb = (C.c_int32 * 4)(nbat, 1, 1, 1)
+    rc = L.lib().csn_gemm_dual(C.byref(A0), C.byref(B0), C.byref(D0), C.byref(A1), C.byref(B1), C.byref(D1), M, N, K, nb, 1.0,
+                               L.stream_ptr())
+    L.check(rc, "csn_gemm_dual")
+    dS3, K3, Q3 = dS.double().view(nbat, M, K), Kmat.double().view(nbat, K, N), Qmat.double().view(nbat, M, N)
+    want_dq = torch.bmm(dS3, K3).view(nbat * M, N)
+    want_dk = torch.bmm(dS3.transpose(1, 2), Q3).view(nbat * K, N)
+    assert (out[:, :N].double() - want_dq).abs().max() < 2e-3 * want_dq.abs().max()
+    assert (out[:, N:2 * N].double() - want_dk).abs().max() < 2e-3 * want_dk.abs().max()
+    assert torch.isnan(out[:, 2 * N:]).all()          # the third column range is untouched
