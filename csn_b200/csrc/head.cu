@@ -375,16 +375,21 @@ __global__ void __launch_bounds__(256, (R == 8 && CMAX == 16 && NK <= 4) ? 2 : 1
 }
 
 // dW[c][ch] = scale * sum_i part[i][c][ch]   (fixed order: deterministic)
-__global__ void head_dw_reduce_kernel(const float* __restrict__ part, float* __restrict__ out, int n_part, int C) {
-  const int c = blockIdx.x, ch = threadIdx.x;
-  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};   // eight independent chains (the loads are what costs)
-  int i = 0;
-  for (; i + 8 <= n_part; i += 8) {
+__global__ void __launch_bounds__(1024) head_dw_reduce_kernel(const float* __restrict__ part, float* __restrict__ out, int n_part, int C) {
+  // block = 256 channels x 4 groups of partials (fixed assignment and order: deterministic), SMEM reduction of the groups
+  __shared__ float red[4][HD_DM];
+  const int c = blockIdx.x, ch = threadIdx.x & 255, grp = threadIdx.x >> 8;
+  const int per = (n_part + 3) / 4, i0 = grp * per, i1 = min(n_part, i0 + per);
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  int i = i0;
+  for (; i + 4 <= i1; i += 4) {
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc[j] += __ldg(part + ((long long)(i + j) * C + c) * HD_DM + ch);
+    for (int j = 0; j < 4; ++j) acc[j] += __ldg(part + ((long long)(i + j) * C + c) * HD_DM + ch);
   }
-  for (; i < n_part; ++i) acc[0] += __ldg(part + ((long long)i * C + c) * HD_DM + ch);
-  out[c * HD_DM + ch] = ((acc[0] + acc[1]) + (acc[2] + acc[3])) + ((acc[4] + acc[5]) + (acc[6] + acc[7]));
+  for (; i < i1; ++i) acc[0] += __ldg(part + ((long long)i * C + c) * HD_DM + ch);
+  red[grp][ch] = (acc[0] + acc[1]) + (acc[2] + acc[3]);
+  __syncthreads();
+  if (grp == 0) out[c * HD_DM + ch] = (red[0][ch] + red[1][ch]) + (red[2][ch] + red[3][ch]);
 }
 
 // loss = (sum of the per-CTA partial sums, fixed order) / max(n_valid, 1)
@@ -491,7 +496,7 @@ extern "C" int csn_csa_head(const float* Z, const float* mean, const float* rstd
     const int tiles = n_b * (rows_pad / 8);
     const int cap = (n_classes <= 16 && n_k <= 4) ? 2 * grid_cap : grid_cap;
     const int grid = tiles < cap ? tiles : cap;
-    head_dw_reduce_kernel<<<n_classes, HD_DM, 0, s>>>(dW_part, dW, grid, n_classes);
+    head_dw_reduce_kernel<<<n_classes, 1024, 0, s>>>(dW_part, dW, grid, n_classes);
     CSN_LAUNCH_OK("head_dw_reduce_kernel");
   }
   return 0;
