@@ -743,6 +743,36 @@ static int launch_simple(K kern, dim3 grid, dim3 block, const A& args, void* str
 
 }  // namespace csn
 
+namespace csn {
+// out[s][c] = mean of x[offsets[s] .. offsets[s+1])[c]: CTA = (segment, 32-column group), 8 row lanes per column.
+__global__ void __launch_bounds__(256) segment_mean_kernel(const float* __restrict__ x, const long long* __restrict__ offsets,
+                                                           int n_cols, float* __restrict__ out) {
+  __shared__ float red[8][33];
+  const int seg = blockIdx.x, c = blockIdx.y * 32 + (threadIdx.x & 31), rl = threadIdx.x >> 5;
+  const long long r0 = offsets[seg], r1 = offsets[seg + 1];
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+  if (c < n_cols) {
+    const float* p = x + c;
+    long long r = r0 + rl;
+    for (; r + 24 < r1; r += 32) {
+      a0 += __ldg(p + r * n_cols);
+      a1 += __ldg(p + (r + 8) * n_cols);
+      a2 += __ldg(p + (r + 16) * n_cols);
+      a3 += __ldg(p + (r + 24) * n_cols);
+    }
+    for (; r < r1; r += 8) a0 += __ldg(p + r * n_cols);
+  }
+  red[rl][threadIdx.x & 31] = (a0 + a1) + (a2 + a3);
+  __syncthreads();
+  if (rl == 0 && c < n_cols) {
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t += red[i][threadIdx.x];
+    out[(long long)seg * n_cols + c] = r1 > r0 ? t / (float)(r1 - r0) : 0.f;
+  }
+}
+}  // namespace csn
+
 extern "C" {
 
 int csn_pack_rows(const float* src, void* dst16, float* dst32, int64_t ch_stride, int32_t n0, int64_t src_s0,
@@ -857,6 +887,18 @@ int csn_ln_bwd(const float* dY, const float* Z, const float* mean, const float* 
   if (occ >= 4) return launch_simple(ln_bwd_kernel<4, false, false>, grid, block, a, stream, "ln_bwd_kernel");
   if (occ >= 3) return launch_simple(ln_bwd_kernel<3, false, false>, grid, block, a, stream, "ln_bwd_kernel");
   return launch_simple(ln_bwd_kernel<2, false, false>, grid, block, a, stream, "ln_bwd_kernel");
+}
+
+int csn_segment_mean(const float* x, const int64_t* offsets, int32_t n_seg, int32_t n_cols, float* out, void* stream) {
+  using namespace csn;
+  clear_error();
+  CSN_CHECK_ARG(x && offsets && out, "csn_segment_mean: null pointer");
+  CSN_CHECK_ARG(n_cols > 0 && n_seg >= 0, "csn_segment_mean: bad shape");
+  if (n_seg == 0) return 0;
+  segment_mean_kernel<<<dim3(n_seg, (n_cols + 31) / 32), 256, 0, (cudaStream_t)stream>>>(
+      x, reinterpret_cast<const long long*>(offsets), n_cols, out);
+  CSN_LAUNCH_OK("segment_mean_kernel");
+  return 0;
 }
 
 int csn_grad_unscale(float* x, int64_t n, const float* amax, void* stream) {

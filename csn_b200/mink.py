@@ -95,6 +95,30 @@ class _MhaFullFn(torch.autograd.Function):
                 None, None)
 
 
+class _SegmentMeanFn(torch.autograd.Function):
+    """Per-shape average pooling `torch.mean(feat, dim=0)` (hrnet.py:378,388) for all shapes of a ragged batch:
+    x (sum L_s, C) fp32 rows, lens -> (S, C)."""
+
+    @staticmethod
+    def forward(ctx, x, lens):
+        _require_cuda(x, "x")
+        x = x.contiguous()
+        offs = [0]
+        for n in lens:
+            offs.append(offs[-1] + n)
+        offs_t = torch.tensor(offs, dtype=torch.int64).to(x.device, non_blocking=True)
+        out = torch.empty(len(lens), x.shape[1], dtype=torch.float32, device=x.device)
+        L.check(L.lib().csn_segment_mean(x.data_ptr(), offs_t.data_ptr(), len(lens), x.shape[1], out.data_ptr(), L.stream_ptr()),
+                "csn_segment_mean")
+        ctx.lens_t = offs_t[1:] - offs_t[:-1]
+        ctx.rows = x.shape[0]
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        return torch.repeat_interleave(g / ctx.lens_t.clamp_min(1).unsqueeze(1).float(), ctx.lens_t, dim=0, output_size=ctx.rows), None
+
+
 class _MhaBlocksFn(torch.autograd.Function):
     """A whole batch of MultiHeadAttention calls on RAGGED shapes in one pass of the kernels.
 
@@ -211,7 +235,7 @@ class MultiHeadAttention(nn.Module):
             return 0.0, 0
         return p, int(torch.randint(0, 2 ** 31 - 1, (1,)).item())
 
-    def forward_blocks(self, shapes, pairs):
+    def forward_blocks(self, shapes, pairs, split=True):
         """Batched form of `forward` for ragged inputs: shapes = list of (L_s, 256) feature tensors, pairs = list
         of (query shape index, key/value shape index).  Returns [MHA(shapes[q][None], shapes[k][None],
         shapes[k][None])[0][0] for (q, k) in pairs], computed in ONE pass of the kernels (each shape projected
@@ -220,7 +244,7 @@ class MultiHeadAttention(nn.Module):
         y = _MhaBlocksFn.apply(torch.cat(list(shapes), dim=0), self.w_qs.weight, self.w_ks.weight, self.w_vs.weight,
                                self.fc.weight, self.norm.weight, self.norm.bias, self.n_head, _PRECISIONS[self.precision],
                                lens, tuple((int(a), int(b)) for a, b in pairs), *self._dropout_state())
-        return list(torch.split(y, [lens[q] for q, _ in pairs], dim=0))
+        return list(torch.split(y, [lens[q] for q, _ in pairs], dim=0)) if split else y
 
 
 class ScaledDotProduct(nn.Module):
@@ -299,20 +323,25 @@ class CSAHead(nn.Module):
         # shapes: [q_0..q_{B-1}, k^1_0..k^1_{B-1}, ..., k^K_0..]; blocks: SSA of every shape, then the K*B cross blocks
         shapes = query_feats + [f for kf in key_feats for f in kf]
         pairs = [(s, s) for s in range(len(shapes))] + [(b, B * (i + 1) + b) for i in range(K) for b in range(B)]
-        ys = self.MHA.forward_blocks(shapes, pairs)
-        n_s = len(shapes)
-        pooled = torch.stack([y.mean(dim=0) for y in ys[:n_s]])                       # (B(K+1), 256)
+        lens = tuple(int(t.shape[0]) for t in shapes)
+        y = self.MHA.forward_blocks(shapes, pairs, split=False)                       # rows of every pair, concatenated
+        n_s, dev = len(shapes), y.device
+        # pairs 0..n_s-1 are the SSA blocks in shape order: their rows are y[:sum(lens)], one segment per shape
+        lens_t = torch.tensor(lens, dtype=torch.int64).to(dev, non_blocking=True)
+        pooled = _SegmentMeanFn.apply(y[:sum(lens)], lens)                            # (B(K+1), 256)
         g_q = F.normalize(self.linear_q(pooled[:B]), dim=-1)                          # (B, 256)
         g_k = F.normalize(self.linear_k(pooled), dim=-1).view(K + 1, B, 256)          # [i][b]
         sims = torch.einsum("bd,ibd->bi", g_q, g_k) / self.sim.temperature           # (B, K+1)
         comp = F.softmax(sims, dim=1)
-        out = []
-        for b in range(B):
-            csa = comp[b, 0] * ys[b]
-            for i in range(K):
-                csa = csa + comp[b, i + 1] * ys[n_s + i * B + b]
-            out.append(csa)
-        return out
+        # the B blocks of neighbour i are consecutive pairs with the query lengths: slice i of y lines up row by
+        # row with the query rows, so the weighted sum is K+1 fused multiply-adds over contiguous slices
+        q_rows = sum(lens[:B])
+        w_rows = torch.repeat_interleave(comp, lens_t[:B], dim=0, output_size=q_rows)  # (q_rows, K+1)
+        csa = y[:q_rows] * w_rows[:, 0:1]
+        off = sum(lens)
+        for i in range(K):
+            csa = torch.addcmul(csa, y[off + i * q_rows: off + (i + 1) * q_rows], w_rows[:, i + 1:i + 2])
+        return list(torch.split(csa, list(lens[:B]), dim=0))
 
 
 def topk_neighbors(similarity: torch.Tensor, K: int, self_index=None) -> torch.Tensor:

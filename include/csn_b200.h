@@ -355,6 +355,11 @@ int csn_ln_bwd(const float* dY, const float* Z, const float* mean, const float* 
  * every parameter gradient of a step. */
 int csn_grad_unscale(float* x, int64_t n, const float* amax, void* stream);
 
+/* out[s][c] = mean over rows offsets[s] <= r < offsets[s+1] of x[r][c] (x row-major, n_cols wide; empty segment -> 0):
+ * the per-shape global descriptors `feats.mean(dim=0)` of MinkowskiNet/models/hrnet.py:378,388 for a ragged batch of
+ * shapes in one launch.  Deterministic (fixed summation order). */
+int csn_segment_mean(const float* x, const int64_t* offsets, int32_t n_seg, int32_t n_cols, float* out, void* stream);
+
 /* out[b][c][n] = sum_k w[b*n_k+k] * Y[blk[b*n_k+k]][padrow(n)][c]: the compatibility-weighted sum
  * of the self- and cross-attention outputs written back channel-major (csa_models.py:232-240);
  * rows16 (optional) receives a 16-bit row-major copy. With n_k = 1, w = 1 it is the plain

@@ -232,3 +232,19 @@ def test_gemm_dual_two_problems_in_one_launch():
     assert (out[:, :N].double() - want_dq).abs().max() < 2e-3 * want_dq.abs().max()
     assert (out[:, N:2 * N].double() - want_dk).abs().max() < 2e-3 * want_dk.abs().max()
     assert torch.isnan(out[:, 2 * N:]).all()          # the third column range is untouched
+
+
+def test_segment_mean_matches_torch():
+    """csn_segment_mean against y.mean(dim=0) per shape (hrnet.py:378,388), ragged lengths incl. an empty one."""
+    from csn_b200 import _lib as L
+    g = torch.Generator().manual_seed(3)
+    lens = [5, 0, 1000, 37, 2049]
+    x = torch.randn(sum(lens), 256, generator=g).cuda()
+    offs = torch.tensor([0] + list(torch.tensor(lens).cumsum(0)), dtype=torch.int64).cuda()
+    out = torch.empty(len(lens), 256, device="cuda")
+    L.check(L.lib().csn_segment_mean(x.data_ptr(), offs.data_ptr(), len(lens), 256, out.data_ptr(), L.stream_ptr()), "seg")
+    o = 0
+    for i, n in enumerate(lens):
+        ref = x[o:o + n].double().mean(dim=0).float() if n else torch.zeros(256, device="cuda")
+        assert float((out[i] - ref).abs().max()) < 2e-6
+        o += n
