@@ -11,6 +11,8 @@
 #include <cstdlib>
 #include "host_util.h"
 #include "ptx.cuh"
+#include <type_traits>
+
 #include "attn_common.cuh"
 
 namespace csn {
@@ -51,6 +53,10 @@ struct AttnBwdArgs {
   float drop_scale;
 };
 
+#ifndef CSN_DQ_EW_WARPS
+#define CSN_DQ_EW_WARPS 16
+#endif
+
 template <int DH>
 struct BwdCfg {
   static constexpr int KB = DH / 64;
@@ -62,10 +68,13 @@ struct BwdCfg {
   static constexpr int COLS_PER_SLOT = 64 * KB_PER_SLOT;     // dQ columns produced from one K slot
   static constexpr int NST = (DH >= 128) ? 2 : 6;
   static constexpr int SMEM_BYTES = 2 * TILE_BYTES + DS_BYTES + NST * SLOT_BYTES + 256 + 1024;
+  static constexpr int EW_WARPS = (DH == 64) ? CSN_DQ_EW_WARPS : 4;   // element-wise warps (several per TMEM lane quadrant at d_head 64)
+  static constexpr int EW_THREADS = 32 * EW_WARPS;
+  static constexpr int THREADS = 128 + EW_THREADS;
 };
 
 template <int DH, int CL, bool WITH_DQ, bool DROP>
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(BwdCfg<DH>::THREADS, 1)
 attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmDO,
                    const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
                    const __grid_constant__ CUtensorMap tmDS, const __grid_constant__ CUtensorMap tmDQ,
@@ -111,9 +120,9 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     mbar_init(bq_empty, 1);
     for (int b = 0; b < 2; ++b) {
       mbar_init(sdp_full(b), 1);
-      mbar_init(sdp_empty(b), 128);
+      mbar_init(sdp_empty(b), Cfg::EW_THREADS);
     }
-    mbar_init(ds_full, 128);
+    mbar_init(ds_full, Cfg::EW_THREADS);
     mbar_init(ds_empty, 1);
     mbar_init(dq_full, 1);
     mbar_init(dq_empty, 128);
@@ -242,7 +251,11 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     }
   } else if (warp >= 4) {
     // ================================================================== element-wise stage + epilogue
+    // warps 4-7 own the TMEM lane quadrants; with EW_WARPS == 8 (d_head 64, where this stage and not the MMAs is
+    // the bottleneck) warp q + 4 shares quadrant q and takes the upper 64 key columns of every tile
     const int q = warp & 3;
+    const int half = (warp - 4) >> 2;
+    constexpr int COLS = 128 / (Cfg::EW_WARPS / 4);
     const int r = q * 32 + lane;
     const uint32_t lane_addr = uint32_t(q * 32) << 16;
     uint32_t sdp_ph[2] = {0, 0};
@@ -262,7 +275,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       const int nkv = (it.kv_len + 127) >> 7;
       const bool valid = r < it.q_valid;
       const float lse_l2 = valid ? p.lse[it.stat_off + r] * LOG2E : 0.f;
-      const float dlt = valid ? p.delta[it.stat_off + r] : 0.f;
+      const float dlt_s = valid ? p.delta[it.stat_off + r] * p.scale : 0.f;
       const uint32_t rk = drop_row_key(p.drop_seed, (uint32_t)(it.stat_off + r));
       for (int j = 0; j < nkv; ++j) {
         const int b = WITH_DQ ? 0 : (j & 1);
@@ -271,52 +284,71 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         tc_fence_after();
         const uint32_t s_addr = tmem_base + lane_addr + b * 256;
         const int nvalid = min(128, it.kv_len - j * 128);
-        bool waited = false;
+        // The stage is instruction-bound at d_head 64 (ncu: ~26 SASS instructions per element pair with per-element
+        // bounds predicates and both 16-bit packings): the operand type and "every row and key of this tile exists"
+        // are compile-time variants of the loop, selected per tile by a warp-uniform branch.
+        auto ew_tile = [&](auto F16C, auto FULLC) {
+          constexpr bool F16 = decltype(F16C)::value, FULL = decltype(FULLC)::value;
+          bool waited = false;
 #pragma unroll 1
-        for (int c = 0; c < 128; c += 32) {
-          uint32_t sv[32], dv[32];
-          tmem_ld_32x32(s_addr + c, sv);
-          tmem_ld_32x32(s_addr + 128 + c, dv);
-          tmem_ld_wait();
-          uint32_t pk[16];
+          for (int c = half * COLS; c < half * COLS + COLS; c += 32) {
+            uint32_t sv[32], dv[32];
+            tmem_ld_32x32(s_addr + c, sv);
+            tmem_ld_32x32(s_addr + 128 + c, dv);
+            tmem_ld_wait();
+            uint32_t pk[16];
 #pragma unroll
-          for (int i = 0; i < 32; i += 2) {
-            float d0 = 0.f, d1 = 0.f;
-            float m0 = 1.f, m1 = 1.f;   // d P_dropped / d P = mask / (1 - p)
-            if (DROP) {
-              const uint32_t hh = drop_pair(rk, (uint32_t)(j * 128 + c + i) >> 1);
-              m0 = drop_keep_lo(hh, p.drop_thresh) ? p.drop_scale : 0.f;
-              m1 = drop_keep_hi(hh, p.drop_thresh) ? p.drop_scale : 0.f;
+            for (int i = 0; i < 32; i += 2) {
+              float m0 = p.scale, m1 = p.scale;   // (d P_dropped / d P = mask / (1 - p)) * scale
+              if (DROP) {
+                const uint32_t hh = drop_pair(rk, (uint32_t)(j * 128 + c + i) >> 1);
+                m0 = drop_keep_lo(hh, p.drop_thresh) ? p.drop_scale * p.scale : 0.f;
+                m1 = drop_keep_hi(hh, p.drop_thresh) ? p.drop_scale * p.scale : 0.f;
+              }
+              float d0 = fast_exp2_b(__uint_as_float(sv[i]) * p.scale_log2 - lse_l2) * fmaf(__uint_as_float(dv[i]), m0, -dlt_s);
+              float d1 = fast_exp2_b(__uint_as_float(sv[i + 1]) * p.scale_log2 - lse_l2) * fmaf(__uint_as_float(dv[i + 1]), m1, -dlt_s);
+              if (!FULL) {
+                if (!(valid && c + i < nvalid)) d0 = 0.f;
+                if (!(valid && c + i + 1 < nvalid)) d1 = 0.f;
+              }
+              if (F16) {
+                __half2 h = __floats2half2_rn(d0, d1);
+                pk[i >> 1] = *reinterpret_cast<uint32_t*>(&h);
+              } else {
+                __nv_bfloat162 h = __floats2bfloat162_rn(d0, d1);
+                pk[i >> 1] = *reinterpret_cast<uint32_t*>(&h);
+              }
             }
-            if (valid && c + i < nvalid)
-              d0 = fast_exp2_b(__uint_as_float(sv[i]) * p.scale_log2 - lse_l2) * (__uint_as_float(dv[i]) * m0 - dlt) * p.scale;
-            if (valid && c + i + 1 < nvalid)
-              d1 = fast_exp2_b(__uint_as_float(sv[i + 1]) * p.scale_log2 - lse_l2) * (__uint_as_float(dv[i + 1]) * m1 - dlt) * p.scale;
-            pk[i >> 1] = pack_pair(d0, d1);
-          }
-          if (!waited) {
-            if (WITH_DQ) {
-              mbar_wait(ds_empty, dse_ph ^ 1);   // dQ MMAs of the previous tile no longer read the staging tile
-              dse_ph ^= 1;
+            if (!waited) {
+              if (WITH_DQ) {
+                mbar_wait(ds_empty, dse_ph ^ 1);   // dQ MMAs of the previous tile no longer read the staging tile
+                dse_ph ^= 1;
+              }
+              if (warp == 4 && lane == 0) tma_store_wait_read<0>();   // ... nor does its TMA store to HBM
+              asm volatile("bar.sync 1, %0;" ::"n"(Cfg::EW_THREADS) : "memory");
+              waited = true;
             }
-            if (warp == 4 && lane == 0) tma_store_wait_read<0>();   // ... nor does its TMA store to HBM
-            asm volatile("bar.sync 1, 128;" ::: "memory");
-            waited = true;
-          }
-          uint8_t* rowp = sDS_ptr + (c >> 6) * 16384 + r * 128;
-          const int chunk0 = (c & 63) >> 3;
+            uint8_t* rowp = sDS_ptr + (c >> 6) * 16384 + r * 128;
+            const int chunk0 = (c & 63) >> 3;
 #pragma unroll
-          for (int t = 0; t < 4; ++t) {
-            const int ch = (chunk0 + t) ^ (r & 7);
-            *reinterpret_cast<uint4*>(rowp + ch * 16) = make_uint4(pk[4 * t], pk[4 * t + 1], pk[4 * t + 2], pk[4 * t + 3]);
+            for (int t = 0; t < 4; ++t) {
+              const int ch = (chunk0 + t) ^ (r & 7);
+              *reinterpret_cast<uint4*>(rowp + ch * 16) = make_uint4(pk[4 * t], pk[4 * t + 1], pk[4 * t + 2], pk[4 * t + 3]);
+            }
           }
+        };
+        const bool full = (nvalid == 128) && __all_sync(0xffffffffu, valid);
+        if (p.dtype == CSN_F16) {
+          if (full) ew_tile(std::true_type{}, std::true_type{}); else ew_tile(std::true_type{}, std::false_type{});
+        } else {
+          if (full) ew_tile(std::false_type{}, std::true_type{}); else ew_tile(std::false_type{}, std::false_type{});
         }
         tc_fence_before();
         mbar_arrive(sdp_empty(b));
         fence_proxy_async_smem();
         if (WITH_DQ) mbar_arrive(ds_full);
         // HBM copy of dS_j for dK = dS^T Q: the staged tile is exactly two TMA boxes [128 rows x 64 keys]
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        asm volatile("bar.sync 1, %0;" ::"n"(Cfg::EW_THREADS) : "memory");
         if (warp == 4 && lane == 0) {
           tma_store_2d(&tmDS, sDS, it.ds_col0 + j * 128, it.ds_row0);
           tma_store_2d(&tmDS, sDS + 16384, it.ds_col0 + j * 128 + 64, it.ds_row0);
@@ -331,7 +363,10 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       // dQ tile -> 16-bit through this warp's own rows of the dS staging tile and TMA stores (rows >= q_valid: zeros).
       // The last dS_j of this item has been consumed (dq_full) and its HBM copy is drained first.
       if (warp == 4 && lane == 0) tma_store_wait_read<0>();
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+      asm volatile("bar.sync 1, %0;" ::"n"(Cfg::EW_THREADS) : "memory");
+      // the upper-half warps go on to the next item: its first write to the staging tile sits behind a barrier that
+      // warps 4-7 only reach once their dQ slabs below have left it
+      if (half != 0) continue;
       const uint32_t o_addr = tmem_base + lane_addr + 256;
       int slab = 0;
 #pragma unroll 1
@@ -770,7 +805,7 @@ static int launch_dq_d(const CUtensorMap& tmQ, const CUtensorMap& tmDO, const CU
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3(grid);
-  cfg.blockDim = dim3(256);
+  cfg.blockDim = dim3(Cfg::THREADS);
   cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];

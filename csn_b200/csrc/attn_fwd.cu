@@ -17,6 +17,8 @@
 //                            LSE written by the same warps.
 #include <stdlib.h>
 
+#include <type_traits>
+
 #include "attn_common.cuh"
 
 namespace csn {
@@ -38,12 +40,19 @@ struct AttnCfg {
   static constexpr int NST = (DH >= 128) ? 4 : 8;
   static constexpr int XSTG_BYTES = 0;
   static constexpr int BAR_BYTES = 256;
-  static constexpr int SMEM_BYTES = Q_BYTES + P_BYTES + NST * SLOT_BYTES + XSTG_BYTES + BAR_BYTES + 1024;
+  // softmax warps: one per TMEM lane quadrant, or (d_head 64, where the exponentials and not the MMAs bound the
+  // kernel: 1118 us with, 493 us without them on the MinkowskiNet batch) two, the second taking key columns 64-127
+  static constexpr int SM_WARPS = (DH == 64) ? 8 : 4;
+  static constexpr int SM_THREADS = 32 * SM_WARPS;
+  static constexpr int THREADS = 128 + SM_THREADS;
+  static constexpr int COLS = 128 / (SM_WARPS / 4);          // key columns of a tile per softmax thread
+  static constexpr int XCH_BYTES = (SM_WARPS == 8) ? 1024 : 0;   // row max / row sum exchange between the two halves
+  static constexpr int SMEM_BYTES = Q_BYTES + P_BYTES + NST * SLOT_BYTES + XSTG_BYTES + BAR_BYTES + XCH_BYTES + 1024;
   static constexpr int O_COL = 256;                        // TMEM: S0 @0, S1 @128, O @256 (DH <= 256)
 };
 
 template <int DH, int MODE, int CL, bool DROP>
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(AttnCfg<DH>::THREADS, 1)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                 const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmO,
                 const __grid_constant__ CUtensorMap tmOlo, const __grid_constant__ AttnFwdArgs p) {
@@ -67,6 +76,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   const uint32_t bo_full = bar_base + 8u * (2 * Cfg::NST + 8);
   const uint32_t bo_empty = bar_base + 8u * (2 * Cfg::NST + 9);
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bar_ptr + 8 * (2 * Cfg::NST + 10));
+  float* xch = reinterpret_cast<float*>(bar_ptr + Cfg::BAR_BYTES);   // [2 halves][128 rows] (SM_WARPS == 8 only)
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -85,9 +95,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     mbar_init(bq_empty, 1);
     for (int b = 0; b < 2; ++b) {
       mbar_init(s_full(b), 1);
-      mbar_init(s_empty(b), 128);
+      mbar_init(s_empty(b), Cfg::SM_THREADS);
     }
-    mbar_init(bp_full, 128);
+    mbar_init(bp_full, Cfg::SM_THREADS);
     mbar_init(bp_empty, 1);
     mbar_init(bo_full, 1);
     mbar_init(bo_empty, 128);
@@ -238,10 +248,30 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   } else if (warp >= 4) {
     // ================================================================== softmax / correction / epilogue
     const int q = warp & 3;
+    const int half = (warp - 4) >> 2;   // SM_WARPS == 8: warp q + 4 shares TMEM lane quadrant q, columns 64-127
+    constexpr int COLS = Cfg::COLS;
+    constexpr bool SPLIT = Cfg::SM_WARPS == 8;
+    const int c_lo = half * COLS, c_hi = half * COLS + COLS;
     const int r = q * 32 + lane;  // row of the tile owned by this thread
     const uint32_t lane_addr = uint32_t(q * 32) << 16;
     uint32_t s_ph[2] = {0, 0};
     uint32_t pe_ph = 0, of_ph = 0;
+    // SPLIT: combine a per-row value of the two halves (both threads of a row return the same result)
+    auto row_exchange = [&](float v, bool is_max) -> float {
+      xch[half * 128 + r] = v;
+      asm volatile("bar.sync 2, %0;" ::"n"(Cfg::SM_THREADS) : "memory");
+      const float o = xch[(half ^ 1) * 128 + r];
+      asm volatile("bar.sync 2, %0;" ::"n"(Cfg::SM_THREADS) : "memory");   // the slots may be written again
+      return is_max ? fmaxf(v, o) : v + o;
+    };
+    // SPLIT: OR of a predicate over every softmax thread (a retry decision must be taken by both halves of a row)
+    auto any_thread = [&](bool pred) -> bool {
+      if (!SPLIT) return __any_sync(0xffffffffu, pred);
+      uint32_t out;
+      asm volatile("{\n\t.reg .pred p, q;\n\tsetp.ne.u32 p, %1, 0;\n\tbar.red.or.pred q, 2, %2, p;\n\tselp.u32 %0, 1, 0, q;\n\t}"
+                   : "=r"(out) : "r"((uint32_t)pred), "n"(Cfg::SM_THREADS) : "memory");
+      return out != 0;
+    };
     uint8_t* sP_ptr = smem + Cfg::Q_BYTES;
     constexpr float LOG2E = 1.4426950408889634f;
     // 64 columns (two tcgen05.ld in flight) -> 16-bit pairs -> the swizzled A-operand tile of the P V MMA
@@ -255,6 +285,14 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     };
     auto pack_pair = [&](float a, float b) -> uint32_t {
       if (p.dtype == CSN_F16) {
+        __half2 h = __floats2half2_rn(a, b);
+        return *reinterpret_cast<uint32_t*>(&h);
+      }
+      __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+      return *reinterpret_cast<uint32_t*>(&h);
+    };
+    auto pack_t = [](auto F16C, float a, float b) -> uint32_t {   // operand type known at compile time
+      if (decltype(F16C)::value) {
         __half2 h = __floats2half2_rn(a, b);
         return *reinterpret_cast<uint32_t*>(&h);
       }
@@ -285,33 +323,49 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           const float lse_l2 = rvalid ? p.lse[it.lse_off + j * 128 + r] * LOG2E : 0.f;
           const int cvalid = rvalid ? it.q_valid : 0;           // resident key columns that exist
           const uint32_t rk = drop_row_key(p.drop_seed, (uint32_t)(it.lse_off + j * 128 + r));
+          auto dv_tile = [&](auto F16C, auto FULLC) {
+            constexpr bool F16 = decltype(F16C)::value, FULL = decltype(FULLC)::value;
 #pragma unroll 1
-          for (int c = 0; c < 128; c += 64) {
-            uint32_t v0[32], v1[32];
-            tmem_ld_32x32(s_addr + c, v0);
-            tmem_ld_32x32(s_addr + c + 32, v1);
-            tmem_ld_wait();
-            uint32_t pk[32];
+            for (int c = c_lo; c < c_hi; c += 64) {
+              uint32_t v0[32], v1[32];
+              tmem_ld_32x32(s_addr + c, v0);
+              tmem_ld_32x32(s_addr + c + 32, v1);
+              tmem_ld_wait();
+              uint32_t pk[32];
 #pragma unroll
-            for (int i = 0; i < 32; i += 2) {
-              float a0 = (c + i < cvalid) ? fast_exp2(__uint_as_float(v0[i]) * p.scale_log2 - lse_l2) : 0.f;
-              float a1 = (c + i + 1 < cvalid) ? fast_exp2(__uint_as_float(v0[i + 1]) * p.scale_log2 - lse_l2) : 0.f;
-              float b0 = (c + 32 + i < cvalid) ? fast_exp2(__uint_as_float(v1[i]) * p.scale_log2 - lse_l2) : 0.f;
-              float b1 = (c + 33 + i < cvalid) ? fast_exp2(__uint_as_float(v1[i + 1]) * p.scale_log2 - lse_l2) : 0.f;
-              if (DROP) {   // the forward pass's dropout mask, regenerated (query row id, key column)
-                const uint32_t h0 = drop_pair(rk, (uint32_t)(it.key0 + c + i) >> 1), h1 = drop_pair(rk, (uint32_t)(it.key0 + c + 32 + i) >> 1);
-                a0 = drop_keep_lo(h0, p.drop_thresh) ? a0 * p.drop_scale : 0.f; a1 = drop_keep_hi(h0, p.drop_thresh) ? a1 * p.drop_scale : 0.f;
-                b0 = drop_keep_lo(h1, p.drop_thresh) ? b0 * p.drop_scale : 0.f; b1 = drop_keep_hi(h1, p.drop_thresh) ? b1 * p.drop_scale : 0.f;
+              for (int i = 0; i < 32; i += 2) {
+                float a0 = fast_exp2(__uint_as_float(v0[i]) * p.scale_log2 - lse_l2);
+                float a1 = fast_exp2(__uint_as_float(v0[i + 1]) * p.scale_log2 - lse_l2);
+                float b0 = fast_exp2(__uint_as_float(v1[i]) * p.scale_log2 - lse_l2);
+                float b1 = fast_exp2(__uint_as_float(v1[i + 1]) * p.scale_log2 - lse_l2);
+                if (!FULL) {
+                  if (!(c + i < cvalid)) a0 = 0.f;
+                  if (!(c + i + 1 < cvalid)) a1 = 0.f;
+                  if (!(c + 32 + i < cvalid)) b0 = 0.f;
+                  if (!(c + 33 + i < cvalid)) b1 = 0.f;
+                }
+                if (DROP) {   // the forward pass's dropout mask, regenerated (query row id, key column)
+                  const uint32_t h0 = drop_pair(rk, (uint32_t)(it.key0 + c + i) >> 1), h1 = drop_pair(rk, (uint32_t)(it.key0 + c + 32 + i) >> 1);
+                  a0 = drop_keep_lo(h0, p.drop_thresh) ? a0 * p.drop_scale : 0.f; a1 = drop_keep_hi(h0, p.drop_thresh) ? a1 * p.drop_scale : 0.f;
+                  b0 = drop_keep_lo(h1, p.drop_thresh) ? b0 * p.drop_scale : 0.f; b1 = drop_keep_hi(h1, p.drop_thresh) ? b1 * p.drop_scale : 0.f;
+                }
+                pk[i >> 1] = pack_t(F16C, a0, a1);
+                pk[16 + (i >> 1)] = pack_t(F16C, b0, b1);
               }
-              pk[i >> 1] = pack_pair(a0, a1);
-              pk[16 + (i >> 1)] = pack_pair(b0, b1);
+              if (!waited_p) {
+                mbar_wait(bp_empty, pe_ph ^ 1);
+                pe_ph ^= 1;
+                waited_p = true;
+              }
+              store_p64(c, pk);
             }
-            if (!waited_p) {
-              mbar_wait(bp_empty, pe_ph ^ 1);
-              pe_ph ^= 1;
-              waited_p = true;
-            }
-            store_p64(c, pk);
+          };
+          // compile-time variants of the loop: operand type x "every row and key column of this thread's slice exists"
+          const bool full = __all_sync(0xffffffffu, cvalid >= c_hi);
+          if (p.dtype == CSN_F16) {
+            if (full) dv_tile(std::true_type{}, std::true_type{}); else dv_tile(std::true_type{}, std::false_type{});
+          } else {
+            if (full) dv_tile(std::false_type{}, std::true_type{}); else dv_tile(std::false_type{}, std::false_type{});
           }
         } else {
           // ---- forward: online softmax. Tile 0 takes the exact row max first; later tiles are
@@ -325,7 +379,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             if (two_pass) {
               float mx = -INFINITY;
 #pragma unroll 1
-              for (int c = 0; c < 128; c += 64) {
+              for (int c = c_lo; c < c_hi; c += 64) {
                 uint32_t v0[32], v1[32];
                 tmem_ld_32x32(s_addr + c, v0);
                 tmem_ld_32x32(s_addr + c + 32, v1);
@@ -336,6 +390,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                   if (c + 32 + i < nvalid) mx = fmaxf(mx, __uint_as_float(v1[i]));
                 }
               }
+              if (SPLIT) mx = row_exchange(mx, true);
               if (j == 0) {
                 m_used = mx;
               } else if ((mx - m_used) * p.scale_log2 > 8.f) {
@@ -348,18 +403,21 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             const uint32_t rk = drop_row_key(p.drop_seed, (uint32_t)(it.lse_off + r));
             lsum = 0.f;
             float cmax = -INFINITY;
+            auto exp_tile = [&](auto F16C, auto FULLC) {
+              constexpr bool FULL = decltype(FULLC)::value;
 #pragma unroll 1
-            for (int c = 0; c < 128; c += 64) {
-              uint32_t v0[32], v1[32];
-              tmem_ld_32x32(s_addr + c, v0);
-              tmem_ld_32x32(s_addr + c + 32, v1);
-              tmem_ld_wait();
-              uint32_t pk[32];
-              if (nvalid == 128) {
+              for (int c = c_lo; c < c_hi; c += 64) {
+                uint32_t v0[32], v1[32];
+                tmem_ld_32x32(s_addr + c, v0);
+                tmem_ld_32x32(s_addr + c + 32, v1);
+                tmem_ld_wait();
+                uint32_t pk[32];
 #pragma unroll
                 for (int i = 0; i < 32; i += 2) {
-                  const float s0 = __uint_as_float(v0[i]), s1 = __uint_as_float(v0[i + 1]);
-                  const float t0 = __uint_as_float(v1[i]), t1 = __uint_as_float(v1[i + 1]);
+                  const float s0 = (FULL || c + i < nvalid) ? __uint_as_float(v0[i]) : -INFINITY;
+                  const float s1 = (FULL || c + i + 1 < nvalid) ? __uint_as_float(v0[i + 1]) : -INFINITY;
+                  const float t0 = (FULL || c + 32 + i < nvalid) ? __uint_as_float(v1[i]) : -INFINITY;
+                  const float t1 = (FULL || c + 33 + i < nvalid) ? __uint_as_float(v1[i + 1]) : -INFINITY;
                   cmax = fmaxf(cmax, fmaxf(fmaxf(s0, s1), fmaxf(t0, t1)));
                   float a0 = fast_exp2(s0 * p.scale_log2 - moff), a1 = fast_exp2(s1 * p.scale_log2 - moff);
                   float b0 = fast_exp2(t0 * p.scale_log2 - moff), b1 = fast_exp2(t1 * p.scale_log2 - moff);
@@ -369,43 +427,30 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                     a0 = drop_keep_lo(h0, p.drop_thresh) ? a0 * p.drop_scale : 0.f; a1 = drop_keep_hi(h0, p.drop_thresh) ? a1 * p.drop_scale : 0.f;
                     b0 = drop_keep_lo(h1, p.drop_thresh) ? b0 * p.drop_scale : 0.f; b1 = drop_keep_hi(h1, p.drop_thresh) ? b1 * p.drop_scale : 0.f;
                   }
-                  pk[i >> 1] = pack_pair(a0, a1);
-                  pk[16 + (i >> 1)] = pack_pair(b0, b1);
+                  pk[i >> 1] = pack_t(F16C, a0, a1);
+                  pk[16 + (i >> 1)] = pack_t(F16C, b0, b1);
                 }
-              } else {
-#pragma unroll
-                for (int i = 0; i < 32; i += 2) {
-                  const float s0 = (c + i < nvalid) ? __uint_as_float(v0[i]) : -INFINITY;
-                  const float s1 = (c + i + 1 < nvalid) ? __uint_as_float(v0[i + 1]) : -INFINITY;
-                  const float t0 = (c + 32 + i < nvalid) ? __uint_as_float(v1[i]) : -INFINITY;
-                  const float t1 = (c + 33 + i < nvalid) ? __uint_as_float(v1[i + 1]) : -INFINITY;
-                  cmax = fmaxf(cmax, fmaxf(fmaxf(s0, s1), fmaxf(t0, t1)));
-                  float a0 = fast_exp2(s0 * p.scale_log2 - moff), a1 = fast_exp2(s1 * p.scale_log2 - moff);
-                  float b0 = fast_exp2(t0 * p.scale_log2 - moff), b1 = fast_exp2(t1 * p.scale_log2 - moff);
-                  lsum += (a0 + a1) + (b0 + b1);   // the softmax denominator sees every key; dropout acts on the result
-                  if (DROP) {
-                    const uint32_t h0 = drop_pair(rk, (uint32_t)(j * 128 + c + i) >> 1), h1 = drop_pair(rk, (uint32_t)(j * 128 + c + 32 + i) >> 1);
-                    a0 = drop_keep_lo(h0, p.drop_thresh) ? a0 * p.drop_scale : 0.f; a1 = drop_keep_hi(h0, p.drop_thresh) ? a1 * p.drop_scale : 0.f;
-                    b0 = drop_keep_lo(h1, p.drop_thresh) ? b0 * p.drop_scale : 0.f; b1 = drop_keep_hi(h1, p.drop_thresh) ? b1 * p.drop_scale : 0.f;
-                  }
-                  pk[i >> 1] = pack_pair(a0, a1);
-                  pk[16 + (i >> 1)] = pack_pair(b0, b1);
+                if (!waited_p) {
+                  // P tile may be overwritten once the P V MMAs of the previous tile have completed
+                  mbar_wait(bp_empty, pe_ph ^ 1);
+                  pe_ph ^= 1;
+                  waited_p = true;
                 }
+                store_p64(c, pk);
               }
-              if (!waited_p) {
-                // P tile may be overwritten once the P V MMAs of the previous tile have completed
-                mbar_wait(bp_empty, pe_ph ^ 1);
-                pe_ph ^= 1;
-                waited_p = true;
-              }
-              store_p64(c, pk);
+            };
+            if (p.dtype == CSN_F16) {
+              if (nvalid == 128) exp_tile(std::true_type{}, std::true_type{}); else exp_tile(std::true_type{}, std::false_type{});
+            } else {
+              if (nvalid == 128) exp_tile(std::false_type{}, std::true_type{}); else exp_tile(std::false_type{}, std::false_type{});
             }
             const bool exceeded = !two_pass && (cmax - m_used) * p.scale_log2 > 8.f;
-            if (!__any_sync(0xffffffffu, exceeded)) break;
+            // (SPLIT: tile 0 is two-pass for everybody, so the barrier inside any_thread is reached by all or none)
+            if (two_pass || !any_thread(exceeded)) break;
             two_pass = true;  // rare: redo this tile against the new maximum
           }
           tc_fence_after();
-          if (__any_sync(0xffffffffu, need)) {
+          if (half == 0 && __any_sync(0xffffffffu, need)) {
             // rescale this warp's 32 rows of O in TMEM (rare); P V of the previous tile has completed
             const uint32_t o_addr = tmem_base + lane_addr + Cfg::O_COL;
 #pragma unroll 1
@@ -418,8 +463,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
               tmem_st_32x32(o_addr + c, v);
             }
             tmem_st_wait();
-            l *= alpha;
           }
+          if (need) l *= alpha;
           l += lsum;
         }
         // S_j fully consumed; P_j visible to the tensor-core (async) proxy
@@ -432,6 +477,14 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       mbar_wait(bo_full, of_ph);
       of_ph ^= 1;
       tc_fence_after();
+      if (SPLIT) {
+        if (MODE == 0) l = row_exchange(l, false);
+        if (half != 0) {
+          // warps 4-7 write the output through the P tile: nobody may refill it before their slabs have left
+          asm volatile("bar.sync 3, %0;" ::"n"(Cfg::SM_THREADS) : "memory");
+          continue;
+        }
+      }
       const float inv_l = (MODE == 1) ? 1.f : 1.f / l;
       const bool valid = r < it.q_valid;
       const bool want_lo = (MODE == 0) && p.Olo != nullptr;
@@ -502,6 +555,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       if (MODE == 0 && p.lse) p.lse[it.lse_off + r] = valid ? (m_used * p.scale + __logf(l)) : 0.f;
       tc_fence_before();
       mbar_arrive(bo_empty);
+      if (SPLIT) asm volatile("bar.sync 3, %0;" ::"n"(Cfg::SM_THREADS) : "memory");
     }
     if (lane == 0) tma_store_wait_all();
   }
@@ -530,7 +584,7 @@ static int launch_attn_fwd_d(const CUtensorMap& tmQ, const CUtensorMap& tmK, con
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3(grid);
-  cfg.blockDim = dim3(256);
+  cfg.blockDim = dim3(Cfg::THREADS);
   cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
