@@ -175,9 +175,14 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
           tma_load_2d(sDO + kb * 16384, &tmDO, bq_full, it.col0 + kb * 64, it.o_row0);
         }
         q_ph ^= 1;
+        // consumption order of the MMA warp: [K0, V0], [K1, V1], K0 (dQ), [K2, V2], K1 (dQ), ...
+        load_tile(&tmK, it.col0, it.kv_row0);   // for S
+        load_tile(&tmV, it.col0, it.kv_row0);   // for dP
         for (int j = 0; j < nkv; ++j) {
-          load_tile(&tmK, it.col0, it.kv_row0 + j * 128);   // for S
-          load_tile(&tmV, it.col0, it.kv_row0 + j * 128);   // for dP
+          if (j + 1 < nkv) {
+            load_tile(&tmK, it.col0, it.kv_row0 + (j + 1) * 128);
+            load_tile(&tmV, it.col0, it.kv_row0 + (j + 1) * 128);
+          }
           if (WITH_DQ) load_tile(&tmK, it.col0, it.kv_row0 + j * 128);   // for dQ (same bytes, consumed MN-major)
         }
       }
@@ -212,7 +217,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         mbar_wait(bq_full, q_ph);
         q_ph ^= 1;
         tc_fence_after();
-        for (int j = 0; j < nkv; ++j) {
+        auto issue_sdp = [&](int j) {
           const int b = WITH_DQ ? 0 : (j & 1);
           mbar_wait(sdp_empty(b), sdp_ph[b] ^ 1);   // S / dP previously held by this buffer have been read
           tc_fence_after();
@@ -221,6 +226,12 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
           umma_commit(sdp_full(b));
           if (j == nkv - 1) umma_commit(bq_empty);   // Q_i / dO_i are not read by the dQ MMAs
           sdp_ph[b] ^= 1;
+        };
+        issue_sdp(0);
+        for (int j = 0; j < nkv; ++j) {
+          // S / dP of the next tile go in FRONT of this tile's dQ MMAs: the element-wise warps (the longer stage)
+          // get their next input as soon as they have read the current one, dQ_j runs in their shadow
+          if (j + 1 < nkv) issue_sdp(j + 1);
           if (!WITH_DQ) continue;
           mbar_wait(ds_full, ds_ph);          // dS_j staged
           ds_ph ^= 1;
