@@ -359,8 +359,8 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         fence_proxy_async_smem();
         if (WITH_DQ) mbar_arrive(ds_full);
         // HBM copy of dS_j for dK = dS^T Q: the staged tile is exactly two TMA boxes [128 rows x 64 keys]
-        asm volatile("bar.sync 1, %0;" ::"n"(Cfg::EW_THREADS) : "memory");
-        if (warp == 4 && lane == 0) {
+        if (!WITH_DQ || p.dS != nullptr) asm volatile("bar.sync 1, %0;" ::"n"(Cfg::EW_THREADS) : "memory");
+        if (warp == 4 && lane == 0 && (!WITH_DQ || p.dS != nullptr)) {   // dS == NULL: dK comes from csn_attn_bwd_dkv
           tma_store_2d(&tmDS, sDS, it.ds_col0 + j * 128, it.ds_row0);
           tma_store_2d(&tmDS, sDS + 16384, it.ds_col0 + j * 128 + 64, it.ds_row0);
           tma_store_commit();
@@ -870,7 +870,7 @@ int csn_attn_bwd_dq(const void* Q, const void* dO, const void* K, const void* V,
                     uint32_t drop_seed, float drop_p, void* stream) {
   using namespace csn;
   clear_error();
-  CSN_CHECK_ARG(Q && dO && K && V && items && dS && lse && delta, "csn_attn_bwd_dq: null pointer");
+  CSN_CHECK_ARG(Q && dO && K && V && items && (dS || dQ) && lse && delta, "csn_attn_bwd_dq: null pointer");
   CSN_CHECK_ARG(drop_p >= 0.f && drop_p < 1.f, "csn_attn_bwd_dq: dropout probability %f outside [0, 1)", (double)drop_p);
   CSN_CHECK_ARG(d_head == 256 || d_head == 64, "csn_attn_bwd_dq: d_head=%d not supported (64 or 256)", d_head);
   CSN_CHECK_ARG(dtype == CSN_F16 || dtype == CSN_BF16, "csn_attn_bwd_dq: 16-bit operands only");
@@ -886,12 +886,15 @@ int csn_attn_bwd_dq(const void* Q, const void* dO, const void* K, const void* V,
   rc = make_tmap_2d(&tmV, V, dtype, width, kv_rows, ldv, 64, 128);
   if (rc) return rc;
   CUtensorMap tmDS, tmDQ;
-  rc = make_tmap_2d(&tmDS, dS, dtype, ldds, ds_rows, ldds, 64, 128);
-  if (rc) return rc;
-  tmDQ = tmDS;
+  if (dS != nullptr) {   // dS == NULL (with dQ): nothing is materialised, dK / dV come from csn_attn_bwd_dkv
+    rc = make_tmap_2d(&tmDS, dS, dtype, ldds, ds_rows, ldds, 64, 128);
+    if (rc) return rc;
+    tmDQ = tmDS;
+  }
   if (dQ != nullptr) {   // dQ == NULL: only dS is produced (dQ = dS K then runs as a csn_gemm)
     rc = make_tmap_2d(&tmDQ, dQ, dtype, width, do_rows, lddq, 64, 32);
     if (rc) return rc;
+    if (dS == nullptr) tmDS = tmDQ;
   }
   AttnBwdArgs a;
   a.items = reinterpret_cast<const AttnBwdItem*>(items);

@@ -1,0 +1,446 @@
+// Key-stationary attention backward for d_head = 64 (MinkowskiNet CSA head, h = 4):
+//   dV = P^T dO   and   dK = dS^T Q,   dS = P o (dP - delta) / sqrt(d),   P = exp(S / sqrt(d) - lse)
+// for one tile of 128 keys per work item, with P and dS recomputed tile by tile and never written to HBM
+// (reference: autograd of ScaledDotProductAttention.forward, MinkowskiNet/models/attention.py:69-75, which
+// keeps the full (B, h, Lq, Lk) attention matrix).  Together with csn_attn_bwd_dq (dQ, query-stationary) this
+// is the whole attention backward in two passes and O(L) memory: at d_head 64 the two [128 x 128] score
+// accumulators and BOTH [128 x 64] output accumulators fit in TMEM (128 + 128 + 64 + 64 = 384 columns).
+//
+// CTA = 384 threads, one per SM, persistent over items:
+//   warp 0     TMA producer : K_i, V_i resident per item; ring of 16 KB slots streaming Q_j, dO_j (for the score
+//                             MMAs, K-major) and again dO_j, Q_j (for the output MMAs, MN-major: same bytes)
+//   warp 1     MMA issuer   : S^T = K_i Q_j^T, dP^T = V_i dO_j^T (lane = key, column = query), then
+//                             dV += P^T dO_j, dK += dS^T Q_j; the score MMAs of tile j+1 go ahead of the output
+//                             MMAs of tile j
+//   warp 2     TMEM allocator
+//   warps 4-11 element-wise : two warps per TMEM lane quadrant (64 query columns each).  lse / delta are per
+//                             COLUMN here: staged per tile in SMEM and read as broadcast float4.
+//                             P^T and dS^T -> two 128B-swizzled SMEM tiles = A operands of the output MMAs.
+//                             Epilogue: warps 4-7 write dV, warps 8-11 dK (TMA stores).
+#include <cstdlib>
+#include <type_traits>
+
+#include "attn_common.cuh"
+
+namespace csn {
+
+struct DkvItem {
+  int k_row0;    // first resident key row (row of the K and V views)
+  int k_valid;   // rows of the tile that exist (<= 128); the others are written as zeros
+  int q_row0;    // first streamed query row (row of the Q view)
+  int q_len;     // number of streamed query rows
+  int o_row0;    // first output row (dK and dV)
+  int col0;      // head * 64
+  int stat_off;  // lse[stat_off + n], delta[stat_off + n] for streamed query n
+  int do_row0;   // first streamed row of dO
+  int key0;      // index of the first resident key inside its chunk (dropout mask column)
+  int pad0, pad1, pad2;
+};
+
+struct DkvArgs {
+  const DkvItem* items;
+  int n_items;
+  const float* lse;
+  const float* delta;
+  float scale_log2, scale;
+  int dtype;
+  uint32_t idesc_s;   // M=128, N=128, K-major x K-major
+  uint32_t idesc_o;   // M=128, N=64, A K-major, B MN-major
+  uint32_t drop_seed, drop_thresh;
+  float drop_scale;
+};
+
+struct DkvCfg {
+  static constexpr int TILE_BYTES = 128 * 64 * 2;     // K_i, V_i
+  static constexpr int ST_BYTES = 128 * 128 * 2;      // P^T, dS^T staging tiles
+  static constexpr int SLOT_BYTES = 128 * 64 * 2;
+  static constexpr int NST = 6;
+  static constexpr int EW_WARPS = 8;
+  static constexpr int EW_THREADS = 32 * EW_WARPS;
+  static constexpr int THREADS = 128 + EW_THREADS;
+  static constexpr int STAT_BYTES = 2 * 2 * 128 * 4;  // [buffer][lse | delta][128 queries]
+  static constexpr int BAR_BYTES = 256;
+  static constexpr int SMEM_BYTES = 2 * TILE_BYTES + 2 * ST_BYTES + NST * SLOT_BYTES + STAT_BYTES + BAR_BYTES + 1024;
+  static constexpr int DV_COL = 256, DK_COL = 320;    // TMEM: S^T @0, dP^T @128, dV @256, dK @320
+};
+
+template <bool DROP>
+__global__ void __launch_bounds__(DkvCfg::THREADS, 1)
+attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
+                    const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmDO,
+                    const __grid_constant__ CUtensorMap tmDK, const __grid_constant__ CUtensorMap tmDV,
+                    const __grid_constant__ DkvArgs p) {
+  using Cfg = DkvCfg;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const uint32_t sK = smem_u32(smem);
+  const uint32_t sV = sK + Cfg::TILE_BYTES;
+  const uint32_t sP = sV + Cfg::TILE_BYTES;
+  const uint32_t sDS = sP + Cfg::ST_BYTES;
+  const uint32_t sRing = sDS + Cfg::ST_BYTES;
+  uint8_t* sP_ptr = smem + 2 * Cfg::TILE_BYTES;
+  uint8_t* sDS_ptr = sP_ptr + Cfg::ST_BYTES;
+  float* stat = reinterpret_cast<float*>(smem + 2 * Cfg::TILE_BYTES + 2 * Cfg::ST_BYTES + Cfg::NST * Cfg::SLOT_BYTES);
+  uint8_t* bar_ptr = reinterpret_cast<uint8_t*>(stat) + Cfg::STAT_BYTES;
+  const uint32_t bar_base = smem_u32(bar_ptr);
+  auto kv_full = [&](int s) { return bar_base + 8u * s; };
+  auto kv_empty = [&](int s) { return bar_base + 8u * (Cfg::NST + s); };
+  const uint32_t bres_full = bar_base + 8u * (2 * Cfg::NST + 0);   // K_i, V_i landed
+  const uint32_t bres_empty = bar_base + 8u * (2 * Cfg::NST + 1);  // every score MMA of the item has been issued
+  const uint32_t sdp_full = bar_base + 8u * (2 * Cfg::NST + 2);    // S^T, dP^T of tile j are in TMEM
+  const uint32_t sdp_empty = bar_base + 8u * (2 * Cfg::NST + 3);   // ... and have been read
+  const uint32_t st_full = bar_base + 8u * (2 * Cfg::NST + 4);     // P^T, dS^T of tile j are staged
+  const uint32_t st_empty = bar_base + 8u * (2 * Cfg::NST + 5);    // output MMAs of tile j done reading them
+  const uint32_t acc_full = bar_base + 8u * (2 * Cfg::NST + 6);
+  const uint32_t acc_empty = bar_base + 8u * (2 * Cfg::NST + 7);
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bar_ptr + 8 * (2 * Cfg::NST + 8));
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmK);
+    tma_prefetch_desc(&tmV);
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmDO);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < Cfg::NST; ++s) {
+      mbar_init(kv_full(s), 1);
+      mbar_init(kv_empty(s), 1);
+    }
+    mbar_init(bres_full, 1);
+    mbar_init(bres_empty, 1);
+    mbar_init(sdp_full, 1);
+    mbar_init(sdp_empty, Cfg::EW_THREADS);
+    mbar_init(st_full, Cfg::EW_THREADS);
+    mbar_init(st_empty, 1);
+    mbar_init(acc_full, 1);
+    mbar_init(acc_empty, Cfg::EW_THREADS);
+    fence_mbar_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(smem_u32(tmem_ptr_smem), 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp == 0) {
+    // ================================================================== TMA producer
+    if (elect_one()) {
+      int st = 0;
+      uint32_t ph = 0, r_ph = 0;
+      auto load_slot = [&](const CUtensorMap* tm, int col0, int row0) {
+        mbar_wait(kv_empty(st), ph ^ 1);
+        mbar_arrive_expect_tx(kv_full(st), Cfg::SLOT_BYTES);
+        tma_load_2d(sRing + st * Cfg::SLOT_BYTES, tm, kv_full(st), col0, row0);
+        if (++st == Cfg::NST) { st = 0; ph ^= 1; }
+      };
+      for (int wk = blockIdx.x; wk < p.n_items; wk += gridDim.x) {
+        const DkvItem it = p.items[wk];
+        const int nq = (it.q_len + 127) >> 7;
+        mbar_wait(bres_empty, r_ph ^ 1);
+        mbar_arrive_expect_tx(bres_full, 2 * Cfg::TILE_BYTES);
+        tma_load_2d(sK, &tmK, bres_full, it.col0, it.k_row0);
+        tma_load_2d(sV, &tmV, bres_full, it.col0, it.k_row0);
+        r_ph ^= 1;
+        // consumption order of the MMA warp: [Q0, dO0], [Q1, dO1], dO0, Q0, [Q2, dO2], dO1, Q1, ...
+        load_slot(&tmQ, it.col0, it.q_row0);
+        load_slot(&tmDO, it.col0, it.do_row0);
+        for (int j = 0; j < nq; ++j) {
+          if (j + 1 < nq) {
+            load_slot(&tmQ, it.col0, it.q_row0 + (j + 1) * 128);
+            load_slot(&tmDO, it.col0, it.do_row0 + (j + 1) * 128);
+          }
+          load_slot(&tmDO, it.col0, it.do_row0 + j * 128);   // for dV (same bytes, consumed MN-major)
+          load_slot(&tmQ, it.col0, it.q_row0 + j * 128);     // for dK
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================================================================== MMA issuer
+    if (elect_one()) {
+      int st = 0;
+      uint32_t ph = 0, r_ph = 0, sdp_ph = 0, stf_ph = 0, acc_ph = 0;
+      auto mma_scores = [&](uint32_t a_tile, uint32_t d_tmem) {   // D[key][query] = A_tile (resident) x slot^T, K = 64
+        mbar_wait(kv_full(st), ph);
+        tc_fence_after();
+        const uint32_t b_tile = sRing + st * Cfg::SLOT_BYTES;
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          umma_f16_ss(d_tmem, umma_desc_sw128(a_tile + k * 32, 0, 1024), umma_desc_sw128(b_tile + k * 32, 0, 1024),
+                      p.idesc_s, k ? 1u : 0u);
+        umma_commit(kv_empty(st));
+        if (++st == Cfg::NST) { st = 0; ph ^= 1; }
+      };
+      auto mma_out = [&](uint32_t a_stage, uint32_t d_tmem, bool accumulate) {   // D[key][d] += stage[key][query] x slot
+        mbar_wait(kv_full(st), ph);
+        tc_fence_after();
+        const uint32_t b_tile = sRing + st * Cfg::SLOT_BYTES;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {   // 128 queries in steps of 16
+          const uint32_t a_addr = a_stage + (k >> 2) * 16384 + (k & 3) * 32;
+          umma_f16_ss(d_tmem, umma_desc_sw128(a_addr, 0, 1024), umma_desc_sw128(b_tile + k * 2048, 16384, 1024),
+                      p.idesc_o, (accumulate || k) ? 1u : 0u);
+        }
+        umma_commit(kv_empty(st));
+        if (++st == Cfg::NST) { st = 0; ph ^= 1; }
+      };
+      for (int wk = blockIdx.x; wk < p.n_items; wk += gridDim.x) {
+        const DkvItem it = p.items[wk];
+        const int nq = (it.q_len + 127) >> 7;
+        mbar_wait(bres_full, r_ph);
+        r_ph ^= 1;
+        tc_fence_after();
+        auto issue_scores = [&](int j) {
+          mbar_wait(sdp_empty, sdp_ph ^ 1);   // the scores of the previous tile have been read
+          tc_fence_after();
+          mma_scores(sK, tmem_base);          // S^T  = K_i Q_j^T
+          mma_scores(sV, tmem_base + 128);    // dP^T = V_i dO_j^T
+          umma_commit(sdp_full);
+          if (j == nq - 1) umma_commit(bres_empty);
+          sdp_ph ^= 1;
+        };
+        issue_scores(0);
+        for (int j = 0; j < nq; ++j) {
+          if (j + 1 < nq) issue_scores(j + 1);
+          mbar_wait(st_full, stf_ph);
+          stf_ph ^= 1;
+          if (j == 0) mbar_wait(acc_empty, acc_ph ^ 1);   // previous item's accumulators have been read out
+          tc_fence_after();
+          mma_out(sP, tmem_base + Cfg::DV_COL, j != 0);    // dV += P^T  dO_j
+          mma_out(sDS, tmem_base + Cfg::DK_COL, j != 0);   // dK += dS^T Q_j
+          umma_commit(st_empty);
+        }
+        umma_commit(acc_full);
+        acc_ph ^= 1;
+      }
+    }
+  } else if (warp >= 4) {
+    // ================================================================== element-wise stage + epilogue
+    const int q = warp & 3;
+    const int half = (warp - 4) >> 2;            // query columns [64 half, 64 half + 64)
+    const int r = q * 32 + lane;                 // key row of the tile owned by this thread
+    const int et = threadIdx.x - 128;            // 0 .. EW_THREADS-1
+    const uint32_t lane_addr = uint32_t(q * 32) << 16;
+    uint32_t sdp_ph = 0, ste_ph = 0, accf_ph = 0;
+    constexpr float LOG2E = 1.4426950408889634f;
+    for (int wk = blockIdx.x; wk < p.n_items; wk += gridDim.x) {
+      const DkvItem it = p.items[wk];
+      const int nq = (it.q_len + 127) >> 7;
+      const bool kvalid = r < it.k_valid;
+      // per-query statistics of tile 0 (lse in log2 units, delta pre-scaled); later tiles are prefetched one ahead
+      asm volatile("bar.sync 1, %0;" ::"n"(Cfg::EW_THREADS) : "memory");   // nobody still reads the buffers / staging rows
+      if (et < 128) {
+        const bool qv = et < it.q_len;
+        stat[et] = qv ? p.lse[it.stat_off + et] * LOG2E : 0.f;
+        stat[128 + et] = qv ? p.delta[it.stat_off + et] * p.scale : 0.f;
+      }
+      for (int j = 0; j < nq; ++j) {
+        const int nvalid = min(128, it.q_len - j * 128);
+        float nl = 0.f, nd = 0.f;
+        if (et < 128 && j + 1 < nq) {
+          const int n = (j + 1) * 128 + et;
+          if (n < it.q_len) {
+            nl = p.lse[it.stat_off + n] * LOG2E;
+            nd = p.delta[it.stat_off + n] * p.scale;
+          }
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(Cfg::EW_THREADS) : "memory");   // statistics of tile j visible
+        const float* st_l = stat + (j & 1) * 256;
+        const float* st_d = st_l + 128;
+        mbar_wait(sdp_full, sdp_ph);
+        sdp_ph ^= 1;
+        tc_fence_after();
+        const uint32_t s_addr = tmem_base + lane_addr;
+        auto ew_tile = [&](auto F16C, auto FULLC) {
+          constexpr bool F16 = decltype(F16C)::value, FULL = decltype(FULLC)::value;
+#pragma unroll 1
+          for (int c = half * 64; c < half * 64 + 64; c += 32) {
+            uint32_t sv[32], dv[32];
+            tmem_ld_32x32(s_addr + c, sv);
+            tmem_ld_32x32(s_addr + 128 + c, dv);
+            tmem_ld_wait();
+            uint32_t pp[16], pd[16];
+#pragma unroll
+            for (int i = 0; i < 32; i += 4) {
+              const float4 l4 = *reinterpret_cast<const float4*>(st_l + c + i);
+              const float4 d4 = *reinterpret_cast<const float4*>(st_d + c + i);
+              const float ls[4] = {l4.x, l4.y, l4.z, l4.w}, ds_[4] = {d4.x, d4.y, d4.z, d4.w};
+              float pv[4], dsv[4];
+#pragma unroll
+              for (int u = 0; u < 4; ++u) {
+                float m = 1.f;   // d P_dropped / d P = mask / (1 - p)
+                if (DROP) {      // the forward mask: row id = query, pair = two adjacent keys
+                  const uint32_t hh = drop_pair(drop_row_key(p.drop_seed, (uint32_t)(it.stat_off + j * 128 + c + i + u)),
+                                                (uint32_t)(it.key0 + r) >> 1);
+                  m = (((it.key0 + r) & 1) ? drop_keep_hi(hh, p.drop_thresh) : drop_keep_lo(hh, p.drop_thresh)) ? p.drop_scale : 0.f;
+                }
+                const float pr = fast_exp2(__uint_as_float(sv[i + u]) * p.scale_log2 - ls[u]);
+                float pe = DROP ? pr * m : pr;
+                float de = pr * fmaf(__uint_as_float(dv[i + u]), DROP ? m * p.scale : p.scale, -ds_[u]);
+                if (!FULL) {
+                  if (!(kvalid && c + i + u < nvalid)) { pe = 0.f; de = 0.f; }
+                }
+                pv[u] = pe;
+                dsv[u] = de;
+              }
+              if (F16) {
+                __half2 a = __floats2half2_rn(pv[0], pv[1]), b = __floats2half2_rn(pv[2], pv[3]);
+                __half2 e = __floats2half2_rn(dsv[0], dsv[1]), f = __floats2half2_rn(dsv[2], dsv[3]);
+                pp[i >> 1] = *reinterpret_cast<uint32_t*>(&a); pp[(i >> 1) + 1] = *reinterpret_cast<uint32_t*>(&b);
+                pd[i >> 1] = *reinterpret_cast<uint32_t*>(&e); pd[(i >> 1) + 1] = *reinterpret_cast<uint32_t*>(&f);
+              } else {
+                __nv_bfloat162 a = __floats2bfloat162_rn(pv[0], pv[1]), b = __floats2bfloat162_rn(pv[2], pv[3]);
+                __nv_bfloat162 e = __floats2bfloat162_rn(dsv[0], dsv[1]), f = __floats2bfloat162_rn(dsv[2], dsv[3]);
+                pp[i >> 1] = *reinterpret_cast<uint32_t*>(&a); pp[(i >> 1) + 1] = *reinterpret_cast<uint32_t*>(&b);
+                pd[i >> 1] = *reinterpret_cast<uint32_t*>(&e); pd[(i >> 1) + 1] = *reinterpret_cast<uint32_t*>(&f);
+              }
+            }
+            if (c == half * 64) {
+              mbar_wait(st_empty, ste_ph ^ 1);   // output MMAs of the previous tile no longer read the staging tiles
+              ste_ph ^= 1;
+            }
+            const int off = (c >> 6) * 16384 + r * 128;
+            const int chunk0 = (c & 63) >> 3;
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+              const int ch = (chunk0 + t) ^ (r & 7);
+              *reinterpret_cast<uint4*>(sP_ptr + off + ch * 16) = make_uint4(pp[4 * t], pp[4 * t + 1], pp[4 * t + 2], pp[4 * t + 3]);
+              *reinterpret_cast<uint4*>(sDS_ptr + off + ch * 16) = make_uint4(pd[4 * t], pd[4 * t + 1], pd[4 * t + 2], pd[4 * t + 3]);
+            }
+          }
+        };
+        const bool full = (nvalid == 128) && __all_sync(0xffffffffu, kvalid);
+        if (p.dtype == CSN_F16) {
+          if (full) ew_tile(std::true_type{}, std::true_type{}); else ew_tile(std::true_type{}, std::false_type{});
+        } else {
+          if (full) ew_tile(std::false_type{}, std::true_type{}); else ew_tile(std::false_type{}, std::false_type{});
+        }
+        tc_fence_before();
+        mbar_arrive(sdp_empty);
+        fence_proxy_async_smem();
+        mbar_arrive(st_full);
+        if (et < 128 && j + 1 < nq) {   // statistics of tile j+1 into the other buffer (its readers passed this tile's barrier)
+          stat[((j + 1) & 1) * 256 + et] = nl;
+          stat[((j + 1) & 1) * 256 + 128 + et] = nd;
+        }
+      }
+      // ---- epilogue: warps 4-7 write dV, warps 8-11 dK; each warp stages its 32 rows in its own rows of one of the
+      //      (now idle) staging tiles and hands the [32 x 64] slab to the TMA store engine
+      mbar_wait(acc_full, accf_ph);
+      accf_ph ^= 1;
+      tc_fence_after();
+      {
+        const uint32_t o_addr = tmem_base + lane_addr + (half == 0 ? Cfg::DV_COL : Cfg::DK_COL);
+        uint32_t v0[32], v1[32];
+        tmem_ld_32x32(o_addr, v0);
+        tmem_ld_32x32(o_addr + 32, v1);
+        tmem_ld_wait();
+        tc_fence_before();
+        mbar_arrive(acc_empty);   // the accumulators are in registers
+        uint32_t w[32];
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) {
+          const float a0 = kvalid ? __uint_as_float(v0[i]) : 0.f, a1 = kvalid ? __uint_as_float(v0[i + 1]) : 0.f;
+          const float b0 = kvalid ? __uint_as_float(v1[i]) : 0.f, b1 = kvalid ? __uint_as_float(v1[i + 1]) : 0.f;
+          if (p.dtype == CSN_F16) {
+            __half2 x = __floats2half2_rn(a0, a1), y = __floats2half2_rn(b0, b1);
+            w[i >> 1] = *reinterpret_cast<uint32_t*>(&x); w[16 + (i >> 1)] = *reinterpret_cast<uint32_t*>(&y);
+          } else {
+            __nv_bfloat162 x = __floats2bfloat162_rn(a0, a1), y = __floats2bfloat162_rn(b0, b1);
+            w[i >> 1] = *reinterpret_cast<uint32_t*>(&x); w[16 + (i >> 1)] = *reinterpret_cast<uint32_t*>(&y);
+          }
+        }
+        // the last output MMAs of this item have completed (acc_full): the staging tiles are idle
+        const uint32_t buf = (half == 0 ? sP : sDS) + q * 4096;
+        const uint32_t rowaddr = buf + lane * 128;
+#pragma unroll
+        for (int t = 0; t < 8; ++t) {
+          const uint32_t a = rowaddr + (((uint32_t)t ^ ((uint32_t)lane & 7u)) << 4);
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(w[4 * t]), "r"(w[4 * t + 1]), "r"(w[4 * t + 2]), "r"(w[4 * t + 3]) : "memory");
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (elect_one()) {
+          tma_store_2d(half == 0 ? &tmDV : &tmDK, buf, it.col0, it.o_row0 + q * 32);
+          tma_store_commit();
+          tma_store_wait_read<0>();   // the slab is rewritten by the next item's first tile
+        }
+        __syncwarp();
+      }
+    }
+    if (lane == 0) tma_store_wait_all();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+template <bool DROP>
+static int launch_dkv(const CUtensorMap& tmK, const CUtensorMap& tmV, const CUtensorMap& tmQ, const CUtensorMap& tmDO,
+                      const CUtensorMap& tmDK, const CUtensorMap& tmDV, const DkvArgs& a, cudaStream_t stream) {
+  auto kern = attn_bwd_dkv_kernel<DROP>;
+  static bool configured = false;
+  if (!configured) {
+    CSN_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, DkvCfg::SMEM_BYTES));
+    configured = true;
+  }
+  const int grid = a.n_items < num_sms() ? a.n_items : num_sms();
+  kern<<<grid, DkvCfg::THREADS, DkvCfg::SMEM_BYTES, stream>>>(tmK, tmV, tmQ, tmDO, tmDK, tmDV, a);
+  CSN_LAUNCH_OK("attn_bwd_dkv_kernel");
+  return 0;
+}
+
+}  // namespace csn
+
+extern "C" int csn_attn_bwd_dkv(const void* K, const void* V, const void* Q, const void* dO, int64_t kv_rows, int64_t q_rows,
+                                int64_t do_rows, int64_t width, int64_t ldk, int64_t ldv, int64_t ldq, int64_t lddo,
+                                int32_t d_head, int32_t dtype, const int32_t* items, int32_t n_items, void* dK, void* dV,
+                                int64_t out_rows, int64_t ldout, const float* lse, const float* delta,
+                                uint32_t drop_seed, float drop_p, void* stream) {
+  using namespace csn;
+  clear_error();
+  CSN_CHECK_ARG(K && V && Q && dO && items && dK && dV && lse && delta, "csn_attn_bwd_dkv: null pointer");
+  CSN_CHECK_ARG(drop_p >= 0.f && drop_p < 1.f, "csn_attn_bwd_dkv: dropout probability %f outside [0, 1)", (double)drop_p);
+  CSN_CHECK_ARG(d_head == 64, "csn_attn_bwd_dkv: d_head=%d not supported (64: both output accumulators must fit in TMEM)", d_head);
+  CSN_CHECK_ARG(dtype == CSN_F16 || dtype == CSN_BF16, "csn_attn_bwd_dkv: 16-bit operands only");
+  CSN_CHECK_ARG((ldout * 2) % 16 == 0, "csn_attn_bwd_dkv: output stride must be a 16B multiple");
+  if (n_items == 0) return 0;
+  CUtensorMap tmK, tmV, tmQ, tmDO, tmDK, tmDV;
+  int rc = make_tmap_2d(&tmK, K, dtype, width, kv_rows, ldk, 64, 128);
+  if (rc) return rc;
+  rc = make_tmap_2d(&tmV, V, dtype, width, kv_rows, ldv, 64, 128);
+  if (rc) return rc;
+  rc = make_tmap_2d(&tmQ, Q, dtype, width, q_rows, ldq, 64, 128);
+  if (rc) return rc;
+  rc = make_tmap_2d(&tmDO, dO, dtype, width, do_rows, lddo, 64, 128);
+  if (rc) return rc;
+  rc = make_tmap_2d(&tmDK, dK, dtype, width, out_rows, ldout, 64, 32);
+  if (rc) return rc;
+  rc = make_tmap_2d(&tmDV, dV, dtype, width, out_rows, ldout, 64, 32);
+  if (rc) return rc;
+  DkvArgs a;
+  a.items = reinterpret_cast<const DkvItem*>(items);
+  a.n_items = n_items;
+  a.lse = lse;
+  a.delta = delta;
+  a.scale = 1.0f / sqrtf((float)d_head);
+  a.scale_log2 = a.scale * 1.4426950408889634f;
+  a.dtype = dtype;
+  const uint32_t fmt = dtype == CSN_F16 ? 0u : 1u;
+  a.idesc_s = umma_idesc_f16(fmt, 0, 0, 128);
+  a.idesc_o = umma_idesc_f16(fmt, 0, 1, 64);
+  a.drop_seed = drop_seed;
+  a.drop_thresh = drop_thresh16(drop_p);
+  a.drop_scale = drop_scale_of(a.drop_thresh);
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  return a.drop_thresh ? launch_dkv<true>(tmK, tmV, tmQ, tmDO, tmDK, tmDV, a, s) : launch_dkv<false>(tmK, tmV, tmQ, tmDO, tmDK, tmDV, a, s);
+}

@@ -196,7 +196,7 @@ def attn_items(groups, geom: Geometry, n_head: int, d: int, device, kind: str = 
                         valid = max(0, min(128, q_len - t_ * 128))      # query rows of tile t_
                         kvalid = max(0, min(128, kv_len - t_ * 128))    # key rows of tile t_
                         stat = (j * n_head + h) * NP + c * CP
-                        if ragged and (kvalid if kind == "dv" else valid) == 0:
+                        if ragged and (kvalid if kind in ("dv", "dkv") else valid) == 0:
                             continue
                         if kind == "fwd":
                             rows.append((qs * NP + c * CP + t_ * 128, valid, ks * NP + c * CP, kv_len,
@@ -204,6 +204,9 @@ def attn_items(groups, geom: Geometry, n_head: int, d: int, device, kind: str = 
                         elif kind == "dv":   # resident tile = keys; streamed = queries (Q view) and dO (block rows)
                             rows.append((ks * NP + c * CP + t_ * 128, kvalid, qs * NP + c * CP, q_len,
                                          j * NP + c * CP + t_ * 128, h * d, stat, 1, j * NP + c * CP, t_ * 128))
+                        elif kind == "dkv":  # csn_attn_bwd_dkv: resident keys, streamed queries + dO, per-query statistics
+                            rows.append((ks * NP + c * CP + t_ * 128, kvalid, qs * NP + c * CP, q_len,
+                                         j * NP + c * CP + t_ * 128, h * d, stat, j * NP + c * CP, t_ * 128, 0, 0, 0))
                         else:                # dq
                             rows.append((qs * NP + c * CP + t_ * 128, valid, ks * NP + c * CP, kv_len,
                                          j * NP + c * CP + t_ * 128, h * d, stat + t_ * 128,
@@ -322,7 +325,8 @@ def attention_forward(Xh, Xf, groups, n_slots, n_blocks, w_q, w_k, w_v, w_o, gam
         # --- fused flash-style core (csa_models.py:139-142): scores never leave TMEM
         items = attn_items(groups, geom, n_head, d, dev)
         lse = torch.empty(n_blocks * n_head * NP, dtype=torch.float32, device=dev)
-        O_lo = (torch.zeros_like(O) if ragged else torch.empty_like(O)) if (torch.is_grad_enabled() or save_for_backward) and not center else None
+        want_lo = (torch.is_grad_enabled() or save_for_backward) and not center and os.environ.get("CSN_O_LO", "1") == "1"
+        O_lo = (torch.zeros_like(O) if ragged else torch.empty_like(O)) if want_lo else None
         rc = L.lib().csn_attn_fwd(Qv.data_ptr(), Kv.data_ptr(), Vv.data_ptr(), n_slots * NP, n_slots * NP, HD,
                                   3 * HD, 3 * HD, 3 * HD, d, L.dtype_code(dt), items.data_ptr(), items.shape[0],
                                   O.data_ptr(), O.shape[0], HD, lse.data_ptr(), O_lo.data_ptr() if O_lo is not None else None,
@@ -447,6 +451,59 @@ def _pick_split(tiles: int, kb_total: int, target: int = 296) -> int:
     return max(1, min(-(-target // max(tiles, 1)), max(1, kb_total // 8)))
 
 
+def _attention_backward_ds(ctx, lib, dO, dQKV, lse, delta, drop, ragged):
+    """dV kernel + dS to HBM (+ dQ inside the kernel at d_head 64) + dK = dS^T Q (and dQ = dS K) as GEMMs: the
+    d_head-256 path (S, dP and a [128 x 256] dQ accumulator do not fit in TMEM together)."""
+    geom, h, d = ctx.geom, ctx.n_head, ctx.d_head
+    NP, CP, NC = geom.rows_pad, geom.chunk_pad, geom.n_chunks
+    HD = h * d
+    S, nblk = ctx.n_slots, ctx.n_blocks
+    dev, dt = ctx.Xh.device, ctx.Xh.dtype
+    Qv, Kv, Vv = ctx.QKV[:, :HD], ctx.QKV[:, HD:2 * HD], ctx.QKV[:, 2 * HD:]
+    dQv, dKv, dVv = dQKV[:, :HD], dQKV[:, HD:2 * HD], dQKV[:, 2 * HD:]
+    prow = NC * h * CP
+    it_dv = attn_items(ctx.groups, geom, h, d, dev, "dv")
+    rc = lib.csn_attn_bwd_dv(Kv.data_ptr(), Qv.data_ptr(), dO.data_ptr(), S * NP, S * NP, nblk * NP, HD, 3 * HD, 3 * HD, HD,
+                             d, L.dtype_code(dt), it_dv.data_ptr(), it_dv.shape[0], dVv.data_ptr(), nblk * NP, 3 * HD,
+                             lse.data_ptr(), _paired(geom), drop[1], drop[0], L.stream_ptr())
+    L.check(rc, "csn_attn_bwd_dv")
+    # the dQ kernel writes the key tiles it visits; columns beyond them must read as zeros in dS^T Q
+    if ragged:
+        dS = _zeroed_workspace(nblk * prow * CP, dt, dev).view(nblk * prow, CP)
+    else:
+        alloc = torch.empty if ((geom.kv_len + 127) // 128) * 128 >= CP else torch.zeros
+        dS = alloc(nblk * prow, CP, dtype=dt, device=dev)
+    it_dq = attn_items(ctx.groups, geom, h, d, dev, "dq")
+    # dQ inside the kernel: slower at d_head 256 (re-reads K_j through a shallow ring), faster at d_head 64
+    fuse_dq = os.environ.get("CSN_FUSED_DQ", "1" if d == 64 else "0") == "1"
+    rc = lib.csn_attn_bwd_dq(Qv.data_ptr(), dO.data_ptr(), Kv.data_ptr(), Vv.data_ptr(), S * NP, nblk * NP, S * NP,
+                             HD, 3 * HD, HD, 3 * HD, 3 * HD, d, L.dtype_code(dt), it_dq.data_ptr(),
+                             it_dq.shape[0], dQv.data_ptr() if fuse_dq else None, 3 * HD, dS.data_ptr(),
+                             dS.shape[0], CP, lse.data_ptr(), delta.data_ptr(), _paired(geom), drop[1], drop[0],
+                             L.stream_ptr())
+    L.check(rc, "csn_attn_bwd_dq")
+    for g in ctx.groups:
+        nb = (h, NC, g.n_in, g.n_out)
+        dSk = L.mat(dS[g.blk0 * prow:], L.MAJOR_K, mn_off=(CP, h * CP, prow, g.n_in * prow))
+        dSt = L.mat(dS[g.blk0 * prow:], L.MAJOR_MN, k_off=(CP, h * CP, prow, g.n_in * prow))          # dS^T
+        Km = L.mat(Kv[g.k0 * NP:], L.MAJOR_MN, mn_off=(d, 0, 0, 0), k_off=(0, CP, g.k_si * NP, g.k_so * NP))
+        Qm = L.mat(Qv[g.q0 * NP:], L.MAJOR_MN, mn_off=(d, 0, 0, 0), k_off=(0, CP, g.q_si * NP, g.q_so * NP))
+        off = (d, CP * 3 * HD, NP * 3 * HD, g.n_in * NP * 3 * HD)
+        if not fuse_dq and d > 128 and os.environ.get("CSN_GEMM_DUAL", "1") != "0":
+            # dQ = dS K and dK = dS^T Q in ONE launch, tiles of the same (block, chunk) back to back: the second
+            # read of the dS tile comes from L2 (csn_gemm_dual)
+            nb4 = (C.c_int32 * 4)(*[int(v) for v in nb])
+            D0 = L.out(dQv[g.blk0 * NP:], 3 * HD, off=off)
+            D1 = L.out(dKv[g.blk0 * NP:], 3 * HD, off=off)
+            rc = lib.csn_gemm_dual(C.byref(dSk), C.byref(Km), C.byref(D0), C.byref(dSt), C.byref(Qm), C.byref(D1),
+                                   CP, d, CP, nb4, 1.0, L.stream_ptr())
+            L.check(rc, "csn_gemm_dual")
+            continue
+        if not fuse_dq:
+            L.gemm(dSk, Km, L.out(dQv[g.blk0 * NP:], 3 * HD, off=off), CP, d, CP, nb=nb)    # dQ = dS K
+        L.gemm(dSt, Qm, L.out(dKv[g.blk0 * NP:], 3 * HD, off=off), CP, d, CP, nb=nb)    # dK = dS^T Q
+
+
 _WORKSPACES: dict = {}
 
 
@@ -544,46 +601,25 @@ def attention_backward(ctx: AttnContext, dY: torch.Tensor, need_dx: bool, amax: 
             rc = lib.csn_attn_delta(dO.data_ptr(), ctx.O.data_ptr(), O_lo.data_ptr() if O_lo is not None else None,
                                     delta.data_ptr(), nblk * NP, NP, h, d, HD, L.dtype_code(dt), L.stream_ptr())
             L.check(rc, "csn_attn_delta")
-        it_dv = attn_items(ctx.groups, geom, h, d, dev, "dv")
-        rc = lib.csn_attn_bwd_dv(Kv.data_ptr(), Qv.data_ptr(), dO.data_ptr(), S * NP, S * NP, nblk * NP, HD, 3 * HD, 3 * HD, HD,
-                                 d, L.dtype_code(dt), it_dv.data_ptr(), it_dv.shape[0], dVv.data_ptr(), nblk * NP, 3 * HD,
-                                 lse.data_ptr(), _paired(geom), drop[1], drop[0], L.stream_ptr())
-        L.check(rc, "csn_attn_bwd_dv")
-        # the dQ kernel writes the key tiles it visits; columns beyond them must read as zeros in dS^T Q
-        if ragged:
-            dS = _zeroed_workspace(nblk * prow * CP, dt, dev).view(nblk * prow, CP)
+        # d_head 64: dK and dV from ONE key-stationary kernel, dQ from the query-stationary one, dS never materialised
+        # (S^T, dP^T and both output accumulators fit in TMEM: attn_dkv.cu).  CSN_FUSED_DKV=0 keeps the older
+        # dV kernel + dS buffer + dK GEMM for cross-checks.
+        fuse_dkv = d == 64 and os.environ.get("CSN_FUSED_DKV", "1") == "1" and os.environ.get("CSN_FUSED_DQ", "1") == "1"
+        if fuse_dkv:
+            it_kv = attn_items(ctx.groups, geom, h, d, dev, "dkv")
+            rc = lib.csn_attn_bwd_dkv(Kv.data_ptr(), Vv.data_ptr(), Qv.data_ptr(), dO.data_ptr(), S * NP, S * NP, nblk * NP, HD,
+                                      3 * HD, 3 * HD, 3 * HD, HD, d, L.dtype_code(dt), it_kv.data_ptr(), it_kv.shape[0],
+                                      dKv.data_ptr(), dVv.data_ptr(), nblk * NP, 3 * HD, lse.data_ptr(), delta.data_ptr(),
+                                      drop[1], drop[0], L.stream_ptr())
+            L.check(rc, "csn_attn_bwd_dkv")
+            it_dq = attn_items(ctx.groups, geom, h, d, dev, "dq")
+            rc = lib.csn_attn_bwd_dq(Qv.data_ptr(), dO.data_ptr(), Kv.data_ptr(), Vv.data_ptr(), S * NP, nblk * NP, S * NP,
+                                     HD, 3 * HD, HD, 3 * HD, 3 * HD, d, L.dtype_code(dt), it_dq.data_ptr(),
+                                     it_dq.shape[0], dQv.data_ptr(), 3 * HD, None, 0, CP, lse.data_ptr(), delta.data_ptr(),
+                                     _paired(geom), drop[1], drop[0], L.stream_ptr())
+            L.check(rc, "csn_attn_bwd_dq")
         else:
-            alloc = torch.empty if ((geom.kv_len + 127) // 128) * 128 >= CP else torch.zeros
-            dS = alloc(nblk * prow, CP, dtype=dt, device=dev)
-        it_dq = attn_items(ctx.groups, geom, h, d, dev, "dq")
-        # dQ inside the kernel: slower at d_head 256 (re-reads K_j through a shallow ring), faster at d_head 64
-        fuse_dq = os.environ.get("CSN_FUSED_DQ", "1" if d == 64 else "0") == "1"
-        rc = lib.csn_attn_bwd_dq(Qv.data_ptr(), dO.data_ptr(), Kv.data_ptr(), Vv.data_ptr(), S * NP, nblk * NP, S * NP,
-                                 HD, 3 * HD, HD, 3 * HD, 3 * HD, d, L.dtype_code(dt), it_dq.data_ptr(),
-                                 it_dq.shape[0], dQv.data_ptr() if fuse_dq else None, 3 * HD, dS.data_ptr(),
-                                 dS.shape[0], CP, lse.data_ptr(), delta.data_ptr(), _paired(geom), drop[1], drop[0],
-                                 L.stream_ptr())
-        L.check(rc, "csn_attn_bwd_dq")
-        for g in ctx.groups:
-            nb = (h, NC, g.n_in, g.n_out)
-            dSk = L.mat(dS[g.blk0 * prow:], L.MAJOR_K, mn_off=(CP, h * CP, prow, g.n_in * prow))
-            dSt = L.mat(dS[g.blk0 * prow:], L.MAJOR_MN, k_off=(CP, h * CP, prow, g.n_in * prow))          # dS^T
-            Km = L.mat(Kv[g.k0 * NP:], L.MAJOR_MN, mn_off=(d, 0, 0, 0), k_off=(0, CP, g.k_si * NP, g.k_so * NP))
-            Qm = L.mat(Qv[g.q0 * NP:], L.MAJOR_MN, mn_off=(d, 0, 0, 0), k_off=(0, CP, g.q_si * NP, g.q_so * NP))
-            off = (d, CP * 3 * HD, NP * 3 * HD, g.n_in * NP * 3 * HD)
-            if not fuse_dq and d > 128 and os.environ.get("CSN_GEMM_DUAL", "1") != "0":
-                # dQ = dS K and dK = dS^T Q in ONE launch, tiles of the same (block, chunk) back to back: the second
-                # read of the dS tile comes from L2 (csn_gemm_dual)
-                nb4 = (C.c_int32 * 4)(*[int(v) for v in nb])
-                D0 = L.out(dQv[g.blk0 * NP:], 3 * HD, off=off)
-                D1 = L.out(dKv[g.blk0 * NP:], 3 * HD, off=off)
-                rc = lib.csn_gemm_dual(C.byref(dSk), C.byref(Km), C.byref(D0), C.byref(dSt), C.byref(Qm), C.byref(D1),
-                                       CP, d, CP, nb4, 1.0, L.stream_ptr())
-                L.check(rc, "csn_gemm_dual")
-                continue
-            if not fuse_dq:
-                L.gemm(dSk, Km, L.out(dQv[g.blk0 * NP:], 3 * HD, off=off), CP, d, CP, nb=nb)    # dQ = dS K
-            L.gemm(dSt, Qm, L.out(dKv[g.blk0 * NP:], 3 * HD, off=off), CP, d, CP, nb=nb)    # dK = dS^T Q
+            _attention_backward_ds(ctx, lib, dO, dQKV, lse, delta, drop, ragged)
     else:
         if drop[0] > 0.0:
             raise L.CsnError("training-mode dropout needs the fused attention backward (CSN_FUSED_BWD=1)")

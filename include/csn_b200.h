@@ -167,6 +167,21 @@ int csn_attn_fwd(const void* Q, const void* K, const void* V, int64_t q_rows, in
                  int32_t n_items, void* O, int64_t o_rows, int64_t ldo, float* lse, void* O_lo, int32_t paired,
                  uint32_t drop_seed, float drop_p, void* stream);
 
+/* Key-stationary attention backward for d_head = 64: dK = dS^T Q and dV = P^T dO of one 128-key tile per item in
+ * ONE pass, P and dS recomputed per tile from K, V, Q, dO, lse and delta and never written to memory (autograd of
+ * ScaledDotProductAttention.forward, MinkowskiNet/models/attention.py:69-75, MID-FC/csa_models.py:138-144, which
+ * keep the (B, h, Lq, Lk) attention matrix).  With csn_attn_bwd_dq(dS = NULL) this is the whole attention
+ * backward in O(L) memory.  items: n_items x 12 int32 {k_row0, k_valid, q_row0, q_len, o_row0, col0, stat_off,
+ * do_row0, key0, 0, 0, 0}: resident key rows [k_row0, +128) of the K / V views (k_valid of them exist), streamed
+ * query rows [q_row0, q_row0 + q_len) of the Q view and [do_row0, ...) of dO, lse / delta of streamed query n at
+ * [stat_off + n], outputs at rows [o_row0, +128) x columns [col0, +64) of dK and dV (rows >= k_valid: zeros).
+ * key0 = index of the first resident key inside its chunk (dropout mask column, see the dropout paragraph). */
+int csn_attn_bwd_dkv(const void* K, const void* V, const void* Q, const void* dO, int64_t kv_rows, int64_t q_rows,
+                     int64_t do_rows, int64_t width, int64_t ldk, int64_t ldv, int64_t ldq, int64_t lddo,
+                     int32_t d_head, int32_t dtype, const int32_t* items, int32_t n_items, void* dK, void* dV,
+                     int64_t out_rows, int64_t ldout, const float* lse, const float* delta,
+                     uint32_t drop_seed, float drop_p, void* stream);
+
 /* Backward of the attention core (autograd of csa_models.py:139-142), three pieces:
  *  csn_attn_delta : delta[(blk*h+head)*rows_pad + r] = sum_c dO[blk*rows_pad+r][head*d+c] * (O + O_lo/2^11)[..]
  *  csn_attn_bwd_dv: dV = P^T dO, P^T rebuilt from K, Q and the forward lse. Same kernel and item layout
