@@ -307,6 +307,10 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
             tmem_ld_32x32(s_addr + c, sv);
             tmem_ld_32x32(s_addr + 128 + c, dv);
             tmem_ld_wait();
+            if (c + 32 >= half * COLS + COLS) {   // this thread's scores are in registers: the MMA warp may overwrite them
+              tc_fence_before();
+              mbar_arrive(sdp_empty(b));
+            }
             uint32_t pk[16];
 #pragma unroll
             for (int i = 0; i < 32; i += 2) {
@@ -354,8 +358,6 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         } else {
           if (full) ew_tile(std::false_type{}, std::true_type{}); else ew_tile(std::false_type{}, std::false_type{});
         }
-        tc_fence_before();
-        mbar_arrive(sdp_empty(b));
         fence_proxy_async_smem();
         if (WITH_DQ) mbar_arrive(ds_full);
         // HBM copy of dS_j for dK = dS^T Q: the staged tile is exactly two TMA boxes [128 rows x 64 keys]

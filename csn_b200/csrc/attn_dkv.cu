@@ -6,14 +6,14 @@
 // is the whole attention backward in two passes and O(L) memory: at d_head 64 the two [128 x 128] score
 // accumulators and BOTH [128 x 64] output accumulators fit in TMEM (128 + 128 + 64 + 64 = 384 columns).
 //
-// CTA = 384 threads, one per SM, persistent over items:
+// CTA = 640 threads, one per SM, persistent over items:
 //   warp 0     TMA producer : K_i, V_i resident per item; ring of 16 KB slots streaming Q_j, dO_j (for the score
 //                             MMAs, K-major) and again dO_j, Q_j (for the output MMAs, MN-major: same bytes)
 //   warp 1     MMA issuer   : S^T = K_i Q_j^T, dP^T = V_i dO_j^T (lane = key, column = query), then
 //                             dV += P^T dO_j, dK += dS^T Q_j; the score MMAs of tile j+1 go ahead of the output
 //                             MMAs of tile j
 //   warp 2     TMEM allocator
-//   warps 4-11 element-wise : two warps per TMEM lane quadrant (64 query columns each).  lse / delta are per
+//   warps 4-19 element-wise : four warps per TMEM lane quadrant (32 query columns each).  lse / delta are per
 //                             COLUMN here: staged per tile in SMEM and read as broadcast float4.
 //                             P^T and dS^T -> two 128B-swizzled SMEM tiles = A operands of the output MMAs.
 //                             Epilogue: warps 4-7 write dV, warps 8-11 dK (TMA stores).
@@ -55,7 +55,12 @@ struct DkvCfg {
   static constexpr int ST_BYTES = 128 * 128 * 2;      // P^T, dS^T staging tiles
   static constexpr int SLOT_BYTES = 128 * 64 * 2;
   static constexpr int NST = 6;
-  static constexpr int EW_WARPS = 8;
+#ifndef CSN_DKV_EW_WARPS
+#define CSN_DKV_EW_WARPS 16
+#endif
+  static constexpr int EW_WARPS = CSN_DKV_EW_WARPS;    // 8: 64 query columns per thread in steps of 32; 16: 32 in steps of 16
+  static constexpr int COLS = 128 / (EW_WARPS / 4);
+  static constexpr int CW = EW_WARPS == 16 ? 16 : 32;   // columns per tcgen05.ld
   static constexpr int EW_THREADS = 32 * EW_WARPS;
   static constexpr int THREADS = 128 + EW_THREADS;
   static constexpr int STAT_BYTES = 2 * 2 * 128 * 4;  // [buffer][lse | delta][128 queries]
@@ -222,7 +227,8 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_consta
   } else if (warp >= 4) {
     // ================================================================== element-wise stage + epilogue
     const int q = warp & 3;
-    const int half = (warp - 4) >> 2;            // query columns [64 half, 64 half + 64)
+    const int half = (warp - 4) >> 2;            // query columns [COLS half, COLS half + COLS)
+    constexpr int COLS = Cfg::COLS, CW = Cfg::CW;
     const int r = q * 32 + lane;                 // key row of the tile owned by this thread
     const int et = threadIdx.x - 128;            // 0 .. EW_THREADS-1
     const uint32_t lane_addr = uint32_t(q * 32) << 16;
@@ -259,14 +265,18 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_consta
         auto ew_tile = [&](auto F16C, auto FULLC) {
           constexpr bool F16 = decltype(F16C)::value, FULL = decltype(FULLC)::value;
 #pragma unroll 1
-          for (int c = half * 64; c < half * 64 + 64; c += 32) {
-            uint32_t sv[32], dv[32];
-            tmem_ld_32x32(s_addr + c, sv);
-            tmem_ld_32x32(s_addr + 128 + c, dv);
+          for (int c = half * COLS; c < half * COLS + COLS; c += CW) {
+            uint32_t sv[CW], dv[CW];
+            tmem_ld_cols(s_addr + c, sv);
+            tmem_ld_cols(s_addr + 128 + c, dv);
             tmem_ld_wait();
-            uint32_t pp[16], pd[16];
+            if (c + CW == half * COLS + COLS) {   // this thread's scores are in registers: the MMA warp may overwrite them
+              tc_fence_before();
+              mbar_arrive(sdp_empty);
+            }
+            uint32_t pp[CW / 2], pd[CW / 2];
 #pragma unroll
-            for (int i = 0; i < 32; i += 4) {
+            for (int i = 0; i < CW; i += 4) {
               const float4 l4 = *reinterpret_cast<const float4*>(st_l + c + i);
               const float4 d4 = *reinterpret_cast<const float4*>(st_d + c + i);
               const float ls[4] = {l4.x, l4.y, l4.z, l4.w}, ds_[4] = {d4.x, d4.y, d4.z, d4.w};
@@ -300,14 +310,14 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_consta
                 pd[i >> 1] = *reinterpret_cast<uint32_t*>(&e); pd[(i >> 1) + 1] = *reinterpret_cast<uint32_t*>(&f);
               }
             }
-            if (c == half * 64) {
+            if (c == half * COLS) {
               mbar_wait(st_empty, ste_ph ^ 1);   // output MMAs of the previous tile no longer read the staging tiles
               ste_ph ^= 1;
             }
             const int off = (c >> 6) * 16384 + r * 128;
             const int chunk0 = (c & 63) >> 3;
 #pragma unroll
-            for (int t = 0; t < 4; ++t) {
+            for (int t = 0; t < CW / 8; ++t) {
               const int ch = (chunk0 + t) ^ (r & 7);
               *reinterpret_cast<uint4*>(sP_ptr + off + ch * 16) = make_uint4(pp[4 * t], pp[4 * t + 1], pp[4 * t + 2], pp[4 * t + 3]);
               *reinterpret_cast<uint4*>(sDS_ptr + off + ch * 16) = make_uint4(pd[4 * t], pd[4 * t + 1], pd[4 * t + 2], pd[4 * t + 3]);
@@ -320,8 +330,6 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_consta
         } else {
           if (full) ew_tile(std::false_type{}, std::true_type{}); else ew_tile(std::false_type{}, std::false_type{});
         }
-        tc_fence_before();
-        mbar_arrive(sdp_empty);
         fence_proxy_async_smem();
         mbar_arrive(st_full);
         if (et < 128 && j + 1 < nq) {   // statistics of tile j+1 into the other buffer (its readers passed this tile's barrier)
@@ -334,7 +342,9 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_consta
       mbar_wait(acc_full, accf_ph);
       accf_ph ^= 1;
       tc_fence_after();
-      {
+      if (half >= 2) {
+        mbar_arrive(acc_empty);
+      } else {
         const uint32_t o_addr = tmem_base + lane_addr + (half == 0 ? Cfg::DV_COL : Cfg::DK_COL);
         uint32_t v0[32], v1[32];
         tmem_ld_32x32(o_addr, v0);
