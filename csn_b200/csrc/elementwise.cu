@@ -744,6 +744,37 @@ static int launch_simple(K kern, dim3 grid, dim3 block, const A& args, void* str
 }  // namespace csn
 
 namespace csn {
+// dst[s][e] = (dst[s][e] + sum over source blocks j with dst_block[j] == s of src[j][e]) * unscale:
+// the residual path of the attention backward (dX[query slot] += dZ[block]) as a deterministic gather.
+__global__ void __launch_bounds__(256) block_add_kernel(const float* __restrict__ src, const int* __restrict__ dst_block, int n_src,
+                                                        float* __restrict__ dst, long long block_elems, const float* __restrict__ amax) {
+  __shared__ int mine[256];
+  __shared__ int n_mine;
+  const int s = blockIdx.y;
+  if (threadIdx.x == 0) {
+    int n = 0;
+    for (int j = 0; j < n_src && n < 256; ++j)
+      if (dst_block[j] == s) mine[n++] = j;
+    n_mine = n;
+  }
+  __syncthreads();
+  const float inv = amax ? 1.f / exp2f(floorf(log2f(128.f / fmaxf(__ldg(amax), 1e-30f)))) : 1.f;
+  const int n = n_mine;
+  float4* d4 = reinterpret_cast<float4*>(dst + (long long)s * block_elems);
+  const long long n4 = block_elems >> 2;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n4; e += (long long)gridDim.x * blockDim.x) {
+    float4 a = d4[e];
+    for (int k = 0; k < n; ++k) {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(src + (long long)mine[k] * block_elems) + e);
+      a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+    }
+    a.x *= inv; a.y *= inv; a.z *= inv; a.w *= inv;
+    d4[e] = a;
+  }
+}
+}  // namespace csn
+
+namespace csn {
 // out[s][c] = mean of x[offsets[s] .. offsets[s+1])[c]: CTA = (segment, 32-column group), 8 row lanes per column.
 __global__ void __launch_bounds__(256) segment_mean_kernel(const float* __restrict__ x, const long long* __restrict__ offsets,
                                                            int n_cols, float* __restrict__ out) {
@@ -898,6 +929,24 @@ int csn_segment_mean(const float* x, const int64_t* offsets, int32_t n_seg, int3
   segment_mean_kernel<<<dim3(n_seg, (n_cols + 31) / 32), 256, 0, (cudaStream_t)stream>>>(
       x, reinterpret_cast<const long long*>(offsets), n_cols, out);
   CSN_LAUNCH_OK("segment_mean_kernel");
+  return 0;
+}
+
+int csn_block_add(const float* src, const int32_t* dst_block, int32_t n_src, float* dst, int32_t n_dst, int64_t block_elems,
+                  const float* amax, void* stream) {
+  using namespace csn;
+  clear_error();
+  CSN_CHECK_ARG(src && dst_block && dst, "csn_block_add: null pointer");
+  CSN_CHECK_ARG(block_elems % 4 == 0, "csn_block_add: block size must be a multiple of 4 elements");
+  CSN_CHECK_ARG(n_src >= 0 && n_src <= 4096 && n_dst >= 0, "csn_block_add: bad block counts");
+  if (n_dst == 0 || block_elems == 0) return 0;
+  const long long n4 = block_elems / 4;
+  long long gx = (n4 + 1023) / 1024;   // 4 float4 per thread
+  const long long cap = (4LL * num_sms() + n_dst - 1) / n_dst;
+  if (gx > cap) gx = cap;
+  if (gx < 1) gx = 1;
+  block_add_kernel<<<dim3((unsigned)gx, (unsigned)n_dst), 256, 0, (cudaStream_t)stream>>>(src, dst_block, n_src, dst, block_elems, amax);
+  CSN_LAUNCH_OK("block_add_kernel");
   return 0;
 }
 

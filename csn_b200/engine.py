@@ -669,15 +669,14 @@ def attention_backward(ctx: AttnContext, dY: torch.Tensor, need_dx: bool, amax: 
                 L.gemm(A, B, D, NP, 256, HD, nb=nb)
         if split_v:
             grads["dXv"] = dXv
-        # residual path: dX[q slot] += dZ[block]
-        dX3 = dX.view(S, NP, 256)
-        dZ3 = dZ.view(nblk, NP, 256)
-        dX3.index_add_(0, ctx.res_block.long(), dZ3)
+        # residual path: dX[q slot] += dZ[block], and the loss scale taken out in the same pass
+        rc = lib.csn_block_add(dZ.data_ptr(), ctx.res_block.data_ptr(), nblk, dX.data_ptr(), S, NP * 256, amax.data_ptr(),
+                               L.stream_ptr())
+        L.check(rc, "csn_block_add")
         grads["dX"] = dX
     rc = lib.csn_grad_unscale(gflat.data_ptr(), gflat.numel(), amax.data_ptr(), L.stream_ptr())
     L.check(rc, "csn_grad_unscale")
-    for key in ("dX", "dXv"):
-        if key in grads:
-            rc = lib.csn_grad_unscale(grads[key].data_ptr(), grads[key].numel(), amax.data_ptr(), L.stream_ptr())
-            L.check(rc, "csn_grad_unscale")
+    if "dXv" in grads:
+        rc = lib.csn_grad_unscale(grads["dXv"].data_ptr(), grads["dXv"].numel(), amax.data_ptr(), L.stream_ptr())
+        L.check(rc, "csn_grad_unscale")
     return grads

@@ -326,21 +326,21 @@ class CSAHead(nn.Module):
         lens = tuple(int(t.shape[0]) for t in shapes)
         y = self.MHA.forward_blocks(shapes, pairs, split=False)                       # rows of every pair, concatenated
         n_s, dev = len(shapes), y.device
-        # pairs 0..n_s-1 are the SSA blocks in shape order: their rows are y[:sum(lens)], one segment per shape
+        # rows of y: [SSA of the B queries | SSA of the K*B key shapes | cross blocks of neighbour 1 | ... | neighbour K];
+        # the B blocks of neighbour i are consecutive pairs with the query lengths, so every part lines up row by row
+        # with the query rows.  ONE split (its backward is one cat) instead of slices (each a zero-fill + add).
+        q_rows, tot = sum(lens[:B]), sum(lens)
+        parts = torch.split(y, [q_rows, tot - q_rows] + [q_rows] * K, dim=0)
         lens_t = torch.tensor(lens, dtype=torch.int64).to(dev, non_blocking=True)
-        pooled = _SegmentMeanFn.apply(y[:sum(lens)], lens)                            # (B(K+1), 256)
+        pooled = torch.cat([_SegmentMeanFn.apply(parts[0], lens[:B]), _SegmentMeanFn.apply(parts[1], lens[B:])])  # (B(K+1), 256)
         g_q = F.normalize(self.linear_q(pooled[:B]), dim=-1)                          # (B, 256)
         g_k = F.normalize(self.linear_k(pooled), dim=-1).view(K + 1, B, 256)          # [i][b]
         sims = torch.einsum("bd,ibd->bi", g_q, g_k) / self.sim.temperature           # (B, K+1)
         comp = F.softmax(sims, dim=1)
-        # the B blocks of neighbour i are consecutive pairs with the query lengths: slice i of y lines up row by
-        # row with the query rows, so the weighted sum is K+1 fused multiply-adds over contiguous slices
-        q_rows = sum(lens[:B])
         w_rows = torch.repeat_interleave(comp, lens_t[:B], dim=0, output_size=q_rows)  # (q_rows, K+1)
-        csa = y[:q_rows] * w_rows[:, 0:1]
-        off = sum(lens)
+        csa = parts[0] * w_rows[:, 0:1]
         for i in range(K):
-            csa = torch.addcmul(csa, y[off + i * q_rows: off + (i + 1) * q_rows], w_rows[:, i + 1:i + 2])
+            csa = torch.addcmul(csa, parts[2 + i], w_rows[:, i + 1:i + 2])
         return list(torch.split(csa, list(lens[:B]), dim=0))
 
 

@@ -370,6 +370,13 @@ int csn_ln_bwd(const float* dY, const float* Z, const float* mean, const float* 
  * every parameter gradient of a step. */
 int csn_grad_unscale(float* x, int64_t n, const float* amax, void* stream);
 
+/* dst[s] = (dst[s] + sum over j < n_src with dst_block[j] == s of src[j]) * u, blocks of block_elems fp32 values
+ * (at most 256 sources per destination); u = csn_grad_unscale's factor when amax != NULL, else 1.  The residual path
+ * of the attention backward: `q = self.layer_norm(q + residual)` (MID-FC/csa_models.py:113, attention.py:53) sends
+ * d z of every attention block to the input gradient of its query shape.  Deterministic (gather, fixed order). */
+int csn_block_add(const float* src, const int32_t* dst_block, int32_t n_src, float* dst, int32_t n_dst, int64_t block_elems,
+                  const float* amax, void* stream);
+
 /* out[s][c] = mean over rows offsets[s] <= r < offsets[s+1] of x[r][c] (x row-major, n_cols wide; empty segment -> 0):
  * the per-shape global descriptors `feats.mean(dim=0)` of MinkowskiNet/models/hrnet.py:378,388 for a ragged batch of
  * shapes in one launch.  Deterministic (fixed summation order). */

@@ -248,3 +248,22 @@ def test_segment_mean_matches_torch():
         ref = x[o:o + n].double().mean(dim=0).float() if n else torch.zeros(256, device="cuda")
         assert float((out[i] - ref).abs().max()) < 2e-6
         o += n
+
+
+def test_block_add_matches_index_add():
+    """csn_block_add (residual path of the attention backward) against index_add_ + the power-of-two unscale."""
+    from csn_b200 import _lib as L
+    g = torch.Generator().manual_seed(5)
+    n_src, n_dst, elems = 11, 4, 3 * 256
+    src = torch.randn(n_src, elems, generator=g).cuda()
+    dst0 = torch.randn(n_dst, elems, generator=g).cuda()
+    blk = torch.tensor([0, 1, 2, 3, 0, 0, 2, 1, 0, 3, 3], dtype=torch.int32).cuda()
+    amax = torch.tensor([3.0]).cuda()
+    for am in (None, amax):
+        dst = dst0.clone()
+        L.check(L.lib().csn_block_add(src.data_ptr(), blk.data_ptr(), n_src, dst.data_ptr(), n_dst, elems,
+                                      am.data_ptr() if am is not None else None, L.stream_ptr()), "block_add")
+        want = dst0.double().index_add(0, blk.long(), src.double())
+        if am is not None:
+            want = want / 2.0 ** float(torch.floor(torch.log2(128.0 / amax.double())))
+        assert float((dst.double() - want).abs().max()) < 1e-5
