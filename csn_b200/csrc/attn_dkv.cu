@@ -4,7 +4,11 @@
 // (reference: autograd of ScaledDotProductAttention.forward, MinkowskiNet/models/attention.py:69-75, which
 // keeps the full (B, h, Lq, Lk) attention matrix).  Together with csn_attn_bwd_dq (dQ, query-stationary) this
 // is the whole attention backward in two passes and O(L) memory: at d_head 64 the two [128 x 128] score
-// accumulators and BOTH [128 x 64] output accumulators fit in TMEM (128 + 128 + 64 + 64 = 384 columns).
+// accumulators, BOTH [128 x 64] output accumulators and the 16-bit P^T / dS^T operands of the output MMAs fit in
+// TMEM (128 + 128 + 64 + 64 + 64 + 64 = 512 columns): P^T and dS^T go from the element-wise warps' registers
+// straight back into TMEM (tcgen05.st) and are consumed as the A operand from there (lane = key = M, 16-bit pairs
+// along the query = K dimension), so they never touch shared memory.  (With 128B-swizzled SMEM staging tiles the
+// st.shared traffic alone was 31 % of the kernel: profiles/r2_experiments.md.)
 //
 // CTA = 640 threads, one per SM, persistent over items:
 //   warp 0     TMA producer : K_i, V_i resident per item; ring of 16 KB slots streaming Q_j, dO_j (for the score
@@ -15,7 +19,7 @@
 //   warp 2     TMEM allocator
 //   warps 4-19 element-wise : four warps per TMEM lane quadrant (32 query columns each).  lse / delta are per
 //                             COLUMN here: staged per tile in SMEM and read as broadcast float4.
-//                             P^T and dS^T -> two 128B-swizzled SMEM tiles = A operands of the output MMAs.
+//                             P^T and dS^T -> TMEM (16-bit pairs) = A operands of the output MMAs.
 //                             Epilogue: warps 4-7 write dV, warps 8-11 dK (TMA stores).
 #include <cstdlib>
 #include <type_traits>
@@ -52,9 +56,9 @@ struct DkvArgs {
 
 struct DkvCfg {
   static constexpr int TILE_BYTES = 128 * 64 * 2;     // K_i, V_i
-  static constexpr int ST_BYTES = 128 * 128 * 2;      // P^T, dS^T staging tiles
+  static constexpr int OUT_BYTES = 8 * 4096;          // output slabs of the epilogue: [32 rows x 64 columns] per warp
   static constexpr int SLOT_BYTES = 128 * 64 * 2;
-  static constexpr int NST = 6;
+  static constexpr int NST = 8;
 #ifndef CSN_DKV_EW_WARPS
 #define CSN_DKV_EW_WARPS 16
 #endif
@@ -65,8 +69,9 @@ struct DkvCfg {
   static constexpr int THREADS = 128 + EW_THREADS;
   static constexpr int STAT_BYTES = 2 * 2 * 128 * 4;  // [buffer][lse | delta][128 queries]
   static constexpr int BAR_BYTES = 256;
-  static constexpr int SMEM_BYTES = 2 * TILE_BYTES + 2 * ST_BYTES + NST * SLOT_BYTES + STAT_BYTES + BAR_BYTES + 1024;
-  static constexpr int DV_COL = 256, DK_COL = 320;    // TMEM: S^T @0, dP^T @128, dV @256, dK @320
+  static constexpr int SMEM_BYTES = 2 * TILE_BYTES + OUT_BYTES + NST * SLOT_BYTES + STAT_BYTES + BAR_BYTES + 1024;
+  // TMEM: S^T @0, dP^T @128 (fp32), dV @256, dK @320 (fp32), P^T @384, dS^T @448 (16-bit pairs: 128 queries = 64 columns)
+  static constexpr int DV_COL = 256, DK_COL = 320, PT_COL = 384, DST_COL = 448;
 };
 
 template <bool DROP>
@@ -80,12 +85,9 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_consta
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const uint32_t sK = smem_u32(smem);
   const uint32_t sV = sK + Cfg::TILE_BYTES;
-  const uint32_t sP = sV + Cfg::TILE_BYTES;
-  const uint32_t sDS = sP + Cfg::ST_BYTES;
-  const uint32_t sRing = sDS + Cfg::ST_BYTES;
-  uint8_t* sP_ptr = smem + 2 * Cfg::TILE_BYTES;
-  uint8_t* sDS_ptr = sP_ptr + Cfg::ST_BYTES;
-  float* stat = reinterpret_cast<float*>(smem + 2 * Cfg::TILE_BYTES + 2 * Cfg::ST_BYTES + Cfg::NST * Cfg::SLOT_BYTES);
+  const uint32_t sOut = sV + Cfg::TILE_BYTES;
+  const uint32_t sRing = sOut + Cfg::OUT_BYTES;
+  float* stat = reinterpret_cast<float*>(smem + 2 * Cfg::TILE_BYTES + Cfg::OUT_BYTES + Cfg::NST * Cfg::SLOT_BYTES);
   uint8_t* bar_ptr = reinterpret_cast<uint8_t*>(stat) + Cfg::STAT_BYTES;
   const uint32_t bar_base = smem_u32(bar_ptr);
   auto kv_full = [&](int s) { return bar_base + 8u * s; };
@@ -94,7 +96,7 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_consta
   const uint32_t bres_empty = bar_base + 8u * (2 * Cfg::NST + 1);  // every score MMA of the item has been issued
   const uint32_t sdp_full = bar_base + 8u * (2 * Cfg::NST + 2);    // S^T, dP^T of tile j are in TMEM
   const uint32_t sdp_empty = bar_base + 8u * (2 * Cfg::NST + 3);   // ... and have been read
-  const uint32_t st_full = bar_base + 8u * (2 * Cfg::NST + 4);     // P^T, dS^T of tile j are staged
+  const uint32_t st_full = bar_base + 8u * (2 * Cfg::NST + 4);     // P^T, dS^T of tile j are in TMEM
   const uint32_t st_empty = bar_base + 8u * (2 * Cfg::NST + 5);    // output MMAs of tile j done reading them
   const uint32_t acc_full = bar_base + 8u * (2 * Cfg::NST + 6);
   const uint32_t acc_empty = bar_base + 8u * (2 * Cfg::NST + 7);
@@ -181,16 +183,14 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_consta
         umma_commit(kv_empty(st));
         if (++st == Cfg::NST) { st = 0; ph ^= 1; }
       };
-      auto mma_out = [&](uint32_t a_stage, uint32_t d_tmem, bool accumulate) {   // D[key][d] += stage[key][query] x slot
+      auto mma_out = [&](uint32_t a_tmem, uint32_t d_tmem, bool accumulate) {   // D[key][d] += A[key][query] (TMEM) x slot
         mbar_wait(kv_full(st), ph);
         tc_fence_after();
         const uint32_t b_tile = sRing + st * Cfg::SLOT_BYTES;
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {   // 128 queries in steps of 16
-          const uint32_t a_addr = a_stage + (k >> 2) * 16384 + (k & 3) * 32;
-          umma_f16_ss(d_tmem, umma_desc_sw128(a_addr, 0, 1024), umma_desc_sw128(b_tile + k * 2048, 16384, 1024),
-                      p.idesc_o, (accumulate || k) ? 1u : 0u);
-        }
+        for (int k = 0; k < 8; ++k)   // 128 queries in steps of 16 = 8 TMEM columns of 16-bit pairs
+          umma_f16_ts(d_tmem, a_tmem + k * 8, umma_desc_sw128(b_tile + k * 2048, 16384, 1024), p.idesc_o,
+                      (accumulate || k) ? 1u : 0u);
         umma_commit(kv_empty(st));
         if (++st == Cfg::NST) { st = 0; ph ^= 1; }
       };
@@ -216,8 +216,8 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_consta
           stf_ph ^= 1;
           if (j == 0) mbar_wait(acc_empty, acc_ph ^ 1);   // previous item's accumulators have been read out
           tc_fence_after();
-          mma_out(sP, tmem_base + Cfg::DV_COL, j != 0);    // dV += P^T  dO_j
-          mma_out(sDS, tmem_base + Cfg::DK_COL, j != 0);   // dK += dS^T Q_j
+          mma_out(tmem_base + Cfg::PT_COL, tmem_base + Cfg::DV_COL, j != 0);    // dV += P^T  dO_j
+          mma_out(tmem_base + Cfg::DST_COL, tmem_base + Cfg::DK_COL, j != 0);   // dK += dS^T Q_j
           umma_commit(st_empty);
         }
         umma_commit(acc_full);
@@ -311,17 +311,12 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_consta
               }
             }
             if (c == half * COLS) {
-              mbar_wait(st_empty, ste_ph ^ 1);   // output MMAs of the previous tile no longer read the staging tiles
+              mbar_wait(st_empty, ste_ph ^ 1);   // output MMAs of the previous tile no longer read P^T / dS^T
               ste_ph ^= 1;
+              tc_fence_after();
             }
-            const int off = (c >> 6) * 16384 + r * 128;
-            const int chunk0 = (c & 63) >> 3;
-#pragma unroll
-            for (int t = 0; t < CW / 8; ++t) {
-              const int ch = (chunk0 + t) ^ (r & 7);
-              *reinterpret_cast<uint4*>(sP_ptr + off + ch * 16) = make_uint4(pp[4 * t], pp[4 * t + 1], pp[4 * t + 2], pp[4 * t + 3]);
-              *reinterpret_cast<uint4*>(sDS_ptr + off + ch * 16) = make_uint4(pd[4 * t], pd[4 * t + 1], pd[4 * t + 2], pd[4 * t + 3]);
-            }
+            tmem_st_cols(s_addr + Cfg::PT_COL + (c >> 1), pp);    // queries c .. c+CW-1 = 16-bit pairs in CW/2 columns
+            tmem_st_cols(s_addr + Cfg::DST_COL + (c >> 1), pd);
           }
         };
         const bool full = (nvalid == 128) && __all_sync(0xffffffffu, kvalid);
@@ -330,7 +325,8 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_consta
         } else {
           if (full) ew_tile(std::false_type{}, std::true_type{}); else ew_tile(std::false_type{}, std::false_type{});
         }
-        fence_proxy_async_smem();
+        tmem_st_wait();
+        tc_fence_before();
         mbar_arrive(st_full);
         if (et < 128 && j + 1 < nq) {   // statistics of tile j+1 into the other buffer (its readers passed this tile's barrier)
           stat[((j + 1) & 1) * 256 + et] = nl;
@@ -365,8 +361,7 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_consta
             w[i >> 1] = *reinterpret_cast<uint32_t*>(&x); w[16 + (i >> 1)] = *reinterpret_cast<uint32_t*>(&y);
           }
         }
-        // the last output MMAs of this item have completed (acc_full): the staging tiles are idle
-        const uint32_t buf = (half == 0 ? sP : sDS) + q * 4096;
+        const uint32_t buf = sOut + (half * 4 + q) * 4096;
         const uint32_t rowaddr = buf + lane * 128;
 #pragma unroll
         for (int t = 0; t < 8; ++t) {
@@ -378,7 +373,7 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_consta
         if (elect_one()) {
           tma_store_2d(half == 0 ? &tmDV : &tmDK, buf, it.col0, it.o_row0 + q * 32);
           tma_store_commit();
-          tma_store_wait_read<0>();   // the slab is rewritten by the next item's first tile
+          tma_store_wait_read<0>();   // the slab is rewritten by the next item's epilogue
         }
         __syncwarp();
       }
