@@ -847,6 +847,10 @@ static int launch_ds_wide(const CUtensorMap& tmQ, const CUtensorMap& tmDO, const
   return launch_ds_wide_d<CL, DBG, false>(tmQ, tmDO, tmK, tmV, tmDS, a, stream);
 }
 
+int launch_dq64(const CUtensorMap& tmQ, const CUtensorMap& tmDO, const CUtensorMap& tmK, const CUtensorMap& tmV,
+                const CUtensorMap& tmDQ, const int32_t* items, int32_t n_items, const float* lse, const float* delta,
+                int32_t dtype, uint32_t drop_seed, float drop_p, cudaStream_t stream);   // attn_dkv.cu
+
 }  // namespace csn
 
 extern "C" {
@@ -915,6 +919,8 @@ int csn_attn_bwd_dq(const void* Q, const void* dO, const void* K, const void* V,
   a.idesc_dq = umma_idesc_f16(fmt, 0, 1, d_head == 256 ? 128u : 64u);
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   const bool pair = paired && n_items % 2 == 0 && d_head == 256;
+  if (dQ != nullptr && dS == nullptr && d_head == 64 && getenv("CSN_DQ64_TS") == nullptr)   // dS lives in TMEM only (attn_dkv.cu)
+    return launch_dq64(tmQ, tmDO, tmK, tmV, tmDQ, items, n_items, lse, delta, dtype, drop_seed, drop_p, s);
   if (dQ != nullptr) {
     if (d_head == 256) return pair ? launch_dq<256, 2, true>(tmQ, tmDO, tmK, tmV, tmDS, tmDQ, a, s) : launch_dq<256, 1, true>(tmQ, tmDO, tmK, tmV, tmDS, tmDQ, a, s);
     return launch_dq<64, 1, true>(tmQ, tmDO, tmK, tmV, tmDS, tmDQ, a, s);

@@ -389,6 +389,345 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_consta
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Query-stationary counterpart: dQ = dS K of one 128-query tile per item, nothing written but dQ (the variant
+// of attn_bwd.cu's kernel used when no dS buffer is requested).  Same machinery: S = Q_i K_j^T and dP = dO_i V_j^T
+// (lane = query, column = key), 16 element-wise warps, dS goes back into TMEM as 16-bit pairs (two buffers) and is
+// the A operand of dQ += dS K_j.  TMEM: S @0, dP @128, dQ @256, dS16 @320 / @384.
+struct Dq64Item {   // = AttnBwdItem of attn_bwd.cu
+  int q_row0, q_valid, kv_row0, kv_len, o_row0, col0, stat_off, ds_row0, ds_col0, flags, pad0, pad1;
+};
+
+struct Dq64Cfg {
+  static constexpr int TILE_BYTES = 128 * 64 * 2;
+  static constexpr int OUT_BYTES = 4 * 4096;
+  static constexpr int SLOT_BYTES = 128 * 64 * 2;
+  static constexpr int NST = 9;
+  static constexpr int EW_WARPS = 16;
+  static constexpr int EW_THREADS = 32 * EW_WARPS;
+  static constexpr int THREADS = 128 + EW_THREADS;
+  static constexpr int COLS = 32, CW = 16;
+  static constexpr int BAR_BYTES = 256;
+  static constexpr int SMEM_BYTES = 2 * TILE_BYTES + OUT_BYTES + NST * SLOT_BYTES + BAR_BYTES + 1024;
+  static constexpr int DQ_COL = 256, DS_COL = 320;
+};
+
+template <bool DROP>
+__global__ void __launch_bounds__(Dq64Cfg::THREADS, 1)
+attn_bwd_dq64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmDO,
+                     const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
+                     const __grid_constant__ CUtensorMap tmDQ, const __grid_constant__ DkvArgs p) {
+  using Cfg = Dq64Cfg;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const uint32_t sQ = smem_u32(smem);
+  const uint32_t sDO = sQ + Cfg::TILE_BYTES;
+  const uint32_t sOut = sDO + Cfg::TILE_BYTES;
+  const uint32_t sRing = sOut + Cfg::OUT_BYTES;
+  uint8_t* bar_ptr = smem + 2 * Cfg::TILE_BYTES + Cfg::OUT_BYTES + Cfg::NST * Cfg::SLOT_BYTES;
+  const uint32_t bar_base = smem_u32(bar_ptr);
+  auto kv_full = [&](int s) { return bar_base + 8u * s; };
+  auto kv_empty = [&](int s) { return bar_base + 8u * (Cfg::NST + s); };
+  const uint32_t bres_full = bar_base + 8u * (2 * Cfg::NST + 0);
+  const uint32_t bres_empty = bar_base + 8u * (2 * Cfg::NST + 1);
+  const uint32_t sdp_full = bar_base + 8u * (2 * Cfg::NST + 2);
+  const uint32_t sdp_empty = bar_base + 8u * (2 * Cfg::NST + 3);
+  auto ds_full = [&](int b) { return bar_base + 8u * (2 * Cfg::NST + 4 + b); };    // dS_j is in TMEM buffer b
+  auto ds_empty = [&](int b) { return bar_base + 8u * (2 * Cfg::NST + 6 + b); };   // dQ MMAs of tile j done reading it
+  const uint32_t acc_full = bar_base + 8u * (2 * Cfg::NST + 8);
+  const uint32_t acc_empty = bar_base + 8u * (2 * Cfg::NST + 9);
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bar_ptr + 8 * (2 * Cfg::NST + 10));
+  const Dq64Item* items = reinterpret_cast<const Dq64Item*>(p.items);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmDO);
+    tma_prefetch_desc(&tmK);
+    tma_prefetch_desc(&tmV);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < Cfg::NST; ++s) {
+      mbar_init(kv_full(s), 1);
+      mbar_init(kv_empty(s), 1);
+    }
+    mbar_init(bres_full, 1);
+    mbar_init(bres_empty, 1);
+    mbar_init(sdp_full, 1);
+    mbar_init(sdp_empty, Cfg::EW_THREADS);
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(ds_full(b), Cfg::EW_THREADS);
+      mbar_init(ds_empty(b), 1);
+    }
+    mbar_init(acc_full, 1);
+    mbar_init(acc_empty, Cfg::EW_THREADS);
+    fence_mbar_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(smem_u32(tmem_ptr_smem), 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp == 0) {
+    // ================================================================== TMA producer
+    if (elect_one()) {
+      int st = 0;
+      uint32_t ph = 0, r_ph = 0;
+      auto load_slot = [&](const CUtensorMap* tm, int col0, int row0) {
+        mbar_wait(kv_empty(st), ph ^ 1);
+        mbar_arrive_expect_tx(kv_full(st), Cfg::SLOT_BYTES);
+        tma_load_2d(sRing + st * Cfg::SLOT_BYTES, tm, kv_full(st), col0, row0);
+        if (++st == Cfg::NST) { st = 0; ph ^= 1; }
+      };
+      for (int wk = blockIdx.x; wk < p.n_items; wk += gridDim.x) {
+        const Dq64Item it = items[wk];
+        const int nkv = (it.kv_len + 127) >> 7;
+        mbar_wait(bres_empty, r_ph ^ 1);
+        mbar_arrive_expect_tx(bres_full, 2 * Cfg::TILE_BYTES);
+        tma_load_2d(sQ, &tmQ, bres_full, it.col0, it.q_row0);
+        tma_load_2d(sDO, &tmDO, bres_full, it.col0, it.o_row0);
+        r_ph ^= 1;
+        // consumption order of the MMA warp: [K0, V0], [K1, V1], K0 (dQ), [K2, V2], K1 (dQ), ...
+        load_slot(&tmK, it.col0, it.kv_row0);
+        load_slot(&tmV, it.col0, it.kv_row0);
+        for (int j = 0; j < nkv; ++j) {
+          if (j + 1 < nkv) {
+            load_slot(&tmK, it.col0, it.kv_row0 + (j + 1) * 128);
+            load_slot(&tmV, it.col0, it.kv_row0 + (j + 1) * 128);
+          }
+          load_slot(&tmK, it.col0, it.kv_row0 + j * 128);   // for dQ (same bytes, consumed MN-major)
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================================================================== MMA issuer
+    if (elect_one()) {
+      int st = 0;
+      uint32_t ph = 0, r_ph = 0, sdp_ph = 0, acc_ph = 0;
+      uint32_t dsf_ph[2] = {0, 0};
+      auto mma_scores = [&](uint32_t a_tile, uint32_t d_tmem) {
+        mbar_wait(kv_full(st), ph);
+        tc_fence_after();
+        const uint32_t b_tile = sRing + st * Cfg::SLOT_BYTES;
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          umma_f16_ss(d_tmem, umma_desc_sw128(a_tile + k * 32, 0, 1024), umma_desc_sw128(b_tile + k * 32, 0, 1024),
+                      p.idesc_s, k ? 1u : 0u);
+        umma_commit(kv_empty(st));
+        if (++st == Cfg::NST) { st = 0; ph ^= 1; }
+      };
+      for (int wk = blockIdx.x; wk < p.n_items; wk += gridDim.x) {
+        const Dq64Item it = items[wk];
+        const int nkv = (it.kv_len + 127) >> 7;
+        mbar_wait(bres_full, r_ph);
+        r_ph ^= 1;
+        tc_fence_after();
+        auto issue_scores = [&](int j) {
+          mbar_wait(sdp_empty, sdp_ph ^ 1);
+          tc_fence_after();
+          mma_scores(sQ, tmem_base);           // S  = Q_i  K_j^T
+          mma_scores(sDO, tmem_base + 128);    // dP = dO_i V_j^T
+          umma_commit(sdp_full);
+          if (j == nkv - 1) umma_commit(bres_empty);
+          sdp_ph ^= 1;
+        };
+        issue_scores(0);
+        for (int j = 0; j < nkv; ++j) {
+          if (j + 1 < nkv) issue_scores(j + 1);
+          const int b = j & 1;
+          mbar_wait(ds_full(b), dsf_ph[b]);
+          dsf_ph[b] ^= 1;
+          if (j == 0) mbar_wait(acc_empty, acc_ph ^ 1);
+          tc_fence_after();
+          mbar_wait(kv_full(st), ph);
+          tc_fence_after();
+          const uint32_t b_tile = sRing + st * Cfg::SLOT_BYTES;
+#pragma unroll
+          for (int k = 0; k < 8; ++k)   // 128 keys in steps of 16 = 8 TMEM columns of 16-bit pairs
+            umma_f16_ts(tmem_base + Cfg::DQ_COL, tmem_base + Cfg::DS_COL + b * 64 + k * 8,
+                        umma_desc_sw128(b_tile + k * 2048, 16384, 1024), p.idesc_o, (j | k) ? 1u : 0u);
+          umma_commit(kv_empty(st));
+          if (++st == Cfg::NST) { st = 0; ph ^= 1; }
+          umma_commit(ds_empty(b));
+        }
+        umma_commit(acc_full);
+        acc_ph ^= 1;
+      }
+    }
+  } else if (warp >= 4) {
+    // ================================================================== element-wise stage + epilogue
+    const int q = warp & 3;
+    const int half = (warp - 4) >> 2;            // key columns [32 half, 32 half + 32)
+    constexpr int COLS = Cfg::COLS, CW = Cfg::CW;
+    const int r = q * 32 + lane;                 // query row of the tile owned by this thread
+    const uint32_t lane_addr = uint32_t(q * 32) << 16;
+    uint32_t sdp_ph = 0, accf_ph = 0;
+    uint32_t dse_ph[2] = {0, 0};
+    constexpr float LOG2E = 1.4426950408889634f;
+    for (int wk = blockIdx.x; wk < p.n_items; wk += gridDim.x) {
+      const Dq64Item it = items[wk];
+      const int nkv = (it.kv_len + 127) >> 7;
+      const bool valid = r < it.q_valid;
+      const float lse_l2 = valid ? p.lse[it.stat_off + r] * LOG2E : 0.f;
+      const float dlt_s = valid ? p.delta[it.stat_off + r] * p.scale : 0.f;
+      const uint32_t rk = drop_row_key(p.drop_seed, (uint32_t)(it.stat_off + r));
+      for (int j = 0; j < nkv; ++j) {
+        const int b = j & 1;
+        const int nvalid = min(128, it.kv_len - j * 128);
+        mbar_wait(sdp_full, sdp_ph);
+        sdp_ph ^= 1;
+        tc_fence_after();
+        const uint32_t s_addr = tmem_base + lane_addr;
+        auto ew_tile = [&](auto F16C, auto FULLC) {
+          constexpr bool F16 = decltype(F16C)::value, FULL = decltype(FULLC)::value;
+#pragma unroll 1
+          for (int c = half * COLS; c < half * COLS + COLS; c += CW) {
+            uint32_t sv[CW], dv[CW];
+            tmem_ld_cols(s_addr + c, sv);
+            tmem_ld_cols(s_addr + 128 + c, dv);
+            tmem_ld_wait();
+            if (c + CW == half * COLS + COLS) {   // this thread's scores are in registers: the MMA warp may overwrite them
+              tc_fence_before();
+              mbar_arrive(sdp_empty);
+            }
+            uint32_t pd[CW / 2];
+#pragma unroll
+            for (int i = 0; i < CW; i += 2) {
+              float m0 = p.scale, m1 = p.scale;   // (d P_dropped / d P = mask / (1 - p)) * scale
+              if (DROP) {
+                const uint32_t hh = drop_pair(rk, (uint32_t)(j * 128 + c + i) >> 1);
+                m0 = drop_keep_lo(hh, p.drop_thresh) ? p.drop_scale * p.scale : 0.f;
+                m1 = drop_keep_hi(hh, p.drop_thresh) ? p.drop_scale * p.scale : 0.f;
+              }
+              float d0 = fast_exp2(__uint_as_float(sv[i]) * p.scale_log2 - lse_l2) * fmaf(__uint_as_float(dv[i]), m0, -dlt_s);
+              float d1 = fast_exp2(__uint_as_float(sv[i + 1]) * p.scale_log2 - lse_l2) * fmaf(__uint_as_float(dv[i + 1]), m1, -dlt_s);
+              if (!FULL) {
+                if (!(valid && c + i < nvalid)) d0 = 0.f;
+                if (!(valid && c + i + 1 < nvalid)) d1 = 0.f;
+              }
+              if (F16) {
+                __half2 h = __floats2half2_rn(d0, d1);
+                pd[i >> 1] = *reinterpret_cast<uint32_t*>(&h);
+              } else {
+                __nv_bfloat162 h = __floats2bfloat162_rn(d0, d1);
+                pd[i >> 1] = *reinterpret_cast<uint32_t*>(&h);
+              }
+            }
+            if (c == half * COLS) {
+              mbar_wait(ds_empty(b), dse_ph[b] ^ 1);   // dQ MMAs of tile j-2 no longer read this buffer
+              dse_ph[b] ^= 1;
+              tc_fence_after();
+            }
+            tmem_st_cols(s_addr + Cfg::DS_COL + b * 64 + (c >> 1), pd);
+          }
+        };
+        const bool full = (nvalid == 128) && __all_sync(0xffffffffu, valid);
+        if (p.dtype == CSN_F16) {
+          if (full) ew_tile(std::true_type{}, std::true_type{}); else ew_tile(std::true_type{}, std::false_type{});
+        } else {
+          if (full) ew_tile(std::false_type{}, std::true_type{}); else ew_tile(std::false_type{}, std::false_type{});
+        }
+        tmem_st_wait();
+        tc_fence_before();
+        mbar_arrive(ds_full(b));
+      }
+      // ---- epilogue: warps 4-7 write the dQ tile (rows >= q_valid: zeros)
+      mbar_wait(acc_full, accf_ph);
+      accf_ph ^= 1;
+      tc_fence_after();
+      if (half != 0) {
+        mbar_arrive(acc_empty);
+      } else {
+        const uint32_t o_addr = tmem_base + lane_addr + Cfg::DQ_COL;
+        uint32_t v0[32], v1[32];
+        tmem_ld_32x32(o_addr, v0);
+        tmem_ld_32x32(o_addr + 32, v1);
+        tmem_ld_wait();
+        tc_fence_before();
+        mbar_arrive(acc_empty);
+        uint32_t w[32];
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) {
+          const float a0 = valid ? __uint_as_float(v0[i]) : 0.f, a1 = valid ? __uint_as_float(v0[i + 1]) : 0.f;
+          const float b0 = valid ? __uint_as_float(v1[i]) : 0.f, b1 = valid ? __uint_as_float(v1[i + 1]) : 0.f;
+          if (p.dtype == CSN_F16) {
+            __half2 x = __floats2half2_rn(a0, a1), y = __floats2half2_rn(b0, b1);
+            w[i >> 1] = *reinterpret_cast<uint32_t*>(&x); w[16 + (i >> 1)] = *reinterpret_cast<uint32_t*>(&y);
+          } else {
+            __nv_bfloat162 x = __floats2bfloat162_rn(a0, a1), y = __floats2bfloat162_rn(b0, b1);
+            w[i >> 1] = *reinterpret_cast<uint32_t*>(&x); w[16 + (i >> 1)] = *reinterpret_cast<uint32_t*>(&y);
+          }
+        }
+        const uint32_t buf = sOut + q * 4096;
+        const uint32_t rowaddr = buf + lane * 128;
+#pragma unroll
+        for (int t = 0; t < 8; ++t) {
+          const uint32_t a = rowaddr + (((uint32_t)t ^ ((uint32_t)lane & 7u)) << 4);
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(w[4 * t]), "r"(w[4 * t + 1]), "r"(w[4 * t + 2]), "r"(w[4 * t + 3]) : "memory");
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (elect_one()) {
+          tma_store_2d(&tmDQ, buf, it.col0, it.o_row0 + q * 32);
+          tma_store_commit();
+          tma_store_wait_read<0>();   // the slab is rewritten by the next item's epilogue
+        }
+        __syncwarp();
+      }
+    }
+    if (lane == 0) tma_store_wait_all();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+template <bool DROP>
+static int launch_dq64_d(const CUtensorMap& tmQ, const CUtensorMap& tmDO, const CUtensorMap& tmK, const CUtensorMap& tmV,
+                         const CUtensorMap& tmDQ, const DkvArgs& a, cudaStream_t stream) {
+  auto kern = attn_bwd_dq64_kernel<DROP>;
+  static bool configured = false;
+  if (!configured) {
+    CSN_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Dq64Cfg::SMEM_BYTES));
+    configured = true;
+  }
+  const int grid = a.n_items < num_sms() ? a.n_items : num_sms();
+  kern<<<grid, Dq64Cfg::THREADS, Dq64Cfg::SMEM_BYTES, stream>>>(tmQ, tmDO, tmK, tmV, tmDQ, a);
+  CSN_LAUNCH_OK("attn_bwd_dq64_kernel");
+  return 0;
+}
+
+// called by csn_attn_bwd_dq (attn_bwd.cu) for d_head 64 when no dS buffer is requested
+int launch_dq64(const CUtensorMap& tmQ, const CUtensorMap& tmDO, const CUtensorMap& tmK, const CUtensorMap& tmV,
+                const CUtensorMap& tmDQ, const int32_t* items, int32_t n_items, const float* lse, const float* delta,
+                int32_t dtype, uint32_t drop_seed, float drop_p, cudaStream_t stream) {
+  DkvArgs a;
+  a.items = reinterpret_cast<const DkvItem*>(items);
+  a.n_items = n_items;
+  a.lse = lse;
+  a.delta = delta;
+  a.scale = 1.0f / sqrtf(64.f);
+  a.scale_log2 = a.scale * 1.4426950408889634f;
+  a.dtype = dtype;
+  const uint32_t fmt = dtype == CSN_F16 ? 0u : 1u;
+  a.idesc_s = umma_idesc_f16(fmt, 0, 0, 128);
+  a.idesc_o = umma_idesc_f16(fmt, 0, 1, 64);
+  a.drop_seed = drop_seed;
+  a.drop_thresh = drop_thresh16(drop_p);
+  a.drop_scale = drop_scale_of(a.drop_thresh);
+  return a.drop_thresh ? launch_dq64_d<true>(tmQ, tmDO, tmK, tmV, tmDQ, a, stream) : launch_dq64_d<false>(tmQ, tmDO, tmK, tmV, tmDQ, a, stream);
+}
+
 template <bool DROP>
 static int launch_dkv(const CUtensorMap& tmK, const CUtensorMap& tmV, const CUtensorMap& tmQ, const CUtensorMap& tmDO,
                       const CUtensorMap& tmDK, const CUtensorMap& tmDV, const DkvArgs& a, cudaStream_t stream) {
