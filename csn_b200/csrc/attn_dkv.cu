@@ -262,18 +262,24 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_consta
         sdp_ph ^= 1;
         tc_fence_after();
         const uint32_t s_addr = tmem_base + lane_addr;
+        // all of this thread's scores into registers first: the MMA warp gets the accumulators back before the
+        // arithmetic starts (the chain scores -> element-wise -> scores is what bounds the kernel)
+        static_assert(COLS == 2 * CW, "two register chunks per thread");
+        uint32_t svA[CW], dvA[CW], svB[CW], dvB[CW];
+        tmem_ld_cols(s_addr + half * COLS, svA);
+        tmem_ld_cols(s_addr + 128 + half * COLS, dvA);
+        tmem_ld_cols(s_addr + half * COLS + CW, svB);
+        tmem_ld_cols(s_addr + 128 + half * COLS + CW, dvB);
+        tmem_ld_wait();
+        tc_fence_before();
+        mbar_arrive(sdp_empty);
         auto ew_tile = [&](auto F16C, auto FULLC) {
           constexpr bool F16 = decltype(F16C)::value, FULL = decltype(FULLC)::value;
-#pragma unroll 1
-          for (int c = half * COLS; c < half * COLS + COLS; c += CW) {
-            uint32_t sv[CW], dv[CW];
-            tmem_ld_cols(s_addr + c, sv);
-            tmem_ld_cols(s_addr + 128 + c, dv);
-            tmem_ld_wait();
-            if (c + CW == half * COLS + COLS) {   // this thread's scores are in registers: the MMA warp may overwrite them
-              tc_fence_before();
-              mbar_arrive(sdp_empty);
-            }
+#pragma unroll
+          for (int cc = 0; cc < 2; ++cc) {
+            const int c = half * COLS + cc * CW;
+            const uint32_t (&sv)[CW] = cc ? svB : svA;
+            const uint32_t (&dv)[CW] = cc ? dvB : dvA;
             uint32_t pp[CW / 2], pd[CW / 2];
 #pragma unroll
             for (int i = 0; i < CW; i += 4) {

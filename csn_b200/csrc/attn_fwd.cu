@@ -49,6 +49,9 @@ struct AttnCfg {
   static constexpr int XCH_BYTES = (SM_WARPS == 8) ? 1024 : 0;   // row max / row sum exchange between the two halves
   static constexpr int SMEM_BYTES = Q_BYTES + P_BYTES + NST * SLOT_BYTES + XSTG_BYTES + BAR_BYTES + XCH_BYTES + 1024;
   static constexpr int O_COL = 256;                        // TMEM: S0 @0, S1 @128, O @256 (DH <= 256)
+  // d_head 64: the 16-bit probabilities go back into TMEM (two buffers of 64 columns = 128 keys as 16-bit pairs,
+  // behind the 64 columns of O) and are the A operand of P V from there; no SMEM round trip, P double-buffered
+  static constexpr int P_COL = 320;
 };
 
 template <int DH, int MODE, int CL, bool DROP>
@@ -71,11 +74,12 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   const uint32_t bq_empty = bar_base + 8u * (2 * Cfg::NST + 1);
   auto s_full = [&](int b) { return bar_base + 8u * (2 * Cfg::NST + 2 + b); };
   auto s_empty = [&](int b) { return bar_base + 8u * (2 * Cfg::NST + 4 + b); };
-  const uint32_t bp_full = bar_base + 8u * (2 * Cfg::NST + 6);
-  const uint32_t bp_empty = bar_base + 8u * (2 * Cfg::NST + 7);
+  constexpr bool TSP = (DH == 64 && MODE == 0);   // P through TMEM (forward, d_head 64)
+  auto bp_full = [&](int b) { return bar_base + 8u * (2 * Cfg::NST + (b ? 10 : 6)); };
+  auto bp_empty = [&](int b) { return bar_base + 8u * (2 * Cfg::NST + (b ? 11 : 7)); };
   const uint32_t bo_full = bar_base + 8u * (2 * Cfg::NST + 8);
   const uint32_t bo_empty = bar_base + 8u * (2 * Cfg::NST + 9);
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bar_ptr + 8 * (2 * Cfg::NST + 10));
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bar_ptr + 8 * (2 * Cfg::NST + 12));
   float* xch = reinterpret_cast<float*>(bar_ptr + Cfg::BAR_BYTES);   // [2 halves][128 rows] (SM_WARPS == 8 only)
 
   const int warp = threadIdx.x >> 5;
@@ -97,8 +101,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       mbar_init(s_full(b), 1);
       mbar_init(s_empty(b), Cfg::SM_THREADS);
     }
-    mbar_init(bp_full, Cfg::SM_THREADS);
-    mbar_init(bp_empty, 1);
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(bp_full(b), Cfg::SM_THREADS);
+      mbar_init(bp_empty(b), 1);
+    }
     mbar_init(bo_full, 1);
     mbar_init(bo_empty, 128);
     fence_mbar_init();
@@ -177,7 +183,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     // ================================================================== MMA issuer
     if (elect_one()) {
       int st = 0;
-      uint32_t ph = 0, q_ph = 0, p_ph = 0, o_ph = 0;
+      uint32_t ph = 0, q_ph = 0, o_ph = 0;
+      uint32_t p_ph[2] = {0, 0};
       uint32_t s_ph[2] = {0, 0};
       auto issue_qk = [&](int j, bool last) {
         const int b = j & 1;
@@ -215,8 +222,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         issue_qk(0, nkv == 1);
         for (int j = 0; j < nkv; ++j) {
           if (j + 1 < nkv) issue_qk(j + 1, j + 2 == nkv);
-          mbar_wait(bp_full, p_ph);  // P_j is in SMEM (and O was rescaled if needed)
-          p_ph ^= 1;
+          const int pb = TSP ? (j & 1) : 0;
+          mbar_wait(bp_full(pb), p_ph[pb]);  // P_j is in SMEM / TMEM (and O was rescaled if needed)
+          p_ph[pb] ^= 1;
           if (j == 0) mbar_wait(bo_empty, o_ph ^ 1);  // previous item's O has been read out
           tc_fence_after();
           const uint32_t o_tmem = tmem_base + Cfg::O_COL;
@@ -231,15 +239,20 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
               // forward: A = P[query][key], K-major (contraction over keys: 32 B per step inside a swizzled row)
               // dV mode: A = P^T: the same tile [query rows][keys] read MN-major (M = keys contiguous, two
               //          64-key atoms 16 KB apart; contraction over queries: 16 rows = 2048 B per step)
-              const uint64_t da = (MODE == 0) ? umma_desc_sw128(sP + (key >> 6) * 16384 + (key & 63) * 2, 0, 1024)
-                                              : umma_desc_sw128(sP + (key >> 4) * 2048, 16384, 1024);
-              umma_f16_ss(o_tmem, da, umma_desc_sw128(v_tile + k * 2048, Cfg::KEYS_PER_VSLOT * 128, 1024), p.idesc_pv,
-                          (j | s | k) ? 1u : 0u);
+              if constexpr (TSP) {   // A = P from TMEM: 16 keys = 8 columns of 16-bit pairs
+                umma_f16_ts(o_tmem, tmem_base + Cfg::P_COL + pb * 64 + (key >> 1),
+                            umma_desc_sw128(v_tile + k * 2048, Cfg::KEYS_PER_VSLOT * 128, 1024), p.idesc_pv, (j | s | k) ? 1u : 0u);
+              } else {
+                const uint64_t da = (MODE == 0) ? umma_desc_sw128(sP + (key >> 6) * 16384 + (key & 63) * 2, 0, 1024)
+                                                : umma_desc_sw128(sP + (key >> 4) * 2048, 16384, 1024);
+                umma_f16_ss(o_tmem, da, umma_desc_sw128(v_tile + k * 2048, Cfg::KEYS_PER_VSLOT * 128, 1024), p.idesc_pv,
+                            (j | s | k) ? 1u : 0u);
+              }
             }
             if (CL == 1) umma_commit(kv_empty(st)); else umma_commit_mc(kv_empty(st), MC_MASK);
             if (++st == Cfg::NST) { st = 0; ph ^= 1; }
           }
-          umma_commit(bp_empty);  // P buffer free / O accumulation of tile j complete
+          umma_commit(bp_empty(pb));  // P buffer free / O accumulation of tile j complete
         }
         umma_commit(bo_full);    // (same completion point as the last bp_empty)
         o_ph ^= 1;
@@ -255,7 +268,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     const int r = q * 32 + lane;  // row of the tile owned by this thread
     const uint32_t lane_addr = uint32_t(q * 32) << 16;
     uint32_t s_ph[2] = {0, 0};
-    uint32_t pe_ph = 0, of_ph = 0;
+    uint32_t pe_ph[2] = {0, 0};
+    uint32_t of_ph = 0;
     // SPLIT: combine a per-row value of the two halves (both threads of a row return the same result)
     auto row_exchange = [&](float v, bool is_max) -> float {
       xch[half * 128 + r] = v;
@@ -311,10 +325,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         tc_fence_after();
         const uint32_t s_addr = tmem_base + lane_addr + b * 128;
         const int nvalid = min(128, it.kv_len - j * 128);
+        const int pb = TSP ? (j & 1) : 0;
         bool waited_p = false;
         if (p.debug & 1) {
-          mbar_wait(bp_empty, pe_ph ^ 1);
-          pe_ph ^= 1;
+          mbar_wait(bp_empty(pb), pe_ph[pb] ^ 1);
+          pe_ph[pb] ^= 1;
           l = 1.f;
         } else if (MODE == 1) {
           // ---- dV mode: lane = query row of the streamed tile, columns = the resident keys.
@@ -353,8 +368,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                 pk[16 + (i >> 1)] = pack_t(F16C, b0, b1);
               }
               if (!waited_p) {
-                mbar_wait(bp_empty, pe_ph ^ 1);
-                pe_ph ^= 1;
+                mbar_wait(bp_empty(pb), pe_ph[pb] ^ 1);
+                pe_ph[pb] ^= 1;
                 waited_p = true;
               }
               store_p64(c, pk);
@@ -431,12 +446,14 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                   pk[16 + (i >> 1)] = pack_t(F16C, b0, b1);
                 }
                 if (!waited_p) {
-                  // P tile may be overwritten once the P V MMAs of the previous tile have completed
-                  mbar_wait(bp_empty, pe_ph ^ 1);
-                  pe_ph ^= 1;
+                  // the P buffer may be overwritten once the P V MMAs that read it have completed
+                  mbar_wait(bp_empty(pb), pe_ph[pb] ^ 1);
+                  pe_ph[pb] ^= 1;
                   waited_p = true;
+                  if (TSP) tc_fence_after();
                 }
-                store_p64(c, pk);
+                if constexpr (TSP) tmem_st_32x32(tmem_base + lane_addr + Cfg::P_COL + pb * 64 + (c >> 1), pk);
+                else store_p64(c, pk);
               }
             };
             if (p.dtype == CSN_F16) {
@@ -468,10 +485,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           l += lsum;
         }
         // S_j fully consumed; P_j visible to the tensor-core (async) proxy
+        if (TSP) tmem_st_wait();
         tc_fence_before();
         mbar_arrive(s_empty(b));
-        fence_proxy_async_smem();
-        mbar_arrive(bp_full);
+        if (!TSP) fence_proxy_async_smem();
+        mbar_arrive(bp_full(pb));
       }
       // ---- epilogue: O / l -> 16-bit, LSE   (dV mode: the accumulator as is)
       mbar_wait(bo_full, of_ph);
