@@ -191,7 +191,9 @@ int csn_attn_bwd_dkv(const void* K, const void* V, const void* Q, const void* dO
  *  csn_attn_bwd_dq: per 128-row query tile: S = Q K^T, dP = dO V^T, dS = P o (dP - delta) / sqrt(d),
  *                   dQ += dS K; dS is also written (16-bit, [ds_row0 + r][ds_col0 + key]) so that
  *                   dK = dS^T Q runs as one csn_gemm.  dQ == NULL: only dS is produced (S|dP are then
- *                   double-buffered in TMEM) and dQ = dS K is left to csn_gemm as well.  items: int32 x 12
+ *                   double-buffered in TMEM) and dQ = dS K is left to csn_gemm as well.  dS == NULL (d_head 64,
+ *                   dQ != NULL): nothing but dQ is written, dS stays in TMEM as the A operand of dQ += dS K
+ *                   (dK and dV then come from csn_attn_bwd_dkv).  items: int32 x 12
  *   {q_row0, q_valid, kv_row0, kv_len, o_row0 (rows of dO and dQ), col0, stat_off, ds_row0, ds_col0, flags, 0, 0}. */
 int csn_attn_delta(const void* dO, const void* O, const void* O_lo, float* delta, int64_t rows, int32_t rows_pad, int32_t n_head,
                    int32_t d_head, int64_t ld, int32_t dtype, void* stream);
