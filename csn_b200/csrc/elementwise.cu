@@ -744,6 +744,43 @@ static int launch_simple(K kern, dim3 grid, dim3 block, const A& args, void* str
 }  // namespace csn
 
 namespace csn {
+// Concatenated rows -> padded slots: out[s][r] = x[offsets[s] + r] for r < len(s), 0 for len(s) <= r < n_pad
+// (fp32 copy and / or 16-bit copy).  One warp per row, 256 columns.
+__global__ void __launch_bounds__(256) ragged_pad_kernel(const float* __restrict__ x, const long long* __restrict__ offsets,
+                                                         int n_pad, float* __restrict__ out32, void* __restrict__ out16, int dtype) {
+  const int s = blockIdx.y;
+  const long long o0 = offsets[s];
+  const int len = (int)(offsets[s + 1] - o0);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int r = blockIdx.x * 8 + warp; r < n_pad; r += gridDim.x * 8) {
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
+    if (r < len) {
+      const float4* src = reinterpret_cast<const float4*>(x + (o0 + r) * 256) + lane * 2;
+      a = __ldg(src);
+      b = __ldg(src + 1);
+    }
+    const long long row = (long long)s * n_pad + r;
+    if (out32) {
+      float4* d = reinterpret_cast<float4*>(out32 + row * 256) + lane * 2;
+      d[0] = a;
+      d[1] = b;
+    }
+    if (out16) {
+      uint4 w;
+      if (dtype == CSN_F16) {
+        __half2 h0 = __floats2half2_rn(a.x, a.y), h1 = __floats2half2_rn(a.z, a.w), h2 = __floats2half2_rn(b.x, b.y), h3 = __floats2half2_rn(b.z, b.w);
+        w = make_uint4(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1), *reinterpret_cast<uint32_t*>(&h2), *reinterpret_cast<uint32_t*>(&h3));
+      } else {
+        __nv_bfloat162 h0 = __floats2bfloat162_rn(a.x, a.y), h1 = __floats2bfloat162_rn(a.z, a.w), h2 = __floats2bfloat162_rn(b.x, b.y), h3 = __floats2bfloat162_rn(b.z, b.w);
+        w = make_uint4(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1), *reinterpret_cast<uint32_t*>(&h2), *reinterpret_cast<uint32_t*>(&h3));
+      }
+      reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(out16) + row * 256)[lane] = w;
+    }
+  }
+}
+}  // namespace csn
+
+namespace csn {
 // dst[s][e] = (dst[s][e] + sum over source blocks j with dst_block[j] == s of src[j][e]) * unscale:
 // the residual path of the attention backward (dX[query slot] += dZ[block]) as a deterministic gather.
 __global__ void __launch_bounds__(256) block_add_kernel(const float* __restrict__ src, const int* __restrict__ dst_block, int n_src,
@@ -929,6 +966,22 @@ int csn_segment_mean(const float* x, const int64_t* offsets, int32_t n_seg, int3
   segment_mean_kernel<<<dim3(n_seg, (n_cols + 31) / 32), 256, 0, (cudaStream_t)stream>>>(
       x, reinterpret_cast<const long long*>(offsets), n_cols, out);
   CSN_LAUNCH_OK("segment_mean_kernel");
+  return 0;
+}
+
+int csn_ragged_pad(const float* x, const int64_t* offsets, int32_t n_slots, int32_t n_pad, float* out32, void* out16,
+                   int32_t dtype, void* stream) {
+  using namespace csn;
+  clear_error();
+  CSN_CHECK_ARG(x && offsets && (out32 || out16), "csn_ragged_pad: null pointer");
+  CSN_CHECK_ARG(!out16 || dtype == CSN_F16 || dtype == CSN_BF16, "csn_ragged_pad: 16-bit output needs dtype f16 / bf16");
+  if (n_slots == 0 || n_pad == 0) return 0;
+  int gx = (n_pad + 7) / 8;
+  const int cap = (8 * num_sms() + n_slots - 1) / n_slots;
+  if (gx > cap) gx = cap;
+  ragged_pad_kernel<<<dim3((unsigned)gx, (unsigned)n_slots), 256, 0, (cudaStream_t)stream>>>(
+      x, reinterpret_cast<const long long*>(offsets), n_pad, out32, out16, dtype);
+  CSN_LAUNCH_OK("ragged_pad_kernel");
   return 0;
 }
 

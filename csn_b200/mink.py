@@ -139,9 +139,12 @@ class _MhaBlocksFn(torch.autograd.Function):
         for n in lens:
             offs.append(offs[-1] + n)
         slot_rows = torch.cat([torch.arange(n, dtype=torch.int64) + s * n_pad for s, n in enumerate(lens)]).to(dev, non_blocking=True)
-        Xf = torch.zeros(S * n_pad, 256, dtype=torch.float32, device=dev)
-        Xf[slot_rows] = x_cat.float()
-        Xh = Xf.to(dt)
+        offs_t = torch.tensor(offs, dtype=torch.int64).to(dev, non_blocking=True)
+        Xf = torch.empty(S * n_pad, 256, dtype=torch.float32, device=dev)
+        Xh = torch.empty(S * n_pad, 256, dtype=dt, device=dev)
+        x32 = x_cat.float().contiguous()
+        L.check(L.lib().csn_ragged_pad(x32.data_ptr(), offs_t.data_ptr(), S, n_pad, Xf.data_ptr(), Xh.data_ptr(),
+                                       L.dtype_code(dt), L.stream_ptr()), "csn_ragged_pad")
         geom = E.Geometry(chunk=n_pad, n_chunks=1, chunk_pad=n_pad, kv_chunk=n_pad)
         # runs of pairs whose (query, key) slots advance with constant strides become one group each, so that the
         # batched GEMMs of the backward pass stay batched (SSA of S shapes: one run; K*B cross blocks: K runs)
@@ -164,16 +167,21 @@ class _MhaBlocksFn(torch.autograd.Function):
         a = E.attention_forward(Xh, Xf, groups, S, P, wq, wk, wv, wo, gamma, beta, geom, n_head, want_colsum=False,
                                 dropout_p=dropout_p, seed=seed)
         out_rows = torch.cat([torch.arange(lens[qs], dtype=torch.int64) + j * n_pad for j, (qs, _) in enumerate(pairs)]).to(dev, non_blocking=True)
+        poffs = [0]
+        for qs, _ in pairs:
+            poffs.append(poffs[-1] + lens[qs])
         ctx.a = a
-        ctx.meta = (S, P, n_pad, slot_rows, out_rows)
+        ctx.meta = (S, P, n_pad, slot_rows, out_rows, torch.tensor(poffs, dtype=torch.int64).to(dev, non_blocking=True))
         return a.Y[out_rows]
 
     @staticmethod
     def backward(ctx, dout):
         a = ctx.a
-        S, P, n_pad, slot_rows, out_rows = ctx.meta
-        dY = torch.zeros(P * n_pad, 256, dtype=torch.float32, device=dout.device)
-        dY[out_rows] = dout.float()
+        S, P, n_pad, slot_rows, out_rows, poffs_t = ctx.meta
+        dY = torch.empty(P * n_pad, 256, dtype=torch.float32, device=dout.device)
+        d32 = dout.float().contiguous()
+        L.check(L.lib().csn_ragged_pad(d32.data_ptr(), poffs_t.data_ptr(), P, n_pad, dY.data_ptr(), None, 0, L.stream_ptr()),
+                "csn_ragged_pad")
         need_dx = ctx.needs_input_grad[0]
         g = E.attention_backward(a, dY, need_dx)
         dx = g["dX"][slot_rows] if need_dx else None

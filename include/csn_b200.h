@@ -372,6 +372,12 @@ int csn_ln_bwd(const float* dY, const float* Z, const float* mean, const float* 
  * every parameter gradient of a step. */
 int csn_grad_unscale(float* x, int64_t n, const float* amax, void* stream);
 
+/* Concatenated rows -> zero-padded slots of n_pad rows, 256 columns: out[s][r] = x[offsets[s] + r] for
+ * r < offsets[s+1] - offsets[s], 0 beyond; out32 (fp32) and / or out16 (dtype f16 / bf16).  The layout change in
+ * front of the ragged attention batch (the reference calls MultiHeadAttention once per shape, hrnet.py:370-417). */
+int csn_ragged_pad(const float* x, const int64_t* offsets, int32_t n_slots, int32_t n_pad, float* out32, void* out16,
+                   int32_t dtype, void* stream);
+
 /* dst[s] = (dst[s] + sum over j < n_src with dst_block[j] == s of src[j]) * u, blocks of block_elems fp32 values
  * (at most 256 sources per destination); u = csn_grad_unscale's factor when amax != NULL, else 1.  The residual path
  * of the attention backward: `q = self.layer_norm(q + residual)` (MID-FC/csa_models.py:113, attention.py:53) sends

@@ -267,3 +267,24 @@ def test_block_add_matches_index_add():
         if am is not None:
             want = want / 2.0 ** float(torch.floor(torch.log2(128.0 / amax.double())))
         assert float((dst.double() - want).abs().max()) < 1e-5
+
+
+def test_ragged_pad_matches_index_put():
+    """csn_ragged_pad: concatenated rows -> zero-padded slots, fp32 and 16-bit copies."""
+    from csn_b200 import _lib as L
+    g = torch.Generator().manual_seed(9)
+    lens, n_pad = [5, 128, 0, 77], 128
+    x = torch.randn(sum(lens), 256, generator=g).cuda()
+    offs = torch.tensor([0] + list(torch.tensor(lens).cumsum(0)), dtype=torch.int64).cuda()
+    for dt in (torch.float16, torch.bfloat16):
+        o32 = torch.full((len(lens) * n_pad, 256), float("nan"), device="cuda")
+        o16 = torch.full((len(lens) * n_pad, 256), float("nan"), device="cuda", dtype=dt)
+        L.check(L.lib().csn_ragged_pad(x.data_ptr(), offs.data_ptr(), len(lens), n_pad, o32.data_ptr(), o16.data_ptr(),
+                                       L.dtype_code(dt), L.stream_ptr()), "ragged_pad")
+        want = torch.zeros(len(lens), n_pad, 256, device="cuda")
+        o = 0
+        for s, n in enumerate(lens):
+            want[s, :n] = x[o:o + n]
+            o += n
+        assert torch.equal(o32.view_as(want), want)
+        assert torch.equal(o16.view_as(want), want.to(dt))
