@@ -46,6 +46,8 @@ struct DkvArgs {
   int n_items;
   const float* lse;
   const float* delta;
+  const float* lse2;    // dkv kernel: lse * log2(e) and delta / sqrt(d), pre-scaled (bulk-copied per tile by the producer)
+  const float* dlt_s;
   float scale_log2, scale;
   int dtype;
   uint32_t idesc_s;   // M=128, N=128, K-major x K-major
@@ -67,8 +69,9 @@ struct DkvCfg {
   static constexpr int CW = EW_WARPS == 16 ? 16 : 32;   // columns per tcgen05.ld
   static constexpr int EW_THREADS = 32 * EW_WARPS;
   static constexpr int THREADS = 128 + EW_THREADS;
-  static constexpr int STAT_BYTES = 2 * 2 * 128 * 4;  // [buffer][lse | delta][128 queries]
-  static constexpr int BAR_BYTES = 256;
+  static constexpr int NSTAT = 4;                      // ring of per-tile statistics: [lse | delta][128 queries]
+  static constexpr int STAT_BYTES = NSTAT * 2 * 128 * 4;
+  static constexpr int BAR_BYTES = 384;
   static constexpr int SMEM_BYTES = 2 * TILE_BYTES + OUT_BYTES + NST * SLOT_BYTES + STAT_BYTES + BAR_BYTES + 1024;
   // TMEM: S^T @0, dP^T @128 (fp32), dV @256, dK @320 (fp32), P^T @384, dS^T @448 (16-bit pairs: 128 queries = 64 columns)
   static constexpr int DV_COL = 256, DK_COL = 320, PT_COL = 384, DST_COL = 448;
@@ -100,7 +103,10 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_consta
   const uint32_t st_empty = bar_base + 8u * (2 * Cfg::NST + 5);    // output MMAs of tile j done reading them
   const uint32_t acc_full = bar_base + 8u * (2 * Cfg::NST + 6);
   const uint32_t acc_empty = bar_base + 8u * (2 * Cfg::NST + 7);
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bar_ptr + 8 * (2 * Cfg::NST + 8));
+  auto stat_full = [&](int s) { return bar_base + 8u * (2 * Cfg::NST + 8 + s); };
+  auto stat_empty = [&](int s) { return bar_base + 8u * (2 * Cfg::NST + 8 + Cfg::NSTAT + s); };
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bar_ptr + 8 * (2 * Cfg::NST + 8 + 2 * Cfg::NSTAT));
+  const uint32_t sStat = smem_u32(stat);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -115,6 +121,10 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_consta
     for (int s = 0; s < Cfg::NST; ++s) {
       mbar_init(kv_full(s), 1);
       mbar_init(kv_empty(s), 1);
+    }
+    for (int s = 0; s < Cfg::NSTAT; ++s) {
+      mbar_init(stat_full(s), 1);
+      mbar_init(stat_empty(s), Cfg::EW_THREADS);
     }
     mbar_init(bres_full, 1);
     mbar_init(bres_empty, 1);
@@ -138,13 +148,20 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_consta
   if (warp == 0) {
     // ================================================================== TMA producer
     if (elect_one()) {
-      int st = 0;
-      uint32_t ph = 0, r_ph = 0;
+      int st = 0, ss = 0;
+      uint32_t ph = 0, r_ph = 0, s_ph = 0;
       auto load_slot = [&](const CUtensorMap* tm, int col0, int row0) {
         mbar_wait(kv_empty(st), ph ^ 1);
         mbar_arrive_expect_tx(kv_full(st), Cfg::SLOT_BYTES);
         tma_load_2d(sRing + st * Cfg::SLOT_BYTES, tm, kv_full(st), col0, row0);
         if (++st == Cfg::NST) { st = 0; ph ^= 1; }
+      };
+      auto load_stats = [&](const DkvItem& it, int j) {   // lse2 | delta_s of the 128 queries of tile j: two 512 B bulk copies
+        mbar_wait(stat_empty(ss), s_ph ^ 1);
+        mbar_arrive_expect_tx(stat_full(ss), 1024);
+        bulk_load_1d(sStat + ss * 1024, p.lse2 + it.stat_off + j * 128, 512, stat_full(ss));
+        bulk_load_1d(sStat + ss * 1024 + 512, p.dlt_s + it.stat_off + j * 128, 512, stat_full(ss));
+        if (++ss == Cfg::NSTAT) { ss = 0; s_ph ^= 1; }
       };
       for (int wk = blockIdx.x; wk < p.n_items; wk += gridDim.x) {
         const DkvItem it = p.items[wk];
@@ -155,10 +172,12 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_consta
         tma_load_2d(sV, &tmV, bres_full, it.col0, it.k_row0);
         r_ph ^= 1;
         // consumption order of the MMA warp: [Q0, dO0], [Q1, dO1], dO0, Q0, [Q2, dO2], dO1, Q1, ...
+        load_stats(it, 0);
         load_slot(&tmQ, it.col0, it.q_row0);
         load_slot(&tmDO, it.col0, it.do_row0);
         for (int j = 0; j < nq; ++j) {
           if (j + 1 < nq) {
+            load_stats(it, j + 1);
             load_slot(&tmQ, it.col0, it.q_row0 + (j + 1) * 128);
             load_slot(&tmDO, it.col0, it.do_row0 + (j + 1) * 128);
           }
@@ -230,33 +249,19 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_consta
     const int half = (warp - 4) >> 2;            // query columns [COLS half, COLS half + COLS)
     constexpr int COLS = Cfg::COLS, CW = Cfg::CW;
     const int r = q * 32 + lane;                 // key row of the tile owned by this thread
-    const int et = threadIdx.x - 128;            // 0 .. EW_THREADS-1
     const uint32_t lane_addr = uint32_t(q * 32) << 16;
-    uint32_t sdp_ph = 0, ste_ph = 0, accf_ph = 0;
-    constexpr float LOG2E = 1.4426950408889634f;
+    uint32_t sdp_ph = 0, ste_ph = 0, accf_ph = 0, stat_ph = 0;
+    int ss = 0;
     for (int wk = blockIdx.x; wk < p.n_items; wk += gridDim.x) {
       const DkvItem it = p.items[wk];
       const int nq = (it.q_len + 127) >> 7;
       const bool kvalid = r < it.k_valid;
-      // per-query statistics of tile 0 (lse in log2 units, delta pre-scaled); later tiles are prefetched one ahead
-      asm volatile("bar.sync 1, %0;" ::"n"(Cfg::EW_THREADS) : "memory");   // nobody still reads the buffers / staging rows
-      if (et < 128) {
-        const bool qv = et < it.q_len;
-        stat[et] = qv ? p.lse[it.stat_off + et] * LOG2E : 0.f;
-        stat[128 + et] = qv ? p.delta[it.stat_off + et] * p.scale : 0.f;
-      }
       for (int j = 0; j < nq; ++j) {
         const int nvalid = min(128, it.q_len - j * 128);
-        float nl = 0.f, nd = 0.f;
-        if (et < 128 && j + 1 < nq) {
-          const int n = (j + 1) * 128 + et;
-          if (n < it.q_len) {
-            nl = p.lse[it.stat_off + n] * LOG2E;
-            nd = p.delta[it.stat_off + n] * p.scale;
-          }
-        }
-        asm volatile("bar.sync 1, %0;" ::"n"(Cfg::EW_THREADS) : "memory");   // statistics of tile j visible
-        const float* st_l = stat + (j & 1) * 256;
+        // per-query statistics of this tile (lse in log2 units, delta pre-scaled): bulk-copied by the producer warp
+        // into a ring; no block-wide barrier anywhere in this loop (it cost 23 % of the warps' time: ncu)
+        mbar_wait(stat_full(ss), stat_ph);
+        const float* st_l = stat + ss * 256;
         const float* st_d = st_l + 128;
         mbar_wait(sdp_full, sdp_ph);
         sdp_ph ^= 1;
@@ -331,13 +336,11 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_consta
         } else {
           if (full) ew_tile(std::false_type{}, std::true_type{}); else ew_tile(std::false_type{}, std::false_type{});
         }
+        mbar_arrive(stat_empty(ss));   // (every read of the statistics precedes the stores above in program order)
+        if (++ss == Cfg::NSTAT) { ss = 0; stat_ph ^= 1; }
         tmem_st_wait();
         tc_fence_before();
         mbar_arrive(st_full);
-        if (et < 128 && j + 1 < nq) {   // statistics of tile j+1 into the other buffer (its readers passed this tile's barrier)
-          stat[((j + 1) & 1) * 256 + et] = nl;
-          stat[((j + 1) & 1) * 256 + 128 + et] = nd;
-        }
       }
       // ---- epilogue: warps 4-7 write dV, warps 8-11 dK; each warp stages its 32 rows in its own rows of one of the
       //      (now idle) staging tiles and hands the [32 x 64] slab to the TMA store engine
@@ -727,6 +730,8 @@ int launch_dq64(const CUtensorMap& tmQ, const CUtensorMap& tmDO, const CUtensorM
   a.n_items = n_items;
   a.lse = lse;
   a.delta = delta;
+  a.lse2 = nullptr;
+  a.dlt_s = nullptr;
   a.scale = 1.0f / sqrtf(64.f);
   a.scale_log2 = a.scale * 1.4426950408889634f;
   a.dtype = dtype;
@@ -737,6 +742,15 @@ int launch_dq64(const CUtensorMap& tmQ, const CUtensorMap& tmDO, const CUtensorM
   a.drop_thresh = drop_thresh16(drop_p);
   a.drop_scale = drop_scale_of(a.drop_thresh);
   return a.drop_thresh ? launch_dq64_d<true>(tmQ, tmDO, tmK, tmV, tmDQ, a, stream) : launch_dq64_d<false>(tmQ, tmDO, tmK, tmV, tmDQ, a, stream);
+}
+
+// lse -> lse * log2(e), delta -> delta / sqrt(d): what the dK/dV kernel's element-wise stage consumes per COLUMN
+__global__ void dkv_stats_scale_kernel(const float* __restrict__ lse, const float* __restrict__ delta, long long n, float scale,
+                                       float* __restrict__ out) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    out[i] = lse[i] * 1.4426950408889634f;
+    out[n + i] = delta[i] * scale;
+  }
 }
 
 template <bool DROP>
@@ -759,11 +773,13 @@ static int launch_dkv(const CUtensorMap& tmK, const CUtensorMap& tmV, const CUte
 extern "C" int csn_attn_bwd_dkv(const void* K, const void* V, const void* Q, const void* dO, int64_t kv_rows, int64_t q_rows,
                                 int64_t do_rows, int64_t width, int64_t ldk, int64_t ldv, int64_t ldq, int64_t lddo,
                                 int32_t d_head, int32_t dtype, const int32_t* items, int32_t n_items, void* dK, void* dV,
-                                int64_t out_rows, int64_t ldout, const float* lse, const float* delta,
-                                uint32_t drop_seed, float drop_p, void* stream) {
+                                int64_t out_rows, int64_t ldout, const float* lse, const float* delta, int64_t n_stats,
+                                float* stat_scratch, uint32_t drop_seed, float drop_p, void* stream) {
   using namespace csn;
   clear_error();
-  CSN_CHECK_ARG(K && V && Q && dO && items && dK && dV && lse && delta, "csn_attn_bwd_dkv: null pointer");
+  CSN_CHECK_ARG(K && V && Q && dO && items && dK && dV && lse && delta && stat_scratch, "csn_attn_bwd_dkv: null pointer");
+  CSN_CHECK_ARG(n_stats > 0 && n_stats % 4 == 0 && (reinterpret_cast<uintptr_t>(stat_scratch) & 15) == 0,
+                "csn_attn_bwd_dkv: statistics scratch must be 16B aligned, n_stats a multiple of 4");
   CSN_CHECK_ARG(drop_p >= 0.f && drop_p < 1.f, "csn_attn_bwd_dkv: dropout probability %f outside [0, 1)", (double)drop_p);
   CSN_CHECK_ARG(d_head == 64, "csn_attn_bwd_dkv: d_head=%d not supported (64: both output accumulators must fit in TMEM)", d_head);
   CSN_CHECK_ARG(dtype == CSN_F16 || dtype == CSN_BF16, "csn_attn_bwd_dkv: 16-bit operands only");
@@ -787,6 +803,8 @@ extern "C" int csn_attn_bwd_dkv(const void* K, const void* V, const void* Q, con
   a.n_items = n_items;
   a.lse = lse;
   a.delta = delta;
+  a.lse2 = stat_scratch;
+  a.dlt_s = stat_scratch + n_stats;
   a.scale = 1.0f / sqrtf((float)d_head);
   a.scale_log2 = a.scale * 1.4426950408889634f;
   a.dtype = dtype;
@@ -797,5 +815,8 @@ extern "C" int csn_attn_bwd_dkv(const void* K, const void* V, const void* Q, con
   a.drop_thresh = drop_thresh16(drop_p);
   a.drop_scale = drop_scale_of(a.drop_thresh);
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  dkv_stats_scale_kernel<<<(unsigned)((n_stats + 1023) / 1024 < 1184 ? (n_stats + 1023) / 1024 : 1184), 256, 0, s>>>(
+      lse, delta, n_stats, a.scale, stat_scratch);
+  CSN_LAUNCH_OK("dkv_stats_scale_kernel");
   return a.drop_thresh ? launch_dkv<true>(tmK, tmV, tmQ, tmDO, tmDK, tmDV, a, s) : launch_dkv<false>(tmK, tmV, tmQ, tmDO, tmDK, tmDV, a, s);
 }

@@ -607,10 +607,11 @@ def attention_backward(ctx: AttnContext, dY: torch.Tensor, need_dx: bool, amax: 
         fuse_dkv = d == 64 and os.environ.get("CSN_FUSED_DKV", "1") == "1" and os.environ.get("CSN_FUSED_DQ", "1") == "1"
         if fuse_dkv:
             it_kv = attn_items(ctx.groups, geom, h, d, dev, "dkv")
+            stat_scratch = torch.empty(2 * lse.numel(), dtype=torch.float32, device=dev)
             rc = lib.csn_attn_bwd_dkv(Kv.data_ptr(), Vv.data_ptr(), Qv.data_ptr(), dO.data_ptr(), S * NP, S * NP, nblk * NP, HD,
                                       3 * HD, 3 * HD, 3 * HD, HD, d, L.dtype_code(dt), it_kv.data_ptr(), it_kv.shape[0],
                                       dKv.data_ptr(), dVv.data_ptr(), nblk * NP, 3 * HD, lse.data_ptr(), delta.data_ptr(),
-                                      drop[1], drop[0], L.stream_ptr())
+                                      lse.numel(), stat_scratch.data_ptr(), drop[1], drop[0], L.stream_ptr())
             L.check(rc, "csn_attn_bwd_dkv")
             it_dq = attn_items(ctx.groups, geom, h, d, dev, "dq")
             rc = lib.csn_attn_bwd_dq(Qv.data_ptr(), dO.data_ptr(), Kv.data_ptr(), Vv.data_ptr(), S * NP, nblk * NP, S * NP,

@@ -175,12 +175,14 @@ int csn_attn_fwd(const void* Q, const void* K, const void* V, int64_t q_rows, in
  * do_row0, key0, 0, 0, 0}: resident key rows [k_row0, +128) of the K / V views (k_valid of them exist), streamed
  * query rows [q_row0, q_row0 + q_len) of the Q view and [do_row0, ...) of dO, lse / delta of streamed query n at
  * [stat_off + n], outputs at rows [o_row0, +128) x columns [col0, +64) of dK and dV (rows >= k_valid: zeros).
- * key0 = index of the first resident key inside its chunk (dropout mask column, see the dropout paragraph). */
+ * key0 = index of the first resident key inside its chunk (dropout mask column, see the dropout paragraph).
+ * lse / delta hold n_stats values (a multiple of 4); stat_scratch (2 * n_stats floats, 16B aligned) receives their
+ * pre-scaled copies (lse * log2 e | delta / sqrt d), which the kernel's producer warp bulk-copies tile by tile. */
 int csn_attn_bwd_dkv(const void* K, const void* V, const void* Q, const void* dO, int64_t kv_rows, int64_t q_rows,
                      int64_t do_rows, int64_t width, int64_t ldk, int64_t ldv, int64_t ldq, int64_t lddo,
                      int32_t d_head, int32_t dtype, const int32_t* items, int32_t n_items, void* dK, void* dV,
-                     int64_t out_rows, int64_t ldout, const float* lse, const float* delta,
-                     uint32_t drop_seed, float drop_p, void* stream);
+                     int64_t out_rows, int64_t ldout, const float* lse, const float* delta, int64_t n_stats,
+                     float* stat_scratch, uint32_t drop_seed, float drop_p, void* stream);
 
 /* Backward of the attention core (autograd of csa_models.py:139-142), three pieces:
  *  csn_attn_delta : delta[(blk*h+head)*rows_pad + r] = sum_c dO[blk*rows_pad+r][head*d+c] * (O + O_lo/2^11)[..]
