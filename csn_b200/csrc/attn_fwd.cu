@@ -51,7 +51,10 @@ struct AttnCfg {
   static constexpr int O_COL = 256;                        // TMEM: S0 @0, S1 @128, O @256 (DH <= 256)
   // d_head 64: the 16-bit probabilities go back into TMEM (two buffers of 64 columns = 128 keys as 16-bit pairs,
   // behind the 64 columns of O) and are the A operand of P V from there; no SMEM round trip, P double-buffered
-  static constexpr int P_COL = 320;
+  // and the two softmax warps of a lane quadrant (key columns 0-63 / 64-127 of every tile) each own a PRIVATE
+  // running max, row sum and [128 x 64] accumulator (O_0 @256, O_1 @320): no cross-warp agreement inside the tile
+  // loop; the two partial results are merged once per item in the epilogue.
+  static constexpr int P_COL = 384;
 };
 
 template <int DH, int MODE, int CL, bool DROP>
@@ -75,6 +78,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   auto s_full = [&](int b) { return bar_base + 8u * (2 * Cfg::NST + 2 + b); };
   auto s_empty = [&](int b) { return bar_base + 8u * (2 * Cfg::NST + 4 + b); };
   constexpr bool TSP = (DH == 64 && MODE == 0);   // P through TMEM (forward, d_head 64)
+  constexpr bool PRIV = TSP;                      // ... with one accumulator per column half
   auto bp_full = [&](int b) { return bar_base + 8u * (2 * Cfg::NST + (b ? 10 : 6)); };
   auto bp_empty = [&](int b) { return bar_base + 8u * (2 * Cfg::NST + (b ? 11 : 7)); };
   const uint32_t bo_full = bar_base + 8u * (2 * Cfg::NST + 8);
@@ -239,9 +243,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
               // forward: A = P[query][key], K-major (contraction over keys: 32 B per step inside a swizzled row)
               // dV mode: A = P^T: the same tile [query rows][keys] read MN-major (M = keys contiguous, two
               //          64-key atoms 16 KB apart; contraction over queries: 16 rows = 2048 B per step)
-              if constexpr (TSP) {   // A = P from TMEM: 16 keys = 8 columns of 16-bit pairs
-                umma_f16_ts(o_tmem, tmem_base + Cfg::P_COL + pb * 64 + (key >> 1),
-                            umma_desc_sw128(v_tile + k * 2048, Cfg::KEYS_PER_VSLOT * 128, 1024), p.idesc_pv, (j | s | k) ? 1u : 0u);
+              if constexpr (TSP) {   // A = P from TMEM: 16 keys = 8 columns of 16-bit pairs; keys 64-127 -> O_1
+                umma_f16_ts(o_tmem + (key >> 6) * 64, tmem_base + Cfg::P_COL + pb * 64 + (key >> 1),
+                            umma_desc_sw128(v_tile + k * 2048, Cfg::KEYS_PER_VSLOT * 128, 1024), p.idesc_pv,
+                            (j | (key & 63)) ? 1u : 0u);
               } else {
                 const uint64_t da = (MODE == 0) ? umma_desc_sw128(sP + (key >> 6) * 16384 + (key & 63) * 2, 0, 1024)
                                                 : umma_desc_sw128(sP + (key >> 4) * 2048, 16384, 1024);
@@ -277,6 +282,13 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       const float o = xch[(half ^ 1) * 128 + r];
       asm volatile("bar.sync 2, %0;" ::"n"(Cfg::SM_THREADS) : "memory");   // the slots may be written again
       return is_max ? fmaxf(v, o) : v + o;
+    };
+    auto row_exchange_raw = [&](float v) -> float {   // the partner's value
+      xch[half * 128 + r] = v;
+      asm volatile("bar.sync 2, %0;" ::"n"(Cfg::SM_THREADS) : "memory");
+      const float o = xch[(half ^ 1) * 128 + r];
+      asm volatile("bar.sync 2, %0;" ::"n"(Cfg::SM_THREADS) : "memory");
+      return o;
     };
     // SPLIT: OR of a predicate over every softmax thread (a retry decision must be taken by both halves of a row)
     auto any_thread = [&](bool pred) -> bool {
@@ -383,6 +395,93 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             if (full) dv_tile(std::false_type{}, std::true_type{}); else dv_tile(std::false_type{}, std::false_type{});
           }
         } else {
+          if constexpr (PRIV) {
+          // ---- forward, d_head 64: this thread's 64 scores go into registers at once (the S buffer is released
+          //      before the arithmetic starts), their exact maximum decides about the (rare, > 2^8) re-scale of the
+          //      thread's own accumulator rows; nothing is shared with the partner warp until the epilogue.
+          uint32_t v0[32], v1[32];
+          tmem_ld_32x32(s_addr + c_lo, v0);
+          tmem_ld_32x32(s_addr + c_lo + 32, v1);
+          tmem_ld_wait();
+          tc_fence_before();
+          mbar_arrive(s_empty(b));
+          const int nv = nvalid - c_lo;   // valid columns among this thread's 64 (<= 0: none)
+          float mx = -INFINITY;
+          if (nv >= 64) {   // (warp-uniform) no padding in this thread's columns: no per-element predicates
+#pragma unroll
+            for (int i = 0; i < 32; ++i) mx = fmaxf(mx, fmaxf(__uint_as_float(v0[i]), __uint_as_float(v1[i])));
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              if (i < nv) mx = fmaxf(mx, __uint_as_float(v0[i]));
+              if (32 + i < nv) mx = fmaxf(mx, __uint_as_float(v1[i]));
+            }
+          }
+          float alpha = 1.f;
+          bool need = false;
+          if (j == 0) {
+            m_used = (mx == -INFINITY) ? 0.f : mx;   // (no valid column at all in this half: P = exp2(-inf) = 0, l stays 0)
+          } else if ((mx - m_used) * p.scale_log2 > 8.f) {
+            alpha = fast_exp2((m_used - mx) * p.scale_log2);
+            m_used = mx;
+            need = true;
+          }
+          if (__any_sync(0xffffffffu, need)) {
+            // the accumulator may still be receiving P V of the previous tile (P is double-buffered): wait for it
+            if (j > 0) mbar_wait(bp_empty(pb ^ 1), pe_ph[pb ^ 1] ^ 1);
+            tc_fence_after();
+            const uint32_t o_addr = tmem_base + lane_addr + Cfg::O_COL + half * 64;
+#pragma unroll 1
+            for (int c = 0; c < 64; c += 32) {
+              uint32_t v[32];
+              tmem_ld_32x32(o_addr + c, v);
+              tmem_ld_wait();
+#pragma unroll
+              for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * alpha);
+              tmem_st_32x32(o_addr + c, v);
+            }
+            tmem_st_wait();
+            l *= alpha;
+          }
+          const float moff = m_used * p.scale_log2;
+          const uint32_t rk = drop_row_key(p.drop_seed, (uint32_t)(it.lse_off + r));
+          float lsum = 0.f;
+          uint32_t pk[32];
+          auto exp_regs = [&](auto F16C, auto FULLC) {
+            constexpr bool FULL = decltype(FULLC)::value;
+#pragma unroll
+            for (int i = 0; i < 32; i += 2) {
+              float a0 = fast_exp2(__uint_as_float(v0[i]) * p.scale_log2 - moff);
+              float a1 = fast_exp2(__uint_as_float(v0[i + 1]) * p.scale_log2 - moff);
+              float b0 = fast_exp2(__uint_as_float(v1[i]) * p.scale_log2 - moff);
+              float b1 = fast_exp2(__uint_as_float(v1[i + 1]) * p.scale_log2 - moff);
+              if (!FULL) {
+                if (!(i < nv)) a0 = 0.f;
+                if (!(i + 1 < nv)) a1 = 0.f;
+                if (!(32 + i < nv)) b0 = 0.f;
+                if (!(33 + i < nv)) b1 = 0.f;
+              }
+              lsum += (a0 + a1) + (b0 + b1);   // the softmax denominator sees every key; dropout acts on the result
+              if (DROP) {
+                const uint32_t h0 = drop_pair(rk, (uint32_t)(j * 128 + c_lo + i) >> 1), h1 = drop_pair(rk, (uint32_t)(j * 128 + c_lo + 32 + i) >> 1);
+                a0 = drop_keep_lo(h0, p.drop_thresh) ? a0 * p.drop_scale : 0.f; a1 = drop_keep_hi(h0, p.drop_thresh) ? a1 * p.drop_scale : 0.f;
+                b0 = drop_keep_lo(h1, p.drop_thresh) ? b0 * p.drop_scale : 0.f; b1 = drop_keep_hi(h1, p.drop_thresh) ? b1 * p.drop_scale : 0.f;
+              }
+              pk[i >> 1] = pack_t(F16C, a0, a1);
+              pk[16 + (i >> 1)] = pack_t(F16C, b0, b1);
+            }
+          };
+          if (p.dtype == CSN_F16) {
+            if (nv >= 64) exp_regs(std::true_type{}, std::true_type{}); else exp_regs(std::true_type{}, std::false_type{});
+          } else {
+            if (nv >= 64) exp_regs(std::false_type{}, std::true_type{}); else exp_regs(std::false_type{}, std::false_type{});
+          }
+          mbar_wait(bp_empty(pb), pe_ph[pb] ^ 1);   // the P buffer may be overwritten once the P V MMAs that read it have completed
+          pe_ph[pb] ^= 1;
+          tc_fence_after();
+          tmem_st_32x32(tmem_base + lane_addr + Cfg::P_COL + pb * 64 + (c_lo >> 1), pk);
+          l += lsum;
+          } else {
           // ---- forward: online softmax. Tile 0 takes the exact row max first; later tiles are
           //      exponentiated optimistically against the running reference max and only redone
           //      (two-pass + rescale of O) if some score exceeds it by more than 2^8.
@@ -483,11 +582,12 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           }
           if (need) l *= alpha;
           l += lsum;
+          }
         }
         // S_j fully consumed; P_j visible to the tensor-core (async) proxy
         if (TSP) tmem_st_wait();
         tc_fence_before();
-        mbar_arrive(s_empty(b));
+        if (!PRIV) mbar_arrive(s_empty(b));
         if (!TSP) fence_proxy_async_smem();
         mbar_arrive(bp_full(pb));
       }
@@ -495,8 +595,21 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       mbar_wait(bo_full, of_ph);
       of_ph ^= 1;
       tc_fence_after();
+      float a_me = 1.f, a_ot = 0.f;   // PRIV: weights of this thread's and the partner's partial results
       if (SPLIT) {
-        if (MODE == 0) l = row_exchange(l, false);
+        if (PRIV) {
+          // merge the two column halves: reference max m = max over the halves that saw a key, weights 2^((m_h - m) scale)
+          const float l_ot = row_exchange_raw(l);
+          const float m_me = l > 0.f ? m_used : -INFINITY;
+          const float m_ot = row_exchange_raw(m_me);
+          const float m = fmaxf(m_me, m_ot);
+          a_me = l > 0.f ? fast_exp2((m_me - m) * p.scale_log2) : 0.f;
+          a_ot = l_ot > 0.f ? fast_exp2((m_ot - m) * p.scale_log2) : 0.f;
+          l = l * a_me + l_ot * a_ot;
+          m_used = m;
+        } else if (MODE == 0) {
+          l = row_exchange(l, false);
+        }
         if (half != 0) {
           // warps 4-7 write the output through the P tile: nobody may refill it before their slabs have left
           asm volatile("bar.sync 3, %0;" ::"n"(Cfg::SM_THREADS) : "memory");
@@ -518,6 +631,17 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         tmem_ld_32x32(o_addr + c, v0);
         tmem_ld_32x32(o_addr + c + 32, v1);
         tmem_ld_wait();
+        if constexpr (PRIV) {   // O = O_0 a_0 + O_1 a_1 (this thread is in half 0: O_0 is its own)
+          uint32_t w0[32], w1[32];
+          tmem_ld_32x32(o_addr + 64, w0);
+          tmem_ld_32x32(o_addr + 96, w1);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            v0[i] = __float_as_uint(__uint_as_float(v0[i]) * a_me + __uint_as_float(w0[i]) * a_ot);
+            v1[i] = __float_as_uint(__uint_as_float(v1[i]) * a_me + __uint_as_float(w1[i]) * a_ot);
+          }
+        }
         uint32_t hi[32], lo[32];
 #pragma unroll
         for (int i = 0; i < 32; i += 2) {

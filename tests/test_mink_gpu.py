@@ -251,3 +251,27 @@ def test_fused_dkv_backward_matches_ds_path(precision, tol):
     for i, (x, y) in enumerate(zip(a, b)):
         assert torch.isfinite(x).all()
         assert G.rel_err(x, y) < tol, (i, G.rel_err(x, y))
+
+
+@pytest.mark.parametrize("L", [300, 1000])
+def test_growing_scores_force_accumulator_rescale(L):
+    """Keys whose scores grow along the sequence: every later key tile raises the running row maximum by far more
+    than the 2^8 the kernels tolerate, so the lazy re-scale of the TMEM accumulators (rare on random data) runs in
+    (almost) every tile, also in the second column half.  Forward + backward against the oracle."""
+    from oracle import csa_oracle as O
+    h = 4
+    m = _mha(21, h)
+    w = synth.mink_state(21, h)
+    g = synth.gen(22)
+    x = torch.relu(torch.randn(1, L, 256, generator=g))
+    x = x * torch.linspace(0.2, 6.0, L).view(1, L, 1)          # row norms (and with them the scores) grow with the index
+    xr = x.clone().requires_grad_(True)
+    want, _ = O.mha_mink(xr, xr, xr, w, h)
+    gy = torch.randn(want.shape, generator=g)
+    (want * gy).sum().backward()
+    xd = x.cuda().requires_grad_(True)
+    got, _ = m(xd, xd, xd)
+    (got * gy.cuda()).sum().backward()
+    assert torch.isfinite(got).all()
+    assert G.rel_err(got.detach().cpu(), want.detach()) < TOL
+    assert G.rel_err(xd.grad.cpu(), xr.grad) < 2e-3
