@@ -48,4 +48,8 @@ struct AttnFwdArgs {
 int launch_attn_wide(int mode, bool pair, const CUtensorMap& tmQ, const CUtensorMap& tmK, const CUtensorMap& tmV,
                      const CUtensorMap& tmO, const CUtensorMap& tmOlo, const AttnFwdArgs& a, cudaStream_t stream);
 
+// attn_fwd64.cu: d_head = 64 forward (16 softmax warps, private accumulators per column quarter, P through TMEM)
+int launch_attn_fwd64(const CUtensorMap& tmQ, const CUtensorMap& tmK, const CUtensorMap& tmV, const CUtensorMap& tmO,
+                      const CUtensorMap& tmOlo, const AttnFwdArgs& a, cudaStream_t stream);
+
 }  // namespace csn

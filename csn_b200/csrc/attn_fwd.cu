@@ -821,6 +821,8 @@ static int attn_launch_common(int mode, const void* Q, const void* K, const void
   }
   if (mode == 0) {
     if (d_head == 256) return pair ? launch_attn_fwd<256, 0, 2>(tmQ, tmK, tmV, tmO, tmOlo, a, s) : launch_attn_fwd<256, 0, 1>(tmQ, tmK, tmV, tmO, tmOlo, a, s);
+    static const int fwd64 = getenv("CSN_FWD64") == nullptr ? 1 : atoi(getenv("CSN_FWD64"));
+    if (fwd64) return launch_attn_fwd64(tmQ, tmK, tmV, tmO, tmOlo, a, s);   // 16 softmax warps (attn_fwd64.cu)
     return launch_attn_fwd<64, 0, 1>(tmQ, tmK, tmV, tmO, tmOlo, a, s);
   }
   CSN_CHECK_ARG(lse != nullptr, "csn_attn_bwd_dv: lse is required");
