@@ -18,6 +18,7 @@
 // epilogue of an item runs after the first score tile of the NEXT item has been read, under that item's S_1.
 // SMEM: R 64 KB | P 64 KB | 3 x 32 KB ring ([256 x 64] K-major slices for S, [64 x 256] MN-major slices for P V).
 #include <stdlib.h>
+#include <type_traits>
 
 #include "attn_common.cuh"
 
@@ -352,16 +353,30 @@ attn_wide_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
           const uint32_t rk0 = drop_row_key(p.drop_seed, (uint32_t)(it.lse_off + r));   // MODE 0: the thread's query row
           const float4* lse4 = reinterpret_cast<const float4*>(xch + half * 128);
           uint32_t va[32], vb[32];
-          auto conv = [&](const uint32_t (&v)[32], int c) {
+          // operand type and "no padding among this warp's rows and columns" are compile-time variants of the
+          // conversion (per-element bounds predicates and both 16-bit packings cost ~10 % of the stage otherwise)
+          auto conv_t = [&](const uint32_t (&v)[32], int c, auto F16C, auto FULLC) {
+            constexpr bool F16 = decltype(F16C)::value, FULL = decltype(FULLC)::value;
+            auto pack_pair = [&](float a, float b) -> uint32_t {   // shadows the run-time version
+              if (F16) { __half2 h = __floats2half2_rn(a, b); return *reinterpret_cast<uint32_t*>(&h); }
+              __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+              return *reinterpret_cast<uint32_t*>(&h);
+            };
 #pragma unroll
             for (int k = 0; k < 32; k += 4) {
               float4 off = make_float4(moff, moff, moff, moff);
               if (MODE == 1) off = lse4[(c * 32 + k) >> 2];
               const int c0 = c * 32 + k;
-              const float p0 = (rvalid && c0 < nvalid) ? fast_exp2(__uint_as_float(v[k]) * p.scale_log2 - off.x) : 0.f;
-              const float p1 = (rvalid && c0 + 1 < nvalid) ? fast_exp2(__uint_as_float(v[k + 1]) * p.scale_log2 - off.y) : 0.f;
-              const float p2 = (rvalid && c0 + 2 < nvalid) ? fast_exp2(__uint_as_float(v[k + 2]) * p.scale_log2 - off.z) : 0.f;
-              const float p3 = (rvalid && c0 + 3 < nvalid) ? fast_exp2(__uint_as_float(v[k + 3]) * p.scale_log2 - off.w) : 0.f;
+              float p0 = fast_exp2(__uint_as_float(v[k]) * p.scale_log2 - off.x);
+              float p1 = fast_exp2(__uint_as_float(v[k + 1]) * p.scale_log2 - off.y);
+              float p2 = fast_exp2(__uint_as_float(v[k + 2]) * p.scale_log2 - off.z);
+              float p3 = fast_exp2(__uint_as_float(v[k + 3]) * p.scale_log2 - off.w);
+              if (!FULL) {
+                if (!(rvalid && c0 < nvalid)) p0 = 0.f;
+                if (!(rvalid && c0 + 1 < nvalid)) p1 = 0.f;
+                if (!(rvalid && c0 + 2 < nvalid)) p2 = 0.f;
+                if (!(rvalid && c0 + 3 < nvalid)) p3 = 0.f;
+              }
               lsum += (p0 + p1) + (p2 + p3);   // the softmax denominator sees every key; dropout acts on the result
               float d0 = p0, d1 = p1, d2 = p2, d3 = p3;
               if (DROP) {
@@ -384,6 +399,15 @@ attn_wide_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
               }
               pk[c * 16 + (k >> 1)] = pack_pair(d0, d1);
               pk[c * 16 + (k >> 1) + 1] = pack_pair(d2, d3);
+            }
+          };
+          const int variant = (f16 ? 2 : 0) | ((nvalid >= 128 && __all_sync(0xffffffffu, rvalid)) ? 1 : 0);   // warp-uniform
+          auto conv = [&](const uint32_t (&v)[32], int c) {
+            switch (variant) {
+              case 0: conv_t(v, c, std::false_type{}, std::false_type{}); break;
+              case 1: conv_t(v, c, std::false_type{}, std::true_type{}); break;
+              case 2: conv_t(v, c, std::true_type{}, std::false_type{}); break;
+              default: conv_t(v, c, std::true_type{}, std::true_type{}); break;
             }
           };
           tmem_ld_32x32(s_addr, va);
