@@ -290,6 +290,11 @@ attn_wide_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     bool have_prev = false;
     AttnItem prev;
     float prev_m = 0.f, prev_l = 0.f;
+    float stat_next = 0.f;   // MODE 1: lse of query column (ew * 32 + lane) of the NEXT step, fetched one step ahead
+    if (MODE == 1 && worker < n_work) {
+      const AttnItem f = p.items[worker * CL + rank];
+      if (ew * 32 + lane < f.kv_len) stat_next = __ldg(p.lse + f.lse_off + ew * 32 + lane);
+    }
     for (int wk = worker; wk < n_work; wk += n_workers) {
       const AttnItem it = p.items[wk * CL + rank];
       const int nst = (it.kv_len + 255) >> 8;
@@ -335,9 +340,21 @@ attn_wide_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         if (MODE == 1) {
           // the step's 256 per-column statistics (log-sum-exp of the streamed query rows, in log2 units) go through
           // SMEM once: thread t of the 256 softmax threads fetches column t, everybody reads them back as broadcasts
-          const int t = ew * 32 + lane, col = i * 256 + t;
+          // (this thread's value was fetched one step ahead: its global-load latency is off the critical path)
+          const int t = ew * 32 + lane;
+          const float mine = stat_next * LOG2E;
+          {   // prefetch for the next step: the same item's next 256 queries, or the first 256 of the next item
+            stat_next = 0.f;
+            if (i + 1 < nst) {
+              const int col = (i + 1) * 256 + t;
+              if (col < it.kv_len) stat_next = __ldg(p.lse + it.lse_off + col);
+            } else if (wk + n_workers < n_work) {
+              const AttnItem nx = p.items[(wk + n_workers) * CL + rank];
+              if (t < nx.kv_len) stat_next = __ldg(p.lse + nx.lse_off + t);
+            }
+          }
           asm volatile("bar.sync 5, 256;" ::: "memory");   // the previous step's values have been consumed
-          xch[t] = (col < it.kv_len) ? __ldg(p.lse + it.lse_off + col) * LOG2E : 0.f;
+          xch[t] = mine;
           asm volatile("bar.sync 5, 256;" ::: "memory");
         }
         // ---- pass 2: probabilities as 16-bit pairs in registers
