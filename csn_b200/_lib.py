@@ -146,6 +146,9 @@ _EXTRA_SIGNATURES: dict[str, list] = {
     "csn_pack_rows": [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int64, C.c_int32, C.c_int64,
                       C.c_int64, C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                       C.c_void_p, C.c_void_p, C.c_void_p],
+    "csn_pack_rows_src16": [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int64, C.c_int32, C.c_int64,
+                            C.c_int64, C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                            C.c_void_p, C.c_void_p, C.c_void_p],
     "csn_softmax_fwd": [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                         C.c_void_p],
     "csn_softmax_bwd": [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32,

@@ -30,8 +30,13 @@ __device__ __forceinline__ float2 unpack2(uint32_t w, int dtype) {
 }
 
 // ------------------------------------------------------------------------------------------ pack
+template <typename T> __device__ __forceinline__ float ld_as_float(const T* p);
+template <> __device__ __forceinline__ float ld_as_float<float>(const float* p) { return __ldg(p); }
+template <> __device__ __forceinline__ float ld_as_float<__half>(const __half* p) { return __half2float(__ldg(p)); }
+template <> __device__ __forceinline__ float ld_as_float<__nv_bfloat16>(const __nv_bfloat16* p) { return __bfloat162float(__ldg(p)); }
+
 struct PackArgs {
-  const float* src;     // channel-major: element (slot, c, n) at src + i0*src_s0 + i1*src_s1 + c*ch_stride + n
+  const void* src;      // channel-major (fp32, or 16-bit for csn_pack_rows_src16): element (slot, c, n) at src + i0*src_s0 + i1*src_s1 + c*ch_stride + n
   void* dst16;          // [slot][rows_pad][256] 16-bit
   float* dst32;         // same layout fp32, or null
   long long ch_stride, src_s0, src_s1;
@@ -44,11 +49,12 @@ struct PackArgs {
   float* chunk_sum;     // optional [slot*n_chunks + chunk][256]: per-chunk channel sums of the valid points (atomically accumulated)
 };
 
+template <typename TS>
 __global__ void __launch_bounds__(256) pack_kernel(const PackArgs p) {
   __shared__ float tile[32][DM + 1];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int i0 = blockIdx.y / p.n1, i1 = blockIdx.y % p.n1;
-  const float* src = p.src + i0 * p.src_s0 + i1 * p.src_s1;
+  const TS* src = reinterpret_cast<const TS*>(p.src) + i0 * p.src_s0 + i1 * p.src_s1;
   const long long slot = p.dst_slot0 + i0 * p.dst_s0 + i1 * p.dst_s1;
   const int r0 = blockIdx.x * 32;  // first padded row of this tile (32 | chunk_pad)
   const int ch = r0 / p.chunk_pad, i = r0 % p.chunk_pad + lane;
@@ -57,7 +63,7 @@ __global__ void __launch_bounds__(256) pack_kernel(const PackArgs p) {
   float amx = 0.f;
   float* csum = p.chunk_sum ? p.chunk_sum + (slot * (p.rows_pad / p.chunk_pad) + ch) * DM : nullptr;
   for (int c = warp; c < DM; c += 8) {
-    const float v = valid ? __ldg(src + c * p.ch_stride + n) : 0.f;
+    const float v = valid ? ld_as_float<TS>(src + c * p.ch_stride + n) : 0.f;
     tile[lane][c] = v;
     amx = fmaxf(amx, fabsf(v));
     if (csum) {
@@ -85,11 +91,12 @@ __global__ void __launch_bounds__(256) pack_kernel(const PackArgs p) {
 // 128 points x 64 channels per CTA (grid.z = the four channel groups): every channel row is read as 512 contiguous
 // bytes (four 128-byte requests back to back) instead of 128, which is what the DRAM pages want; the other three
 // quarters of each output row come from the sibling CTAs and merge in L2.
+template <typename TS>
 __global__ void __launch_bounds__(256) pack128_kernel(const PackArgs p) {
   __shared__ float tile[128][65];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int i0 = blockIdx.y / p.n1, i1 = blockIdx.y % p.n1;
-  const float* src = p.src + i0 * p.src_s0 + i1 * p.src_s1;
+  const TS* src = reinterpret_cast<const TS*>(p.src) + i0 * p.src_s0 + i1 * p.src_s1;
   const long long slot = p.dst_slot0 + i0 * p.dst_s0 + i1 * p.dst_s1;
   const int r0 = blockIdx.x * 128;            // first padded row of this tile (128 | chunk_pad)
   const int c0 = blockIdx.z * 64;             // first channel of this CTA
@@ -99,13 +106,13 @@ __global__ void __launch_bounds__(256) pack128_kernel(const PackArgs p) {
 #pragma unroll
   for (int k = 0; k < 8; ++k) {
     const int c = warp + 8 * k;
-    const float* row = src + (long long)(c0 + c) * p.ch_stride + (long long)ch * p.chunk;
+    const TS* row = src + (long long)(c0 + c) * p.ch_stride + (long long)ch * p.chunk;
     float sv = 0.f;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const int i = ib + lane + 32 * j;
       const int n = ch * p.chunk + i;
-      const float v = (i < p.chunk && n < p.n_points) ? __ldg(row + i) : 0.f;
+      const float v = (i < p.chunk && n < p.n_points) ? ld_as_float<TS>(row + i) : 0.f;
       tile[lane + 32 * j][c] = v;
       amx = fmaxf(amx, fabsf(v));
       sv += v;
@@ -841,12 +848,19 @@ __global__ void __launch_bounds__(256) segment_mean_kernel(const float* __restri
 }
 }  // namespace csn
 
-extern "C" {
+template <typename TS>
+static int launch_pack(const csn::PackArgs& a, void* stream) {
+  using namespace csn;
+  static const bool wide = getenv("CSN_PACK128") == nullptr || atoi(getenv("CSN_PACK128")) != 0;
+  if (wide && a.chunk_pad % 128 == 0)
+    return launch_simple(pack128_kernel<TS>, dim3(a.rows_pad / 128, a.n0 * a.n1, 4), dim3(256), a, stream, "pack128_kernel");
+  return launch_simple(pack_kernel<TS>, dim3(a.rows_pad / 32, a.n0 * a.n1), dim3(256), a, stream, "pack_kernel");
+}
 
-int csn_pack_rows(const float* src, void* dst16, float* dst32, int64_t ch_stride, int32_t n0, int64_t src_s0,
-                  int32_t n1, int64_t src_s1, int64_t dst_slot0, int64_t dst_s0, int64_t dst_s1,
-                  int32_t n_points, int32_t chunk, int32_t chunk_pad, int32_t rows_pad, int32_t dtype,
-                  float* amax, float* chunk_sum, void* stream) {
+static int pack_rows_common(const void* src, int32_t src_dtype, void* dst16, float* dst32, int64_t ch_stride, int32_t n0,
+                            int64_t src_s0, int32_t n1, int64_t src_s1, int64_t dst_slot0, int64_t dst_s0, int64_t dst_s1,
+                            int32_t n_points, int32_t chunk, int32_t chunk_pad, int32_t rows_pad, int32_t dtype,
+                            float* amax, float* chunk_sum, void* stream) {
   using namespace csn;
   clear_error();
   CSN_CHECK_ARG(src && (dst16 || dst32), "csn_pack_rows: null pointer");
@@ -854,10 +868,31 @@ int csn_pack_rows(const float* src, void* dst16, float* dst32, int64_t ch_stride
   CSN_CHECK_ARG(dtype == CSN_F16 || dtype == CSN_BF16, "csn_pack_rows: 16-bit destination only");
   if (n0 * n1 == 0) return 0;
   PackArgs a{src, dst16, dst32, ch_stride, src_s0, src_s1, dst_slot0, dst_s0, dst_s1, n0, n1, n_points, chunk, chunk_pad, rows_pad, dtype, amax, chunk_sum};
-  static const bool wide = getenv("CSN_PACK128") == nullptr || atoi(getenv("CSN_PACK128")) != 0;
-  if (wide && chunk_pad % 128 == 0)
-    return launch_simple(pack128_kernel, dim3(rows_pad / 128, n0 * n1, 4), dim3(256), a, stream, "pack128_kernel");
-  return launch_simple(pack_kernel, dim3(rows_pad / 32, n0 * n1), dim3(256), a, stream, "pack_kernel");
+  if (src_dtype == CSN_F16) return launch_pack<__half>(a, stream);
+  if (src_dtype == CSN_BF16) return launch_pack<__nv_bfloat16>(a, stream);
+  return launch_pack<float>(a, stream);
+}
+
+extern "C" {
+
+int csn_pack_rows(const float* src, void* dst16, float* dst32, int64_t ch_stride, int32_t n0, int64_t src_s0,
+                  int32_t n1, int64_t src_s1, int64_t dst_slot0, int64_t dst_s0, int64_t dst_s1,
+                  int32_t n_points, int32_t chunk, int32_t chunk_pad, int32_t rows_pad, int32_t dtype,
+                  float* amax, float* chunk_sum, void* stream) {
+  return pack_rows_common(src, -1, dst16, dst32, ch_stride, n0, src_s0, n1, src_s1, dst_slot0, dst_s0, dst_s1, n_points, chunk,
+                          chunk_pad, rows_pad, dtype, amax, chunk_sum, stream);
+}
+
+int csn_pack_rows_src16(const void* src, int32_t src_dtype, void* dst16, float* dst32, int64_t ch_stride, int32_t n0,
+                        int64_t src_s0, int32_t n1, int64_t src_s1, int64_t dst_slot0, int64_t dst_s0, int64_t dst_s1,
+                        int32_t n_points, int32_t chunk, int32_t chunk_pad, int32_t rows_pad, int32_t dtype,
+                        float* amax, float* chunk_sum, void* stream) {
+  if (src_dtype != CSN_F16 && src_dtype != CSN_BF16) {
+    csn::clear_error();
+    CSN_CHECK_ARG(false, "csn_pack_rows_src16: source dtype must be f16 or bf16");
+  }
+  return pack_rows_common(src, src_dtype, dst16, dst32, ch_stride, n0, src_s0, n1, src_s1, dst_slot0, dst_s0, dst_s1, n_points,
+                          chunk, chunk_pad, rows_pad, dtype, amax, chunk_sum, stream);
 }
 
 int csn_softmax_fwd(const float* S, void* P, int64_t rows, int32_t cols_pad, int32_t cols_valid,

@@ -70,12 +70,16 @@ class Group:
 
 def _launch_pack(src: torch.Tensor, dst16, dst32, n0, s0, n1, s1, slot0, d0, d1, geom: Geometry, n_src_points,
                  chunk_sum=None):
-    """src: fp32 view whose element (i0,i1,c,n) sits at i0*s0 + i1*s1 + c*n_src_points + n.
+    """src: fp32 (or fp16 / bf16) view whose element (i0,i1,c,n) sits at i0*s0 + i1*s1 + c*n_src_points + n.
     chunk_sum (optional, zero-initialised [n_slots*n_chunks, 256]): per-chunk channel sums of every packed shape."""
-    rc = L.lib().csn_pack_rows(src.data_ptr(), dst16.data_ptr(), dst32.data_ptr() if dst32 is not None else None,
-                               n_src_points, n0, s0, n1, s1, slot0, d0, d1, geom.n_points, geom.chunk,
-                               geom.chunk_pad, geom.rows_pad, L.dtype_code(dst16.dtype), None,
-                               chunk_sum.data_ptr() if chunk_sum is not None else None, L.stream_ptr())
+    tail = (dst16.data_ptr(), dst32.data_ptr() if dst32 is not None else None,
+            n_src_points, n0, s0, n1, s1, slot0, d0, d1, geom.n_points, geom.chunk,
+            geom.chunk_pad, geom.rows_pad, L.dtype_code(dst16.dtype), None,
+            chunk_sum.data_ptr() if chunk_sum is not None else None, L.stream_ptr())
+    if src.dtype in (torch.float16, torch.bfloat16):   # 16-bit feature cache (strides are in elements either way)
+        rc = L.lib().csn_pack_rows_src16(src.data_ptr(), L.dtype_code(src.dtype), *tail)
+    else:
+        rc = L.lib().csn_pack_rows(src.data_ptr(), *tail)
     L.check(rc, "csn_pack_rows")
 
 

@@ -347,17 +347,20 @@ def _csa_forward_core(x, x_neighbors, wq, wk, wv, wo, gamma, beta, cq_w, cq_b, c
     n_src_nb = n_src if ssa_only or K == 0 else x_neighbors.shape[3]
     geom = _geom_for(min(n_src, n_src_nb), iters, chunk)
     S = B * (K + 1)
-    xs = _std_layout(x.float())
+    # 16-bit inputs (a caller-side 16-bit feature cache: half the host-to-device bytes) are packed as they are; the
+    # residual then comes from the fp32 copy the pack kernel writes instead of the caller's channel-major tensors
+    in16 = x.dtype in (torch.float16, torch.bfloat16) and (ssa_only or x_neighbors.dtype == x.dtype)
+    xs = _std_layout(x if in16 else x.float())
     sources = [(xs, 0, K + 1, 0)]
     nbs = None
     if K > 0:
-        nbs = _std_layout(x_neighbors.float())
+        nbs = _std_layout(x_neighbors if in16 else x_neighbors.float())
         sources.append((nbs[:, 1:], 1, K + 1, 1))
     # the residual of the output projection is read straight from these channel-major tensors by the fused
     # projection/LayerNorm kernel (slot s = b*(K+1)+j: j = 0 the query, j >= 1 neighbour j)
     res_cm = None
     # (TMA needs 16-byte aligned rows: point counts that are not multiples of 4 take the unfused path)
-    tma_ok = xs.shape[2] % 4 == 0 and xs.data_ptr() % 16 == 0 and (nbs is None or nbs.data_ptr() % 16 == 0)
+    tma_ok = (not in16) and xs.shape[2] % 4 == 0 and xs.data_ptr() % 16 == 0 and (nbs is None or nbs.data_ptr() % 16 == 0)
     if tma_ok and (K == 0 or nbs.shape[3] == xs.shape[2]):
         sel = tuple(0 if j == 0 else 1 for b in range(B) for j in range(K + 1))
         off = tuple(b * xs.stride(0) if j == 0 else b * nbs.stride(0) + j * nbs.stride(1)

@@ -282,6 +282,14 @@ int csn_pack_rows(const float* src, void* dst16, float* dst32, int64_t ch_stride
                   int64_t dst_s1, int32_t n_points, int32_t chunk, int32_t chunk_pad, int32_t rows_pad,
                   int32_t dtype, float* amax, float* chunk_sum, void* stream);
 
+/* The same packing from a 16-bit channel-major source (src_dtype = CSN_F16 / CSN_BF16; strides in elements): for
+ * callers that keep their feature collection as a 16-bit pinned host cache, which halves the host-to-device bytes
+ * of a step (MID-FC/features_data_loader.py:124-140 reads fp32 .npy files per step). */
+int csn_pack_rows_src16(const void* src, int32_t src_dtype, void* dst16, float* dst32, int64_t ch_stride, int32_t n0,
+                        int64_t src_s0, int32_t n1, int64_t src_s1, int64_t dst_slot0, int64_t dst_s0, int64_t dst_s1,
+                        int32_t n_points, int32_t chunk, int32_t chunk_pad, int32_t rows_pad, int32_t dtype,
+                        float* amax, float* chunk_sum, void* stream);
+
 /* P = softmax over the first cols_valid columns of each fp32 row (F.softmax(dim=-1),
  * csa_models.py:141), 16-bit, zero in pad columns and in pad rows (row % group_rows >= rows_valid). */
 int csn_softmax_fwd(const float* S, void* P, int64_t rows, int32_t cols_pad, int32_t cols_valid,

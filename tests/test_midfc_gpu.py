@@ -339,3 +339,31 @@ def test_config5_point_n5000_iters10():
     G.compare_sampled(g, "y", y, 1e-3)
     for pname, prm in m.named_parameters():
         G.compare_sampled(g, "grad." + pname, prm.grad, 1e-3, what=pname)
+
+
+@pytest.mark.parametrize("dt16", [torch.float16, torch.bfloat16])
+def test_sixteen_bit_inputs_match_the_same_values_in_fp32(dt16):
+    """A caller-side 16-bit feature cache (csn_pack_rows_src16: half the host-to-device bytes of a step): the loss
+    and the parameter gradients must equal those of the fp32 path run on the SAME (16-bit representable) values."""
+    from csn_b200 import midfc
+    g = G.load("midfc_csa_cfg1")
+    seed, h, K, B, C = (int(g[k]) for k in ("seed", "n_heads", "K", "batch", "num_classes"))
+    m = midfc.get_model("csa", C, h, K).cuda().eval()
+    m.load_state_dict(synth.midfc_state(seed, h, C))
+    x, nb = synth.csa_batch(seed + 1, B, K)
+    label = _labels(seed + 2, B, x.shape[2], C).cuda()
+    x16, nb16 = x.cuda().to(dt16), nb.cuda().to(dt16)
+
+    def run(xi, nbi):
+        for p_ in m.parameters():
+            p_.grad = None
+        loss = m.forward_loss(xi, "test", nbi, label)
+        loss.backward()
+        return loss.item(), {n: p_.grad.clone() for n, p_ in m.named_parameters() if p_.grad is not None}
+
+    l16, g16 = run(x16, nb16)
+    l32, g32 = run(x16.float(), nb16.float())
+    assert abs(l16 - l32) < 2e-6 * max(1.0, abs(l32))
+    assert g16.keys() == g32.keys() and len(g16) >= 8
+    for n in g16:
+        assert G.rel_err(g16[n], g32[n]) < 1e-4, n
