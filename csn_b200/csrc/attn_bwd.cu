@@ -775,11 +775,7 @@ static int launch_ds_wide_d(const CUtensorMap& tmQ, const CUtensorMap& tmDO, con
                           const CUtensorMap& tmDS, const AttnBwdArgs& a, cudaStream_t stream) {
   auto kern = attn_bwd_ds_wide_kernel<CL, DBG, DROP>;
   using WideCfg = WideCfgT<DBG>;
-  static bool configured = false;
-  if (!configured) {
-    CSN_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, WideCfg::SMEM_BYTES));
-    configured = true;
-  }
+  CSN_SET_MAX_SMEM(kern, WideCfg::SMEM_BYTES);
   const int n_work = a.n_items / CL;
   const int workers = num_sms() / CL;
   const int grid = (n_work < workers ? n_work : workers) * CL;
@@ -847,11 +843,7 @@ static int launch_dq_d(const CUtensorMap& tmQ, const CUtensorMap& tmDO, const CU
                      const CUtensorMap& tmDS, const CUtensorMap& tmDQ, const AttnBwdArgs& a, cudaStream_t stream) {
   using Cfg = BwdCfg<DH>;
   auto kern = attn_bwd_dq_kernel<DH, CL, WITH_DQ, DROP>;
-  static bool configured = false;
-  if (!configured) {
-    CSN_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-    configured = true;
-  }
+  CSN_SET_MAX_SMEM(kern, Cfg::SMEM_BYTES);
   const int n_work = a.n_items / CL;
   const int workers = num_sms() / CL;
   const int grid = (n_work < workers ? n_work : workers) * CL;

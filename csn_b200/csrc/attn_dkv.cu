@@ -710,11 +710,7 @@ template <bool DROP>
 static int launch_dq64_d(const CUtensorMap& tmQ, const CUtensorMap& tmDO, const CUtensorMap& tmK, const CUtensorMap& tmV,
                          const CUtensorMap& tmDQ, const DkvArgs& a, cudaStream_t stream) {
   auto kern = attn_bwd_dq64_kernel<DROP>;
-  static bool configured = false;
-  if (!configured) {
-    CSN_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Dq64Cfg::SMEM_BYTES));
-    configured = true;
-  }
+  CSN_SET_MAX_SMEM(kern, Dq64Cfg::SMEM_BYTES);
   const int grid = a.n_items < num_sms() ? a.n_items : num_sms();
   kern<<<grid, Dq64Cfg::THREADS, Dq64Cfg::SMEM_BYTES, stream>>>(tmQ, tmDO, tmK, tmV, tmDQ, a);
   CSN_LAUNCH_OK("attn_bwd_dq64_kernel");
@@ -757,11 +753,7 @@ template <bool DROP>
 static int launch_dkv(const CUtensorMap& tmK, const CUtensorMap& tmV, const CUtensorMap& tmQ, const CUtensorMap& tmDO,
                       const CUtensorMap& tmDK, const CUtensorMap& tmDV, const DkvArgs& a, cudaStream_t stream) {
   auto kern = attn_bwd_dkv_kernel<DROP>;
-  static bool configured = false;
-  if (!configured) {
-    CSN_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, DkvCfg::SMEM_BYTES));
-    configured = true;
-  }
+  CSN_SET_MAX_SMEM(kern, DkvCfg::SMEM_BYTES);
   const int grid = a.n_items < num_sms() ? a.n_items : num_sms();
   kern<<<grid, DkvCfg::THREADS, DkvCfg::SMEM_BYTES, stream>>>(tmK, tmV, tmQ, tmDO, tmDK, tmDV, a);
   CSN_LAUNCH_OK("attn_bwd_dkv_kernel");

@@ -715,11 +715,7 @@ static int launch_attn_fwd_d(const CUtensorMap& tmQ, const CUtensorMap& tmK, con
                            const CUtensorMap& tmO, const CUtensorMap& tmOlo, const AttnFwdArgs& a, cudaStream_t stream) {
   using Cfg = AttnCfg<DH>;
   auto kern = attn_fwd_kernel<DH, MODE, CL, DROP>;
-  static bool configured = false;
-  if (!configured) {
-    CSN_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-    configured = true;
-  }
+  CSN_SET_MAX_SMEM(kern, Cfg::SMEM_BYTES);
   const int n_work = a.n_items / CL;
   const int workers = num_sms() / CL;
   const int grid = (n_work < workers ? n_work : workers) * CL;

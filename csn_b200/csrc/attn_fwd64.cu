@@ -384,11 +384,7 @@ template <bool DROP>
 static int launch_fwd64_d(const CUtensorMap& tmQ, const CUtensorMap& tmK, const CUtensorMap& tmV, const CUtensorMap& tmO,
                           const CUtensorMap& tmOlo, const AttnFwdArgs& a, cudaStream_t stream) {
   auto kern = attn_fwd64_kernel<DROP>;
-  static bool configured = false;
-  if (!configured) {
-    CSN_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Fwd64Cfg::SMEM_BYTES));
-    configured = true;
-  }
+  CSN_SET_MAX_SMEM(kern, Fwd64Cfg::SMEM_BYTES);
   const int grid = a.n_items < num_sms() ? a.n_items : num_sms();
   kern<<<grid, Fwd64Cfg::THREADS, Fwd64Cfg::SMEM_BYTES, stream>>>(tmQ, tmK, tmV, tmO, tmOlo, a);
   CSN_LAUNCH_OK("attn_fwd64_kernel");

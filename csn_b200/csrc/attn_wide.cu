@@ -494,11 +494,7 @@ template <int MODE, int CL, bool DROP>
 static int launch_wide_d(const CUtensorMap& tmQ, const CUtensorMap& tmK, const CUtensorMap& tmV, const CUtensorMap& tmO,
                        const CUtensorMap& tmOlo, const AttnFwdArgs& a, cudaStream_t stream) {
   auto kern = attn_wide_kernel<MODE, CL, DROP>;
-  static bool configured = false;
-  if (!configured) {
-    CSN_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, WideAttnCfg::SMEM_BYTES));
-    configured = true;
-  }
+  CSN_SET_MAX_SMEM(kern, WideAttnCfg::SMEM_BYTES);
   const int n_work = a.n_items / CL;
   const int workers = num_sms() / CL;
   const int grid = (n_work < workers ? n_work : workers) * CL;

@@ -705,11 +705,7 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUt
                        const CUtensorMap* tmR1 = nullptr) {
   using Cfg = GemmCfg<BN>;
   auto kern = gemm_kernel<BN, A_MN, B_MN, CL, LN, DL, CB, DROP, DUAL>;
-  static bool configured = false;
-  if (!configured) {
-    CSN_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-    configured = true;
-  }
+  CSN_SET_MAX_SMEM(kern, Cfg::SMEM_BYTES);
   const long long workers = num_sms() / CL;
   const long long grid = (args.total_tiles < workers ? args.total_tiles : workers) * CL;
   cudaLaunchConfig_t cfg;

@@ -210,11 +210,7 @@ extern "C" int csn_gemm_pair(const void* A, const void* B, void* D, int32_t M, i
   a.alpha = alpha;
   a.idesc = umma_idesc_f16(dtype == CSN_F16 ? 0u : 1u, 0, 0, PBN, 256);
   a.out_dtype = out_dtype;
-  static bool configured = false;
-  if (!configured) {
-    CSN_CUDA_OK(cudaFuncSetAttribute(gemm_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PSMEM_BYTES));
-    configured = true;
-  }
+  CSN_SET_MAX_SMEM(gemm_pair_kernel, PSMEM_BYTES);
   const long long total = (long long)a.tiles_m2 * a.tiles_n;
   const long long pairs = num_sms() / 2;
   const long long grid = (total < pairs ? total : pairs) * 2;

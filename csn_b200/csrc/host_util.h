@@ -43,6 +43,18 @@ int make_tmap_2d_any(CUtensorMap* tm, const void* ptr, int dtype, int64_t inner,
     }                                                                                       \
   } while (0)
 
+// cudaFuncSetAttribute applies to the CURRENT device: remember per (call site, device), not per process
+#define CSN_SET_MAX_SMEM(kern, bytes)                                                                      \
+  do {                                                                                                     \
+    static bool cfg__[64] = {false};                                                                       \
+    int dev__ = 0;                                                                                         \
+    if (cudaGetDevice(&dev__) != cudaSuccess) dev__ = -1;                                                  \
+    if (dev__ < 0 || dev__ >= 64 || !cfg__[dev__]) {                                                       \
+      CSN_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes))); \
+      if (dev__ >= 0 && dev__ < 64) cfg__[dev__] = true;                                                   \
+    }                                                                                                      \
+  } while (0)
+
 // Call after every kernel launch.
 #define CSN_LAUNCH_OK(name)                                                             \
   do {                                                                                  \

@@ -653,11 +653,7 @@ int csn_knn_scores(const void* feat_q, int64_t rows_q, const void* feat_c, int64
   a.partial = partial;
   a.n_items = n_items;
   a.idesc = umma_idesc_f16(dtype == CSN_F16 ? 0u : 1u, 0, 0, KNN_BN);
-  static bool configured = false;
-  if (!configured) {
-    CSN_CUDA_OK(cudaFuncSetAttribute(knn_score_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, KNN_SMEM));
-    configured = true;
-  }
+  CSN_SET_MAX_SMEM(knn_score_kernel, KNN_SMEM);
   const int grid = n_items < num_sms() ? n_items : num_sms();
   knn_score_kernel<<<grid, KNN_THREADS, KNN_SMEM, (cudaStream_t)stream>>>(tmQ, tmC, a);
   CSN_LAUNCH_OK("knn_score_kernel");
@@ -699,11 +695,7 @@ int csn_knn_scores_exact(const void* q_hi, const void* q_lo, int64_t rows_q, con
   a.partial = partial;
   a.n_items = n_items;
   a.idesc = umma_idesc_f16(0u, 0, 0, KNX_BN);
-  static bool configured = false;
-  if (!configured) {
-    CSN_CUDA_OK(cudaFuncSetAttribute(knn_score_exact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, KNX_SMEM));
-    configured = true;
-  }
+  CSN_SET_MAX_SMEM(knn_score_exact_kernel, KNX_SMEM);
   const int grid = n_items < num_sms() ? n_items : num_sms();
   knn_score_exact_kernel<<<grid, KNN_THREADS, KNX_SMEM, (cudaStream_t)stream>>>(tmQh, tmQl, tmCh, tmCl, a);
   CSN_LAUNCH_OK("knn_score_exact_kernel");
