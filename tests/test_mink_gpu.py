@@ -43,7 +43,7 @@ def test_ragged_self_attention_against_oracle():
     h = 4
     m = _mha(7, h)
     w = synth.mink_state(7, h)
-    for L in (37, 129, 1000):
+    for L in (1, 5, 37, 64, 65, 129, 1000):
         x = torch.relu(torch.randn(1, L, 256, generator=synth.gen(L)))
         want, _ = O.mha_mink(x, x, x, w, h)
         got, attn = m(x.cuda(), x.cuda(), x.cuda())
@@ -229,8 +229,8 @@ def test_fused_dkv_backward_matches_ds_path(precision, tol):
     m = mink.MultiHeadAttention(h, 256, 64, 64, precision=precision).cuda().eval()
     m.load_state_dict({k[len("MHA."):]: v for k, v in synth.mink_state(11, h).items() if k.startswith("MHA.")})
     gen = synth.gen(12)
-    lens = [130, 517, 64, 300]
-    pairs = [(0, 0), (1, 1), (2, 2), (3, 3), (0, 1), (1, 3), (2, 0)]
+    lens = [130, 517, 64, 300, 1, 33]          # incl. shapes shorter than one column quarter of a tile
+    pairs = [(0, 0), (1, 1), (2, 2), (3, 3), (4, 4), (5, 5), (0, 1), (1, 3), (2, 0), (4, 1), (1, 5), (5, 4)]
     xs = [torch.relu(torch.randn(n, 256, generator=gen)).cuda() for n in lens]
     gy = [torch.randn(lens[q], 256, generator=gen).cuda() for q, _ in pairs]
 
