@@ -261,8 +261,7 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_consta
         // per-query statistics of this tile (lse in log2 units, delta pre-scaled): bulk-copied by the producer warp
         // into a ring; no block-wide barrier anywhere in this loop (it cost 23 % of the warps' time: ncu)
         mbar_wait(stat_full(ss), stat_ph);
-        const float* st_l = stat + ss * 256;
-        const float* st_d = st_l + 128;
+        const uint32_t st_l = sStat + ss * 1024, st_d = st_l + 512;   // shared-window addresses (ld.shared, not generic loads)
         mbar_wait(sdp_full, sdp_ph);
         sdp_ph ^= 1;
         tc_fence_after();
@@ -288,8 +287,8 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_consta
             uint32_t pp[CW / 2], pd[CW / 2];
 #pragma unroll
             for (int i = 0; i < CW; i += 4) {
-              const float4 l4 = *reinterpret_cast<const float4*>(st_l + c + i);
-              const float4 d4 = *reinterpret_cast<const float4*>(st_d + c + i);
+              const float4 l4 = lds_f4(st_l + (c + i) * 4);
+              const float4 d4 = lds_f4(st_d + (c + i) * 4);
               const float ls[4] = {l4.x, l4.y, l4.z, l4.w}, ds_[4] = {d4.x, d4.y, d4.z, d4.w};
               float pv[4], dsv[4];
 #pragma unroll

@@ -302,11 +302,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     constexpr float LOG2E = 1.4426950408889634f;
     // 64 columns (two tcgen05.ld in flight) -> 16-bit pairs -> the swizzled A-operand tile of the P V MMA
     auto store_p64 = [&](int c, const uint32_t (&pk)[32]) {
-      uint8_t* rowp = sP_ptr + (c >> 6) * 16384 + r * 128;
+      const uint32_t rowp = sP + (c >> 6) * 16384 + r * 128;
 #pragma unroll
       for (int t = 0; t < 8; ++t) {
         const int ch = t ^ (r & 7);
-        *reinterpret_cast<uint4*>(rowp + ch * 16) = make_uint4(pk[4 * t], pk[4 * t + 1], pk[4 * t + 2], pk[4 * t + 3]);
+        sts_v4(rowp + ch * 16, pk[4 * t], pk[4 * t + 1], pk[4 * t + 2], pk[4 * t + 3]);
       }
     };
     auto pack_pair = [&](float a, float b) -> uint32_t {

@@ -368,7 +368,7 @@ attn_wide_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
           const float moff = m_used * p.scale_log2;
           const bool rvalid = (MODE == 0) ? true : (r < it.q_valid);
           const uint32_t rk0 = drop_row_key(p.drop_seed, (uint32_t)(it.lse_off + r));   // MODE 0: the thread's query row
-          const float4* lse4 = reinterpret_cast<const float4*>(xch + half * 128);
+          const uint32_t lse4 = sX + half * 512;   // shared-window address of this warp's 128 per-column statistics
           uint32_t va[32], vb[32];
           // operand type and "no padding among this warp's rows and columns" are compile-time variants of the
           // conversion (per-element bounds predicates and both 16-bit packings cost ~10 % of the stage otherwise)
@@ -382,7 +382,7 @@ attn_wide_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
 #pragma unroll
             for (int k = 0; k < 32; k += 4) {
               float4 off = make_float4(moff, moff, moff, moff);
-              if (MODE == 1) off = lse4[(c * 32 + k) >> 2];
+              if (MODE == 1) off = lds_f4(lse4 + (c * 32 + k) * 4);
               const int c0 = c * 32 + k;
               float p0 = fast_exp2(__uint_as_float(v[k]) * p.scale_log2 - off.x);
               float p1 = fast_exp2(__uint_as_float(v[k + 1]) * p.scale_log2 - off.y);
@@ -465,11 +465,11 @@ attn_wide_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         l += lsum;
 #pragma unroll
         for (int s2 = 0; s2 < 2; ++s2) {   // this warp's two 64-column slices of the P tile
-          uint8_t* rowp = sP_ptr + (half * 2 + s2) * 16384 + r * 128;
+          const uint32_t rowp = sP + (half * 2 + s2) * 16384 + r * 128;
 #pragma unroll
           for (int t = 0; t < 8; ++t) {
             const int ch = t ^ (r & 7);
-            *reinterpret_cast<uint4*>(rowp + ch * 16) = make_uint4(pk[s2 * 32 + 4 * t], pk[s2 * 32 + 4 * t + 1], pk[s2 * 32 + 4 * t + 2], pk[s2 * 32 + 4 * t + 3]);
+            sts_v4(rowp + ch * 16, pk[s2 * 32 + 4 * t], pk[s2 * 32 + 4 * t + 1], pk[s2 * 32 + 4 * t + 2], pk[s2 * 32 + 4 * t + 3]);
           }
         }
         tc_fence_before();
