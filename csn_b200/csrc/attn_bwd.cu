@@ -343,12 +343,12 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
               asm volatile("bar.sync 1, %0;" ::"n"(Cfg::EW_THREADS) : "memory");
               waited = true;
             }
-            uint8_t* rowp = sDS_ptr + (c >> 6) * 16384 + r * 128;
+            const uint32_t rowp = sDS + (c >> 6) * 16384 + r * 128;
             const int chunk0 = (c & 63) >> 3;
 #pragma unroll
             for (int t = 0; t < 4; ++t) {
               const int ch = (chunk0 + t) ^ (r & 7);
-              *reinterpret_cast<uint4*>(rowp + ch * 16) = make_uint4(pk[4 * t], pk[4 * t + 1], pk[4 * t + 2], pk[4 * t + 3]);
+              sts_v4(rowp + ch * 16, pk[4 * t], pk[4 * t + 1], pk[4 * t + 2], pk[4 * t + 3]);
             }
           }
         };
