@@ -42,7 +42,10 @@ struct AttnCfg {
   static constexpr int BAR_BYTES = 256;
   // softmax warps: one per TMEM lane quadrant, or (d_head 64, where the exponentials and not the MMAs bound the
   // kernel: 1118 us with, 493 us without them on the MinkowskiNet batch) two, the second taking key columns 64-127
-  static constexpr int SM_WARPS = (DH == 64) ? 8 : 4;
+#ifndef CSN_FWD256_SM_WARPS
+#define CSN_FWD256_SM_WARPS 4   // 8 (column halves, row statistics exchanged through SMEM) was measured: 402 vs 389-400 us, no gain
+#endif
+  static constexpr int SM_WARPS = (DH == 64) ? 8 : CSN_FWD256_SM_WARPS;
   static constexpr int SM_THREADS = 32 * SM_WARPS;
   static constexpr int THREADS = 128 + SM_THREADS;
   static constexpr int COLS = 128 / (SM_WARPS / 4);          // key columns of a tile per softmax thread
