@@ -215,6 +215,11 @@ def attn_items(groups, geom: Geometry, n_head: int, d: int, device, kind: str = 
                             rows.append((qs * NP + c * CP + t_ * 128, valid, ks * NP + c * CP, kv_len,
                                          j * NP + c * CP + t_ * 128, h * d, stat + t_ * 128,
                                          ((j * NC + c) * n_head + h) * CP + t_ * 128, 0, 1, 0, 0))
+    if d != 256 and any(g.q_lens or g.kv_lens for g in groups) and os.environ.get("CSN_ITEM_SORT", "1") == "1":
+        # ragged batch: items cost ~ their streamed length (column 3 of every item layout).  The persistent CTAs take
+        # items round-robin, so handing them out longest-first keeps the per-CTA sums within ~1.5 % of each other
+        # (6 % in table order on the config-4 batch).  (d_head 256 pairs items 2m / 2m+1 into clusters: order kept.)
+        rows.sort(key=lambda r: -r[3])
     t = torch.tensor(rows, dtype=torch.int32).to(device)
     while len(_ITEM_CACHE) >= _ITEM_CACHE_MAX:
         _ITEM_CACHE.popitem(last=False)
