@@ -754,17 +754,21 @@ namespace csn {
 // Concatenated rows -> padded slots: out[s][r] = x[offsets[s] + r] for r < len(s), 0 for len(s) <= r < n_pad
 // (fp32 copy and / or 16-bit copy).  One warp per row, 256 columns.
 __global__ void __launch_bounds__(256) ragged_pad_kernel(const float* __restrict__ x, const long long* __restrict__ offsets,
-                                                         int n_pad, float* __restrict__ out32, void* __restrict__ out16, int dtype) {
+                                                         int n_pad, float* __restrict__ out32, void* __restrict__ out16, int dtype,
+                                                         float* __restrict__ amax) {
   const int s = blockIdx.y;
   const long long o0 = offsets[s];
   const int len = (int)(offsets[s + 1] - o0);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float amx = 0.f;
   for (int r = blockIdx.x * 8 + warp; r < n_pad; r += gridDim.x * 8) {
     float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
     if (r < len) {
       const float4* src = reinterpret_cast<const float4*>(x + (o0 + r) * 256) + lane * 2;
       a = __ldg(src);
       b = __ldg(src + 1);
+      amx = fmaxf(amx, fmaxf(fmaxf(fmaxf(fabsf(a.x), fabsf(a.y)), fmaxf(fabsf(a.z), fabsf(a.w))),
+                             fmaxf(fmaxf(fabsf(b.x), fabsf(b.y)), fmaxf(fabsf(b.z), fabsf(b.w)))));
     }
     const long long row = (long long)s * n_pad + r;
     if (out32) {
@@ -783,6 +787,10 @@ __global__ void __launch_bounds__(256) ragged_pad_kernel(const float* __restrict
       }
       reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(out16) + row * 256)[lane] = w;
     }
+  }
+  if (amax) {   // max |x| over everything copied (non-negative floats order like their bit patterns)
+    amx = warp_max(amx);
+    if (lane == 0 && amx > 0.f) atomicMax(reinterpret_cast<int*>(amax), __float_as_int(amx));
   }
 }
 }  // namespace csn
@@ -819,30 +827,31 @@ __global__ void __launch_bounds__(256) block_add_kernel(const float* __restrict_
 }  // namespace csn
 
 namespace csn {
-// out[s][c] = mean of x[offsets[s] .. offsets[s+1])[c]: CTA = (segment, 32-column group), 8 row lanes per column.
-__global__ void __launch_bounds__(256) segment_mean_kernel(const float* __restrict__ x, const long long* __restrict__ offsets,
-                                                           int n_cols, float* __restrict__ out) {
-  __shared__ float red[8][33];
+// out[s][c] = mean of x[offsets[s] .. offsets[s+1])[c]: CTA = (segment, 32-column group), 32 row lanes per column,
+// four loads in flight per thread (a handful of long segments must keep the memory system busy on their own).
+__global__ void __launch_bounds__(1024) segment_mean_kernel(const float* __restrict__ x, const long long* __restrict__ offsets,
+                                                            int n_cols, float* __restrict__ out) {
+  __shared__ float red[32][33];
   const int seg = blockIdx.x, c = blockIdx.y * 32 + (threadIdx.x & 31), rl = threadIdx.x >> 5;
   const long long r0 = offsets[seg], r1 = offsets[seg + 1];
   float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
   if (c < n_cols) {
     const float* p = x + c;
     long long r = r0 + rl;
-    for (; r + 24 < r1; r += 32) {
+    for (; r + 96 < r1; r += 128) {
       a0 += __ldg(p + r * n_cols);
-      a1 += __ldg(p + (r + 8) * n_cols);
-      a2 += __ldg(p + (r + 16) * n_cols);
-      a3 += __ldg(p + (r + 24) * n_cols);
+      a1 += __ldg(p + (r + 32) * n_cols);
+      a2 += __ldg(p + (r + 64) * n_cols);
+      a3 += __ldg(p + (r + 96) * n_cols);
     }
-    for (; r < r1; r += 8) a0 += __ldg(p + r * n_cols);
+    for (; r < r1; r += 32) a0 += __ldg(p + r * n_cols);
   }
   red[rl][threadIdx.x & 31] = (a0 + a1) + (a2 + a3);
   __syncthreads();
   if (rl == 0 && c < n_cols) {
     float t = 0.f;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) t += red[i][threadIdx.x];
+    for (int i = 0; i < 32; ++i) t += red[i][threadIdx.x];
     out[(long long)seg * n_cols + c] = r1 > r0 ? t / (float)(r1 - r0) : 0.f;
   }
 }
@@ -998,14 +1007,14 @@ int csn_segment_mean(const float* x, const int64_t* offsets, int32_t n_seg, int3
   CSN_CHECK_ARG(x && offsets && out, "csn_segment_mean: null pointer");
   CSN_CHECK_ARG(n_cols > 0 && n_seg >= 0, "csn_segment_mean: bad shape");
   if (n_seg == 0) return 0;
-  segment_mean_kernel<<<dim3(n_seg, (n_cols + 31) / 32), 256, 0, (cudaStream_t)stream>>>(
+  segment_mean_kernel<<<dim3(n_seg, (n_cols + 31) / 32), 1024, 0, (cudaStream_t)stream>>>(
       x, reinterpret_cast<const long long*>(offsets), n_cols, out);
   CSN_LAUNCH_OK("segment_mean_kernel");
   return 0;
 }
 
 int csn_ragged_pad(const float* x, const int64_t* offsets, int32_t n_slots, int32_t n_pad, float* out32, void* out16,
-                   int32_t dtype, void* stream) {
+                   int32_t dtype, float* amax, void* stream) {
   using namespace csn;
   clear_error();
   CSN_CHECK_ARG(x && offsets && (out32 || out16), "csn_ragged_pad: null pointer");
@@ -1015,7 +1024,7 @@ int csn_ragged_pad(const float* x, const int64_t* offsets, int32_t n_slots, int3
   const int cap = (8 * num_sms() + n_slots - 1) / n_slots;
   if (gx > cap) gx = cap;
   ragged_pad_kernel<<<dim3((unsigned)gx, (unsigned)n_slots), 256, 0, (cudaStream_t)stream>>>(
-      x, reinterpret_cast<const long long*>(offsets), n_pad, out32, out16, dtype);
+      x, reinterpret_cast<const long long*>(offsets), n_pad, out32, out16, dtype, amax);
   CSN_LAUNCH_OK("ragged_pad_kernel");
   return 0;
 }

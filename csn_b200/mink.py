@@ -144,7 +144,7 @@ class _MhaBlocksFn(torch.autograd.Function):
         Xh = torch.empty(S * n_pad, 256, dtype=dt, device=dev)
         x32 = x_cat.float().contiguous()
         L.check(L.lib().csn_ragged_pad(x32.data_ptr(), offs_t.data_ptr(), S, n_pad, Xf.data_ptr(), Xh.data_ptr(),
-                                       L.dtype_code(dt), L.stream_ptr()), "csn_ragged_pad")
+                                       L.dtype_code(dt), None, L.stream_ptr()), "csn_ragged_pad")
         geom = E.Geometry(chunk=n_pad, n_chunks=1, chunk_pad=n_pad, kv_chunk=n_pad)
         # runs of pairs whose (query, key) slots advance with constant strides become one group each, so that the
         # batched GEMMs of the backward pass stay batched (SSA of S shapes: one run; K*B cross blocks: K runs)
@@ -180,10 +180,11 @@ class _MhaBlocksFn(torch.autograd.Function):
         S, P, n_pad, slot_rows, out_rows, poffs_t = ctx.meta
         dY = torch.empty(P * n_pad, 256, dtype=torch.float32, device=dout.device)
         d32 = dout.float().contiguous()
-        L.check(L.lib().csn_ragged_pad(d32.data_ptr(), poffs_t.data_ptr(), P, n_pad, dY.data_ptr(), None, 0, L.stream_ptr()),
-                "csn_ragged_pad")
+        amax = torch.zeros(1, dtype=torch.float32, device=dout.device)   # max |dY|: the loss scale of the backward pass
+        L.check(L.lib().csn_ragged_pad(d32.data_ptr(), poffs_t.data_ptr(), P, n_pad, dY.data_ptr(), None, 0, amax.data_ptr(),
+                                       L.stream_ptr()), "csn_ragged_pad")
         need_dx = ctx.needs_input_grad[0]
-        g = E.attention_backward(a, dY, need_dx)
+        g = E.attention_backward(a, dY, need_dx, amax=amax)
         dx = g["dX"][slot_rows] if need_dx else None
         return (dx, g["dWq"], g["dWk"], g["dWv"], g["dWo"], g["dgamma"], g["dbeta"], None, None, None, None, None, None)
 

@@ -384,9 +384,10 @@ int csn_grad_unscale(float* x, int64_t n, const float* amax, void* stream);
 
 /* Concatenated rows -> zero-padded slots of n_pad rows, 256 columns: out[s][r] = x[offsets[s] + r] for
  * r < offsets[s+1] - offsets[s], 0 beyond; out32 (fp32) and / or out16 (dtype f16 / bf16).  The layout change in
- * front of the ragged attention batch (the reference calls MultiHeadAttention once per shape, hrnet.py:370-417). */
+ * front of the ragged attention batch (the reference calls MultiHeadAttention once per shape, hrnet.py:370-417).
+ * amax (optional, zero-initialised): receives max |x| (the loss scale of the backward pass). */
 int csn_ragged_pad(const float* x, const int64_t* offsets, int32_t n_slots, int32_t n_pad, float* out32, void* out16,
-                   int32_t dtype, void* stream);
+                   int32_t dtype, float* amax, void* stream);
 
 /* dst[s] = (dst[s] + sum over j < n_src with dst_block[j] == s of src[j]) * u, blocks of block_elems fp32 values
  * (at most 256 sources per destination); u = csn_grad_unscale's factor when amax != NULL, else 1.  The residual path

@@ -279,8 +279,10 @@ def test_ragged_pad_matches_index_put():
     for dt in (torch.float16, torch.bfloat16):
         o32 = torch.full((len(lens) * n_pad, 256), float("nan"), device="cuda")
         o16 = torch.full((len(lens) * n_pad, 256), float("nan"), device="cuda", dtype=dt)
+        amax = torch.zeros(1, device="cuda")
         L.check(L.lib().csn_ragged_pad(x.data_ptr(), offs.data_ptr(), len(lens), n_pad, o32.data_ptr(), o16.data_ptr(),
-                                       L.dtype_code(dt), L.stream_ptr()), "ragged_pad")
+                                       L.dtype_code(dt), amax.data_ptr(), L.stream_ptr()), "ragged_pad")
+        assert float(amax) == float(x.abs().max())
         want = torch.zeros(len(lens), n_pad, 256, device="cuda")
         o = 0
         for s, n in enumerate(lens):
