@@ -671,12 +671,20 @@ def attention_backward(ctx: AttnContext, dY: torch.Tensor, need_dx: bool, amax: 
         Wq16, Wk16, Wv16 = ctx.Wqkv16[:HD], ctx.Wqkv16[HD:2 * HD], ctx.Wqkv16[2 * HD:]
         for g in ctx.groups:
             nb = (g.n_in, g.n_out, 1, 1)
-            for (dproj, W16, s0, si, so, dst) in ((dQv, Wq16, g.q0, g.q_si, g.q_so, dX), (dKv, Wk16, g.k0, g.k_si, g.k_so, dX),
-                                                  (dVv, Wv16, g.v0, g.v_si, g.v_so, dXv)):
+            q_sl, k_sl, v_sl = (g.q0, g.q_si, g.q_so), (g.k0, g.k_si, g.k_so), (g.v0, g.v_si, g.v_so)
+            # roles that land in the same slots are ONE contraction over their concatenated columns of dQKV / rows of
+            # Wqkv (self blocks: K = 3 HD; cross blocks: dQ alone, dK|dV together) instead of one launch per role
+            if not split_v and q_sl == k_sl == v_sl:
+                roles = ((dQKV, ctx.Wqkv16, 3 * HD, q_sl, dX),)
+            elif not split_v and k_sl == v_sl:
+                roles = ((dQv, Wq16, HD, q_sl, dX), (dQKV[:, HD:], ctx.Wqkv16[HD:], 2 * HD, k_sl, dX))
+            else:
+                roles = ((dQv, Wq16, HD, q_sl, dX), (dKv, Wk16, HD, k_sl, dX), (dVv, Wv16, HD, v_sl, dXv))
+            for (dproj, W16, Kdim, (s0, si, so), dst) in roles:
                 A = L.mat(dproj[g.blk0 * NP:], L.MAJOR_K, mn_off=(NP, g.n_in * NP))
                 B = L.mat(W16, L.MAJOR_MN)
                 D = L.out(dst[s0 * NP:], 256, off=(si * NP * 256, so * NP * 256), accumulate=True)
-                L.gemm(A, B, D, NP, 256, HD, nb=nb)
+                L.gemm(A, B, D, NP, 256, Kdim, nb=nb)
         if split_v:
             grads["dXv"] = dXv
         # residual path: dX[q slot] += dZ[block], and the loss scale taken out in the same pass
