@@ -805,8 +805,11 @@ __global__ void __launch_bounds__(256) block_add_kernel(const float* __restrict_
   const int s = blockIdx.y;
   if (threadIdx.x == 0) {
     int n = 0;
-    for (int j = 0; j < n_src && n < 256; ++j)
-      if (dst_block[j] == s) mine[n++] = j;
+    for (int j = 0; j < n_src; ++j)
+      if (dst_block[j] == s) {
+        if (n == 256) asm volatile("trap;");   // more sources per destination than the table holds: fail loudly
+        mine[n++] = j;
+      }
     n_mine = n;
   }
   __syncthreads();
