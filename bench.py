@@ -294,10 +294,14 @@ def run_ours(args) -> None:
         graphs = [GraphedStep(local_step, *b) for b in batches]
         launch_mode = "CUDA graph replay of the local step (csn_b200.graphs.GraphedStep)"
 
+    step_no = [0]
+
     def train_step(k):
         if graphs is None:
             return eager_step(*batches[k])
-        loss = graphs[k].replay()
+        step_no[0] += 1
+        # train mode: the seeds are frozen in the captured graph, the device-resident epoch makes every replay draw new masks
+        loss = graphs[k].replay(epoch=step_no[0] if args.train_mode else None)
         exchange()
         return loss
 
@@ -739,7 +743,7 @@ def run_ours(args) -> None:
             "config": {"workload": f"MID-FC CSA training step B={CSA_B} K={CSA_K} h={h} N={N_POINTS} D={D} per GPU (configs[1])",
                        "heads": h, "parallelism": f"dp{world} over query shapes", "l2": "inputs 410 MB/step > L2, two alternating batches",
                        "dropout": "off (model.eval(): the parity-checkable semantics; training-mode dropout is in the kernels "
-                                  "and measured by --train-mode)" if not args.train_mode else "on (model.train(), p = 0.1)",
+                                  "and measured by --train-mode)" if not args.train_mode else "on (model.train(), p = 0.1; fresh masks per replay via csn_set_drop_epoch)",
                        "loss": "module forward + ATen conv / cross-entropy" if args.unfused_loss else
                                "CrossShapeAt.forward_loss (fused head: weighted sum + logit conv + masked CE + IoU counters + backward)",
                        "timed_blocks": n_blocks_timed, "block_ms": [round(b_, 3) for b_ in block_ms],

@@ -207,6 +207,7 @@ _EXTRA_SIGNATURES: dict[str, list] = {
                          C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_uint32, C.c_float, C.c_void_p],
     "csn_block_add": [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p],
     "csn_ragged_pad": [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p],
+    "csn_set_drop_epoch": [C.c_uint32, C.c_void_p],
     "csn_segment_mean": [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p],
     "csn_compat_fanout": [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_void_p,
                           C.c_void_p, C.c_void_p],

@@ -51,6 +51,7 @@ struct AttnBwdArgs {
   // dropout on the probabilities (attn_common.cuh): dP/dP_dropped = mask/(1-p); row id = stat_off + row, column = key
   uint32_t drop_seed, drop_thresh;
   float drop_scale;
+  const uint32_t* drop_epoch;
 };
 
 #ifndef CSN_DQ_EW_WARPS
@@ -287,7 +288,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       const bool valid = r < it.q_valid;
       const float lse_l2 = valid ? p.lse[it.stat_off + r] * LOG2E : 0.f;
       const float dlt_s = valid ? p.delta[it.stat_off + r] * p.scale : 0.f;
-      const uint32_t rk = drop_row_key(p.drop_seed, (uint32_t)(it.stat_off + r));
+      const uint32_t rk = drop_row_key(drop_seed_eff(p.drop_seed, p.drop_epoch), (uint32_t)(it.stat_off + r));
       for (int j = 0; j < nkv; ++j) {
         const int b = WITH_DQ ? 0 : (j & 1);
         mbar_wait(sdp_full(b), sdp_ph[b]);
@@ -609,7 +610,7 @@ attn_bwd_ds_wide_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
       const bool valid = r < it.q_valid;
       const float lse_l2 = valid ? p.lse[it.stat_off + r] * LOG2E : 0.f;
       const float dlt = valid ? p.delta[it.stat_off + r] : 0.f;
-      const uint32_t rk = drop_row_key(p.drop_seed, (uint32_t)(it.stat_off + r));
+      const uint32_t rk = drop_row_key(drop_seed_eff(p.drop_seed, p.drop_epoch), (uint32_t)(it.stat_off + r));
       for (int j = 0; j < nst; ++j) {
         const int key0 = j * 256 + half * 128;          // first key of this warp's 128 columns
         const int nvalid = valid ? it.kv_len - key0 : 0;   // columns [0, nvalid) of the 128 are real keys
@@ -945,6 +946,7 @@ int csn_attn_bwd_dq(const void* Q, const void* dO, const void* K, const void* V,
   a.drop_seed = drop_seed;
   a.drop_thresh = drop_thresh16(drop_p);
   a.drop_scale = drop_scale_of(a.drop_thresh);
+  a.drop_epoch = a.drop_thresh ? drop_epoch_ptr() : nullptr;
   a.prefetch = 0;
   const uint32_t fmt = dtype == CSN_F16 ? 0u : 1u;
   a.idesc_s = umma_idesc_f16(fmt, 0, 0, 128);

@@ -42,6 +42,7 @@ struct AttnFwdArgs {
   // (lse_off + row: unique per block, head and row), column = key index inside the chunk.
   uint32_t drop_seed, drop_thresh;
   float drop_scale;
+  const uint32_t* drop_epoch;   // device word added (x 0x9E3779B9) to drop_seed: graph replays draw fresh masks
 };
 
 // attn_wide.cu: d_head = 256 with [128 x 256] score tiles (mode 0 forward, mode 1 dV)

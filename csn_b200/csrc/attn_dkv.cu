@@ -54,6 +54,7 @@ struct DkvArgs {
   uint32_t idesc_o;   // M=128, N=64, A K-major, B MN-major
   uint32_t drop_seed, drop_thresh;
   float drop_scale;
+  const uint32_t* drop_epoch;
 };
 
 struct DkvCfg {
@@ -295,7 +296,7 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_consta
               for (int u = 0; u < 4; ++u) {
                 float m = 1.f;   // d P_dropped / d P = mask / (1 - p)
                 if (DROP) {      // the forward mask: row id = query, pair = two adjacent keys
-                  const uint32_t hh = drop_pair(drop_row_key(p.drop_seed, (uint32_t)(it.stat_off + j * 128 + c + i + u)),
+                  const uint32_t hh = drop_pair(drop_row_key(drop_seed_eff(p.drop_seed, p.drop_epoch), (uint32_t)(it.stat_off + j * 128 + c + i + u)),
                                                 (uint32_t)(it.key0 + r) >> 1);
                   m = (((it.key0 + r) & 1) ? drop_keep_hi(hh, p.drop_thresh) : drop_keep_lo(hh, p.drop_thresh)) ? p.drop_scale : 0.f;
                 }
@@ -584,7 +585,7 @@ attn_bwd_dq64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       const bool valid = r < it.q_valid;
       const float lse_l2 = valid ? p.lse[it.stat_off + r] * LOG2E : 0.f;
       const float dlt_s = valid ? p.delta[it.stat_off + r] * p.scale : 0.f;
-      const uint32_t rk = drop_row_key(p.drop_seed, (uint32_t)(it.stat_off + r));
+      const uint32_t rk = drop_row_key(drop_seed_eff(p.drop_seed, p.drop_epoch), (uint32_t)(it.stat_off + r));
       for (int j = 0; j < nkv; ++j) {
         const int b = j & 1;
         const int nvalid = min(128, it.kv_len - j * 128);
@@ -736,6 +737,7 @@ int launch_dq64(const CUtensorMap& tmQ, const CUtensorMap& tmDO, const CUtensorM
   a.drop_seed = drop_seed;
   a.drop_thresh = drop_thresh16(drop_p);
   a.drop_scale = drop_scale_of(a.drop_thresh);
+  a.drop_epoch = a.drop_thresh ? drop_epoch_ptr() : nullptr;
   return a.drop_thresh ? launch_dq64_d<true>(tmQ, tmDO, tmK, tmV, tmDQ, a, stream) : launch_dq64_d<false>(tmQ, tmDO, tmK, tmV, tmDQ, a, stream);
 }
 
@@ -805,6 +807,7 @@ extern "C" int csn_attn_bwd_dkv(const void* K, const void* V, const void* Q, con
   a.drop_seed = drop_seed;
   a.drop_thresh = drop_thresh16(drop_p);
   a.drop_scale = drop_scale_of(a.drop_thresh);
+  a.drop_epoch = a.drop_thresh ? drop_epoch_ptr() : nullptr;
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   dkv_stats_scale_kernel<<<(unsigned)((n_stats + 1023) / 1024 < 1184 ? (n_stats + 1023) / 1024 : 1184), 256, 0, s>>>(
       lse, delta, n_stats, a.scale, stat_scratch);

@@ -352,7 +352,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           const bool rvalid = r < nvalid;                       // query row exists
           const float lse_l2 = rvalid ? p.lse[it.lse_off + j * 128 + r] * LOG2E : 0.f;
           const int cvalid = rvalid ? it.q_valid : 0;           // resident key columns that exist
-          const uint32_t rk = drop_row_key(p.drop_seed, (uint32_t)(it.lse_off + j * 128 + r));
+          const uint32_t rk = drop_row_key(drop_seed_eff(p.drop_seed, p.drop_epoch), (uint32_t)(it.lse_off + j * 128 + r));
           auto dv_tile = [&](auto F16C, auto FULLC) {
             constexpr bool F16 = decltype(F16C)::value, FULL = decltype(FULLC)::value;
 #pragma unroll 1
@@ -447,7 +447,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             l *= alpha;
           }
           const float moff = m_used * p.scale_log2;
-          const uint32_t rk = drop_row_key(p.drop_seed, (uint32_t)(it.lse_off + r));
+          const uint32_t rk = drop_row_key(drop_seed_eff(p.drop_seed, p.drop_epoch), (uint32_t)(it.lse_off + r));
           float lsum = 0.f;
           uint32_t pk[32];
           auto exp_regs = [&](auto F16C, auto FULLC) {
@@ -517,7 +517,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
               }
             }
             const float moff = m_used * p.scale_log2;
-            const uint32_t rk = drop_row_key(p.drop_seed, (uint32_t)(it.lse_off + r));
+            const uint32_t rk = drop_row_key(drop_seed_eff(p.drop_seed, p.drop_epoch), (uint32_t)(it.lse_off + r));
             lsum = 0.f;
             float cmax = -INFINITY;
             auto exp_tile = [&](auto F16C, auto FULLC) {
@@ -788,6 +788,7 @@ static int attn_launch_common(int mode, const void* Q, const void* K, const void
   a.drop_seed = drop_seed;
   a.drop_thresh = drop_thresh16(drop_p);
   a.drop_scale = drop_scale_of(a.drop_thresh);
+  a.drop_epoch = a.drop_thresh ? drop_epoch_ptr() : nullptr;
   {
     const char* dbg = getenv("CSN_ATTN_DEBUG");
     a.debug = dbg ? atoi(dbg) : 0;

@@ -254,6 +254,7 @@ struct AddLnArgs {
   float eps;
   int dtype;
   uint32_t drop_seed, drop_thresh; float drop_scale;   // dropout on the fc output (csa_models.py:115), off when thresh == 0
+  const uint32_t* drop_epoch;
 };
 
 // dropout mask of the 8 fc-output values a lane holds for one row (columns lane*4.. and 128 + lane*4..): four hashes
@@ -296,7 +297,7 @@ __global__ void __launch_bounds__(256) add_ln_fwd_kernel(const AddLnArgs p) {
     }
     const float4* r4 = reinterpret_cast<const float4*>(p.R + (rblk * p.block_rows + rin) * DM);
     float4 a = z4[lane], c = z4[32 + lane];
-    if (p.drop_thresh) drop_apply8(p.drop_seed, p.drop_thresh, p.drop_scale, (uint32_t)row, lane, a, c);
+    if (p.drop_thresh) drop_apply8(drop_seed_eff(p.drop_seed, p.drop_epoch), p.drop_thresh, p.drop_scale, (uint32_t)row, lane, a, c);
     const float4 ra = __ldg(r4 + lane), rc = __ldg(r4 + 32 + lane);
     a.x += ra.x; a.y += ra.y; a.z += ra.z; a.w += ra.w;
     c.x += rc.x; c.y += rc.y; c.z += rc.z; c.w += rc.w;
@@ -398,6 +399,7 @@ struct LnBwdArgs {
   // dropout on the fc output: the 16-bit copy (what flows on into fc / the attention output) is masked and scaled,
   // the fp32 dZ (gradient of the residual input) is not
   uint32_t drop_seed, drop_thresh; float drop_scale;
+  const uint32_t* drop_epoch;
 };
 
 // Block = 8 warps x 8 rows = 64 consecutive rows: they lie inside one attention block AND one chunk (64 | group_rows),
@@ -496,7 +498,7 @@ __global__ void __launch_bounds__(256, MINB) ln_bwd_kernel(const LnBwdArgs p) {
     }
     if (DROP) {   // the 16-bit copy flows on into fc / the attention output: masked and scaled; the fp32 dZ is not
       float4 ma = make_float4(o8[0], o8[1], o8[2], o8[3]), mc = make_float4(o8[4], o8[5], o8[6], o8[7]);
-      drop_apply8(p.drop_seed, p.drop_thresh, p.drop_scale, (uint32_t)(wrow + i), lane, ma, mc);
+      drop_apply8(drop_seed_eff(p.drop_seed, p.drop_epoch), p.drop_thresh, p.drop_scale, (uint32_t)(wrow + i), lane, ma, mc);
       o8[0] = ma.x; o8[1] = ma.y; o8[2] = ma.z; o8[3] = ma.w; o8[4] = mc.x; o8[5] = mc.y; o8[6] = mc.z; o8[7] = mc.w;
     }
     dz16[i * 64] = make_uint2(pack2(o8[0], o8[1], p.dtype), pack2(o8[2], o8[3], p.dtype));
@@ -950,7 +952,7 @@ int csn_add_ln_fwd(float* Z, const float* R, const int32_t* res_block, float* Y,
   if (rows == 0) return 0;
   const uint32_t dth = drop_thresh16(drop_p);
   AddLnArgs a{Z, R, res_block, Y, Y16, mean, rstd, gamma, beta, colsum, rows, block_rows, group_rows, rows_valid, eps, dtype,
-              drop_seed, dth, drop_scale_of(dth)};
+              drop_seed, dth, drop_scale_of(dth), dth ? drop_epoch_ptr() : nullptr};
   return launch_simple(add_ln_fwd_kernel, dim3((unsigned)(rows / 64)), dim3(256), a, stream, "add_ln_fwd_kernel");
 }
 
@@ -991,7 +993,7 @@ int csn_ln_bwd(const float* dY, const float* Z, const float* mean, const float* 
                 "csn_ln_bwd: rows, block_rows and group_rows must be multiples of 64, block_rows a multiple of group_rows");
   if (rows == 0) return 0;
   LnBwdArgs a{dY, Z, mean, rstd, gamma, dZ, dZ16, dgamma, dbeta, rows, group_rows, rows_valid, block_rows, dtype, amax, bcast, bcast_idx, bcast_scale, src_idx, src_w, getenv("CSN_LN_BWD_DEBUG") ? atoi(getenv("CSN_LN_BWD_DEBUG")) : 0, chunk_gsum,
-              drop_seed, drop_thresh16(drop_p), drop_scale_of(drop_thresh16(drop_p))};
+              drop_seed, drop_thresh16(drop_p), drop_scale_of(drop_thresh16(drop_p)), drop_thresh16(drop_p) ? drop_epoch_ptr() : nullptr};
   CSN_CHECK_ARG(drop_p >= 0.f && drop_p < 1.f, "csn_ln_bwd: dropout probability outside [0, 1)");
   CSN_CHECK_ARG(!(chunk_gsum && drop_p > 0.f), "csn_ln_bwd: chunk_gsum (V centring) is not combined with dropout");
   static const int occ = getenv("CSN_LN_BWD_OCC") ? atoi(getenv("CSN_LN_BWD_OCC")) : 3;   // resident CTAs/SM (tuning knob)

@@ -64,6 +64,7 @@ struct GemmArgs {
   const float* zbias;
   // csn_gemm_res_ln: dropout on the projection output before the residual add (csa_models.py:115), off when thresh == 0
   uint32_t drop_seed, drop_thresh; float drop_scale;
+  const uint32_t* drop_epoch;
   // csn_gemm_dual: a second problem of the same shape whose tiles are interleaved with the first one's, batch by batch
   // (problem 1: A consumed MN-major through tensor map slot tmR0, B through tmR1): the two problems of the attention
   // backward that read the same dS tile — dQ = dS K and dK = dS^T Q — run back to back, so the second read hits L2
@@ -487,7 +488,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         if (lane == 0) { fetch_res(0); fetch_res(1); }
         float mu = 0.f, m2 = 0.f;
         uint32_t ra[32], rb[32];
-        const uint32_t drop_rk = drop_row_key(p.drop_seed, (uint32_t)row);
+        const uint32_t drop_rk = drop_row_key(drop_seed_eff(p.drop_seed, p.drop_epoch), (uint32_t)row);
         auto emit = [&](uint32_t (&r)[32], int u) {
           // residual slab of this unit
           mbar_wait(rbar0 + 8u * (u & 1), (res_ph >> (u & 1)) & 1u);
@@ -931,6 +932,7 @@ static int gemm_impl(const csn_mat* A, const csn_mat* B, const csn_out* D, int32
     g.block_rows = ln->block_rows; g.group_rows = ln->group_rows; g.rows_valid = ln->rows_valid; g.n_points = ln->n_points;
     g.eps = ln->eps; g.mean = ln->mean; g.rstd = ln->rstd; g.zbias = ln->zbias;
     g.drop_seed = ln->drop_seed; g.drop_thresh = drop_thresh16(ln->drop_p); g.drop_scale = drop_scale_of(g.drop_thresh);
+    g.drop_epoch = g.drop_thresh ? drop_epoch_ptr() : nullptr;
     // the thread owns its whole row; two warp sets alternate tiles (one per accumulator buffer); per warp 2 output
     // + 2 residual slabs -> 128 KB of staging next to a 2-deep operand ring (K is short: the epilogue is the critical path)
     g.stages = 2; g.stg_bufs = 4; g.epi_warps = 8; g.alt_tiles = 1; g.tempty_count = 128;

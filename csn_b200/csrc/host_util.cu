@@ -27,6 +27,31 @@ int num_sms() {   // of the current device (cached per device)
   return n[dev];
 }
 
+static uint32_t* g_drop_epoch[64] = {nullptr};
+
+static uint32_t* drop_epoch_slot() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+  if (!g_drop_epoch[dev]) {
+    uint32_t* p = nullptr;
+    if (cudaMalloc(&p, sizeof(uint32_t)) != cudaSuccess) return nullptr;
+    cudaMemset(p, 0, sizeof(uint32_t));
+    g_drop_epoch[dev] = p;
+  }
+  return g_drop_epoch[dev];
+}
+
+const uint32_t* drop_epoch_ptr() { return drop_epoch_slot(); }
+
+__global__ void set_epoch_kernel(uint32_t* p, uint32_t v) { *p = v; }
+
+int set_drop_epoch(uint32_t epoch, void* stream) {
+  uint32_t* p = drop_epoch_slot();
+  if (!p) { set_error("csn_set_drop_epoch: could not allocate the epoch word"); return 2; }
+  set_epoch_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(p, epoch);
+  return cudaGetLastError() == cudaSuccess ? 0 : 2;
+}
+
 typedef CUresult (*encode_tiled_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
                                     const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
                                     const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -93,5 +118,9 @@ int make_tmap_2d_any(CUtensorMap* tm, const void* ptr, int dtype, int64_t inner,
 extern "C" {
 const char* csn_last_error(void) { return csn::g_err; }
 int csn_abi_version(void) { return 2; }
+int csn_set_drop_epoch(uint32_t epoch, void* stream) {
+  csn::clear_error();
+  return csn::set_drop_epoch(epoch, stream);
+}
 int64_t csn_launch_count(void) { return csn::launch_counter().load(); }
 }

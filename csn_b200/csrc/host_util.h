@@ -16,6 +16,8 @@ void set_error(const char* fmt, ...);
 void clear_error();
 std::atomic<int64_t>& launch_counter();
 int num_sms();
+// device word (per device, zero until csn_set_drop_epoch) that every dropout mask's seed is offset by: see ptx.cuh
+const uint32_t* drop_epoch_ptr();
 
 // 2-D tiled tensor map over 16-bit elements with 128-byte swizzle.  dims/box are {inner, outer}.
 // Out-of-bounds elements of a box are filled with zeros.  Returns 0 on success.

@@ -375,6 +375,12 @@ __host__ __device__ __forceinline__ uint32_t drop_mix(uint32_t x) {
   return x;
 }
 // per-row part of the hash, hoisted out of the column loops
+// The seed every mask of a launch is derived from: the launch's own seed plus a device-resident epoch counter, so
+// that a captured CUDA graph (whose kernel arguments are frozen) draws fresh masks on every replay
+// (csn_set_drop_epoch, outside the graph, before the replay).  epoch == NULL or *epoch == 0: the plain seed.
+__device__ __forceinline__ uint32_t drop_seed_eff(uint32_t seed, const uint32_t* epoch) {
+  return epoch ? seed + __ldg(epoch) * 0x9E3779B9u : seed;
+}
 __host__ __device__ __forceinline__ uint32_t drop_row_key(uint32_t seed, uint32_t row_id) {
   return row_id * 0x9E3779B1u + seed;   // (cheap on purpose: the dV kernel forms it per element; drop_pair does the mixing)
 }

@@ -40,6 +40,16 @@ class GraphedStep:
         from . import engine as _E
         self._tables = _E.pin_tables()
 
-    def replay(self):
+    def replay(self, epoch: int | None = None):
+        """epoch: training-mode steps (dropout on) pass a different value per replay -- e.g. the step counter --
+        so that every replay draws fresh masks: the seeds were frozen into the graph when it was captured, the
+        device-resident epoch word (`csn_set_drop_epoch`) offsets them.  None leaves the word as it is."""
+        if epoch is not None:
+            set_drop_epoch(epoch)
         self.graph.replay()
         return self.outputs
+
+
+def set_drop_epoch(epoch: int) -> None:
+    """Offset of every dropout seed on the current device (0 = plain seeds), set on the current stream."""
+    L.check(L.lib().csn_set_drop_epoch(int(epoch) & 0xFFFFFFFF, L.stream_ptr()), "csn_set_drop_epoch")

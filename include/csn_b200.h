@@ -31,6 +31,11 @@ enum { CSN_MAJOR_K = 0, CSN_MAJOR_MN = 1 };
 const char* csn_last_error(void);
 /* library/ABI version, bumped on any signature change */
 int csn_abi_version(void);
+
+/* Dropout epoch (one word per device, 0 at start): every launch's mask seed is drop_seed + epoch * 0x9E3779B9.  A
+ * training step captured as a CUDA graph freezes its kernel arguments, seeds included; calling this on the same
+ * stream before each replay makes the replay draw fresh masks (csn_b200.graphs.GraphedStep.replay(epoch=...)). */
+int csn_set_drop_epoch(uint32_t epoch, void* stream);
 /* number of kernels this library has launched since load (all streams); used by bench.py */
 int64_t csn_launch_count(void);
 

@@ -193,3 +193,39 @@ def test_csa_training_step_in_train_mode():
     m.eval()
     logits_e = m(x, "test", nb)
     assert G.rel_err(logits_t, logits_e) > 1e-3 and torch.isfinite(logits_t).all()
+
+
+def test_graph_replay_draws_fresh_masks_per_epoch():
+    """A train-mode step captured as a CUDA graph freezes its seeds; the device-resident epoch word offsets them:
+    same epoch -> bit-identical loss, different epochs -> different masks, epoch 0 -> the eager result."""
+    from csn_b200 import midfc, graphs
+    torch.manual_seed(3)
+    m = midfc.get_model("csa", 15, 1, 2).cuda().train()
+    m.load_state_dict(synth.midfc_state(5, 1, 15))
+    x, nb = synth.csa_batch(6, 2, 2)
+    x, nb = x.cuda(), nb.cuda()
+    lab = torch.randint(1, 15, (2, x.shape[2]), generator=torch.Generator().manual_seed(1)).cuda()
+    params = [p_ for n, p_ in m.named_parameters() if not n.startswith("fc_1")]
+
+    def step(x, nb, lab):
+        for p_ in params:
+            p_.grad = None
+        loss = m.forward_loss(x, "train", nb, lab)
+        loss.backward()
+        return loss
+
+    g = graphs.GraphedStep(step, x, nb, lab)
+    try:
+        l0 = g.replay(epoch=0).item()
+        l0b = g.replay(epoch=0).item()
+        l1 = g.replay(epoch=1).item()
+        l2 = g.replay(epoch=2).item()
+        g1 = m.attention.w_qs.weight.grad.clone()
+        l1b = g.replay(epoch=1).item()
+        assert l0 == l0b and l1 == l1b
+        assert len({l0, l1, l2}) == 3
+        assert torch.isfinite(g1).all() and float(g1.abs().max()) > 0
+        # all within dropout noise of each other
+        assert max(abs(l1 - l0), abs(l2 - l0)) < 0.2 * abs(l0)
+    finally:
+        graphs.set_drop_epoch(0)
