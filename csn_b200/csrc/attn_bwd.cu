@@ -105,6 +105,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const uint32_t dseed = DROP ? drop_seed_eff(p.drop_seed, p.drop_epoch) : 0u;   // (one load per thread, train-mode variants only)
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmQ);
@@ -288,7 +289,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       const bool valid = r < it.q_valid;
       const float lse_l2 = valid ? p.lse[it.stat_off + r] * LOG2E : 0.f;
       const float dlt_s = valid ? p.delta[it.stat_off + r] * p.scale : 0.f;
-      const uint32_t rk = drop_row_key(drop_seed_eff(p.drop_seed, p.drop_epoch), (uint32_t)(it.stat_off + r));
+      const uint32_t rk = drop_row_key(dseed, (uint32_t)(it.stat_off + r));
       for (int j = 0; j < nkv; ++j) {
         const int b = WITH_DQ ? 0 : (j & 1);
         mbar_wait(sdp_full(b), sdp_ph[b]);
@@ -474,6 +475,7 @@ attn_bwd_ds_wide_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const uint32_t dseed = DROP ? drop_seed_eff(p.drop_seed, p.drop_epoch) : 0u;   // (one load per thread, train-mode variants only)
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmDO); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV);
   }
@@ -610,7 +612,7 @@ attn_bwd_ds_wide_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
       const bool valid = r < it.q_valid;
       const float lse_l2 = valid ? p.lse[it.stat_off + r] * LOG2E : 0.f;
       const float dlt = valid ? p.delta[it.stat_off + r] : 0.f;
-      const uint32_t rk = drop_row_key(drop_seed_eff(p.drop_seed, p.drop_epoch), (uint32_t)(it.stat_off + r));
+      const uint32_t rk = drop_row_key(dseed, (uint32_t)(it.stat_off + r));
       for (int j = 0; j < nst; ++j) {
         const int key0 = j * 256 + half * 128;          // first key of this warp's 128 columns
         const int nvalid = valid ? it.kv_len - key0 : 0;   // columns [0, nvalid) of the 128 are real keys

@@ -111,6 +111,7 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_consta
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const uint32_t dseed = DROP ? drop_seed_eff(p.drop_seed, p.drop_epoch) : 0u;   // (one load per thread, train-mode variants only)
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmK);
@@ -296,7 +297,7 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_consta
               for (int u = 0; u < 4; ++u) {
                 float m = 1.f;   // d P_dropped / d P = mask / (1 - p)
                 if (DROP) {      // the forward mask: row id = query, pair = two adjacent keys
-                  const uint32_t hh = drop_pair(drop_row_key(drop_seed_eff(p.drop_seed, p.drop_epoch), (uint32_t)(it.stat_off + j * 128 + c + i + u)),
+                  const uint32_t hh = drop_pair(drop_row_key(dseed, (uint32_t)(it.stat_off + j * 128 + c + i + u)),
                                                 (uint32_t)(it.key0 + r) >> 1);
                   m = (((it.key0 + r) & 1) ? drop_keep_hi(hh, p.drop_thresh) : drop_keep_lo(hh, p.drop_thresh)) ? p.drop_scale : 0.f;
                 }
@@ -450,6 +451,7 @@ attn_bwd_dq64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const uint32_t dseed = DROP ? drop_seed_eff(p.drop_seed, p.drop_epoch) : 0u;   // (one load per thread, train-mode variants only)
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmQ);
@@ -585,7 +587,7 @@ attn_bwd_dq64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       const bool valid = r < it.q_valid;
       const float lse_l2 = valid ? p.lse[it.stat_off + r] * LOG2E : 0.f;
       const float dlt_s = valid ? p.delta[it.stat_off + r] * p.scale : 0.f;
-      const uint32_t rk = drop_row_key(drop_seed_eff(p.drop_seed, p.drop_epoch), (uint32_t)(it.stat_off + r));
+      const uint32_t rk = drop_row_key(dseed, (uint32_t)(it.stat_off + r));
       for (int j = 0; j < nkv; ++j) {
         const int b = j & 1;
         const int nvalid = min(128, it.kv_len - j * 128);

@@ -91,6 +91,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const uint32_t dseed = DROP ? drop_seed_eff(p.drop_seed, p.drop_epoch) : 0u;   // (one load per thread, train-mode variants only)
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmQ);
@@ -352,7 +353,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           const bool rvalid = r < nvalid;                       // query row exists
           const float lse_l2 = rvalid ? p.lse[it.lse_off + j * 128 + r] * LOG2E : 0.f;
           const int cvalid = rvalid ? it.q_valid : 0;           // resident key columns that exist
-          const uint32_t rk = drop_row_key(drop_seed_eff(p.drop_seed, p.drop_epoch), (uint32_t)(it.lse_off + j * 128 + r));
+          const uint32_t rk = drop_row_key(dseed, (uint32_t)(it.lse_off + j * 128 + r));
           auto dv_tile = [&](auto F16C, auto FULLC) {
             constexpr bool F16 = decltype(F16C)::value, FULL = decltype(FULLC)::value;
 #pragma unroll 1
@@ -447,7 +448,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             l *= alpha;
           }
           const float moff = m_used * p.scale_log2;
-          const uint32_t rk = drop_row_key(drop_seed_eff(p.drop_seed, p.drop_epoch), (uint32_t)(it.lse_off + r));
+          const uint32_t rk = drop_row_key(dseed, (uint32_t)(it.lse_off + r));
           float lsum = 0.f;
           uint32_t pk[32];
           auto exp_regs = [&](auto F16C, auto FULLC) {
@@ -517,7 +518,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
               }
             }
             const float moff = m_used * p.scale_log2;
-            const uint32_t rk = drop_row_key(drop_seed_eff(p.drop_seed, p.drop_epoch), (uint32_t)(it.lse_off + r));
+            const uint32_t rk = drop_row_key(dseed, (uint32_t)(it.lse_off + r));
             lsum = 0.f;
             float cmax = -INFINITY;
             auto exp_tile = [&](auto F16C, auto FULLC) {

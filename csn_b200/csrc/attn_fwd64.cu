@@ -65,6 +65,7 @@ attn_fwd64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const uint32_t dseed = DROP ? drop_seed_eff(p.drop_seed, p.drop_epoch) : 0u;   // (one load per thread, train-mode variants only)
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmQ);
@@ -187,7 +188,7 @@ attn_fwd64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
       const AttnItem it = p.items[wk];
       const int nkv = (it.kv_len + 127) >> 7;
       float m_used = 0.f, l = 0.f;
-      const uint32_t rk = drop_row_key(drop_seed_eff(p.drop_seed, p.drop_epoch), (uint32_t)(it.lse_off + r));
+      const uint32_t rk = drop_row_key(dseed, (uint32_t)(it.lse_off + r));
       for (int j = 0; j < nkv; ++j) {
         const int pb = j & 1;
         const int nv = min(128, it.kv_len - j * 128) - g * 32;   // valid columns among this thread's 32 (<= 0: none)

@@ -59,6 +59,7 @@ attn_wide_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const uint32_t dseed = DROP ? drop_seed_eff(p.drop_seed, p.drop_epoch) : 0u;   // (one load per thread, train-mode variants only)
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV);
   }
@@ -367,7 +368,7 @@ attn_wide_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         } else {
           const float moff = m_used * p.scale_log2;
           const bool rvalid = (MODE == 0) ? true : (r < it.q_valid);
-          const uint32_t rk0 = drop_row_key(drop_seed_eff(p.drop_seed, p.drop_epoch), (uint32_t)(it.lse_off + r));   // MODE 0: the thread's query row
+          const uint32_t rk0 = drop_row_key(dseed, (uint32_t)(it.lse_off + r));   // MODE 0: the thread's query row
           const uint32_t lse4 = sX + half * 512;   // shared-window address of this warp's 128 per-column statistics
           uint32_t va[32], vb[32];
           // operand type and "no padding among this warp's rows and columns" are compile-time variants of the
@@ -406,8 +407,8 @@ attn_wide_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
                   const uint32_t kp = (uint32_t)(it.key0 + r) >> 1;
                   const bool hi = ((it.key0 + r) & 1) != 0;
                   const uint32_t q0 = (uint32_t)(it.lse_off + col_first + c0);
-                  const uint32_t h0 = drop_pair(drop_row_key(drop_seed_eff(p.drop_seed, p.drop_epoch), q0), kp), h1 = drop_pair(drop_row_key(drop_seed_eff(p.drop_seed, p.drop_epoch), q0 + 1), kp);
-                  const uint32_t h2 = drop_pair(drop_row_key(drop_seed_eff(p.drop_seed, p.drop_epoch), q0 + 2), kp), h3 = drop_pair(drop_row_key(drop_seed_eff(p.drop_seed, p.drop_epoch), q0 + 3), kp);
+                  const uint32_t h0 = drop_pair(drop_row_key(dseed, q0), kp), h1 = drop_pair(drop_row_key(dseed, q0 + 1), kp);
+                  const uint32_t h2 = drop_pair(drop_row_key(dseed, q0 + 2), kp), h3 = drop_pair(drop_row_key(dseed, q0 + 3), kp);
                   d0 = (hi ? drop_keep_hi(h0, p.drop_thresh) : drop_keep_lo(h0, p.drop_thresh)) ? p0 * p.drop_scale : 0.f;
                   d1 = (hi ? drop_keep_hi(h1, p.drop_thresh) : drop_keep_lo(h1, p.drop_thresh)) ? p1 * p.drop_scale : 0.f;
                   d2 = (hi ? drop_keep_hi(h2, p.drop_thresh) : drop_keep_lo(h2, p.drop_thresh)) ? p2 * p.drop_scale : 0.f;

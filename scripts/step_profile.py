@@ -7,9 +7,12 @@ from torch.profiler import profile, ProfilerActivity
 from csn_b200 import midfc, synth
 import bench
 
-h = int(sys.argv[1]) if len(sys.argv) > 1 else 1
+train = "--train" in sys.argv   # model.train(): dropout on
+argv = [a for a in sys.argv[1:] if a != "--train"]
+h = int(argv[0]) if argv else 1
 dev = torch.device("cuda:0")
-model = midfc.get_model("csa", 15, h, 3).to(dev).eval()
+model = midfc.get_model("csa", 15, h, 3).to(dev)
+model = model.train() if train else model.eval()
 model.load_state_dict(synth.midfc_state(1, h, 15))
 g = torch.Generator(device=dev).manual_seed(1)
 nb = torch.relu(torch.randn(8, 4, 256, 10000, 1, device=dev, generator=g))
