@@ -541,6 +541,10 @@ def run_ours(args) -> None:
     gs_ = torch.Generator(device=dev).manual_seed(7 + rank)
     for s0 in range(0, store.hi - store.lo, 16):
         store.feats[s0:s0 + 16] = torch.relu(torch.randn(16, D, N_POINTS, device=dev, generator=gs_))
+    store.barrier()   # every shard is loaded before anybody reads a peer's
+    store_plane = ("one-sided: device-to-device copies out of the owners' symmetric-memory shards (copy engines over NVLink, no SMs)"
+                   if store.one_sided else "two-sided: one batched NCCL point-to-point exchange per step"
+                   + (f" (symmetric memory unavailable: {getattr(store, 'symm_error', 'n/a')[:120]})" if world > 1 else ""))
     # ids of EVERY rank's batch, derived from one shared seed (the replicated kNN graph + a DistributedSampler-style
     # permutation): queries are the rank's own shapes, neighbours are arbitrary shapes of the collection, so at N ranks
     # a fraction (N-1)/N of the neighbour blocks is fetched from its owner over NVLink
@@ -552,6 +556,29 @@ def run_ours(args) -> None:
         id_steps.append((ids_all, nbr_all))
     hl_s = [torch.randint(0, N_CLASSES, (CSA_B, N_POINTS), generator=gh).pin_memory() for _ in range(2)]
     remote_blocks = []
+
+    # one-time check of the data plane: a block fetched from a peer equals what its owner generated (same seed here)
+    store_verified = None
+    if world > 1:
+        ids0, nbr0 = id_steps[0]
+        xv, nbv = store.batch(ids0, nbr0)
+        torch.cuda.synchronize()
+        store_verified = True
+        done_check = False
+        for b_ in range(CSA_B):
+            for k_ in range(CSA_K):
+                sid = nbr0[rank][b_][k_]
+                o_ = store.owner(sid)
+                if o_ == rank or done_check:
+                    continue
+                go = torch.Generator(device=dev).manual_seed(7 + o_)
+                lo_o = store.bounds[o_][0]
+                for s0 in range(0, sid - lo_o + 1, 16):   # replay the owner's generator up to the chunk that holds sid
+                    chunk = torch.relu(torch.randn(16, D, N_POINTS, device=dev, generator=go))
+                want = chunk[(sid - lo_o) % 16]
+                store_verified = bool(torch.equal(nbv[b_, k_ + 1].view(D, N_POINTS), want))
+                done_check = True
+        del xv, nbv
 
     consumed_s = [None, None]
 
@@ -598,9 +625,10 @@ def run_ours(args) -> None:
                  "h2d_bytes_per_step": int(hl_s[0].numel() * 8 + CSA_B * (CSA_K + 1) * 8), "d2h_bytes_per_step": 4,
                  "steps": store_steps,
                  "nvlink_bytes_per_step_per_rank": int(sum(remote_blocks[-store_steps:]) / max(1, store_steps) * D * N_POINTS * 4),
+                 "data_plane": store_plane, "remote_block_verified": store_verified,
                  "note": "collection sharded by shape id over the ranks' HBM (csn_b200.store.ShardedFeatureStore): queries are "
-                         "local, neighbour blocks are fetched from their owners by one batched NCCL point-to-point exchange "
-                         "per step on a side stream; only ids and labels cross PCIe"}
+                         "local, neighbour blocks are fetched from their owners on a side stream under the previous step; "
+                         "only ids and labels cross PCIe"}
     del store
     clocks = sampler.stop() if rank == 0 else None
     del batches, hx, hn, hl

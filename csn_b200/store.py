@@ -102,10 +102,46 @@ class ShardedFeatureStore:
         self.bounds = [shard_range(n_shapes, r, self.world) for r in range(self.world)]
         lo, hi = self.bounds[self.rank]
         self.lo, self.hi = lo, hi
-        self.feats = torch.zeros(hi - lo, d_model, n_points, dtype=dtype, device=device)
+        # One-sided data plane: the shard lives in SYMMETRIC memory (torch.distributed._symmetric_memory: every rank
+        # maps every peer's shard), so a neighbour block is fetched by a plain device-to-device copy from the owner's
+        # memory -- copy engines over NVLink, no SMs (an NCCL send/recv pair competes with the persistent compute
+        # kernels for them), no action on the owner's side, no per-step synchronisation (the collection is constant
+        # after put_local + barrier()).  Falls back to the two-sided batched exchange when symmetric memory is not
+        # available (CPU / gloo tests, CSN_STORE_SYMM=0, or a platform without peer mapping).
+        self._peer = None
+        self.feats = None
+        import os
+        if (self.dist_on and self.world > 1 and torch.device(device).type == "cuda"
+                and os.environ.get("CSN_STORE_SYMM", "1") == "1" and dist.get_backend(group) == "nccl"):
+            try:
+                import torch.distributed._symmetric_memory as symm
+                n_max = max(h_ - l_ for l_, h_ in self.bounds)
+                t = symm.empty((n_max, d_model, n_points), dtype=dtype, device=torch.device(device))
+                hdl = symm.rendezvous(t, group if group is not None else dist.group.WORLD)
+                self._symm = hdl
+                self._peer = [hdl.get_buffer(r, (n_max, d_model, n_points), dtype) for r in range(self.world)]
+                t.zero_()
+                self.feats = t[:hi - lo]
+            except Exception as e:   # noqa: BLE001  (any failure of the experimental API selects the fallback)
+                self._peer = None
+                self.symm_error = f"{type(e).__name__}: {e}"
+        if self.feats is None:
+            self.feats = torch.zeros(hi - lo, d_model, n_points, dtype=dtype, device=device)
         self.device = self.feats.device
         self._buf: dict = {}
         self.last_remote_blocks = 0    # blocks received from peers by the last batch() (bench: bytes over NVLink)
+
+    @property
+    def one_sided(self) -> bool:
+        return self._peer is not None
+
+    def barrier(self) -> None:
+        """After every rank has loaded its shard (put_local) and before the first batch(): one-sided reads have no
+        other synchronisation point."""
+        import torch.distributed as dist
+        if self.dist_on:
+            torch.cuda.synchronize() if self.device.type == "cuda" else None
+            dist.barrier(self.group)
 
     def owner(self, shape_id: int) -> int:
         for r, (lo, hi) in enumerate(self.bounds):
@@ -158,6 +194,20 @@ class ShardedFeatureStore:
             if not (self.lo <= s < self.hi):
                 raise IndexError(f"query shape {s} is not owned by rank {self.rank} (queries are sharded by owner)")
         x.view(B, D, N).copy_(self.feats.index_select(0, torch.as_tensor([s - self.lo for s in ids], dtype=torch.int64).to(dev, non_blocking=True)))
+        if self._peer is not None:
+            # one-sided: every block this rank does not own is copied straight out of its owner's shard
+            n_remote = 0
+            for k in range(K):
+                for b in range(B):
+                    sid = nbr[b][k]
+                    if self.lo <= sid < self.hi:
+                        xn[b, k + 1].view(D, N).copy_(self.feats[sid - self.lo], non_blocking=True)
+                    else:
+                        o = self.owner(sid)
+                        xn[b, k + 1].view(D, N).copy_(self._peer[o][sid - self.bounds[o][0]], non_blocking=True)
+                        n_remote += 1
+            self.last_remote_blocks = n_remote
+            return x, xn
         send, recv = self.plan(all_nbr)
         # one batched point-to-point exchange: isend the blocks peers need, irecv the ones this rank needs
         ops, recv_bufs, keep = [], {}, []
