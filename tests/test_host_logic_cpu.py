@@ -175,3 +175,36 @@ def test_sharded_feature_store_fetches_neighbours_from_their_owners(tmp_path):
     assert r0["ok"] and r1["ok"]
     assert r0["remote"] == 3 and r0["recv"][1] == [5, 6, 4] and r0["send"][1] == [0, 3]   # rank 0 needs 5, 6, 4 (5 once)
     assert r1["remote"] == 2 and r1["recv"][0] == [0, 3] and r1["send"][0] == [5, 6, 4]
+
+
+def test_ragged_work_tables_are_longest_first_and_complete(monkeypatch):
+    """Work tables of a ragged batch (csn_b200.engine.attn_items): every kind lists the same tiles with and without
+    the longest-first order, the order is by streamed length (column 3), and the key-stationary 'dkv' table covers
+    every key tile the query-stationary 'dq' table streams."""
+    from csn_b200 import engine as E
+    lens = (130, 517, 64, 300, 1)
+    pairs = ((0, 0), (1, 1), (2, 2), (3, 3), (4, 4), (0, 1), (1, 3), (4, 1))
+    n_pad = 640
+    geom = E.Geometry(chunk=n_pad, n_chunks=1, chunk_pad=n_pad, kv_chunk=n_pad)
+    groups = tuple(E.Group(n_in=1, n_out=1, blk0=j, q0=q, q_si=0, q_so=0, k0=k, k_si=0, k_so=0, v0=k, v_si=0, v_so=0,
+                           q_lens=(lens[q],), kv_lens=(lens[k],)) for j, (q, k) in enumerate(pairs))
+    h, d = 4, 64
+    for kind in ("fwd", "dq", "dkv", "dv"):
+        E._ITEM_CACHE.clear()
+        monkeypatch.setenv("CSN_ITEM_SORT", "1")
+        a = E.attn_items(groups, geom, h, d, "cpu", kind).tolist()
+        E._ITEM_CACHE.clear()
+        monkeypatch.setenv("CSN_ITEM_SORT", "0")
+        b = E.attn_items(groups, geom, h, d, "cpu", kind).tolist()
+        assert sorted(map(tuple, a)) == sorted(map(tuple, b)) and len(a) > 0
+        assert [r[3] for r in a] == sorted((r[3] for r in a), reverse=True)
+    E._ITEM_CACHE.clear()
+    monkeypatch.setenv("CSN_ITEM_SORT", "1")
+    dq = E.attn_items(groups, geom, h, d, "cpu", "dq").tolist()
+    dkv = E.attn_items(groups, geom, h, d, "cpu", "dkv").tolist()
+    # per (block, head): query tiles x key tiles of the two tables describe the same rectangle
+    n_q_tiles = sum((lens[q] + 127) // 128 for q, _ in pairs) * h
+    n_k_tiles = sum((lens[k] + 127) // 128 for _, k in pairs) * h
+    assert len(dq) == n_q_tiles and len(dkv) == n_k_tiles
+    assert all(r[1] > 0 for r in dq) and all(r[1] > 0 for r in dkv)          # no tile that lies entirely in the padding
+    E._ITEM_CACHE.clear()
