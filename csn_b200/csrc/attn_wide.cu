@@ -407,8 +407,13 @@ attn_wide_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
                   const uint32_t kp = (uint32_t)(it.key0 + r) >> 1;
                   const bool hi = ((it.key0 + r) & 1) != 0;
                   const uint32_t q0 = (uint32_t)(it.lse_off + col_first + c0);
-                  const uint32_t h0 = drop_pair(drop_row_key(dseed, q0), kp), h1 = drop_pair(drop_row_key(dseed, q0 + 1), kp);
-                  const uint32_t h2 = drop_pair(drop_row_key(dseed, q0 + 2), kp), h3 = drop_pair(drop_row_key(dseed, q0 + 3), kp);
+                  // lanes 2m / 2m+1 hold the two keys of one pair: they need the SAME four hashes (one takes the low,
+                  // the other the high 16 bits), so each computes two and receives the partner's two by shuffle
+                  const bool odd = (lane & 1) != 0;
+                  const uint32_t qa = q0 + (odd ? 2u : 0u);
+                  const uint32_t ha = drop_pair(drop_row_key(dseed, qa), kp), hb = drop_pair(drop_row_key(dseed, qa + 1), kp);
+                  const uint32_t oa = __shfl_xor_sync(0xffffffffu, ha, 1), ob = __shfl_xor_sync(0xffffffffu, hb, 1);
+                  const uint32_t h0 = odd ? oa : ha, h1 = odd ? ob : hb, h2 = odd ? ha : oa, h3 = odd ? hb : ob;
                   d0 = (hi ? drop_keep_hi(h0, p.drop_thresh) : drop_keep_lo(h0, p.drop_thresh)) ? p0 * p.drop_scale : 0.f;
                   d1 = (hi ? drop_keep_hi(h1, p.drop_thresh) : drop_keep_lo(h1, p.drop_thresh)) ? p1 * p.drop_scale : 0.f;
                   d2 = (hi ? drop_keep_hi(h2, p.drop_thresh) : drop_keep_lo(h2, p.drop_thresh)) ? p2 * p.drop_scale : 0.f;
